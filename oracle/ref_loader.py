@@ -1,0 +1,126 @@
+"""TEST INFRASTRUCTURE ONLY -- loader that executes the *reference's own* PyTorch
+definitions from /root/reference (read-only, present in the build container only).
+
+It is used by `oracle/make_golden.py` to generate the committed fixtures under
+`tests/golden/` and by the `-m "not gpu"` pinning tests (skipped when
+/root/reference is absent, e.g. on the GPU box).  Nothing in the product path
+(`audio-denoiser-onnx_b200/`), `bench.py` or `smoke()` imports this file.
+
+Recipe: the reference's `Export_*.py` files run their ONNX
+export at import time and import `onnx`/`onnxruntime`/`onnxslim`, none of which is
+installed here.  We therefore (1) register stub modules for those names, (2) read the
+source, cut it before `def _run_inference_demo` (i.e. keep only the class
+definitions), (3) text-patch the module-level constants, (4) `exec` it.
+No reference source is copied into this repository.
+"""
+from __future__ import annotations
+
+import sys
+import types
+from pathlib import Path
+
+REFERENCE_ROOT = Path("/root/reference")
+
+
+def reference_available() -> bool:
+    return (REFERENCE_ROOT / "GTCRN" / "Export_GTCRN.py").exists()
+
+
+def _install_stubs() -> None:
+    for name in ("onnxruntime", "onnx", "onnxslim", "ml_collections"):
+        if name not in sys.modules:
+            mod = types.ModuleType(name)
+            if name == "onnxslim":
+                mod.slim = lambda *a, **k: None
+            if name == "ml_collections":
+                mod.ConfigDict = dict
+            sys.modules[name] = mod
+    if "Rewrite_ONNX_GRU_Zero_State" not in sys.modules:
+        mod = types.ModuleType("Rewrite_ONNX_GRU_Zero_State")
+        mod.rewrite = lambda *a, **k: None
+        sys.modules["Rewrite_ONNX_GRU_Zero_State"] = mod
+
+
+def load_stft_module(model_dir: str):
+    """Import `<model_dir>/STFT_Process.py` from the reference as a fresh module.
+
+    Each model folder carries its own variant, so the module is
+    loaded under a unique name."""
+    import importlib.util
+
+    _install_stubs()
+    path = REFERENCE_ROOT / model_dir / "STFT_Process.py"
+    name = "ref_stft_" + model_dir.replace("/", "_").replace("-", "_")
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def load_export_namespace(model_dir: str, script: str, patches: dict[str, str]) -> dict:
+    """Exec the class-definition part of an Export script with patched constants.
+
+    `patches` maps an exact source line prefix (e.g. ``"INPUT_AUDIO_LENGTH   = 32000"``)
+    to its replacement text."""
+    _install_stubs()
+    mdir = REFERENCE_ROOT / model_dir
+    for p in (str(mdir), str(REFERENCE_ROOT)):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    # the per-model STFT_Process must win over a previously imported sibling variant
+    sys.modules.pop("STFT_Process", None)
+    src = (mdir / script).read_text()
+    src = src.split("\ndef _run_inference_demo")[0]
+    for old, new in patches.items():
+        if old not in src:
+            raise RuntimeError(f"patch anchor not found in {script}: {old!r}")
+        src = src.replace(old, new, 1)
+    ns: dict = {"__file__": str(mdir / script), "__name__": "ref_export_" + model_dir}
+    exec(compile(src, str(mdir / script), "exec"), ns)
+    sys.modules.pop("STFT_Process", None)
+    return ns
+
+
+def load_gtcrn(input_audio_length: int = 16000, io_dtype: str = "F32"):
+    """Build the reference GTCRN_CUSTOM wrapper (random init, eval) for one chunk length.
+
+    Returns (namespace, build) where build(state_dict|None) -> wrapper module.
+    Static buffers are baked per chunk length (Export_GTCRN.py:44-46,234-239)."""
+    import torch
+
+    ns = load_export_namespace(
+        "GTCRN",
+        "Export_GTCRN.py",
+        {
+            "INPUT_AUDIO_LENGTH   = 32000": f"INPUT_AUDIO_LENGTH   = {int(input_audio_length)}",
+            "IN_AUDIO_DTYPE       = 'INT16'": f"IN_AUDIO_DTYPE       = '{io_dtype}'",
+            "OUT_AUDIO_DTYPE      = 'INT16'": f"OUT_AUDIO_DTYPE      = '{io_dtype}'",
+        },
+    )
+
+    def build(state_dict=None):
+        with torch.inference_mode():
+            STFT_Process = ns["STFT_Process"]
+            stft = STFT_Process(
+                model_type="stft_B", n_fft=ns["NFFT"], hop_len=ns["HOP_LENGTH"],
+                win_length=ns["WINDOW_LENGTH"], max_frames=0, window_type=ns["WINDOW_TYPE"],
+                center_pad=True, pad_mode=ns["PAD_MODE"], input_scale=1.0,
+            ).eval()
+            istft = STFT_Process(
+                model_type="istft_B", n_fft=ns["NFFT"], hop_len=ns["HOP_LENGTH"],
+                win_length=ns["WINDOW_LENGTH"], max_frames=ns["MAX_SIGNAL_LENGTH"],
+                window_type=ns["WINDOW_TYPE"], center_pad=True, pad_mode=ns["PAD_MODE"],
+                output_scale=1.0, static_norm=True,
+            ).eval()
+            g = ns["GTCRN"]().eval()
+            if state_dict is not None:
+                missing, unexpected = g.load_state_dict(state_dict, strict=False)
+                assert not unexpected, unexpected
+            g.prepare_for_export_()
+            wrapper = ns["GTCRN_CUSTOM"](
+                g.float(), stft, istft, ns["IN_SAMPLE_RATE"], ns["OUT_SAMPLE_RATE"],
+                False, ns["FOLD_WINDOW_LENGTH"],
+            ).eval()
+        return wrapper
+
+    return ns, build
