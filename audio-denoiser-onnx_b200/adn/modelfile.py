@@ -1,0 +1,69 @@
+"""`.adn` model file: the build's stand-in for `<Model>.onnx` + `<Model>_Metadata.onnx`.
+
+The reference ships weights as ONNX initializers and its run-time constants as string
+`metadata_props` (audio_onnx_metadata.py:83-112).  libadn needs neither a graph nor
+protobuf, so the model file is a flat container:
+
+    b"ADN1" | u32 header_len | JSON header | fp32 payload
+
+header = {"metadata": {key: str}, "tensors": [{"name", "offset", "count", "shape"}]},
+offsets/counts in floats.  The metadata keys are the reference's own
+(REQUIRED_AUDIO_METADATA_KEYS, audio_onnx_metadata.py:8-26).
+"""
+from __future__ import annotations
+
+import json
+import struct
+from pathlib import Path
+
+import numpy as np
+
+MAGIC = b"ADN1"
+
+
+def save(path, metadata: dict[str, str], tensors: dict[str, np.ndarray]) -> None:
+    index, chunks, off = [], [], 0
+    for name, arr in tensors.items():
+        a = np.ascontiguousarray(arr, dtype=np.float32)
+        pad = (-off) % 4                       # keep every tensor 16-byte aligned
+        if pad:
+            chunks.append(np.zeros(pad, np.float32))
+            off += pad
+        index.append({"name": name, "offset": off, "count": int(a.size), "shape": list(a.shape)})
+        chunks.append(a.reshape(-1))
+        off += a.size
+    header = json.dumps({"metadata": {str(k): str(v) for k, v in metadata.items()}, "tensors": index}).encode()
+    path = Path(path)
+    path.parent.mkdir(parents=True, exist_ok=True)
+    with open(path, "wb") as f:
+        f.write(MAGIC)
+        f.write(struct.pack("<I", len(header)))
+        f.write(header)
+        f.write(np.concatenate(chunks).tobytes() if chunks else b"")
+
+
+def load(path):
+    """Returns (metadata dict, tensor index list, flat fp32 payload)."""
+    raw = Path(path).read_bytes()
+    if raw[:4] != MAGIC:
+        raise ValueError(f"{path}: not an ADN1 model file")
+    (hlen,) = struct.unpack("<I", raw[4:8])
+    header = json.loads(raw[8:8 + hlen].decode())
+    payload = np.frombuffer(raw, dtype=np.float32, offset=8 + hlen).copy() if (len(raw) - 8 - hlen) % 4 == 0 \
+        else np.frombuffer(raw[8 + hlen:], dtype=np.float32).copy()
+    return header["metadata"], header["tensors"], payload
+
+
+def flatten(tensors: dict[str, np.ndarray]):
+    """In-memory equivalent of save()+load(): (index, payload)."""
+    index, chunks, off = [], [], 0
+    for name, arr in tensors.items():
+        a = np.ascontiguousarray(arr, dtype=np.float32)
+        pad = (-off) % 4
+        if pad:
+            chunks.append(np.zeros(pad, np.float32))
+            off += pad
+        index.append({"name": name, "offset": off, "count": int(a.size), "shape": list(a.shape)})
+        chunks.append(a.reshape(-1))
+        off += a.size
+    return index, np.concatenate(chunks)

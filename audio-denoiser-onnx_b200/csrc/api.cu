@@ -1,0 +1,724 @@
+// C ABI of libadn.so (include/adn.h).  Host-side C++ only: model construction from the
+// flat weight blob, workspace management, stream-ordered launch sequence.
+#include "adn.h"
+#include "common.cuh"
+#include "gtcrn.cuh"
+
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace {
+
+std::string g_last_error;   // for failures without a handle (adn_create)
+std::mutex g_err_mu;
+
+void set_global_error(const std::string& s) {
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  g_last_error = s;
+}
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct TensorRef {
+  uint64_t offset, count;
+};
+
+// Overlap-add weight for the row-gather GEMM: raw output block j (hop samples) is
+//   sum_{q'=0}^{R-1} frame[j-R+1+q'] . Kinv[:, n' + (R-1-q')*hop]
+// -> W[n'][q'*ld + r] (zero where the tap falls outside the frame).  This is exactly
+// conv_transpose1d(inp, inverse_kernel, stride=hop) (GTCRN/STFT_Process.py:328).
+std::vector<float> build_ola_weight(const float* inv_basis, int nfft, int hop, int ld, int R) {
+  const int rows2f = nfft + 2;
+  std::vector<float> w((size_t)hop * R * ld, 0.f);
+  for (int n = 0; n < hop; ++n)
+    for (int q = 0; q < R; ++q) {
+      int src = n + (R - 1 - q) * hop;
+      if (src >= nfft) continue;
+      for (int r = 0; r < rows2f; ++r) w[(size_t)n * R * ld + (size_t)q * ld + r] = inv_basis[(size_t)r * nfft + src];
+    }
+  return w;
+}
+
+struct StftPlan {
+  int nfft = 0, hop = 0, half = 0, center = 1, reflect = 1, norm_mul = 0;
+  int rows2f = 0, ld = 0, R = 0;
+  int n_frames(int L) const { return center ? L / hop + 1 : (L - nfft) / hop + 1; }
+  int padded_len(int L) const { return round_up(L + (center ? 2 * half : 0), 4); }
+  int out_len(int T) const { int raw = nfft + hop * (T - 1); return center ? raw - 2 * half : raw; }
+  int pad_frames() const { return R - 1; }
+  int blk_lo() const { return center ? half / hop : 0; }
+  int blk_hi(int T) const {   // inclusive last raw block that intersects the kept range
+    int raw = nfft + hop * (T - 1);
+    int end = center ? raw - half : raw;
+    return (end - 1) / hop;
+  }
+  void init(int nfft_, int hop_, int center_, int reflect_, int norm_mul_) {
+    nfft = nfft_; hop = hop_; half = nfft_ / 2; center = center_; reflect = reflect_; norm_mul = norm_mul_;
+    rows2f = nfft + 2;
+    ld = round_up(rows2f, 8);
+    R = (nfft + hop - 1) / hop;
+  }
+};
+
+void fill_stft_gemm(GemmArgs& g, const StftPlan& p, const float* xp, int Lp, const float* fwd, int B, int T,
+                    float* C, long long c_sB, long long c_sT, long long c_sN) {
+  memset(&g, 0, sizeof(g));
+  g.A = xp; g.a_sB = Lp; g.a_sT = p.hop; g.a_t0 = 0; g.TM = T;
+  g.W = fwd; g.ldw = p.nfft;
+  g.M = B * T; g.N = p.rows2f; g.K = p.nfft;
+  g.C = C; g.c_sB = c_sB; g.c_sT = c_sT; g.c_sN = c_sN;
+}
+
+void fill_istft_gemm(GemmArgs& g, const StftPlan& p, const float* enh_padded, const float* ola_w,
+                     const float* norm, int B, int T, void* out, int out_dtype) {
+  memset(&g, 0, sizeof(g));
+  const int lo = p.blk_lo(), hi = p.blk_hi(T);
+  g.A = enh_padded; g.a_sB = (long long)(T + 2 * p.pad_frames()) * p.ld; g.a_sT = p.ld; g.a_t0 = lo;
+  g.TM = hi - lo + 1;
+  g.W = ola_w; g.ldw = p.R * p.ld;
+  g.M = B * g.TM; g.N = p.hop; g.K = p.R * p.ld;
+  g.norm = norm; g.norm_mul = p.norm_mul; g.hop = p.hop; g.shift = p.center ? p.half : 0;
+  g.out_len = p.out_len(T); g.out_dtype = out_dtype; g.out = out;
+}
+
+}  // namespace
+
+// ===================================================================================
+struct adn_model {
+  std::string err;
+  int device = 0;
+  std::string family;
+  std::map<std::string, std::string> meta;
+  std::map<std::string, TensorRef> index;
+  float* d_blob = nullptr;
+  size_t nfloats = 0;
+
+  int in_dtype = ADN_F32, out_dtype = ADN_F32;
+  int L = 0, T = 0, Lp = 0, Lout = 0;
+  StftPlan stft;
+  const float* d_fwd = nullptr;
+  float* d_ola = nullptr;
+  float* d_norm = nullptr;
+
+  gtcrn::Weights w;
+  gtcrn::Buffers buf{};
+  int capacity = 0;
+  size_t ws_bytes = 0;
+  std::vector<void*> allocs;
+  void* d_in = nullptr;     // device staging for adn_run_host
+  void* d_out = nullptr;
+  cudaStream_t own_stream = nullptr;
+
+  bool profiling = false;
+  std::vector<cudaEvent_t> events;
+  std::vector<const char*> ev_names;
+  std::vector<float> ev_ms;
+  size_t ev_used = 0;
+  cudaStream_t ev_stream = nullptr;
+  int last_launches = 0;
+  int last_batch = 0;
+  int stop_after = 0;       // diagnostics: stop the launch sequence after N kernels
+};
+
+namespace {
+
+size_t dtype_size(int dt) { return dt == ADN_F32 ? 4 : 2; }
+
+int parse_dtype(const std::string& s, int& out) {
+  if (s == "F32") out = ADN_F32;
+  else if (s == "INT16") out = ADN_I16;
+  else if (s == "F16") out = ADN_F16;
+  else return 0;
+  return 1;
+}
+
+const float* dptr(adn_model* m, const std::string& name, size_t expect, bool& ok) {
+  auto it = m->index.find(name);
+  if (it == m->index.end()) {
+    if (ok) m->err = "weight blob has no tensor '" + name + "'";
+    ok = false;
+    return nullptr;
+  }
+  if (expect && it->second.count != expect) {
+    if (ok) m->err = "tensor '" + name + "' has " + std::to_string(it->second.count) + " floats, expected " +
+                     std::to_string(expect);
+    ok = false;
+    return nullptr;
+  }
+  return m->d_blob + it->second.offset;
+}
+
+template <typename S>
+void load_struct(adn_model* m, const float* hblob, const std::string& name, S& dst, bool& ok) {
+  auto it = m->index.find(name);
+  if (it == m->index.end() || it->second.count != sizeof(S) / sizeof(float)) {
+    if (ok) m->err = "tensor '" + name + "' missing or not " + std::to_string(sizeof(S) / sizeof(float)) + " floats";
+    ok = false;
+    return;
+  }
+  memcpy(&dst, hblob + it->second.offset, sizeof(S));
+}
+
+gtcrn::GruPtrs gru_ptrs(adn_model* m, const std::string& p, int I, int H, bool& ok) {
+  gtcrn::GruPtrs g;
+  g.w_ih = dptr(m, p + ".w_ih", (size_t)3 * H * I, ok);
+  g.w_hh = dptr(m, p + ".w_hh", (size_t)3 * H * H, ok);
+  g.b_ih = dptr(m, p + ".b_ih", (size_t)3 * H, ok);
+  g.b_hh = dptr(m, p + ".b_hh", (size_t)3 * H, ok);
+  return g;
+}
+
+adn_status dev_alloc(adn_model* m, void** p, size_t bytes, bool zero) {
+  ADN_CUDA_TRY(cudaMalloc(p, bytes), m->err);
+  m->allocs.push_back(*p);
+  m->ws_bytes += bytes;
+  if (zero) ADN_CUDA_TRY(cudaMemset(*p, 0, bytes), m->err);
+  return ADN_OK;
+}
+
+void free_workspace(adn_model* m) {
+  for (void* p : m->allocs) cudaFree(p);
+  m->allocs.clear();
+  m->ws_bytes = 0;
+  m->capacity = 0;
+}
+
+size_t workspace_bytes_for(const adn_model* m, int B) {
+  using namespace gtcrn;
+  size_t T = m->T, f = 0;
+  f += (size_t)B * m->Lp;                       // xp
+  f += (size_t)B * T * SPEC_LD;                 // spec
+  f += (size_t)B * T * FRAME_E0;                // e0
+  f += (size_t)4 * B * T * FRAME16;             // e1..e4
+  f += (size_t)B * T * 8 * E1_F + (size_t)B * T * 8;   // h1, zt
+  f += (size_t)3 * B * T * FRAME16;             // xa, xb, inter
+  f += (size_t)B * (T + 2 * m->stft.pad_frames()) * SPEC_LD;   // enh
+  size_t bytes = f * sizeof(float);
+  bytes += (size_t)B * m->L * dtype_size(m->in_dtype) + (size_t)B * m->Lout * dtype_size(m->out_dtype);
+  return bytes;
+}
+
+adn_status ensure_capacity(adn_model* m, int B) {
+  using namespace gtcrn;
+  if (B <= m->capacity) return ADN_OK;
+  ADN_CUDA_TRY(cudaDeviceSynchronize(), m->err);
+  free_workspace(m);
+  const size_t T = m->T;
+  adn_status s;
+#define A(ptr, nfl, zero) \
+  if ((s = dev_alloc(m, (void**)&(ptr), (size_t)(nfl) * sizeof(float), zero)) != ADN_OK) return s;
+  A(m->buf.xp, (size_t)B * m->Lp, false);
+  A(m->buf.spec, (size_t)B * T * SPEC_LD, true);
+  A(m->buf.e0, (size_t)B * T * FRAME_E0, false);
+  m->buf.e[0] = nullptr;
+  for (int i = 1; i <= 4; ++i) A(m->buf.e[i], (size_t)B * T * FRAME16, false);
+  A(m->buf.h1, (size_t)B * T * 8 * E1_F, false);
+  A(m->buf.zt, (size_t)B * T * 8, false);
+  A(m->buf.xa, (size_t)B * T * FRAME16, false);
+  A(m->buf.xb, (size_t)B * T * FRAME16, false);
+  A(m->buf.inter, (size_t)B * T * FRAME16, false);
+  A(m->buf.enh, (size_t)B * (T + 2 * m->stft.pad_frames()) * SPEC_LD, true);
+#undef A
+  if ((s = dev_alloc(m, &m->d_in, (size_t)B * m->L * dtype_size(m->in_dtype), false)) != ADN_OK) return s;
+  if ((s = dev_alloc(m, &m->d_out, (size_t)B * m->Lout * dtype_size(m->out_dtype), false)) != ADN_OK) return s;
+  m->capacity = B;
+  return ADN_OK;
+}
+
+void tick_cb(void* ctx, const char* name) {
+  adn_model* m = (adn_model*)ctx;
+  if (!m->profiling) return;
+  if (m->ev_used >= m->events.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    m->events.push_back(e);
+    m->ev_names.push_back(name);
+  }
+  m->ev_names[m->ev_used] = name;
+  cudaEventRecord(m->events[m->ev_used], m->ev_stream);
+  ++m->ev_used;
+}
+
+adn_status build_gtcrn(adn_model* m, const float* hblob) {
+  bool ok = true;
+  auto& w = m->w;
+  load_struct(m, hblob, "enc_front", w.enc_front, ok);
+  load_struct(m, hblob, "dec_tail", w.dec_tail, ok);
+  for (int i = 0; i < 3; ++i) {
+    load_struct(m, hblob, "enc_gt." + std::to_string(i), w.enc_gt[i], ok);
+    load_struct(m, hblob, "dec_gt." + std::to_string(i), w.dec_gt[i], ok);
+    std::string pe = "enc_tra." + std::to_string(i), pd = "dec_tra." + std::to_string(i);
+    w.enc_tra[i].gru = gru_ptrs(m, pe, 8, 16, ok);
+    w.enc_tra[i].fc_w = dptr(m, pe + ".fc_w", 128, ok);
+    w.enc_tra[i].fc_b = dptr(m, pe + ".fc_b", 8, ok);
+    w.dec_tra[i].gru = gru_ptrs(m, pd, 8, 16, ok);
+    w.dec_tra[i].fc_w = dptr(m, pd + ".fc_w", 128, ok);
+    w.dec_tra[i].fc_b = dptr(m, pd + ".fc_b", 8, ok);
+  }
+  for (int i = 0; i < 2; ++i) {
+    std::string p = "dp." + std::to_string(i);
+    for (int g = 0; g < 2; ++g) {
+      for (int d = 0; d < 2; ++d)
+        w.dp[i].intra[g][d] = gru_ptrs(m, p + ".intra." + std::to_string(g) + "." + std::to_string(d), 8, 4, ok);
+      w.dp[i].inter[g] = gru_ptrs(m, p + ".inter." + std::to_string(g), 8, 8, ok);
+    }
+    w.dp[i].intra_fc_w = dptr(m, p + ".intra_fc_w", 256, ok);
+    w.dp[i].intra_fc_b = dptr(m, p + ".intra_fc_b", 16, ok);
+    w.dp[i].intra_ln_w = dptr(m, p + ".intra_ln_w", 528, ok);
+    w.dp[i].intra_ln_b = dptr(m, p + ".intra_ln_b", 528, ok);
+    w.dp[i].inter_fc_w = dptr(m, p + ".inter_fc_w", 256, ok);
+    w.dp[i].inter_fc_b = dptr(m, p + ".inter_fc_b", 16, ok);
+    w.dp[i].inter_ln_w = dptr(m, p + ".inter_ln_w", 528, ok);
+    w.dp[i].inter_ln_b = dptr(m, p + ".inter_ln_b", 528, ok);
+  }
+  w.erb.bm = dptr(m, "erb.bm", 192 * 64, ok);
+  w.erb.bm_lo = dptr(m, "erb.bm_lo", 64, ok);
+  w.erb.bm_hi = dptr(m, "erb.bm_hi", 64, ok);
+  w.erb.bs = dptr(m, "erb.bs", 64 * 192, ok);
+  w.erb.bs_lo = dptr(m, "erb.bs_lo", 192, ok);
+  w.erb.bs_hi = dptr(m, "erb.bs_hi", 192, ok);
+  m->d_fwd = dptr(m, "stft.fwd", (size_t)514 * 512, ok);
+  if (!ok) return ADN_ERR_INVALID;
+
+  auto inv = m->index.find("istft.inv");
+  auto nrm = m->index.find("istft.norm");
+  if (inv == m->index.end() || inv->second.count != (size_t)514 * 512) {
+    m->err = "tensor 'istft.inv' missing or wrong size";
+    return ADN_ERR_INVALID;
+  }
+  if (nrm == m->index.end() || nrm->second.count != (size_t)m->Lout) {
+    m->err = "tensor 'istft.norm' must have output_audio_length floats";
+    return ADN_ERR_INVALID;
+  }
+  std::vector<float> ola = build_ola_weight(hblob + inv->second.offset, m->stft.nfft, m->stft.hop, m->stft.ld, m->stft.R);
+  ADN_CUDA_TRY(cudaMalloc((void**)&m->d_ola, ola.size() * sizeof(float)), m->err);
+  ADN_CUDA_TRY(cudaMemcpy(m->d_ola, ola.data(), ola.size() * sizeof(float), cudaMemcpyHostToDevice), m->err);
+  m->d_norm = m->d_blob + nrm->second.offset;
+  return ADN_OK;
+}
+
+}  // namespace
+
+// ===================================================================================
+extern "C" {
+
+const char* adn_version(void) { return "adn 0.1 sm_100a"; }
+
+const char* adn_last_error(const adn_model* m) {
+  if (m) return m->err.c_str();
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  return g_last_error.c_str();
+}
+
+adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weights, size_t nfloats,
+                      int device_id) {
+  if (!out) return ADN_ERR_INVALID;
+  *out = nullptr;
+  if (!desc || !weights) {
+    set_global_error("adn_create: null descriptor or weights");
+    return ADN_ERR_INVALID;
+  }
+  adn_model* m = new adn_model();
+  auto fail = [&](adn_status s) {
+    set_global_error(m->err);
+    adn_destroy(m);
+    return s;
+  };
+  m->device = device_id;
+  for (int i = 0; i < desc->n_kv; ++i) m->meta[desc->keys[i]] = desc->values[i];
+  for (int i = 0; i < desc->n_tensors; ++i) {
+    const auto& t = desc->tensors[i];
+    if (t.offset + t.count > nfloats) {
+      m->err = std::string("tensor '") + t.name + "' exceeds the blob";
+      return fail(ADN_ERR_INVALID);
+    }
+    m->index[t.name] = TensorRef{t.offset, t.count};
+  }
+  auto need = [&](const char* k, std::string& v) {
+    auto it = m->meta.find(k);
+    if (it == m->meta.end() || it->second.empty()) {
+      m->err = std::string("Required metadata key ") + k + " is missing.";
+      return false;
+    }
+    v = it->second;
+    return true;
+  };
+  std::string fam, sL, sin, sout, snfft, shop;
+  if (!need("model_family", fam) || !need("input_audio_length", sL) || !need("input_audio_dtype", sin) ||
+      !need("output_audio_dtype", sout) || !need("nfft", snfft) || !need("hop_length", shop))
+    return fail(ADN_ERR_INVALID);
+  m->family = fam;
+  if (fam != "gtcrn") {
+    m->err = "unsupported model_family '" + fam + "'";
+    return fail(ADN_ERR_UNSUPPORTED);
+  }
+  if (!parse_dtype(sin, m->in_dtype) || !parse_dtype(sout, m->out_dtype)) {
+    m->err = "input/output_audio_dtype must be F32, F16 or INT16";
+    return fail(ADN_ERR_INVALID);
+  }
+  m->L = atoi(sL.c_str());
+  int nfft = atoi(snfft.c_str()), hop = atoi(shop.c_str());
+  if (nfft != gtcrn::NFFT || hop != gtcrn::HOP) {
+    m->err = "gtcrn requires nfft=512, hop_length=256";
+    return fail(ADN_ERR_INVALID);
+  }
+  if (m->L < nfft) {
+    m->err = "input_audio_length must be >= nfft";
+    return fail(ADN_ERR_INVALID);
+  }
+  m->stft.init(nfft, hop, 1, 1, 0);
+  m->T = m->stft.n_frames(m->L);
+  m->Lp = m->stft.padded_len(m->L);
+  m->Lout = m->stft.out_len(m->T);
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device_id) {
+    m->err = "no usable CUDA device " + std::to_string(device_id) + " (libadn has no CPU fallback)";
+    return fail(ADN_ERR_CUDA);
+  }
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device_id) != cudaSuccess || cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) {
+    m->err = "cudaSetDevice failed";
+    return fail(ADN_ERR_CUDA);
+  }
+  if (prop.major != 10) {
+    m->err = "libadn is built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor);
+    return fail(ADN_ERR_CUDA);
+  }
+  if (cudaMalloc((void**)&m->d_blob, nfloats * sizeof(float)) != cudaSuccess ||
+      cudaMemcpy(m->d_blob, weights, nfloats * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+    m->err = "failed to upload the weight blob";
+    return fail(ADN_ERR_CUDA);
+  }
+  m->nfloats = nfloats;
+  adn_status s = build_gtcrn(m, weights);
+  if (s != ADN_OK) return fail(s);
+  if (cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    m->err = "cudaStreamCreate failed";
+    return fail(ADN_ERR_CUDA);
+  }
+  *out = m;
+  return ADN_OK;
+}
+
+void adn_destroy(adn_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  cudaDeviceSynchronize();
+  free_workspace(m);
+  if (m->d_blob) cudaFree(m->d_blob);
+  if (m->d_ola) cudaFree(m->d_ola);
+  for (auto e : m->events) cudaEventDestroy(e);
+  if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  delete m;
+}
+
+adn_status adn_io_info(const adn_model* m, adn_tensor_info* in, adn_tensor_info* outs, int32_t* n_out) {
+  if (!m || !in || !outs || !n_out) return ADN_ERR_INVALID;
+  memset(in, 0, sizeof(*in));
+  memset(outs, 0, sizeof(*outs));
+  strncpy(in->name, "noisy_audio", sizeof(in->name) - 1);       // Export_GTCRN.py:768
+  in->dtype = m->in_dtype; in->channels = 1; in->length = m->L;
+  strncpy(outs->name, "denoised_audio", sizeof(outs->name) - 1); // Export_GTCRN.py:769
+  outs->dtype = m->out_dtype; outs->channels = 1; outs->length = m->Lout;
+  *n_out = 1;
+  return ADN_OK;
+}
+
+size_t adn_workspace_bytes(const adn_model* m, int32_t batch) {
+  if (!m || batch <= 0) return 0;
+  return workspace_bytes_for(m, batch);
+}
+
+int32_t adn_launches_per_run(const adn_model* m, int32_t batch) {
+  (void)batch;
+  return m ? 22 : 0;   // prep, stft, enc_front, 6x(gt_main, tra_apply), 2x(intra, inter), ln_res, dec_tail, istft
+}
+
+adn_status adn_run(adn_model* m, const void* d_in, void* const* d_outs, int32_t batch, void* stream) {
+  if (!m) return ADN_ERR_INVALID;
+  if (!d_in || !d_outs || !d_outs[0] || batch <= 0) {
+    m->err = "adn_run: null buffer or non-positive batch";
+    return ADN_ERR_INVALID;
+  }
+  ADN_CUDA_TRY(cudaSetDevice(m->device), m->err);
+  adn_status s = ensure_capacity(m, batch);
+  if (s != ADN_OK) return s;
+  cudaStream_t st = (cudaStream_t)stream;
+  m->ev_used = 0;
+  m->ev_stream = st;
+  int n = 0;
+  tick_cb(m, "start");
+
+  gtcrn::launch_prep(d_in, m->in_dtype, m->buf.xp, batch, m->L, m->Lp, m->stft.half, /*remove_dc=*/1,
+                     m->stft.reflect, st);
+  ++n; tick_cb(m, "prep");
+
+  GemmArgs g;
+  fill_stft_gemm(g, m->stft, m->buf.xp, m->Lp, m->d_fwd, batch, m->T, m->buf.spec,
+                 (long long)m->T * gtcrn::SPEC_LD, gtcrn::SPEC_LD, 1);
+  launch_gemm_ffma(g, EPI_STORE, st);
+  ++n; tick_cb(m, "stft_gemm");
+
+  gtcrn::Dims d{batch, m->L, m->Lp, m->T};
+  const int stop_bb = m->stop_after > 0 ? (m->stop_after > 2 ? m->stop_after - 2 : 1) : 0;
+  n += gtcrn::launch_backbone(m->w, m->buf, d, m->stft.pad_frames(), st, tick_cb, m, stop_bb);
+  m->last_launches = n;
+  m->last_batch = batch;
+  if (m->stop_after > 0 && n >= m->stop_after) {
+    ADN_CUDA_TRY(cudaGetLastError(), m->err);
+    return ADN_OK;
+  }
+
+  fill_istft_gemm(g, m->stft, m->buf.enh, m->d_ola, m->d_norm, batch, m->T, d_outs[0], m->out_dtype);
+  launch_gemm_ffma(g, EPI_ISTFT, st);
+  ++n; tick_cb(m, "istft_gemm");
+
+  m->last_launches = n;
+  m->last_batch = batch;
+  ADN_CUDA_TRY(cudaGetLastError(), m->err);
+  return ADN_OK;
+}
+
+adn_status adn_run_host(adn_model* m, const void* h_in, void* const* h_outs, int32_t batch) {
+  if (!m) return ADN_ERR_INVALID;
+  if (!h_in || !h_outs || !h_outs[0] || batch <= 0) {
+    m->err = "adn_run_host: null buffer or non-positive batch";
+    return ADN_ERR_INVALID;
+  }
+  ADN_CUDA_TRY(cudaSetDevice(m->device), m->err);
+  adn_status s = ensure_capacity(m, batch);
+  if (s != ADN_OK) return s;
+  cudaStream_t st = m->own_stream;
+  size_t in_bytes = (size_t)batch * m->L * dtype_size(m->in_dtype);
+  size_t out_bytes = (size_t)batch * m->Lout * dtype_size(m->out_dtype);
+  ADN_CUDA_TRY(cudaMemcpyAsync(m->d_in, h_in, in_bytes, cudaMemcpyHostToDevice, st), m->err);
+  void* outs[1] = {m->d_out};
+  s = adn_run(m, m->d_in, outs, batch, st);
+  if (s != ADN_OK) return s;
+  ADN_CUDA_TRY(cudaMemcpyAsync(h_outs[0], m->d_out, out_bytes, cudaMemcpyDeviceToHost, st), m->err);
+  ADN_CUDA_TRY(cudaStreamSynchronize(st), m->err);
+  return ADN_OK;
+}
+
+adn_status adn_debug_stop_after(adn_model* m, int32_t n_launches) {
+  if (!m) return ADN_ERR_INVALID;
+  m->stop_after = n_launches;
+  return ADN_OK;
+}
+
+adn_status adn_set_profiling(adn_model* m, int32_t enabled) {
+  if (!m) return ADN_ERR_INVALID;
+  m->profiling = enabled != 0;
+  return ADN_OK;
+}
+
+adn_status adn_last_kernel_times(adn_model* m, const char** names, float* ms, int32_t cap, int32_t* n) {
+  if (!m || !n) return ADN_ERR_INVALID;
+  *n = 0;
+  if (m->ev_used < 2) return ADN_OK;
+  ADN_CUDA_TRY(cudaEventSynchronize(m->events[m->ev_used - 1]), m->err);
+  for (size_t i = 1; i < m->ev_used && (int)(i - 1) < cap; ++i) {
+    float t = 0.f;
+    ADN_CUDA_TRY(cudaEventElapsedTime(&t, m->events[i - 1], m->events[i]), m->err);
+    names[i - 1] = m->ev_names[i];
+    ms[i - 1] = t;
+    *n = (int)i;
+  }
+  return ADN_OK;
+}
+
+adn_status adn_debug_read(adn_model* m, const char* name, float* h_dst, size_t count, size_t* actual) {
+  if (!m || !name) return ADN_ERR_INVALID;
+  using namespace gtcrn;
+  const size_t B = m->last_batch, T = m->T;
+  if (B == 0) {
+    m->err = "adn_debug_read: no run yet";
+    return ADN_ERR_INVALID;
+  }
+  std::map<std::string, std::pair<const float*, size_t>> tbl = {
+      {"xp", {m->buf.xp, B * m->Lp}},
+      {"spec", {m->buf.spec, B * T * SPEC_LD}},
+      {"e0", {m->buf.e0, B * T * FRAME_E0}},
+      {"e1", {m->buf.e[1], B * T * FRAME16}},
+      {"e2", {m->buf.e[2], B * T * FRAME16}},
+      {"e3", {m->buf.e[3], B * T * FRAME16}},
+      {"e4", {m->buf.e[4], B * T * FRAME16}},
+      {"h1", {m->buf.h1, B * T * 8 * E1_F}},
+      {"zt", {m->buf.zt, B * T * 8}},
+      {"xa", {m->buf.xa, B * T * FRAME16}},
+      {"xb", {m->buf.xb, B * T * FRAME16}},
+      {"inter", {m->buf.inter, B * T * FRAME16}},
+      {"enh", {m->buf.enh, B * (T + 2 * m->stft.pad_frames()) * SPEC_LD}},
+  };
+  auto it = tbl.find(name);
+  if (it == tbl.end()) {
+    m->err = std::string("adn_debug_read: unknown tensor '") + name + "'";
+    return ADN_ERR_INVALID;
+  }
+  if (actual) *actual = it->second.second;
+  if (!h_dst) return ADN_OK;
+  size_t nc = count < it->second.second ? count : it->second.second;
+  ADN_CUDA_TRY(cudaSetDevice(m->device), m->err);
+  ADN_CUDA_TRY(cudaDeviceSynchronize(), m->err);
+  ADN_CUDA_TRY(cudaMemcpy(h_dst, it->second.first, nc * sizeof(float), cudaMemcpyDeviceToHost), m->err);
+  return ADN_OK;
+}
+
+}  // extern "C"
+
+// ===================================================================================
+// stand-alone STFT / ISTFT operators
+// ===================================================================================
+struct adn_stft {
+  int device = 0;
+  StftPlan p;
+  int T = 0;            // frames the norm table was built for
+  float* d_fwd = nullptr;
+  float* d_ola = nullptr;
+  float* d_norm = nullptr;
+  float* d_xp = nullptr;
+  size_t xp_cap = 0;
+  float* d_fm = nullptr;   // frame-major padded spectrum for the inverse
+  size_t fm_cap = 0;
+};
+
+namespace {
+
+__global__ void pack_to_frame_major_kernel(const float* __restrict__ spec, float* __restrict__ fm, int rows2f,
+                                           int T, int ld, int pad) {
+  // spec (B, 2F, T) -> fm (B, T+2*pad, ld); 32x32 smem transpose tiles
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const float* s = spec + (long long)b * rows2f * T;
+  float* o = fm + (long long)b * (T + 2 * pad) * ld;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int r = r0 + i, t = t0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows2f && t < T) ? s[(long long)r * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int t = t0 + i, r = r0 + threadIdx.x;
+    if (t < T && r < rows2f) o[(long long)(t + pad) * ld + r] = tile[threadIdx.x][i];
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+adn_status adn_stft_create(adn_stft** out, const adn_stft_geom* g, const float* fwd_basis,
+                           const float* inv_basis, const float* win_norm, int32_t n_frames, int device_id) {
+  if (!out) return ADN_ERR_INVALID;
+  *out = nullptr;
+  if (!g || !fwd_basis || !inv_basis || !win_norm || g->nfft <= 0 || g->hop <= 0 || n_frames <= 0) {
+    set_global_error("adn_stft_create: invalid argument");
+    return ADN_ERR_INVALID;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device_id || cudaSetDevice(device_id) != cudaSuccess) {
+    set_global_error("no usable CUDA device (libadn has no CPU fallback)");
+    return ADN_ERR_CUDA;
+  }
+  adn_stft* s = new adn_stft();
+  s->device = device_id;
+  s->p.init(g->nfft, g->hop, g->center, g->pad_reflect, g->norm_multiply);
+  s->T = n_frames;
+  const size_t nb = (size_t)s->p.rows2f * g->nfft;
+  std::vector<float> ola = build_ola_weight(inv_basis, g->nfft, g->hop, s->p.ld, s->p.R);
+  const int lout = s->p.out_len(n_frames);
+  bool ok = cudaMalloc((void**)&s->d_fwd, nb * 4) == cudaSuccess &&
+            cudaMalloc((void**)&s->d_ola, ola.size() * 4) == cudaSuccess &&
+            cudaMalloc((void**)&s->d_norm, (size_t)lout * 4) == cudaSuccess &&
+            cudaMemcpy(s->d_fwd, fwd_basis, nb * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMemcpy(s->d_ola, ola.data(), ola.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMemcpy(s->d_norm, win_norm, (size_t)lout * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+  if (!ok) {
+    set_global_error(std::string("adn_stft_create: ") + cudaGetErrorString(cudaGetLastError()));
+    adn_stft_destroy(s);
+    return ADN_ERR_CUDA;
+  }
+  *out = s;
+  return ADN_OK;
+}
+
+void adn_stft_destroy(adn_stft* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  cudaDeviceSynchronize();
+  cudaFree(s->d_fwd); cudaFree(s->d_ola); cudaFree(s->d_norm); cudaFree(s->d_xp); cudaFree(s->d_fm);
+  delete s;
+}
+
+adn_status adn_stft_forward(adn_stft* s, const float* d_x, float* d_spec, int32_t batch, int32_t length,
+                            void* stream) {
+  if (!s || !d_x || !d_spec || batch <= 0 || length < s->p.nfft) {
+    set_global_error("adn_stft_forward: invalid argument");
+    return ADN_ERR_INVALID;
+  }
+  std::string err;
+  ADN_CUDA_TRY(cudaSetDevice(s->device), err);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Lp = s->p.padded_len(length), T = s->p.n_frames(length);
+  size_t need = (size_t)batch * Lp;
+  if (need > s->xp_cap) {
+    cudaDeviceSynchronize();
+    cudaFree(s->d_xp);
+    if (cudaMalloc((void**)&s->d_xp, need * 4) != cudaSuccess) {
+      set_global_error("adn_stft_forward: out of memory");
+      s->d_xp = nullptr; s->xp_cap = 0;
+      return ADN_ERR_CUDA;
+    }
+    s->xp_cap = need;
+  }
+  gtcrn::launch_prep(d_x, ADN_F32, s->d_xp, batch, length, Lp, s->p.center ? s->p.half : 0, 0, s->p.reflect, st);
+  GemmArgs g;
+  fill_stft_gemm(g, s->p, s->d_xp, Lp, s->d_fwd, batch, T, d_spec, (long long)s->p.rows2f * T, 1, T);
+  launch_gemm_ffma(g, EPI_STORE, st);
+  if (cudaGetLastError() != cudaSuccess) {
+    set_global_error("adn_stft_forward: launch failed");
+    return ADN_ERR_CUDA;
+  }
+  return ADN_OK;
+}
+
+adn_status adn_stft_inverse(adn_stft* s, const float* d_spec, float* d_y, int32_t batch, int32_t n_frames,
+                            void* stream) {
+  if (!s || !d_spec || !d_y || batch <= 0 || n_frames != s->T) {
+    set_global_error("adn_stft_inverse: invalid argument (n_frames must equal the plan's)");
+    return ADN_ERR_INVALID;
+  }
+  std::string err;
+  ADN_CUDA_TRY(cudaSetDevice(s->device), err);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int T = n_frames, pad = s->p.pad_frames(), ld = s->p.ld;
+  size_t need = (size_t)batch * (T + 2 * pad) * ld;
+  if (need > s->fm_cap) {
+    cudaDeviceSynchronize();
+    cudaFree(s->d_fm);
+    if (cudaMalloc((void**)&s->d_fm, need * 4) != cudaSuccess) {
+      set_global_error("adn_stft_inverse: out of memory");
+      s->d_fm = nullptr; s->fm_cap = 0;
+      return ADN_ERR_CUDA;
+    }
+    s->fm_cap = need;
+  }
+  cudaMemsetAsync(s->d_fm, 0, need * 4, st);
+  dim3 grid((T + 31) / 32, (s->p.rows2f + 31) / 32, batch), block(32, 8);
+  pack_to_frame_major_kernel<<<grid, block, 0, st>>>(d_spec, s->d_fm, s->p.rows2f, T, ld, pad);
+  GemmArgs g;
+  fill_istft_gemm(g, s->p, s->d_fm, s->d_ola, s->d_norm, batch, T, d_y, ADN_F32);
+  launch_gemm_ffma(g, EPI_ISTFT, st);
+  if (cudaGetLastError() != cudaSuccess) {
+    set_global_error("adn_stft_inverse: launch failed");
+    return ADN_ERR_CUDA;
+  }
+  return ADN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,805 @@
+// GTCRN backbone kernels (fp32, CUDA cores; channel counts are 2..24 so there is no
+// GEMM-shaped work here -- the dense DFT GEMMs live in gemm_*.cu).
+//
+// Layout: every activation is frame-major (B, T, C, F): one frame's (C,F) block is
+// contiguous, so per-frame kernels stage it with fully coalesced loads and the causal
+// time-dilated taps of the GTConv blocks fetch whole contiguous frames.
+//
+// Reference map (GTCRN/Export_GTCRN.py):
+//   enc_front_kernel  : forward_packed magnitude :592-596, ERB.bm :99-102, SFE :131-141,
+//                       en_convs.0/.1 :488-489,499-501
+//   gt_main_kernel    : GTConvBlock.forward :303-320 (SFE, point_conv1, depth_conv, point_conv2)
+//   tra_apply_kernel  : TRA :152-156 + channel shuffle :324 (+ decoder skip add :524-528)
+//   dp_intra_kernel   : DPGRNN intra path :471-475 (+ previous inter LayerNorm :481)
+//   dp_inter_kernel   : DPGRNN inter path :478-480
+//   ln_res_kernel     : final inter LayerNorm + residual :481 (+ skip add :524)
+//   dec_tail_kernel   : de_convs.3/.4 :515-516,527-528, ERB.bs :104-107, complex mask :585-590
+#include "adn.h"
+#include "gtcrn.cuh"
+
+namespace gtcrn {
+
+// =================================================================================
+// prep: cast + scale + DC removal + centre padding.  One CTA per chunk.
+// =================================================================================
+template <typename Tin>
+__device__ __forceinline__ float load_sample(const Tin* p, long long i);
+template <>
+__device__ __forceinline__ float load_sample<float>(const float* p, long long i) { return p[i]; }
+template <>
+__device__ __forceinline__ float load_sample<int16_t>(const int16_t* p, long long i) {
+  return (float)p[i] * (1.0f / 32768.0f);   // Export_GTCRN.py:645-646
+}
+template <>
+__device__ __forceinline__ float load_sample<__half>(const __half* p, long long i) {
+  return __half2float(p[i]);
+}
+
+template <typename Tin>
+__global__ void __launch_bounds__(256) prep_kernel(const Tin* __restrict__ in, float* __restrict__ xp,
+                                                   int L, int Lp, int half, int remove_dc, int reflect) {
+  const int b = blockIdx.x;
+  const Tin* x = in + (long long)b * L;
+  float* o = xp + (long long)b * Lp;
+  __shared__ double red[8];
+  __shared__ float mean_s;
+  float mean = 0.f;
+  if (remove_dc) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) s += (double)load_sample<Tin>(x, i);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += red[w];
+      mean_s = (float)(t / (double)L);
+    }
+    __syncthreads();
+    mean = mean_s;
+  }
+  for (int i = threadIdx.x; i < Lp; i += blockDim.x) {
+    int j = i - half;        // index into the unpadded signal
+    float v = 0.f;
+    if (j >= 0 && j < L) {
+      v = load_sample<Tin>(x, j) - mean;
+    } else if (reflect) {
+      int jj = j < 0 ? -j : 2 * (L - 1) - j;   // reflect without repeating the edge sample
+      if (jj >= 0 && jj < L) v = load_sample<Tin>(x, jj) - mean;
+    }
+    o[i] = v;
+  }
+}
+
+void launch_prep(const void* in, int in_dtype, float* xp, int B, int L, int Lp, int half,
+                 int remove_dc, int reflect, cudaStream_t st) {
+  if (in_dtype == ADN_F32)
+    prep_kernel<float><<<B, 256, 0, st>>>((const float*)in, xp, L, Lp, half, remove_dc, reflect);
+  else if (in_dtype == ADN_I16)
+    prep_kernel<int16_t><<<B, 256, 0, st>>>((const int16_t*)in, xp, L, Lp, half, remove_dc, reflect);
+  else
+    prep_kernel<__half><<<B, 256, 0, st>>>((const __half*)in, xp, L, Lp, half, remove_dc, reflect);
+}
+
+// =================================================================================
+// enc_front: spectrum frame -> |X|, ERB, SFE, en_convs.0, en_convs.1.  Kernel height is 1
+// for all of these, so frames are independent.  FR frames per CTA.
+// =================================================================================
+constexpr int EF_FR = 4;
+constexpr int EF_THREADS = 288;
+
+__global__ void __launch_bounds__(EF_THREADS)
+enc_front_kernel(const __grid_constant__ EncFrontW w, const ErbW erb, const float* __restrict__ spec,
+                 float* __restrict__ e0, float* __restrict__ e1, int nframes) {
+  __shared__ float sp[EF_FR][SPEC_LD];            // packed spectrum frame
+  __shared__ float fe[EF_FR][3][ERB_F + 8];       // ERB features, 4 zeros each side
+  __shared__ float e0s[EF_FR][16][E0_F + 4];      // en_convs.0 output, 2 zeros each side
+
+  const int tid = threadIdx.x;
+  const long long f0 = (long long)blockIdx.x * EF_FR;
+
+  for (int i = tid; i < EF_FR * SPEC_LD; i += EF_THREADS) {
+    int fr = i / SPEC_LD, c = i - fr * SPEC_LD;
+    long long fg = f0 + fr;
+    sp[fr][c] = (fg < nframes) ? __ldg(spec + fg * SPEC_LD + c) : 0.f;
+  }
+  for (int i = tid; i < EF_FR * 3 * (ERB_F + 8); i += EF_THREADS) (&fe[0][0][0])[i] = 0.f;
+  for (int i = tid; i < EF_FR * 16 * (E0_F + 4); i += EF_THREADS) (&e0s[0][0][0])[i] = 0.f;
+  __syncthreads();
+
+  // low 65 bins pass through, |X| = sqrt(re^2+im^2+1e-12) (:594-595)
+  for (int i = tid; i < EF_FR * 65; i += EF_THREADS) {
+    int fr = i / 65, f = i - fr * 65;
+    float re = sp[fr][f], im = sp[fr][FB + f];
+    fe[fr][0][4 + f] = sqrtf(re * re + im * im + 1e-12f);
+    fe[fr][1][4 + f] = re;
+    fe[fr][2][4 + f] = im;
+  }
+  // 192 high bins -> 64 ERB bands, ascending-bin accumulation over the nonzero range
+  for (int i = tid; i < EF_FR * 3 * 64; i += EF_THREADS) {
+    int fr = i / 192, r = i - fr * 192;
+    int c = r >> 6, j = r & 63;
+    int lo = (int)__ldg(erb.bm_lo + j), hi = (int)__ldg(erb.bm_hi + j);
+    float acc = 0.f;
+    for (int k = lo; k < hi; ++k) {
+      int f = 65 + k;
+      float v;
+      if (c == 0) {
+        float re = sp[fr][f], im = sp[fr][FB + f];
+        v = sqrtf(re * re + im * im + 1e-12f);
+      } else {
+        v = sp[fr][(c == 1 ? 0 : FB) + f];
+      }
+      acc = fmaf(v, __ldg(erb.bm + k * 64 + j), acc);
+    }
+    fe[fr][c][4 + 65 + j] = acc;
+  }
+  __syncthreads();
+
+  // en_convs.0: Conv2d(9->16,(1,5),stride 2,pad 2) over SFE(k=3) of the 3 ERB channels.
+  // SFE channel c*3+s at position p is fe[c][p+s-1]; positions p outside [0,129) are the
+  // conv's own zero padding.
+  for (int i = tid; i < EF_FR * E0_F; i += EF_THREADS) {
+    int fr = i / E0_F, g = i - fr * E0_F;
+    float acc[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) acc[o] = w.b0[o];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      int p = 2 * g + k - 2;
+      bool pv = (p >= 0) && (p < ERB_F);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          float v = pv ? fe[fr][c][4 + p + s - 1] : 0.f;
+#pragma unroll
+          for (int o = 0; o < 16; ++o) acc[o] = fmaf(w.w0[o][c * 3 + s][k], v, acc[o]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 16; ++o) e0s[fr][o][2 + g] = adn_prelu(acc[o], w.a0);
+  }
+  __syncthreads();
+
+  for (int i = tid; i < EF_FR * FRAME_E0; i += EF_THREADS) {
+    int fr = i / FRAME_E0, r = i - fr * FRAME_E0;
+    int o = r / E0_F, g = r - o * E0_F;
+    long long fg = f0 + fr;
+    if (fg < nframes) e0[fg * FRAME_E0 + r] = e0s[fr][o][2 + g];
+  }
+
+  // en_convs.1: Conv2d(16->16,(1,5),stride 2,pad 2,groups 2).  item = (frame, group, g)
+  for (int i = tid; i < EF_FR * 2 * E1_F; i += EF_THREADS) {
+    int fr = i / (2 * E1_F), r = i - fr * (2 * E1_F);
+    int grp = r / E1_F, g = r - grp * E1_F;
+    float acc[8];
+    if (grp == 0) {
+#pragma unroll
+      for (int o = 0; o < 8; ++o) acc[o] = w.b1[o];
+#pragma unroll
+      for (int ci = 0; ci < 8; ++ci)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          float v = e0s[fr][ci][2 * g + k];
+#pragma unroll
+          for (int o = 0; o < 8; ++o) acc[o] = fmaf(w.w1[o][ci][k], v, acc[o]);
+        }
+    } else {
+#pragma unroll
+      for (int o = 0; o < 8; ++o) acc[o] = w.b1[8 + o];
+#pragma unroll
+      for (int ci = 0; ci < 8; ++ci)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          float v = e0s[fr][8 + ci][2 * g + k];
+#pragma unroll
+          for (int o = 0; o < 8; ++o) acc[o] = fmaf(w.w1[8 + o][ci][k], v, acc[o]);
+        }
+    }
+    long long fg = f0 + fr;
+    if (fg < nframes) {
+#pragma unroll
+      for (int o = 0; o < 8; ++o) e1[fg * FRAME16 + (grp * 8 + o) * E1_F + g] = adn_prelu(acc[o], w.a1);
+    }
+  }
+}
+
+// =================================================================================
+// gt_main: GTConvBlock up to point_conv2 (+ the TRA energy z_t).  Frames with the same
+// residue t mod d form an undilated causal sequence, so a CTA owns KT consecutive steps
+// of one residue class (+2 recomputed halo frames) of one chunk.
+// =================================================================================
+constexpr int GT_KT = 6;
+constexpr int GT_FL = GT_KT + 2;
+constexpr int GT_THREADS = 288;   // >= GT_FL*33 = 264
+
+__global__ void __launch_bounds__(GT_THREADS)
+gt_main_kernel(const __grid_constant__ GTW w, const float* __restrict__ xin, float* __restrict__ h1,
+               float* __restrict__ zt, int T, int dil) {
+  __shared__ float xs[GT_FL][8][E1_F + 2];     // x1 tile, one zero column each side
+  __shared__ float hs[GT_FL][16][E1_F + 2];    // point_conv1 output tile
+  __shared__ float h1s[GT_KT][8][E1_F];
+
+  const int tid = threadIdx.x;
+  const int r = blockIdx.y, b = blockIdx.z;
+  const int nk = (T - r + dil - 1) / dil;      // frames in this residue class
+  const int k0 = blockIdx.x * GT_KT;
+  if (r >= T || k0 >= nk) return;
+  const float* xb = xin + (long long)b * T * FRAME16;
+
+  for (int i = tid; i < GT_FL * 8 * (E1_F + 2); i += GT_THREADS) {
+    int fl = i / (8 * (E1_F + 2)), rem = i - fl * (8 * (E1_F + 2));
+    int c = rem / (E1_F + 2), fp = rem - c * (E1_F + 2);
+    int k = k0 - 2 + fl;
+    float v = 0.f;
+    if (k >= 0 && k < nk && fp >= 1 && fp <= E1_F) {
+      int t = r + k * dil;
+      v = __ldg(xb + (long long)t * FRAME16 + c * E1_F + (fp - 1));
+    }
+    xs[fl][c][fp] = v;
+  }
+  for (int i = tid; i < GT_FL * 16; i += GT_THREADS) {
+    hs[i / 16][i % 16][0] = 0.f;
+    hs[i / 16][i % 16][E1_F + 1] = 0.f;
+  }
+  __syncthreads();
+
+  // phase 1: SFE(k=3) + point_conv1 (24->16) + PReLU.  Frames before the chunk start are the
+  // causal zero padding of the depthwise conv's INPUT (:314-318), i.e. exact zeros.
+  if (tid < GT_FL * E1_F) {
+    int fl = tid / E1_F, f = tid - fl * E1_F;
+    int k = k0 - 2 + fl;
+    float acc[16];
+    if (k >= 0 && k < nk) {
+      float in[24];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) in[c * 3 + s] = xs[fl][c][f + s];
+#pragma unroll
+      for (int o = 0; o < 16; ++o) {
+        float a = w.b1[o];
+#pragma unroll
+        for (int i = 0; i < 24; ++i) a = fmaf(w.w1[o][i], in[i], a);
+        acc[o] = adn_prelu(a, w.a1);
+      }
+    } else {
+#pragma unroll
+      for (int o = 0; o < 16; ++o) acc[o] = 0.f;
+    }
+#pragma unroll
+    for (int o = 0; o < 16; ++o) hs[fl][o][f + 1] = acc[o];
+  }
+  __syncthreads();
+
+  // phase 2: depthwise (3,3) dilated causal conv + PReLU + point_conv2 (16->8)
+  if (tid < GT_KT * E1_F) {
+    int kl = tid / E1_F, f = tid - kl * E1_F;
+    int k = k0 + kl;
+    if (k < nk) {
+      float acc[8];
+#pragma unroll
+      for (int o = 0; o < 8; ++o) acc[o] = w.b2[o];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        float d = w.bd[c];
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt)
+#pragma unroll
+          for (int kf = 0; kf < 3; ++kf) d = fmaf(w.wd[c][kt][kf], hs[kl + kt][c][f + kf], d);
+        d = adn_prelu(d, w.ad);
+#pragma unroll
+        for (int o = 0; o < 8; ++o) acc[o] = fmaf(w.w2[o][c], d, acc[o]);
+      }
+      int t = r + k * dil;
+      float* ho = h1 + ((long long)b * T + t) * (8 * E1_F);
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        ho[o * E1_F + f] = acc[o];
+        h1s[kl][o][f] = acc[o];
+      }
+    }
+  }
+  __syncthreads();
+
+  // phase 3: z_t[c] = mean_f h1^2 (TRA input, :154)
+  if (tid < GT_KT * 8) {
+    int kl = tid >> 3, c = tid & 7;
+    int k = k0 + kl;
+    if (k < nk) {
+      float s = 0.f;
+#pragma unroll
+      for (int f = 0; f < E1_F; ++f) s = fmaf(h1s[kl][c][f], h1s[kl][c][f], s);
+      int t = r + k * dil;
+      zt[((long long)b * T + t) * 8 + c] = s / (float)E1_F;
+    }
+  }
+}
+
+// =================================================================================
+// GRU cell helpers (PyTorch gate order r,z,n; n = tanh(i_n + r*(W_hn h + b_hn))).
+// =================================================================================
+template <int I, int H>
+struct GruLane {       // one lane owns hidden unit j of one GRU
+  float wi[3][I];
+  float wh[3][H];
+  float bi[3], bh[3];
+  __device__ void load(const GruPtrs& p, int j) {
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+#pragma unroll
+      for (int i = 0; i < I; ++i) wi[g][i] = __ldg(p.w_ih + (g * H + j) * I + i);
+#pragma unroll
+      for (int k = 0; k < H; ++k) wh[g][k] = __ldg(p.w_hh + (g * H + j) * H + k);
+      bi[g] = __ldg(p.b_ih + g * H + j);
+      bh[g] = __ldg(p.b_hh + g * H + j);
+    }
+  }
+  // x: inputs, hv: all H hidden values of this GRU (previous step), hself: own previous h
+  __device__ __forceinline__ float step(const float (&x)[I], const float (&hv)[H], float hself) const {
+    float gi[3], gh[3];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      float a = bi[g];
+#pragma unroll
+      for (int i = 0; i < I; ++i) a = fmaf(wi[g][i], x[i], a);
+      gi[g] = a;
+      float c = bh[g];
+#pragma unroll
+      for (int k = 0; k < H; ++k) c = fmaf(wh[g][k], hv[k], c);
+      gh[g] = c;
+    }
+    float rg = adn_sigmoid(gi[0] + gh[0]);
+    float zg = adn_sigmoid(gi[1] + gh[1]);
+    float ng = tanhf(gi[2] + rg * gh[2]);
+    return (1.0f - zg) * ng + zg * hself;
+  }
+};
+
+// =================================================================================
+// tra_apply: TRA attention GRU over T (16 lanes of warp 0), then the whole CTA applies the
+// gate, interleaves with the bypass half (:324) and optionally adds the next decoder skip.
+// =================================================================================
+constexpr int TRA_THREADS = 256;
+
+__global__ void __launch_bounds__(TRA_THREADS)
+tra_apply_kernel(const TraW w, const float* __restrict__ zt, const float* __restrict__ h1,
+                 const float* __restrict__ xin, const float* __restrict__ skip,
+                 float* __restrict__ out, int T) {
+  extern __shared__ float at_s[];     // (T, 8)
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* z = zt + (long long)b * T * 8;
+
+  if (tid < 32) {
+    const int j = tid & 15;
+    GruLane<8, 16> cell;
+    cell.load(w.gru, j);
+    float fw[16], fb = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) fw[k] = __ldg(w.fc_w + (j & 7) * 16 + k);
+    fb = __ldg(w.fc_b + (j & 7));
+    float h = 0.f;
+    float hv[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) hv[k] = 0.f;
+    float4 xa = __ldg(reinterpret_cast<const float4*>(z));
+    float4 xb4 = __ldg(reinterpret_cast<const float4*>(z) + 1);
+    for (int t = 0; t < T; ++t) {
+      float x[8] = {xa.x, xa.y, xa.z, xa.w, xb4.x, xb4.y, xb4.z, xb4.w};
+      if (t + 1 < T) {
+        xa = __ldg(reinterpret_cast<const float4*>(z + (t + 1) * 8));
+        xb4 = __ldg(reinterpret_cast<const float4*>(z + (t + 1) * 8) + 1);
+      }
+      h = cell.step(x, hv, h);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) hv[k] = __shfl_sync(0xffffffffu, h, k, 16);
+      float a = fb;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) a = fmaf(fw[k], hv[k], a);
+      if (tid < 8) at_s[t * 8 + tid] = adn_sigmoid(a);
+    }
+  }
+  __syncthreads();
+
+  const long long base = (long long)b * T * FRAME16;
+  const float* hb = h1 + (long long)b * T * (8 * E1_F);
+  const int total = T * FRAME16;
+  for (int i = tid; i < total; i += TRA_THREADS) {
+    int t = i / FRAME16, rem = i - t * FRAME16;
+    int ch = rem / E1_F, f = rem - ch * E1_F;
+    int c = ch >> 1;
+    float v;
+    if (ch & 1) v = __ldg(xin + base + (long long)t * FRAME16 + (8 + c) * E1_F + f);
+    else v = __ldg(hb + (long long)t * (8 * E1_F) + c * E1_F + f) * at_s[t * 8 + c];
+    if (skip) v += __ldg(skip + base + i);
+    out[base + i] = v;
+  }
+}
+
+// =================================================================================
+// Per-frame LayerNorm((33,16), eps=1e-8) helpers on a half-warp (16 lanes).
+// =================================================================================
+__device__ __forceinline__ float half_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// z (smem, 528 values, any fixed layout matching lnw/lnb) -> mean / rstd over the frame
+__device__ __forceinline__ void frame_stats(const float* z, int hl, float& mean, float& rstd) {
+  float s = 0.f;
+  for (int i = hl; i < FRAME16; i += 16) s += z[i];
+  mean = half_sum(s) * (1.0f / FRAME16);
+  float q = 0.f;
+  for (int i = hl; i < FRAME16; i += 16) {
+    float d = z[i] - mean;
+    q = fmaf(d, d, q);
+  }
+  float var = half_sum(q) * (1.0f / FRAME16);
+  rstd = 1.0f / sqrtf(var + 1e-8f);
+}
+
+// =================================================================================
+// dp_intra: x = a (+ LN(zprev)) ; bi-GRU over F in 2 groups ; FC ; LN ; out = x + LN(..)
+// One half-warp per frame: lane = (group, direction, hidden unit) = 2*2*4.
+// =================================================================================
+constexpr int DI_FRAMES = 4;     // frames per CTA (2 warps)
+
+__global__ void __launch_bounds__(DI_FRAMES * 16)
+dp_intra_kernel(const DpW w, const float* __restrict__ a, const float* __restrict__ zprev,
+                const float* __restrict__ pln_w, const float* __restrict__ pln_b,
+                float* __restrict__ out, int nframes) {
+  __shared__ float xs[DI_FRAMES][FRAME16];     // [c][f]
+  __shared__ float ys[DI_FRAMES][E1_F * 16];   // [f][16]  GRU outputs
+  __shared__ float zs[DI_FRAMES][FRAME16];     // [c][f]   FC outputs
+
+  const int lane = threadIdx.x & 31, hl = lane & 15;
+  const int fi = (threadIdx.x >> 5) * 2 + (lane >> 4);
+  const long long fg = (long long)blockIdx.x * DI_FRAMES + fi;
+  const bool live = fg < nframes;
+  const long long off = (live ? fg : 0) * FRAME16;
+  float* x = xs[fi];
+  float* y = ys[fi];
+  float* z = zs[fi];
+
+  if (zprev) {
+    for (int i = hl; i < FRAME16; i += 16) z[i] = __ldg(zprev + off + i);
+    __syncwarp();
+    float mean, rstd;
+    frame_stats(z, hl, mean, rstd);
+    for (int i = hl; i < FRAME16; i += 16)
+      x[i] = __ldg(a + off + i) + ((z[i] - mean) * rstd * __ldg(pln_w + i) + __ldg(pln_b + i));
+  } else {
+    for (int i = hl; i < FRAME16; i += 16) x[i] = __ldg(a + off + i);
+  }
+  __syncwarp();
+
+  {
+    const int g = hl >> 3, dir = (hl >> 2) & 1, j = hl & 3;
+    GruLane<8, 4> cell;
+    cell.load(w.intra[g][dir], j);
+    float h = 0.f;
+    float hv[4] = {0.f, 0.f, 0.f, 0.f};
+    const int src0 = lane & ~3;
+    for (int s = 0; s < E1_F; ++s) {
+      int f = dir ? (E1_F - 1 - s) : s;
+      float xv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xv[i] = x[(g * 8 + i) * E1_F + f];
+      h = cell.step(xv, hv, h);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) hv[k] = __shfl_sync(0xffffffffu, h, src0 + k);
+      y[f * 16 + hl] = h;     // channel order [g][fwd 4 | bwd 4] == torch.cat in GRNN.forward
+    }
+  }
+  __syncwarp();
+
+  {
+    const int o = hl;
+    float fw[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) fw[k] = __ldg(w.intra_fc_w + o * 16 + k);
+    const float fb = __ldg(w.intra_fc_b + o);
+    for (int f = 0; f < E1_F; ++f) {
+      float acc = fb;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc = fmaf(fw[k], y[f * 16 + k], acc);
+      z[o * E1_F + f] = acc;
+    }
+  }
+  __syncwarp();
+  float mean, rstd;
+  frame_stats(z, hl, mean, rstd);
+  if (live) {
+    for (int i = hl; i < FRAME16; i += 16)
+      out[off + i] = x[i] + ((z[i] - mean) * rstd * __ldg(w.intra_ln_w + i) + __ldg(w.intra_ln_b + i));
+  }
+}
+
+// =================================================================================
+// dp_inter: uni-directional grouped GRU over T for every (chunk, f), then FC.  One CTA per
+// chunk; thread = (f, group, hidden unit); frames stream through a double-buffered smem
+// stage so global traffic is one coalesced 2112-byte frame in and out per step.
+// =================================================================================
+constexpr int DX_THREADS = 544;   // 33*16 = 528 workers, rounded to warps
+
+__global__ void __launch_bounds__(DX_THREADS)
+dp_inter_kernel(const DpW w, const float* __restrict__ xin, float* __restrict__ zout, int T) {
+  __shared__ float xbuf[2][FRAME16];
+  __shared__ float zbuf[2][FRAME16];
+  const int tid = threadIdx.x, b = blockIdx.x;
+  const bool worker = tid < FRAME16;
+  const int f = worker ? (tid >> 4) : 0;
+  const int hl = tid & 15, g = hl >> 3, j = hl & 7;
+  const float* xb = xin + (long long)b * T * FRAME16;
+  float* zb = zout + (long long)b * T * FRAME16;
+
+  GruLane<8, 8> cell;
+  cell.load(w.inter[g], j);
+  float fw[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) fw[k] = __ldg(w.inter_fc_w + hl * 16 + k);
+  const float fb = __ldg(w.inter_fc_b + hl);
+
+  if (worker) xbuf[0][tid] = __ldg(xb + tid);
+  __syncthreads();
+
+  float h = 0.f;
+  float hv[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) hv[k] = 0.f;
+  const int half_base = (threadIdx.x & 31) & 16;
+
+  for (int t = 0; t < T; ++t) {
+    const int cur = t & 1;
+    float nxt = 0.f;
+    if (worker && t + 1 < T) nxt = __ldg(xb + (long long)(t + 1) * FRAME16 + tid);
+    float xv[8], hg[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      xv[i] = xbuf[cur][(g * 8 + i) * E1_F + f];
+      hg[i] = g ? hv[8 + i] : hv[i];
+    }
+    h = cell.step(xv, hg, h);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) hv[k] = __shfl_sync(0xffffffffu, h, half_base + k);
+    float acc = fb;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc = fmaf(fw[k], hv[k], acc);
+    if (worker) {
+      zbuf[cur][hl * E1_F + f] = acc;
+      xbuf[cur ^ 1][tid] = nxt;
+    }
+    __syncthreads();
+    if (worker) zb[(long long)t * FRAME16 + tid] = zbuf[cur][tid];
+  }
+}
+
+// =================================================================================
+// ln_res: out = a + LN(z) (+ skip).  Half-warp per frame.
+// =================================================================================
+__global__ void __launch_bounds__(128)
+ln_res_kernel(const float* __restrict__ a, const float* __restrict__ zin, const float* __restrict__ ln_w,
+              const float* __restrict__ ln_b, const float* __restrict__ skip, float* __restrict__ out,
+              int nframes) {
+  __shared__ float zs[8][FRAME16];
+  const int lane = threadIdx.x & 31, hl = lane & 15;
+  const int fi = (threadIdx.x >> 5) * 2 + (lane >> 4);
+  const long long fg = (long long)blockIdx.x * 8 + fi;
+  const bool live = fg < nframes;
+  const long long off = (live ? fg : 0) * FRAME16;
+  float* z = zs[fi];
+  for (int i = hl; i < FRAME16; i += 16) z[i] = __ldg(zin + off + i);
+  __syncwarp();
+  float mean, rstd;
+  frame_stats(z, hl, mean, rstd);
+  if (live) {
+    for (int i = hl; i < FRAME16; i += 16) {
+      float v = __ldg(a + off + i) + ((z[i] - mean) * rstd * __ldg(ln_w + i) + __ldg(ln_b + i));
+      if (skip) v += __ldg(skip + off + i);
+      out[off + i] = v;
+    }
+  }
+}
+
+// =================================================================================
+// dec_tail: de_convs.3 (ConvT 16->16,(1,5),s2,g2)+PReLU, +e0, de_convs.4 (ConvT 16->2)+tanh,
+// ERB.bs, complex ratio mask on the noisy spectrum -> enhanced spectrum frame.
+// Transposed conv (stride 2, pad 2): out[g] += in[i]*w[k] with g = 2i + k - 2.
+// =================================================================================
+// Transposed-conv taps with compile-time group / parity so every weight is a constant-bank
+// operand.  Even outputs take kernel taps 0,2,4, odd outputs taps 1,3.
+template <int GRP, int PAR>
+__device__ __forceinline__ void deconv3_taps(const DecTailW& w, const float (*x)[E1_F + 2], int g,
+                                             float (&acc)[8]) {
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = w.b3[GRP * 8 + o];
+#pragma unroll
+  for (int k = PAR; k < 5; k += 2) {
+    int i = (g + 2 - k) >> 1;      // -1..33 -> column i+1 (0 and 34 are zeros)
+#pragma unroll
+    for (int ci = 0; ci < 8; ++ci) {
+      float v = x[GRP * 8 + ci][i + 1];
+#pragma unroll
+      for (int o = 0; o < 8; ++o) acc[o] = fmaf(w.w3[GRP * 8 + ci][o][k], v, acc[o]);
+    }
+  }
+}
+
+template <int PAR>
+__device__ __forceinline__ void deconv4_taps(const DecTailW& w, const float (*y)[E0_F + 2], int g,
+                                             float (&a)[2]) {
+  a[0] = w.b4[0];
+  a[1] = w.b4[1];
+#pragma unroll
+  for (int k = PAR; k < 5; k += 2) {
+    int i = (g + 2 - k) >> 1;      // -1..65 -> column i+1 (0 and 66 are zeros)
+#pragma unroll
+    for (int ci = 0; ci < 16; ++ci) {
+      float v = y[ci][i + 1];
+      a[0] = fmaf(w.w4[ci][0][k], v, a[0]);
+      a[1] = fmaf(w.w4[ci][1][k], v, a[1]);
+    }
+  }
+}
+
+constexpr int DT_FR = 4;
+constexpr int DT_THREADS = 288;
+
+__global__ void __launch_bounds__(DT_THREADS)
+dec_tail_kernel(const __grid_constant__ DecTailW w, const ErbW erb, const float* __restrict__ xin,
+                const float* __restrict__ e0, const float* __restrict__ spec, float* __restrict__ enh,
+                int T, int nframes, int pad_frames) {
+  __shared__ float xs[DT_FR][16][E1_F + 2];      // zero column each side
+  __shared__ float ys[DT_FR][16][E0_F + 2];      // d3 + e0, zero column each side
+  __shared__ float ms[DT_FR][2][ERB_F];
+  __shared__ float mf[DT_FR][2][FB];
+
+  const int tid = threadIdx.x;
+  const long long f0 = (long long)blockIdx.x * DT_FR;
+
+  for (int i = tid; i < DT_FR * 16 * (E1_F + 2); i += DT_THREADS) {
+    int fr = i / (16 * (E1_F + 2)), rem = i - fr * (16 * (E1_F + 2));
+    int c = rem / (E1_F + 2), fp = rem - c * (E1_F + 2);
+    long long fg = f0 + fr;
+    float v = 0.f;
+    if (fg < nframes && fp >= 1 && fp <= E1_F) v = __ldg(xin + fg * FRAME16 + c * E1_F + fp - 1);
+    xs[fr][c][fp] = v;
+  }
+  for (int i = tid; i < DT_FR * 16; i += DT_THREADS) {
+    ys[i / 16][i % 16][0] = 0.f;
+    ys[i / 16][i % 16][E0_F + 1] = 0.f;
+  }
+  __syncthreads();
+
+  // de_convs.3: item = (frame, group, g in 0..64); 8 outputs per item
+  for (int it = tid; it < DT_FR * 2 * E0_F; it += DT_THREADS) {
+    int fr = it / (2 * E0_F), rem = it - fr * (2 * E0_F);
+    int grp = rem / E0_F, g = rem - grp * E0_F;
+    long long fg = f0 + fr;
+    float acc[8];
+    if (grp == 0) {
+      if (g & 1) deconv3_taps<0, 1>(w, xs[fr], g, acc);
+      else deconv3_taps<0, 0>(w, xs[fr], g, acc);
+    } else {
+      if (g & 1) deconv3_taps<1, 1>(w, xs[fr], g, acc);
+      else deconv3_taps<1, 0>(w, xs[fr], g, acc);
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      float e0v = (fg < nframes) ? __ldg(e0 + fg * FRAME_E0 + (grp * 8 + o) * E0_F + g) : 0.f;
+      ys[fr][grp * 8 + o][g + 1] = adn_prelu(acc[o], w.a3) + e0v;
+    }
+  }
+  __syncthreads();
+
+  // de_convs.4 + tanh: item = (frame, g in 0..128), 2 outputs
+  for (int it = tid; it < DT_FR * ERB_F; it += DT_THREADS) {
+    int fr = it / ERB_F, g = it - fr * ERB_F;
+    float a[2];
+    if (g & 1) deconv4_taps<1>(w, ys[fr], g, a);
+    else deconv4_taps<0>(w, ys[fr], g, a);
+    ms[fr][0][g] = tanhf(a[0]);
+    ms[fr][1][g] = tanhf(a[1]);
+  }
+  __syncthreads();
+
+  // ERB.bs: 65 low bins pass through, 64 bands -> 192 high bins
+  for (int it = tid; it < DT_FR * 2 * FB; it += DT_THREADS) {
+    int fr = it / (2 * FB), rem = it - fr * (2 * FB);
+    int c = rem / FB, f = rem - c * FB;
+    float v;
+    if (f < 65) {
+      v = ms[fr][c][f];
+    } else {
+      int i = f - 65;
+      int lo = (int)__ldg(erb.bs_lo + i), hi = (int)__ldg(erb.bs_hi + i);
+      v = 0.f;
+      for (int j = lo; j < hi; ++j) v = fmaf(ms[fr][c][65 + j], __ldg(erb.bs + j * 192 + i), v);
+    }
+    mf[fr][c][f] = v;
+  }
+  __syncthreads();
+
+  // complex ratio mask (:585-590) -> enhanced spectrum frame (inside the zero-framed buffer)
+  for (int it = tid; it < DT_FR * FB; it += DT_THREADS) {
+    int fr = it / FB, f = it - fr * FB;
+    long long fg = f0 + fr;
+    if (fg >= nframes) continue;
+    long long b = fg / T, t = fg - b * T;
+    float re = __ldg(spec + fg * SPEC_LD + f), im = __ldg(spec + fg * SPEC_LD + FB + f);
+    float m0 = mf[fr][0][f], m1 = mf[fr][1][f];
+    float* o = enh + (b * (T + 2 * pad_frames) + pad_frames + t) * SPEC_LD;
+    o[f] = re * m0 - im * m1;
+    o[FB + f] = im * m0 + re * m1;
+  }
+}
+
+// =================================================================================
+// launcher
+// =================================================================================
+#define TICK(name) do { ++n; if (tick) tick(tick_ctx, name); if (stop_after > 0 && n >= stop_after) return n; } while (0)
+
+int launch_backbone(const Weights& w, const Buffers& buf, const Dims& d, int enh_pad_frames,
+                    cudaStream_t st, TickFn tick, void* tick_ctx, int stop_after) {
+  int n = 0;
+  const int B = d.B, T = d.T;
+  const int nframes = B * T;
+
+  enc_front_kernel<<<(nframes + EF_FR - 1) / EF_FR, EF_THREADS, 0, st>>>(w.enc_front, w.erb, buf.spec,
+                                                                       buf.e0, buf.e[1], nframes);
+  TICK("enc_front");
+
+  const int dil_enc[3] = {1, 2, 5};
+  const size_t tra_smem = (size_t)T * 8 * sizeof(float);
+  for (int i = 0; i < 3; ++i) {
+    int dl = dil_enc[i];
+    int nkmax = (T + dl - 1) / dl;
+    dim3 grid((nkmax + GT_KT - 1) / GT_KT, dl, B);
+    gt_main_kernel<<<grid, GT_THREADS, 0, st>>>(w.enc_gt[i], buf.e[i + 1], buf.h1, buf.zt, T, dl);
+    TICK("gt_main");
+    tra_apply_kernel<<<B, TRA_THREADS, tra_smem, st>>>(w.enc_tra[i], buf.zt, buf.h1, buf.e[i + 1], nullptr,
+                                                      buf.e[i + 2], T);
+    TICK("tra_apply");
+  }
+
+  // DPGRNN x2: x = e4
+  dp_intra_kernel<<<(nframes + DI_FRAMES - 1) / DI_FRAMES, DI_FRAMES * 16, 0, st>>>(
+      w.dp[0], buf.e[4], nullptr, nullptr, nullptr, buf.xa, nframes);
+  TICK("dp_intra");
+  dp_inter_kernel<<<B, DX_THREADS, 0, st>>>(w.dp[0], buf.xa, buf.inter, T);
+  TICK("dp_inter");
+  dp_intra_kernel<<<(nframes + DI_FRAMES - 1) / DI_FRAMES, DI_FRAMES * 16, 0, st>>>(
+      w.dp[1], buf.xa, buf.inter, w.dp[0].inter_ln_w, w.dp[0].inter_ln_b, buf.xb, nframes);
+  TICK("dp_intra");
+  dp_inter_kernel<<<B, DX_THREADS, 0, st>>>(w.dp[1], buf.xb, buf.inter, T);
+  TICK("dp_inter");
+  // decoder input 0 = dp2 output + e4
+  ln_res_kernel<<<(nframes + 7) / 8, 128, 0, st>>>(buf.xb, buf.inter, w.dp[1].inter_ln_w, w.dp[1].inter_ln_b,
+                                                   buf.e[4], buf.xa, nframes);
+  TICK("ln_res");
+
+  const int dil_dec[3] = {5, 2, 1};
+  float* cur = buf.xa;
+  float* nxt = buf.xb;
+  for (int i = 0; i < 3; ++i) {
+    int dl = dil_dec[i];
+    int nkmax = (T + dl - 1) / dl;
+    dim3 grid((nkmax + GT_KT - 1) / GT_KT, dl, B);
+    gt_main_kernel<<<grid, GT_THREADS, 0, st>>>(w.dec_gt[i], cur, buf.h1, buf.zt, T, dl);
+    TICK("gt_main");
+    // next stage input = this block's output + encoder skip (e3, e2, e1)
+    tra_apply_kernel<<<B, TRA_THREADS, tra_smem, st>>>(w.dec_tra[i], buf.zt, buf.h1, cur, buf.e[3 - i], nxt, T);
+    TICK("tra_apply");
+    float* tmp = cur; cur = nxt; nxt = tmp;
+  }
+  dec_tail_kernel<<<(nframes + DT_FR - 1) / DT_FR, DT_THREADS, 0, st>>>(w.dec_tail, w.erb, cur, buf.e0, buf.spec,
+                                                                      buf.enh, T, nframes, enh_pad_frames);
+  TICK("dec_tail");
+  return n;
+}
+
+}  // namespace gtcrn

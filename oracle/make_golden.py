@@ -1,0 +1,130 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by EXECUTING THE REFERENCE
+(/root/reference, build container only) on seeded inputs / weights.
+
+    python oracle/make_golden.py
+
+The fixtures travel to the GPU box; /root/reference does not.  Every fixture stores the
+inputs, the reference outputs and the seeds, so the `-m gpu` tests can compare the CUDA
+path with the reference itself, not only with the restated oracle.
+"""
+from __future__ import annotations
+
+import hashlib
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE))
+
+import gtcrn_oracle as go           # noqa: E402
+import ref_loader                   # noqa: E402
+from stft_oracle import SPECS       # noqa: E402
+
+GOLDEN = HERE.parent / "tests" / "golden"
+
+# (oracle spec name, reference folder, stft model_type, istft model_type, istft static kwarg, L)
+STFT_CASES = [
+    ("gtcrn", "GTCRN", "stft_B", "istft_B", {"static_norm": True}, 4096),
+    ("zipenhancer", "ZipEnhancer", "stft_B", "istft_B", {"static_norm": True}, 3200),
+    ("mossformer2_se_48k", "MossFormer2_SE_48K", "stft_B", "istft_B", {"static_frames": True}, 9600),
+    ("mel_band_roformer", "Mel_Band_Roformer/Stereo", "stft_B", "istft_B", {"static_frames": True}, 8820),
+    ("mossformergan_se_16k", "MossFormerGAN_SE_16K", "stft_C", "istft_C", {"precompute_window_sum": True}, 3200),
+]
+
+
+def synth_audio(n: int, seed: int = 1234, batch: int = 1) -> torch.Tensor:
+    """Band-limited speech-like noise + sinusoids, peak 0.5 FS."""
+    g = torch.Generator().manual_seed(seed)
+    x = 0.1 * torch.randn(batch, 1, n, generator=g)
+    k = torch.hann_window(33, periodic=False)
+    k = (k / k.sum()).reshape(1, 1, -1)
+    x = torch.nn.functional.conv1d(x, k, padding=16)
+    t = torch.arange(n, dtype=torch.float32) / 16000.0
+    for i, f0 in enumerate((220.0, 587.0, 1310.0)):
+        amp = 0.3 / (i + 1)
+        ph = torch.rand(batch, 1, 1, generator=g) * 6.2831853
+        x = x + amp * torch.sin(2 * torch.pi * f0 * t.reshape(1, 1, -1) + ph)
+    x = x / x.abs().amax(dim=-1, keepdim=True) * 0.5
+    return x.float().contiguous()
+
+
+def sd_digest(sd: dict) -> str:
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(sd[k].detach().cpu().numpy().tobytes())
+    return h.hexdigest()
+
+
+def ref_stft_pair(spec_name: str, folder: str, st_type: str, ist_type: str, static_kw: dict, length: int):
+    spec = SPECS[spec_name]
+    mod = ref_loader.load_stft_module(folder)
+    wt = {"hamming_sym": "hamming"}.get(spec.window_type, spec.window_type)
+    t = spec.n_frames(length)
+    stft = mod.STFT_Process(model_type=st_type, n_fft=spec.nfft, hop_len=spec.hop, win_length=spec.win_length,
+                            max_frames=0, window_type=wt, center_pad=spec.center, pad_mode=spec.pad_mode).eval()
+    istft = mod.STFT_Process(model_type=ist_type, n_fft=spec.nfft, hop_len=spec.hop, win_length=spec.win_length,
+                             max_frames=t, window_type=wt, center_pad=spec.center, pad_mode=spec.pad_mode,
+                             **static_kw).eval()
+    return stft, istft
+
+
+def ref_stft_forward(stft, x):
+    out = stft(x)
+    if isinstance(out, (tuple, list)):
+        out = torch.cat(out, dim=1)
+    return out
+
+
+def ref_istft_forward(istft, s, fbins):
+    if istft.model_type == "istft_C":
+        return istft(s)
+    return istft(s[:, :fbins], s[:, fbins:])
+
+
+def main():
+    assert ref_loader.reference_available(), "/root/reference is required to generate fixtures"
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    torch.manual_seed(1234)
+    with torch.inference_mode():
+        # ---- STFT / ISTFT, all in-scope variants
+        for name, folder, st, ist, kw, L in STFT_CASES:
+            spec = SPECS[name]
+            stft, istft = ref_stft_pair(name, folder, st, ist, kw, L)
+            g = torch.Generator().manual_seed(1234)
+            x = torch.rand(2, 1, L, generator=g) * 2 - 1          # uniform[-1,1] like SURVEY App. B
+            s = ref_stft_forward(stft, x)
+            # a spectrum that is NOT a valid STFT exercises the ISTFT alone
+            s2 = s * (0.5 + torch.rand(s.shape, generator=g))
+            y = ref_istft_forward(istft, s2, spec.fbins)
+            np.savez_compressed(GOLDEN / f"stft_{name}.npz", x=x.numpy(), spec=s.numpy(), spec_in=s2.numpy(),
+                                y=y.numpy(), length=L)
+            print(f"stft_{name}: x{tuple(x.shape)} -> spec{tuple(s.shape)} -> y{tuple(y.shape)}")
+
+        # ---- GTCRN end to end, F32 I/O and INT16 I/O (SURVEY.md 8a a1-a5,a10-a12)
+        sd = go.random_state_dict(0)
+        digest = sd_digest(sd)
+        x = synth_audio(16000, 1234, batch=3)
+        x[2] = 0.0                                               # all-zero chunk edge case
+        for dt in ("F32", "INT16"):
+            _, build = ref_loader.load_gtcrn(16000, dt)
+            w = build(sd)
+            xin = x if dt == "F32" else torch.round(x * 32767.0).to(torch.int16)
+            y = torch.cat([w(xin[i:i + 1]) for i in range(xin.shape[0])], dim=0)
+            np.savez_compressed(GOLDEN / f"gtcrn_{dt.lower()}_L16000.npz", x=xin.numpy(), y=y.numpy(),
+                                seed=0, sd_digest=digest)
+            print(f"gtcrn {dt}: {tuple(xin.shape)} -> {tuple(y.shape)}")
+        # second chunk length (different T, exercises partial tiles): 2 s like the reference default
+        _, build = ref_loader.load_gtcrn(8000, "F32")
+        w = build(sd)
+        x8 = synth_audio(8000, 99, batch=2)
+        y8 = torch.cat([w(x8[i:i + 1]) for i in range(2)], dim=0)
+        np.savez_compressed(GOLDEN / "gtcrn_f32_L8000.npz", x=x8.numpy(), y=y8.numpy(), seed=0, sd_digest=digest)
+        print(f"gtcrn F32 L8000: {tuple(x8.shape)} -> {tuple(y8.shape)}")
+
+
+if __name__ == "__main__":
+    main()

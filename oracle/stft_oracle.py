@@ -54,7 +54,7 @@ SPECS = {
     # SURVEY.md A.1
     "gtcrn": StftSpec(512, 512, 256, "hann_sqrt", True, "reflect", "divide"),
     "zipenhancer": StftSpec(400, 400, 100, "hann", True, "reflect", "multiply"),
-    "mossformer2_se_48k": StftSpec(1920, 1920, 384, "hamming_sym", False, "reflect", "divide"),
+    "mossformer2_se_48k": StftSpec(1920, 1920, 384, "hamming_sym", False, "constant", "divide"),
     "mel_band_roformer": StftSpec(2048, 2048, 441, "hann", True, "reflect", "divide"),
     "mossformergan_se_16k": StftSpec(400, 400, 100, "hamming", True, "reflect", "divide"),
 }

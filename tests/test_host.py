@@ -1,0 +1,162 @@
+"""CPU-side tests: C-ABI library loads and exports every symbol include/adn.h declares (no
+compute calls without a GPU), host logic (model file, metadata, chunk planner, weight
+packing) and the loud failure when no GPU is usable."""
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import gtcrn_oracle as go
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol(libadn):
+    header = (ROOT / "include" / "adn.h").read_text()
+    declared = sorted(set(re.findall(r"\b(adn_[a-z_0-9]+)\s*\(", header)))
+    from adn import _lib
+
+    assert sorted(_lib.EXPORTED) == declared, (sorted(_lib.EXPORTED), declared)
+    for name in declared:
+        assert hasattr(libadn, name), f"libadn.so does not export {name}"
+    assert b"sm_100a" in libadn.adn_version()
+
+
+def test_library_is_sm100a_only(libadn):
+    import subprocess
+
+    from adn import build
+
+    out = subprocess.run(["cuobjdump", "--list-elf", str(build.LIB_PATH)], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_gpu_fails_loudly(libadn):
+    from adn import _lib, export
+
+    with pytest.raises(_lib.AdnError, match="no CPU fallback"):
+        export.gtcrn_model(go.random_state_dict(0), 16000)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from adn import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setenv("ADN_LIB", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        _lib.lib()
+
+
+def test_modelfile_round_trip(tmp_path):
+    from adn import export, gtcrn_params, modelfile
+
+    sd = go.random_state_dict(0)
+    md = export.export_gtcrn(sd, tmp_path / "m.adn", 16000, "INT16", "F32")
+    md2, index, payload = modelfile.load(tmp_path / "m.adn")
+    assert md2 == md and md2["model_family"] == "gtcrn" and md2["output_audio_length"] == "15872"
+    blob = gtcrn_params.pack(sd, 16000)
+    assert [t["name"] for t in index] == list(blob)
+    for t in index:
+        assert t["offset"] % 4 == 0
+        a = payload[t["offset"]: t["offset"] + t["count"]]
+        assert np.array_equal(a, blob[t["name"]].reshape(-1))
+    with pytest.raises(ValueError):
+        (tmp_path / "bad.adn").write_bytes(b"ONNX....")
+        modelfile.load(tmp_path / "bad.adn")
+
+
+def test_weight_packing_matches_oracle_fold():
+    """BN fold + deconv->conv rewrite: the packed GTConv block reproduces the oracle's
+    (reference-order) block on random input, computed with plain torch ops."""
+    import torch.nn.functional as F
+
+    from adn import gtcrn_params
+
+    sd = go.random_state_dict(4)
+    blob = gtcrn_params.pack(sd, 16000)
+    for name, prefix, dil, deconv in (("enc_gt.1", "encoder.en_convs.3", 2, False),
+                                      ("dec_gt.0", "decoder.de_convs.0", 5, True)):
+        p = torch.from_numpy(blob[name])
+        w1, b1 = p[:384].reshape(16, 24), p[384:400]
+        wd, bd = p[400:544].reshape(16, 3, 3), p[544:560]
+        w2, b2 = p[560:688].reshape(8, 16), p[688:696]
+        a1, ad = p[696], p[697]
+        g = torch.Generator().manual_seed(0)
+        x = torch.randn(1, 16, 20, 33, generator=g)
+        dbg = {}
+        go._gtconv(sd, prefix, x, dil, deconv, dbg)
+        ref = dbg[f"{prefix}.h1"]
+        s = go._sfe(x[:, :8])
+        h = F.prelu(F.conv2d(s, w1.reshape(16, 24, 1, 1), b1), a1.reshape(1))
+        h = F.pad(h, [0, 0, 2 * dil, 0])
+        h = F.prelu(F.conv2d(h, wd.reshape(16, 1, 3, 3), bd, padding=(0, 1), dilation=(dil, 1), groups=16),
+                    ad.reshape(1))
+        h = F.conv2d(h, w2.reshape(8, 16, 1, 1), b2)
+        assert (h - ref).abs().max() < 1e-5, name
+    # ERB nonzero ranges cover every nonzero of the dense matrices
+    bm = blob["erb.bm"]
+    for j in range(64):
+        nz = np.nonzero(bm[:, j])[0]
+        assert nz.min() >= blob["erb.bm_lo"][j] and nz.max() < blob["erb.bm_hi"][j]
+    bs = blob["erb.bs"]
+    for i in range(192):
+        nz = np.nonzero(bs[:, i])[0]
+        assert nz.min() >= blob["erb.bs_lo"][i] and nz.max() < blob["erb.bs_hi"][i]
+
+
+def test_metadata_reader_matches_reference_contract():
+    from adn import gtcrn_params, metadata
+
+    md = gtcrn_params.metadata(16000)
+    r = metadata.MetadataReader(md)
+    for k in metadata.REQUIRED_AUDIO_METADATA_KEYS:
+        assert r.string(k, required=True)
+    cfg = metadata.runtime_config_from_metadata(r)
+    assert len(cfg) == 22      # the reference's 22 typed constants (audio_onnx_metadata.py:359-385)
+    assert cfg["FOLD_WINDOW_LENGTH"] == 24064 and cfg["BATCH_FOLD_INFERENCE"] is False
+    assert cfg["PAD_HEAD"] == 0 and cfg["OUTPUT_SOURCES"] == 1 and cfg["SCALE_FACTOR"] == 1.0
+    bad = dict(md)
+    del bad["in_sample_rate"]
+    with pytest.raises(KeyError, match="Required metadata key in_sample_rate is missing"):
+        metadata.runtime_config_from_metadata(metadata.MetadataReader(bad))
+    bad = dict(md, normalize_audio_default="maybe")
+    with pytest.raises(ValueError, match="must be a boolean"):
+        metadata.runtime_config_from_metadata(metadata.MetadataReader(bad))
+
+
+@pytest.mark.parametrize("n,in_len,out_len,exp", [
+    (52800, 16000, 15872, (15872, 4, 63616)),      # GTCRN: stride = out length (:289-290)
+    (16000, 16000, 15872, (16000, 1, 16000)),
+    (100, 16000, 15872, (16000, 1, 16000)),        # short input zero-padded (:296-298)
+    (40000, 16000, 16000, (16000, 3, 48000)),      # length-preserving model
+])
+def test_chunk_planner(n, in_len, out_len, exp):
+    from adn import chunker
+
+    assert chunker.plan_windows(n, in_len, out_len) == exp
+    a = np.arange(n, dtype=np.int32)
+    w, stride = chunker.split(a, in_len, out_len)
+    assert w.shape == (exp[1], 1, in_len) and stride == exp[0]
+    assert w[0, 0, 0] == 0 and (n < in_len or w[-1, 0, 0] == (exp[1] - 1) * stride)
+
+
+def test_ort_shim_surface_without_gpu(tmp_path):
+    """Metadata sidecar sessions need no device (audio_onnx_metadata.py:290-303)."""
+    import adn.ort_shim as onnxruntime
+    from adn import export, metadata
+
+    export.export_gtcrn(go.random_state_dict(0), tmp_path / "GTCRN.adn", 16000)
+    s = onnxruntime.InferenceSession(str(tmp_path / "GTCRN_Metadata.onnx"))
+    r = metadata.load_runtime_metadata(s)
+    assert r.required_int("input_audio_length") == 16000
+    with pytest.raises(FileNotFoundError):
+        onnxruntime.InferenceSession(str(tmp_path / "missing.adn"))
+    opts = onnxruntime.SessionOptions()
+    opts.add_session_config_entry("session.set_denormal_as_zero", "1")
+    ro = onnxruntime.RunOptions()
+    ro.add_run_config_entry("disable_synchronize_execution_providers", "0")
+    assert onnxruntime.capi._pybind_state.OrtDevice.cpu() == 0

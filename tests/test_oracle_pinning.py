@@ -1,0 +1,154 @@
+"""Pins the CPU oracle (oracle/) -- against the reference executed from /root/reference when
+it is present (build container), against torch.stft/istft (the reference's own
+known-answer check, GTCRN/STFT_Process.py:384-455,555-600, seed 1234) and against the
+committed fixtures generated from the reference (oracle/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+import gtcrn_oracle as go
+import ref_loader
+import stft_oracle as so
+from make_golden import STFT_CASES, ref_istft_forward, ref_stft_forward, ref_stft_pair, sd_digest
+
+needs_ref = pytest.mark.skipif(not ref_loader.reference_available(), reason="/root/reference not present")
+CASES = {c[0]: c for c in STFT_CASES}
+
+
+@pytest.mark.parametrize("name", list(so.SPECS))
+def test_stft_oracle_matches_golden(name, golden_dir):
+    spec = so.SPECS[name]
+    g = np.load(golden_dir / f"stft_{name}.npz")
+    x = torch.from_numpy(g["x"])
+    s = so.stft_packed(spec, x)
+    assert s.shape == g["spec"].shape
+    # same torch primitive (conv1d) on the same basis bits: agreement is at rounding level
+    assert np.abs(s.numpy() - g["spec"]).max() <= 2e-5 * max(1.0, np.abs(g["spec"]).max())
+    y = so.istft_packed(spec, torch.from_numpy(g["spec_in"]))
+    assert y.shape == g["y"].shape
+    assert np.abs(y.numpy() - g["y"]).max() <= 1e-5 * max(1.0, np.abs(g["y"]).max())
+
+
+@needs_ref
+@pytest.mark.parametrize("name", list(so.SPECS))
+def test_stft_tables_bit_equal_reference(name):
+    """Appendix C.13: the uploaded DFT tables must be bit-identical to the reference buffers."""
+    from adn import stft_tables
+
+    spec = so.SPECS[name]
+    _, folder, st, ist, kw, L = CASES[name]
+    stft, istft = ref_stft_pair(name, folder, st, ist, kw, L)
+    ref_fwd = stft.stft_kernel.squeeze(1)
+    ref_inv = istft.inverse_kernel.squeeze(1)
+    assert torch.equal(so.forward_basis(spec), ref_fwd)
+    assert torch.equal(so.inverse_basis(spec), ref_inv)
+    geo = stft_tables.GEOMETRY[name]
+    assert torch.equal(stft_tables.forward_basis(geo), ref_fwd)
+    assert torch.equal(stft_tables.inverse_basis(geo), ref_inv)
+    t = spec.n_frames(L)
+    if hasattr(istft, "inv_win_sum"):
+        assert torch.equal(stft_tables.norm_table(geo, t), istft.inv_win_sum.reshape(-1))
+    else:
+        ws = istft.win_sum.reshape(-1)
+        tab = stft_tables.norm_table(geo, t)
+        if ws.numel() == tab.numel():
+            assert torch.equal(tab, ws)
+        else:  # GTCRN keeps one hop-long period (STFT_Process.py:265-273)
+            assert torch.equal(tab.reshape(-1, ws.numel()), ws.expand(tab.numel() // ws.numel(), -1))
+
+
+@needs_ref
+@pytest.mark.parametrize("name", list(so.SPECS))
+def test_stft_oracle_matches_reference_module(name):
+    spec = so.SPECS[name]
+    _, folder, st, ist, kw, L = CASES[name]
+    stft, istft = ref_stft_pair(name, folder, st, ist, kw, L)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(1, 1, L, generator=g)
+    with torch.inference_mode():
+        s_ref = ref_stft_forward(stft, x)
+        s = so.stft_packed(spec, x)
+        assert torch.equal(s, s_ref)
+        y_ref = ref_istft_forward(istft, s_ref, spec.fbins)
+        y = so.istft_packed(spec, s_ref)
+    assert (y - y_ref).abs().max() <= 1e-6 * max(1.0, float(y_ref.abs().max()))
+
+
+@pytest.mark.parametrize("name", ["gtcrn", "zipenhancer", "mossformergan_se_16k"])
+def test_stft_oracle_vs_torch_stft(name):
+    """The reference's own check: Conv-STFT vs torch.stft / torch.istft on randn, seed 1234.
+    Tolerances are the measured deviations of the reference's inexact basis."""
+    spec = so.SPECS[name]
+    torch.manual_seed(1234)
+    x = torch.randn(1, 1, 16000)
+    w = so.make_window(spec)
+    ts = torch.view_as_real(torch.stft(x.squeeze(0), n_fft=spec.nfft, hop_length=spec.hop, win_length=spec.win_length,
+                                       return_complex=True, window=w, pad_mode="reflect", center=True))
+    s = so.stft_packed(spec, x)
+    re, im = s[:, :spec.fbins], s[:, spec.fbins:]
+    assert (re - ts[..., 0]).abs().mean() < 5e-4 and (im - ts[..., 1]).abs().mean() < 5e-4
+    assert (re - ts[..., 0]).abs().max() < 5e-3
+    y = so.istft_packed(spec, s)                           # round trip, :580-600
+    n = y.shape[-1]
+    assert (y[0, 0] - x[0, 0, :n]).abs().max() < 2e-4
+    yt = torch.istft(torch.complex(ts[..., 0], ts[..., 1]), n_fft=spec.nfft, hop_length=spec.hop,
+                     win_length=spec.win_length, window=w, center=True)
+    y2 = so.istft_packed(spec, torch.cat([ts[..., 0], ts[..., 1]], dim=1))
+    m = min(yt.shape[-1], y2.shape[-1])
+    assert (y2[0, 0, :m] - yt[0, :m]).abs().max() < 3e-4
+
+
+def test_frame_and_length_arithmetic():
+    """Appendix C.2: T = L//hop+1 (centred) / (L-nfft)//hop+1; output lengths per config."""
+    s = so.SPECS
+    assert s["gtcrn"].n_frames(16000) == 63 and s["gtcrn"].out_length(63) == 15872
+    assert s["zipenhancer"].n_frames(16000) == 161 and s["zipenhancer"].out_length(161) == 16000
+    assert s["mossformer2_se_48k"].n_frames(48000) == 121 and s["mossformer2_se_48k"].out_length(121) == 48000
+    assert s["mel_band_roformer"].n_frames(352800) == 801 and s["mel_band_roformer"].out_length(801) == 352800
+
+
+def test_reflect_pad_excludes_edge():
+    """Appendix C.1."""
+    spec = so.SPECS["gtcrn"]
+    x = torch.arange(2000, dtype=torch.float32).reshape(1, 1, -1)
+    p = so.pad_signal(spec, x)
+    assert torch.equal(p, torch.nn.functional.pad(x, (256, 256), mode="reflect"))
+    assert p[0, 0, 255] == 1.0 and p[0, 0, 0] == 256.0 and p[0, 0, -1] == 2000 - 257
+
+
+def test_gtcrn_state_dict_inventory():
+    shapes = go.state_dict_shapes()
+    nparams = sum(int(np.prod(v)) for k, v in shapes.items() if "running_" not in k)
+    assert nparams == 48245          # 48 245 parameters (incl. the fixed ERB matrices)
+    sd = go.random_state_dict(0)
+    assert set(sd) == set(shapes)
+
+
+@pytest.mark.parametrize("fixture,dtype", [("gtcrn_f32_L16000", "F32"), ("gtcrn_int16_L16000", "INT16"),
+                                           ("gtcrn_f32_L8000", "F32")])
+def test_gtcrn_oracle_matches_golden(fixture, dtype, golden_dir):
+    g = np.load(golden_dir / f"{fixture}.npz")
+    sd = go.random_state_dict(int(g["seed"]))
+    assert sd_digest(sd) == str(g["sd_digest"]), "seeded weights differ from the ones the fixture was made with"
+    x = torch.from_numpy(g["x"])
+    y = go.gtcrn_forward_batch(sd, x, dtype, dtype).numpy()
+    assert y.shape == g["y"].shape and y.dtype == g["y"].dtype
+    if dtype == "INT16":
+        assert np.abs(y.astype(np.int32) - g["y"].astype(np.int32)).max() <= 1      # <= 1 LSB (Export_GTCRN.py:50-52)
+    else:
+        assert np.abs(y - g["y"]).max() <= 2e-6 * max(1.0, np.abs(g["y"]).max())
+
+
+@needs_ref
+def test_gtcrn_oracle_matches_reference_modules():
+    """Restated forward vs the reference's own GTCRN_CUSTOM on identical seeded weights."""
+    sd = go.random_state_dict(3)
+    _, build = ref_loader.load_gtcrn(16000, "F32")
+    w = build(sd)
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(1, 1, 16000, generator=g) * 2 - 1) * 0.5
+    with torch.inference_mode():
+        yr = w(x)
+        yo = go.gtcrn_forward(sd, x)
+    assert yr.shape == yo.shape == (1, 1, 15872)
+    assert (yr - yo).abs().max() <= 2e-6 * max(1.0, float(yr.abs().max()))
