@@ -2,6 +2,7 @@
 // flat weight blob, workspace management, stream-ordered launch sequence.
 #include "adn.h"
 #include "common.cuh"
+#include "gemm_tc.cuh"
 #include "gtcrn.cuh"
 
 #include <cstdlib>
@@ -85,6 +86,40 @@ void fill_istft_gemm(GemmArgs& g, const StftPlan& p, const float* enh_padded, co
   g.out_len = p.out_len(T); g.out_dtype = out_dtype; g.out = out;
 }
 
+int choose_bn(int N) {
+  const int cands[3] = {256, 176, 128};
+  int best = 128, best_pad = 1 << 30;
+  for (int c : cands) {
+    int pad = (N + c - 1) / c * c;
+    if (pad < best_pad) { best_pad = pad; best = c; }
+  }
+  return best;
+}
+
+// (rows, cols) row-major -> zero-padded (n_pad, k_pad) hi|lo planes (3xTF32 operand split)
+std::vector<float> split_pad_weight(const float* w, int rows, int cols, int n_pad, int k_pad) {
+  std::vector<float> out((size_t)2 * n_pad * k_pad, 0.f);
+  float* hi = out.data();
+  float* lo = out.data() + (size_t)n_pad * k_pad;
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < cols; ++c) {
+      float v = w[(size_t)r * cols + c];
+      uint32_t bits;
+      memcpy(&bits, &v, 4);
+      bits &= 0xFFFFE000u;
+      float h;
+      memcpy(&h, &bits, 4);
+      hi[(size_t)r * k_pad + c] = h;
+      lo[(size_t)r * k_pad + c] = v - h;
+    }
+  return out;
+}
+
+void tile_rows(int TM, int& bt, int& bb, int& tpc) {
+  if (TM >= 128) { bt = 128; bb = 1; tpc = (TM + 127) / 128; }
+  else { bt = TM; bb = 128 / TM; tpc = 1; }
+}
+
 }  // namespace
 
 // ===================================================================================
@@ -103,6 +138,18 @@ struct adn_model {
   const float* d_fwd = nullptr;
   float* d_ola = nullptr;
   float* d_norm = nullptr;
+
+  // tensor-core (tcgen05, 3xTF32) DFT GEMMs
+  bool use_tc = false;
+  int sms = 148;
+  float* d_wf_hl = nullptr;   // forward basis  hi|lo planes, (n_pad, k_pad) each
+  float* d_wo_hl = nullptr;   // overlap-add W  hi|lo planes
+  int wf_npad = 0, wf_kpad = 0, wo_npad = 0, wo_kpad = 0;
+  float* xp_hl = nullptr;     // A planes (hi|lo) of the padded waveform
+  float* enh_hl = nullptr;    // A planes (hi|lo) of the enhanced spectrum
+  size_t enh_plane = 0;
+  tc::TcPlan stft_plan, istft_plan;
+  tc::TcArgs stft_args{}, istft_args{};
 
   gtcrn::Weights w;
   gtcrn::Buffers buf{};
@@ -222,9 +269,41 @@ adn_status ensure_capacity(adn_model* m, int B) {
   A(m->buf.xb, (size_t)B * T * FRAME16, false);
   A(m->buf.inter, (size_t)B * T * FRAME16, false);
   A(m->buf.enh, (size_t)B * (T + 2 * m->stft.pad_frames()) * SPEC_LD, true);
-#undef A
+  if (m->use_tc) {
+    const StftPlan& p = m->stft;
+    const size_t xp_plane = (size_t)B * m->Lp;
+    m->enh_plane = (size_t)B * (T + 2 * p.pad_frames()) * SPEC_LD + m->wo_kpad;   // + slack for the k overrun
+    A(m->xp_hl, 2 * xp_plane, false);
+    A(m->enh_hl, 2 * m->enh_plane, true);
+    int bt, bb, tpc;
+    // forward: rows = frames, row stride = hop
+    tile_rows((int)T, bt, bb, tpc);
+    tc::TcArgs& a = m->stft_args;
+    a = tc::TcArgs{};
+    a.bb = bb; a.bt = bt; a.tiles_per_chunk = tpc; a.t0 = 0; a.TM = (int)T;
+    a.N = p.rows2f; a.K = p.nfft;
+    a.C = m->buf.spec; a.c_sB = (long long)T * SPEC_LD; a.c_sT = SPEC_LD;
+    if (!tc::make_row_map(&m->stft_plan.map_a_hi, m->xp_hl, p.nfft, (int)T, p.hop, B, m->Lp, bt, bb, m->err) ||
+        !tc::make_row_map(&m->stft_plan.map_a_lo, m->xp_hl + xp_plane, p.nfft, (int)T, p.hop, B, m->Lp, bt, bb, m->err))
+      return ADN_ERR_CUDA;
+    // inverse: rows = raw hop-blocks, each a run of R consecutive (zero-framed) spectrum frames
+    const int lo = p.blk_lo(), hi = p.blk_hi((int)T), TM = hi - lo + 1;
+    tile_rows(TM, bt, bb, tpc);
+    tc::TcArgs& c = m->istft_args;
+    c = tc::TcArgs{};
+    c.bb = bb; c.bt = bt; c.tiles_per_chunk = tpc; c.t0 = lo; c.TM = TM;
+    c.N = p.hop; c.K = p.R * p.ld;
+    c.norm = m->d_norm; c.norm_mul = p.norm_mul; c.hop = p.hop; c.shift = p.center ? p.half : 0;
+    c.out_len = m->Lout; c.out_dtype = m->out_dtype;
+    const int rows = (int)T + 2 * p.pad_frames();
+    if (!tc::make_row_map(&m->istft_plan.map_a_hi, m->enh_hl, m->wo_kpad, rows, p.ld, B, (long long)rows * p.ld, bt, bb, m->err) ||
+        !tc::make_row_map(&m->istft_plan.map_a_lo, m->enh_hl + m->enh_plane, m->wo_kpad, rows, p.ld, B,
+                          (long long)rows * p.ld, bt, bb, m->err))
+      return ADN_ERR_CUDA;
+  }
   if ((s = dev_alloc(m, &m->d_in, (size_t)B * m->L * dtype_size(m->in_dtype), false)) != ADN_OK) return s;
   if ((s = dev_alloc(m, &m->d_out, (size_t)B * m->Lout * dtype_size(m->out_dtype), false)) != ADN_OK) return s;
+#undef A
   m->capacity = B;
   return ADN_OK;
 }
@@ -298,6 +377,33 @@ adn_status build_gtcrn(adn_model* m, const float* hblob) {
   ADN_CUDA_TRY(cudaMalloc((void**)&m->d_ola, ola.size() * sizeof(float)), m->err);
   ADN_CUDA_TRY(cudaMemcpy(m->d_ola, ola.data(), ola.size() * sizeof(float), cudaMemcpyHostToDevice), m->err);
   m->d_norm = m->d_blob + nrm->second.offset;
+
+  // tensor-core path: pre-split, zero-padded weight planes + their TMA maps
+  const char* env = getenv("ADN_GEMM");
+  m->use_tc = !(env && std::string(env) == "ffma");
+  if (m->use_tc) {
+    const StftPlan& p = m->stft;
+    auto fwd = m->index.find("stft.fwd");
+    m->stft_plan.bn = choose_bn(p.rows2f);
+    m->wf_npad = (p.rows2f + m->stft_plan.bn - 1) / m->stft_plan.bn * m->stft_plan.bn;
+    m->wf_kpad = round_up(p.nfft, 32);
+    std::vector<float> wf = split_pad_weight(hblob + fwd->second.offset, p.rows2f, p.nfft, m->wf_npad, m->wf_kpad);
+    m->istft_plan.bn = choose_bn(p.hop);
+    m->wo_npad = (p.hop + m->istft_plan.bn - 1) / m->istft_plan.bn * m->istft_plan.bn;
+    m->wo_kpad = round_up(p.R * p.ld, 32);
+    std::vector<float> wo = split_pad_weight(ola.data(), p.hop, p.R * p.ld, m->wo_npad, m->wo_kpad);
+    ADN_CUDA_TRY(cudaMalloc((void**)&m->d_wf_hl, wf.size() * sizeof(float)), m->err);
+    ADN_CUDA_TRY(cudaMemcpy(m->d_wf_hl, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice), m->err);
+    ADN_CUDA_TRY(cudaMalloc((void**)&m->d_wo_hl, wo.size() * sizeof(float)), m->err);
+    ADN_CUDA_TRY(cudaMemcpy(m->d_wo_hl, wo.data(), wo.size() * sizeof(float), cudaMemcpyHostToDevice), m->err);
+    if (!tc::make_weight_map(&m->stft_plan.map_w_hi, m->d_wf_hl, m->wf_kpad, m->wf_npad, m->stft_plan.bn, m->err) ||
+        !tc::make_weight_map(&m->stft_plan.map_w_lo, m->d_wf_hl + (size_t)m->wf_npad * m->wf_kpad, m->wf_kpad,
+                             m->wf_npad, m->stft_plan.bn, m->err) ||
+        !tc::make_weight_map(&m->istft_plan.map_w_hi, m->d_wo_hl, m->wo_kpad, m->wo_npad, m->istft_plan.bn, m->err) ||
+        !tc::make_weight_map(&m->istft_plan.map_w_lo, m->d_wo_hl + (size_t)m->wo_npad * m->wo_kpad, m->wo_kpad,
+                             m->wo_npad, m->istft_plan.bn, m->err))
+      return ADN_ERR_CUDA;
+  }
   return ADN_OK;
 }
 
@@ -395,6 +501,7 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
     return fail(ADN_ERR_CUDA);
   }
   m->nfloats = nfloats;
+  m->sms = prop.multiProcessorCount;
   adn_status s = build_gtcrn(m, weights);
   if (s != ADN_OK) return fail(s);
   if (cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -412,6 +519,8 @@ void adn_destroy(adn_model* m) {
   free_workspace(m);
   if (m->d_blob) cudaFree(m->d_blob);
   if (m->d_ola) cudaFree(m->d_ola);
+  if (m->d_wf_hl) cudaFree(m->d_wf_hl);
+  if (m->d_wo_hl) cudaFree(m->d_wo_hl);
   for (auto e : m->events) cudaEventDestroy(e);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   delete m;
@@ -436,7 +545,8 @@ size_t adn_workspace_bytes(const adn_model* m, int32_t batch) {
 
 int32_t adn_launches_per_run(const adn_model* m, int32_t batch) {
   (void)batch;
-  return m ? 22 : 0;   // prep, stft, enc_front, 6x(gt_main, tra_apply), 2x(intra, inter), ln_res, dec_tail, istft
+  // prep, stft, enc_front, 6x(gt_main, tra_apply), 2x(intra, inter), ln_res, dec_tail, istft (+2 tf32 splits)
+  return m ? (m->use_tc ? 24 : 22) : 0;
 }
 
 adn_status adn_run(adn_model* m, const void* d_in, void* const* d_outs, int32_t batch, void* stream) {
@@ -459,13 +569,24 @@ adn_status adn_run(adn_model* m, const void* d_in, void* const* d_outs, int32_t 
   ++n; tick_cb(m, "prep");
 
   GemmArgs g;
-  fill_stft_gemm(g, m->stft, m->buf.xp, m->Lp, m->d_fwd, batch, m->T, m->buf.spec,
-                 (long long)m->T * gtcrn::SPEC_LD, gtcrn::SPEC_LD, 1);
-  launch_gemm_ffma(g, EPI_STORE, st);
-  ++n; tick_cb(m, "stft_gemm");
+  if (m->use_tc) {
+    const long long plane = (long long)m->capacity * m->Lp;
+    tc::split_tf32(m->buf.xp, m->xp_hl, m->xp_hl + plane, (long long)batch * m->Lp, st);
+    ++n; tick_cb(m, "split_tf32");
+    tc::TcArgs a = m->stft_args;
+    a.B = batch;
+    a.m_tiles = a.bb > 1 ? (batch + a.bb - 1) / a.bb : batch * a.tiles_per_chunk;
+    ADN_CUDA_TRY(tc::launch(m->stft_plan, a, EPI_STORE, m->sms, st), m->err);
+    ++n; tick_cb(m, "stft_gemm_tc");
+  } else {
+    fill_stft_gemm(g, m->stft, m->buf.xp, m->Lp, m->d_fwd, batch, m->T, m->buf.spec,
+                   (long long)m->T * gtcrn::SPEC_LD, gtcrn::SPEC_LD, 1);
+    launch_gemm_ffma(g, EPI_STORE, st);
+    ++n; tick_cb(m, "stft_gemm");
+  }
 
   gtcrn::Dims d{batch, m->L, m->Lp, m->T};
-  const int stop_bb = m->stop_after > 0 ? (m->stop_after > 2 ? m->stop_after - 2 : 1) : 0;
+  const int stop_bb = m->stop_after > 0 ? (m->stop_after > n ? m->stop_after - n : 1) : 0;
   n += gtcrn::launch_backbone(m->w, m->buf, d, m->stft.pad_frames(), st, tick_cb, m, stop_bb);
   m->last_launches = n;
   m->last_batch = batch;
@@ -474,9 +595,21 @@ adn_status adn_run(adn_model* m, const void* d_in, void* const* d_outs, int32_t 
     return ADN_OK;
   }
 
-  fill_istft_gemm(g, m->stft, m->buf.enh, m->d_ola, m->d_norm, batch, m->T, d_outs[0], m->out_dtype);
-  launch_gemm_ffma(g, EPI_ISTFT, st);
-  ++n; tick_cb(m, "istft_gemm");
+  if (m->use_tc) {
+    const long long nel = (long long)batch * (m->T + 2 * m->stft.pad_frames()) * gtcrn::SPEC_LD;
+    tc::split_tf32(m->buf.enh, m->enh_hl, m->enh_hl + m->enh_plane, nel, st);
+    ++n; tick_cb(m, "split_tf32");
+    tc::TcArgs a = m->istft_args;
+    a.B = batch;
+    a.m_tiles = a.bb > 1 ? (batch + a.bb - 1) / a.bb : batch * a.tiles_per_chunk;
+    a.out = d_outs[0];
+    ADN_CUDA_TRY(tc::launch(m->istft_plan, a, EPI_ISTFT, m->sms, st), m->err);
+    ++n; tick_cb(m, "istft_gemm_tc");
+  } else {
+    fill_istft_gemm(g, m->stft, m->buf.enh, m->d_ola, m->d_norm, batch, m->T, d_outs[0], m->out_dtype);
+    launch_gemm_ffma(g, EPI_ISTFT, st);
+    ++n; tick_cb(m, "istft_gemm");
+  }
 
   m->last_launches = n;
   m->last_batch = batch;

@@ -1,0 +1,386 @@
+// Row-gather GEMM on the 5th-gen tensor cores: tcgen05.mma kind::tf32 with the 3xTF32
+// split (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM) so the reference's fp32 "DFT as a
+// convolution" (GTCRN/STFT_Process.py:316,328) keeps fp32-class accuracy.
+//
+//   C[m,n] = sum_k A(m,k) * W[n,k],  m = (chunk b, row t),  A(m,k) = A[b*sB + (t+t0)*sT + k]
+//
+// * A is never framed in memory: a 3-D TMA tensor map with row stride sT (< K: rows overlap)
+//   gathers 128-row tiles straight from the padded waveform (STFT) or from runs of R
+//   consecutive spectrum frames (ISTFT overlap-add).  Operands are pre-split into tf32
+//   hi/lo planes by their producers, so the main loop is pure TMA -> smem -> tcgen05.mma.
+// * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+//   warps 2..5 = epilogue (TMEM -> registers -> global).  Persistent over output tiles with
+//   two TMEM accumulator buffers so the epilogue of tile i overlaps the main loop of i+1.
+#include "adn.h"
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+#include <cuda.h>
+
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                 // 32 fp32 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 8;              // tf32: 32 bytes of K per instruction
+constexpr int NTHREADS = 192;
+constexpr uint32_t A_TILE_BYTES = BM * BK * 4;   // 16 KiB
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46)
+// (8 rows * 128 B = 1024) | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1,
+// A=TF32 [7,10)=2, B=TF32 [10,13)=2, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN>
+struct Smem {
+  static constexpr uint32_t W_TILE_BYTES = BN * BK * 4;
+  static constexpr uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * W_TILE_BYTES;
+  static constexpr int STAGES = (BN <= 128) ? 3 : 2;
+  static constexpr uint32_t TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+               const TcArgs g) {
+  using S = Smem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + S::STAGES * S::STAGE_BYTES);
+  uint64_t* full = bars;                    // [STAGES]
+  uint64_t* empty = bars + S::STAGES;       // [STAGES]
+  uint64_t* tfull = bars + 2 * S::STAGES;   // [2]
+  uint64_t* tempty = tfull + 2;             // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles_n = (g.N + BN - 1) / BN;
+  const int n_tiles = g.m_tiles * n_tiles_n;
+  const int k_blocks = (g.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a_hi);
+    prefetch_tmap(&map_a_lo);
+    prefetch_tmap(&map_w_hi);
+    prefetch_tmap(&map_w_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S::STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int mt = tile / n_tiles_n, nt = tile - mt * n_tiles_n;
+        int b0, t0;
+        if (g.bb > 1) { b0 = mt * g.bb; t0 = g.t0; }
+        else { b0 = mt / g.tiles_per_chunk; t0 = g.t0 + (mt - b0 * g.tiles_per_chunk) * BM; }
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * S::STAGE_BYTES;
+          mbar_expect_tx(&full[stage], (uint32_t)(2 * g.bt * g.bb * BK * 4) + 2 * S::W_TILE_BYTES);
+          tma_load_3d(st, &map_a_hi, &full[stage], kb * BK, t0, b0);
+          tma_load_3d(st + A_TILE_BYTES, &map_a_lo, &full[stage], kb * BK, t0, b0);
+          tma_load_2d(st + 2 * A_TILE_BYTES, &map_w_hi, &full[stage], kb * BK, nt * BN);
+          tma_load_2d(st + 2 * A_TILE_BYTES + S::W_TILE_BYTES, &map_w_lo, &full[stage], kb * BK, nt * BN);
+          if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int ab = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty[ab], aphase ^ 1);       // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + ab * 256;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_TILE_BYTES);
+          const uint64_t w_hi = make_desc(sa + 2 * A_TILE_BYTES);
+          const uint64_t w_lo = make_desc(sa + 2 * A_TILE_BYTES + S::W_TILE_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+            const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);   // +32 B inside the swizzle row
+            umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, (kb | kk) ? 1u : 0u);
+            umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1u);
+            umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1u);
+          }
+          umma_commit(&empty[stage]);              // smem slot free once these MMAs retire
+          if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[ab]);                   // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                   // row of the tile
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int mt = tile / n_tiles_n, nt = tile - mt * n_tiles_n;
+      const int ab = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      int b, t;
+      if (g.bb > 1) { int bi = r / g.bt; b = mt * g.bb + bi; t = r - bi * g.bt; if (bi >= g.bb) b = g.B; }
+      else { b = mt / g.tiles_per_chunk; t = (mt - b * g.tiles_per_chunk) * BM + r; }
+      const bool row_ok = (b < g.B) && (t < g.TM);
+      mbar_wait(&tfull[ab], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ab * 256 + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait();
+        const int n0 = nt * BN + c0;
+        if (!row_ok || n0 >= g.N) continue;
+        if (EPI == EPI_STORE) {
+          float* dst = g.C + (long long)b * g.c_sB + (long long)t * g.c_sT + n0;
+          if (c0 + 32 <= BN && n0 + 32 <= g.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                 __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < BN && n0 + j < g.N) dst[j] = __uint_as_float(v[j]);
+          }
+        } else {
+          // ISTFT: s = (t + t0)*hop + n - shift ; y = acc (/|*) norm[s]
+          const int s0 = (t + g.t0) * g.hop + n0 - g.shift;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int s = s0 + j;
+            if (c0 + j >= BN || n0 + j >= g.N || s < 0 || s >= g.out_len) continue;
+            float x = __uint_as_float(v[j]);
+            const float nv = __ldg(g.norm + s);
+            x = g.norm_mul ? x * nv : x / nv;
+            const long long o = (long long)b * g.out_len + s;
+            if (g.out_dtype == ADN_F32) reinterpret_cast<float*>(g.out)[o] = x;
+            else if (g.out_dtype == ADN_I16) {
+              float qv = fminf(fmaxf(x * 32767.0f, -32768.0f), 32767.0f);
+              reinterpret_cast<int16_t*>(g.out)[o] = (int16_t)(int)qv;
+            } else reinterpret_cast<__half*>(g.out)[o] = __float2half_rn(x);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[ab]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+bool make_row_map(CUtensorMap* map, const float* base, int k_extent, int rows, long long row_stride, int batches,
+                  long long batch_stride, int box_rows, int box_batches, std::string& err) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { err = "cuTensorMapEncodeTiled entry point not available"; return false; }
+  if ((row_stride * 4) % 16 || (batch_stride * 4) % 16 || ((uintptr_t)base) % 16) {
+    err = "TMA needs 16-byte aligned base and strides";
+    return false;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)k_extent, (cuuint64_t)rows, (cuuint64_t)batches};
+  cuuint64_t strides[2] = {(cuuint64_t)row_stride * 4, (cuuint64_t)batch_stride * 4};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, (cuuint32_t)box_batches};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r); return false; }
+  return true;
+}
+
+bool make_weight_map(CUtensorMap* map, const float* base, int k_pad, int n_pad, int box_n, std::string& err) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { err = "cuTensorMapEncodeTiled entry point not available"; return false; }
+  cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)n_pad};
+  cuuint64_t strides[1] = {(cuuint64_t)k_pad * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_n};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(W) failed: " + std::to_string((int)r); return false; }
+  return true;
+}
+
+template <int BN, int EPI>
+static cudaError_t launch_t(const TcPlan& p, const TcArgs& a, int sms, cudaStream_t st) {
+  using S = Smem<BN>;
+  static bool configured = false;
+  auto kern = gemm_tc_kernel<BN, EPI>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int n_tiles = a.m_tiles * ((a.N + BN - 1) / BN);
+  const int grid = n_tiles < sms ? n_tiles : sms;
+  kern<<<grid, NTHREADS, S::TOTAL, st>>>(p.map_a_hi, p.map_a_lo, p.map_w_hi, p.map_w_lo, a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch(const TcPlan& p, const TcArgs& a, int epi, int sms, cudaStream_t st) {
+  if (p.bn == 176) return epi == EPI_STORE ? launch_t<176, EPI_STORE>(p, a, sms, st) : launch_t<176, EPI_ISTFT>(p, a, sms, st);
+  if (p.bn == 256) return epi == EPI_STORE ? launch_t<256, EPI_STORE>(p, a, sms, st) : launch_t<256, EPI_ISTFT>(p, a, sms, st);
+  if (p.bn == 128) return epi == EPI_STORE ? launch_t<128, EPI_STORE>(p, a, sms, st) : launch_t<128, EPI_ISTFT>(p, a, sms, st);
+  return cudaErrorInvalidValue;
+}
+
+// x -> (hi, lo): hi = x with the 13 low mantissa bits cleared (exactly representable in tf32),
+// lo = x - hi (exact in fp32).
+__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
+                                  long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float v = x[i];
+    float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
+void split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t st) {
+  split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, hi, lo, n);
+}
+
+}  // namespace tc

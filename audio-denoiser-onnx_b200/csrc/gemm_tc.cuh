@@ -1,0 +1,40 @@
+// tcgen05 / TMA row-gather GEMM (3xTF32): host interface.  See gemm_tc.cu.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <string>
+
+namespace tc {
+
+struct TcArgs {
+  int m_tiles;           // number of 128-row tiles
+  int bb, bt;            // TMA box: bb chunks x bt rows per tile (bb*bt <= 128)
+  int tiles_per_chunk;   // when bb == 1: ceil(TM / 128)
+  int t0;                // first row (per chunk) in the A tensor map
+  int B, TM;             // chunks, valid rows per chunk
+  int N, K;
+  // EPI_STORE: C[b*c_sB + t*c_sT + n]
+  float* C;
+  long long c_sB, c_sT;
+  // EPI_ISTFT (see GemmArgs in common.cuh)
+  const float* norm;
+  int norm_mul, hop, shift, out_len, out_dtype;
+  void* out;
+};
+
+struct TcPlan {
+  CUtensorMap map_a_hi, map_a_lo, map_w_hi, map_w_lo;
+  int bn = 0;            // N tile: 128 | 176 | 256
+};
+
+// A planes: element (b, t, k) at base[b*batch_stride + t*row_stride + k]; rows may overlap.
+bool make_row_map(CUtensorMap* map, const float* base, int k_extent, int rows, long long row_stride, int batches,
+                  long long batch_stride, int box_rows, int box_batches, std::string& err);
+// W planes: (n_pad, k_pad) row-major, zero padded.
+bool make_weight_map(CUtensorMap* map, const float* base, int k_pad, int n_pad, int box_n, std::string& err);
+
+cudaError_t launch(const TcPlan& p, const TcArgs& a, int epi, int sms, cudaStream_t st);
+
+void split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t st);
+
+}  // namespace tc
