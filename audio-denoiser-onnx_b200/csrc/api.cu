@@ -241,7 +241,9 @@ size_t workspace_bytes_for(const adn_model* m, int B) {
   f += (size_t)B * T * SPEC_LD;                 // spec
   f += (size_t)B * T * FRAME_E0;                // e0
   f += (size_t)4 * B * T * FRAME16;             // e1..e4
-  f += (size_t)B * T * 8 * E1_F + (size_t)B * T * 8;   // h1, zt
+  f += (size_t)B * T * 8 * E1_F + (size_t)2 * B * T * 8;   // h1, zt, at
+  f += (size_t)B * T * 3 * FRAME16;             // gi
+  if (m->use_tc) f += (size_t)2 * B * m->Lp + (size_t)2 * (B * (T + 2 * m->stft.pad_frames()) * SPEC_LD + m->wo_kpad);
   f += (size_t)3 * B * T * FRAME16;             // xa, xb, inter
   f += (size_t)B * (T + 2 * m->stft.pad_frames()) * SPEC_LD;   // enh
   size_t bytes = f * sizeof(float);
@@ -265,6 +267,9 @@ adn_status ensure_capacity(adn_model* m, int B) {
   for (int i = 1; i <= 4; ++i) A(m->buf.e[i], (size_t)B * T * FRAME16, false);
   A(m->buf.h1, (size_t)B * T * 8 * E1_F, false);
   A(m->buf.zt, (size_t)B * T * 8, false);
+  A(m->buf.at, (size_t)B * T * 8, false);
+  A(m->buf.gi, (size_t)B * T * 3 * FRAME16, false);
+  m->buf.xp_hi = m->buf.xp_lo = m->buf.enh_hi = m->buf.enh_lo = nullptr;
   A(m->buf.xa, (size_t)B * T * FRAME16, false);
   A(m->buf.xb, (size_t)B * T * FRAME16, false);
   A(m->buf.inter, (size_t)B * T * FRAME16, false);
@@ -275,6 +280,8 @@ adn_status ensure_capacity(adn_model* m, int B) {
     m->enh_plane = (size_t)B * (T + 2 * p.pad_frames()) * SPEC_LD + m->wo_kpad;   // + slack for the k overrun
     A(m->xp_hl, 2 * xp_plane, false);
     A(m->enh_hl, 2 * m->enh_plane, true);
+    m->buf.xp_hi = m->xp_hl; m->buf.xp_lo = m->xp_hl + xp_plane;
+    m->buf.enh_hi = m->enh_hl; m->buf.enh_lo = m->enh_hl + m->enh_plane;
     int bt, bb, tpc;
     // forward: rows = frames, row stride = hop
     tile_rows((int)T, bt, bb, tpc);
@@ -545,8 +552,8 @@ size_t adn_workspace_bytes(const adn_model* m, int32_t batch) {
 
 int32_t adn_launches_per_run(const adn_model* m, int32_t batch) {
   (void)batch;
-  // prep, stft, enc_front, 6x(gt_main, tra_apply), 2x(intra, inter), ln_res, dec_tail, istft (+2 tf32 splits)
-  return m ? (m->use_tc ? 24 : 22) : 0;
+  // prep, stft, enc_front, 6x(gt_main, tra_gru, tra_apply), 2x(dp_intra, dp_inter), ln_res, dec_tail, istft
+  return m ? 28 : 0;
 }
 
 adn_status adn_run(adn_model* m, const void* d_in, void* const* d_outs, int32_t batch, void* stream) {
@@ -564,15 +571,12 @@ adn_status adn_run(adn_model* m, const void* d_in, void* const* d_outs, int32_t 
   int n = 0;
   tick_cb(m, "start");
 
-  gtcrn::launch_prep(d_in, m->in_dtype, m->buf.xp, batch, m->L, m->Lp, m->stft.half, /*remove_dc=*/1,
-                     m->stft.reflect, st);
+  gtcrn::launch_prep(d_in, m->in_dtype, m->buf.xp, m->buf.xp_hi, m->buf.xp_lo, batch, m->L, m->Lp, m->stft.half,
+                     /*remove_dc=*/1, m->stft.reflect, st);
   ++n; tick_cb(m, "prep");
 
   GemmArgs g;
   if (m->use_tc) {
-    const long long plane = (long long)m->capacity * m->Lp;
-    tc::split_tf32(m->buf.xp, m->xp_hl, m->xp_hl + plane, (long long)batch * m->Lp, st);
-    ++n; tick_cb(m, "split_tf32");
     tc::TcArgs a = m->stft_args;
     a.B = batch;
     a.m_tiles = a.bb > 1 ? (batch + a.bb - 1) / a.bb : batch * a.tiles_per_chunk;
@@ -596,9 +600,6 @@ adn_status adn_run(adn_model* m, const void* d_in, void* const* d_outs, int32_t 
   }
 
   if (m->use_tc) {
-    const long long nel = (long long)batch * (m->T + 2 * m->stft.pad_frames()) * gtcrn::SPEC_LD;
-    tc::split_tf32(m->buf.enh, m->enh_hl, m->enh_hl + m->enh_plane, nel, st);
-    ++n; tick_cb(m, "split_tf32");
     tc::TcArgs a = m->istft_args;
     a.B = batch;
     a.m_tiles = a.bb > 1 ? (batch + a.bb - 1) / a.bb : batch * a.tiles_per_chunk;
@@ -683,6 +684,8 @@ adn_status adn_debug_read(adn_model* m, const char* name, float* h_dst, size_t c
       {"e4", {m->buf.e[4], B * T * FRAME16}},
       {"h1", {m->buf.h1, B * T * 8 * E1_F}},
       {"zt", {m->buf.zt, B * T * 8}},
+      {"at", {m->buf.at, B * T * 8}},
+      {"gi", {m->buf.gi, B * T * 3 * FRAME16}},
       {"xa", {m->buf.xa, B * T * FRAME16}},
       {"xb", {m->buf.xb, B * T * FRAME16}},
       {"inter", {m->buf.inter, B * T * FRAME16}},
@@ -809,7 +812,8 @@ adn_status adn_stft_forward(adn_stft* s, const float* d_x, float* d_spec, int32_
     }
     s->xp_cap = need;
   }
-  gtcrn::launch_prep(d_x, ADN_F32, s->d_xp, batch, length, Lp, s->p.center ? s->p.half : 0, 0, s->p.reflect, st);
+  gtcrn::launch_prep(d_x, ADN_F32, s->d_xp, nullptr, nullptr, batch, length, Lp, s->p.center ? s->p.half : 0, 0,
+                     s->p.reflect, st);
   GemmArgs g;
   fill_stft_gemm(g, s->p, s->d_xp, Lp, s->d_fwd, batch, T, d_spec, (long long)s->p.rows2f * T, 1, T);
   launch_gemm_ffma(g, EPI_STORE, st);

@@ -37,6 +37,7 @@ __device__ __forceinline__ float load_sample<__half>(const __half* p, long long 
 
 template <typename Tin>
 __global__ void __launch_bounds__(256) prep_kernel(const Tin* __restrict__ in, float* __restrict__ xp,
+                                                   float* __restrict__ hi, float* __restrict__ lo,
                                                    int L, int Lp, int half, int remove_dc, int reflect) {
   const int b = blockIdx.x;
   const Tin* x = in + (long long)b * L;
@@ -69,17 +70,18 @@ __global__ void __launch_bounds__(256) prep_kernel(const Tin* __restrict__ in, f
       if (jj >= 0 && jj < L) v = load_sample<Tin>(x, jj) - mean;
     }
     o[i] = v;
+    if (hi) split_tf32_store(v, hi, lo, (long long)b * Lp + i);
   }
 }
 
-void launch_prep(const void* in, int in_dtype, float* xp, int B, int L, int Lp, int half,
+void launch_prep(const void* in, int in_dtype, float* xp, float* hi, float* lo, int B, int L, int Lp, int half,
                  int remove_dc, int reflect, cudaStream_t st) {
   if (in_dtype == ADN_F32)
-    prep_kernel<float><<<B, 256, 0, st>>>((const float*)in, xp, L, Lp, half, remove_dc, reflect);
+    prep_kernel<float><<<B, 256, 0, st>>>((const float*)in, xp, hi, lo, L, Lp, half, remove_dc, reflect);
   else if (in_dtype == ADN_I16)
-    prep_kernel<int16_t><<<B, 256, 0, st>>>((const int16_t*)in, xp, L, Lp, half, remove_dc, reflect);
+    prep_kernel<int16_t><<<B, 256, 0, st>>>((const int16_t*)in, xp, hi, lo, L, Lp, half, remove_dc, reflect);
   else
-    prep_kernel<__half><<<B, 256, 0, st>>>((const __half*)in, xp, L, Lp, half, remove_dc, reflect);
+    prep_kernel<__half><<<B, 256, 0, st>>>((const __half*)in, xp, hi, lo, L, Lp, half, remove_dc, reflect);
 }
 
 // =================================================================================
@@ -320,292 +322,6 @@ gt_main_kernel(const __grid_constant__ GTW w, const float* __restrict__ xin, flo
 }
 
 // =================================================================================
-// GRU cell helpers (PyTorch gate order r,z,n; n = tanh(i_n + r*(W_hn h + b_hn))).
-// =================================================================================
-template <int I, int H>
-struct GruLane {       // one lane owns hidden unit j of one GRU
-  float wi[3][I];
-  float wh[3][H];
-  float bi[3], bh[3];
-  __device__ void load(const GruPtrs& p, int j) {
-#pragma unroll
-    for (int g = 0; g < 3; ++g) {
-#pragma unroll
-      for (int i = 0; i < I; ++i) wi[g][i] = __ldg(p.w_ih + (g * H + j) * I + i);
-#pragma unroll
-      for (int k = 0; k < H; ++k) wh[g][k] = __ldg(p.w_hh + (g * H + j) * H + k);
-      bi[g] = __ldg(p.b_ih + g * H + j);
-      bh[g] = __ldg(p.b_hh + g * H + j);
-    }
-  }
-  // x: inputs, hv: all H hidden values of this GRU (previous step), hself: own previous h
-  __device__ __forceinline__ float step(const float (&x)[I], const float (&hv)[H], float hself) const {
-    float gi[3], gh[3];
-#pragma unroll
-    for (int g = 0; g < 3; ++g) {
-      float a = bi[g];
-#pragma unroll
-      for (int i = 0; i < I; ++i) a = fmaf(wi[g][i], x[i], a);
-      gi[g] = a;
-      float c = bh[g];
-#pragma unroll
-      for (int k = 0; k < H; ++k) c = fmaf(wh[g][k], hv[k], c);
-      gh[g] = c;
-    }
-    float rg = adn_sigmoid(gi[0] + gh[0]);
-    float zg = adn_sigmoid(gi[1] + gh[1]);
-    float ng = tanhf(gi[2] + rg * gh[2]);
-    return (1.0f - zg) * ng + zg * hself;
-  }
-};
-
-// =================================================================================
-// tra_apply: TRA attention GRU over T (16 lanes of warp 0), then the whole CTA applies the
-// gate, interleaves with the bypass half (:324) and optionally adds the next decoder skip.
-// =================================================================================
-constexpr int TRA_THREADS = 256;
-
-__global__ void __launch_bounds__(TRA_THREADS)
-tra_apply_kernel(const TraW w, const float* __restrict__ zt, const float* __restrict__ h1,
-                 const float* __restrict__ xin, const float* __restrict__ skip,
-                 float* __restrict__ out, int T) {
-  extern __shared__ float at_s[];     // (T, 8)
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const float* z = zt + (long long)b * T * 8;
-
-  if (tid < 32) {
-    const int j = tid & 15;
-    GruLane<8, 16> cell;
-    cell.load(w.gru, j);
-    float fw[16], fb = 0.f;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) fw[k] = __ldg(w.fc_w + (j & 7) * 16 + k);
-    fb = __ldg(w.fc_b + (j & 7));
-    float h = 0.f;
-    float hv[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) hv[k] = 0.f;
-    float4 xa = __ldg(reinterpret_cast<const float4*>(z));
-    float4 xb4 = __ldg(reinterpret_cast<const float4*>(z) + 1);
-    for (int t = 0; t < T; ++t) {
-      float x[8] = {xa.x, xa.y, xa.z, xa.w, xb4.x, xb4.y, xb4.z, xb4.w};
-      if (t + 1 < T) {
-        xa = __ldg(reinterpret_cast<const float4*>(z + (t + 1) * 8));
-        xb4 = __ldg(reinterpret_cast<const float4*>(z + (t + 1) * 8) + 1);
-      }
-      h = cell.step(x, hv, h);
-#pragma unroll
-      for (int k = 0; k < 16; ++k) hv[k] = __shfl_sync(0xffffffffu, h, k, 16);
-      float a = fb;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) a = fmaf(fw[k], hv[k], a);
-      if (tid < 8) at_s[t * 8 + tid] = adn_sigmoid(a);
-    }
-  }
-  __syncthreads();
-
-  const long long base = (long long)b * T * FRAME16;
-  const float* hb = h1 + (long long)b * T * (8 * E1_F);
-  const int total = T * FRAME16;
-  for (int i = tid; i < total; i += TRA_THREADS) {
-    int t = i / FRAME16, rem = i - t * FRAME16;
-    int ch = rem / E1_F, f = rem - ch * E1_F;
-    int c = ch >> 1;
-    float v;
-    if (ch & 1) v = __ldg(xin + base + (long long)t * FRAME16 + (8 + c) * E1_F + f);
-    else v = __ldg(hb + (long long)t * (8 * E1_F) + c * E1_F + f) * at_s[t * 8 + c];
-    if (skip) v += __ldg(skip + base + i);
-    out[base + i] = v;
-  }
-}
-
-// =================================================================================
-// Per-frame LayerNorm((33,16), eps=1e-8) helpers on a half-warp (16 lanes).
-// =================================================================================
-__device__ __forceinline__ float half_sum(float v) {
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// z (smem, 528 values, any fixed layout matching lnw/lnb) -> mean / rstd over the frame
-__device__ __forceinline__ void frame_stats(const float* z, int hl, float& mean, float& rstd) {
-  float s = 0.f;
-  for (int i = hl; i < FRAME16; i += 16) s += z[i];
-  mean = half_sum(s) * (1.0f / FRAME16);
-  float q = 0.f;
-  for (int i = hl; i < FRAME16; i += 16) {
-    float d = z[i] - mean;
-    q = fmaf(d, d, q);
-  }
-  float var = half_sum(q) * (1.0f / FRAME16);
-  rstd = 1.0f / sqrtf(var + 1e-8f);
-}
-
-// =================================================================================
-// dp_intra: x = a (+ LN(zprev)) ; bi-GRU over F in 2 groups ; FC ; LN ; out = x + LN(..)
-// One half-warp per frame: lane = (group, direction, hidden unit) = 2*2*4.
-// =================================================================================
-constexpr int DI_FRAMES = 4;     // frames per CTA (2 warps)
-
-__global__ void __launch_bounds__(DI_FRAMES * 16)
-dp_intra_kernel(const DpW w, const float* __restrict__ a, const float* __restrict__ zprev,
-                const float* __restrict__ pln_w, const float* __restrict__ pln_b,
-                float* __restrict__ out, int nframes) {
-  __shared__ float xs[DI_FRAMES][FRAME16];     // [c][f]
-  __shared__ float ys[DI_FRAMES][E1_F * 16];   // [f][16]  GRU outputs
-  __shared__ float zs[DI_FRAMES][FRAME16];     // [c][f]   FC outputs
-
-  const int lane = threadIdx.x & 31, hl = lane & 15;
-  const int fi = (threadIdx.x >> 5) * 2 + (lane >> 4);
-  const long long fg = (long long)blockIdx.x * DI_FRAMES + fi;
-  const bool live = fg < nframes;
-  const long long off = (live ? fg : 0) * FRAME16;
-  float* x = xs[fi];
-  float* y = ys[fi];
-  float* z = zs[fi];
-
-  if (zprev) {
-    for (int i = hl; i < FRAME16; i += 16) z[i] = __ldg(zprev + off + i);
-    __syncwarp();
-    float mean, rstd;
-    frame_stats(z, hl, mean, rstd);
-    for (int i = hl; i < FRAME16; i += 16)
-      x[i] = __ldg(a + off + i) + ((z[i] - mean) * rstd * __ldg(pln_w + i) + __ldg(pln_b + i));
-  } else {
-    for (int i = hl; i < FRAME16; i += 16) x[i] = __ldg(a + off + i);
-  }
-  __syncwarp();
-
-  {
-    const int g = hl >> 3, dir = (hl >> 2) & 1, j = hl & 3;
-    GruLane<8, 4> cell;
-    cell.load(w.intra[g][dir], j);
-    float h = 0.f;
-    float hv[4] = {0.f, 0.f, 0.f, 0.f};
-    const int src0 = lane & ~3;
-    for (int s = 0; s < E1_F; ++s) {
-      int f = dir ? (E1_F - 1 - s) : s;
-      float xv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) xv[i] = x[(g * 8 + i) * E1_F + f];
-      h = cell.step(xv, hv, h);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) hv[k] = __shfl_sync(0xffffffffu, h, src0 + k);
-      y[f * 16 + hl] = h;     // channel order [g][fwd 4 | bwd 4] == torch.cat in GRNN.forward
-    }
-  }
-  __syncwarp();
-
-  {
-    const int o = hl;
-    float fw[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) fw[k] = __ldg(w.intra_fc_w + o * 16 + k);
-    const float fb = __ldg(w.intra_fc_b + o);
-    for (int f = 0; f < E1_F; ++f) {
-      float acc = fb;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) acc = fmaf(fw[k], y[f * 16 + k], acc);
-      z[o * E1_F + f] = acc;
-    }
-  }
-  __syncwarp();
-  float mean, rstd;
-  frame_stats(z, hl, mean, rstd);
-  if (live) {
-    for (int i = hl; i < FRAME16; i += 16)
-      out[off + i] = x[i] + ((z[i] - mean) * rstd * __ldg(w.intra_ln_w + i) + __ldg(w.intra_ln_b + i));
-  }
-}
-
-// =================================================================================
-// dp_inter: uni-directional grouped GRU over T for every (chunk, f), then FC.  One CTA per
-// chunk; thread = (f, group, hidden unit); frames stream through a double-buffered smem
-// stage so global traffic is one coalesced 2112-byte frame in and out per step.
-// =================================================================================
-constexpr int DX_THREADS = 544;   // 33*16 = 528 workers, rounded to warps
-
-__global__ void __launch_bounds__(DX_THREADS)
-dp_inter_kernel(const DpW w, const float* __restrict__ xin, float* __restrict__ zout, int T) {
-  __shared__ float xbuf[2][FRAME16];
-  __shared__ float zbuf[2][FRAME16];
-  const int tid = threadIdx.x, b = blockIdx.x;
-  const bool worker = tid < FRAME16;
-  const int f = worker ? (tid >> 4) : 0;
-  const int hl = tid & 15, g = hl >> 3, j = hl & 7;
-  const float* xb = xin + (long long)b * T * FRAME16;
-  float* zb = zout + (long long)b * T * FRAME16;
-
-  GruLane<8, 8> cell;
-  cell.load(w.inter[g], j);
-  float fw[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) fw[k] = __ldg(w.inter_fc_w + hl * 16 + k);
-  const float fb = __ldg(w.inter_fc_b + hl);
-
-  if (worker) xbuf[0][tid] = __ldg(xb + tid);
-  __syncthreads();
-
-  float h = 0.f;
-  float hv[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) hv[k] = 0.f;
-  const int half_base = (threadIdx.x & 31) & 16;
-
-  for (int t = 0; t < T; ++t) {
-    const int cur = t & 1;
-    float nxt = 0.f;
-    if (worker && t + 1 < T) nxt = __ldg(xb + (long long)(t + 1) * FRAME16 + tid);
-    float xv[8], hg[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      xv[i] = xbuf[cur][(g * 8 + i) * E1_F + f];
-      hg[i] = g ? hv[8 + i] : hv[i];
-    }
-    h = cell.step(xv, hg, h);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) hv[k] = __shfl_sync(0xffffffffu, h, half_base + k);
-    float acc = fb;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) acc = fmaf(fw[k], hv[k], acc);
-    if (worker) {
-      zbuf[cur][hl * E1_F + f] = acc;
-      xbuf[cur ^ 1][tid] = nxt;
-    }
-    __syncthreads();
-    if (worker) zb[(long long)t * FRAME16 + tid] = zbuf[cur][tid];
-  }
-}
-
-// =================================================================================
-// ln_res: out = a + LN(z) (+ skip).  Half-warp per frame.
-// =================================================================================
-__global__ void __launch_bounds__(128)
-ln_res_kernel(const float* __restrict__ a, const float* __restrict__ zin, const float* __restrict__ ln_w,
-              const float* __restrict__ ln_b, const float* __restrict__ skip, float* __restrict__ out,
-              int nframes) {
-  __shared__ float zs[8][FRAME16];
-  const int lane = threadIdx.x & 31, hl = lane & 15;
-  const int fi = (threadIdx.x >> 5) * 2 + (lane >> 4);
-  const long long fg = (long long)blockIdx.x * 8 + fi;
-  const bool live = fg < nframes;
-  const long long off = (live ? fg : 0) * FRAME16;
-  float* z = zs[fi];
-  for (int i = hl; i < FRAME16; i += 16) z[i] = __ldg(zin + off + i);
-  __syncwarp();
-  float mean, rstd;
-  frame_stats(z, hl, mean, rstd);
-  if (live) {
-    for (int i = hl; i < FRAME16; i += 16) {
-      float v = __ldg(a + off + i) + ((z[i] - mean) * rstd * __ldg(ln_w + i) + __ldg(ln_b + i));
-      if (skip) v += __ldg(skip + off + i);
-      out[off + i] = v;
-    }
-  }
-}
-
-// =================================================================================
 // dec_tail: de_convs.3 (ConvT 16->16,(1,5),s2,g2)+PReLU, +e0, de_convs.4 (ConvT 16->2)+tanh,
 // ERB.bs, complex ratio mask on the noisy spectrum -> enhanced spectrum frame.
 // Transposed conv (stride 2, pad 2): out[g] += in[i]*w[k] with g = 2i + k - 2.
@@ -652,7 +368,7 @@ constexpr int DT_THREADS = 288;
 __global__ void __launch_bounds__(DT_THREADS)
 dec_tail_kernel(const __grid_constant__ DecTailW w, const ErbW erb, const float* __restrict__ xin,
                 const float* __restrict__ e0, const float* __restrict__ spec, float* __restrict__ enh,
-                int T, int nframes, int pad_frames) {
+                float* __restrict__ enh_hi, float* __restrict__ enh_lo, int T, int nframes, int pad_frames) {
   __shared__ float xs[DT_FR][16][E1_F + 2];      // zero column each side
   __shared__ float ys[DT_FR][16][E0_F + 2];      // d3 + e0, zero column each side
   __shared__ float ms[DT_FR][2][ERB_F];
@@ -732,9 +448,14 @@ dec_tail_kernel(const __grid_constant__ DecTailW w, const ErbW erb, const float*
     long long b = fg / T, t = fg - b * T;
     float re = __ldg(spec + fg * SPEC_LD + f), im = __ldg(spec + fg * SPEC_LD + FB + f);
     float m0 = mf[fr][0][f], m1 = mf[fr][1][f];
-    float* o = enh + (b * (T + 2 * pad_frames) + pad_frames + t) * SPEC_LD;
-    o[f] = re * m0 - im * m1;
-    o[FB + f] = im * m0 + re * m1;
+    const long long base = (b * (T + 2 * pad_frames) + pad_frames + t) * SPEC_LD;
+    const float er = re * m0 - im * m1, ei = im * m0 + re * m1;
+    enh[base + f] = er;
+    enh[base + FB + f] = ei;
+    if (enh_hi) {
+      split_tf32_store(er, enh_hi, enh_lo, base + f);
+      split_tf32_store(ei, enh_hi, enh_lo, base + FB + f);
+    }
   }
 }
 
@@ -754,32 +475,29 @@ int launch_backbone(const Weights& w, const Buffers& buf, const Dims& d, int enh
   TICK("enc_front");
 
   const int dil_enc[3] = {1, 2, 5};
-  const size_t tra_smem = (size_t)T * 8 * sizeof(float);
   for (int i = 0; i < 3; ++i) {
     int dl = dil_enc[i];
     int nkmax = (T + dl - 1) / dl;
     dim3 grid((nkmax + GT_KT - 1) / GT_KT, dl, B);
     gt_main_kernel<<<grid, GT_THREADS, 0, st>>>(w.enc_gt[i], buf.e[i + 1], buf.h1, buf.zt, T, dl);
     TICK("gt_main");
-    tra_apply_kernel<<<B, TRA_THREADS, tra_smem, st>>>(w.enc_tra[i], buf.zt, buf.h1, buf.e[i + 1], nullptr,
-                                                      buf.e[i + 2], T);
+    launch_tra_gru(w.enc_tra[i], buf.zt, buf.at, B, T, st);
+    TICK("tra_gru");
+    launch_tra_apply(buf.at, buf.h1, buf.e[i + 1], nullptr, buf.e[i + 2], B, T, st);
     TICK("tra_apply");
   }
 
   // DPGRNN x2: x = e4
-  dp_intra_kernel<<<(nframes + DI_FRAMES - 1) / DI_FRAMES, DI_FRAMES * 16, 0, st>>>(
-      w.dp[0], buf.e[4], nullptr, nullptr, nullptr, buf.xa, nframes);
+  launch_dp_intra(w.dp[0], buf.e[4], nullptr, nullptr, buf.xa, buf.gi, nframes, st);
   TICK("dp_intra");
-  dp_inter_kernel<<<B, DX_THREADS, 0, st>>>(w.dp[0], buf.xa, buf.inter, T);
+  launch_dp_inter(w.dp[0], buf.gi, buf.inter, B, T, st);
   TICK("dp_inter");
-  dp_intra_kernel<<<(nframes + DI_FRAMES - 1) / DI_FRAMES, DI_FRAMES * 16, 0, st>>>(
-      w.dp[1], buf.xa, buf.inter, w.dp[0].inter_ln_w, w.dp[0].inter_ln_b, buf.xb, nframes);
+  launch_dp_intra(w.dp[1], buf.xa, buf.inter, &w.dp[0], buf.xb, buf.gi, nframes, st);
   TICK("dp_intra");
-  dp_inter_kernel<<<B, DX_THREADS, 0, st>>>(w.dp[1], buf.xb, buf.inter, T);
+  launch_dp_inter(w.dp[1], buf.gi, buf.inter, B, T, st);
   TICK("dp_inter");
   // decoder input 0 = dp2 output + e4
-  ln_res_kernel<<<(nframes + 7) / 8, 128, 0, st>>>(buf.xb, buf.inter, w.dp[1].inter_ln_w, w.dp[1].inter_ln_b,
-                                                   buf.e[4], buf.xa, nframes);
+  launch_ln_res(w.dp[1], buf.xb, buf.inter, buf.e[4], buf.xa, nframes, st);
   TICK("ln_res");
 
   const int dil_dec[3] = {5, 2, 1};
@@ -792,12 +510,15 @@ int launch_backbone(const Weights& w, const Buffers& buf, const Dims& d, int enh
     gt_main_kernel<<<grid, GT_THREADS, 0, st>>>(w.dec_gt[i], cur, buf.h1, buf.zt, T, dl);
     TICK("gt_main");
     // next stage input = this block's output + encoder skip (e3, e2, e1)
-    tra_apply_kernel<<<B, TRA_THREADS, tra_smem, st>>>(w.dec_tra[i], buf.zt, buf.h1, cur, buf.e[3 - i], nxt, T);
+    launch_tra_gru(w.dec_tra[i], buf.zt, buf.at, B, T, st);
+    TICK("tra_gru");
+    launch_tra_apply(buf.at, buf.h1, cur, buf.e[3 - i], nxt, B, T, st);
     TICK("tra_apply");
     float* tmp = cur; cur = nxt; nxt = tmp;
   }
   dec_tail_kernel<<<(nframes + DT_FR - 1) / DT_FR, DT_THREADS, 0, st>>>(w.dec_tail, w.erb, cur, buf.e0, buf.spec,
-                                                                      buf.enh, T, nframes, enh_pad_frames);
+                                                                      buf.enh, buf.enh_hi, buf.enh_lo, T, nframes,
+                                                                      enh_pad_frames);
   TICK("dec_tail");
   return n;
 }

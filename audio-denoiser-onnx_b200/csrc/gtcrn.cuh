@@ -92,10 +92,16 @@ struct Buffers {            // all fp32, frame-major: (B, T, C, F) with F innerm
   float* e0;                // (B, T, 16, 65)
   float* e[5];              // e[1..4]: (B, T, 16, 33) encoder skips; e[0] unused
   float* h1;                // (B, T, 8, 33) GTConvBlock output before TRA
-  float* zt;                // (B, T, 8)
+  float* zt;                // (B, T, 8)   TRA energies
+  float* at;                // (B, T, 8)   TRA gates
+  float* gi;                // (B, T, 3, 33, 16) inter-GRU input projections
+  float* xp_hi;             // tf32 hi/lo planes of xp / enh for the tensor-core GEMMs (may be null)
+  float* xp_lo;
+  float* enh_hi;
+  float* enh_lo;
   float* xa;                // (B, T, 16, 33) ping
   float* xb;                // (B, T, 16, 33) pong
-  float* inter;             // (B, T, 16, 33) inter-path FC output (pre-LN)
+  float* inter;             // (B, T, 33, 16) inter-path GRU output h (pre-Linear/LN)
   float* enh;               // (B, T + 2*(R-1), 520) enhanced spectrum, zero frames around
 };
 
@@ -114,7 +120,24 @@ int launch_backbone(const Weights& w, const Buffers& buf, const Dims& d, int enh
 
 // Input conditioning (cast, 1/32768, DC removal, centre pad): Export_GTCRN.py:637-647 +
 // STFT_Process.py:305-309.
-void launch_prep(const void* in, int in_dtype, float* xp, int B, int L, int Lp, int half,
+// hi/lo (nullable): additionally emit the 3xTF32 operand planes.
+void launch_prep(const void* in, int in_dtype, float* xp, float* hi, float* lo, int B, int L, int Lp, int half,
                  int remove_dc, int reflect, cudaStream_t st);
+
+// recurrent stages (gtcrn_rnn.cu)
+void launch_tra_gru(const TraW& w, const float* zt, float* at, int B, int T, cudaStream_t st);
+void launch_tra_apply(const float* at, const float* h1, const float* xin, const float* skip, float* out, int B,
+                      int T, cudaStream_t st);
+void launch_dp_intra(const DpW& w, const float* a, const float* hprev, const DpW* prev, float* out, float* gi,
+                     int nframes, cudaStream_t st);
+void launch_dp_inter(const DpW& w, const float* gi, float* hout, int B, int T, cudaStream_t st);
+void launch_ln_res(const DpW& w, const float* a, const float* hin, const float* skip, float* out, int nframes,
+                   cudaStream_t st);
+
+__device__ __forceinline__ void split_tf32_store(float v, float* hi, float* lo, long long i) {
+  const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  hi[i] = h;
+  lo[i] = v - h;
+}
 
 }  // namespace gtcrn

@@ -1,0 +1,376 @@
+// GTCRN recurrent stages: TRA attention GRU, grouped dual-path GRUs, LayerNorm glue.
+// Reference: GTCRN/Export_GTCRN.py  TRA :144-156, GRNN :409-428, DPGRNN :466-481.
+//
+// All GRUs are tiny (hidden 4/8/16) and strictly serial along their sequence axis, so the
+// design goal is (1) many independent sequences resident per SM, (2) the shortest possible
+// dependent chain per step.  Each hidden unit is one lane; the hidden vector is exchanged with
+// warp shuffles; weights live in registers.  Everything that does not depend on h_{t-1}
+// (input projections W_ih x + b_ih, the Linear after the GRU) is hoisted into the neighbouring
+// frame-parallel kernels.
+#include "adn.h"
+#include "gtcrn.cuh"
+
+namespace gtcrn {
+
+// GRU activations: exp via ex2.approx (rel. err ~2^-21); abs. error of the gate values ~1e-7,
+// far inside the 1e-4 waveform budget.
+__device__ __forceinline__ float sigm(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_e(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+
+template <int H>
+struct GruH {          // recurrent half of one hidden unit: W_hh rows (r,z,n) + b_hh
+  float wh[3][H];
+  float bh[3];
+  __device__ void load(const GruPtrs& p, int j) {
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+#pragma unroll
+      for (int k = 0; k < H; ++k) wh[g][k] = __ldg(p.w_hh + (g * H + j) * H + k);
+      bh[g] = __ldg(p.b_hh + g * H + j);
+    }
+  }
+  // gi: precomputed W_ih x + b_ih for (r,z,n); hv: previous hidden vector; hself: own entry
+  __device__ __forceinline__ float step(float gir, float giz, float gin, const float (&hv)[H], float hself) const {
+    float gh[3];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      float a0 = bh[g], a1 = 0.f;     // two partial sums halve the dependent FMA chain
+#pragma unroll
+      for (int k = 0; k < H; k += 2) {
+        a0 = fmaf(wh[g][k], hv[k], a0);
+        a1 = fmaf(wh[g][k + 1], hv[k + 1], a1);
+      }
+      gh[g] = a0 + a1;
+    }
+    const float r = sigm(gir + gh[0]);
+    const float z = sigm(giz + gh[1]);
+    const float n = tanh_e(gin + r * gh[2]);
+    return (1.0f - z) * n + z * hself;
+  }
+};
+
+template <int I, int H>
+struct GruI {          // input half: W_ih rows (r,z,n) + b_ih of one hidden unit
+  float wi[3][I];
+  float bi[3];
+  __device__ void load(const GruPtrs& p, int j) {
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+#pragma unroll
+      for (int i = 0; i < I; ++i) wi[g][i] = __ldg(p.w_ih + (g * H + j) * I + i);
+      bi[g] = __ldg(p.b_ih + g * H + j);
+    }
+  }
+  __device__ __forceinline__ float proj(int g, const float (&x)[I]) const {
+    float a = bi[g];
+#pragma unroll
+    for (int i = 0; i < I; ++i) a = fmaf(wi[g][i], x[i], a);
+    return a;
+  }
+};
+
+// =================================================================================
+// tra_gru: attention GRU(8->16) over T + Linear(16->8) + sigmoid  ->  at (B,T,8).
+// One half-warp per chunk, 8 chunks per CTA: every chunk of the batch is resident at once.
+// =================================================================================
+constexpr int TG_THREADS = 128;
+
+__global__ void __launch_bounds__(TG_THREADS)
+tra_gru_kernel(const TraW w, const float* __restrict__ zt, float* __restrict__ at, int B, int T) {
+  const int lane = threadIdx.x & 31, hl = lane & 15;
+  int b = (blockIdx.x * TG_THREADS + threadIdx.x) >> 4;
+  const bool live = b < B;
+  if (!live) b = B - 1;
+  const float* z = zt + (long long)b * T * 8;
+  float* a_out = at + (long long)b * T * 8;
+
+  GruI<8, 16> in;
+  GruH<16> rec;
+  in.load(w.gru, hl);
+  rec.load(w.gru, hl);
+  float fw[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) fw[k] = __ldg(w.fc_w + (hl & 7) * 16 + k);
+  const float fb = __ldg(w.fc_b + (hl & 7));
+
+  float h = 0.f, hv[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) hv[k] = 0.f;
+  const int src0 = lane & 16;
+
+  float4 xa = __ldg(reinterpret_cast<const float4*>(z));
+  float4 xb = __ldg(reinterpret_cast<const float4*>(z) + 1);
+  for (int t = 0; t < T; ++t) {
+    const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+    if (t + 1 < T) {
+      xa = __ldg(reinterpret_cast<const float4*>(z + (t + 1) * 8));
+      xb = __ldg(reinterpret_cast<const float4*>(z + (t + 1) * 8) + 1);
+    }
+    h = rec.step(in.proj(0, x), in.proj(1, x), in.proj(2, x), hv, h);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) hv[k] = __shfl_sync(0xffffffffu, h, src0 + k);
+    float a = fb;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a = fmaf(fw[k], hv[k], a);
+    if (live && hl < 8) a_out[t * 8 + hl] = adn_sigmoid(a);
+  }
+}
+
+// =================================================================================
+// tra_apply: out[2c] = h1[c]*at[c], out[2c+1] = x2[c]  (channel shuffle :324), + optional
+// decoder skip.  Pure streaming kernel.
+// =================================================================================
+__global__ void __launch_bounds__(256)
+tra_apply_kernel(const float* __restrict__ at, const float* __restrict__ h1, const float* __restrict__ xin,
+                 const float* __restrict__ skip, float* __restrict__ out, long long nframes) {
+  const long long total = nframes * FRAME16;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long fr = i / FRAME16;
+    const int rem = (int)(i - fr * FRAME16);
+    const int ch = rem / E1_F, f = rem - ch * E1_F;
+    const int c = ch >> 1;
+    float v;
+    if (ch & 1) v = __ldg(xin + fr * FRAME16 + (8 + c) * E1_F + f);
+    else v = __ldg(h1 + fr * (8 * E1_F) + c * E1_F + f) * __ldg(at + fr * 8 + c);
+    if (skip) v += __ldg(skip + i);
+    out[i] = v;
+  }
+}
+
+// =================================================================================
+// Per-frame LayerNorm((33,16), eps=1e-8) on a half-warp (16 lanes); z holds 528 values.
+// =================================================================================
+__device__ __forceinline__ float half_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void frame_stats(const float* z, int hl, float& mean, float& rstd) {
+  float s = 0.f;
+  for (int i = hl; i < FRAME16; i += 16) s += z[i];
+  mean = half_sum(s) * (1.0f / FRAME16);
+  float q = 0.f;
+  for (int i = hl; i < FRAME16; i += 16) {
+    const float d = z[i] - mean;
+    q = fmaf(d, d, q);
+  }
+  rstd = 1.0f / sqrtf(half_sum(q) * (1.0f / FRAME16) + 1e-8f);
+}
+
+// y (smem, [f][16]) -> z (smem, [c][f]) = Linear(16->16): lane o owns output channel o
+__device__ __forceinline__ void frame_fc(const float* y, float* z, const float* __restrict__ fc_w,
+                                         const float* __restrict__ fc_b, int o) {
+  float fw[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) fw[k] = __ldg(fc_w + o * 16 + k);
+  const float fb = __ldg(fc_b + o);
+  for (int f = 0; f < E1_F; ++f) {
+    const float4* yv = reinterpret_cast<const float4*>(y + f * 16);
+    float acc = fb;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 v = yv[q];
+      acc = fmaf(fw[4 * q + 0], v.x, acc);
+      acc = fmaf(fw[4 * q + 1], v.y, acc);
+      acc = fmaf(fw[4 * q + 2], v.z, acc);
+      acc = fmaf(fw[4 * q + 3], v.w, acc);
+    }
+    z[o * E1_F + f] = acc;
+  }
+}
+
+// =================================================================================
+// dp_intra: x = a (+ LN(FC(h_prev)))  ;  bi-GRU over F in 2 groups ; FC ; LN ; out = x + LN(.)
+// and the inter-path input projections gi = W_ih out + b_ih for the following dp_inter.
+// One half-warp per frame: lane = (group, direction, hidden unit) = 2*2*4.
+// =================================================================================
+constexpr int DI_FRAMES = 4;     // frames per CTA (2 warps)
+
+__global__ void __launch_bounds__(DI_FRAMES * 16)
+dp_intra_kernel(const DpW w, const float* __restrict__ a, const float* __restrict__ hprev,
+                const float* __restrict__ pfc_w, const float* __restrict__ pfc_b,
+                const float* __restrict__ pln_w, const float* __restrict__ pln_b,
+                float* __restrict__ out, float* __restrict__ gi_out, int nframes) {
+  __shared__ __align__(16) float xs[DI_FRAMES][FRAME16];     // [c][f]
+  __shared__ __align__(16) float ys[DI_FRAMES][E1_F * 16];   // [f][16]
+  __shared__ __align__(16) float zs[DI_FRAMES][FRAME16];     // [c][f]
+
+  const int lane = threadIdx.x & 31, hl = lane & 15;
+  const int fi = (threadIdx.x >> 5) * 2 + (lane >> 4);
+  const long long fg = (long long)blockIdx.x * DI_FRAMES + fi;
+  const bool live = fg < nframes;
+  const long long off = (live ? fg : 0) * FRAME16;
+  float* x = xs[fi];
+  float* y = ys[fi];
+  float* z = zs[fi];
+
+  if (hprev) {
+    // previous DPGRNN's inter path: h ([f][16]) -> Linear -> LayerNorm -> + residual (:479-481)
+    for (int i = hl; i < FRAME16; i += 16) y[i] = __ldg(hprev + off + i);
+    __syncwarp();
+    frame_fc(y, z, pfc_w, pfc_b, hl);
+    __syncwarp();
+    float mean, rstd;
+    frame_stats(z, hl, mean, rstd);
+    for (int i = hl; i < FRAME16; i += 16)
+      x[i] = __ldg(a + off + i) + ((z[i] - mean) * rstd * __ldg(pln_w + i) + __ldg(pln_b + i));
+  } else {
+    for (int i = hl; i < FRAME16; i += 16) x[i] = __ldg(a + off + i);
+  }
+  __syncwarp();
+
+  {
+    const int g = hl >> 3, dir = (hl >> 2) & 1, j = hl & 3;
+    GruI<8, 4> in;
+    GruH<4> rec;
+    in.load(w.intra[g][dir], j);
+    rec.load(w.intra[g][dir], j);
+    float h = 0.f;
+    float hv[4] = {0.f, 0.f, 0.f, 0.f};
+    const int src0 = lane & ~3;
+    for (int s = 0; s < E1_F; ++s) {
+      const int f = dir ? (E1_F - 1 - s) : s;
+      float xv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xv[i] = x[(g * 8 + i) * E1_F + f];
+      h = rec.step(in.proj(0, xv), in.proj(1, xv), in.proj(2, xv), hv, h);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) hv[k] = __shfl_sync(0xffffffffu, h, src0 + k);
+      y[f * 16 + hl] = h;     // channel order [g][fwd 4 | bwd 4] == torch.cat in GRNN.forward
+    }
+  }
+  __syncwarp();
+  frame_fc(y, z, w.intra_fc_w, w.intra_fc_b, hl);
+  __syncwarp();
+  float mean, rstd;
+  frame_stats(z, hl, mean, rstd);
+  for (int i = hl; i < FRAME16; i += 16) {
+    const float v = x[i] + ((z[i] - mean) * rstd * __ldg(w.intra_ln_w + i) + __ldg(w.intra_ln_b + i));
+    x[i] = v;
+    if (live) out[off + i] = v;
+  }
+  __syncwarp();
+
+  // inter-path input projections for every (f, group, unit): gi[gate][f][16]
+  {
+    const int g = hl >> 3, j = hl & 7;
+    GruI<8, 8> in;
+    in.load(w.inter[g], j);
+    float* go = gi_out + (live ? fg : 0) * (3 * FRAME16);
+    for (int f = 0; f < E1_F; ++f) {
+      float xv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xv[i] = x[(g * 8 + i) * E1_F + f];
+      if (live) {
+#pragma unroll
+        for (int gate = 0; gate < 3; ++gate) go[gate * FRAME16 + f * 16 + hl] = in.proj(gate, xv);
+      }
+    }
+  }
+}
+
+// =================================================================================
+// dp_inter: uni-directional grouped GRU(8->8) over T for every (chunk, f, group).  Pure
+// recurrence on precomputed input projections; thread = (chunk, f, group, unit); 16-lane groups
+// are independent, so there is no block-level synchronisation and no shared memory.
+// Output h in [t][f][16] order (coalesced; the consumer applies the Linear).
+// =================================================================================
+__global__ void __launch_bounds__(256)
+dp_inter_kernel(const DpW w, const float* __restrict__ gi, float* __restrict__ hout, int B, int T) {
+  const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;   // over B*528
+  const int lane = threadIdx.x & 31;
+  long long b = gid / FRAME16;
+  int e = (int)(gid - b * FRAME16);          // f*16 + hl
+  const bool live = b < B;
+  if (!live) { b = B - 1; }
+  const int hl = e & 15, g = hl >> 3, j = hl & 7;
+
+  GruH<8> rec;
+  rec.load(w.inter[g], j);
+  const float* gp = gi + (long long)b * T * (3 * FRAME16) + e;
+  float* hp = hout + (long long)b * T * FRAME16 + e;
+
+  float h = 0.f, hv[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) hv[k] = 0.f;
+  const int src0 = lane & ~7;
+
+  float g0 = __ldg(gp), g1 = __ldg(gp + FRAME16), g2 = __ldg(gp + 2 * FRAME16);
+  for (int t = 0; t < T; ++t) {
+    const float c0 = g0, c1 = g1, c2 = g2;
+    if (t + 1 < T) {
+      const float* nx = gp + (long long)(t + 1) * (3 * FRAME16);
+      g0 = __ldg(nx); g1 = __ldg(nx + FRAME16); g2 = __ldg(nx + 2 * FRAME16);
+    }
+    h = rec.step(c0, c1, c2, hv, h);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) hv[k] = __shfl_sync(0xffffffffu, h, src0 + k);
+    if (live) hp[(long long)t * FRAME16] = h;
+  }
+}
+
+// =================================================================================
+// ln_res: out = a + LN(FC(h)) (+ skip): the tail of the last DPGRNN (:479-481) fused with the
+// first decoder skip add (:524).  Half-warp per frame.
+// =================================================================================
+__global__ void __launch_bounds__(128)
+ln_res_kernel(const float* __restrict__ a, const float* __restrict__ hin, const float* __restrict__ fc_w,
+              const float* __restrict__ fc_b, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+              const float* __restrict__ skip, float* __restrict__ out, int nframes) {
+  __shared__ __align__(16) float ys[8][FRAME16];
+  __shared__ __align__(16) float zs[8][FRAME16];
+  const int lane = threadIdx.x & 31, hl = lane & 15;
+  const int fi = (threadIdx.x >> 5) * 2 + (lane >> 4);
+  const long long fg = (long long)blockIdx.x * 8 + fi;
+  const bool live = fg < nframes;
+  const long long off = (live ? fg : 0) * FRAME16;
+  float* y = ys[fi];
+  float* z = zs[fi];
+  for (int i = hl; i < FRAME16; i += 16) y[i] = __ldg(hin + off + i);
+  __syncwarp();
+  frame_fc(y, z, fc_w, fc_b, hl);
+  __syncwarp();
+  float mean, rstd;
+  frame_stats(z, hl, mean, rstd);
+  if (live) {
+    for (int i = hl; i < FRAME16; i += 16) {
+      float v = __ldg(a + off + i) + ((z[i] - mean) * rstd * __ldg(ln_w + i) + __ldg(ln_b + i));
+      if (skip) v += __ldg(skip + off + i);
+      out[off + i] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ launch wrappers
+void launch_tra_gru(const TraW& w, const float* zt, float* at, int B, int T, cudaStream_t st) {
+  tra_gru_kernel<<<(B * 16 + TG_THREADS - 1) / TG_THREADS, TG_THREADS, 0, st>>>(w, zt, at, B, T);
+}
+
+void launch_tra_apply(const float* at, const float* h1, const float* xin, const float* skip, float* out, int B,
+                      int T, cudaStream_t st) {
+  const long long nframes = (long long)B * T;
+  long long blocks = (nframes * FRAME16 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  tra_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(at, h1, xin, skip, out, nframes);
+}
+
+void launch_dp_intra(const DpW& w, const float* a, const float* hprev, const DpW* prev, float* out, float* gi,
+                     int nframes, cudaStream_t st) {
+  dp_intra_kernel<<<(nframes + DI_FRAMES - 1) / DI_FRAMES, DI_FRAMES * 16, 0, st>>>(
+      w, a, hprev, prev ? prev->inter_fc_w : nullptr, prev ? prev->inter_fc_b : nullptr,
+      prev ? prev->inter_ln_w : nullptr, prev ? prev->inter_ln_b : nullptr, out, gi, nframes);
+}
+
+void launch_dp_inter(const DpW& w, const float* gi, float* hout, int B, int T, cudaStream_t st) {
+  const long long n = (long long)B * FRAME16;
+  dp_inter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, gi, hout, B, T);
+}
+
+void launch_ln_res(const DpW& w, const float* a, const float* hin, const float* skip, float* out, int nframes,
+                   cudaStream_t st) {
+  ln_res_kernel<<<(nframes + 7) / 8, 128, 0, st>>>(a, hin, w.inter_fc_w, w.inter_fc_b, w.inter_ln_w, w.inter_ln_b,
+                                                   skip, out, nframes);
+}
+
+}  // namespace gtcrn

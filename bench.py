@@ -51,12 +51,15 @@ def kernel_work():
     return {
         "prep": (CHUNK * 4 + 16512 * 4, 2 * CHUNK),
         "stft_gemm": (16512 * 4 + spec, 2 * 514 * 512 * T),
+        "stft_gemm_tc": (2 * 16512 * 4 + spec, 2 * 514 * 512 * T),
+        "istft_gemm_tc": (2 * spec + L_OUT * 4, 2 * 514 * 512 * T),
         "enc_front": (spec + 16 * 65 * 4 * T + f16, 2 * T * (65 * 720 + 33 * 16 * 40 + 3 * 2 * 192)),
         "gt_main": (f16 // 2 + f16 // 2 + 8 * 4 * T, 2 * T * 33 * (384 + 144 + 128)),
-        "tra_apply": (f16 // 2 + f16 // 2 + f16, 2 * T * (3 * 16 * 24 + 128) + T * 528),
-        "dp_intra": (2 * f16, 2 * T * (33 * 16 * 3 * 12 + 33 * 256) + 8 * T * 528),
-        "dp_inter": (2 * f16, 2 * T * 33 * (16 * 3 * 16 + 256)),
-        "ln_res": (4 * f16, 8 * T * 528),
+        "tra_gru": (2 * 8 * 4 * T, 2 * T * (3 * 16 * 24 + 128)),
+        "tra_apply": (f16 // 2 + f16 // 2 + f16, T * 528),
+        "dp_intra": (2 * f16 + 3 * f16, 2 * T * (33 * 16 * 3 * 12 + 2 * 33 * 256 + 33 * 48 * 8) + 8 * T * 528),
+        "dp_inter": (3 * f16 + f16, 2 * T * 33 * 16 * 3 * 8),
+        "ln_res": (4 * f16, 2 * T * 33 * 256 + 8 * T * 528),
         "dec_tail": (f16 + 16 * 65 * 4 * T + 2 * spec, 2 * T * (65 * 16 * 20 + 129 * 2 * 40 + 2 * 2 * 192 + 4 * 257)),
         "istft_gemm": (spec + L_OUT * 4, 2 * 514 * 512 * T),
     }
