@@ -1,0 +1,74 @@
+"""N>1 path on CPU: world_size-2 gloo run of the batch scatter / run / gather plumbing
+(adn/dist.py) with a stand-in per-chunk function (the CUDA model cannot run here)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _fake_model(x):
+    # independent per chunk, length-changing like GTCRN (16000 -> 15872 becomes L -> L-8)
+    return (x[..., :-8] * 2.0 + x.mean(dim=-1, keepdim=True)).contiguous()
+
+
+def _worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "audio-denoiser-onnx_b200"))
+    from adn import dist as adist
+
+    g = torch.Generator().manual_seed(0)
+    full = torch.randn(n, 1, 64, generator=g)
+    out = adist.run_sharded(_fake_model, full if rank == 0 else None, n, (1, 64), torch.float32, torch.device("cpu"))
+    if rank == 0:
+        q.put(out.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 8])
+def test_sharded_run_matches_single_process(n):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(0)
+    full = torch.randn(n, 1, 64, generator=g)
+    assert got.shape == (n, 1, 56)
+    assert torch.equal(torch.from_numpy(got), _fake_model(full))
+
+
+def test_shard_bounds_cover_everything():
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "audio-denoiser-onnx_b200"))
+    from adn.dist import shard_bounds
+
+    for n in (0, 1, 7, 64, 512, 513):
+        for world in (1, 2, 4, 8):
+            cuts = [shard_bounds(n, world, r) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in cuts]
+            assert max(sizes) - min(sizes) <= 1
