@@ -52,7 +52,7 @@ def _gt_block(sd, p, deconv) -> np.ndarray:
         w1 = w1[:, :, 0, 0]
         w2 = w2[:, :, 0, 0]
         wd = wd[:, 0]
-    parts = [w1.reshape(-1), b1, wd.reshape(-1), bd, w2.reshape(-1), b2,
+    parts = [w1.reshape(-1), b1, wd.reshape(-1), bd, w2.T.contiguous().reshape(-1), b2,   # w2 stored [c][o]
              sd[f"{p}.point_act.weight"].reshape(-1), sd[f"{p}.depth_act.weight"].reshape(-1)]
     out = torch.cat([x.float().reshape(-1) for x in parts])
     assert out.numel() == 16 * 24 + 16 + 144 + 16 + 128 + 8 + 2
@@ -91,8 +91,10 @@ def pack(state_dict: dict, input_audio_length: int) -> dict[str, np.ndarray]:
     # encoder front: en_convs.0 (16,9,1,5) and en_convs.1 (16,8,1,5, groups 2)
     w0, b0 = _fold(sd, "encoder.en_convs.0.conv", "encoder.en_convs.0.bn")
     w1, b1 = _fold(sd, "encoder.en_convs.1.conv", "encoder.en_convs.1.bn")
+    w0p = w0[:, :, 0, :].permute(2, 1, 0).contiguous()                       # (o,ci,k) -> [k][ci][o]
+    w1p = w1[:, :, 0, :].reshape(2, 8, 8, 5).permute(0, 2, 3, 1).contiguous()  # (grp,ol,ci,k) -> [grp][ci][k][ol]
     blob["enc_front"] = _f(torch.cat([
-        w0[:, :, 0, :].reshape(-1), b0, w1[:, :, 0, :].reshape(-1), b1,
+        w0p.reshape(-1), b0, w1p.reshape(-1), b1,
         sd["encoder.en_convs.0.act.weight"].reshape(-1), sd["encoder.en_convs.1.act.weight"].reshape(-1)]))
     assert blob["enc_front"].size == 720 + 16 + 640 + 16 + 2
 
@@ -122,8 +124,10 @@ def pack(state_dict: dict, input_audio_length: int) -> dict[str, np.ndarray]:
     # decoder tail: de_convs.3 ConvT(16->16, groups 2) weight (16, 8, 1, 5); de_convs.4 (16, 2, 1, 5)
     w3, b3 = _fold(sd, "decoder.de_convs.3.conv", "decoder.de_convs.3.bn", True, groups=2)
     w4, b4 = _fold(sd, "decoder.de_convs.4.conv", "decoder.de_convs.4.bn", True)
+    w3p = w3[:, :, 0, :].permute(0, 2, 1).contiguous()   # (ci,ol,k) -> [ci][k][ol]
+    w4p = w4[:, :, 0, :].permute(0, 2, 1).contiguous()   # (ci,o,k)  -> [ci][k][o]
     blob["dec_tail"] = _f(torch.cat([
-        w3[:, :, 0, :].reshape(-1), b3, w4[:, :, 0, :].reshape(-1), b4,
+        w3p.reshape(-1), b3, w4p.reshape(-1), b4,
         sd["decoder.de_convs.3.act.weight"].reshape(-1)]))
     assert blob["dec_tail"].size == 640 + 16 + 160 + 2 + 1
 

@@ -157,7 +157,7 @@ enc_front_kernel(const __grid_constant__ EncFrontW w, const ErbW erb, const floa
         for (int s = 0; s < 3; ++s) {
           float v = pv ? fe[fr][c][4 + p + s - 1] : 0.f;
 #pragma unroll
-          for (int o = 0; o < 16; ++o) acc[o] = fmaf(w.w0[o][c * 3 + s][k], v, acc[o]);
+          for (int o = 0; o < 16; ++o) acc[o] = fmaf(w.w0[k][c * 3 + s][o], v, acc[o]);
         }
       }
     }
@@ -187,7 +187,7 @@ enc_front_kernel(const __grid_constant__ EncFrontW w, const ErbW erb, const floa
         for (int k = 0; k < 5; ++k) {
           float v = e0s[fr][ci][2 * g + k];
 #pragma unroll
-          for (int o = 0; o < 8; ++o) acc[o] = fmaf(w.w1[o][ci][k], v, acc[o]);
+          for (int o = 0; o < 8; ++o) acc[o] = fmaf(w.w1[0][ci][k][o], v, acc[o]);
         }
     } else {
 #pragma unroll
@@ -198,7 +198,7 @@ enc_front_kernel(const __grid_constant__ EncFrontW w, const ErbW erb, const floa
         for (int k = 0; k < 5; ++k) {
           float v = e0s[fr][8 + ci][2 * g + k];
 #pragma unroll
-          for (int o = 0; o < 8; ++o) acc[o] = fmaf(w.w1[8 + o][ci][k], v, acc[o]);
+          for (int o = 0; o < 8; ++o) acc[o] = fmaf(w.w1[1][ci][k][o], v, acc[o]);
         }
     }
     long long fg = f0 + fr;
@@ -211,114 +211,167 @@ enc_front_kernel(const __grid_constant__ EncFrontW w, const ErbW erb, const floa
 
 // =================================================================================
 // gt_main: GTConvBlock up to point_conv2 (+ the TRA energy z_t).  Frames with the same
-// residue t mod d form an undilated causal sequence, so a CTA owns KT consecutive steps
-// of one residue class (+2 recomputed halo frames) of one chunk.
+// residue t mod d form an undilated causal sequence, so a CTA owns KT consecutive steps of
+// one residue class (+2 recomputed halo frames) of one chunk.  Each thread computes TWO
+// frames at one frequency bin, so every weight fetched from the constant bank feeds two
+// FFMAs and the depthwise taps of adjacent steps share their shared-memory loads.
 // =================================================================================
-constexpr int GT_KT = 6;
-constexpr int GT_FL = GT_KT + 2;
-constexpr int GT_THREADS = 288;   // >= GT_FL*33 = 264
+template <int KT>
+struct GtCfg {
+  static constexpr int FL = KT + 2;                       // frames in the tile (2 halo)
+  static constexpr int P1 = FL / 2, P2 = KT / 2;          // frame pairs in phase 1 / 2
+  static constexpr int THREADS = ((P1 * E1_F + 31) / 32) * 32;
+  static constexpr int XS = FL * 8 * (E1_F + 2);          // floats
+  static constexpr int HS = FL * 16 * (E1_F + 2);
+  static constexpr size_t SMEM = (size_t)(XS + HS) * sizeof(float);
+  static_assert(KT % 2 == 0, "pairs");
+  static_assert(KT * 8 * E1_F <= XS, "h1 staging aliases the x tile");
+};
 
-__global__ void __launch_bounds__(GT_THREADS)
+template <int KT>
+__global__ void __launch_bounds__(GtCfg<KT>::THREADS)
 gt_main_kernel(const __grid_constant__ GTW w, const float* __restrict__ xin, float* __restrict__ h1,
                float* __restrict__ zt, int T, int dil) {
-  __shared__ float xs[GT_FL][8][E1_F + 2];     // x1 tile, one zero column each side
-  __shared__ float hs[GT_FL][16][E1_F + 2];    // point_conv1 output tile
-  __shared__ float h1s[GT_KT][8][E1_F];
+  using C = GtCfg<KT>;
+  constexpr int FP = E1_F + 2;
+  extern __shared__ __align__(16) float gt_smem[];
+  float (*xs)[8][FP] = reinterpret_cast<float (*)[8][FP]>(gt_smem);             // [FL][8][35]
+  float (*hs)[16][FP] = reinterpret_cast<float (*)[16][FP]>(gt_smem + C::XS);   // [FL][16][35]
+  float (*h1s)[8][E1_F] = reinterpret_cast<float (*)[8][E1_F]>(gt_smem);        // [KT][8][33], aliases xs
 
   const int tid = threadIdx.x;
   const int r = blockIdx.y, b = blockIdx.z;
   const int nk = (T - r + dil - 1) / dil;      // frames in this residue class
-  const int k0 = blockIdx.x * GT_KT;
+  const int k0 = blockIdx.x * KT;
   if (r >= T || k0 >= nk) return;
   const float* xb = xin + (long long)b * T * FRAME16;
 
-  for (int i = tid; i < GT_FL * 8 * (E1_F + 2); i += GT_THREADS) {
-    int fl = i / (8 * (E1_F + 2)), rem = i - fl * (8 * (E1_F + 2));
-    int c = rem / (E1_F + 2), fp = rem - c * (E1_F + 2);
-    int k = k0 - 2 + fl;
+  // x1 = first 8 channels = first 264 contiguous floats of every frame
+  for (int i = tid; i < C::FL * 264; i += C::THREADS) {
+    const int fl = i / 264, rem = i - fl * 264;
+    const int c = rem / E1_F, f = rem - c * E1_F;
+    const int k = k0 - 2 + fl;
     float v = 0.f;
-    if (k >= 0 && k < nk && fp >= 1 && fp <= E1_F) {
-      int t = r + k * dil;
-      v = __ldg(xb + (long long)t * FRAME16 + c * E1_F + (fp - 1));
-    }
-    xs[fl][c][fp] = v;
+    if (k >= 0 && k < nk) v = __ldg(xb + (long long)(r + k * dil) * FRAME16 + rem);
+    xs[fl][c][f + 1] = v;
   }
-  for (int i = tid; i < GT_FL * 16; i += GT_THREADS) {
-    hs[i / 16][i % 16][0] = 0.f;
-    hs[i / 16][i % 16][E1_F + 1] = 0.f;
+  for (int i = tid; i < C::FL * 8; i += C::THREADS) {
+    xs[i >> 3][i & 7][0] = 0.f;
+    xs[i >> 3][i & 7][FP - 1] = 0.f;
   }
-  __syncthreads();
-
-  // phase 1: SFE(k=3) + point_conv1 (24->16) + PReLU.  Frames before the chunk start are the
-  // causal zero padding of the depthwise conv's INPUT (:314-318), i.e. exact zeros.
-  if (tid < GT_FL * E1_F) {
-    int fl = tid / E1_F, f = tid - fl * E1_F;
-    int k = k0 - 2 + fl;
-    float acc[16];
-    if (k >= 0 && k < nk) {
-      float in[24];
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-#pragma unroll
-        for (int s = 0; s < 3; ++s) in[c * 3 + s] = xs[fl][c][f + s];
-#pragma unroll
-      for (int o = 0; o < 16; ++o) {
-        float a = w.b1[o];
-#pragma unroll
-        for (int i = 0; i < 24; ++i) a = fmaf(w.w1[o][i], in[i], a);
-        acc[o] = adn_prelu(a, w.a1);
-      }
-    } else {
-#pragma unroll
-      for (int o = 0; o < 16; ++o) acc[o] = 0.f;
-    }
-#pragma unroll
-    for (int o = 0; o < 16; ++o) hs[fl][o][f + 1] = acc[o];
+  for (int i = tid; i < C::FL * 16; i += C::THREADS) {
+    hs[i >> 4][i & 15][0] = 0.f;
+    hs[i >> 4][i & 15][FP - 1] = 0.f;
   }
   __syncthreads();
 
-  // phase 2: depthwise (3,3) dilated causal conv + PReLU + point_conv2 (16->8)
-  if (tid < GT_KT * E1_F) {
-    int kl = tid / E1_F, f = tid - kl * E1_F;
-    int k = k0 + kl;
-    if (k < nk) {
-      float acc[8];
+  // phase 1: SFE(k=3) + point_conv1 (24->16) + PReLU for frames (2p, 2p+1).  Frames before the
+  // chunk start are the causal zero padding of the depthwise conv's INPUT (:314-318): exact zeros.
+  if (tid < C::P1 * E1_F) {
+    const int p = tid / E1_F, f = tid - p * E1_F;
+    const int fl0 = 2 * p, fl1 = fl0 + 1;
+    const int ka = k0 - 2 + fl0, kb = ka + 1;
+    float in0[24], in1[24];
 #pragma unroll
-      for (int o = 0; o < 8; ++o) acc[o] = w.b2[o];
+    for (int c = 0; c < 8; ++c)
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        float d = w.bd[c];
-#pragma unroll
-        for (int kt = 0; kt < 3; ++kt)
-#pragma unroll
-          for (int kf = 0; kf < 3; ++kf) d = fmaf(w.wd[c][kt][kf], hs[kl + kt][c][f + kf], d);
-        d = adn_prelu(d, w.ad);
-#pragma unroll
-        for (int o = 0; o < 8; ++o) acc[o] = fmaf(w.w2[o][c], d, acc[o]);
+      for (int s = 0; s < 3; ++s) {
+        in0[c * 3 + s] = xs[fl0][c][f + s];
+        in1[c * 3 + s] = xs[fl1][c][f + s];
       }
-      int t = r + k * dil;
-      float* ho = h1 + ((long long)b * T + t) * (8 * E1_F);
+    const bool va = (ka >= 0 && ka < nk), vb = (kb >= 0 && kb < nk);
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+      float a0 = w.b1[o], a1 = w.b1[o];
+#pragma unroll
+      for (int i = 0; i < 24; ++i) {
+        a0 = fmaf(w.w1[o][i], in0[i], a0);
+        a1 = fmaf(w.w1[o][i], in1[i], a1);
+      }
+      hs[fl0][o][f + 1] = va ? adn_prelu(a0, w.a1) : 0.f;
+      hs[fl1][o][f + 1] = vb ? adn_prelu(a1, w.a1) : 0.f;
+    }
+  }
+  __syncthreads();
+
+  // phase 2: depthwise (3,3) dilated causal conv + PReLU + point_conv2 (16->8) for steps (2q, 2q+1)
+  if (tid < C::P2 * E1_F) {
+    const int q = tid / E1_F, f = tid - q * E1_F;
+    const int kl = 2 * q;
+    float acc0[8], acc1[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) { acc0[o] = w.b2[o]; acc1[o] = w.b2[o]; }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float v[4][3];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int kf = 0; kf < 3; ++kf) v[j][kf] = hs[kl + j][c][f + kf];
+      float d0 = w.bd[c], d1 = w.bd[c];
+#pragma unroll
+      for (int kt = 0; kt < 3; ++kt)
+#pragma unroll
+        for (int kf = 0; kf < 3; ++kf) {
+          d0 = fmaf(w.wd[c][kt][kf], v[kt][kf], d0);
+          d1 = fmaf(w.wd[c][kt][kf], v[kt + 1][kf], d1);
+        }
+      d0 = adn_prelu(d0, w.ad);
+      d1 = adn_prelu(d1, w.ad);
 #pragma unroll
       for (int o = 0; o < 8; ++o) {
-        ho[o * E1_F + f] = acc[o];
-        h1s[kl][o][f] = acc[o];
+        acc0[o] = fmaf(w.w2[c][o], d0, acc0[o]);
+        acc1[o] = fmaf(w.w2[c][o], d1, acc1[o]);
       }
+    }
+    const int ka = k0 + kl, kb = ka + 1;
+    if (ka < nk) {
+      float* ho = h1 + ((long long)b * T + (r + ka * dil)) * (8 * E1_F);
+#pragma unroll
+      for (int o = 0; o < 8; ++o) { ho[o * E1_F + f] = acc0[o]; h1s[kl][o][f] = acc0[o]; }
+    }
+    if (kb < nk) {
+      float* ho = h1 + ((long long)b * T + (r + kb * dil)) * (8 * E1_F);
+#pragma unroll
+      for (int o = 0; o < 8; ++o) { ho[o * E1_F + f] = acc1[o]; h1s[kl + 1][o][f] = acc1[o]; }
     }
   }
   __syncthreads();
 
   // phase 3: z_t[c] = mean_f h1^2 (TRA input, :154)
-  if (tid < GT_KT * 8) {
-    int kl = tid >> 3, c = tid & 7;
-    int k = k0 + kl;
+  if (tid < KT * 8) {
+    const int kl = tid >> 3, c = tid & 7;
+    const int k = k0 + kl;
     if (k < nk) {
       float s = 0.f;
 #pragma unroll
       for (int f = 0; f < E1_F; ++f) s = fmaf(h1s[kl][c][f], h1s[kl][c][f], s);
-      int t = r + k * dil;
-      zt[((long long)b * T + t) * 8 + c] = s / (float)E1_F;
+      zt[((long long)b * T + (r + k * dil)) * 8 + c] = s / (float)E1_F;
     }
   }
+}
+
+template <int KT>
+static void launch_gt_main_t(const GTW& w, const float* xin, float* h1, float* zt, int B, int T, int dil,
+                             cudaStream_t st) {
+  using C = GtCfg<KT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(gt_main_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    configured = true;
+  }
+  const int nkmax = (T + dil - 1) / dil;
+  dim3 grid((nkmax + KT - 1) / KT, dil, B);
+  gt_main_kernel<KT><<<grid, C::THREADS, C::SMEM, st>>>(w, xin, h1, zt, T, dil);
+}
+
+static void launch_gt_main(const GTW& w, const float* xin, float* h1, float* zt, int B, int T, int dil,
+                           cudaStream_t st) {
+  // pick the tile length that wastes the fewest steps of the residue classes
+  const int nk = (T + dil - 1) / dil;
+  const int waste16 = (nk + 15) / 16 * 16 - nk, waste14 = (nk + 13) / 14 * 14 - nk;
+  if (waste14 < waste16) launch_gt_main_t<14>(w, xin, h1, zt, B, T, dil, st);
+  else launch_gt_main_t<16>(w, xin, h1, zt, B, T, dil, st);
 }
 
 // =================================================================================
@@ -340,7 +393,7 @@ __device__ __forceinline__ void deconv3_taps(const DecTailW& w, const float (*x)
     for (int ci = 0; ci < 8; ++ci) {
       float v = x[GRP * 8 + ci][i + 1];
 #pragma unroll
-      for (int o = 0; o < 8; ++o) acc[o] = fmaf(w.w3[GRP * 8 + ci][o][k], v, acc[o]);
+      for (int o = 0; o < 8; ++o) acc[o] = fmaf(w.w3[GRP * 8 + ci][k][o], v, acc[o]);
     }
   }
 }
@@ -356,8 +409,8 @@ __device__ __forceinline__ void deconv4_taps(const DecTailW& w, const float (*y)
 #pragma unroll
     for (int ci = 0; ci < 16; ++ci) {
       float v = y[ci][i + 1];
-      a[0] = fmaf(w.w4[ci][0][k], v, a[0]);
-      a[1] = fmaf(w.w4[ci][1][k], v, a[1]);
+      a[0] = fmaf(w.w4[ci][k][0], v, a[0]);
+      a[1] = fmaf(w.w4[ci][k][1], v, a[1]);
     }
   }
 }
@@ -477,9 +530,7 @@ int launch_backbone(const Weights& w, const Buffers& buf, const Dims& d, int enh
   const int dil_enc[3] = {1, 2, 5};
   for (int i = 0; i < 3; ++i) {
     int dl = dil_enc[i];
-    int nkmax = (T + dl - 1) / dl;
-    dim3 grid((nkmax + GT_KT - 1) / GT_KT, dl, B);
-    gt_main_kernel<<<grid, GT_THREADS, 0, st>>>(w.enc_gt[i], buf.e[i + 1], buf.h1, buf.zt, T, dl);
+    launch_gt_main(w.enc_gt[i], buf.e[i + 1], buf.h1, buf.zt, B, T, dl, st);
     TICK("gt_main");
     launch_tra_gru(w.enc_tra[i], buf.zt, buf.at, B, T, st);
     TICK("tra_gru");
@@ -505,9 +556,7 @@ int launch_backbone(const Weights& w, const Buffers& buf, const Dims& d, int enh
   float* nxt = buf.xb;
   for (int i = 0; i < 3; ++i) {
     int dl = dil_dec[i];
-    int nkmax = (T + dl - 1) / dl;
-    dim3 grid((nkmax + GT_KT - 1) / GT_KT, dl, B);
-    gt_main_kernel<<<grid, GT_THREADS, 0, st>>>(w.dec_gt[i], cur, buf.h1, buf.zt, T, dl);
+    launch_gt_main(w.dec_gt[i], cur, buf.h1, buf.zt, B, T, dl, st);
     TICK("gt_main");
     // next stage input = this block's output + encoder skip (e3, e2, e1)
     launch_tra_gru(w.dec_tra[i], buf.zt, buf.at, B, T, st);

@@ -15,9 +15,9 @@ constexpr int FRAME_E0 = 16 * E0_F;                // 1040 floats: one (16,65) f
 // kernel parameters: they land in the constant bank and feed FFMA directly as c[0][..]
 // operands once the loops are unrolled.
 struct EncFrontW {          // en_convs.0 / en_convs.1, BN folded (Export_GTCRN.py:171-194)
-  float w0[16][9][5];
+  float w0[5][9][16];       // [k][ci][o]: the unrolled inner loop (o) walks contiguous constants (LDCU.128)
   float b0[16];
-  float w1[16][8][5];       // groups=2: out o uses inputs (o/8)*8 .. +8
+  float w1[2][8][5][8];     // [group][ci][k][o_local]; groups=2: out o uses inputs (o/8)*8 .. +8
   float b1[16];
   float a0, a1;             // PReLU slopes
 };
@@ -27,15 +27,15 @@ struct GTW {                // one GTConvBlock, BN folded; deconv blocks are sto
   float b1[16];
   float wd[16][3][3];       // [c][kt][kf], kt=0 is the oldest frame (t-2d)
   float bd[16];
-  float w2[8][16];
+  float w2[16][8];          // [c][o]
   float b2[8];
   float a1, ad;
 };
 
 struct DecTailW {           // de_convs.3 (groups=2) / de_convs.4, BN folded
-  float w3[16][8][5];       // [ci][o_local][k]
+  float w3[16][5][8];       // [ci][k][o_local]
   float b3[16];
-  float w4[16][2][5];       // [ci][o][k]
+  float w4[16][5][2];       // [ci][k][o]
   float b4[2];
   float a3;
 };

@@ -83,7 +83,7 @@ def test_weight_packing_matches_oracle_fold():
         p = torch.from_numpy(blob[name])
         w1, b1 = p[:384].reshape(16, 24), p[384:400]
         wd, bd = p[400:544].reshape(16, 3, 3), p[544:560]
-        w2, b2 = p[560:688].reshape(8, 16), p[688:696]
+        w2, b2 = p[560:688].reshape(16, 8).T.contiguous(), p[688:696]      # stored [c][o]
         a1, ad = p[696], p[697]
         g = torch.Generator().manual_seed(0)
         x = torch.randn(1, 16, 20, 33, generator=g)
