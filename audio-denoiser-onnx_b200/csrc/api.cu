@@ -159,6 +159,9 @@ struct adn_model {
   void* d_in = nullptr;     // device staging for adn_run_host
   void* d_out = nullptr;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t st_in = nullptr, st_out = nullptr;      // copy streams of adn_run_host
+  cudaEvent_t ev_h2d[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_done[4] = {nullptr, nullptr, nullptr, nullptr};
 
   bool profiling = false;
   std::vector<cudaEvent_t> events;
@@ -241,7 +244,7 @@ size_t workspace_bytes_for(const adn_model* m, int B) {
   f += (size_t)B * T * SPEC_LD;                 // spec
   f += (size_t)B * T * FRAME_E0;                // e0
   f += (size_t)4 * B * T * FRAME16;             // e1..e4
-  f += (size_t)B * T * 8 * E1_F + (size_t)2 * B * T * 8;   // h1, zt, at
+  f += (size_t)B * T * 8 * E1_F + (size_t)B * T * (8 + 16 + 48);   // h1, zt, at, tgi
   f += (size_t)B * T * 3 * FRAME16;             // gi
   if (m->use_tc) f += (size_t)2 * B * m->Lp + (size_t)2 * (B * (T + 2 * m->stft.pad_frames()) * SPEC_LD + m->wo_kpad);
   f += (size_t)3 * B * T * FRAME16;             // xa, xb, inter
@@ -268,6 +271,8 @@ adn_status ensure_capacity(adn_model* m, int B) {
   A(m->buf.h1, (size_t)B * T * 8 * E1_F, false);
   A(m->buf.zt, (size_t)B * T * 8, false);
   A(m->buf.at, (size_t)B * T * 8, false);
+  A(m->buf.tgi, (size_t)B * T * 48, false);
+  A(m->buf.thid, (size_t)B * T * 16, false);
   A(m->buf.gi, (size_t)B * T * 3 * FRAME16, false);
   m->buf.xp_hi = m->buf.xp_lo = m->buf.enh_hi = m->buf.enh_lo = nullptr;
   A(m->buf.xa, (size_t)B * T * FRAME16, false);
@@ -530,6 +535,12 @@ void adn_destroy(adn_model* m) {
   if (m->d_wo_hl) cudaFree(m->d_wo_hl);
   for (auto e : m->events) cudaEventDestroy(e);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  if (m->st_in) cudaStreamDestroy(m->st_in);
+  if (m->st_out) cudaStreamDestroy(m->st_out);
+  for (int i = 0; i < 4; ++i) {
+    if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
+    if (m->ev_done[i]) cudaEventDestroy(m->ev_done[i]);
+  }
   delete m;
 }
 
@@ -627,14 +638,45 @@ adn_status adn_run_host(adn_model* m, const void* h_in, void* const* h_outs, int
   ADN_CUDA_TRY(cudaSetDevice(m->device), m->err);
   adn_status s = ensure_capacity(m, batch);
   if (s != ADN_OK) return s;
+  // Pipeline in sub-batches: H2D of slice i+1 and D2H of slice i-1 overlap the kernels of slice i
+  // (three streams, events in between).  The compute stream serialises the slices, so they share
+  // the workspace; the staging buffers are sliced.
+  const size_t in_row = (size_t)m->L * dtype_size(m->in_dtype);
+  const size_t out_row = (size_t)m->Lout * dtype_size(m->out_dtype);
+  // slices below ~512 chunks under-fill the GPU (the GRU kernels are latency-bound), so only very
+  // large batches are pipelined
+  const int nsub = batch >= 2048 ? 4 : (batch >= 1024 ? 2 : 1);
+  const int per = (batch + nsub - 1) / nsub;
+  if (!m->ev_h2d[0]) {
+    ADN_CUDA_TRY(cudaStreamCreateWithFlags(&m->st_in, cudaStreamNonBlocking), m->err);
+    ADN_CUDA_TRY(cudaStreamCreateWithFlags(&m->st_out, cudaStreamNonBlocking), m->err);
+    for (int i = 0; i < 4; ++i) {
+      ADN_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming), m->err);
+      ADN_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming), m->err);
+    }
+  }
   cudaStream_t st = m->own_stream;
-  size_t in_bytes = (size_t)batch * m->L * dtype_size(m->in_dtype);
-  size_t out_bytes = (size_t)batch * m->Lout * dtype_size(m->out_dtype);
-  ADN_CUDA_TRY(cudaMemcpyAsync(m->d_in, h_in, in_bytes, cudaMemcpyHostToDevice, st), m->err);
-  void* outs[1] = {m->d_out};
-  s = adn_run(m, m->d_in, outs, batch, st);
-  if (s != ADN_OK) return s;
-  ADN_CUDA_TRY(cudaMemcpyAsync(h_outs[0], m->d_out, out_bytes, cudaMemcpyDeviceToHost, st), m->err);
+  for (int i = 0; i < nsub; ++i) {
+    const int b0 = i * per, nb = (b0 + per <= batch) ? per : batch - b0;
+    if (nb <= 0) break;
+    ADN_CUDA_TRY(cudaMemcpyAsync((char*)m->d_in + b0 * in_row, (const char*)h_in + b0 * in_row, nb * in_row,
+                                 cudaMemcpyHostToDevice, m->st_in), m->err);
+    ADN_CUDA_TRY(cudaEventRecord(m->ev_h2d[i], m->st_in), m->err);
+  }
+  for (int i = 0; i < nsub; ++i) {
+    const int b0 = i * per, nb = (b0 + per <= batch) ? per : batch - b0;
+    if (nb <= 0) break;
+    ADN_CUDA_TRY(cudaStreamWaitEvent(st, m->ev_h2d[i], 0), m->err);
+    void* outs[1] = {(char*)m->d_out + b0 * out_row};
+    s = adn_run(m, (char*)m->d_in + b0 * in_row, outs, nb, st);
+    if (s != ADN_OK) return s;
+    ADN_CUDA_TRY(cudaEventRecord(m->ev_done[i], st), m->err);
+    ADN_CUDA_TRY(cudaStreamWaitEvent(m->st_out, m->ev_done[i], 0), m->err);
+    ADN_CUDA_TRY(cudaMemcpyAsync((char*)h_outs[0] + b0 * out_row, (char*)m->d_out + b0 * out_row, nb * out_row,
+                                 cudaMemcpyDeviceToHost, m->st_out), m->err);
+  }
+  m->last_batch = batch;
+  ADN_CUDA_TRY(cudaStreamSynchronize(m->st_out), m->err);
   ADN_CUDA_TRY(cudaStreamSynchronize(st), m->err);
   return ADN_OK;
 }
@@ -685,6 +727,7 @@ adn_status adn_debug_read(adn_model* m, const char* name, float* h_dst, size_t c
       {"h1", {m->buf.h1, B * T * 8 * E1_F}},
       {"zt", {m->buf.zt, B * T * 8}},
       {"at", {m->buf.at, B * T * 8}},
+      {"tgi", {m->buf.tgi, B * T * 48}},
       {"gi", {m->buf.gi, B * T * 3 * FRAME16}},
       {"xa", {m->buf.xa, B * T * FRAME16}},
       {"xb", {m->buf.xb, B * T * FRAME16}},

@@ -342,11 +342,12 @@ gt_main_kernel(const __grid_constant__ GTW w, const float* __restrict__ xin, flo
   if (tid < KT * 8) {
     const int kl = tid >> 3, c = tid & 7;
     const int k = k0 + kl;
+    float s = 0.f;
     if (k < nk) {
-      float s = 0.f;
 #pragma unroll
       for (int f = 0; f < E1_F; ++f) s = fmaf(h1s[kl][c][f], h1s[kl][c][f], s);
-      zt[((long long)b * T + (r + k * dil)) * 8 + c] = s / (float)E1_F;
+      s = s / (float)E1_F;
+      zt[((long long)b * T + (r + k * dil)) * 8 + c] = s;
     }
   }
 }
@@ -532,7 +533,7 @@ int launch_backbone(const Weights& w, const Buffers& buf, const Dims& d, int enh
     int dl = dil_enc[i];
     launch_gt_main(w.enc_gt[i], buf.e[i + 1], buf.h1, buf.zt, B, T, dl, st);
     TICK("gt_main");
-    launch_tra_gru(w.enc_tra[i], buf.zt, buf.at, B, T, st);
+    launch_tra_gru(w.enc_tra[i], buf.zt, buf.tgi, buf.thid, buf.at, B, T, st);
     TICK("tra_gru");
     launch_tra_apply(buf.at, buf.h1, buf.e[i + 1], nullptr, buf.e[i + 2], B, T, st);
     TICK("tra_apply");
@@ -559,7 +560,7 @@ int launch_backbone(const Weights& w, const Buffers& buf, const Dims& d, int enh
     launch_gt_main(w.dec_gt[i], cur, buf.h1, buf.zt, B, T, dl, st);
     TICK("gt_main");
     // next stage input = this block's output + encoder skip (e3, e2, e1)
-    launch_tra_gru(w.dec_tra[i], buf.zt, buf.at, B, T, st);
+    launch_tra_gru(w.dec_tra[i], buf.zt, buf.tgi, buf.thid, buf.at, B, T, st);
     TICK("tra_gru");
     launch_tra_apply(buf.at, buf.h1, cur, buf.e[3 - i], nxt, B, T, st);
     TICK("tra_apply");

@@ -94,6 +94,8 @@ struct Buffers {            // all fp32, frame-major: (B, T, C, F) with F innerm
   float* h1;                // (B, T, 8, 33) GTConvBlock output before TRA
   float* zt;                // (B, T, 8)   TRA energies
   float* at;                // (B, T, 8)   TRA gates
+  float* tgi;               // (B, T, 48)  TRA GRU input projections (scratch of tra_gru)
+  float* thid;              // (B, T, 16)  TRA GRU hidden states     (scratch of tra_gru)
   float* gi;                // (B, T, 3, 33, 16) inter-GRU input projections
   float* xp_hi;             // tf32 hi/lo planes of xp / enh for the tensor-core GEMMs (may be null)
   float* xp_lo;
@@ -125,7 +127,8 @@ void launch_prep(const void* in, int in_dtype, float* xp, float* hi, float* lo, 
                  int remove_dc, int reflect, cudaStream_t st);
 
 // recurrent stages (gtcrn_rnn.cu)
-void launch_tra_gru(const TraW& w, const float* zt, float* at, int B, int T, cudaStream_t st);
+void launch_tra_gru(const TraW& w, const float* zt, float* tgi, float* hbuf, float* at, int B, int T,
+                    cudaStream_t st);
 void launch_tra_apply(const float* at, const float* h1, const float* xin, const float* skip, float* out, int B,
                       int T, cudaStream_t st);
 void launch_dp_intra(const DpW& w, const float* a, const float* hprev, const DpW* prev, float* out, float* gi,

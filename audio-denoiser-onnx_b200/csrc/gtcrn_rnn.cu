@@ -70,49 +70,130 @@ struct GruI {          // input half: W_ih rows (r,z,n) + b_ih of one hidden uni
 };
 
 // =================================================================================
-// tra_gru: attention GRU(8->16) over T + Linear(16->8) + sigmoid  ->  at (B,T,8).
-// One half-warp per chunk, 8 chunks per CTA: every chunk of the batch is resident at once.
+// tra_gru: TRA attention for one chunk per half-warp, in three passes:
+//   (1) input projections gi[t] = W_ih z_t + b_ih for all t (parallel over lanes),
+//   (2) the serial GRU(8->16) recurrence -- only 48 FMA, 16 shuffles and 3 activations per step,
+//       projections fetched one 4-step block ahead,
+//   (3) at[t] = sigmoid(Linear(h_t)) for all t (parallel over lanes).
 // =================================================================================
-constexpr int TG_THREADS = 128;
+constexpr int TG_THREADS = 64;
 
 __global__ void __launch_bounds__(TG_THREADS)
-tra_gru_kernel(const TraW w, const float* __restrict__ zt, float* __restrict__ at, int B, int T) {
+tra_gru_kernel(const TraW w, const float* __restrict__ zt, float* __restrict__ tgi, float* __restrict__ hbuf,
+               float* __restrict__ at, int B, int T) {
+  __shared__ __align__(16) float hx[TG_THREADS / 16][2][16];
   const int lane = threadIdx.x & 31, hl = lane & 15;
   int b = (blockIdx.x * TG_THREADS + threadIdx.x) >> 4;
   const bool live = b < B;
   if (!live) b = B - 1;
   const float* z = zt + (long long)b * T * 8;
-  float* a_out = at + (long long)b * T * 8;
+  float* gq = tgi + (long long)b * T * 48;
+  float* hq = hbuf + (long long)b * T * 16;
+  float* aq = at + (long long)b * T * 8;
 
-  GruI<8, 16> in;
-  GruH<16> rec;
-  in.load(w.gru, hl);
-  rec.load(w.gru, hl);
-  float fw[16];
+  // ---- pass 1: lane owns projection rows u = hl, hl+16, hl+32 (= gates r,z,n of unit hl)
+  {
+    GruI<8, 16> in;
+    in.load(w.gru, hl);
+    for (int t0 = 0; t0 < T; t0 += 8) {
+      float4 xa[8], xb[8];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) fw[k] = __ldg(w.fc_w + (hl & 7) * 16 + k);
-  const float fb = __ldg(w.fc_b + (hl & 7));
-
-  float h = 0.f, hv[16];
+      for (int u = 0; u < 8; ++u) {           // all loads of the block first (latency overlapped)
+        const int t = (t0 + u < T) ? t0 + u : T - 1;
+        xa[u] = __ldg(reinterpret_cast<const float4*>(z + t * 8));
+        xb[u] = __ldg(reinterpret_cast<const float4*>(z + t * 8) + 1);
+      }
 #pragma unroll
-  for (int k = 0; k < 16; ++k) hv[k] = 0.f;
-  const int src0 = lane & 16;
-
-  float4 xa = __ldg(reinterpret_cast<const float4*>(z));
-  float4 xb = __ldg(reinterpret_cast<const float4*>(z) + 1);
-  for (int t = 0; t < T; ++t) {
-    const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-    if (t + 1 < T) {
-      xa = __ldg(reinterpret_cast<const float4*>(z + (t + 1) * 8));
-      xb = __ldg(reinterpret_cast<const float4*>(z + (t + 1) * 8) + 1);
+      for (int u = 0; u < 8; ++u) {
+        const int t = t0 + u;
+        const float x[8] = {xa[u].x, xa[u].y, xa[u].z, xa[u].w, xb[u].x, xb[u].y, xb[u].z, xb[u].w};
+        if (live && t < T) {
+#pragma unroll
+          for (int g = 0; g < 3; ++g) gq[t * 48 + g * 16 + hl] = in.proj(g, x);
+        }
+      }
     }
-    h = rec.step(in.proj(0, x), in.proj(1, x), in.proj(2, x), hv, h);
+  }
+  // each lane reads back exactly the values it wrote: no cross-lane dependency on tgi
+
+  // ---- pass 2: recurrence
+  const float* gp = gq + hl;
+  float* hp = hq + hl;
+  {
+    GruH<16> rec;
+    rec.load(w.gru, hl);
+    float h = 0.f, hv[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) hv[k] = __shfl_sync(0xffffffffu, h, src0 + k);
-    float a = fb;
+    for (int k = 0; k < 16; ++k) hv[k] = 0.f;
+    float cur[4][3], nxt[4][3];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) a = fmaf(fw[k], hv[k], a);
-    if (live && hl < 8) a_out[t * 8 + hl] = adn_sigmoid(a);
+    for (int u = 0; u < 4; ++u) {
+      const int tn = u < T ? u : T - 1;
+#pragma unroll
+      for (int g = 0; g < 3; ++g) cur[u][g] = gp[tn * 48 + g * 16];
+    }
+    for (int t0 = 0; t0 < T; t0 += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int tn = (t0 + 4 + u < T) ? t0 + 4 + u : T - 1;
+#pragma unroll
+        for (int g = 0; g < 3; ++g) nxt[u][g] = gp[tn * 48 + g * 16];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + u;
+        if (t < T) {
+          h = rec.step(cur[u][0], cur[u][1], cur[u][2], hv, h);
+          // exchange the hidden vector through shared memory (1 STS + 4 broadcast LDS.128 instead of
+          // 16 shuffles); ping-pong buffers make one __syncwarp per step sufficient
+          float* hb = hx[threadIdx.x >> 4][u & 1];
+          hb[hl] = h;
+          __syncwarp();
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const float4 v = *reinterpret_cast<const float4*>(hb + 4 * k4);
+            hv[4 * k4 + 0] = v.x; hv[4 * k4 + 1] = v.y; hv[4 * k4 + 2] = v.z; hv[4 * k4 + 3] = v.w;
+          }
+          if (live) hp[t * 16] = h;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int g = 0; g < 3; ++g) cur[u][g] = nxt[u][g];
+    }
+  }
+  __syncwarp();      // h_t written by the other lanes of this half-warp is visible below
+
+  // ---- pass 3: lane (half, c) computes at[t][c] for t = half, half+2, ...
+  {
+    const int c = hl & 7, half = hl >> 3;
+    float fw[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) fw[k] = __ldg(w.fc_w + c * 16 + k);
+    const float fb = __ldg(w.fc_b + c);
+    for (int t0 = half; t0 < T; t0 += 8) {
+      float4 v[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = (t0 + 2 * u < T) ? t0 + 2 * u : T - 1;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) v[u][k4] = *reinterpret_cast<const float4*>(hq + t * 16 + 4 * k4);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + 2 * u;
+        float a = fb;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          a = fmaf(fw[4 * k4 + 0], v[u][k4].x, a);
+          a = fmaf(fw[4 * k4 + 1], v[u][k4].y, a);
+          a = fmaf(fw[4 * k4 + 2], v[u][k4].z, a);
+          a = fmaf(fw[4 * k4 + 3], v[u][k4].w, a);
+        }
+        if (live && t < T) aq[t * 8 + c] = adn_sigmoid(a);
+      }
+    }
   }
 }
 
@@ -296,17 +377,35 @@ dp_inter_kernel(const DpW w, const float* __restrict__ gi, float* __restrict__ h
   for (int k = 0; k < 8; ++k) hv[k] = 0.f;
   const int src0 = lane & ~7;
 
-  float g0 = __ldg(gp), g1 = __ldg(gp + FRAME16), g2 = __ldg(gp + 2 * FRAME16);
-  for (int t = 0; t < T; ++t) {
-    const float c0 = g0, c1 = g1, c2 = g2;
-    if (t + 1 < T) {
-      const float* nx = gp + (long long)(t + 1) * (3 * FRAME16);
-      g0 = __ldg(nx); g1 = __ldg(nx + FRAME16); g2 = __ldg(nx + 2 * FRAME16);
-    }
-    h = rec.step(c0, c1, c2, hv, h);
+  const long long tstride = 3 * FRAME16;
+  float cur[4][3], nxt[4][3];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) hv[k] = __shfl_sync(0xffffffffu, h, src0 + k);
-    if (live) hp[(long long)t * FRAME16] = h;
+  for (int u = 0; u < 4; ++u) {
+    const int tn = u < T ? u : T - 1;
+#pragma unroll
+    for (int gg = 0; gg < 3; ++gg) cur[u][gg] = __ldg(gp + tn * tstride + gg * FRAME16);
+  }
+  for (int t0 = 0; t0 < T; t0 += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int tn = (t0 + 4 + u < T) ? t0 + 4 + u : T - 1;
+#pragma unroll
+      for (int gg = 0; gg < 3; ++gg) nxt[u][gg] = __ldg(gp + tn * tstride + gg * FRAME16);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u;
+      if (t < T) {
+        h = rec.step(cur[u][0], cur[u][1], cur[u][2], hv, h);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hv[k] = __shfl_sync(0xffffffffu, h, src0 + k);
+        if (live) hp[(long long)t * FRAME16] = h;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int gg = 0; gg < 3; ++gg) cur[u][gg] = nxt[u][gg];
   }
 }
 
@@ -343,8 +442,9 @@ ln_res_kernel(const float* __restrict__ a, const float* __restrict__ hin, const 
 }
 
 // ------------------------------------------------------------------ launch wrappers
-void launch_tra_gru(const TraW& w, const float* zt, float* at, int B, int T, cudaStream_t st) {
-  tra_gru_kernel<<<(B * 16 + TG_THREADS - 1) / TG_THREADS, TG_THREADS, 0, st>>>(w, zt, at, B, T);
+void launch_tra_gru(const TraW& w, const float* zt, float* tgi, float* hbuf, float* at, int B, int T,
+                    cudaStream_t st) {
+  tra_gru_kernel<<<(B * 16 + TG_THREADS - 1) / TG_THREADS, TG_THREADS, 0, st>>>(w, zt, tgi, hbuf, at, B, T);
 }
 
 void launch_tra_apply(const float* at, const float* h1, const float* xin, const float* skip, float* out, int B,
