@@ -288,15 +288,18 @@ dp_intra_kernel(const DpW w, const float* __restrict__ a, const float* __restric
 
   if (hprev) {
     // previous DPGRNN's inter path: h ([f][16]) -> Linear -> LayerNorm -> + residual (:479-481)
+#pragma unroll 11
     for (int i = hl; i < FRAME16; i += 16) y[i] = __ldg(hprev + off + i);
     __syncwarp();
     frame_fc(y, z, pfc_w, pfc_b, hl);
     __syncwarp();
     float mean, rstd;
     frame_stats(z, hl, mean, rstd);
+#pragma unroll 11
     for (int i = hl; i < FRAME16; i += 16)
       x[i] = __ldg(a + off + i) + ((z[i] - mean) * rstd * __ldg(pln_w + i) + __ldg(pln_b + i));
   } else {
+#pragma unroll 11
     for (int i = hl; i < FRAME16; i += 16) x[i] = __ldg(a + off + i);
   }
   __syncwarp();
@@ -326,6 +329,7 @@ dp_intra_kernel(const DpW w, const float* __restrict__ a, const float* __restric
   __syncwarp();
   float mean, rstd;
   frame_stats(z, hl, mean, rstd);
+#pragma unroll 11
   for (int i = hl; i < FRAME16; i += 16) {
     const float v = x[i] + ((z[i] - mean) * rstd * __ldg(w.intra_ln_w + i) + __ldg(w.intra_ln_b + i));
     x[i] = v;
@@ -426,6 +430,7 @@ ln_res_kernel(const float* __restrict__ a, const float* __restrict__ hin, const 
   const long long off = (live ? fg : 0) * FRAME16;
   float* y = ys[fi];
   float* z = zs[fi];
+#pragma unroll 11
   for (int i = hl; i < FRAME16; i += 16) y[i] = __ldg(hin + off + i);
   __syncwarp();
   frame_fc(y, z, fc_w, fc_b, hl);
@@ -433,6 +438,7 @@ ln_res_kernel(const float* __restrict__ a, const float* __restrict__ hin, const 
   float mean, rstd;
   frame_stats(z, hl, mean, rstd);
   if (live) {
+#pragma unroll 11
     for (int i = hl; i < FRAME16; i += 16) {
       float v = __ldg(a + off + i) + ((z[i] - mean) * rstd * __ldg(ln_w + i) + __ldg(ln_b + i));
       if (skip) v += __ldg(skip + off + i);
