@@ -186,12 +186,12 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=512, help="chunks per GPU per step")
     ap.add_argument("--impl", default="adn", choices=["adn", "reference"])
-    ap.add_argument("--ref-chunks", type=int, default=16, help="CPU chunks per step for --impl reference")
-    ap.add_argument("--cpu-baseline-chunks", type=int, default=150)
+    ap.add_argument("--ref-chunks", type=int, default=24, help="CPU chunks per step for --impl reference")
+    ap.add_argument("--cpu-baseline-chunks", type=int, default=600)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -237,12 +237,13 @@ def main():
         model.run(dev_sets[i % n_sets], out=out)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
-        e0.record(stream)
-        for i in range(args.steps):
-            model.run(dev_sets[i % n_sets], out=out)
-        e1.record(stream)
-        barrier()
+    clk = ClockSampler(local_rank)
+    clk.__enter__()              # sampled across all GPU loops of this run (timed + per-kernel + e2e)
+    e0.record(stream)
+    for i in range(args.steps):
+        model.run(dev_sets[i % n_sets], out=out)
+    e1.record(stream)
+    barrier()
     ms = e0.elapsed_time(e1)
     if dist is not None:
         t = torch.tensor([ms], device=dev)
@@ -315,6 +316,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_value = audio_s / (e2e_ms * 1e-3)
+    clk.__exit__(None, None, None)
 
     # ---------------- CPU baseline on this box's host cores (rank 0, N=1 only)
     cpu = None
