@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "gtcrn.cuh"
+#include "model_impl.h"
 
 #include <cstdlib>
 #include <cstring>
@@ -23,10 +24,6 @@ void set_global_error(const std::string& s) {
 }
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
-
-struct TensorRef {
-  uint64_t offset, count;
-};
 
 // Overlap-add weight for the row-gather GEMM: raw output block j (hop samples) is
 //   sum_{q'=0}^{R-1} frame[j-R+1+q'] . Kinv[:, n' + (R-1-q')*hop]
@@ -125,6 +122,7 @@ void tile_rows(int TM, int& bt, int& bb, int& tpc) {
 // ===================================================================================
 struct adn_model {
   std::string err;
+  ModelImpl* impl = nullptr;   // non-GTCRN families (GTCRN state is inline below)
   int device = 0;
   std::string family;
   std::map<std::string, std::string> meta;
@@ -133,7 +131,7 @@ struct adn_model {
   size_t nfloats = 0;
 
   int in_dtype = ADN_F32, out_dtype = ADN_F32;
-  int L = 0, T = 0, Lp = 0, Lout = 0;
+  int L = 0, T = 0, Lp = 0, Lout = 0, chans = 1;
   StftPlan stft;
   const float* d_fwd = nullptr;
   float* d_ola = nullptr;
@@ -158,6 +156,7 @@ struct adn_model {
   std::vector<void*> allocs;
   void* d_in = nullptr;     // device staging for adn_run_host
   void* d_out = nullptr;
+  int io_cap = 0;           // staging capacity when `impl` owns the workspace
   cudaStream_t own_stream = nullptr;
   cudaStream_t st_in = nullptr, st_out = nullptr;      // copy streams of adn_run_host
   cudaEvent_t ev_h2d[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -470,7 +469,7 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
       !need("output_audio_dtype", sout) || !need("nfft", snfft) || !need("hop_length", shop))
     return fail(ADN_ERR_INVALID);
   m->family = fam;
-  if (fam != "gtcrn") {
+  if (fam != "gtcrn" && fam != "mel_band_roformer") {
     m->err = "unsupported model_family '" + fam + "'";
     return fail(ADN_ERR_UNSUPPORTED);
   }
@@ -480,7 +479,8 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
   }
   m->L = atoi(sL.c_str());
   int nfft = atoi(snfft.c_str()), hop = atoi(shop.c_str());
-  if (nfft != gtcrn::NFFT || hop != gtcrn::HOP) {
+  const bool is_gtcrn = fam == "gtcrn";
+  if (is_gtcrn && (nfft != gtcrn::NFFT || hop != gtcrn::HOP)) {
     m->err = "gtcrn requires nfft=512, hop_length=256";
     return fail(ADN_ERR_INVALID);
   }
@@ -492,6 +492,7 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
   m->T = m->stft.n_frames(m->L);
   m->Lp = m->stft.padded_len(m->L);
   m->Lout = m->stft.out_len(m->T);
+  m->chans = is_gtcrn ? 1 : 2;
 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device_id) {
@@ -514,7 +515,13 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
   }
   m->nfloats = nfloats;
   m->sms = prop.multiProcessorCount;
-  adn_status s = build_gtcrn(m, weights);
+  adn_status s = ADN_OK;
+  if (is_gtcrn) {
+    s = build_gtcrn(m, weights);
+  } else {
+    m->impl = mbr_create(m->meta, m->index, weights, m->d_blob, device_id, m->sms, m->err);
+    if (!m->impl) s = ADN_ERR_INVALID;
+  }
   if (s != ADN_OK) return fail(s);
   if (cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     m->err = "cudaStreamCreate failed";
@@ -528,12 +535,14 @@ void adn_destroy(adn_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   cudaDeviceSynchronize();
+  delete m->impl;
   free_workspace(m);
   if (m->d_blob) cudaFree(m->d_blob);
   if (m->d_ola) cudaFree(m->d_ola);
   if (m->d_wf_hl) cudaFree(m->d_wf_hl);
   if (m->d_wo_hl) cudaFree(m->d_wo_hl);
   for (auto e : m->events) cudaEventDestroy(e);
+  if (m->io_cap) { cudaFree(m->d_in); cudaFree(m->d_out); }
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   if (m->st_in) cudaStreamDestroy(m->st_in);
   if (m->st_out) cudaStreamDestroy(m->st_out);
@@ -546,6 +555,11 @@ void adn_destroy(adn_model* m) {
 
 adn_status adn_io_info(const adn_model* m, adn_tensor_info* in, adn_tensor_info* outs, int32_t* n_out) {
   if (!m || !in || !outs || !n_out) return ADN_ERR_INVALID;
+  if (m->impl) {
+    m->impl->io_info(in, outs);
+    *n_out = 1;
+    return ADN_OK;
+  }
   memset(in, 0, sizeof(*in));
   memset(outs, 0, sizeof(*outs));
   strncpy(in->name, "noisy_audio", sizeof(in->name) - 1);       // Export_GTCRN.py:768
@@ -558,12 +572,14 @@ adn_status adn_io_info(const adn_model* m, adn_tensor_info* in, adn_tensor_info*
 
 size_t adn_workspace_bytes(const adn_model* m, int32_t batch) {
   if (!m || batch <= 0) return 0;
+  if (m->impl) return m->impl->workspace_bytes(batch);
   return workspace_bytes_for(m, batch);
 }
 
 int32_t adn_launches_per_run(const adn_model* m, int32_t batch) {
   (void)batch;
   // prep, stft, enc_front, 6x(gt_main, tra_gru, tra_apply), 2x(dp_intra, dp_inter), ln_res, dec_tail, istft
+  if (m && m->impl) return m->impl->launches(batch);
   return m ? 28 : 0;
 }
 
@@ -574,6 +590,12 @@ adn_status adn_run(adn_model* m, const void* d_in, void* const* d_outs, int32_t 
     return ADN_ERR_INVALID;
   }
   ADN_CUDA_TRY(cudaSetDevice(m->device), m->err);
+  if (m->impl) {
+    adn_status r = m->impl->run(d_in, d_outs[0], batch, (cudaStream_t)stream);
+    if (r != ADN_OK) m->err = m->impl->err;
+    m->last_batch = batch;
+    return r;
+  }
   adn_status s = ensure_capacity(m, batch);
   if (s != ADN_OK) return s;
   cudaStream_t st = (cudaStream_t)stream;
@@ -636,13 +658,24 @@ adn_status adn_run_host(adn_model* m, const void* h_in, void* const* h_outs, int
     return ADN_ERR_INVALID;
   }
   ADN_CUDA_TRY(cudaSetDevice(m->device), m->err);
-  adn_status s = ensure_capacity(m, batch);
-  if (s != ADN_OK) return s;
+  adn_status s = ADN_OK;
+  if (m->impl) {
+    if (batch > m->io_cap) {     // staging buffers for families that own their workspace
+      ADN_CUDA_TRY(cudaDeviceSynchronize(), m->err);
+      if (m->io_cap) { cudaFree(m->d_in); cudaFree(m->d_out); }
+      ADN_CUDA_TRY(cudaMalloc(&m->d_in, (size_t)batch * m->chans * m->L * dtype_size(m->in_dtype)), m->err);
+      ADN_CUDA_TRY(cudaMalloc(&m->d_out, (size_t)batch * m->chans * m->Lout * dtype_size(m->out_dtype)), m->err);
+      m->io_cap = batch;
+    }
+  } else {
+    s = ensure_capacity(m, batch);
+    if (s != ADN_OK) return s;
+  }
   // Pipeline in sub-batches: H2D of slice i+1 and D2H of slice i-1 overlap the kernels of slice i
   // (three streams, events in between).  The compute stream serialises the slices, so they share
   // the workspace; the staging buffers are sliced.
-  const size_t in_row = (size_t)m->L * dtype_size(m->in_dtype);
-  const size_t out_row = (size_t)m->Lout * dtype_size(m->out_dtype);
+  const size_t in_row = (size_t)m->chans * m->L * dtype_size(m->in_dtype);
+  const size_t out_row = (size_t)m->chans * m->Lout * dtype_size(m->out_dtype);
   // slices below ~512 chunks under-fill the GPU (the GRU kernels are latency-bound), so only very
   // large batches are pipelined
   const int nsub = batch >= 2048 ? 4 : (batch >= 1024 ? 2 : 1);
@@ -684,6 +717,7 @@ adn_status adn_run_host(adn_model* m, const void* h_in, void* const* h_outs, int
 adn_status adn_debug_stop_after(adn_model* m, int32_t n_launches) {
   if (!m) return ADN_ERR_INVALID;
   m->stop_after = n_launches;
+  if (m->impl) m->impl->set_stop_after(n_launches);
   return ADN_OK;
 }
 
@@ -710,6 +744,11 @@ adn_status adn_last_kernel_times(adn_model* m, const char** names, float* ms, in
 
 adn_status adn_debug_read(adn_model* m, const char* name, float* h_dst, size_t count, size_t* actual) {
   if (!m || !name) return ADN_ERR_INVALID;
+  if (m->impl) {
+    adn_status r = m->impl->debug_read(name, h_dst, count, actual);
+    if (r != ADN_OK) m->err = m->impl->err;
+    return r;
+  }
   using namespace gtcrn;
   const size_t B = m->last_batch, T = m->T;
   if (B == 0) {

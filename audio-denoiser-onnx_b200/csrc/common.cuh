@@ -35,7 +35,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // With a_sT < K the rows overlap: that is the STFT framing (a_sT = hop, K = nfft) and
 // the ISTFT overlap-add (rows = runs of R consecutive spectrum frames).
 // ---------------------------------------------------------------------------------
-enum { EPI_STORE = 0, EPI_ISTFT = 1 };
+enum { EPI_STORE = 0, EPI_ISTFT = 1, EPI_LIN = 2 };
 
 struct GemmArgs {
   const float* A;

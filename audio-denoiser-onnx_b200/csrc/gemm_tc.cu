@@ -181,14 +181,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         int b0, t0;
         if (g.bb > 1) { b0 = mt * g.bb; t0 = g.t0; }
         else { b0 = mt / g.tiles_per_chunk; t0 = g.t0 + (mt - b0 * g.tiles_per_chunk) * BM; }
+        b0 += g.b_off;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * S::STAGE_BYTES;
           mbar_expect_tx(&full[stage], (uint32_t)(2 * g.bt * g.bb * BK * 4) + 2 * S::W_TILE_BYTES);
           tma_load_3d(st, &map_a_hi, &full[stage], kb * BK, t0, b0);
           tma_load_3d(st + A_TILE_BYTES, &map_a_lo, &full[stage], kb * BK, t0, b0);
-          tma_load_2d(st + 2 * A_TILE_BYTES, &map_w_hi, &full[stage], kb * BK, nt * BN);
-          tma_load_2d(st + 2 * A_TILE_BYTES + S::W_TILE_BYTES, &map_w_lo, &full[stage], kb * BK, nt * BN);
+          const int wb = g.w_batched ? b0 : 0;      // per-batch weights (mask-estimator bands)
+          tma_load_3d(st + 2 * A_TILE_BYTES, &map_w_hi, &full[stage], kb * BK, nt * BN, wb);
+          tma_load_3d(st + 2 * A_TILE_BYTES + S::W_TILE_BYTES, &map_w_lo, &full[stage], kb * BK, nt * BN, wb);
           if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -238,6 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       int b, t;
       if (g.bb > 1) { int bi = r / g.bt; b = mt * g.bb + bi; t = r - bi * g.bt; if (bi >= g.bb) b = g.B; }
       else { b = mt / g.tiles_per_chunk; t = (mt - b * g.tiles_per_chunk) * BM + r; }
+      b += g.b_off;
       const bool row_ok = (b < g.B) && (t < g.TM);
       mbar_wait(&tfull[ab], aphase);
       tc_fence_after();
@@ -260,6 +263,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (c0 + j < BN && n0 + j < g.N) dst[j] = __uint_as_float(v[j]);
+          }
+        } else if (EPI == EPI_LIN) {
+          // Linear layer: v = act(acc * rowscale[m] + bias[n]) (+ residual) -> fp32 and/or tf32 planes
+          const long long m = (long long)b * g.TM + t;
+          const float rs = g.rowscale ? __ldg(g.rowscale + m) : 1.0f;
+          const long long o = m * g.ldc + n0;
+#pragma unroll
+          for (int j0 = 0; j0 < 32; j0 += 4) {
+            if (c0 + j0 >= BN || n0 + j0 >= g.N) continue;     // N, BN and ldc are multiples of 4
+            float x[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a = __uint_as_float(v[j0 + j]) * rs;
+              if (g.bias) a += __ldg(g.bias + (long long)b * g.bias_bstride + n0 + j0 + j);
+              if (g.act == ACT_GELU) a = 0.5f * a * (1.0f + erff(a * 0.70710678118654752440f));
+              else if (g.act == ACT_TANH) a = tanhf(a);
+              x[j] = a;
+            }
+            if (g.resid) {
+              const float4 r4 = *reinterpret_cast<const float4*>(g.resid + o + j0);
+              x[0] += r4.x; x[1] += r4.y; x[2] += r4.z; x[3] += r4.w;
+            }
+            if (g.C) *reinterpret_cast<float4*>(g.C + o + j0) = make_float4(x[0], x[1], x[2], x[3]);
+            if (g.Chi) {
+              float h[4], l[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                h[j] = __uint_as_float(__float_as_uint(x[j]) & 0xFFFFE000u);
+                l[j] = x[j] - h[j];
+              }
+              *reinterpret_cast<float4*>(g.Chi + o + j0) = make_float4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<float4*>(g.Clo + o + j0) = make_float4(l[0], l[1], l[2], l[3]);
+            }
           }
         } else {
           // ISTFT: s = (t + t0)*hop + n - shift ; y = acc (/|*) norm[s]
@@ -329,14 +365,15 @@ bool make_row_map(CUtensorMap* map, const float* base, int k_extent, int rows, l
   return true;
 }
 
-bool make_weight_map(CUtensorMap* map, const float* base, int k_pad, int n_pad, int box_n, std::string& err) {
+bool make_weight_map(CUtensorMap* map, const float* base, int k_pad, int n_pad, int box_n, std::string& err,
+                     int batches) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { err = "cuTensorMapEncodeTiled entry point not available"; return false; }
-  cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)n_pad};
-  cuuint64_t strides[1] = {(cuuint64_t)k_pad * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_n};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es,
+  cuuint64_t dims[3] = {(cuuint64_t)k_pad, (cuuint64_t)n_pad, (cuuint64_t)batches};
+  cuuint64_t strides[2] = {(cuuint64_t)k_pad * 4, (cuuint64_t)k_pad * 4 * (cuuint64_t)n_pad};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_n, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(W) failed: " + std::to_string((int)r); return false; }
@@ -359,10 +396,18 @@ static cudaError_t launch_t(const TcPlan& p, const TcArgs& a, int sms, cudaStrea
   return cudaGetLastError();
 }
 
+template <int BN>
+static cudaError_t launch_bn(const TcPlan& p, const TcArgs& a, int epi, int sms, cudaStream_t st) {
+  if (epi == EPI_STORE) return launch_t<BN, EPI_STORE>(p, a, sms, st);
+  if (epi == EPI_ISTFT) return launch_t<BN, EPI_ISTFT>(p, a, sms, st);
+  if (epi == EPI_LIN) return launch_t<BN, EPI_LIN>(p, a, sms, st);
+  return cudaErrorInvalidValue;
+}
+
 cudaError_t launch(const TcPlan& p, const TcArgs& a, int epi, int sms, cudaStream_t st) {
-  if (p.bn == 176) return epi == EPI_STORE ? launch_t<176, EPI_STORE>(p, a, sms, st) : launch_t<176, EPI_ISTFT>(p, a, sms, st);
-  if (p.bn == 256) return epi == EPI_STORE ? launch_t<256, EPI_STORE>(p, a, sms, st) : launch_t<256, EPI_ISTFT>(p, a, sms, st);
-  if (p.bn == 128) return epi == EPI_STORE ? launch_t<128, EPI_STORE>(p, a, sms, st) : launch_t<128, EPI_ISTFT>(p, a, sms, st);
+  if (p.bn == 176) return launch_bn<176>(p, a, epi, sms, st);
+  if (p.bn == 256) return launch_bn<256>(p, a, epi, sms, st);
+  if (p.bn == 128) return launch_bn<128>(p, a, epi, sms, st);
   return cudaErrorInvalidValue;
 }
 

@@ -11,7 +11,9 @@ struct TcArgs {
   int bb, bt;            // TMA box: bb chunks x bt rows per tile (bb*bt <= 128)
   int tiles_per_chunk;   // when bb == 1: ceil(TM / 128)
   int t0;                // first row (per chunk) in the A tensor map
-  int B, TM;             // chunks, valid rows per chunk
+  int B, TM;             // chunks (exclusive upper bound of the chunk index), valid rows per chunk
+  int b_off;             // first chunk index of this launch
+  int w_batched;         // 1: weights differ per chunk (W map has a chunk dimension)
   int N, K;
   // EPI_STORE: C[b*c_sB + t*c_sT + n]
   float* C;
@@ -20,7 +22,19 @@ struct TcArgs {
   const float* norm;
   int norm_mul, hop, shift, out_len, out_dtype;
   void* out;
+  // EPI_LIN: row m = b*TM + t;  v = act(acc*rowscale[m] + bias[n]) (+ resid[m*ldc+n]);
+  //          C[m*ldc+n] = v (fp32, optional; may alias resid) and/or Chi/Clo (tf32 planes, optional)
+  const float* rowscale;
+  const float* bias;
+  long long bias_bstride; // bias of chunk b starts at bias + b*bias_bstride (batched weights)
+  const float* resid;
+  float* Chi;
+  float* Clo;
+  long long ldc;
+  int act;               // ACT_NONE | ACT_GELU | ACT_TANH
 };
+
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_TANH = 2 };
 
 struct TcPlan {
   CUtensorMap map_a_hi, map_a_lo, map_w_hi, map_w_lo;
@@ -31,7 +45,8 @@ struct TcPlan {
 bool make_row_map(CUtensorMap* map, const float* base, int k_extent, int rows, long long row_stride, int batches,
                   long long batch_stride, int box_rows, int box_batches, std::string& err);
 // W planes: (n_pad, k_pad) row-major, zero padded.
-bool make_weight_map(CUtensorMap* map, const float* base, int k_pad, int n_pad, int box_n, std::string& err);
+bool make_weight_map(CUtensorMap* map, const float* base, int k_pad, int n_pad, int box_n, std::string& err,
+                     int batches = 1);
 
 cudaError_t launch(const TcPlan& p, const TcArgs& a, int epi, int sms, cudaStream_t st);
 

@@ -1,0 +1,26 @@
+// Internal interface between the C ABI (api.cu) and per-family model implementations.
+#pragma once
+#include "adn.h"
+
+#include <cuda_runtime.h>
+#include <map>
+#include <string>
+
+struct TensorRef {
+  uint64_t offset, count;
+};
+
+struct ModelImpl {
+  std::string err;
+  virtual ~ModelImpl() {}
+  virtual void io_info(adn_tensor_info* in, adn_tensor_info* out) = 0;
+  virtual adn_status run(const void* d_in, void* d_out, int batch, cudaStream_t st) = 0;
+  virtual size_t workspace_bytes(int batch) = 0;
+  virtual int launches(int batch) = 0;
+  virtual adn_status debug_read(const char* name, float* h_dst, size_t count, size_t* actual) = 0;
+  virtual void set_stop_after(int n) = 0;
+};
+
+// Mel-Band-Roformer (stereo): csrc/mbr.cu
+ModelImpl* mbr_create(const std::map<std::string, std::string>& meta, const std::map<std::string, TensorRef>& index,
+                      const float* h_blob, float* d_blob, int device, int sms, std::string& err);

@@ -126,5 +126,37 @@ def main():
         print(f"gtcrn F32 L8000: {tuple(x8.shape)} -> {tuple(y8.shape)}")
 
 
+def mbr_kwargs(cfg):
+    return dict(dim=cfg.dim, depth=cfg.depth, stereo=True, num_stems=1, time_transformer_depth=1,
+                freq_transformer_depth=1, num_bands=cfg.num_bands, dim_head=cfg.dim_head, heads=cfg.heads,
+                mask_estimator_depth=2, stft_n_fft=cfg.nfft, stft_hop_length=cfg.hop, stft_win_length=cfg.nfft,
+                sample_rate=cfg.sample_rate)
+
+
+def main_mbr():
+    """Mel-Band-Roformer (stereo) fixtures: the reference's own module on seeded weights, one
+    un-folded window per run (depth 2 keeps the fixture generation and the CPU oracle quick; the
+    mask estimator -- 92 % of the parameters -- is depth independent)."""
+    import mbr_oracle as mo
+
+    assert ref_loader.reference_available()
+    cfg = mo.MbrConfig(depth=2)
+    sd = mo.random_state_dict(cfg, 0)
+    with torch.inference_mode():
+        for L, dt in ((4410, "F32"), (13230, "INT16")):
+            _, build = ref_loader.load_mbr(L, dt)
+            m = build(sd, **mbr_kwargs(cfg))
+            g = torch.Generator().manual_seed(1234)
+            x = (torch.rand(2, 2, L, generator=g) * 2 - 1) * 0.5
+            x[1, :, L // 2:] = 0.0
+            xin = x if dt == "F32" else torch.round(x * 32767.0).to(torch.int16)
+            y = torch.cat([m(xin[i:i + 1]) for i in range(2)], dim=0)
+            np.savez_compressed(GOLDEN / f"mbr_{dt.lower()}_L{L}_d2.npz", x=xin.numpy(), y=y.numpy(), seed=0, depth=2)
+            print(f"mbr {dt} L{L}: {tuple(xin.shape)} -> {tuple(y.shape)} max|y| {y.abs().max().item():.4f}")
+
+
 if __name__ == "__main__":
-    main()
+    if "--mbr" in sys.argv:
+        main_mbr()
+    else:
+        main()

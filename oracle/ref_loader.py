@@ -75,7 +75,8 @@ def load_export_namespace(model_dir: str, script: str, patches: dict[str, str]) 
         if old not in src:
             raise RuntimeError(f"patch anchor not found in {script}: {old!r}")
         src = src.replace(old, new, 1)
-    ns: dict = {"__file__": str(mdir / script), "__name__": "ref_export_" + model_dir}
+    ns: dict = {"__file__": str(mdir / script),
+                "__name__": "ref_export_" + model_dir.replace("/", "_").replace("-", "_")}
     exec(compile(src, str(mdir / script), "exec"), ns)
     sys.modules.pop("STFT_Process", None)
     return ns
@@ -122,5 +123,44 @@ def load_gtcrn(input_audio_length: int = 16000, io_dtype: str = "F32"):
                 False, ns["FOLD_WINDOW_LENGTH"],
             ).eval()
         return wrapper
+
+    return ns, build
+
+
+def load_mbr(input_audio_length: int, io_dtype: str = "F32"):
+    """Reference Mel-Band-Roformer (stereo) wrapper for one un-folded window.
+
+    Returns (namespace, build) with build(state_dict, **model_kwargs) -> module.  The
+    checkpoint load inside `MelBandRoformer.__init__` (Export_MelBandRoformer.py:391-394) is
+    redirected to the given state_dict by patching `torch.load` for the duration of the call."""
+    import torch
+
+    ns = load_export_namespace(
+        "Mel_Band_Roformer/Stereo",
+        "Export_MelBandRoformer.py",
+        {
+            "INPUT_AUDIO_LENGTH  = 88200": f"INPUT_AUDIO_LENGTH  = {int(input_audio_length)}",
+            "USE_BATCH_FOLD       = True": "USE_BATCH_FOLD       = False",
+            "IN_AUDIO_DTYPE        = 'INT16'": f"IN_AUDIO_DTYPE        = '{io_dtype}'",
+            "OUT_AUDIO_DTYPE       = 'INT16'": f"OUT_AUDIO_DTYPE       = '{io_dtype}'",
+        },
+    )
+
+    def build(state_dict, **model_kwargs):
+        real_load = torch.load
+        torch.load = lambda *a, **k: state_dict
+        try:
+            with torch.inference_mode():
+                S = ns["STFT_Process"]
+                stft = S(model_type="stft_B", n_fft=ns["NFFT"], hop_len=ns["HOP_LENGTH"], win_length=ns["WINDOW_LENGTH"],
+                         max_frames=0, window_type=ns["WINDOW_TYPE"], center_pad=True, pad_mode="reflect").eval()
+                istft = S(model_type="istft_B", n_fft=ns["NFFT"], hop_len=ns["HOP_LENGTH"],
+                          win_length=ns["WINDOW_LENGTH"], max_frames=ns["MAX_SIGNAL_LENGTH"],
+                          window_type=ns["WINDOW_TYPE"], center_pad=True, pad_mode="reflect", static_frames=True).eval()
+                m = ns["MelBandRoformer"](stft, istft, ns["MAX_SIGNAL_LENGTH"], False, ns["FOLD_WINDOW_LENGTH"],
+                                          ns["EXPORT_AUDIO_LENGTH"], **model_kwargs).eval()
+        finally:
+            torch.load = real_load
+        return m
 
     return ns, build
