@@ -120,7 +120,7 @@ class Model:
         _lib.check(_lib.lib().adn_set_profiling(self._h, 1 if on else 0), self._h, "adn_set_profiling")
 
     def kernel_times(self) -> list[tuple[str, float]]:
-        cap = 128
+        cap = 4096
         names = (C.c_char_p * cap)()
         ms = (C.c_float * cap)()
         n = C.c_int32(0)

@@ -591,6 +591,11 @@ adn_status adn_run(adn_model* m, const void* d_in, void* const* d_outs, int32_t 
   }
   ADN_CUDA_TRY(cudaSetDevice(m->device), m->err);
   if (m->impl) {
+    m->ev_used = 0;
+    m->ev_stream = (cudaStream_t)stream;
+    m->impl->tick = tick_cb;
+    m->impl->tick_ctx = m;
+    tick_cb(m, "start");
     adn_status r = m->impl->run(d_in, d_outs[0], batch, (cudaStream_t)stream);
     if (r != ADN_OK) m->err = m->impl->err;
     m->last_batch = batch;

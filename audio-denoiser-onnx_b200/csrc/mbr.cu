@@ -552,9 +552,9 @@ class Model : public ModelImpl {
   int launches(int) override { return 3 + nb + 1 + 2 * depth * 7 + 2 + nb + 2; }
   void set_stop_after(int n) override { stop_after = n; }
 
-#define MBR_TICK() do { ++n; if (stop_after > 0 && n >= stop_after) return ADN_OK; } while (0)
-#define MBR_GEMM(G) do { cudaError_t e_ = tc::launch((G).plan, (G).args, EPI_LIN, sms, st); \
-    if (e_ != cudaSuccess) { err = std::string("gemm launch: ") + cudaGetErrorString(e_); return ADN_ERR_CUDA; } MBR_TICK(); } while (0)
+#define MBR_TICK(name) do { ++n; if (tick) tick(tick_ctx, name); if (stop_after > 0 && n >= stop_after) return ADN_OK; } while (0)
+#define MBR_GEMM(G, name) do { cudaError_t e_ = tc::launch((G).plan, (G).args, EPI_LIN, sms, st); \
+    if (e_ != cudaSuccess) { err = std::string("gemm launch: ") + cudaGetErrorString(e_); return ADN_ERR_CUDA; } MBR_TICK(name); } while (0)
 
   adn_status run(const void* d_in, void* d_out, int B, cudaStream_t st) override {
     if (!ensure(B)) return ADN_ERR_CUDA;
@@ -564,7 +564,7 @@ class Model : public ModelImpl {
     const int B2 = B * CH;
     // 1-2: conditioning + STFT (reference kernel pre-scaled by 1/32768 for int16 input, :327-328)
     gtcrn::launch_prep(d_in, in_dtype, xp, nullptr, nullptr, B2, W, Lp, NFFT / 2, 0, 1, st);
-    MBR_TICK();
+    MBR_TICK("prep");
     {
       GemmArgs g;
       memset(&g, 0, sizeof(g));
@@ -572,19 +572,19 @@ class Model : public ModelImpl {
       g.W = d_fwd; g.ldw = NFFT; g.M = B2 * T; g.N = 2050; g.K = NFFT;
       g.C = spec; g.c_sB = (long long)T * LD; g.c_sT = LD; g.c_sN = 1;
       launch_gemm_ffma(g, EPI_STORE, st);
-      MBR_TICK();
+      MBR_TICK("stft_gemm");
     }
     gather_kernel<<<(unsigned)Mf, 256, (size_t)SD * sizeof(float), st>>>(spec, d_freq_idx, d_band_off, xg, xg + Mf * SD,
                                                                          rs_bs, T, (int)Mf, SD, nb);
-    MBR_TICK();
-    for (int i = 0; i < nb; ++i) MBR_GEMM(g_bs[i]);
+    MBR_TICK("gather");
+    for (int i = 0; i < nb; ++i) MBR_GEMM(g_bs[i], "bs_gemm");
     const unsigned rn_blocks = (unsigned)((M * 32 + 255) / 256);
     rownorm_kernel<<<rn_blocks, 256, 0, st>>>(x, rn, M, D);
-    MBR_TICK();
+    MBR_TICK("rownorm");
     for (int l = 0; l < 2 * depth; ++l) {
       LayerG& G = g_layers[l];
       const bool freq = l & 1;
-      MBR_GEMM(G.in);
+      MBR_GEMM(G.in, "in_proj");
       {
         const int nseq = freq ? nb : T;
         const long long nq = freq ? Mf : (long long)nb * B;
@@ -593,22 +593,22 @@ class Model : public ModelImpl {
         if (!cfg) { cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); cfg = true; }
         attention_kernel<<<dim3((unsigned)nq, heads), ATT_WARPS * 32, smem, st>>>(
             qkvg, DQ, freq ? fcos : tcos, freq ? fsin : tsin, ao, ao + M * DI, nseq, freq ? Mf : 1, freq ? 1 : 0, heads);
-        MBR_TICK();
+        MBR_TICK(freq ? "attention_freq" : "attention_time");
       }
-      MBR_GEMM(G.out);
+      MBR_GEMM(G.out, "out_proj");
       rownorm_kernel<<<rn_blocks, 256, 0, st>>>(x, rn, M, D);
-      MBR_TICK();
-      MBR_GEMM(G.ff1);
-      MBR_GEMM(G.ff2);
+      MBR_TICK("rownorm");
+      MBR_GEMM(G.ff1, "ff1");
+      MBR_GEMM(G.ff2, "ff2");
       renorm_kernel<<<rn_blocks, 256, 0, st>>>(x, layers[l].out_g, xpl, xpl + M * D, rn, M, D);
-      MBR_TICK();
+      MBR_TICK("renorm");
     }
-    MBR_GEMM(g_me1);
-    MBR_GEMM(g_me2);
-    for (int i = 0; i < nb; ++i) MBR_GEMM(g_me3[i]);
+    MBR_GEMM(g_me1, "me1");
+    MBR_GEMM(g_me2, "me2");
+    for (int i = 0; i < nb; ++i) MBR_GEMM(g_me3[i], "me3");
     mask_apply_kernel<<<(unsigned)Mf, 256, 0, st>>>(me3out, d_dst_src, d_src_a, d_src_g, spec, enh, T, pad,
                                                    (long long)2 * SD);
-    MBR_TICK();
+    MBR_TICK("mask_apply");
     {
       GemmArgs g;
       memset(&g, 0, sizeof(g));
@@ -619,7 +619,7 @@ class Model : public ModelImpl {
       g.W = d_ola; g.ldw = R * LD; g.M = B2 * g.TM; g.N = HOP; g.K = R * LD;
       g.norm = d_norm; g.norm_mul = 0; g.hop = HOP; g.shift = half; g.out_len = W; g.out_dtype = out_dtype; g.out = d_out;
       launch_gemm_ffma(g, EPI_ISTFT, st);
-      MBR_TICK();
+      MBR_TICK("istft_gemm");
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("mbr run: ") + cudaGetErrorString(e); return ADN_ERR_CUDA; }

@@ -10,8 +10,12 @@ struct TensorRef {
   uint64_t offset, count;
 };
 
+typedef void (*ImplTickFn)(void* ctx, const char* name);
+
 struct ModelImpl {
   std::string err;
+  ImplTickFn tick = nullptr;   // called after every launch (per-kernel event timing), may be null
+  void* tick_ctx = nullptr;
   virtual ~ModelImpl() {}
   virtual void io_info(adn_tensor_info* in, adn_tensor_info* out) = 0;
   virtual adn_status run(const void* d_in, void* d_out, int batch, cudaStream_t st) = 0;

@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Benchmark of the north-star path: noisy chunk in -> clean chunk out (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl adn|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model gtcrn|mbr] [--batch B] [--impl adn|reference]
 
-A "step" is one pass of the hot path over one batch of B synthetic 1 s chunks per GPU.
+A "step" is one pass of the hot path over one batch of B synthetic chunks per GPU.
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field's definition.
 """
 from __future__ import annotations
@@ -27,10 +27,6 @@ import torch  # noqa: E402
 
 METRIC = "audio_seconds_per_second"
 UNIT = "audio-s/s"
-CHUNK = 16000          # 1 s @ 16 kHz
-SR = 16000
-T_FRAMES = 63
-L_OUT = 15872
 
 
 def peaks():
@@ -42,31 +38,170 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
 
 
-# Algorithmic work per chunk of each kernel (DESIGN.md "Kernels"): (bytes moved to/from HBM
-# if every operand is touched exactly once, fp32 flops).  T=63 frames, F=257.
-def kernel_work():
-    T = T_FRAMES
-    f16 = 16 * 33 * 4 * T           # one (T,16,33) fp32 activation
-    spec = 514 * 4 * T
-    return {
-        "prep": (CHUNK * 4 + 16512 * 4, 2 * CHUNK),
-        "stft_gemm": (16512 * 4 + spec, 2 * 514 * 512 * T),
-        "stft_gemm_tc": (2 * 16512 * 4 + spec, 2 * 514 * 512 * T),
-        "istft_gemm_tc": (2 * spec + L_OUT * 4, 2 * 514 * 512 * T),
-        "enc_front": (spec + 16 * 65 * 4 * T + f16, 2 * T * (65 * 720 + 33 * 16 * 40 + 3 * 2 * 192)),
-        "gt_main": (f16 // 2 + f16 // 2 + 8 * 4 * T, 2 * T * 33 * (384 + 144 + 128)),
-        "tra_gru": (2 * 8 * 4 * T, 2 * T * (3 * 16 * 24 + 128)),
-        "tra_apply": (f16 // 2 + f16 // 2 + f16, T * 528),
-        "dp_intra": (2 * f16 + 3 * f16, 2 * T * (33 * 16 * 3 * 12 + 2 * 33 * 256 + 33 * 48 * 8) + 8 * T * 528),
-        "dp_inter": (3 * f16 + f16, 2 * T * 33 * 16 * 3 * 8),
-        "ln_res": (4 * f16, 2 * T * 33 * 256 + 8 * T * 528),
-        "dec_tail": (f16 + 16 * 65 * 4 * T + 2 * spec, 2 * T * (65 * 16 * 20 + 129 * 2 * 40 + 2 * 2 * 192 + 4 * 257)),
-        "istft_gemm": (spec + L_OUT * 4, 2 * 514 * 512 * T),
-    }
+# =====================================================================================
+# workloads
+# =====================================================================================
+class GtcrnWorkload:
+    """GTCRN 16 kHz, 1 s chunks (BASELINE.json configs[0] shape, batched)."""
+    name = "gtcrn"
+    default_batch = 512
+    chunk, sr, channels, t_frames, l_out = 16000, 16000, 1, 63, 15872
+    cpu_chunks, ref_chunks = 600, 24
+    cpu_desc = "oracle/gtcrn_oracle.py (PyTorch-eager restatement of the graph ORT would run)"
+
+    def describe(self, B):
+        return f"GTCRN 16 kHz, {B} x 1 s chunks per GPU per step, F32 in / F32 out"
+
+    def audio_seconds(self, B):
+        return B * self.chunk / self.sr
+
+    def weights(self):
+        import gtcrn_oracle as go
+        return go.random_state_dict(0)
+
+    def build(self, sd, device):
+        from adn import export
+        return export.gtcrn_model(sd, self.chunk, "F32", "F32", device_id=device)
+
+    def export(self, sd, path):
+        from adn import export
+        export.export_gtcrn(sd, path, self.chunk, "F32", "F32")
+
+    def inputs(self, B, n_sets, seed):
+        from make_golden import synth_audio
+        base = synth_audio(self.chunk, seed, min(B, 64))
+        sets = []
+        for s in range(n_sets):
+            g = torch.Generator().manual_seed(seed + 1 + s)
+            idx = torch.randint(0, base.shape[0], (B,), generator=g)
+            gain = 0.25 + 0.75 * torch.rand(B, 1, 1, generator=g)
+            x = torch.roll(base[idx] * gain, shifts=int(torch.randint(0, self.chunk, (1,), generator=g)), dims=-1)
+            sets.append(x.contiguous())
+        return sets
+
+    def cpu_rate(self, sd, n_chunks, threads):
+        import gtcrn_oracle as go
+        from make_golden import synth_audio
+        torch.set_num_threads(threads)
+        x = synth_audio(self.chunk, 4321, 4)
+        with torch.inference_mode():
+            for i in range(3):
+                go.gtcrn_forward(sd, x[i % 4:i % 4 + 1])
+            t0 = time.perf_counter()
+            for i in range(n_chunks):
+                go.gtcrn_forward(sd, x[i % 4:i % 4 + 1])
+            dt = time.perf_counter() - t0
+        return n_chunks * self.chunk / self.sr / dt, dt
+
+    def kernel_work(self):
+        """Algorithmic (bytes, flops) per chunk and per LAUNCH of each kernel."""
+        T = self.t_frames
+        f16 = 16 * 33 * 4 * T
+        spec = 514 * 4 * T
+        return {
+            "prep": (self.chunk * 4 + 3 * 16512 * 4, 2 * self.chunk),
+            "stft_gemm": (16512 * 4 + spec, 2 * 514 * 512 * T),
+            "stft_gemm_tc": (2 * 16512 * 4 + spec, 2 * 514 * 512 * T),
+            "istft_gemm_tc": (2 * spec + self.l_out * 4, 2 * 514 * 512 * T),
+            "istft_gemm": (spec + self.l_out * 4, 2 * 514 * 512 * T),
+            "enc_front": (spec + 16 * 65 * 4 * T + f16, 2 * T * (65 * 720 + 33 * 16 * 40 + 3 * 2 * 192)),
+            "gt_main": (f16 // 2 + f16 // 2 + 8 * 4 * T, 2 * T * 33 * (384 + 144 + 128)),
+            "tra_gru": ((8 + 8) * 4 * T, 2 * T * (3 * 16 * 24 + 128)),
+            "tra_apply": (f16 // 2 + f16 // 2 + f16, T * 528),
+            "dp_intra": (2 * f16 + 3 * f16, 2 * T * (33 * 16 * 3 * 12 + 2 * 33 * 256 + 33 * 48 * 8) + 8 * T * 528),
+            "dp_inter": (3 * f16 + f16, 2 * T * 33 * 16 * 3 * 8),
+            "ln_res": (4 * f16, 2 * T * 33 * 256 + 8 * T * 528),
+            "dec_tail": (f16 + 16 * 65 * 4 * T + 4 * spec, 2 * T * (65 * 16 * 20 + 129 * 2 * 40 + 2 * 2 * 192 + 4 * 257)),
+        }
+
+
+class MbrWorkload:
+    """Mel-Band-Roformer stereo 44.1 kHz, the reference's default 1.5 s fold windows (66150 samples,
+    T=151), depth 6 (BASELINE.json configs[3] model; an 8 s segment = 6 such windows)."""
+    name = "mbr"
+    default_batch = 16
+    chunk, sr, channels, t_frames, depth = 66150, 44100, 2, 151, 6
+    cpu_chunks, ref_chunks = 4, 1
+    cpu_desc = "oracle/mbr_oracle.py (PyTorch-eager restatement, bit-equal to the reference module)"
+
+    def describe(self, B):
+        return (f"Mel-Band-Roformer stereo 44.1 kHz depth {self.depth}, {B} x 1.5 s fold windows (66150 samples) "
+                f"per GPU per step, F32 in / F32 out")
+
+    def audio_seconds(self, B):
+        return B * self.chunk / self.sr
+
+    def weights(self):
+        import mbr_oracle as mo
+        return mo.random_state_dict(mo.MbrConfig(depth=self.depth), 0)
+
+    def build(self, sd, device):
+        from adn import export, mbr_params
+        return export.mbr_model(sd, mbr_params.MbrHyper(depth=self.depth), self.chunk, "F32", "F32", device_id=device)
+
+    def export(self, sd, path):
+        from adn import export, mbr_params
+        export.export_mbr(sd, path, mbr_params.MbrHyper(depth=self.depth), self.chunk, "F32", "F32")
+
+    def inputs(self, B, n_sets, seed):
+        sets = []
+        for s in range(n_sets):
+            g = torch.Generator().manual_seed(seed + s)
+            x = 0.2 * torch.randn(B, 2, self.chunk, generator=g)
+            t = torch.arange(self.chunk, dtype=torch.float32) / self.sr
+            x = x + 0.3 * torch.sin(2 * torch.pi * (220.0 + 10 * s) * t).reshape(1, 1, -1)
+            sets.append((x / x.abs().amax() * 0.5).contiguous())
+        return sets
+
+    def cpu_rate(self, sd, n_chunks, threads):
+        import mbr_oracle as mo
+        cfg = mo.MbrConfig(depth=self.depth)
+        fw = mo.fuse(sd, cfg)
+        torch.set_num_threads(threads)
+        g = torch.Generator().manual_seed(7)
+        x = (torch.rand(1, 2, self.chunk, generator=g) * 2 - 1) * 0.3
+        with torch.inference_mode():
+            mo.mbr_forward(cfg, fw, x)
+            t0 = time.perf_counter()
+            for _ in range(n_chunks):
+                mo.mbr_forward(cfg, fw, x)
+            dt = time.perf_counter() - t0
+        return n_chunks * self.chunk / self.sr / dt, dt
+
+    def kernel_work(self):
+        """Algorithmic (bytes, flops) per window and per LAUNCH of each kernel."""
+        T, nb, D, DI, DQ, DH, SD = self.t_frames, 60, 384, 512, 1544, 1536, 7916
+        M = nb * T
+
+        def gemm(m, k, n, outs=1):          # A planes (hi+lo) in, `outs` fp32-sized outputs
+            return (4 * (2 * m * k + outs * m * n), 2 * m * k * n)
+
+        return {
+            "prep": (2 * (self.chunk + 68200) * 4, 0),
+            "stft_gemm": (2 * (68200 * 4 + 2050 * 4 * T), 2 * 2 * 2050 * 2048 * T),
+            "gather": (2 * 2050 * 4 * T + 2 * SD * 4 * T, 2 * SD * T),
+            "bs_gemm": (4 * (2 * T * SD + 3 * M * D) // nb, 2 * T * SD * D // nb),
+            "rownorm": (M * D * 4, 2 * M * D),
+            "in_proj": gemm(M, D, DQ),
+            "attention_time": (M * DQ * 4 + 2 * M * DI * 4, 4 * nb * 8 * T * T * 64),
+            "attention_freq": (M * DQ * 4 + 2 * M * DI * 4, 4 * T * 8 * nb * nb * 64),
+            "out_proj": gemm(M, DI, D, 4),
+            "ff1": gemm(M, D, DH, 2),
+            "ff2": gemm(M, DH, D, 2),
+            "renorm": (M * D * 4 * 4, 6 * M * D),
+            "me1": gemm(M, D, DH, 2),
+            "me2": gemm(M, DH, DH, 2),
+            "me3": (4 * (2 * M * DH + T * 2 * SD) // nb, 2 * T * 2 * SD * DH // nb),
+            "mask_apply": (T * 2 * SD * 4 + 4 * 2050 * 4 * T, 12 * 2050 * T),
+            "istft_gemm": (2 * (2050 * 4 * T + self.chunk * 4), 2 * 2 * (T + 3) * 441 * 5 * 2056),
+        }
+
+
+WORKLOADS = {"gtcrn": GtcrnWorkload, "mbr": MbrWorkload}
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the GPU loops."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -90,11 +225,10 @@ class ClockSampler:
                 pass
             self._stop.wait(0.1)
 
-    def __enter__(self):
+    def start(self):
         self._t.start()
-        return self
 
-    def __exit__(self, *a):
+    def stop(self):
         self._stop.set()
         self._t.join(timeout=6)
 
@@ -108,76 +242,37 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": sorted(reasons),
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
 
 
-def make_inputs(batch: int, n_sets: int, seed: int = 1234):
-    """Synthetic speech-like chunks.  n_sets distinct batches so consecutive
-    steps never re-read the same input lines from L2."""
-    from make_golden import synth_audio
-
-    base = synth_audio(CHUNK, seed, min(batch, 64))
-    sets = []
-    for s in range(n_sets):
-        g = torch.Generator().manual_seed(seed + 1 + s)
-        idx = torch.randint(0, base.shape[0], (batch,), generator=g)
-        gain = 0.25 + 0.75 * torch.rand(batch, 1, 1, generator=g)
-        x = base[idx] * gain
-        x = torch.roll(x, shifts=int(torch.randint(0, CHUNK, (1,), generator=g)), dims=-1)
-        sets.append(x.contiguous())
-    return sets
-
-
-def cpu_oracle_rate(sd, n_chunks: int, threads: int):
-    """Reference-arm / cpu_baseline: the oracle port of the reference's PyTorch graph, one
-    (1,1,L) call per chunk like process_segment (Inference_GTCRN_ONNX.py:314-317)."""
-    import gtcrn_oracle as go
-    from make_golden import synth_audio
-
-    torch.set_num_threads(threads)
-    x = synth_audio(CHUNK, 4321, 4)
-    with torch.inference_mode():
-        for i in range(3):
-            go.gtcrn_forward(sd, x[i % 4:i % 4 + 1])
-        t0 = time.perf_counter()
-        for i in range(n_chunks):
-            go.gtcrn_forward(sd, x[i % 4:i % 4 + 1])
-        dt = time.perf_counter() - t0
-    return n_chunks * (CHUNK / SR) / dt, dt
-
-
-def run_reference(args):
+def run_reference(args, wl):
     """`--impl reference`: the reference's CPU implementation of the path on the host cores.
-    onnxruntime / onnx are not installable here and /root/reference does not travel, so this
-    arm times the oracle port (PyTorch eager, the modules the ONNX graph is traced from)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    onnxruntime / onnx are not installable here and /root/reference does not travel, so this arm
+    times the oracle port (PyTorch eager: the modules the ONNX graph is traced from)."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    import gtcrn_oracle as go
-
-    sd = go.random_state_dict(0)
+    sd = wl.weights()
     threads = os.cpu_count() or 1
-    per_step = args.ref_chunks
-    torch.set_num_threads(threads)
-    for _ in range(max(args.warmup, 3)):
-        cpu_oracle_rate(sd, 2, threads)
+    per_step = args.ref_chunks or wl.ref_chunks
+    wl.cpu_rate(sd, 1, threads)
     t0 = time.perf_counter()
     total = 0
     for _ in range(args.steps):
-        _, _ = cpu_oracle_rate(sd, per_step, threads)
+        wl.cpu_rate(sd, per_step, threads)
         total += per_step
     dt = time.perf_counter() - t0
-    val = total * (CHUNK / SR) / dt
+    val = total * wl.chunk / wl.sr / dt
+    B = args.batch or wl.default_batch
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"GTCRN 16 kHz, {args.batch} x 1 s chunks per GPU, F32 I/O (CPU arm: bounded sample of "
-                               f"{per_step} chunks per step, chunk-at-a-time)", "model": "gtcrn"},
+        "config": {"workload": wl.describe(B) + f" (CPU arm: bounded sample of {per_step} chunks per step, "
+                                                "chunk-at-a-time)", "model": wl.name},
         "rtf": 1.0 / val,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{per_step} chunks/step x {args.steps} steps, oracle/gtcrn_oracle.py (PyTorch eager "
-                                   f"restatement of Export_GTCRN.py; ORT itself is not installable offline)"},
+                         "sample": f"{per_step} chunks/step x {args.steps} steps; {wl.cpu_desc}; ORT itself is not "
+                                   "installable offline"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -186,22 +281,25 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=0)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=512, help="chunks per GPU per step")
+    ap.add_argument("--model", default="gtcrn", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="chunks per GPU per step (default: per model)")
     ap.add_argument("--impl", default="adn", choices=["adn", "reference"])
-    ap.add_argument("--ref-chunks", type=int, default=24, help="CPU chunks per step for --impl reference")
-    ap.add_argument("--cpu-baseline-chunks", type=int, default=600)
+    ap.add_argument("--ref-chunks", type=int, default=0, help="CPU chunks per step for --impl reference")
+    ap.add_argument("--cpu-baseline-chunks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-
+    wl = WORKLOADS[args.model]()
+    if args.steps <= 0:
+        args.steps = 100 if args.model == "gtcrn" else 10
     if args.impl == "reference":
-        run_reference(args)
+        args.steps = min(args.steps, 20)
+        run_reference(args, wl)
         return
 
-    import gtcrn_oracle as go   # seeded synthetic weights only (no compute from oracle/ in the timed path)
-    from adn import _lib, build, export
+    from adn import _lib, build
     import adn.ort_shim as onnxruntime
 
     rank = int(os.environ.get("RANK", "0"))
@@ -218,13 +316,16 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     build.build()
 
-    B = args.batch
-    sd = go.random_state_dict(0)
-    model = export.gtcrn_model(sd, CHUNK, "F32", "F32", device_id=local_rank)
-    n_sets = 8                                           # 8 x 32 MiB inputs > 126 MB L2
-    host_sets = make_inputs(B, n_sets, seed=1234 + rank)
+    B = args.batch or wl.default_batch
+    sd = wl.weights()                      # seeded synthetic weights (no compute from oracle/ on the GPU path)
+    model = wl.build(sd, local_rank)
+    out_info = model.outputs[0]
+    out_shape = (B, out_info.channels, out_info.length)
+    in_bytes = B * wl.channels * wl.chunk * 4
+    n_sets = max(2, min(8, int(np.ceil(160 * 2**20 / in_bytes))))      # rotated inputs exceed the 126 MB L2
+    host_sets = wl.inputs(B, n_sets, seed=1234 + rank)
     dev_sets = [x.to(dev) for x in host_sets]
-    out = torch.empty((B, 1, L_OUT), dtype=torch.float32, device=dev)
+    out = torch.empty(out_shape, dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream(dev)
 
     def barrier():
@@ -232,71 +333,78 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def allmax(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ---------------- device-resident throughput ("value")
     for i in range(args.warmup):
         model.run(dev_sets[i % n_sets], out=out)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clk = ClockSampler(local_rank)
-    clk.__enter__()              # sampled across all GPU loops of this run (timed + per-kernel + e2e)
+    clk.start()                                           # sampled across all GPU loops of this run
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(args.steps):
         model.run(dev_sets[i % n_sets], out=out)
     e1.record(stream)
     barrier()
-    ms = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    audio_s = world * B * args.steps * (CHUNK / SR)
+    ms = allmax(e0.elapsed_time(e1))
+    audio_s = world * wl.audio_seconds(B) * args.steps
     value = audio_s / (ms * 1e-3)
 
     # ---------------- per-kernel device times (CUDA events on the launching stream)
     model.set_profiling(True)
     acc: dict[str, list[float]] = {}
-    for i in range(args.steps):
+    psteps = min(args.steps, 20)
+    for i in range(psteps):
         model.run(dev_sets[i % n_sets], out=out)
         torch.cuda.synchronize(dev)
         for name, t_ms in model.kernel_times():
             acc.setdefault(name, []).append(t_ms)
     model.set_profiling(False)
-    per_kernel = {k: (sum(v) / args.steps, len(v) // args.steps) for k, v in acc.items()}   # (ms per step, launches)
+    per_kernel = {k: (sum(v) / psteps, max(1, len(v) // psteps)) for k, v in acc.items()}   # (ms/step, launches/step)
     step_ms_prof = sum(v[0] for v in per_kernel.values())
     pk = peaks()
-    work = kernel_work()
+    work = wl.kernel_work()
     top = max(per_kernel, key=lambda k: per_kernel[k][0])
-    top_ms, top_launches = per_kernel[top]
-    launch_ms = top_ms / top_launches
-    wb, wf = work[top]
-    t_hbm = wb * B / (pk["hbm_gbs"] * 1e9)
-    t_tc = wf * B / (pk["bf16_tflops_sustained"] * 1e12)
+    top_ms, n_l = per_kernel[top]
+    launch_ms = top_ms / n_l
+    wb, wf = work[top]                                    # per chunk and per launch
+    lb, lf = wb * B, wf * B
+    t_hbm = lb / (pk["hbm_gbs"] * 1e9)
+    t_tc = lf / (pk["bf16_tflops_sustained"] * 1e12)
     if t_hbm >= t_tc:
-        roof = {"bound": "hbm", "achieved": wb * B / (launch_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s"}
+        roof = {"bound": "hbm", "achieved": lb / (launch_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s"}
     else:
-        roof = {"bound": "tensor", "achieved": wf * B / (launch_ms * 1e-3) / 1e12,
-                "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s"}
+        roof = {"bound": "tensor", "achieved": lf / (launch_ms * 1e-3) / 1e12, "peak": pk["bf16_tflops_sustained"],
+                "unit": "TFLOP/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof.update({"traffic": None, "kernel": top, "kernel_ms_per_launch": launch_ms,
+    roof.update({"traffic": None, "kernel": top, "kernel_ms_per_launch": launch_ms, "launches_per_step": n_l,
                  "kernel_share_of_step": top_ms / step_ms_prof, "peak_source": pk["src"],
-                 "algorithmic_bytes_per_launch": wb * B, "algorithmic_flops_per_launch": wf * B})
+                 "algorithmic_bytes_per_launch": lb, "algorithmic_flops_per_launch": lf,
+                 "note": "3xTF32 kernels issue 3 tf32 MMAs per algorithmic MAC: their ceiling is bf16 peak / 6"})
 
     # ---------------- end to end through the reference-facing API, host buffers
     # (OrtValue over pinned host memory -> run_with_iobinding -> adn_run_host: H2D, kernels, D2H)
+    launches = model.launches_per_run(B)
+    ws_mib = model.workspace_bytes(B) / 2**20
+    model.close()
+    del dev_sets, out
+    torch.cuda.empty_cache()
     tmpdir = Path(os.environ.get("TMPDIR", "/tmp")) / f"adn_bench_{os.getpid()}"
     tmpdir.mkdir(parents=True, exist_ok=True)
-    mpath = tmpdir / "GTCRN.adn"
-    export.export_gtcrn(sd, mpath, CHUNK, "F32", "F32")
+    mpath = tmpdir / f"{wl.name}.adn"
+    wl.export(sd, mpath)
     sess = onnxruntime.InferenceSession(str(mpath), providers=["CPUExecutionProvider"], device_id=local_rank)
+    mpath.unlink(missing_ok=True)
     pin_in = [x.pin_memory() for x in host_sets]
-    pin_out = torch.empty((B, 1, L_OUT), dtype=torch.float32).pin_memory()
+    pin_out = torch.empty(out_shape, dtype=torch.float32).pin_memory()
     vout = onnxruntime.OrtValue.ortvalue_from_numpy(pin_out.numpy())
-    vout._a = pin_out.numpy()                                   # keep the pinned storage (no copy)
-    vins = []
-    for p in pin_in:
-        v = onnxruntime.OrtValue.ortvalue_from_numpy(p.numpy())
-        v._a = p.numpy()
-        vins.append(v)
+    vins = [onnxruntime.OrtValue.ortvalue_from_numpy(p.numpy()) for p in pin_in]
     bind = sess.io_binding()
     bind.bind_ortvalue_output("denoised_audio", vout)
     checksum = 0.0
@@ -310,46 +418,40 @@ def main():
         sess.run_with_iobinding(bind)                           # synchronous, result is in host memory
         checksum += float(pin_out[0, 0, 0])
     barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    if dist is not None:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_ms = allmax((time.perf_counter() - t0) * 1e3)
     e2e_value = audio_s / (e2e_ms * 1e-3)
-    clk.__exit__(None, None, None)
+    clk.stop()
 
     # ---------------- CPU baseline on this box's host cores (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        rate, dt = cpu_oracle_rate(sd, args.cpu_baseline_chunks, threads)
+        n = args.cpu_baseline_chunks or wl.cpu_chunks
+        rate, dt = wl.cpu_rate(sd, n, threads)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{args.cpu_baseline_chunks} of the {B} chunks of one step, chunk-at-a-time, {dt:.1f} s; "
-                         "oracle/gtcrn_oracle.py (PyTorch-eager restatement of the graph ORT would run)"}
+               "sample": f"{n} of the {B} chunks of one step, chunk-at-a-time, {dt:.1f} s; {wl.cpu_desc}"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"GTCRN 16 kHz, {B} x 1 s chunks per GPU per step, F32 in / F32 out",
-                       "model": "gtcrn", "batch_per_gpu": B, "chunk_samples": CHUNK,
-                       "l2_policy": f"{n_sets} distinct input batches rotated ({n_sets * B * CHUNK * 4 / 2**20:.0f} MiB) "
-                                    f"+ {model.workspace_bytes(B) / 2**20:.0f} MiB workspace streamed per step, both > 126 MB L2",
+            "config": {"workload": wl.describe(B), "model": wl.name, "batch_per_gpu": B, "chunk_samples": wl.chunk,
+                       "l2_policy": f"{n_sets} distinct input batches rotated ({n_sets * in_bytes / 2**20:.0f} MiB) "
+                                    f"+ {ws_mib:.0f} MiB workspace streamed per step, both > 126 MB L2",
                        "parallelism": f"batch-shard x{world}, weights replicated, no data-path collective"},
             "rtf": 1.0 / value,
             "clocks": clk.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * CHUNK * 4,
-                    "d2h_bytes_per_step": B * L_OUT * 4, "ms_per_step": e2e_ms / args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": int(np.prod(out_shape)) * 4, "ms_per_step": e2e_ms / args.steps,
                     "api": "adn.ort_shim.InferenceSession.run_with_iobinding -> adn_run_host (pinned host buffers)"},
-            "gpu_launches": model.launches_per_run(B) * args.steps,
+            "gpu_launches": launches * args.steps,
             "roofline": roof,
             "cpu_baseline": cpu,
             "kernels_ms_per_step": {k: round(v[0], 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][0])},
             "lib": _lib.lib().adn_version().decode(),
         }
         print(json.dumps(line))
-    model.close()
     if dist is not None:
         dist.destroy_process_group()
 

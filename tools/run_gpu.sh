@@ -1,7 +1,7 @@
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests -m gpu -x -q -s > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
 grep -E "tc vs|passed|failed|FAIL|Error|error|wave " gpurun_out/pytest_gpu.log | head -20
-timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench.log 2>&1
+timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench.log 2>&1
 python - <<PY
 import json
 l=open("gpurun_out/bench.log").read().strip().splitlines()[-1]
