@@ -1,7 +1,14 @@
-"""Chunk scheduler: the host loop of `Inference_GTCRN_ONNX.py:276-333` (pad -> fixed
-windows -> run -> concatenate -> trim), with the B200 difference that all windows of a
-file (or of many files) are stacked into ONE batched run instead of a Python while-loop
-of batch-1 runs.  Window/stride/padding arithmetic is the reference's, bit for bit."""
+"""Chunk scheduler: the host loop of `Inference_GTCRN_ONNX.py:276-333` /
+`Mel_Band_Roformer/Stereo/Inference_MelBandRoformer_ONNX.py:266-345` (pad -> fixed windows -> run ->
+concatenate -> trim), with the B200 difference that all windows of a file (or of many files) are
+stacked into ONE batched run instead of a Python while-loop of batch-1 runs.  Window / stride /
+padding arithmetic is the reference's, bit for bit.
+
+Batch fold (reference default for Mel-Band-Roformer, `Export_MelBandRoformer.py:46-51,645-650`):
+the graph reshapes `(1, C, n*W)` into `n` independent windows `(n*C, 1, W)`, window-major /
+channel-minor, and stitches them back.  Here the model already takes `(B, C, W)` windows, so
+folding *is* the host-side split with stride W and a zero-padded tail (`:298-300`).
+"""
 from __future__ import annotations
 
 import numpy as np
@@ -20,38 +27,76 @@ def plan_windows(audio_len: int, in_len: int, out_len: int, same_rate: bool = Tr
     return stride, num, total
 
 
-def split(audio: np.ndarray, in_len: int, out_len: int) -> tuple[np.ndarray, int]:
-    """audio (N,) -> windows (num_windows, 1, in_len) (zero-padded tail), stride."""
-    n = audio.shape[-1]
+def tail_pad(audio: np.ndarray, pad_amount: int, mode: str = "zeros", rng=None) -> np.ndarray:
+    """audio (C, N) -> (C, N+pad).  'zeros' (GTCRN :291-298, folded Mel-Band :298-300) or 'noise':
+    RMS-matched gaussian tail of the un-folded Mel-Band script (:301-303, :309-311)."""
+    if pad_amount <= 0:
+        return audio
+    c = audio.shape[0]
+    if mode == "zeros":
+        block = np.zeros((c, pad_amount), dtype=audio.dtype)
+    elif mode == "noise":
+        rng = rng or np.random.default_rng()
+        ref = audio[:, -pad_amount:] if audio.shape[1] > pad_amount else audio
+        ref = ref.astype(np.float32)
+        rms = np.sqrt(np.mean(ref * ref, dtype=np.float32), dtype=np.float32)
+        block = (rms * rng.normal(loc=0.0, scale=1.0, size=(c, pad_amount))).astype(audio.dtype)
+    else:
+        raise ValueError(f"unknown tail pad mode {mode!r}")
+    return np.concatenate((audio, block), axis=-1)
+
+
+def split(audio: np.ndarray, in_len: int, out_len: int, tail: str = "zeros", rng=None) -> tuple[np.ndarray, int]:
+    """audio (N,) or (C, N) -> windows (num_windows, C, in_len), stride."""
+    a = np.asarray(audio)
+    if a.ndim == 1:
+        a = a.reshape(1, -1)
+    n = a.shape[-1]
     stride, num, total = plan_windows(n, in_len, out_len)
-    a = audio.reshape(-1)
-    if total > n:
-        a = np.concatenate((a, np.zeros(total - n, dtype=a.dtype)))
+    a = tail_pad(a, total - n, tail, rng)
     idx = np.arange(num)[:, None] * stride + np.arange(in_len)[None, :]
-    return np.ascontiguousarray(a[idx]).reshape(num, 1, in_len), stride
+    w = a[:, idx]                                   # (C, num, in_len)
+    return np.ascontiguousarray(w.transpose(1, 0, 2)), stride
 
 
-def denoise(session, audio: np.ndarray, max_batch: int = 4096) -> np.ndarray:
-    """Whole-file drop-in for the reference's run section (:306-332): returns the
-    concatenated output trimmed to the input length (`[:audio_len]`, :332)."""
+def match_channels(audio: np.ndarray, channels: int) -> np.ndarray:
+    """Mono -> duplicated channels, extra channels dropped (Inference_MelBandRoformer_ONNX.py:273-287)."""
+    a = np.asarray(audio)
+    if a.ndim == 1:
+        a = a.reshape(1, -1)
+    if a.shape[0] < channels:
+        a = np.concatenate((a, np.repeat(a[-1:], channels - a.shape[0], axis=0)), axis=0)
+    elif a.shape[0] > channels:
+        a = a[:channels]
+    return a
+
+
+def denoise(session, audio: np.ndarray, max_batch: int = 4096, tail: str = "zeros", rng=None) -> np.ndarray:
+    """Whole-file drop-in for the reference's run section: returns the concatenated output trimmed
+    to the input length (`[:audio_len]`, GTCRN :332 / Mel-Band :345).  audio (N,) -> (N,) for mono
+    models, (C, N) -> (C, N) otherwise."""
     from .ort_shim import OrtValue
 
     i = session.get_inputs()[0]
     o = session.get_outputs()[0]
-    in_len, out_len = i.shape[-1], o.shape[-1]
-    audio = np.asarray(audio).reshape(-1)
-    windows, _ = split(audio, in_len, out_len)
+    chans, in_len, out_len = i.shape[-2], i.shape[-1], o.shape[-1]
+    mono_in = np.asarray(audio).ndim == 1
+    a = match_channels(audio, chans)
+    n = a.shape[-1]
+    windows, _ = split(a, in_len, out_len, tail, rng)
     outs = []
     for s in range(0, windows.shape[0], max_batch):
-        w = windows[s:s + max_batch]
+        w = np.ascontiguousarray(windows[s:s + max_batch])
         vin = OrtValue.ortvalue_from_numpy(w)
-        vout = OrtValue.ortvalue_from_numpy(np.zeros((w.shape[0], 1, out_len), dtype=_np_dtype(o.type)))
+        vout = OrtValue.ortvalue_from_numpy(np.zeros((w.shape[0], o.shape[-2], out_len), dtype=_np_dtype(o.type)))
         b = session.io_binding()
         b.bind_ortvalue_input(i.name, vin)
         b.bind_ortvalue_output(o.name, vout)
         session.run_with_iobinding(b)
         outs.append(vout.numpy())
-    return np.concatenate(outs, axis=0).reshape(-1)[: audio.shape[0]]
+    y = np.concatenate(outs, axis=0)                # (num, C, out_len)
+    y = y.transpose(1, 0, 2).reshape(y.shape[1], -1)[:, :n]
+    return y.reshape(-1) if (mono_in and y.shape[0] == 1) else y
 
 
 def _np_dtype(ort_type: str):

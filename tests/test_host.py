@@ -160,3 +160,49 @@ def test_ort_shim_surface_without_gpu(tmp_path):
     ro = onnxruntime.RunOptions()
     ro.add_run_config_entry("disable_synchronize_execution_providers", "0")
     assert onnxruntime.capi._pybind_state.OrtDevice.cpu() == 0
+
+
+def test_fold_split_is_reference_fold():
+    """Host-side fold == the graph's `audio.reshape(C, n, W).transpose(0, 1)` (Export_MelBandRoformer.py:648)
+    plus the zero tail pad of the folded loop (Inference_MelBandRoformer_ONNX.py:298-300)."""
+    from adn import chunker
+
+    W, C, n = 441 * 4, 2, 3
+    a = np.arange(C * (n * W - 100), dtype=np.float32).reshape(C, -1)
+    w, stride = chunker.split(a, W, W)
+    assert w.shape == (n, C, W) and stride == W
+    padded = np.concatenate((a, np.zeros((C, 100), np.float32)), axis=-1)
+    ref = torch.from_numpy(padded).reshape(C, n, W).transpose(0, 1).numpy()
+    assert np.array_equal(w, ref)
+    # mono -> both channels, extra channels dropped (:273-287)
+    assert np.array_equal(chunker.match_channels(np.arange(5), 2), np.stack([np.arange(5)] * 2))
+    assert chunker.match_channels(np.zeros((3, 7)), 2).shape == (2, 7)
+    # un-folded script: RMS-matched gaussian tail (:301-303)
+    x = np.random.default_rng(0).normal(size=(2, 1000)).astype(np.float32)
+    p = chunker.tail_pad(x, 400, "noise", np.random.default_rng(1))
+    assert p.shape == (2, 1400) and np.array_equal(p[:, :1000], x)
+    assert abs(float(p[:, 1000:].std()) - float(np.sqrt(np.mean(x[:, -400:] ** 2)))) < 0.15
+
+
+def test_mbr_packing_and_band_layout_match_oracle():
+    """Product host code (adn/mbr_params.py) vs the oracle's restatement of the reference fusions."""
+    import mbr_oracle as mo
+    from adn import mbr_params as mp
+
+    cfg, h = mo.MbrConfig(depth=1), mp.MbrHyper(depth=1)
+    i1, w1, d1 = mo.band_layout(cfg)
+    i2, w2, d2 = mp.band_layout(h)
+    assert torch.equal(i1, i2) and w1 == w2 and torch.equal(d1, d2)
+    assert len(w1) == 60 and sum(w1) == 7916 and i1.numel() == 3958          # SURVEY A.3
+    sd = mo.random_state_dict(cfg, 0)
+    fw, blob = mo.fuse(sd, cfg), mp.pack(sd, h, 4410)
+    for b in (0, 17, 59):
+        assert np.array_equal(blob[f"bs_w.{b}"], fw[f"bs_w_{b}"].numpy())
+        assert np.array_equal(blob[f"me_w3.{b}"], fw[f"me_w3_{b}"].numpy())
+    assert np.array_equal(blob["tf.0.in_w"], fw["time0_in_w"].numpy())
+    assert np.array_equal(blob["tf.1.ff2_w"], fw["freq0_ff2_w"].numpy())
+    assert np.array_equal(blob["me_w2"], fw["me_w2t"].transpose(1, 2).numpy())
+    tc, ts, fc, fs = mo.rotary_tables(cfg, 11)
+    assert np.array_equal(blob["rope.tcos"], tc.numpy()) and np.array_equal(blob["rope.fsin"], fs.numpy())
+    md = mp.metadata(h, 4410)
+    assert md["model_family"] == "mel_band_roformer" and md["input_channels"] == "2"

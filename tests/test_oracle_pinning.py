@@ -152,3 +152,47 @@ def test_gtcrn_oracle_matches_reference_modules():
         yo = go.gtcrn_forward(sd, x)
     assert yr.shape == yo.shape == (1, 1, 15872)
     assert (yr - yo).abs().max() <= 2e-6 * max(1.0, float(yr.abs().max()))
+
+
+# ----------------------------------------------------------------------------- Mel-Band-Roformer
+@pytest.mark.parametrize("fixture,dt", [("mbr_f32_L4410_d2", "F32"), ("mbr_int16_L13230_d2", "INT16")])
+def test_mbr_oracle_matches_golden(fixture, dt, golden_dir):
+    import mbr_oracle as mo
+
+    g = np.load(golden_dir / f"{fixture}.npz")
+    cfg = mo.MbrConfig(depth=int(g["depth"]))
+    fw = mo.fuse(mo.random_state_dict(cfg, int(g["seed"])), cfg)
+    y = mo.mbr_forward_batch(cfg, fw, torch.from_numpy(g["x"]), dt, dt).numpy()
+    assert y.shape == g["y"].shape and y.dtype == g["y"].dtype
+    if dt == "INT16":
+        assert np.abs(y.astype(np.int32) - g["y"].astype(np.int32)).max() <= 1
+    else:
+        assert np.abs(y - g["y"]).max() <= 1e-6
+
+
+@needs_ref
+def test_mbr_oracle_matches_reference_module():
+    """Restated forward + fusions vs the reference's own MelBandRoformer on identical seeded
+    weights: fused buffers, band layout and rotary tables bit-equal, waveform <= 1e-6."""
+    import mbr_oracle as mo
+    from make_golden import mbr_kwargs
+
+    cfg = mo.MbrConfig(depth=1)
+    L = 4410
+    sd = mo.random_state_dict(cfg, 3)
+    _, build = ref_loader.load_mbr(L, "F32")
+    m = build(sd, **mbr_kwargs(cfg))
+    fw = mo.fuse(sd, cfg)
+    assert all(torch.equal(getattr(m, k), v) for k, v in fw.items())
+    idx, dim_inputs, _ = mo.band_layout(cfg)
+    assert torch.equal(idx.to(torch.int32), m.freq_indices) and tuple(dim_inputs) == tuple(m.dim_inputs)
+    tc, ts, fc, fs = mo.rotary_tables(cfg, L // 441 + 1)
+    assert torch.equal(tc, m.time_cos[0, 0]) and torch.equal(ts, m.time_sin[0, 0])
+    assert torch.equal(fc, m.freq_cos[0, 0]) and torch.equal(fs, m.freq_sin[0, 0])
+    g = torch.Generator().manual_seed(1)
+    x = (torch.rand(1, 2, L, generator=g) * 2 - 1) * 0.5
+    with torch.inference_mode():
+        yr = m(x)
+        yo = mo.mbr_forward(cfg, fw, x)
+    assert yr.shape == yo.shape == (1, 2, L)
+    assert (yr - yo).abs().max() <= 1e-6
