@@ -22,7 +22,7 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 32;                 // 32 fp32 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 8;              // tf32: 32 bytes of K per instruction
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;           // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 constexpr uint32_t A_TILE_BYTES = BM * BK * 4;   // 16 KiB
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -121,7 +121,8 @@ struct Smem {
   static constexpr uint32_t W_TILE_BYTES = BN * BK * 4;
   static constexpr uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * W_TILE_BYTES;
   static constexpr int STAGES = (BN <= 128) ? 3 : 2;
-  static constexpr uint32_t TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t EPI_STAGE_BYTES = 8 * 16 * 36 * 4;      // per-warp 16x36 transpose tiles of the epilogue
+  static constexpr uint32_t TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 };
 
 template <int BN, int EPI>
@@ -138,6 +139,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   uint64_t* tfull = bars + 2 * S::STAGES;   // [2]
   uint64_t* tempty = tfull + 2;             // [2]
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  float* stage = (float*)(smem + S::STAGES * S::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles_n = (g.N + BN - 1) / BN;
@@ -157,7 +159,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -231,6 +233,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;             // the two warps of a quarter take alternate 32-column chunks
     const int r = q * 32 + lane;                   // row of the tile
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -246,11 +249,75 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       tc_fence_after();
       const uint32_t taddr = tmem_base + ab * 256 + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = chalf * 32; c0 < BN; c0 += 64) {
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait();
         const int n0 = nt * BN + c0;
+        if (EPI == EPI_LIN) {
+          // Linear layer: v = act(acc * rowscale[m] + bias[n]) (+ residual) -> fp32 and/or tf32 planes.
+          // The TMEM load gives lane = row; a per-warp smem transpose turns that into lane = column
+          // quad so every global access is a full 128-byte row segment (8 lanes x 16 B, 4 rows/instr).
+          float* stg = stage + (warp - 2) * (16 * 36);
+          const int cq = lane & 7;
+          const bool col_ok = (c0 + 4 * cq < BN) && (n0 + 4 * cq < g.N);      // N, BN, ldc multiples of 4
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          bool have_bias = false;
+#pragma unroll
+          for (int hrow = 0; hrow < 2; ++hrow) {             // 16 rows at a time through a 16x36 tile
+            if ((lane >> 4) == hrow) {
+#pragma unroll
+              for (int j0 = 0; j0 < 8; ++j0)
+                *reinterpret_cast<float4*>(stg + (lane & 15) * 36 + 4 * j0) =
+                    make_float4(__uint_as_float(v[4 * j0]), __uint_as_float(v[4 * j0 + 1]),
+                                __uint_as_float(v[4 * j0 + 2]), __uint_as_float(v[4 * j0 + 3]));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int rl = it * 4 + (lane >> 3);
+              const int r2 = q * 32 + hrow * 16 + rl;
+              int b2, t2;
+              if (g.bb > 1) { int bi = r2 / g.bt; b2 = mt * g.bb + bi; t2 = r2 - bi * g.bt; if (bi >= g.bb) b2 = g.B; }
+              else { b2 = mt / g.tiles_per_chunk; t2 = (mt - b2 * g.tiles_per_chunk) * BM + r2; }
+              b2 += g.b_off;
+              if (!col_ok || b2 >= g.B || t2 >= g.TM) continue;
+              if (g.bias && (!have_bias || g.w_batched)) {
+                bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + (long long)b2 * g.bias_bstride + n0) + cq);
+                have_bias = true;
+              }
+              const long long m = (long long)b2 * g.TM + t2;
+              const float rs = g.rowscale ? __ldg(g.rowscale + m) : 1.0f;
+              const float4 a4 = *reinterpret_cast<const float4*>(stg + rl * 36 + 4 * cq);
+              float x[4] = {a4.x * rs + bias4.x, a4.y * rs + bias4.y, a4.z * rs + bias4.z, a4.w * rs + bias4.w};
+              if (g.act == ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = 0.5f * x[j] * (1.0f + erff(x[j] * 0.70710678118654752440f));
+              } else if (g.act == ACT_TANH) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = tanhf(x[j]);
+              }
+              const long long o = m * g.ldc + n0 + 4 * cq;
+              if (g.resid) {
+                const float4 r4 = *reinterpret_cast<const float4*>(g.resid + o);
+                x[0] += r4.x; x[1] += r4.y; x[2] += r4.z; x[3] += r4.w;
+              }
+              if (g.C) *reinterpret_cast<float4*>(g.C + o) = make_float4(x[0], x[1], x[2], x[3]);
+              if (g.Chi) {
+                float h[4], l[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  h[j] = __uint_as_float(__float_as_uint(x[j]) & 0xFFFFE000u);
+                  l[j] = x[j] - h[j];
+                }
+                *reinterpret_cast<float4*>(g.Chi + o) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(g.Clo + o) = make_float4(l[0], l[1], l[2], l[3]);
+              }
+            }
+            __syncwarp();
+          }
+          continue;
+        }
         if (!row_ok || n0 >= g.N) continue;
         if (EPI == EPI_STORE) {
           float* dst = g.C + (long long)b * g.c_sB + (long long)t * g.c_sT + n0;
@@ -263,39 +330,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (c0 + j < BN && n0 + j < g.N) dst[j] = __uint_as_float(v[j]);
-          }
-        } else if (EPI == EPI_LIN) {
-          // Linear layer: v = act(acc * rowscale[m] + bias[n]) (+ residual) -> fp32 and/or tf32 planes
-          const long long m = (long long)b * g.TM + t;
-          const float rs = g.rowscale ? __ldg(g.rowscale + m) : 1.0f;
-          const long long o = m * g.ldc + n0;
-#pragma unroll
-          for (int j0 = 0; j0 < 32; j0 += 4) {
-            if (c0 + j0 >= BN || n0 + j0 >= g.N) continue;     // N, BN and ldc are multiples of 4
-            float x[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float a = __uint_as_float(v[j0 + j]) * rs;
-              if (g.bias) a += __ldg(g.bias + (long long)b * g.bias_bstride + n0 + j0 + j);
-              if (g.act == ACT_GELU) a = 0.5f * a * (1.0f + erff(a * 0.70710678118654752440f));
-              else if (g.act == ACT_TANH) a = tanhf(a);
-              x[j] = a;
-            }
-            if (g.resid) {
-              const float4 r4 = *reinterpret_cast<const float4*>(g.resid + o + j0);
-              x[0] += r4.x; x[1] += r4.y; x[2] += r4.z; x[3] += r4.w;
-            }
-            if (g.C) *reinterpret_cast<float4*>(g.C + o + j0) = make_float4(x[0], x[1], x[2], x[3]);
-            if (g.Chi) {
-              float h[4], l[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                h[j] = __uint_as_float(__float_as_uint(x[j]) & 0xFFFFE000u);
-                l[j] = x[j] - h[j];
-              }
-              *reinterpret_cast<float4*>(g.Chi + o + j0) = make_float4(h[0], h[1], h[2], h[3]);
-              *reinterpret_cast<float4*>(g.Clo + o + j0) = make_float4(l[0], l[1], l[2], l[3]);
-            }
           }
         } else {
           // ISTFT: s = (t + t0)*hop + n - shift ; y = acc (/|*) norm[s]

@@ -186,6 +186,155 @@ attention_kernel(const float* __restrict__ qkvg, int ldq, const float* __restric
 }
 
 // ---------------------------------------------------------------------------------
+// attention2: same math as attention_kernel for sequences that fit in shared memory (n <= 160)
+// organised as two register-tiled shared-memory GEMMs (4x4 outputs per thread, 16 FMA per
+// 2 (scores) / 5 (PV) shared loads) around an in-place row softmax.
+//   smem: Qt[64][np] | Kt[64][np] | V[n][64] | S[n][np+1] | rinv[n]      (np = n rounded up to 4)
+// ---------------------------------------------------------------------------------
+constexpr int ATT2_THREADS = 512;
+
+__host__ __device__ inline size_t att2_smem_floats(int n) {
+  const int np = (n + 3) & ~3;
+  size_t s_region = (size_t)n * (np + 1);
+  const size_t tmp = (size_t)2 * n * 65;            // staging of rotated q,k aliases the S region
+  if (tmp > s_region) s_region = tmp;
+  return (size_t)2 * 64 * np + (size_t)n * 64 + s_region + (size_t)((n + 3) & ~3) + 4;
+}
+
+__global__ void __launch_bounds__(ATT2_THREADS)
+attention2_kernel(const float* __restrict__ qkvg, int ldq, const float* __restrict__ rcos,
+                  const float* __restrict__ rsin, float* __restrict__ ao_hi, float* __restrict__ ao_lo, int n,
+                  long long stride, int freq_mode, int heads) {
+  extern __shared__ __align__(16) float sm2[];
+  const int np = (n + 3) & ~3, ns = np + 1;
+  float* Qt = sm2;                               // [64][np]
+  float* Kt = Qt + 64 * np;                      // [64][np]
+  float* Vs = Kt + 64 * np;                      // [n][64]
+  float* S = Vs + (size_t)n * 64;                // [n][ns]   (first used as tq[n][65] | tk[n][65])
+  size_t s_region = (size_t)n * ns;
+  if ((size_t)2 * n * 65 > s_region) s_region = (size_t)2 * n * 65;
+  float* rinv = S + ((s_region + 3) & ~(size_t)3);   // [n]  gate / softmax sum
+  float* tq = S;
+  float* tk = S + (size_t)n * 65;
+  const int q = blockIdx.x, head = blockIdx.y, tid = threadIdx.x;
+  const int di = heads * DHEAD;
+  const long long base = freq_mode ? (long long)q : (long long)q * n;
+
+  // phase 0a: coalesced row loads, rotary on q,k
+  for (int i = tid; i < n * 32; i += ATT2_THREADS) {
+    const int s = i >> 5, p = i & 31;
+    const float* row = qkvg + (base + (long long)s * stride) * ldq + head * DHEAD;
+    const float2 qq = *reinterpret_cast<const float2*>(row + 2 * p);
+    const float2 kk = *reinterpret_cast<const float2*>(row + di + 2 * p);
+    const float2 vv = *reinterpret_cast<const float2*>(row + 2 * di + 2 * p);
+    const float2 c = *reinterpret_cast<const float2*>(rcos + s * DHEAD + 2 * p);
+    const float2 sn = *reinterpret_cast<const float2*>(rsin + s * DHEAD + 2 * p);
+    tq[s * 65 + 2 * p] = qq.x * c.x + qq.y * sn.x;
+    tq[s * 65 + 2 * p + 1] = qq.y * c.y + qq.x * sn.y;
+    tk[s * 65 + 2 * p] = kk.x * c.x + kk.y * sn.x;
+    tk[s * 65 + 2 * p + 1] = kk.y * c.y + kk.x * sn.y;
+    *reinterpret_cast<float2*>(Vs + s * 64 + 2 * p) = vv;
+  }
+  __syncthreads();
+  // phase 0b: transpose to [d][s] (zero the padded columns)
+  for (int i = tid; i < 64 * np; i += ATT2_THREADS) {
+    const int d = i / np, s = i - d * np;
+    Qt[i] = s < n ? tq[s * 65 + d] : 0.f;
+    Kt[i] = s < n ? tk[s * 65 + d] : 0.f;
+  }
+  __syncthreads();
+
+  // phase 1: S = Q K^T
+  const int nt = np >> 2;
+  for (int tile = tid; tile < nt * nt; tile += ATT2_THREADS) {
+    const int i0 = (tile / nt) * 4, j0 = (tile - (tile / nt) * nt) * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) {
+      const float4 qa = *reinterpret_cast<const float4*>(Qt + k * np + i0);
+      const float4 kb = *reinterpret_cast<const float4*>(Kt + k * np + j0);
+      const float qv[4] = {qa.x, qa.y, qa.z, qa.w}, kv[4] = {kb.x, kb.y, kb.z, kb.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(qv[a], kv[c], acc[a][c]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (i0 + a < n && j0 + c < n) S[(i0 + a) * ns + j0 + c] = acc[a][c];
+  }
+  __syncthreads();
+
+  // phase 2: row softmax (unnormalised exp in place; gate / sum kept per row)
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int i = warp; i < n; i += ATT2_THREADS / 32) {
+      float* sr = S + i * ns;
+      float mx = -INFINITY;
+      for (int j = lane; j < n; j += 32) mx = fmaxf(mx, sr[j]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.f;
+      for (int j = lane; j < n; j += 32) {
+        const float e = expf(sr[j] - mx);
+        sr[j] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      if (lane == 0) {
+        const long long row = base + (long long)i * stride;
+        rinv[i] = adn_sigmoid(__ldg(qkvg + row * ldq + 3 * di + head)) / sum;
+      }
+    }
+  }
+  __syncthreads();
+
+  // phase 3: O = P V, scaled by gate/sum, written as tf32 planes
+  for (int tile = tid; tile < nt * 16; tile += ATT2_THREADS) {
+    const int i0 = (tile >> 4) * 4, d0 = (tile & 15) * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+    const float* s0 = S + (size_t)i0 * ns;
+    const int r1 = (i0 + 1 < n) ? 1 : 0, r2 = (i0 + 2 < n) ? 2 : 0, r3 = (i0 + 3 < n) ? 3 : 0;
+#pragma unroll 4
+    for (int j = 0; j < n; ++j) {
+      const float4 v4 = *reinterpret_cast<const float4*>(Vs + j * 64 + d0);
+      const float pv[4] = {s0[j], s0[r1 * ns + j], s0[r2 * ns + j], s0[r3 * ns + j]};
+      const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(pv[a], vv[c], acc[a][c]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int i = i0 + a;
+      if (i >= n) continue;
+      const float sc = rinv[i];
+      const long long o = (base + (long long)i * stride) * di + head * DHEAD + d0;
+      float h[4], l[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float x = acc[a][c] * sc;
+        h[c] = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+        l[c] = x - h[c];
+      }
+      *reinterpret_cast<float4*>(ao_hi + o) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(ao_lo + o) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // mask_apply: GLU of the mask-estimator output, scatter-add as a gather over the (<= 2)
 // contributing bands of every (freq,chan) row (:615-618, averaging pre-folded into the weights),
 // complex mask on the spectrum (:620-623), de-interleave into the per-channel ISTFT input.
@@ -588,11 +737,21 @@ class Model : public ModelImpl {
       {
         const int nseq = freq ? nb : T;
         const long long nq = freq ? Mf : (long long)nb * B;
-        const size_t smem = ((size_t)nseq * 65 + 4 + (size_t)nseq * 64 + (size_t)ATT_WARPS * (nseq + 4) + ATT_WARPS * 64) * sizeof(float);
         static bool cfg = false;
-        if (!cfg) { cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); cfg = true; }
-        attention_kernel<<<dim3((unsigned)nq, heads), ATT_WARPS * 32, smem, st>>>(
-            qkvg, DQ, freq ? fcos : tcos, freq ? fsin : tsin, ao, ao + M * DI, nseq, freq ? Mf : 1, freq ? 1 : 0, heads);
+        if (!cfg) {
+          cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+          cfg = true;
+        }
+        const size_t smem2 = att2_smem_floats(nseq) * sizeof(float);
+        if (smem2 <= 220 * 1024) {
+          attention2_kernel<<<dim3((unsigned)nq, heads), ATT2_THREADS, smem2, st>>>(
+              qkvg, DQ, freq ? fcos : tcos, freq ? fsin : tsin, ao, ao + M * DI, nseq, freq ? Mf : 1, freq ? 1 : 0, heads);
+        } else {
+          const size_t smem = ((size_t)nseq * 65 + 4 + (size_t)nseq * 64 + (size_t)ATT_WARPS * (nseq + 4) + ATT_WARPS * 64) * sizeof(float);
+          attention_kernel<<<dim3((unsigned)nq, heads), ATT_WARPS * 32, smem, st>>>(
+              qkvg, DQ, freq ? fcos : tcos, freq ? fsin : tsin, ao, ao + M * DI, nseq, freq ? Mf : 1, freq ? 1 : 0, heads);
+        }
         MBR_TICK(freq ? "attention_freq" : "attention_time");
       }
       MBR_GEMM(G.out, "out_proj");
