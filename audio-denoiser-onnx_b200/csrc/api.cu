@@ -418,6 +418,87 @@ adn_status build_gtcrn(adn_model* m, const float* hblob) {
   return ADN_OK;
 }
 
+
+// Two-range pipelining hooks for adn_run_host: the front stage (conditioning + STFT) of a range
+// starts as soon as its H2D copy has landed, the D2H copy of a range starts as soon as its ISTFT
+// is done; the backbone in between runs once over the whole batch.
+struct PhaseSync {
+  int mid;                          // ranges [0, mid) and [mid, batch); mid is even
+  cudaEvent_t h2d_done[2];          // waited on before the front stage of each range
+  cudaEvent_t out_ready[2];         // recorded after the tail stage of each range
+};
+
+adn_status gtcrn_run(adn_model* m, const void* d_in, void* d_out, int batch, cudaStream_t st, const PhaseSync* ps) {
+  adn_status s = ensure_capacity(m, batch);
+  if (s != ADN_OK) return s;
+  m->ev_used = 0;
+  m->ev_stream = st;
+  int n = 0;
+  tick_cb(m, "start");
+  const int nr = ps ? 2 : 1;
+  const int lo[2] = {0, ps ? ps->mid : 0}, hi[2] = {ps ? ps->mid : batch, batch};
+  const size_t in_row = (size_t)m->L * dtype_size(m->in_dtype);
+  GemmArgs g;
+
+  for (int r = 0; r < nr; ++r) {
+    const int b0 = lo[r], nb = hi[r] - lo[r];
+    if (ps) ADN_CUDA_TRY(cudaStreamWaitEvent(st, ps->h2d_done[r], 0), m->err);
+    gtcrn::launch_prep((const char*)d_in + b0 * in_row, m->in_dtype, m->buf.xp + (size_t)b0 * m->Lp,
+                       m->buf.xp_hi ? m->buf.xp_hi + (size_t)b0 * m->Lp : nullptr,
+                       m->buf.xp_lo ? m->buf.xp_lo + (size_t)b0 * m->Lp : nullptr, nb, m->L, m->Lp, m->stft.half,
+                       /*remove_dc=*/1, m->stft.reflect, st);
+    if (r == 0) { ++n; tick_cb(m, "prep"); }
+    if (m->use_tc) {
+      tc::TcArgs a = m->stft_args;
+      a.b_off = b0;
+      a.B = hi[r];
+      a.m_tiles = a.bb > 1 ? (nb + a.bb - 1) / a.bb : nb * a.tiles_per_chunk;
+      ADN_CUDA_TRY(tc::launch(m->stft_plan, a, EPI_STORE, m->sms, st), m->err);
+      if (r == 0) { ++n; tick_cb(m, "stft_gemm_tc"); }
+    } else {
+      fill_stft_gemm(g, m->stft, m->buf.xp + (size_t)b0 * m->Lp, m->Lp, m->d_fwd, nb, m->T,
+                     m->buf.spec + (size_t)b0 * m->T * gtcrn::SPEC_LD, (long long)m->T * gtcrn::SPEC_LD,
+                     gtcrn::SPEC_LD, 1);
+      launch_gemm_ffma(g, EPI_STORE, st);
+      if (r == 0) { ++n; tick_cb(m, "stft_gemm"); }
+    }
+  }
+
+  gtcrn::Dims d{batch, m->L, m->Lp, m->T};
+  const int stop_bb = m->stop_after > 0 ? (m->stop_after > n ? m->stop_after - n : 1) : 0;
+  n += gtcrn::launch_backbone(m->w, m->buf, d, m->stft.pad_frames(), st, tick_cb, m, stop_bb);
+  m->last_launches = n;
+  m->last_batch = batch;
+  if (m->stop_after > 0 && n >= m->stop_after) {
+    ADN_CUDA_TRY(cudaGetLastError(), m->err);
+    return ADN_OK;
+  }
+
+  const size_t out_row = (size_t)m->Lout * dtype_size(m->out_dtype);
+  for (int r = 0; r < nr; ++r) {
+    const int b0 = lo[r], nb = hi[r] - lo[r];
+    if (m->use_tc) {
+      tc::TcArgs a = m->istft_args;
+      a.b_off = b0;
+      a.B = hi[r];
+      a.m_tiles = a.bb > 1 ? (nb + a.bb - 1) / a.bb : nb * a.tiles_per_chunk;
+      a.out = d_out;
+      ADN_CUDA_TRY(tc::launch(m->istft_plan, a, EPI_ISTFT, m->sms, st), m->err);
+      if (r == 0) { ++n; tick_cb(m, "istft_gemm_tc"); }
+    } else {
+      fill_istft_gemm(g, m->stft, m->buf.enh + (size_t)b0 * (m->T + 2 * m->stft.pad_frames()) * gtcrn::SPEC_LD,
+                      m->d_ola, m->d_norm, nb, m->T, (char*)d_out + b0 * out_row, m->out_dtype);
+      launch_gemm_ffma(g, EPI_ISTFT, st);
+      if (r == 0) { ++n; tick_cb(m, "istft_gemm"); }
+    }
+    if (ps) ADN_CUDA_TRY(cudaEventRecord(ps->out_ready[r], st), m->err);
+  }
+  m->last_launches = n;
+  m->last_batch = batch;
+  ADN_CUDA_TRY(cudaGetLastError(), m->err);
+  return ADN_OK;
+}
+
 }  // namespace
 
 // ===================================================================================
@@ -601,59 +682,7 @@ adn_status adn_run(adn_model* m, const void* d_in, void* const* d_outs, int32_t 
     m->last_batch = batch;
     return r;
   }
-  adn_status s = ensure_capacity(m, batch);
-  if (s != ADN_OK) return s;
-  cudaStream_t st = (cudaStream_t)stream;
-  m->ev_used = 0;
-  m->ev_stream = st;
-  int n = 0;
-  tick_cb(m, "start");
-
-  gtcrn::launch_prep(d_in, m->in_dtype, m->buf.xp, m->buf.xp_hi, m->buf.xp_lo, batch, m->L, m->Lp, m->stft.half,
-                     /*remove_dc=*/1, m->stft.reflect, st);
-  ++n; tick_cb(m, "prep");
-
-  GemmArgs g;
-  if (m->use_tc) {
-    tc::TcArgs a = m->stft_args;
-    a.B = batch;
-    a.m_tiles = a.bb > 1 ? (batch + a.bb - 1) / a.bb : batch * a.tiles_per_chunk;
-    ADN_CUDA_TRY(tc::launch(m->stft_plan, a, EPI_STORE, m->sms, st), m->err);
-    ++n; tick_cb(m, "stft_gemm_tc");
-  } else {
-    fill_stft_gemm(g, m->stft, m->buf.xp, m->Lp, m->d_fwd, batch, m->T, m->buf.spec,
-                   (long long)m->T * gtcrn::SPEC_LD, gtcrn::SPEC_LD, 1);
-    launch_gemm_ffma(g, EPI_STORE, st);
-    ++n; tick_cb(m, "stft_gemm");
-  }
-
-  gtcrn::Dims d{batch, m->L, m->Lp, m->T};
-  const int stop_bb = m->stop_after > 0 ? (m->stop_after > n ? m->stop_after - n : 1) : 0;
-  n += gtcrn::launch_backbone(m->w, m->buf, d, m->stft.pad_frames(), st, tick_cb, m, stop_bb);
-  m->last_launches = n;
-  m->last_batch = batch;
-  if (m->stop_after > 0 && n >= m->stop_after) {
-    ADN_CUDA_TRY(cudaGetLastError(), m->err);
-    return ADN_OK;
-  }
-
-  if (m->use_tc) {
-    tc::TcArgs a = m->istft_args;
-    a.B = batch;
-    a.m_tiles = a.bb > 1 ? (batch + a.bb - 1) / a.bb : batch * a.tiles_per_chunk;
-    a.out = d_outs[0];
-    ADN_CUDA_TRY(tc::launch(m->istft_plan, a, EPI_ISTFT, m->sms, st), m->err);
-    ++n; tick_cb(m, "istft_gemm_tc");
-  } else {
-    fill_istft_gemm(g, m->stft, m->buf.enh, m->d_ola, m->d_norm, batch, m->T, d_outs[0], m->out_dtype);
-    launch_gemm_ffma(g, EPI_ISTFT, st);
-    ++n; tick_cb(m, "istft_gemm");
-  }
-
-  m->last_launches = n;
-  m->last_batch = batch;
-  ADN_CUDA_TRY(cudaGetLastError(), m->err);
-  return ADN_OK;
+  return gtcrn_run(m, d_in, d_outs[0], batch, (cudaStream_t)stream, nullptr);
 }
 
 adn_status adn_run_host(adn_model* m, const void* h_in, void* const* h_outs, int32_t batch) {
@@ -676,15 +705,8 @@ adn_status adn_run_host(adn_model* m, const void* h_in, void* const* h_outs, int
     s = ensure_capacity(m, batch);
     if (s != ADN_OK) return s;
   }
-  // Pipeline in sub-batches: H2D of slice i+1 and D2H of slice i-1 overlap the kernels of slice i
-  // (three streams, events in between).  The compute stream serialises the slices, so they share
-  // the workspace; the staging buffers are sliced.
   const size_t in_row = (size_t)m->chans * m->L * dtype_size(m->in_dtype);
   const size_t out_row = (size_t)m->chans * m->Lout * dtype_size(m->out_dtype);
-  // slices below ~512 chunks under-fill the GPU (the GRU kernels are latency-bound), so only very
-  // large batches are pipelined
-  const int nsub = batch >= 2048 ? 4 : (batch >= 1024 ? 2 : 1);
-  const int per = (batch + nsub - 1) / nsub;
   if (!m->ev_h2d[0]) {
     ADN_CUDA_TRY(cudaStreamCreateWithFlags(&m->st_in, cudaStreamNonBlocking), m->err);
     ADN_CUDA_TRY(cudaStreamCreateWithFlags(&m->st_out, cudaStreamNonBlocking), m->err);
@@ -694,27 +716,36 @@ adn_status adn_run_host(adn_model* m, const void* h_in, void* const* h_outs, int
     }
   }
   cudaStream_t st = m->own_stream;
-  for (int i = 0; i < nsub; ++i) {
-    const int b0 = i * per, nb = (b0 + per <= batch) ? per : batch - b0;
-    if (nb <= 0) break;
-    ADN_CUDA_TRY(cudaMemcpyAsync((char*)m->d_in + b0 * in_row, (const char*)h_in + b0 * in_row, nb * in_row,
-                                 cudaMemcpyHostToDevice, m->st_in), m->err);
-    ADN_CUDA_TRY(cudaEventRecord(m->ev_h2d[i], m->st_in), m->err);
-  }
-  for (int i = 0; i < nsub; ++i) {
-    const int b0 = i * per, nb = (b0 + per <= batch) ? per : batch - b0;
-    if (nb <= 0) break;
-    ADN_CUDA_TRY(cudaStreamWaitEvent(st, m->ev_h2d[i], 0), m->err);
-    void* outs[1] = {(char*)m->d_out + b0 * out_row};
-    s = adn_run(m, (char*)m->d_in + b0 * in_row, outs, nb, st);
+  if (!m->impl && batch >= 64 && m->stop_after == 0) {
+    // Two ranges: the second half's H2D overlaps the first half's conditioning + STFT, the first
+    // half's D2H overlaps the second half's ISTFT.  The backbone runs once over the whole batch
+    // (its GRU kernels are latency-bound, so slicing it would cost more than the copies).
+    PhaseSync ps;
+    ps.mid = (batch / 2) & ~1;
+    const int lo[2] = {0, ps.mid}, hi[2] = {ps.mid, batch};
+    for (int r = 0; r < 2; ++r) {
+      ADN_CUDA_TRY(cudaMemcpyAsync((char*)m->d_in + lo[r] * in_row, (const char*)h_in + lo[r] * in_row,
+                                   (hi[r] - lo[r]) * in_row, cudaMemcpyHostToDevice, m->st_in), m->err);
+      ADN_CUDA_TRY(cudaEventRecord(m->ev_h2d[r], m->st_in), m->err);
+      ps.h2d_done[r] = m->ev_h2d[r];
+      ps.out_ready[r] = m->ev_done[r];
+    }
+    s = gtcrn_run(m, m->d_in, m->d_out, batch, st, &ps);
     if (s != ADN_OK) return s;
-    ADN_CUDA_TRY(cudaEventRecord(m->ev_done[i], st), m->err);
-    ADN_CUDA_TRY(cudaStreamWaitEvent(m->st_out, m->ev_done[i], 0), m->err);
-    ADN_CUDA_TRY(cudaMemcpyAsync((char*)h_outs[0] + b0 * out_row, (char*)m->d_out + b0 * out_row, nb * out_row,
-                                 cudaMemcpyDeviceToHost, m->st_out), m->err);
+    for (int r = 0; r < 2; ++r) {
+      ADN_CUDA_TRY(cudaStreamWaitEvent(m->st_out, m->ev_done[r], 0), m->err);
+      ADN_CUDA_TRY(cudaMemcpyAsync((char*)h_outs[0] + lo[r] * out_row, (char*)m->d_out + lo[r] * out_row,
+                                   (hi[r] - lo[r]) * out_row, cudaMemcpyDeviceToHost, m->st_out), m->err);
+    }
+    ADN_CUDA_TRY(cudaStreamSynchronize(m->st_out), m->err);
+    ADN_CUDA_TRY(cudaStreamSynchronize(st), m->err);
+    return ADN_OK;
   }
-  m->last_batch = batch;
-  ADN_CUDA_TRY(cudaStreamSynchronize(m->st_out), m->err);
+  ADN_CUDA_TRY(cudaMemcpyAsync(m->d_in, h_in, batch * in_row, cudaMemcpyHostToDevice, st), m->err);
+  void* outs[1] = {m->d_out};
+  s = adn_run(m, m->d_in, outs, batch, st);
+  if (s != ADN_OK) return s;
+  ADN_CUDA_TRY(cudaMemcpyAsync(h_outs[0], m->d_out, batch * out_row, cudaMemcpyDeviceToHost, st), m->err);
   ADN_CUDA_TRY(cudaStreamSynchronize(st), m->err);
   return ADN_OK;
 }
