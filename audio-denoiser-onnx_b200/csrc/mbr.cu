@@ -191,7 +191,7 @@ attention_kernel(const float* __restrict__ qkvg, int ldq, const float* __restric
 // 2 (scores) / 5 (PV) shared loads) around an in-place row softmax.
 //   smem: Qt[64][np] | Kt[64][np] | V[n][64] | S[n][np+1] | rinv[n]      (np = n rounded up to 4)
 // ---------------------------------------------------------------------------------
-constexpr int ATT2_THREADS = 512;
+constexpr int ATT2_THREADS = 1024;
 
 __host__ __device__ inline size_t att2_smem_floats(int n) {
   const int np = (n + 3) & ~3;
@@ -201,7 +201,7 @@ __host__ __device__ inline size_t att2_smem_floats(int n) {
   return (size_t)2 * 64 * np + (size_t)n * 64 + s_region + (size_t)((n + 3) & ~3) + 4;
 }
 
-__global__ void __launch_bounds__(ATT2_THREADS)
+__global__ void __launch_bounds__(1024)
 attention2_kernel(const float* __restrict__ qkvg, int ldq, const float* __restrict__ rcos,
                   const float* __restrict__ rsin, float* __restrict__ ao_hi, float* __restrict__ ao_lo, int n,
                   long long stride, int freq_mode, int heads) {
@@ -217,11 +217,12 @@ attention2_kernel(const float* __restrict__ qkvg, int ldq, const float* __restri
   float* tq = S;
   float* tk = S + (size_t)n * 65;
   const int q = blockIdx.x, head = blockIdx.y, tid = threadIdx.x;
+  const int NT = blockDim.x;
   const int di = heads * DHEAD;
   const long long base = freq_mode ? (long long)q : (long long)q * n;
 
   // phase 0a: coalesced row loads, rotary on q,k
-  for (int i = tid; i < n * 32; i += ATT2_THREADS) {
+  for (int i = tid; i < n * 32; i += NT) {
     const int s = i >> 5, p = i & 31;
     const float* row = qkvg + (base + (long long)s * stride) * ldq + head * DHEAD;
     const float2 qq = *reinterpret_cast<const float2*>(row + 2 * p);
@@ -237,7 +238,7 @@ attention2_kernel(const float* __restrict__ qkvg, int ldq, const float* __restri
   }
   __syncthreads();
   // phase 0b: transpose to [d][s] (zero the padded columns)
-  for (int i = tid; i < 64 * np; i += ATT2_THREADS) {
+  for (int i = tid; i < 64 * np; i += NT) {
     const int d = i / np, s = i - d * np;
     Qt[i] = s < n ? tq[s * 65 + d] : 0.f;
     Kt[i] = s < n ? tk[s * 65 + d] : 0.f;
@@ -246,7 +247,7 @@ attention2_kernel(const float* __restrict__ qkvg, int ldq, const float* __restri
 
   // phase 1: S = Q K^T
   const int nt = np >> 2;
-  for (int tile = tid; tile < nt * nt; tile += ATT2_THREADS) {
+  for (int tile = tid; tile < nt * nt; tile += NT) {
     const int i0 = (tile / nt) * 4, j0 = (tile - (tile / nt) * nt) * 4;
     float acc[4][4];
 #pragma unroll
@@ -274,7 +275,7 @@ attention2_kernel(const float* __restrict__ qkvg, int ldq, const float* __restri
   // phase 2: row softmax (unnormalised exp in place; gate / sum kept per row)
   {
     const int warp = tid >> 5, lane = tid & 31;
-    for (int i = warp; i < n; i += ATT2_THREADS / 32) {
+    for (int i = warp; i < n; i += NT / 32) {
       float* sr = S + i * ns;
       float mx = -INFINITY;
       for (int j = lane; j < n; j += 32) mx = fmaxf(mx, sr[j]);
@@ -296,7 +297,7 @@ attention2_kernel(const float* __restrict__ qkvg, int ldq, const float* __restri
   __syncthreads();
 
   // phase 3: O = P V, scaled by gate/sum, written as tf32 planes
-  for (int tile = tid; tile < nt * 16; tile += ATT2_THREADS) {
+  for (int tile = tid; tile < nt * 16; tile += NT) {
     const int i0 = (tile >> 4) * 4, d0 = (tile & 15) * 4;
     float acc[4][4];
 #pragma unroll
@@ -745,7 +746,8 @@ class Model : public ModelImpl {
         }
         const size_t smem2 = att2_smem_floats(nseq) * sizeof(float);
         if (smem2 <= 220 * 1024) {
-          attention2_kernel<<<dim3((unsigned)nq, heads), ATT2_THREADS, smem2, st>>>(
+          const int att_threads = nseq > 96 ? 1024 : 512;     // small sequences: more CTAs per SM instead
+          attention2_kernel<<<dim3((unsigned)nq, heads), att_threads, smem2, st>>>(
               qkvg, DQ, freq ? fcos : tcos, freq ? fsin : tsin, ao, ao + M * DI, nseq, freq ? Mf : 1, freq ? 1 : 0, heads);
         } else {
           const size_t smem = ((size_t)nseq * 65 + 4 + (size_t)nseq * 64 + (size_t)ATT_WARPS * (nseq + 4) + ATT_WARPS * 64) * sizeof(float);
