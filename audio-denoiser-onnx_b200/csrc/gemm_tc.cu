@@ -254,7 +254,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait();
         const int n0 = nt * BN + c0;
-        if (EPI == EPI_LIN) {
+        if (EPI == EPI_LIN || EPI == EPI_ISTFT) {
           // Linear layer: v = act(acc * rowscale[m] + bias[n]) (+ residual) -> fp32 and/or tf32 planes.
           // The TMEM load gives lane = row; a per-warp smem transpose turns that into lane = column
           // quad so every global access is a full 128-byte row segment (8 lanes x 16 B, 4 rows/instr).
@@ -282,6 +282,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               else { b2 = mt / g.tiles_per_chunk; t2 = (mt - b2 * g.tiles_per_chunk) * BM + r2; }
               b2 += g.b_off;
               if (!col_ok || b2 >= g.B || t2 >= g.TM) continue;
+              if (EPI == EPI_ISTFT) {
+                // overlap-added block row -> 4 consecutive output samples: COLA normalise, scale, convert
+                const float4 a4 = *reinterpret_cast<const float4*>(stg + rl * 36 + 4 * cq);
+                const float xv[4] = {a4.x, a4.y, a4.z, a4.w};
+                const int s0 = (t2 + g.t0) * g.hop + n0 + 4 * cq - g.shift;
+                const long long ob = (long long)b2 * g.out_len;
+                if (s0 >= 0 && s0 + 3 < g.out_len && ((s0 | g.out_len) & 3) == 0 && n0 + 4 * cq + 3 < g.N) {
+                  const float4 nv = __ldg(reinterpret_cast<const float4*>(g.norm + s0));
+                  float y[4];
+                  if (g.norm_mul) { y[0] = xv[0] * nv.x; y[1] = xv[1] * nv.y; y[2] = xv[2] * nv.z; y[3] = xv[3] * nv.w; }
+                  else { y[0] = xv[0] / nv.x; y[1] = xv[1] / nv.y; y[2] = xv[2] / nv.z; y[3] = xv[3] / nv.w; }
+                  if (g.out_dtype == ADN_F32) {
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + ob + s0) = make_float4(y[0], y[1], y[2], y[3]);
+                  } else if (g.out_dtype == ADN_I16) {
+                    short q4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                      q4[j] = (short)(int)fminf(fmaxf(y[j] * 32767.0f, -32768.0f), 32767.0f);
+                    *reinterpret_cast<short4*>(reinterpret_cast<int16_t*>(g.out) + ob + s0) = make_short4(q4[0], q4[1], q4[2], q4[3]);
+                  } else {
+                    __half2 h01 = __floats2half2_rn(y[0], y[1]), h23 = __floats2half2_rn(y[2], y[3]);
+                    __half2* dst = reinterpret_cast<__half2*>(reinterpret_cast<__half*>(g.out) + ob + s0);
+                    dst[0] = h01; dst[1] = h23;
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const int sj = s0 + j;
+                    if (n0 + 4 * cq + j >= g.N || sj < 0 || sj >= g.out_len) continue;
+                    const float nv = __ldg(g.norm + sj);
+                    const float y = g.norm_mul ? xv[j] * nv : xv[j] / nv;
+                    if (g.out_dtype == ADN_F32) reinterpret_cast<float*>(g.out)[ob + sj] = y;
+                    else if (g.out_dtype == ADN_I16)
+                      reinterpret_cast<int16_t*>(g.out)[ob + sj] = (int16_t)(int)fminf(fmaxf(y * 32767.0f, -32768.0f), 32767.0f);
+                    else reinterpret_cast<__half*>(g.out)[ob + sj] = __float2half_rn(y);
+                  }
+                }
+                continue;
+              }
               if (g.bias && (!have_bias || g.w_batched)) {
                 bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + (long long)b2 * g.bias_bstride + n0) + cq);
                 have_bias = true;

@@ -204,17 +204,29 @@ tra_gru_kernel(const TraW w, const float* __restrict__ zt, float* __restrict__ t
 __global__ void __launch_bounds__(256)
 tra_apply_kernel(const float* __restrict__ at, const float* __restrict__ h1, const float* __restrict__ xin,
                  const float* __restrict__ skip, float* __restrict__ out, long long nframes) {
-  const long long total = nframes * FRAME16;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const long long fr = i / FRAME16;
-    const int rem = (int)(i - fr * FRAME16);
-    const int ch = rem / E1_F, f = rem - ch * E1_F;
-    const int c = ch >> 1;
-    float v;
-    if (ch & 1) v = __ldg(xin + fr * FRAME16 + (8 + c) * E1_F + f);
-    else v = __ldg(h1 + fr * (8 * E1_F) + c * E1_F + f) * __ldg(at + fr * 8 + c);
-    if (skip) v += __ldg(skip + i);
-    out[i] = v;
+  // 4 consecutive outputs per thread (FRAME16 = 528 is a multiple of 4): vector skip load / out store,
+  // scalar gathers for the two interleaved sources
+  const long long total4 = nframes * (FRAME16 / 4);
+  for (long long i4 = (long long)blockIdx.x * 256 + threadIdx.x; i4 < total4; i4 += (long long)gridDim.x * 256) {
+    const long long fr = i4 / (FRAME16 / 4);
+    const int rem0 = (int)(i4 - fr * (FRAME16 / 4)) * 4;
+    const float* hb = h1 + fr * (8 * E1_F);
+    const float* xb = xin + fr * FRAME16;
+    const float* ab = at + fr * 8;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rem = rem0 + j;
+      const int ch = rem / E1_F, f = rem - ch * E1_F;
+      const int c = ch >> 1;
+      v[j] = (ch & 1) ? __ldg(xb + (8 + c) * E1_F + f) : __ldg(hb + c * E1_F + f) * __ldg(ab + c);
+    }
+    const long long o = fr * FRAME16 + rem0;
+    if (skip) {
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(skip + o));
+      v[0] += s4.x; v[1] += s4.y; v[2] += s4.z; v[3] += s4.w;
+    }
+    *reinterpret_cast<float4*>(out + o) = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -456,7 +468,7 @@ void launch_tra_gru(const TraW& w, const float* zt, float* tgi, float* hbuf, flo
 void launch_tra_apply(const float* at, const float* h1, const float* xin, const float* skip, float* out, int B,
                       int T, cudaStream_t st) {
   const long long nframes = (long long)B * T;
-  long long blocks = (nframes * FRAME16 + 255) / 256;
+  long long blocks = (nframes * (FRAME16 / 4) + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   tra_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(at, h1, xin, skip, out, nframes);
 }
