@@ -155,8 +155,33 @@ def main_mbr():
             print(f"mbr {dt} L{L}: {tuple(xin.shape)} -> {tuple(y.shape)} max|y| {y.abs().max().item():.4f}")
 
 
+def main_mf2se():
+    """MossFormer2-SE-48K fixtures: the reference wrapper executed around `mf2se_oracle.skeleton()`
+    on seeded weights, 2 FLASH+FSMN layers (the layer count is the only reduced hyper-parameter),
+    windows of 31 and 26 frames, one all-zero window."""
+    import mf2se_oracle as mo
+
+    assert ref_loader.reference_available()
+    cfg = mo.Mf2Config(layers=2)
+    sd = mo.random_state_dict(cfg, 0)
+    hold = mo.skeleton(cfg)
+    hold.load_state_dict(sd)
+    with torch.inference_mode():
+        for L, dt in ((13440, "F32"), (11520, "INT16")):
+            _, build = ref_loader.load_mf2se(L, dt)
+            w = build(hold)
+            x = synth_audio(L, 4321, batch=3)
+            x[2] = 0.0
+            xin = x if dt == "F32" else torch.round(x * 32767.0).to(torch.int16)
+            y = torch.cat([w(xin[i:i + 1].clone()) for i in range(3)], dim=0)
+            np.savez_compressed(GOLDEN / f"mf2se_{dt.lower()}_L{L}_l2.npz", x=xin.numpy(), y=y.numpy(), seed=0, layers=2)
+            print(f"mf2se {dt} L{L}: {tuple(xin.shape)} -> {tuple(y.shape)} max|y| {y.float().abs().max().item():.4f}")
+
+
 if __name__ == "__main__":
     if "--mbr" in sys.argv:
         main_mbr()
+    elif "--mf2se" in sys.argv:
+        main_mf2se()
     else:
         main()

@@ -164,3 +164,42 @@ def load_mbr(input_audio_length: int, io_dtype: str = "F32"):
         return m
 
     return ns, build
+
+
+def load_mf2se(input_audio_length: int, io_dtype: str = "F32"):
+    """Reference MossFormer2-SE-48K wrapper (`MOSSFORMER_SE`) for one un-folded window.
+
+    The wrapper's forward is made of leaf ops; only its constructor reads the absent
+    `clearvoice` model.  Returns (namespace, build) with
+    build(holder) -> wrapper, where `holder` is `mf2se_oracle.skeleton()` carrying the weights."""
+    import torch
+
+    for name in ("clearvoice", "clearvoice.models", "clearvoice.models.mossformer2_se",
+                 "clearvoice.models.mossformer2_se.mossformer2_se_wrapper"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["clearvoice.models.mossformer2_se.mossformer2_se_wrapper"].MossFormer2_SE_48K = object
+
+    ns = load_export_namespace(
+        "MossFormer2_SE_48K",
+        "Export_MossFormer_SE.py",
+        {
+            "INPUT_AUDIO_LENGTH = 96000": f"INPUT_AUDIO_LENGTH = {int(input_audio_length)}",
+            "IN_AUDIO_DTYPE     = 'INT16'": f"IN_AUDIO_DTYPE     = '{io_dtype}'",
+            "OUT_AUDIO_DTYPE    = 'INT16'": f"OUT_AUDIO_DTYPE    = '{io_dtype}'",
+        },
+    )
+
+    def build(holder):
+        with torch.inference_mode():
+            S = ns["STFT_Process"]
+            stft = S(model_type="stft_B", n_fft=ns["NFFT"], hop_len=ns["HOP_LENGTH"], win_length=ns["WINDOW_LENGTH"],
+                     max_frames=0, window_type=ns["WINDOW_TYPE"], center_pad=False, pad_mode="constant").eval()
+            istft = S(model_type="istft_B", n_fft=ns["NFFT"], hop_len=ns["HOP_LENGTH"], win_length=ns["WINDOW_LENGTH"],
+                      max_frames=ns["MAX_SIGNAL_LENGTH"], window_type=ns["WINDOW_TYPE"], center_pad=False,
+                      pad_mode="constant", static_frames=True).eval()
+            outer = types.SimpleNamespace(mossformer=holder.eval().float())
+            return ns["MOSSFORMER_SE"](outer, stft, istft, ns["NFFT"], ns["N_MELS"], ns["IN_SAMPLE_RATE"],
+                                       ns["OUT_SAMPLE_RATE"], ns["MAX_SIGNAL_LENGTH"], False, ns["FOLD_WINDOW_LENGTH"]).eval()
+
+    return ns, build

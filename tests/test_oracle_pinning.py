@@ -9,7 +9,7 @@ import torch
 import gtcrn_oracle as go
 import ref_loader
 import stft_oracle as so
-from make_golden import STFT_CASES, ref_istft_forward, ref_stft_forward, ref_stft_pair, sd_digest
+from make_golden import STFT_CASES, ref_istft_forward, ref_stft_forward, ref_stft_pair, sd_digest, synth_audio
 
 needs_ref = pytest.mark.skipif(not ref_loader.reference_available(), reason="/root/reference not present")
 CASES = {c[0]: c for c in STFT_CASES}
@@ -196,3 +196,50 @@ def test_mbr_oracle_matches_reference_module():
         yo = mo.mbr_forward(cfg, fw, x)
     assert yr.shape == yo.shape == (1, 2, L)
     assert (yr - yo).abs().max() <= 1e-6
+
+
+# ----------------------------------------------------------------------------- MossFormer2-SE-48K
+@pytest.mark.parametrize("fixture,dt", [("mf2se_f32_L13440_l2", "F32"), ("mf2se_int16_L11520_l2", "INT16")])
+def test_mf2se_oracle_matches_golden(fixture, dt, golden_dir):
+    import mf2se_oracle as mo
+
+    g = np.load(golden_dir / f"{fixture}.npz")
+    cfg = mo.Mf2Config(layers=int(g["layers"]))
+    sd = mo.random_state_dict(cfg, int(g["seed"]))
+    with torch.inference_mode():
+        y = mo.mf2se_forward_batch(sd, torch.from_numpy(g["x"]), cfg, dt, dt, chunk=1).numpy()
+    assert y.shape == g["y"].shape and y.dtype == g["y"].dtype
+    if dt == "INT16":
+        assert np.abs(y.astype(np.int32) - g["y"].astype(np.int32)).max() <= 1
+    else:
+        assert np.abs(y - g["y"]).max() <= 2e-6
+    assert not np.any(y[2])                         # all-zero window stays silent
+
+
+@needs_ref
+def test_mf2se_oracle_matches_reference_module():
+    """Restated folds + forward vs the reference's own MOSSFORMER_SE executed around the
+    parameter skeleton: fused buffers bit-equal, waveform <= 2e-6."""
+    import mf2se_oracle as mo
+
+    cfg = mo.Mf2Config(layers=2)
+    L = 1920 + 384 * 19
+    sd = mo.random_state_dict(cfg, 7)
+    hold = mo.skeleton(cfg)
+    hold.load_state_dict(sd)
+    _, build = ref_loader.load_mf2se(L, "F32")
+    w = build(hold)
+    P = mo.fold(sd, cfg, cfg.n_frames(L))
+    assert torch.equal(P["frontend"], w.frontend_kernel[:, 0]) and torch.equal(P["mel_banks"], w.mel_banks[0])
+    assert torch.equal(P["emb_pos"], w.emb_pos[0].float().t()) and torch.equal(P["rot_cos"], w.rot_cos[0, :, 0].float())
+    for i in range(cfg.layers):
+        for mine, theirs in (("in_w", "fl_in_w"), ("in_b", "fl_in_b"), ("out_w", "fl_out_w"), ("qk_gamma", "qkos_gamma"),
+                             ("qk_beta", "qkos_beta"), ("uv_w", "fs_uv_w"), ("uv_b", "fs_uv_b"), ("mem_c", "fs_mem_c")):
+            assert torch.equal(P[f"L{i}.{mine}"], getattr(w, f"{theirs}_{i}").reshape(P[f"L{i}.{mine}"].shape)), mine
+    assert torch.equal(P["gate_w"], w.tail_gate_w[:, :, 0]) and torch.equal(P["gate_b"], w.tail_gate_b)
+    x = synth_audio(L, 11)
+    with torch.inference_mode():
+        yr = w(x.clone())
+        yo = mo.mf2se_forward(sd, x, cfg)
+    assert yr.shape == yo.shape == (1, 1, L)
+    assert (yr - yo).abs().max() <= 2e-6
