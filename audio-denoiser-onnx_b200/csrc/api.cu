@@ -550,7 +550,7 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
       !need("output_audio_dtype", sout) || !need("nfft", snfft) || !need("hop_length", shop))
     return fail(ADN_ERR_INVALID);
   m->family = fam;
-  if (fam != "gtcrn" && fam != "mel_band_roformer") {
+  if (fam != "gtcrn" && fam != "mel_band_roformer" && fam != "mossformer2_se") {
     m->err = "unsupported model_family '" + fam + "'";
     return fail(ADN_ERR_UNSUPPORTED);
   }
@@ -573,7 +573,7 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
   m->T = m->stft.n_frames(m->L);
   m->Lp = m->stft.padded_len(m->L);
   m->Lout = m->stft.out_len(m->T);
-  m->chans = is_gtcrn ? 1 : 2;
+  m->chans = fam == "mel_band_roformer" ? 2 : 1;
 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device_id) {
@@ -600,7 +600,9 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
   if (is_gtcrn) {
     s = build_gtcrn(m, weights);
   } else {
-    m->impl = mbr_create(m->meta, m->index, weights, m->d_blob, device_id, m->sms, m->err);
+    m->impl = fam == "mossformer2_se"
+                  ? mf2se_create(m->meta, m->index, weights, m->d_blob, device_id, m->sms, m->err)
+                  : mbr_create(m->meta, m->index, weights, m->d_blob, device_id, m->sms, m->err);
     if (!m->impl) s = ADN_ERR_INVALID;
   }
   if (s != ADN_OK) return fail(s);

@@ -116,6 +116,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+__device__ __forceinline__ int16_t to_i16(float y, int mode) {
+  if (mode == 1) return (int16_t)(int)(fminf(fmaxf(y, -1.0f), 32767.0f / 32768.0f) * 32768.0f);
+  return (int16_t)(int)fminf(fmaxf(y * 32767.0f, -32768.0f), 32767.0f);
+}
+
 template <int BN>
 struct Smem {
   static constexpr uint32_t W_TILE_BYTES = BN * BK * 4;
@@ -298,8 +303,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                   } else if (g.out_dtype == ADN_I16) {
                     short q4[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                      q4[j] = (short)(int)fminf(fmaxf(y[j] * 32767.0f, -32768.0f), 32767.0f);
+                    for (int j = 0; j < 4; ++j) q4[j] = to_i16(y[j], g.i16_mode);
                     *reinterpret_cast<short4*>(reinterpret_cast<int16_t*>(g.out) + ob + s0) = make_short4(q4[0], q4[1], q4[2], q4[3]);
                   } else {
                     __half2 h01 = __floats2half2_rn(y[0], y[1]), h23 = __floats2half2_rn(y[2], y[3]);
@@ -315,7 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     const float y = g.norm_mul ? xv[j] * nv : xv[j] / nv;
                     if (g.out_dtype == ADN_F32) reinterpret_cast<float*>(g.out)[ob + sj] = y;
                     else if (g.out_dtype == ADN_I16)
-                      reinterpret_cast<int16_t*>(g.out)[ob + sj] = (int16_t)(int)fminf(fmaxf(y * 32767.0f, -32768.0f), 32767.0f);
+                      reinterpret_cast<int16_t*>(g.out)[ob + sj] = to_i16(y, g.i16_mode);
                     else reinterpret_cast<__half*>(g.out)[ob + sj] = __float2half_rn(y);
                   }
                 }
@@ -335,6 +339,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               } else if (g.act == ACT_TANH) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) x[j] = tanhf(x[j]);
+              } else if (g.act == ACT_SILU) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = x[j] / (1.0f + expf(-x[j]));
+              } else if (g.act == ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.f);
+              } else if (g.act == ACT_RELU2) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float r = fmaxf(x[j], 0.f); x[j] = r * r; }
+              } else if (g.act == ACT_PRELU) {
+                const float slope = __ldg(g.act_param);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = x[j] >= 0.f ? x[j] : slope * x[j];
               }
               const long long o = m * g.ldc + n0 + 4 * cq;
               if (g.resid) {
@@ -383,8 +400,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const long long o = (long long)b * g.out_len + s;
             if (g.out_dtype == ADN_F32) reinterpret_cast<float*>(g.out)[o] = x;
             else if (g.out_dtype == ADN_I16) {
-              float qv = fminf(fmaxf(x * 32767.0f, -32768.0f), 32767.0f);
-              reinterpret_cast<int16_t*>(g.out)[o] = (int16_t)(int)qv;
+              reinterpret_cast<int16_t*>(g.out)[o] = to_i16(x, g.i16_mode);
             } else reinterpret_cast<__half*>(g.out)[o] = __float2half_rn(x);
           }
         }

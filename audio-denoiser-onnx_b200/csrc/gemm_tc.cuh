@@ -31,10 +31,13 @@ struct TcArgs {
   float* Chi;
   float* Clo;
   long long ldc;
-  int act;               // ACT_NONE | ACT_GELU | ACT_TANH
+  int act;               // ACT_*
+  const float* act_param; // ACT_PRELU: device scalar slope
+  int i16_mode;          // EPI_ISTFT int16 output: 0 = x*32767, clamp, truncate (GTCRN, Export_GTCRN.py:680-693)
+                         //   1 = clamp(x,-1,32767/32768)*32768, truncate (MossFormer2_SE_48K/Export_MossFormer_SE.py:499-504)
 };
 
-enum { ACT_NONE = 0, ACT_GELU = 1, ACT_TANH = 2 };
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_TANH = 2, ACT_SILU = 3, ACT_RELU = 4, ACT_RELU2 = 5, ACT_PRELU = 6 };
 
 struct TcPlan {
   CUtensorMap map_a_hi, map_a_lo, map_w_hi, map_w_lo;

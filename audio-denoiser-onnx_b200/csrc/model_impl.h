@@ -28,3 +28,7 @@ struct ModelImpl {
 // Mel-Band-Roformer (stereo): csrc/mbr.cu
 ModelImpl* mbr_create(const std::map<std::string, std::string>& meta, const std::map<std::string, TensorRef>& index,
                       const float* h_blob, float* d_blob, int device, int sms, std::string& err);
+
+// MossFormer2-SE-48K: csrc/mf2se.cu
+ModelImpl* mf2se_create(const std::map<std::string, std::string>& meta, const std::map<std::string, TensorRef>& index,
+                        const float* h_blob, float* d_blob, int device, int sms, std::string& err);
