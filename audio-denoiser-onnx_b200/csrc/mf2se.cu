@@ -6,13 +6,15 @@
 // overlap-add) runs on the tcgen05 3xTF32 GEMM (gemm_tc.cu); producers write the tf32 hi/lo
 // operand planes directly.  The attention products are batched per window with the window's own
 // keys / values as the "weight" operand:
-//     S   = relu(Qq Kq^T)^2            A = quad_q (T x 128)      W = quad_k   (T x 128)
+//     S1  = Ql Kl^T                    A = lin_q  (T x 128)      W = lin_k    (T x 128)
+//     S   = relu(Qq Kq^T)^2 + S1       A = quad_q (T x 128)      W = quad_k   (T x 128)
 //     O   = S [v|u]                    A = S      (T x Tp)       W = [v|u]^T  (2048 x Tp)
-//     KV^T= [v|u]^T Kl                 A = [v|u]^T (2048 x Tp)   W = lin_k^T  (128 x Tp)
-//     O  += Ql KV                      A = lin_q  (T x 128)      W = KV^T     (2048 x 128)
-// so no transposed stores are needed: the depthwise-conv kernel that follows the input projection
-// emits [v|u]^T and lin_k^T through a shared-memory transpose.  A window is one FLASH group
-// (T <= 256 frames); zero-padded keys contribute exactly nothing (:417-420) and are never stored.
+// A window is one FLASH group (T <= 256 frames), so the reference's linear branch
+// Ql (Kl^T [v|u]) (:422-427) is re-associated to (Ql Kl^T) [v|u] and shares the value product with
+// the quadratic branch: T <= 256 makes the T x T form the cheaper one, and it removes two GEMMs and
+// the 2048 x 128 per-window KV round trip.  The depthwise-conv kernel that follows the input
+// projection emits [v|u]^T through a shared-memory transpose.  Zero-padded keys contribute exactly
+// nothing (:417-420) and are never stored.
 //
 // Kernel <-> reference map:
 //   feat_kernel       power spectrum, mel filterbank, log (:337-341)
@@ -166,18 +168,47 @@ shiftnorm_kernel(const float* __restrict__ h, float* __restrict__ xhi, float* __
   if (lane == 0) rs[m] = 1.0f / (sqrtf(ss) + EPS_IN);
 }
 
+// Depthwise k=17 conv + residual for one channel (lane) over frames [t_begin, t_end) of a staged
+// [(T+16)][32] tile: the 17-frame window lives in registers and rotates by one frame per output
+// (2 shared-memory loads per output instead of 17).  emit(t, value) consumes the result.
+template <typename F>
+__device__ __forceinline__ void dwconv_run(const float* tile, const float (&w)[DW], int lane, int t_begin, int t_end,
+                                           int T, F&& emit) {
+  float reg[DW];
+#pragma unroll
+  for (int k = 0; k < DW; ++k) {
+    const int r = t_begin + k;
+    reg[k] = r < T + 2 * DWH ? tile[r * 32 + lane] : 0.f;
+  }
+  for (int t0 = t_begin; t0 < t_end; t0 += DW) {
+#pragma unroll
+    for (int j = 0; j < DW; ++j) {
+      const int t = t0 + j;
+      if (t < t_end) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < DW; ++k) acc += w[k] * reg[(j + k) % DW];
+        acc += reg[(j + DWH) % DW];
+        emit(t, acc);
+      }
+      const int r = t + DW;
+      reg[j] = r < T + 2 * DWH ? tile[r * 32 + lane] : 0.f;
+    }
+  }
+}
+
 // CTA = (32-channel tile, window).  Depthwise k=17 'same' conv over time + residual on the fused
 // to_hidden||to_qk projection.  Tiles of the 2048 value channels write [v|u] (token-major fp32, for
 // the gate) and [v|u]^T (tf32 planes, the attention operand); tiles of the 128 qk channels apply the
-// four OffsetScale heads and the rotary embedding and write quad_q / lin_q / quad_k (token-major
-// planes) and lin_k^T.
+// four OffsetScale heads and the rotary embedding and write quad_q / lin_q / quad_k / lin_k
+// (token-major planes).
 __global__ void __launch_bounds__(256)
 dwconv_in_kernel(const float* __restrict__ proj, const float* __restrict__ taps, const float* __restrict__ gamma,
                  const float* __restrict__ beta, const float* __restrict__ rcos, const float* __restrict__ rsin,
                  float* __restrict__ vu, float* __restrict__ vuT_hi, float* __restrict__ vuT_lo,
                  float* __restrict__ qq_hi, float* __restrict__ qq_lo, float* __restrict__ lq_hi,
                  float* __restrict__ lq_lo, float* __restrict__ qk_hi, float* __restrict__ qk_lo,
-                 float* __restrict__ lkT_hi, float* __restrict__ lkT_lo, int T, int Tp, int Tn) {
+                 float* __restrict__ lk_hi, float* __restrict__ lk_lo, int T, int Tp, int Tn) {
   extern __shared__ float sm[];
   float* sin_ = sm;                          // [(T+16)][32]
   float* sout = sm + (T + 2 * DWH) * 32;     // [32][Tp+1]
@@ -199,11 +230,8 @@ dwconv_in_kernel(const float* __restrict__ proj, const float* __restrict__ taps,
 #pragma unroll
     for (int hd = 0; hd < 4; ++hd) { g4[hd] = __ldg(gamma + hd * QK + q); b4[hd] = __ldg(beta + hd * QK + q); }
   }
-  for (int t = warp; t < T; t += 8) {
-    float acc = 0.f;
-#pragma unroll
-    for (int k = 0; k < DW; ++k) acc += w[k] * sin_[(t + k) * 32 + lane];
-    acc += sin_[(t + DWH) * 32 + lane];
+  const int tw = (T + 7) / 8, t_begin = warp * tw, t_end = min(T, t_begin + tw);
+  dwconv_run(sin_, w, lane, t_begin, t_end, T, [&](int t, float acc) {
     const long long m = (long long)b * T + t;
     if (!is_qk) {
       vu[m * VU2 + c0 + lane] = acc;
@@ -224,13 +252,14 @@ dwconv_in_kernel(const float* __restrict__ proj, const float* __restrict__ taps,
       split_tf32_store(s[0], qq_hi, qq_lo, m * QK + q);
       split_tf32_store(s[1], lq_hi, lq_lo, m * QK + q);
       split_tf32_store(s[2], qk_hi, qk_lo, ((long long)b * Tn + t) * QK + q);
-      sout[lane * (Tp + 1) + t] = s[3];
+      split_tf32_store(s[3], lk_hi, lk_lo, ((long long)b * Tn + t) * QK + q);
     }
-  }
+  });
+  if (is_qk) return;
   __syncthreads();
   for (int c = warp; c < 32; c += 8) {
-    float* dhi = is_qk ? lkT_hi + ((long long)b * QK + (c0 - VU2) + c) * Tp : vuT_hi + ((long long)b * VU2 + c0 + c) * Tp;
-    float* dlo = is_qk ? lkT_lo + ((long long)b * QK + (c0 - VU2) + c) * Tp : vuT_lo + ((long long)b * VU2 + c0 + c) * Tp;
+    float* dhi = vuT_hi + ((long long)b * VU2 + c0 + c) * Tp;
+    float* dlo = vuT_lo + ((long long)b * VU2 + c0 + c) * Tp;
     for (int t = lane; t < T; t += 32) split_tf32_store(sout[c * (Tp + 1) + t], dhi, dlo, t);
   }
 }
@@ -278,16 +307,13 @@ dwconv_kernel(const float* __restrict__ x, const float* __restrict__ taps, const
 #pragma unroll
   for (int k = 0; k < DW; ++k) w[k] = __ldg(taps + k * C + c0 + lane);
   __syncthreads();
-  for (int t = warp; t < T; t += 8) {
-    float acc = 0.f;
-#pragma unroll
-    for (int k = 0; k < DW; ++k) acc += w[k] * sm[(t + k) * 32 + lane];
-    acc += sm[(t + DWH) * 32 + lane];
+  const int tw = (T + 7) / 8, t_begin = warp * tw, t_end = min(T, t_begin + tw);
+  dwconv_run(sm, w, lane, t_begin, t_end, T, [&](int t, float acc) {
     const long long m = (long long)b * T + t;
     if (resid) acc += __ldg(resid + m * C + c0 + lane);
     out[m * C + c0 + lane] = acc;
     if (phi && c0 < plane_cols) split_tf32_store(acc, phi, plo, m * plane_cols + c0 + lane);
-  }
+  });
 }
 
 __device__ __forceinline__ void ln256(const float (&v)[8], float& mean, float& rstd) {
@@ -538,13 +564,13 @@ class Model : public ModelImpl {
   size_t ws_bytes = 0;
   float *xp = nullptr, *xpl = nullptr, *fr = nullptr, *mel = nullptr, *featpl = nullptr, *z = nullptr, *h = nullptr;
   float *xs = nullptr, *rs = nullptr, *proj = nullptr, *vu = nullptr, *vuT = nullptr, *qq = nullptr, *lq = nullptr;
-  float *qk = nullptr, *lkT = nullptr, *ppl = nullptr, *att = nullptr, *kvuT = nullptr, *gated = nullptr, *rs2 = nullptr;
+  float *qk = nullptr, *lk = nullptr, *s1 = nullptr, *ppl = nullptr, *att = nullptr, *gated = nullptr, *rs2 = nullptr;
   float *y = nullptr, *hpl = nullptr, *c1y = nullptr, *gin = nullptr, *xn = nullptr, *uvp = nullptr, *uv = nullptr;
   float *xupl = nullptr, *f1 = nullptr, *xp2 = nullptr, *yn = nullptr, *hn = nullptr, *tpl = nullptr, *gbuf = nullptr;
   float *tg = nullptr, *mask = nullptr, *enh = nullptr;
   size_t enh_plane = 0;
-  Lin a_qk, a_vuT, a_lkT, a_kvuT;          // per-window activation operands (W side)
-  Gemm g_front, g_enc, g_qk, g_pv, g_kvu, g_lin, g_gate, g_dec, g_istft;
+  Lin a_qk, a_lk, a_vuT;                   // per-window activation operands (W side)
+  Gemm g_front, g_enc, g_lk, g_qk, g_pv, g_gate, g_dec, g_istft;
   struct LayerG { Gemm in, out, c1, uv, ul, up, c2; };
   std::vector<LayerG> lg;
   int stop_after = 0, last_batch = 0;
@@ -731,7 +757,7 @@ class Model : public ModelImpl {
   size_t floats_needed(size_t B) const {
     const size_t M = B * T;
     return B * Lp * 3 + M * FRONT + M * NM + 2 * M * FEATP + 2 * M * D + 2 * M * D + 2 * M + M * PROJ + M * VU2 +
-           2 * B * VU2 * Tp + 4 * M * QK + 2 * B * Tn * QK + 2 * B * QK * Tp + 2 * M * Tp + M * VU2 + 2 * B * VU2 * QK +
+           2 * B * VU2 * Tp + 4 * M * QK + 4 * B * Tn * QK + 3 * M * Tp + M * VU2 +
            2 * M * VU + M * D + 2 * M * D + 2 * M * FI + 2 * M * FI + 2 * M * D + 2 * M * FI + 2 * M * FI + M * FI +
            2 * M * FI + M * D + 2 * M * D + M * 2 * D + 2 * M * D + M * BINSP + 2 * (B * (T + 2 * PADF) * SPEC_LD + 9664);
   }
@@ -749,8 +775,8 @@ class Model : public ModelImpl {
         !alloc(proj, (size_t)M * PROJ, false) || !alloc(vu, (size_t)M * VU2, false) ||
         !alloc(vuT, 2 * (size_t)B * VU2 * Tp, true) || !alloc(qq, 2 * (size_t)M * QK, false) ||
         !alloc(lq, 2 * (size_t)M * QK, false) || !alloc(qk, 2 * (size_t)B * Tn * QK, true) ||
-        !alloc(lkT, 2 * (size_t)B * QK * Tp, true) || !alloc(ppl, 2 * (size_t)M * Tp, true) ||
-        !alloc(att, (size_t)M * VU2, false) || !alloc(kvuT, 2 * (size_t)B * VU2 * QK, false) ||
+        !alloc(lk, 2 * (size_t)B * Tn * QK, true) || !alloc(s1, (size_t)M * Tp, true) ||
+        !alloc(ppl, 2 * (size_t)M * Tp, true) || !alloc(att, (size_t)M * VU2, false) ||
         !alloc(gated, 2 * (size_t)M * VU, false) || !alloc(rs2, (size_t)M, false) || !alloc(y, (size_t)M * D, false) ||
         !alloc(hpl, 2 * (size_t)M * D, false) || !alloc(c1y, (size_t)M * FI, false) || !alloc(gin, (size_t)M * FI, false) ||
         !alloc(xn, 2 * (size_t)M * FI, false) || !alloc(uvp, (size_t)M * 2 * FI, false) || !alloc(uv, (size_t)M * 2 * FI, false) ||
@@ -769,18 +795,15 @@ class Model : public ModelImpl {
     // attention operands that live in activations
     const int bn_qk = Tn;                    // 128 or 256 keys per tile
     if (!make_act_lin(a_qk, qk, qk + (size_t)B * Tn * QK, T4, Tn, QK, QK, bn_qk, B) ||
-        !make_act_lin(a_vuT, vuT, vuT + (size_t)B * VU2 * Tp, VU2, VU2, Tp, Tp, 256, B) ||
-        !make_act_lin(a_lkT, lkT, lkT + (size_t)B * QK * Tp, QK, QK, Tp, Tp, 128, B) ||
-        !make_act_lin(a_kvuT, kvuT, kvuT + (size_t)B * VU2 * QK, VU2, VU2, QK, QK, 256, B))
+        !make_act_lin(a_lk, lk, lk + (size_t)B * Tn * QK, T4, Tn, QK, QK, bn_qk, B) ||
+        !make_act_lin(a_vuT, vuT, vuT + (size_t)B * VU2 * Tp, VU2, VU2, Tp, Tp, 256, B))
       return false;
+    if (!plan_gemm(g_lk, lq, M * QK, QK, T, QK, B, (long long)T * QK, a_lk)) return false;
+    g_lk.args.C = s1; g_lk.args.ldc = Tp;
     if (!plan_gemm(g_qk, qq, M * QK, QK, T, QK, B, (long long)T * QK, a_qk)) return false;
-    g_qk.args.act = tc::ACT_RELU2; g_qk.args.Chi = ppl; g_qk.args.Clo = ppl + M * Tp; g_qk.args.ldc = Tp;
+    g_qk.args.act = tc::ACT_RELU2; g_qk.args.resid = s1; g_qk.args.Chi = ppl; g_qk.args.Clo = ppl + M * Tp; g_qk.args.ldc = Tp;
     if (!plan_gemm(g_pv, ppl, M * Tp, Tp, T, Tp, B, (long long)T * Tp, a_vuT)) return false;
     g_pv.args.C = att; g_pv.args.ldc = VU2;
-    if (!plan_gemm(g_kvu, vuT, (long long)B * VU2 * Tp, Tp, VU2, Tp, B, (long long)VU2 * Tp, a_lkT)) return false;
-    g_kvu.args.Chi = kvuT; g_kvu.args.Clo = kvuT + (size_t)B * VU2 * QK; g_kvu.args.ldc = QK;
-    if (!plan_gemm(g_lin, lq, M * QK, QK, T, QK, B, (long long)T * QK, a_kvuT)) return false;
-    g_lin.args.resid = att; g_lin.args.C = att; g_lin.args.ldc = VU2;
 
     lg.assign(layers, LayerG{});
     for (int i = 0; i < layers; ++i) {
@@ -834,7 +857,7 @@ class Model : public ModelImpl {
     out->dtype = out_dtype; out->channels = 1; out->length = L;
   }
   size_t workspace_bytes(int batch) override { return floats_needed((size_t)batch) * sizeof(float); }
-  int launches(int) override { return 5 + layers * 18 + 7; }
+  int launches(int) override { return 5 + layers * 17 + 6; }
   void set_stop_after(int n) override { stop_after = n; }
 
 #define MF_TICK(name) do { ++n; if (tick) tick(tick_ctx, name); if (stop_after > 0 && n >= stop_after) return ADN_OK; } while (0)
@@ -877,12 +900,11 @@ class Model : public ModelImpl {
       MF_GEMM(G.in, EPI_LIN, "fl_in");
       dwconv_in_kernel<<<dim3(PROJ / 32, B), 256, sm_in, st>>>(
           proj, Y.in_c, Y.gamma, Y.beta, rcos, rsin, vu, vuT, vuT + (size_t)B * VU2 * Tp, qq, qq + M * QK, lq, lq + M * QK,
-          qk, qk + (size_t)B * Tn * QK, lkT, lkT + (size_t)B * QK * Tp, T, Tp, Tn);
+          qk, qk + (size_t)B * Tn * QK, lk, lk + (size_t)B * Tn * QK, T, Tp, Tn);
       MF_TICK("dwconv_in");
+      MF_GEMM(g_lk, EPI_LIN, "att_lk");
       MF_GEMM(g_qk, EPI_LIN, "att_qk");
       MF_GEMM(g_pv, EPI_LIN, "att_pv");
-      MF_GEMM(g_kvu, EPI_LIN, "att_kvu");
-      MF_GEMM(g_lin, EPI_LIN, "att_lin");
       gate_kernel<<<wtok, 256, 0, st>>>(att, vu, gated, gated + M * VU, rs2, M);
       MF_TICK("gate");
       MF_GEMM(G.out, EPI_LIN, "fl_out");

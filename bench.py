@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the north-star path: noisy chunk in -> clean chunk out (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--model gtcrn|mbr] [--batch B] [--impl adn|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model gtcrn|mbr|mf2se] [--batch B] [--impl adn|reference]
 
 A "step" is one pass of the hot path over one batch of B synthetic chunks per GPU.
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field's definition.
@@ -123,6 +123,7 @@ class MbrWorkload:
     chunk, sr, channels, t_frames, depth = 66150, 44100, 2, 151, 6
     cpu_chunks, ref_chunks = 4, 1
     cpu_desc = "oracle/mbr_oracle.py (PyTorch-eager restatement, bit-equal to the reference module)"
+    tc3_kernels = ("bs_gemm", "in_proj", "out_proj", "ff1", "ff2", "me1", "me2", "me3")
 
     def describe(self, B):
         return (f"Mel-Band-Roformer stereo 44.1 kHz depth {self.depth}, {B} x 1.5 s fold windows (66150 samples) "
@@ -197,7 +198,101 @@ class MbrWorkload:
         }
 
 
-WORKLOADS = {"gtcrn": GtcrnWorkload, "mbr": MbrWorkload}
+class Mf2seWorkload:
+    """MossFormer2-SE-48K (BASELINE.json configs[2]): 24 FLASH+FSMN layers, 1 s windows at 48 kHz
+    (48000 samples, 121 frames), mono."""
+    name = "mf2se"
+    default_batch = 256
+    chunk, sr, channels, t_frames, layers = 48000, 48000, 1, 121, 24
+    cpu_chunks, ref_chunks = 32, 8
+    cpu_desc = "oracle/mf2se_oracle.py (PyTorch-eager restatement, pinned to the executed reference wrapper)"
+    tc3_kernels = ("frontend_gemm", "enc_gemm", "fl_in", "att_lk", "att_qk", "att_pv", "fl_out", "fsmn_conv1", "fsmn_uv",
+                   "fsmn_linear", "fsmn_project", "fsmn_conv2", "tail_gate_gemm", "mask_gemm", "istft_gemm")
+
+    def describe(self, B):
+        return (f"MossFormer2-SE-48K, {self.layers} layers, {B} x 1 s windows (48000 samples, 121 frames) per GPU per "
+                f"step, F32 in / F32 out")
+
+    def audio_seconds(self, B):
+        return B * self.chunk / self.sr
+
+    def weights(self):
+        import mf2se_oracle as mo
+        return mo.random_state_dict(mo.Mf2Config(layers=self.layers), 0)
+
+    def build(self, sd, device):
+        from adn import export, mf2se_params
+        return export.mf2se_model(sd, mf2se_params.Mf2Hyper(layers=self.layers), self.chunk, "F32", "F32", device_id=device)
+
+    def export(self, sd, path):
+        from adn import export, mf2se_params
+        export.export_mf2se(sd, path, mf2se_params.Mf2Hyper(layers=self.layers), self.chunk, "F32", "F32")
+
+    def inputs(self, B, n_sets, seed):
+        sets = []
+        for s in range(n_sets):
+            g = torch.Generator().manual_seed(seed + s)
+            x = 0.2 * torch.randn(B, 1, self.chunk, generator=g)
+            t = torch.arange(self.chunk, dtype=torch.float32) / self.sr
+            x = x + 0.3 * torch.sin(2 * torch.pi * (220.0 + 10 * s) * t).reshape(1, 1, -1)
+            sets.append((x / x.abs().amax() * 0.5).contiguous())
+        return sets
+
+    def cpu_rate(self, sd, n_chunks, threads):
+        import mf2se_oracle as mo
+        cfg = mo.Mf2Config(layers=self.layers)
+        P = mo.fold(sd, cfg, self.t_frames)
+        torch.set_num_threads(threads)
+        g = torch.Generator().manual_seed(7)
+        x = (torch.rand(1, 1, self.chunk, generator=g) * 2 - 1) * 0.3
+        with torch.inference_mode():
+            mo.mf2se_forward(sd, x, cfg, folded=P)
+            t0 = time.perf_counter()
+            for _ in range(n_chunks):
+                mo.mf2se_forward(sd, x, cfg, folded=P)
+            dt = time.perf_counter() - t0
+        return n_chunks * self.chunk / self.sr / dt, dt
+
+    def kernel_work(self):
+        """Algorithmic (bytes, flops) per window and per LAUNCH of each kernel."""
+        T, L, Tp = self.t_frames, self.chunk, 128
+
+        def gemm(m, k, n, outs=1):          # A planes (hi+lo) in, `outs` fp32-sized outputs
+            return (4 * (2 * m * k + outs * m * n), 2 * m * k * n)
+
+        return {
+            "prep": (4 * L * 4, 0),
+            "frontend_gemm": (2 * L * 4 + T * 3972 * 4, 2 * T * 1920 * 3972),
+            "feat": (T * (2050 + 60) * 4, T * (3 * 1025 + 2 * 2050)),
+            "featnorm": (T * (60 + 2 * 192 + 512) * 4, 30 * T * 180),
+            "enc_gemm": gemm(T, 192, 512, 2),
+            "shiftnorm": (3 * T * 512 * 4, 3 * T * 512),
+            "fl_in": gemm(T, 512, 2176),
+            "dwconv_in": (T * 2176 * 4 + T * 2048 * 4 + 2 * 2048 * Tp * 4 + 8 * T * 128 * 4, 2 * 17 * T * 2176),
+            "att_lk": (4 * T * 128 * 4 + T * Tp * 4, 2 * T * T * 128),
+            "att_qk": (4 * T * 128 * 4 + 3 * T * Tp * 4, 2 * T * T * 128),
+            "att_pv": (2 * T * Tp * 4 + 2 * 2048 * Tp * 4 + T * 2048 * 4, 2 * T * Tp * 2048),
+            "gate": (2 * T * 2048 * 4 + 2 * T * 1024 * 4, 8 * T * 1024),
+            "fl_out": gemm(T, 1024, 512),
+            "dwconv_out": (5 * T * 512 * 4, 2 * 17 * T * 512),
+            "fsmn_conv1": gemm(T, 512, 256),
+            "ln2": (4 * T * 256 * 4, 16 * T * 256),
+            "fsmn_uv": gemm(T, 256, 512),
+            "dwconv_uv": (2 * T * 512 * 4 + 2 * T * 256 * 4, 2 * 17 * T * 512),
+            "fsmn_linear": gemm(T, 256, 256, 2),
+            "fsmn_project": gemm(T, 256, 256),
+            "fsmn_mem": (6 * T * 256 * 4, 2 * 39 * T * 256),
+            "fsmn_conv2": gemm(T, 256, 512, 2),
+            "tail_norm": (6 * T * 512 * 4, 20 * T * 512),
+            "tail_gate_gemm": gemm(T, 512, 1024),
+            "tail_gate": (4 * T * 512 * 4, 8 * T * 512),
+            "mask_gemm": gemm(T, 512, 964),
+            "mask_apply": (T * (1922 + 964 + 2 * 1928) * 4, T * 1922),
+            "istft_gemm": (2 * (T + 8) * 1928 * 4 + L * 4, 2 * (T + 4) * 384 * 9640),
+        }
+
+
+WORKLOADS = {"gtcrn": GtcrnWorkload, "mbr": MbrWorkload, "mf2se": Mf2seWorkload}
 
 
 class ClockSampler:
@@ -376,13 +471,17 @@ def main():
     wb, wf = work[top]                                    # per chunk and per launch
     lb, lf = wb * B, wf * B
     t_hbm = lb / (pk["hbm_gbs"] * 1e9)
-    t_tc = lf / (pk["bf16_tflops_sustained"] * 1e12)
+    tc3 = top in getattr(wl, "tc3_kernels", ())           # 3xTF32 tcgen05 GEMM: 3 tf32 MMAs per MAC, tf32 = bf16 rate / 2
+    t_tc = lf * (6.0 if tc3 else 1.0) / (pk["bf16_tflops_sustained"] * 1e12)
     if t_hbm >= t_tc:
         roof = {"bound": "hbm", "achieved": lb / (launch_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s"}
     else:
         roof = {"bound": "tensor", "achieved": lf / (launch_ms * 1e-3) / 1e12, "peak": pk["bf16_tflops_sustained"],
                 "unit": "TFLOP/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
+    if tc3 and roof["bound"] == "tensor":
+        roof["tf32x3_ceiling"] = pk["bf16_tflops_sustained"] / 6.0
+        roof["frac_of_tf32x3_ceiling"] = roof["achieved"] / roof["tf32x3_ceiling"]
     roof.update({"traffic": None, "kernel": top, "kernel_ms_per_launch": launch_ms, "launches_per_step": n_l,
                  "kernel_share_of_step": top_ms / step_ms_prof, "peak_source": pk["src"],
                  "algorithmic_bytes_per_launch": lb, "algorithmic_flops_per_launch": lf,
