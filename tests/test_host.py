@@ -206,3 +206,27 @@ def test_mbr_packing_and_band_layout_match_oracle():
     assert np.array_equal(blob["rope.tcos"], tc.numpy()) and np.array_equal(blob["rope.fsin"], fs.numpy())
     md = mp.metadata(h, 4410)
     assert md["model_family"] == "mel_band_roformer" and md["input_channels"] == "2"
+
+
+def test_mf2se_packing_matches_oracle_fold():
+    """adn.mf2se_params.pack (product) == mf2se_oracle.fold (restated reference __init__), bit for bit;
+    depthwise taps are stored tap-major in the blob."""
+    import mf2se_oracle as mo
+    from adn import mf2se_params as mp
+
+    cfg = mo.Mf2Config(layers=2)
+    sd = mo.random_state_dict(cfg, 1)
+    L = 1920 + 384 * 30
+    P = mo.fold(sd, cfg, cfg.n_frames(L))
+    blob = mp.pack(sd, mp.Mf2Hyper(layers=2), L)
+    for k, v in P.items():
+        ref = v.numpy()
+        if k.split(".")[-1] in ("in_c", "out_c", "uv_c", "mem_c"):
+            ref = ref.T
+        assert np.array_equal(blob[k].reshape(ref.shape), ref), k
+    md = mp.metadata(mp.Mf2Hyper(layers=2), L)
+    assert md["model_family"] == "mossformer2_se" and md["center_pad"] == "0" and md["max_signal_length"] == "31"
+    with pytest.raises(ValueError):
+        mp.pack(sd, mp.Mf2Hyper(layers=2), 48001)            # not nfft + k*hop
+    with pytest.raises(ValueError):
+        mp.pack(sd, mp.Mf2Hyper(layers=2), 1920 + 384 * 256)  # more than one FLASH group
