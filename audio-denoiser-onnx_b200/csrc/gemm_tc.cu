@@ -245,9 +245,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const int mt = tile / n_tiles_n, nt = tile - mt * n_tiles_n;
       const int ab = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      const int tile_b = mt / g.tiles_per_chunk, tile_t = (mt - tile_b * g.tiles_per_chunk) * BM;   // bb == 1 tiles
       int b, t;
       if (g.bb > 1) { int bi = r / g.bt; b = mt * g.bb + bi; t = r - bi * g.bt; if (bi >= g.bb) b = g.B; }
-      else { b = mt / g.tiles_per_chunk; t = (mt - b * g.tiles_per_chunk) * BM + r; }
+      else { b = tile_b; t = tile_t + r; }
       b += g.b_off;
       const bool row_ok = (b < g.B) && (t < g.TM);
       mbar_wait(&tfull[ab], aphase);
@@ -268,6 +269,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const bool col_ok = (c0 + 4 * cq < BN) && (n0 + 4 * cq < g.N);      // N, BN, ldc multiples of 4
           float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
           bool have_bias = false;
+          // residual / row-scale operands of this 32x32 chunk are fetched up front (8 independent loads
+          // in flight) instead of one dependent DRAM round trip per 4-row step
+          float4 res4[2][4];
+          float rsc[2][4];
+#pragma unroll
+          for (int hrow = 0; hrow < 2; ++hrow)
+#pragma unroll
+            for (int it = 0; it < 4; ++it) { res4[hrow][it] = make_float4(0.f, 0.f, 0.f, 0.f); rsc[hrow][it] = 1.0f; }
+          if (EPI == EPI_LIN && (g.resid || g.rowscale)) {
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow)
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int r2 = q * 32 + hrow * 16 + it * 4 + (lane >> 3);
+                int b2, t2;
+                if (g.bb > 1) { int bi = r2 / g.bt; b2 = mt * g.bb + bi; t2 = r2 - bi * g.bt; if (bi >= g.bb) b2 = g.B; }
+                else { b2 = tile_b; t2 = tile_t + r2; }
+                b2 += g.b_off;
+                const bool ok = col_ok && b2 < g.B && t2 < g.TM;
+                const long long m = (long long)b2 * g.TM + t2;
+                if (ok && g.resid) res4[hrow][it] = *reinterpret_cast<const float4*>(g.resid + m * g.ldc + n0 + 4 * cq);
+                if (ok && g.rowscale) rsc[hrow][it] = __ldg(g.rowscale + m);
+              }
+          }
 #pragma unroll
           for (int hrow = 0; hrow < 2; ++hrow) {             // 16 rows at a time through a 16x36 tile
             if ((lane >> 4) == hrow) {
@@ -284,7 +309,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               const int r2 = q * 32 + hrow * 16 + rl;
               int b2, t2;
               if (g.bb > 1) { int bi = r2 / g.bt; b2 = mt * g.bb + bi; t2 = r2 - bi * g.bt; if (bi >= g.bb) b2 = g.B; }
-              else { b2 = mt / g.tiles_per_chunk; t2 = (mt - b2 * g.tiles_per_chunk) * BM + r2; }
+              else { b2 = tile_b; t2 = tile_t + r2; }
               b2 += g.b_off;
               if (!col_ok || b2 >= g.B || t2 >= g.TM) continue;
               if (EPI == EPI_ISTFT) {
@@ -330,7 +355,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 have_bias = true;
               }
               const long long m = (long long)b2 * g.TM + t2;
-              const float rs = g.rowscale ? __ldg(g.rowscale + m) : 1.0f;
+              const float rs = rsc[hrow][it];
               const float4 a4 = *reinterpret_cast<const float4*>(stg + rl * 36 + 4 * cq);
               float x[4] = {a4.x * rs + bias4.x, a4.y * rs + bias4.y, a4.z * rs + bias4.z, a4.w * rs + bias4.w};
               if (g.act == ACT_GELU) {
@@ -354,8 +379,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 for (int j = 0; j < 4; ++j) x[j] = x[j] >= 0.f ? x[j] : slope * x[j];
               }
               const long long o = m * g.ldc + n0 + 4 * cq;
-              if (g.resid) {
-                const float4 r4 = *reinterpret_cast<const float4*>(g.resid + o);
+              {
+                const float4 r4 = res4[hrow][it];
                 x[0] += r4.x; x[1] += r4.y; x[2] += r4.z; x[3] += r4.w;
               }
               if (g.C) *reinterpret_cast<float4*>(g.C + o) = make_float4(x[0], x[1], x[2], x[3]);
