@@ -168,99 +168,102 @@ shiftnorm_kernel(const float* __restrict__ h, float* __restrict__ xhi, float* __
   if (lane == 0) rs[m] = 1.0f / (sqrtf(ss) + EPS_IN);
 }
 
-// Depthwise k=17 conv + residual for one channel (lane) over frames [t_begin, t_end) of a staged
-// [(T+16)][32] tile: the 17-frame window lives in registers and rotates by one frame per output
-// (2 shared-memory loads per output instead of 17).  emit(t, value) consumes the result.
-template <typename F>
-__device__ __forceinline__ void dwconv_run(const float* tile, const float (&w)[DW], int lane, int t_begin, int t_end,
-                                           int T, F&& emit) {
-  float reg[DW];
+// Depthwise k=17 'same' conv over time + residual, streamed: one warp owns a 32-channel strip of one
+// window (lane = channel) and walks the frames once.  The 17-frame window plus the prefetched frames
+// live in a RING-register ring (static indices after unrolling), so every frame costs one coalesced
+// 128-byte global load issued RING-16 frames ahead of its first use, 17 FMAs and no shared memory or
+// CTA barrier.  emit(t, value) consumes frame t; flush(t0) runs after every 32 frames.
+template <int RING, typename F, typename G>
+__device__ __forceinline__ void dwconv_stream(const float* __restrict__ src, long long ld, const float (&w)[DW], int T,
+                                              F&& emit, G&& flush) {
+  static_assert(RING % 32 == 0 && RING > DW, "ring = whole 32-frame groups");
+  float ring[RING];
 #pragma unroll
-  for (int k = 0; k < DW; ++k) {
-    const int r = t_begin + k;
-    reg[k] = r < T + 2 * DWH ? tile[r * 32 + lane] : 0.f;
+  for (int i = 0; i < RING; ++i) {
+    const int r = i - DWH;
+    ring[i] = (r >= 0 && r < T) ? __ldg(src + (long long)r * ld) : 0.f;
   }
-  for (int t0 = t_begin; t0 < t_end; t0 += DW) {
+  for (int t0 = 0; t0 < T; t0 += RING) {
 #pragma unroll
-    for (int j = 0; j < DW; ++j) {
+    for (int j = 0; j < RING; ++j) {
       const int t = t0 + j;
-      if (t < t_end) {
+      if (t < T) {
         float acc = 0.f;
 #pragma unroll
-        for (int k = 0; k < DW; ++k) acc += w[k] * reg[(j + k) % DW];
-        acc += reg[(j + DWH) % DW];
+        for (int k = 0; k < DW; ++k) acc += w[k] * ring[(j + k) % RING];
+        acc += ring[(j + DWH) % RING];
         emit(t, acc);
       }
-      const int r = t + DW;
-      reg[j] = r < T + 2 * DWH ? tile[r * 32 + lane] : 0.f;
+      const int r = t + RING - DWH;
+      ring[j] = r < T ? __ldg(src + (long long)r * ld) : 0.f;
+      if ((j & 31) == 31 && t0 + j - 31 < T) flush(t0 + j - 31);
     }
   }
 }
 
-// CTA = (32-channel tile, window).  Depthwise k=17 'same' conv over time + residual on the fused
-// to_hidden||to_qk projection.  Tiles of the 2048 value channels write [v|u] (token-major fp32, for
-// the gate) and [v|u]^T (tf32 planes, the attention operand); tiles of the 128 qk channels apply the
-// four OffsetScale heads and the rotary embedding and write quad_q / lin_q / quad_k / lin_k
-// (token-major planes).
-__global__ void __launch_bounds__(256)
+// ConvModule residual on the fused to_hidden||to_qk projection; CTA = 4 warps = 4 adjacent 32-channel
+// strips of one window.  Strips of the 2048 value channels write [v|u] (token-major fp32, for the
+// gate) and [v|u]^T (tf32 planes, the attention operand; 32x32 per-warp transposes); the last CTA
+// column holds the 128 qk channels: four OffsetScale heads + rotary embedding -> quad_q / lin_q /
+// quad_k / lin_k (token-major planes).
+constexpr int DWI_WARPS = 4;
+__global__ void __launch_bounds__(DWI_WARPS * 32)
 dwconv_in_kernel(const float* __restrict__ proj, const float* __restrict__ taps, const float* __restrict__ gamma,
                  const float* __restrict__ beta, const float* __restrict__ rcos, const float* __restrict__ rsin,
                  float* __restrict__ vu, float* __restrict__ vuT_hi, float* __restrict__ vuT_lo,
                  float* __restrict__ qq_hi, float* __restrict__ qq_lo, float* __restrict__ lq_hi,
                  float* __restrict__ lq_lo, float* __restrict__ qk_hi, float* __restrict__ qk_lo,
                  float* __restrict__ lk_hi, float* __restrict__ lk_lo, int T, int Tp, int Tn) {
-  extern __shared__ float sm[];
-  float* sin_ = sm;                          // [(T+16)][32]
-  float* sout = sm + (T + 2 * DWH) * 32;     // [32][Tp+1]
-  const int c0 = blockIdx.x * 32, b = blockIdx.y;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* src = proj + (long long)b * T * PROJ + c0;
-  for (int i = tid; i < (T + 2 * DWH) * 32; i += 256) {
-    const int r = i >> 5, c = i & 31, t = r - DWH;
-    sin_[i] = (t >= 0 && t < T) ? __ldg(src + (long long)t * PROJ + c) : 0.f;
-  }
+  __shared__ float stage[DWI_WARPS][32 * 33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = (blockIdx.x * DWI_WARPS + warp) * 32, b = blockIdx.y;
+  const float* src = proj + (long long)b * T * PROJ + c0 + lane;
   float w[DW];
 #pragma unroll
   for (int k = 0; k < DW; ++k) w[k] = __ldg(taps + k * PROJ + c0 + lane);
-  __syncthreads();
-  const bool is_qk = c0 >= VU2;
-  const int q = c0 - VU2 + lane;             // qk channel (qk tiles only)
-  float g4[4], b4[4];
-  if (is_qk) {
+  if (c0 < VU2) {
+    float* st = stage[warp];
+    dwconv_stream<64>(src, PROJ, w, T,
+                  [&](int t, float acc) {
+                    vu[((long long)b * T + t) * VU2 + c0 + lane] = acc;
+                    st[(t & 31) * 33 + lane] = acc;
+                  },
+                  [&](int t0) {
+                    __syncwarp();
+                    const int t = t0 + lane;
+                    if (t < T) {
+#pragma unroll 8
+                      for (int c = 0; c < 32; ++c)
+                        split_tf32_store(st[lane * 33 + c], vuT_hi, vuT_lo, ((long long)b * VU2 + c0 + c) * Tp + t);
+                    }
+                    __syncwarp();
+                  });
+  } else {
+    const int q = c0 - VU2 + lane;             // qk channel
+    float g4[4], b4[4];
 #pragma unroll
     for (int hd = 0; hd < 4; ++hd) { g4[hd] = __ldg(gamma + hd * QK + q); b4[hd] = __ldg(beta + hd * QK + q); }
-  }
-  const int tw = (T + 7) / 8, t_begin = warp * tw, t_end = min(T, t_begin + tw);
-  dwconv_run(sin_, w, lane, t_begin, t_end, T, [&](int t, float acc) {
-    const long long m = (long long)b * T + t;
-    if (!is_qk) {
-      vu[m * VU2 + c0 + lane] = acc;
-      sout[lane * (Tp + 1) + t] = acc;
-    } else {
-      float s[4];
+    dwconv_stream<64>(src, PROJ, w, T,
+                  [&](int t, float acc) {
+                    float s[4];
 #pragma unroll
-      for (int hd = 0; hd < 4; ++hd) s[hd] = acc * g4[hd] + b4[hd];
-      if (c0 == VU2) {                       // rotary on the first 32 qk channels, interleaved pairs
-        const float cs = __ldg(rcos + t * ROT + lane), sn = __ldg(rsin + t * ROT + lane);
+                    for (int hd = 0; hd < 4; ++hd) s[hd] = acc * g4[hd] + b4[hd];
+                    if (c0 == VU2) {           // rotary on the first 32 qk channels, interleaved pairs
+                      const float cs = __ldg(rcos + t * ROT + lane), sn = __ldg(rsin + t * ROT + lane);
 #pragma unroll
-        for (int hd = 0; hd < 4; ++hd) {
-          const float other = __shfl_xor_sync(0xffffffffu, s[hd], 1);
-          const float rot = (lane & 1) ? other : -other;
-          s[hd] = s[hd] * cs + rot * sn;
-        }
-      }
-      split_tf32_store(s[0], qq_hi, qq_lo, m * QK + q);
-      split_tf32_store(s[1], lq_hi, lq_lo, m * QK + q);
-      split_tf32_store(s[2], qk_hi, qk_lo, ((long long)b * Tn + t) * QK + q);
-      split_tf32_store(s[3], lk_hi, lk_lo, ((long long)b * Tn + t) * QK + q);
-    }
-  });
-  if (is_qk) return;
-  __syncthreads();
-  for (int c = warp; c < 32; c += 8) {
-    float* dhi = vuT_hi + ((long long)b * VU2 + c0 + c) * Tp;
-    float* dlo = vuT_lo + ((long long)b * VU2 + c0 + c) * Tp;
-    for (int t = lane; t < T; t += 32) split_tf32_store(sout[c * (Tp + 1) + t], dhi, dlo, t);
+                      for (int hd = 0; hd < 4; ++hd) {
+                        const float other = __shfl_xor_sync(0xffffffffu, s[hd], 1);
+                        const float rot = (lane & 1) ? other : -other;
+                        s[hd] = s[hd] * cs + rot * sn;
+                      }
+                    }
+                    const long long m = (long long)b * T + t;
+                    split_tf32_store(s[0], qq_hi, qq_lo, m * QK + q);
+                    split_tf32_store(s[1], lq_hi, lq_lo, m * QK + q);
+                    split_tf32_store(s[2], qk_hi, qk_lo, ((long long)b * Tn + t) * QK + q);
+                    split_tf32_store(s[3], lk_hi, lk_lo, ((long long)b * Tn + t) * QK + q);
+                  },
+                  [](int) {});
   }
 }
 
@@ -290,30 +293,25 @@ gate_kernel(const float* __restrict__ att, const float* __restrict__ vu, float* 
   if (lane == 0) rs[m] = 1.0f / (sqrtf(ss) + EPS_OUT);
 }
 
-// CTA = (32-channel tile, window): out = x + dwconv17(x) (+ resid); optional tf32 planes of the first
-// `plane_cols` channels.
-__global__ void __launch_bounds__(256)
+// out = x + dwconv17(x) (+ resid); optional tf32 planes of the first `plane_cols` channels.
+// CTA = 4 warps = 4 adjacent 32-channel strips of one window (see dwconv_stream).
+__global__ void __launch_bounds__(DWI_WARPS * 32)
 dwconv_kernel(const float* __restrict__ x, const float* __restrict__ taps, const float* __restrict__ resid,
               float* __restrict__ out, float* __restrict__ phi, float* __restrict__ plo, int plane_cols, int T, int C) {
-  extern __shared__ float sm[];
-  const int c0 = blockIdx.x * 32, b = blockIdx.y;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* src = x + (long long)b * T * C + c0;
-  for (int i = tid; i < (T + 2 * DWH) * 32; i += 256) {
-    const int r = i >> 5, c = i & 31, t = r - DWH;
-    sm[i] = (t >= 0 && t < T) ? __ldg(src + (long long)t * C + c) : 0.f;
-  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = (blockIdx.x * DWI_WARPS + warp) * 32 + lane, b = blockIdx.y;
   float w[DW];
 #pragma unroll
-  for (int k = 0; k < DW; ++k) w[k] = __ldg(taps + k * C + c0 + lane);
-  __syncthreads();
-  const int tw = (T + 7) / 8, t_begin = warp * tw, t_end = min(T, t_begin + tw);
-  dwconv_run(sm, w, lane, t_begin, t_end, T, [&](int t, float acc) {
-    const long long m = (long long)b * T + t;
-    if (resid) acc += __ldg(resid + m * C + c0 + lane);
-    out[m * C + c0 + lane] = acc;
-    if (phi && c0 < plane_cols) split_tf32_store(acc, phi, plo, m * plane_cols + c0 + lane);
-  });
+  for (int k = 0; k < DW; ++k) w[k] = __ldg(taps + k * C + c);
+  const bool planes = phi && c < plane_cols;
+  dwconv_stream<32>(x + (long long)b * T * C + c, C, w, T,
+                [&](int t, float acc) {
+                  const long long m = (long long)b * T + t;
+                  if (resid) acc += __ldg(resid + m * C + c);
+                  out[m * C + c] = acc;
+                  if (planes) split_tf32_store(acc, phi, plo, m * plane_cols + c);
+                },
+                [](int) {});
 }
 
 __device__ __forceinline__ void ln256(const float (&v)[8], float& mean, float& rstd) {
@@ -873,12 +871,9 @@ class Model : public ModelImpl {
     static bool cfg = false;
     if (!cfg) {
       cudaFuncSetAttribute(featnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 2 * NM * 4);
-      cudaFuncSetAttribute(dwconv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ((256 + 16) * 32 + 32 * 257) * 4);
       cudaFuncSetAttribute(fsmn_mem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * FM_TOK + 2 * MEMH) * FI * 4);
       cfg = true;
     }
-    const size_t sm_conv = (size_t)(T + 2 * DWH) * 32 * sizeof(float);
-    const size_t sm_in = sm_conv + (size_t)32 * (Tp + 1) * sizeof(float);
 
     // 1-3: cast (+1/32768 for int16, :315-317), fused Kaldi||STFT frontend (:335), log-mel (:337-341)
     gtcrn::launch_prep(d_in, in_dtype, xp, xpl, xpl + (size_t)B * Lp, B, L, Lp, 0, 0, 0, st);
@@ -898,7 +893,7 @@ class Model : public ModelImpl {
       shiftnorm_kernel<<<wtok, 256, 0, st>>>(hin, xs, xs + M * D, rs, M, T);
       MF_TICK("shiftnorm");
       MF_GEMM(G.in, EPI_LIN, "fl_in");
-      dwconv_in_kernel<<<dim3(PROJ / 32, B), 256, sm_in, st>>>(
+      dwconv_in_kernel<<<dim3(PROJ / 32 / DWI_WARPS, B), DWI_WARPS * 32, 0, st>>>(
           proj, Y.in_c, Y.gamma, Y.beta, rcos, rsin, vu, vuT, vuT + (size_t)B * VU2 * Tp, qq, qq + M * QK, lq, lq + M * QK,
           qk, qk + (size_t)B * Tn * QK, lk, lk + (size_t)B * Tn * QK, T, Tp, Tn);
       MF_TICK("dwconv_in");
@@ -908,13 +903,13 @@ class Model : public ModelImpl {
       gate_kernel<<<wtok, 256, 0, st>>>(att, vu, gated, gated + M * VU, rs2, M);
       MF_TICK("gate");
       MF_GEMM(G.out, EPI_LIN, "fl_out");
-      dwconv_kernel<<<dim3(D / 32, B), 256, sm_conv, st>>>(y, Y.out_c, hin, h, hpl, hpl + M * D, D, T, D);
+      dwconv_kernel<<<dim3(D / 32 / DWI_WARPS, B), DWI_WARPS * 32, 0, st>>>(y, Y.out_c, hin, h, hpl, hpl + M * D, D, T, D);
       MF_TICK("dwconv_out");
       MF_GEMM(G.c1, EPI_LIN, "fsmn_conv1");
       ln2_kernel<<<wtok, 256, 0, st>>>(c1y, Y.n1_w, Y.n1_b, gin, xn, xn + M * FI, M);
       MF_TICK("ln2");
       MF_GEMM(G.uv, EPI_LIN, "fsmn_uv");
-      dwconv_kernel<<<dim3(2 * FI / 32, B), 256, sm_conv, st>>>(uvp, Y.uv_c, nullptr, uv, xupl, xupl + M * FI, FI, T, 2 * FI);
+      dwconv_kernel<<<dim3(2 * FI / 32 / DWI_WARPS, B), DWI_WARPS * 32, 0, st>>>(uvp, Y.uv_c, nullptr, uv, xupl, xupl + M * FI, FI, T, 2 * FI);
       MF_TICK("dwconv_uv");
       MF_GEMM(G.ul, EPI_LIN, "fsmn_linear");
       MF_GEMM(G.up, EPI_LIN, "fsmn_project");
