@@ -19,7 +19,8 @@ EXPORTED = [
     "adn_version", "adn_create", "adn_destroy", "adn_io_info", "adn_run", "adn_run_host",
     "adn_workspace_bytes", "adn_launches_per_run", "adn_debug_read", "adn_debug_stop_after", "adn_set_profiling",
     "adn_last_kernel_times", "adn_last_error", "adn_stft_create", "adn_stft_forward",
-    "adn_stft_inverse", "adn_stft_destroy",
+    "adn_stft_inverse", "adn_stft_destroy", "adn_resample_linear", "adn_rms_normalize", "adn_two_stage_rms",
+    "adn_spec_features", "adn_spec_recombine", "adn_condition_output",
 ]
 
 
@@ -89,6 +90,15 @@ def lib():
     L.adn_stft_inverse.restype = i32
     L.adn_stft_destroy.argtypes = [vp]
     L.adn_stft_destroy.restype = None
+    L.adn_resample_linear.argtypes = [vp, i32, vp, i32, i32, i32, C.c_double, vp]
+    L.adn_rms_normalize.argtypes = [vp, i32, C.c_float, C.c_float, vp, vp, i32, i32, i32, vp]
+    L.adn_two_stage_rms.argtypes = [vp, i32, C.c_float, C.c_float, vp, vp, i32, i32, vp]
+    L.adn_spec_features.argtypes = [i32, vp, vp, vp, i32, i32, i32, vp]
+    L.adn_spec_recombine.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, vp]
+    L.adn_condition_output.argtypes = [i32, vp, i32, vp, i32, vp, i32, i32, i32, vp]
+    for fn in (L.adn_resample_linear, L.adn_rms_normalize, L.adn_two_stage_rms, L.adn_spec_features,
+               L.adn_spec_recombine, L.adn_condition_output):
+        fn.restype = i32
     _lib = L
     return L
 

@@ -119,6 +119,9 @@ void tile_rows(int TM, int& bt, int& bb, int& tpc) {
 
 }  // namespace
 
+// last-error slot for handle-less entry points in other translation units (ends.cu)
+void adn_internal_set_error(const std::string& s) { set_global_error(s); }
+
 // ===================================================================================
 struct adn_model {
   std::string err;

@@ -141,6 +141,47 @@ adn_status adn_stft_inverse(adn_stft* s, const float* d_spec, float* d_y, int32_
                             int32_t n_frames, void* stream);
 void adn_stft_destroy(adn_stft* s);
 
+/* ---- stand-alone conditioning / feature / recombine / output operators ------------------------
+ * The wrapper-forward steps either side of the backbones that are not built in this library
+ * (ZipEnhancer, MossFormerGAN-SE-16K, MossFormer2-SS-16K) and the linear resampler every wrapper
+ * shares.  With adn_stft_forward / adn_stft_inverse they form the complete front and back ends
+ * around those backbones.  All pointers are DEVICE pointers, rows are contiguous, `stream` is a
+ * cudaStream_t (NULL = default stream); errors go to adn_last_error(NULL). */
+enum { ADN_FAMILY_ZIPENHANCER = 1, ADN_FAMILY_MOSSFORMERGAN = 2, ADN_FAMILY_MOSSFORMER2_SS = 3 };
+
+/* torch.nn.functional.interpolate(mode='linear', align_corners=False) (GTCRN/Export_GTCRN.py:638-654,
+ * ZipEnhancer/Export_ZipEnhancer.py:826-832, :906-912): d_in (rows, len_in) of in_dtype -> d_out
+ * (rows, len_out) fp32.  scale_factor > 0: coordinate scale 1/scale_factor (the scale_factor= form);
+ * otherwise len_in/len_out (the size= form). */
+adn_status adn_resample_linear(const void* d_in, int32_t in_dtype, float* d_out, int32_t rows,
+                               int32_t len_in, int32_t len_out, double scale_factor, void* stream);
+/* Per-window RMS normalisation (Export_ZipEnhancer.py:839-840; MossFormerGAN_SE_16K/Export_MossFormer_SE.py
+ * :564-568): y = (x*pre_scale) / sqrt(mean((x*pre_scale)^2) + eps); d_norm (rows) receives the factor.
+ * len_out > len appends the head of the window (MossFormerGAN's wrap-around pad to a hop multiple). */
+adn_status adn_rms_normalize(const void* d_in, int32_t in_dtype, float pre_scale, float eps, float* d_out,
+                             float* d_norm, int32_t rows, int32_t len, int32_t len_out, void* stream);
+/* MossFormer2_SS_16K norm_audio (Export_MossFormer2_SS_16K.py:403-423): two-stage RMS normalisation of raw
+ * PCM amplitude; d_rms_in (rows) receives the gain-restore reference. */
+adn_status adn_two_stage_rms(const void* d_in, int32_t in_dtype, float target, float eps, float* d_out,
+                             float* d_rms_in, int32_t rows, int32_t len, void* stream);
+/* Packed spectrum (batch, 2F, T) -> backbone input (batch, C, T, F).  ZIPENHANCER (:843-850): C = 2,
+ * [(re^2+im^2+1e-9)^0.15, atan2(im, re+1e-5)].  MOSSFORMERGAN (:578-586): C = 3, power-law compressed
+ * [magnitude, re, im]; d_keep (batch, 2, F, T) receives the compressed complex spectrum for recombine. */
+adn_status adn_spec_features(int32_t family, const float* d_spec, float* d_feat, float* d_keep, int32_t batch,
+                             int32_t fbins, int32_t frames, void* stream);
+/* Backbone outputs -> packed spectrum (batch, 2F, T) for adn_stft_inverse.  ZIPENHANCER (:882-892):
+ * d_a = mask-decoder output (batch,1,T,F), d_b = rectangular phase (batch,2,T,F).  MOSSFORMERGAN (:863-868):
+ * d_a = mask (batch,F,T), d_b = complex branch (batch,2,F,T), d_keep from adn_spec_features. */
+adn_status adn_spec_recombine(int32_t family, const float* d_a, const float* d_b, const float* d_keep,
+                              float* d_spec, int32_t batch, int32_t fbins, int32_t frames, void* stream);
+/* ISTFT output (rows, len_src) -> model output (rows, len) of out_dtype: trim, gain, family rule
+ * (Export_ZipEnhancer.py:899-926; MossFormerGAN :880-897; MossFormer2_SS :627-660).  d_gain holds one value per
+ * `gain_group` consecutive rows: the norm factor (ZIPENHANCER, MOSSFORMERGAN) or rms_in (MOSSFORMER2_SS, rows =
+ * windows x speakers, gain_group = speakers). */
+adn_status adn_condition_output(int32_t family, const float* d_wave, int32_t len_src, const float* d_gain,
+                                int32_t gain_group, void* d_out, int32_t out_dtype, int32_t rows, int32_t len,
+                                void* stream);
+
 /* Library/build identification: returns e.g. "adn 0.1 sm_100a". */
 const char* adn_version(void);
 
