@@ -178,8 +178,35 @@ def main_mf2se():
             print(f"mf2se {dt} L{L}: {tuple(xin.shape)} -> {tuple(y.shape)} max|y| {y.float().abs().max().item():.4f}")
 
 
+def main_mf2ss():
+    """MossFormer2-SS-16K fixtures: the reference wrapper (`MOSSFORMER_SS`) executed around
+    `mf2ss_oracle.skeleton()` on seeded weights, 2 FLASH + dilated-FSMN layers (the layer count is the
+    only reduced hyper-parameter); 600 frames = 3 FLASH groups with 168 padded keys, and 300 frames;
+    int16-scale samples; one all-zero window (the `rms_out > 0` guard, :631)."""
+    import mf2ss_oracle as so
+
+    assert ref_loader.reference_available()
+    cfg = so.SsConfig(layers=2)
+    sd = so.random_state_dict(cfg, 0)
+    hold = so.skeleton(cfg)
+    hold.load_state_dict(sd)
+    with torch.inference_mode():
+        for L, dt in ((4808, "F32"), (2408, "INT16")):
+            _, build = ref_loader.load_mf2ss(L, dt)
+            w = build(hold)
+            x = synth_audio(L, 4321, batch=3) * 32767.0
+            x[2] = 0.0
+            xin = x if dt == "F32" else torch.round(x).to(torch.int16)
+            ys = [torch.cat([w(xin[i:i + 1].clone())[s] for i in range(3)], dim=0) for s in range(2)]
+            np.savez_compressed(GOLDEN / f"mf2ss_{dt.lower()}_L{L}_l2.npz", x=xin.numpy(), y0=ys[0].numpy(), y1=ys[1].numpy(),
+                                seed=0, layers=2)
+            print(f"mf2ss {dt} L{L}: {tuple(xin.shape)} -> 2 x {tuple(ys[0].shape)} max|y| {ys[0].float().abs().max().item():.4f}")
+
+
 if __name__ == "__main__":
-    if "--mbr" in sys.argv:
+    if "--mf2ss" in sys.argv:
+        main_mf2ss()
+    elif "--mbr" in sys.argv:
         main_mbr()
     elif "--mf2se" in sys.argv:
         main_mf2se()

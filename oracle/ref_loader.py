@@ -203,3 +203,36 @@ def load_mf2se(input_audio_length: int, io_dtype: str = "F32"):
                                        ns["OUT_SAMPLE_RATE"], ns["MAX_SIGNAL_LENGTH"], False, ns["FOLD_WINDOW_LENGTH"]).eval()
 
     return ns, build
+
+
+def load_mf2ss(input_audio_length: int, io_dtype: str = "F32"):
+    """Reference MossFormer2-SS-16K wrapper (`MOSSFORMER_SS`) for one un-folded window.
+
+    The wrapper's forward is made of leaf ops on packed buffers; only its constructor reads the
+    absent `clearvoice` model.  Returns (namespace, build) with
+    build(holder) -> wrapper, where `holder` is `mf2ss_oracle.skeleton()` carrying the weights."""
+    import torch
+
+    for name in ("clearvoice", "clearvoice.models", "clearvoice.models.mossformer2_ss",
+                 "clearvoice.models.mossformer2_ss.mossformer2"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["clearvoice.models.mossformer2_ss.mossformer2"].MossFormer2_SS_16K = object
+
+    ns = load_export_namespace(
+        "MossFormer2_SS_16K",
+        "Export_MossFormer2_SS_16K.py",
+        {
+            "INPUT_AUDIO_LENGTH      = 32000": f"INPUT_AUDIO_LENGTH      = {int(input_audio_length)}",
+            "IN_AUDIO_DTYPE          = 'INT16'": f"IN_AUDIO_DTYPE          = '{io_dtype}'",
+            "OUT_AUDIO_DTYPE         = 'INT16'": f"OUT_AUDIO_DTYPE         = '{io_dtype}'",
+            "USE_BATCH_FOLD          = True": "USE_BATCH_FOLD          = False",
+        },
+    )
+
+    def build(holder):
+        with torch.inference_mode():
+            return ns["MOSSFORMER_SS"](holder.eval().float(), ns["INPUT_AUDIO_LENGTH"], ns["IN_SAMPLE_RATE"],
+                                       ns["OUT_SAMPLE_RATE"], False, ns["FOLD_WINDOW_LENGTH"]).eval()
+
+    return ns, build

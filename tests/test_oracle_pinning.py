@@ -243,3 +243,58 @@ def test_mf2se_oracle_matches_reference_module():
         yo = mo.mf2se_forward(sd, x, cfg)
     assert yr.shape == yo.shape == (1, 1, L)
     assert (yr - yo).abs().max() <= 2e-6
+
+
+# ----------------------------------------------------------------------------- MossFormer2-SS-16K
+@pytest.mark.parametrize("fixture,dt", [("mf2ss_f32_L4808_l2", "F32"), ("mf2ss_int16_L2408_l2", "INT16")])
+def test_mf2ss_oracle_matches_golden(fixture, dt, golden_dir):
+    import mf2ss_oracle as so
+
+    g = np.load(golden_dir / f"{fixture}.npz")
+    cfg = so.SsConfig(layers=int(g["layers"]))
+    sd = so.random_state_dict(cfg, int(g["seed"]))
+    with torch.inference_mode():
+        ys = so.mf2ss_forward_batch(sd, torch.from_numpy(g["x"]), cfg, dt, dt, chunk=1)
+    for s in range(2):
+        y, ref = ys[s].numpy(), g[f"y{s}"]
+        assert y.shape == ref.shape and y.dtype == ref.dtype
+        if dt == "INT16":
+            assert np.abs(y.astype(np.int32) - ref.astype(np.int32)).max() <= 1
+        else:
+            assert np.abs(y - ref).max() <= 5e-6
+        assert not np.any(y[2])                     # all-zero window stays silent (rms_out > 0 guard)
+
+
+@needs_ref
+def test_mf2ss_oracle_matches_reference_module():
+    """Restated folds + forward vs the reference's own MOSSFORMER_SS executed around the parameter
+    skeleton: fused buffers bit-equal, both speaker waveforms <= 5e-6 (two FLASH groups)."""
+    import mf2ss_oracle as so
+
+    cfg = so.SsConfig(layers=2)
+    L = 16 + 8 * 399
+    sd = so.random_state_dict(cfg, 7)
+    hold = so.skeleton(cfg)
+    hold.load_state_dict(sd)
+    _, build = ref_loader.load_mf2ss(L, "F32")
+    w = build(hold)
+    n = cfg.n_frames(L)
+    P = so.fold(sd, cfg, n)
+    assert w.static_frames == n == 400 and w.static_window_output == cfg.out_len(L) == L
+    assert torch.equal(P["emb_pos"], w.emb_pos[0].t()) and torch.equal(P["rot_cos"], w.rot_cos[0, :, 0])
+    assert torch.equal(P["rot_sin"].abs(), w.rot_signed_sin[0, :, 0].abs())
+    assert torch.equal(P["front_w"], w.front_w[:, :, 0]) and torch.equal(P["front_b"], w.front_b)
+    for i in range(cfg.layers):
+        for mine, theirs in (("in_w", "fl_in_w"), ("in_b", "fl_in_b"), ("out_w", "fl_out_w"), ("qk_gamma", "qkos_gamma"),
+                             ("qk_beta", "qkos_beta"), ("uv_w", "fs_uv_w"), ("uv_b", "fs_uv_b"), ("mem0_w", "fs_mem_w_%d_0"),
+                             ("mem1_w", "fs_mem_w_%d_1")):
+            ref = getattr(w, theirs % i if "%d" in theirs else f"{theirs}_{i}")
+            assert torch.equal(P[f"L{i}.{mine}"], ref.reshape(P[f"L{i}.{mine}"].shape)), mine
+    assert torch.equal(P["gate_w"], w.tail_gate_w[:, :, 0]) and torch.equal(P["gate_b"], w.tail_gate_b)
+    x = synth_audio(L, 11) * 32767.0
+    with torch.inference_mode():
+        yr = w(x.clone())
+        yo = so.mf2ss_forward(sd, x, cfg)
+    for a, b in zip(yr, yo):
+        assert a.shape == b.shape == (1, 1, L)
+        assert (a - b).abs().max() <= 5e-6
