@@ -70,31 +70,39 @@ class Model:
 
         assert audio.is_cuda and audio.is_contiguous(), "adn.Model.run needs a contiguous CUDA tensor"
         B = audio.shape[0]
-        o = self.outputs[0]
         tdt = {np.float32: torch.float32, np.int16: torch.int16, np.float16: torch.float16}
         assert audio.dtype == tdt[self.input.np_dtype], (audio.dtype, self.input)
         assert tuple(audio.shape[1:]) == (self.input.channels, self.input.length), (audio.shape, self.input)
+        multi = len(self.outputs) > 1            # MossFormer2-SS: one tensor per speaker, returned as a tuple
         if out is None:
-            out = torch.empty((B, o.channels, o.length), dtype=tdt[o.np_dtype], device=audio.device)
+            out = tuple(torch.empty((B, o.channels, o.length), dtype=tdt[o.np_dtype], device=audio.device)
+                        for o in self.outputs)
+        elif not multi:
+            out = (out,)
+        assert len(out) == len(self.outputs)
         st = torch.cuda.current_stream(audio.device).cuda_stream if stream is None else stream
-        outs = (C.c_void_p * 1)(out.data_ptr())
+        outs = (C.c_void_p * len(out))(*[t.data_ptr() for t in out])
         _lib.check(_lib.lib().adn_run(self._h, C.c_void_p(audio.data_ptr()), outs, B, C.c_void_p(st)),
                    self._h, "adn_run")
-        return out
+        return tuple(out) if multi else out[0]
 
     def run_host(self, audio: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
         """audio: host array (B, C, L); synchronous (H2D + kernels + D2H inside the call)."""
         a = np.ascontiguousarray(audio, dtype=self.input.np_dtype)
         B = a.shape[0]
-        o = self.outputs[0]
+        multi = len(self.outputs) > 1
         if out is None:
-            out = np.empty((B, o.channels, o.length), dtype=o.np_dtype)
-        outs = (C.c_void_p * 1)(out.ctypes.data)
+            out = tuple(np.empty((B, o.channels, o.length), dtype=o.np_dtype) for o in self.outputs)
+        elif not multi:
+            out = (out,)
+        outs = (C.c_void_p * len(out))(*[t.ctypes.data for t in out])
         _lib.check(_lib.lib().adn_run_host(self._h, C.c_void_p(a.ctypes.data), outs, B), self._h, "adn_run_host")
-        return out
+        return tuple(out) if multi else out[0]
 
-    def run_host_ptr(self, in_ptr: int, out_ptr: int, batch: int):
-        outs = (C.c_void_p * 1)(out_ptr)
+    def run_host_ptr(self, in_ptr: int, out_ptr, batch: int):
+        """out_ptr: one host address, or a sequence with one address per model output."""
+        ptrs = list(out_ptr) if isinstance(out_ptr, (list, tuple)) else [out_ptr]
+        outs = (C.c_void_p * len(ptrs))(*ptrs)
         _lib.check(_lib.lib().adn_run_host(self._h, C.c_void_p(in_ptr), outs, batch), self._h, "adn_run_host")
 
     # ------------------------------------------------------------------ diagnostics

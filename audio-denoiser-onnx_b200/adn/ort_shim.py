@@ -238,33 +238,35 @@ class InferenceSession:
             raise RuntimeError("metadata-only session cannot run")
         m = self._model
         vin = binding.inputs.get(m.input.name)
-        vout = binding.outputs.get(m.outputs[0].name)
-        if vin is None or vout is None:
-            raise RuntimeError("run_with_iobinding: input and output must be bound")
+        vouts = [binding.outputs.get(o.name) for o in m.outputs]     # MossFormer2-SS binds separated_0 and separated_1
+        if vin is None or any(v is None for v in vouts):              # (MossFormer2_SS_16K/Inference_MossFormer_SS_ONNX.py:312-317)
+            raise RuntimeError("run_with_iobinding: input and every output must be bound")
         if vin._t is not None:            # device-resident binding
-            if vout._t is None:
+            if any(v._t is None for v in vouts):
                 raise RuntimeError("input is bound on cuda but output is on cpu")
             import torch
 
-            m.run(vin._t, out=vout._t)
+            m.run(vin._t, out=vouts[0]._t if len(vouts) == 1 else tuple(v._t for v in vouts))
             torch.cuda.current_stream(vin._t.device).synchronize()   # ORT runs synchronously (:146)
             return
-        a, o = vin._a, vout._a
+        a = vin._a
         exp_in = (m.input.channels, m.input.length)
-        exp_out = (m.outputs[0].channels, m.outputs[0].length)
         if a.dtype != m.input.np_dtype or tuple(a.shape[-2:]) != exp_in:
             raise ValueError(f"input buffer {a.shape}/{a.dtype} does not match model input "
                              f"(B,{exp_in[0]},{exp_in[1]})/{np.dtype(m.input.np_dtype)}")
         batch = int(np.prod(a.shape[:-2])) if a.ndim > 2 else 1
-        if o.dtype != m.outputs[0].np_dtype or tuple(o.shape[-2:]) != exp_out or o.size != batch * exp_out[0] * exp_out[1]:
-            raise ValueError(f"output buffer {o.shape}/{o.dtype} does not match model output "
-                             f"({batch},{exp_out[0]},{exp_out[1]})/{np.dtype(m.outputs[0].np_dtype)}")
-        m.run_host_ptr(a.ctypes.data, o.ctypes.data, batch)
+        for meta, v in zip(m.outputs, vouts):
+            o, exp_out = v._a, (meta.channels, meta.length)
+            if o.dtype != meta.np_dtype or tuple(o.shape[-2:]) != exp_out or o.size != batch * exp_out[0] * exp_out[1]:
+                raise ValueError(f"output buffer {o.shape}/{o.dtype} does not match model output "
+                                 f"({batch},{exp_out[0]},{exp_out[1]})/{np.dtype(meta.np_dtype)}")
+        m.run_host_ptr(a.ctypes.data, [v._a.ctypes.data for v in vouts], batch)
 
     def run(self, output_names, input_feed: dict, run_options=None):
         m = self._model
         a = np.ascontiguousarray(input_feed[m.input.name])
-        return [m.run_host(a)]
+        r = m.run_host(a)
+        return list(r) if isinstance(r, tuple) else [r]
 
 
 def get_available_providers():

@@ -158,7 +158,8 @@ struct adn_model {
   size_t ws_bytes = 0;
   std::vector<void*> allocs;
   void* d_in = nullptr;     // device staging for adn_run_host
-  void* d_out = nullptr;
+  void* d_out = nullptr;    // n_out consecutive (batch, chans, Lout) blocks
+  int n_out = 1;
   int io_cap = 0;           // staging capacity when `impl` owns the workspace
   cudaStream_t own_stream = nullptr;
   cudaStream_t st_in = nullptr, st_out = nullptr;      // copy streams of adn_run_host
@@ -550,10 +551,13 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
   };
   std::string fam, sL, sin, sout, snfft, shop;
   if (!need("model_family", fam) || !need("input_audio_length", sL) || !need("input_audio_dtype", sin) ||
-      !need("output_audio_dtype", sout) || !need("nfft", snfft) || !need("hop_length", shop))
+      !need("output_audio_dtype", sout))
     return fail(ADN_ERR_INVALID);
+  const bool is_ss = fam == "mossformer2_ss";       // learned encoder / decoder: no STFT keys (feature_kind conv_encoder_decoder)
+  if (!is_ss && (!need("nfft", snfft) || !need("hop_length", shop))) return fail(ADN_ERR_INVALID);
+  if (is_ss) { snfft = "16"; shop = "8"; }          // Conv1d(k16, s8) framing, snip-edges
   m->family = fam;
-  if (fam != "gtcrn" && fam != "mel_band_roformer" && fam != "mossformer2_se") {
+  if (fam != "gtcrn" && fam != "mel_band_roformer" && fam != "mossformer2_se" && !is_ss) {
     m->err = "unsupported model_family '" + fam + "'";
     return fail(ADN_ERR_UNSUPPORTED);
   }
@@ -576,6 +580,11 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
   m->T = m->stft.n_frames(m->L);
   m->Lp = m->stft.padded_len(m->L);
   m->Lout = m->stft.out_len(m->T);
+  if (is_ss) {
+    m->T = (m->L - nfft) / hop + 1;
+    m->Lout = (m->T - 1) * hop + nfft;
+    m->n_out = 2;
+  }
   m->chans = fam == "mel_band_roformer" ? 2 : 1;
 
   int ndev = 0;
@@ -605,7 +614,8 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
   } else {
     m->impl = fam == "mossformer2_se"
                   ? mf2se_create(m->meta, m->index, weights, m->d_blob, device_id, m->sms, m->err)
-                  : mbr_create(m->meta, m->index, weights, m->d_blob, device_id, m->sms, m->err);
+                  : is_ss ? mf2ss_create(m->meta, m->index, weights, m->d_blob, device_id, m->sms, m->err)
+                          : mbr_create(m->meta, m->index, weights, m->d_blob, device_id, m->sms, m->err);
     if (!m->impl) s = ADN_ERR_INVALID;
   }
   if (s != ADN_OK) return fail(s);
@@ -643,7 +653,7 @@ adn_status adn_io_info(const adn_model* m, adn_tensor_info* in, adn_tensor_info*
   if (!m || !in || !outs || !n_out) return ADN_ERR_INVALID;
   if (m->impl) {
     m->impl->io_info(in, outs);
-    *n_out = 1;
+    *n_out = m->impl->n_outputs();
     return ADN_OK;
   }
   memset(in, 0, sizeof(*in));
@@ -682,7 +692,7 @@ adn_status adn_run(adn_model* m, const void* d_in, void* const* d_outs, int32_t 
     m->impl->tick = tick_cb;
     m->impl->tick_ctx = m;
     tick_cb(m, "start");
-    adn_status r = m->impl->run(d_in, d_outs[0], batch, (cudaStream_t)stream);
+    adn_status r = m->impl->run_multi(d_in, d_outs, batch, (cudaStream_t)stream);
     if (r != ADN_OK) m->err = m->impl->err;
     m->last_batch = batch;
     return r;
@@ -703,7 +713,7 @@ adn_status adn_run_host(adn_model* m, const void* h_in, void* const* h_outs, int
       ADN_CUDA_TRY(cudaDeviceSynchronize(), m->err);
       if (m->io_cap) { cudaFree(m->d_in); cudaFree(m->d_out); }
       ADN_CUDA_TRY(cudaMalloc(&m->d_in, (size_t)batch * m->chans * m->L * dtype_size(m->in_dtype)), m->err);
-      ADN_CUDA_TRY(cudaMalloc(&m->d_out, (size_t)batch * m->chans * m->Lout * dtype_size(m->out_dtype)), m->err);
+      ADN_CUDA_TRY(cudaMalloc(&m->d_out, (size_t)m->n_out * batch * m->chans * m->Lout * dtype_size(m->out_dtype)), m->err);
       m->io_cap = batch;
     }
   } else {
@@ -747,10 +757,15 @@ adn_status adn_run_host(adn_model* m, const void* h_in, void* const* h_outs, int
     return ADN_OK;
   }
   ADN_CUDA_TRY(cudaMemcpyAsync(m->d_in, h_in, batch * in_row, cudaMemcpyHostToDevice, st), m->err);
-  void* outs[1] = {m->d_out};
+  void* outs[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int o = 0; o < m->n_out; ++o) {
+    if (!h_outs[o]) { m->err = "adn_run_host: null output buffer"; return ADN_ERR_INVALID; }
+    outs[o] = (char*)m->d_out + (size_t)o * batch * out_row;
+  }
   s = adn_run(m, m->d_in, outs, batch, st);
   if (s != ADN_OK) return s;
-  ADN_CUDA_TRY(cudaMemcpyAsync(h_outs[0], m->d_out, batch * out_row, cudaMemcpyDeviceToHost, st), m->err);
+  for (int o = 0; o < m->n_out; ++o)
+    ADN_CUDA_TRY(cudaMemcpyAsync(h_outs[o], outs[o], batch * out_row, cudaMemcpyDeviceToHost, st), m->err);
   ADN_CUDA_TRY(cudaStreamSynchronize(st), m->err);
   return ADN_OK;
 }

@@ -195,9 +195,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           mbar_expect_tx(&full[stage], (uint32_t)(2 * g.bt * g.bb * BK * 4) + 2 * S::W_TILE_BYTES);
           tma_load_3d(st, &map_a_hi, &full[stage], kb * BK, t0, b0);
           tma_load_3d(st + A_TILE_BYTES, &map_a_lo, &full[stage], kb * BK, t0, b0);
-          const int wb = g.w_batched ? b0 : 0;      // per-batch weights (mask-estimator bands)
-          tma_load_3d(st + 2 * A_TILE_BYTES, &map_w_hi, &full[stage], kb * BK, nt * BN, wb);
-          tma_load_3d(st + 2 * A_TILE_BYTES + S::W_TILE_BYTES, &map_w_lo, &full[stage], kb * BK, nt * BN, wb);
+          int wb = g.w_batched ? b0 : 0;            // per-batch weights (mask-estimator bands, attention operands)
+          int wk = kb * BK;
+          if (g.w_group > 1) { wk += (wb % g.w_group) * g.w_kstep; wb /= g.w_group; }   // FLASH group of a window
+          tma_load_3d(st + 2 * A_TILE_BYTES, &map_w_hi, &full[stage], wk, nt * BN, wb);
+          tma_load_3d(st + 2 * A_TILE_BYTES + S::W_TILE_BYTES, &map_w_lo, &full[stage], wk, nt * BN, wb);
           if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
         }
       }

@@ -14,6 +14,8 @@ struct TcArgs {
   int B, TM;             // chunks (exclusive upper bound of the chunk index), valid rows per chunk
   int b_off;             // first chunk index of this launch
   int w_batched;         // 1: weights differ per chunk (W map has a chunk dimension)
+  int w_group;           // > 1: `w_group` consecutive chunks share one W batch and walk its K axis:
+  int w_kstep;           //   chunk c reads W batch c / w_group at K offset (c % w_group) * w_kstep
   int N, K;
   // EPI_STORE: C[b*c_sB + t*c_sT + n]
   float* C;

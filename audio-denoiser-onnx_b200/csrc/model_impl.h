@@ -19,6 +19,12 @@ struct ModelImpl {
   virtual ~ModelImpl() {}
   virtual void io_info(adn_tensor_info* in, adn_tensor_info* out) = 0;
   virtual adn_status run(const void* d_in, void* d_out, int batch, cudaStream_t st) = 0;
+  // families with several outputs (MossFormer2-SS: one waveform per speaker) override these two;
+  // io_info() then fills n_outputs() consecutive entries of `out`
+  virtual int n_outputs() { return 1; }
+  virtual adn_status run_multi(const void* d_in, void* const* d_outs, int batch, cudaStream_t st) {
+    return run(d_in, d_outs[0], batch, st);
+  }
   virtual size_t workspace_bytes(int batch) = 0;
   virtual int launches(int batch) = 0;
   virtual adn_status debug_read(const char* name, float* h_dst, size_t count, size_t* actual) = 0;
@@ -31,4 +37,8 @@ ModelImpl* mbr_create(const std::map<std::string, std::string>& meta, const std:
 
 // MossFormer2-SE-48K: csrc/mf2se.cu
 ModelImpl* mf2se_create(const std::map<std::string, std::string>& meta, const std::map<std::string, TensorRef>& index,
+                        const float* h_blob, float* d_blob, int device, int sms, std::string& err);
+
+// MossFormer2-SS-16K: csrc/mf2ss.cu
+ModelImpl* mf2ss_create(const std::map<std::string, std::string>& meta, const std::map<std::string, TensorRef>& index,
                         const float* h_blob, float* d_blob, int device, int sms, std::string& err);

@@ -230,3 +230,34 @@ def test_mf2se_packing_matches_oracle_fold():
         mp.pack(sd, mp.Mf2Hyper(layers=2), 48001)            # not nfft + k*hop
     with pytest.raises(ValueError):
         mp.pack(sd, mp.Mf2Hyper(layers=2), 1920 + 384 * 256)  # more than one FLASH group
+
+
+def test_mf2ss_packing_matches_oracle_fold():
+    """adn.mf2ss_params.pack (product) == mf2ss_oracle.fold (restated reference __init__), bit for bit; depthwise
+    taps are stored tap-major, the dilated memory kernels (channel, slot, tap) as (slot, tap, channel)."""
+    import mf2ss_oracle as so
+    from adn import mf2ss_params as sp
+
+    cfg = so.SsConfig(layers=2)
+    sd = so.random_state_dict(cfg, 1)
+    L = 16 + 8 * 299
+    P = so.fold(sd, cfg, cfg.n_frames(L))
+    blob = sp.pack(sd, sp.SsHyper(layers=2), L)
+    seen = set()
+    for k, v in P.items():
+        ref, name = v.numpy(), k
+        leaf = k.split(".")[-1]
+        if leaf in ("in_c", "out_c", "uv_c"):
+            ref = ref.T
+        elif leaf in ("mem0_w", "mem1_w"):
+            ref, name = ref.transpose(1, 2, 0), k[:-1] + "c"
+        assert np.array_equal(blob[name].reshape(ref.shape), ref), k
+        seen.add(name)
+    assert seen == set(blob)
+    h = sp.SsHyper(layers=2)
+    md = sp.metadata(h, L)
+    assert md["model_family"] == "mossformer2_ss" and md["output_sources"] == "2" and md["enc_stride"] == "8"
+    assert "nfft" not in md and md["pad_head"] == "8000" and md["output_audio_length"] == str(L)
+    assert h.n_frames(16000) == 1999 and h.out_len(16000) == 16000 and h.out_len(16005) == 16000
+    with pytest.raises(ValueError):
+        sp.pack(sd, h, 8)
