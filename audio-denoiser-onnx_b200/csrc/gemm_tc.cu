@@ -134,6 +134,7 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+               const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
                const TcArgs g) {
   using S = Smem<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -156,6 +157,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     prefetch_tmap(&map_a_lo);
     prefetch_tmap(&map_w_hi);
     prefetch_tmap(&map_w_lo);
+    if (g.k_split > 0) { prefetch_tmap(&map_w2_hi); prefetch_tmap(&map_w2_lo); }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S::STAGES; ++i) {
@@ -197,9 +199,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           tma_load_3d(st + A_TILE_BYTES, &map_a_lo, &full[stage], kb * BK, t0, b0);
           int wb = g.w_batched ? b0 : 0;            // per-batch weights (mask-estimator bands, attention operands)
           int wk = kb * BK;
-          if (g.w_group > 1) { wk += (wb % g.w_group) * g.w_kstep; wb /= g.w_group; }   // FLASH group of a window
-          tma_load_3d(st + 2 * A_TILE_BYTES, &map_w_hi, &full[stage], wk, nt * BN, wb);
-          tma_load_3d(st + 2 * A_TILE_BYTES + S::W_TILE_BYTES, &map_w_lo, &full[stage], wk, nt * BN, wb);
+          if (g.w_group > 1) { wk += (b0 % g.w_group) * g.w_kstep; wb = b0 / g.w_group; }   // FLASH group of a window
+          if (g.k_split > 0 && kb * BK >= g.k_split) {        // second operand of a K-concatenated product
+            tma_load_3d(st + 2 * A_TILE_BYTES, &map_w2_hi, &full[stage], kb * BK - g.k_split, nt * BN, wb);
+            tma_load_3d(st + 2 * A_TILE_BYTES + S::W_TILE_BYTES, &map_w2_lo, &full[stage], kb * BK - g.k_split, nt * BN, wb);
+          } else {
+            tma_load_3d(st + 2 * A_TILE_BYTES, &map_w_hi, &full[stage], wk, nt * BN, wb);
+            tma_load_3d(st + 2 * A_TILE_BYTES + S::W_TILE_BYTES, &map_w_lo, &full[stage], wk, nt * BN, wb);
+          }
           if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -508,7 +515,7 @@ static cudaError_t launch_t(const TcPlan& p, const TcArgs& a, int sms, cudaStrea
   }
   const int n_tiles = a.m_tiles * ((a.N + BN - 1) / BN);
   const int grid = n_tiles < sms ? n_tiles : sms;
-  kern<<<grid, NTHREADS, S::TOTAL, st>>>(p.map_a_hi, p.map_a_lo, p.map_w_hi, p.map_w_lo, a);
+  kern<<<grid, NTHREADS, S::TOTAL, st>>>(p.map_a_hi, p.map_a_lo, p.map_w_hi, p.map_w_lo, p.map_w2_hi, p.map_w2_lo, a);
   return cudaGetLastError();
 }
 

@@ -16,6 +16,8 @@ struct TcArgs {
   int w_batched;         // 1: weights differ per chunk (W map has a chunk dimension)
   int w_group;           // > 1: `w_group` consecutive chunks share one W batch and walk its K axis:
   int w_kstep;           //   chunk c reads W batch c / w_group at K offset (c % w_group) * w_kstep
+  int k_split;           // > 0: K is a concatenation; columns >= k_split come from the second W operand (plan.map_w2_*,
+                         //   batch c / w_group, K offset 0): C = A[:, :k_split] W1^T + A[:, k_split:] W2^T in one pass
   int N, K;
   // EPI_STORE: C[b*c_sB + t*c_sT + n]
   float* C;
@@ -43,6 +45,7 @@ enum { ACT_NONE = 0, ACT_GELU = 1, ACT_TANH = 2, ACT_SILU = 3, ACT_RELU = 4, ACT
 
 struct TcPlan {
   CUtensorMap map_a_hi, map_a_lo, map_w_hi, map_w_lo;
+  CUtensorMap map_w2_hi, map_w2_lo;   // only read when args.k_split > 0
   int bn = 0;            // N tile: 128 | 176 | 256
 };
 

@@ -65,25 +65,27 @@ shiftnorm_kernel(const float* __restrict__ h, float* __restrict__ xhi, float* __
 }
 
 // Depthwise k=17 'same' conv over time + residual, streamed: one warp owns a 32-channel strip of one
-// window (lane = channel) and walks the frames once.  The 17-frame window plus the prefetched frames
-// live in a RING-register ring (static indices after unrolling), so every frame costs one coalesced
-// 128-byte global load issued RING-16 frames ahead of its first use, 17 FMAs and no shared memory or
-// CTA barrier.  emit(t, value) consumes frame t; flush(t0) runs after every 32 frames.
+// window (lane = channel) and walks the frames [t_begin, t_end) once (long windows are cut into segments so
+// that enough warps are in flight; the halo frames come from global memory, zeros outside [0, T)).  The
+// 17-frame window plus the prefetched frames live in a RING-register ring (static indices after unrolling),
+// so every frame costs one coalesced 128-byte global load issued RING-16 frames ahead of its first use,
+// 17 FMAs and no shared memory or CTA barrier.  emit(t, value) consumes frame t; flush(t0) runs after every
+// 32 frames (t_begin must be a multiple of 32).
 template <int RING, typename F, typename G>
 __device__ __forceinline__ void dwconv_stream(const float* __restrict__ src, long long ld, const float (&w)[DW], int T,
-                                              F&& emit, G&& flush) {
+                                              int t_begin, int t_end, F&& emit, G&& flush) {
   static_assert(RING % 32 == 0 && RING > DW, "ring = whole 32-frame groups");
   float ring[RING];
 #pragma unroll
   for (int i = 0; i < RING; ++i) {
-    const int r = i - DWH;
+    const int r = t_begin + i - DWH;
     ring[i] = (r >= 0 && r < T) ? __ldg(src + (long long)r * ld) : 0.f;
   }
-  for (int t0 = 0; t0 < T; t0 += RING) {
+  for (int t0 = t_begin; t0 < t_end; t0 += RING) {
 #pragma unroll
     for (int j = 0; j < RING; ++j) {
       const int t = t0 + j;
-      if (t < T) {
+      if (t < t_end) {
         float acc = 0.f;
 #pragma unroll
         for (int k = 0; k < DW; ++k) acc += w[k] * ring[(j + k) % RING];
@@ -92,10 +94,13 @@ __device__ __forceinline__ void dwconv_stream(const float* __restrict__ src, lon
       }
       const int r = t + RING - DWH;
       ring[j] = r < T ? __ldg(src + (long long)r * ld) : 0.f;
-      if ((j & 31) == 31 && t0 + j - 31 < T) flush(t0 + j - 31);
+      if ((j & 31) == 31 && t0 + j - 31 < t_end) flush(t0 + j - 31);
     }
   }
 }
+
+// frames per time segment of the streamed depthwise convs (blockIdx.z)
+constexpr int DW_SEG = 256;
 
 // ConvModule residual on the fused to_hidden||to_qk projection; CTA = 4 warps = 4 adjacent 32-channel
 // strips of one window.  Strips of the 2048 value channels write [v|u] (token-major fp32, for the
@@ -111,17 +116,18 @@ dwconv_in_kernel(const float* __restrict__ proj, const float* __restrict__ taps,
                  float* __restrict__ qq_hi, float* __restrict__ qq_lo, float* __restrict__ lq_hi,
                  float* __restrict__ lq_lo, float* __restrict__ qk_hi, float* __restrict__ qk_lo,
                  float* __restrict__ lk_hi, float* __restrict__ lk_lo, float* __restrict__ lkT_hi,
-                 float* __restrict__ lkT_lo, int T, int Tp, int Tn, int Tq) {
+                 float* __restrict__ lkT_lo, int T, int Tp, int Tn, int Tq, int lq_ld) {
   __shared__ float stage[DWI_WARPS][32 * 33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c0 = (blockIdx.x * DWI_WARPS + warp) * 32, b = blockIdx.y;
+  const int t_begin = blockIdx.z * DW_SEG, t_end = min(T, t_begin + DW_SEG);
   const float* src = proj + (long long)b * T * PROJ + c0 + lane;
   float w[DW];
 #pragma unroll
   for (int k = 0; k < DW; ++k) w[k] = __ldg(taps + k * PROJ + c0 + lane);
   if (c0 < VU2) {
     float* st = stage[warp];
-    dwconv_stream<64>(src, PROJ, w, T,
+    dwconv_stream<64>(src, PROJ, w, T, t_begin, t_end,
                   [&](int t, float acc) {
                     vu[((long long)b * T + t) * VU2 + c0 + lane] = acc;
                     st[(t & 31) * 33 + lane] = acc;
@@ -141,7 +147,7 @@ dwconv_in_kernel(const float* __restrict__ proj, const float* __restrict__ taps,
     float g4[4], b4[4];
 #pragma unroll
     for (int hd = 0; hd < 4; ++hd) { g4[hd] = __ldg(gamma + hd * QK + q); b4[hd] = __ldg(beta + hd * QK + q); }
-    dwconv_stream<64>(src, PROJ, w, T,
+    dwconv_stream<64>(src, PROJ, w, T, t_begin, t_end,
                   [&](int t, float acc) {
                     float s[4];
 #pragma unroll
@@ -157,7 +163,7 @@ dwconv_in_kernel(const float* __restrict__ proj, const float* __restrict__ taps,
                     }
                     const long long m = (long long)b * Tq + t;
                     split_tf32_store(s[0], qq_hi, qq_lo, m * QK + q);
-                    split_tf32_store(s[1], lq_hi, lq_lo, m * QK + q);
+                    split_tf32_store(s[1], lq_hi, lq_lo, m * lq_ld + q);     // lq_ld > QK: columns of a wider operand
                     split_tf32_store(s[2], qk_hi, qk_lo, ((long long)b * Tn + t) * QK + q);
                     if (lkT_hi) stage[warp][(t & 31) * 33 + lane] = s[3];      // multi-group windows: lin_k^T (SS)
                     else split_tf32_store(s[3], lk_hi, lk_lo, ((long long)b * Tn + t) * QK + q);
@@ -214,7 +220,8 @@ dwconv_kernel(const float* __restrict__ x, const float* __restrict__ taps, const
 #pragma unroll
   for (int k = 0; k < DW; ++k) w[k] = __ldg(taps + k * C + c);
   const bool planes = phi && c < plane_cols;
-  dwconv_stream<32>(x + (long long)b * T * C + c, C, w, T,
+  const int t_begin = blockIdx.z * DW_SEG, t_end = min(T, t_begin + DW_SEG);
+  dwconv_stream<32>(x + (long long)b * T * C + c, C, w, T, t_begin, t_end,
                 [&](int t, float acc) {
                   const long long m = (long long)b * T + t;
                   if (resid) acc += __ldg(resid + m * C + c);

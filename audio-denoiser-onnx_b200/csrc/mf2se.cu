@@ -469,9 +469,9 @@ class Model : public Base {
       shiftnorm_kernel<<<wtok, 256, 0, st>>>(hin, xs, xs + M * D, rs, M, T, 0);
       MF_TICK("shiftnorm");
       MF_GEMM(G.in, EPI_LIN, "fl_in");
-      dwconv_in_kernel<<<dim3(PROJ / 32 / DWI_WARPS, B), DWI_WARPS * 32, 0, st>>>(
+      dwconv_in_kernel<<<dim3(PROJ / 32 / DWI_WARPS, B, (T + DW_SEG - 1) / DW_SEG), DWI_WARPS * 32, 0, st>>>(
           proj, Y.in_c, Y.gamma, Y.beta, rcos, rsin, vu, vuT, vuT + (size_t)B * VU2 * Tp, qq, qq + M * QK, lq, lq + M * QK,
-          qk, qk + (size_t)B * Tn * QK, lk, lk + (size_t)B * Tn * QK, nullptr, nullptr, T, Tp, Tn, T);
+          qk, qk + (size_t)B * Tn * QK, lk, lk + (size_t)B * Tn * QK, nullptr, nullptr, T, Tp, Tn, T, QK);
       MF_TICK("dwconv_in");
       MF_GEMM(g_lk, EPI_LIN, "att_lk");
       MF_GEMM(g_qk, EPI_LIN, "att_qk");
@@ -479,13 +479,13 @@ class Model : public Base {
       gate_kernel<<<wtok, 256, 0, st>>>(att, vu, gated, gated + M * VU, rs2, M, T, T, 0);
       MF_TICK("gate");
       MF_GEMM(G.out, EPI_LIN, "fl_out");
-      dwconv_kernel<<<dim3(D / 32 / DWI_WARPS, B), DWI_WARPS * 32, 0, st>>>(y, Y.out_c, hin, h, hpl, hpl + M * D, D, T, D);
+      dwconv_kernel<<<dim3(D / 32 / DWI_WARPS, B, (T + DW_SEG - 1) / DW_SEG), DWI_WARPS * 32, 0, st>>>(y, Y.out_c, hin, h, hpl, hpl + M * D, D, T, D);
       MF_TICK("dwconv_out");
       MF_GEMM(G.c1, EPI_LIN, "fsmn_conv1");
       ln2_kernel<<<wtok, 256, 0, st>>>(c1y, Y.n1_w, Y.n1_b, gin, xn, xn + M * FI, M);
       MF_TICK("ln2");
       MF_GEMM(G.uv, EPI_LIN, "fsmn_uv");
-      dwconv_kernel<<<dim3(2 * FI / 32 / DWI_WARPS, B), DWI_WARPS * 32, 0, st>>>(uvp, Y.uv_c, nullptr, uv, xupl, xupl + M * FI, FI, T, 2 * FI);
+      dwconv_kernel<<<dim3(2 * FI / 32 / DWI_WARPS, B, (T + DW_SEG - 1) / DW_SEG), DWI_WARPS * 32, 0, st>>>(uvp, Y.uv_c, nullptr, uv, xupl, xupl + M * FI, FI, T, 2 * FI);
       MF_TICK("dwconv_uv");
       MF_GEMM(G.ul, EPI_LIN, "fsmn_linear");
       MF_GEMM(G.up, EPI_LIN, "fsmn_project");

@@ -7,10 +7,11 @@
 // layout (row = window*Tg + frame, Tg = 256*G) whose pad rows stay zero, which is exactly the reference's
 // zero padding of keys and values (:482-493).  All dense contractions run on the tcgen05 3xTF32 GEMM:
 //     S_g  = relu(Qq_g Kq_g^T)^2          chunk = (window, group)      A = quad_q   W = quad_k (per chunk)
-//     O_g  = S_g [v|u]_g                  chunk = (window, group)      A = S        W = [v|u]^T, K offset 256*g
 //     KV^T = [v|u]^T Kl                   chunk = window, K = Tg       A = [v|u]^T  W = lin_k^T
-//     O   += Ql KV                        chunk = window               A = lin_q    W = KV^T   (accumulates onto O)
-// The linear branch is global over the window (:500-504; 1/n is folded into lin_k, :250-251).
+//     O_g  = [S_g | Ql_g] [[v|u]_g ; KV]  chunk = (window, group)      A = [S | lin_q] (K = 256 + 128)
+//                                                                      W = [v|u]^T at K offset 256*g, then KV^T
+// The linear branch is global over the window (:500-504; 1/n is folded into lin_k, :250-251); its product with
+// lin_q rides along the quadratic value product as 128 extra K columns, so O is written exactly once.
 //
 // Kernel <-> reference map (shared FLASH / FSMN kernels: mf2_kernels.cuh):
 //   adn_two_stage_rms   norm_audio (:403-423)                       [ends.cu]
@@ -26,6 +27,7 @@
 namespace mf2 {
 
 constexpr int ENC_K = 16, ENC_S = 8, SPK = 2, GROUP = 256;
+constexpr int SQ = GROUP + QK;              // row of the attention A operand: [S (256 keys of the group) | lin_q (128)]
 constexpr int ENC_TT = 32;                  // frames per encoder CTA
 constexpr int MEM_TT = 64;                  // frames per memory-conv CTA
 constexpr int MEM1_ROWS = MEM_TT + 2 * MEMH;        // dilation 1: halo 19 each side
@@ -210,19 +212,26 @@ mem2_kernel(const float* __restrict__ m1, const float* __restrict__ stats1, cons
   for (int i = 0; i < MEMK; ++i) { k0[i] = __ldg(taps + i * FI + c); k1[i] = __ldg(taps + (MEMK + i) * FI + c); }
   __syncthreads();
   float su = 0.f, sq = 0.f;
-  for (int tt = th * (MEM_TT / 2); tt < (th + 1) * (MEM_TT / 2); tt += 2) {
-    // outputs tt and tt+1 read rows tt + 2i and tt + 1 + 2i
-    float a0 = 0.f, a1 = 0.f;
+  for (int tt = th * (MEM_TT / 2); tt < (th + 1) * (MEM_TT / 2); tt += 8) {
+    // 8 outputs per pass: output tt + q reads rows tt + q + 2i, so the four even (odd) outputs share the 42 rows
+    // tt (+1) + 2r -- one 64-bit shared load feeds up to 8 FMAs
+    float a[8];
 #pragma unroll
-    for (int i = 0; i < MEMK; ++i) {
-      const float2 v0 = *reinterpret_cast<const float2*>(&tile[tt + 2 * i][2 * j]);
-      const float2 v1 = *reinterpret_cast<const float2*>(&tile[tt + 1 + 2 * i][2 * j]);
-      a0 += k0[i] * v0.x + k1[i] * v0.y;
-      a1 += k0[i] * v1.x + k1[i] * v1.y;
+    for (int q = 0; q < 8; ++q) a[q] = 0.f;
+#pragma unroll
+    for (int par = 0; par < 2; ++par) {
+#pragma unroll
+      for (int r = 0; r < MEMK + 3; ++r) {
+        const float2 v = *reinterpret_cast<const float2*>(&tile[tt + par + 2 * r][2 * j]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = r - e;
+          if (i >= 0 && i < MEMK) a[2 * e + par] += k0[i] * v.x + k1[i] * v.y;
+        }
+      }
     }
-    const float a[2] = {a0, a1};
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < 8; ++q) {
       const int t = t0 + tt + q;
       if (t < T) {
         out[(base + t) * FI + c] = a[q];
@@ -373,14 +382,14 @@ class SsModel : public Base {
   Lin front, gate, maskl;
 
   float *xn = nullptr, *rms_in = nullptr, *xenc = nullptr, *z = nullptr, *h = nullptr, *xs = nullptr, *rs = nullptr;
-  float *proj = nullptr, *vu = nullptr, *vuT = nullptr, *qq = nullptr, *lq = nullptr, *qk = nullptr, *lkT = nullptr;
+  float *proj = nullptr, *vu = nullptr, *vuT = nullptr, *qq = nullptr, *qk = nullptr, *lkT = nullptr;
   float *spl = nullptr, *kvT = nullptr, *att = nullptr, *gated = nullptr, *rs2 = nullptr, *y = nullptr, *hpl = nullptr;
   float *c1y = nullptr, *gin = nullptr, *xnp = nullptr, *uvp = nullptr, *uv = nullptr, *xupl = nullptr, *f1 = nullptr;
   float *xp2 = nullptr, *m1 = nullptr, *m2 = nullptr, *part = nullptr, *stats = nullptr, *yn = nullptr, *hn = nullptr;
   float *tpl = nullptr, *gbuf = nullptr, *tg = nullptr, *mask = nullptr, *fo = nullptr, *wav = nullptr;
   double* encpart = nullptr;
   Lin a_qk, a_vuT, a_lkT, a_kvT;
-  Gemm g_front, g_qk, g_pv, g_kv, g_lin, g_gate, g_mask;
+  Gemm g_front, g_qk, g_pv, g_kv, g_gate, g_mask;
   struct LayerG { Gemm in, out, c1, uv, ul, up, c2; };
   std::vector<LayerG> lg;
   int stop_after = 0, last_batch = 0;
@@ -471,8 +480,8 @@ class SsModel : public Base {
 
   size_t floats_needed(size_t B) const {
     const size_t M = B * T, Mg = B * Tg;
-    return B * L + B + 3 * M * D + 2 * M * D + M + M * PROJ + M * VU2 + 2 * B * VU2 * Tg + 6 * Mg * QK + 2 * B * QK * Tg +
-           2 * Mg * GROUP + 2 * B * VU2 * QK + Mg * VU2 + 2 * M * VU + M + M * D + 2 * M * D + 2 * M * FI + 2 * M * FI +
+    return B * L + B + 3 * M * D + 2 * M * D + M + M * PROJ + M * VU2 + 2 * B * VU2 * Tg + 4 * Mg * QK + 2 * B * QK * Tg +
+           2 * Mg * SQ + 2 * B * VU2 * QK + Mg * VU2 + 2 * M * VU + M + M * D + 2 * M * D + 2 * M * FI + 2 * M * FI +
            2 * M * 2 * FI + 4 * M * FI + 3 * M * FI + 2 * B * mem_tiles * FI * 2 + 2 * B * FI * 2 + 2 * M * FI + M * D +
            2 * M * D + M * SPK * 2 * D + 2 * M * SPK * D + M * SPK * D + M * SPK * ENC_K + B * SPK * Lout + B * enc_tiles * 4;
   }
@@ -486,8 +495,8 @@ class SsModel : public Base {
     if (!alloc(xn, (size_t)B * L, false) || !alloc(rms_in, B, false) || !alloc(xenc, M * D, false) || !alloc(z, M * D, false) ||
         !alloc(h, M * D, false) || !alloc(xs, 2 * M * D, false) || !alloc(rs, M, false) || !alloc(proj, M * PROJ, false) ||
         !alloc(vu, M * VU2, false) || !alloc(vuT, 2 * (size_t)B * VU2 * Tg, true) || !alloc(qq, 2 * Mg * QK, true) ||
-        !alloc(lq, 2 * Mg * QK, true) || !alloc(qk, 2 * Mg * QK, true) || !alloc(lkT, 2 * (size_t)B * QK * Tg, true) ||
-        !alloc(spl, 2 * Mg * GROUP, false) || !alloc(kvT, 2 * (size_t)B * VU2 * QK, false) || !alloc(att, Mg * VU2, false) ||
+        !alloc(qk, 2 * Mg * QK, true) || !alloc(lkT, 2 * (size_t)B * QK * Tg, true) ||
+        !alloc(spl, 2 * Mg * SQ, true) || !alloc(kvT, 2 * (size_t)B * VU2 * QK, false) || !alloc(att, Mg * VU2, false) ||
         !alloc(gated, 2 * M * VU, false) || !alloc(rs2, M, false) || !alloc(y, M * D, false) || !alloc(hpl, 2 * M * D, false) ||
         !alloc(c1y, M * FI, false) || !alloc(gin, M * FI, false) || !alloc(xnp, 2 * M * FI, false) ||
         !alloc(uvp, M * 2 * FI, false) || !alloc(uv, M * 2 * FI, false) || !alloc(xupl, 2 * M * FI, false) ||
@@ -512,13 +521,13 @@ class SsModel : public Base {
         !make_act_lin(a_kvT, kvT, kvT + (size_t)B * VU2 * QK, VU2, VU2, QK, QK, 256, B))
       return false;
     if (!plan_gemm(g_qk, qq, (long long)(Mg * QK), QK, GROUP, QK, BG, (long long)GROUP * QK, a_qk)) return false;
-    g_qk.args.w_batched = 1; g_qk.args.act = tc::ACT_RELU2; g_qk.args.Chi = spl; g_qk.args.Clo = spl + Mg * GROUP; g_qk.args.ldc = GROUP;
-    if (!plan_gemm(g_pv, spl, (long long)(Mg * GROUP), GROUP, GROUP, GROUP, BG, (long long)GROUP * GROUP, a_vuT)) return false;
+    g_qk.args.w_batched = 1; g_qk.args.act = tc::ACT_RELU2; g_qk.args.Chi = spl; g_qk.args.Clo = spl + Mg * SQ; g_qk.args.ldc = SQ;
+    if (!plan_gemm(g_pv, spl, (long long)(Mg * SQ), SQ, GROUP, SQ, BG, (long long)GROUP * SQ, a_vuT)) return false;
     g_pv.args.w_batched = 1; g_pv.args.w_group = G; g_pv.args.w_kstep = GROUP; g_pv.args.C = att; g_pv.args.ldc = VU2;
+    g_pv.args.K = SQ; g_pv.args.k_split = GROUP;
+    g_pv.plan.map_w2_hi = a_kvT.w_hi; g_pv.plan.map_w2_lo = a_kvT.w_lo;
     if (!plan_gemm(g_kv, vuT, (long long)B * VU2 * Tg, Tg, VU2, Tg, B, (long long)VU2 * Tg, a_lkT)) return false;
     g_kv.args.w_batched = 1; g_kv.args.Chi = kvT; g_kv.args.Clo = kvT + (size_t)B * VU2 * QK; g_kv.args.ldc = QK;
-    if (!plan_gemm(g_lin, lq, (long long)(Mg * QK), QK, Tg, QK, B, (long long)Tg * QK, a_kvT)) return false;
-    g_lin.args.w_batched = 1; g_lin.args.resid = att; g_lin.args.C = att; g_lin.args.ldc = VU2;
 
     lg.assign(layers, LayerG{});
     const long long Ml = (long long)M;
@@ -562,7 +571,7 @@ class SsModel : public Base {
     }
   }
   size_t workspace_bytes(int batch) override { return floats_needed((size_t)batch) * sizeof(float); }
-  int launches(int) override { return 4 + layers * 22 + 6; }
+  int launches(int) override { return 4 + layers * 21 + 6; }
   void set_stop_after(int n) override { stop_after = n; }
 
 #define SS_TICK(name) do { ++n; if (tick) tick(tick_ctx, name); if (stop_after > 0 && n >= stop_after) return ADN_OK; } while (0)
@@ -607,24 +616,23 @@ class SsModel : public Base {
       shiftnorm_kernel<<<wtok, 256, 0, st>>>(hin, xs, xs + M * D, rs, M, T, 1);
       SS_TICK("shiftnorm");
       SS_GEMM(Gm.in, "fl_in");
-      dwconv_in_kernel<<<dim3(PROJ / 32 / DWI_WARPS, B), DWI_WARPS * 32, 0, st>>>(
-          proj, Y.in_c, Y.gamma, Y.beta, rcos, rsin, vu, vuT, vuT + (size_t)B * VU2 * Tg, qq, qq + Mg * QK, lq, lq + Mg * QK,
-          qk, qk + Mg * QK, nullptr, nullptr, lkT, lkT + (size_t)B * QK * Tg, T, Tg, Tg, Tg);
+      dwconv_in_kernel<<<dim3(PROJ / 32 / DWI_WARPS, B, (T + DW_SEG - 1) / DW_SEG), DWI_WARPS * 32, 0, st>>>(
+          proj, Y.in_c, Y.gamma, Y.beta, rcos, rsin, vu, vuT, vuT + (size_t)B * VU2 * Tg, qq, qq + Mg * QK, spl + GROUP, spl + Mg * SQ + GROUP,
+          qk, qk + Mg * QK, nullptr, nullptr, lkT, lkT + (size_t)B * QK * Tg, T, Tg, Tg, Tg, SQ);
       SS_TICK("dwconv_in");
       SS_GEMM(g_qk, "att_qk");
-      SS_GEMM(g_pv, "att_pv");
       SS_GEMM(g_kv, "att_kv");
-      SS_GEMM(g_lin, "att_lin");
+      SS_GEMM(g_pv, "att_pv");
       gate_kernel<<<wtok, 256, 0, st>>>(att, vu, gated, gated + M * VU, rs2, M, T, Tg, 1);
       SS_TICK("gate");
       SS_GEMM(Gm.out, "fl_out");
-      dwconv_kernel<<<dim3(D / 32 / DWI_WARPS, B), DWI_WARPS * 32, 0, st>>>(y, Y.out_c, hin, h, hpl, hpl + M * D, D, T, D);
+      dwconv_kernel<<<dim3(D / 32 / DWI_WARPS, B, (T + DW_SEG - 1) / DW_SEG), DWI_WARPS * 32, 0, st>>>(y, Y.out_c, hin, h, hpl, hpl + M * D, D, T, D);
       SS_TICK("dwconv_out");
       SS_GEMM(Gm.c1, "fsmn_conv1");
       ln2_kernel<<<wtok, 256, 0, st>>>(c1y, Y.n1_w, Y.n1_b, gin, xnp, xnp + M * FI, M);
       SS_TICK("ln2");
       SS_GEMM(Gm.uv, "fsmn_uv");
-      dwconv_kernel<<<dim3(2 * FI / 32 / DWI_WARPS, B), DWI_WARPS * 32, 0, st>>>(uvp, Y.uv_c, nullptr, uv, xupl, xupl + M * FI, FI, T, 2 * FI);
+      dwconv_kernel<<<dim3(2 * FI / 32 / DWI_WARPS, B, (T + DW_SEG - 1) / DW_SEG), DWI_WARPS * 32, 0, st>>>(uvp, Y.uv_c, nullptr, uv, xupl, xupl + M * FI, FI, T, 2 * FI);
       SS_TICK("dwconv_uv");
       SS_GEMM(Gm.ul, "fsmn_linear");
       SS_GEMM(Gm.up, "fsmn_project");

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the north-star path: noisy chunk in -> clean chunk out (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--model gtcrn|mbr|mf2se] [--batch B] [--impl adn|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model gtcrn|mbr|mf2se|mf2ss] [--batch B] [--impl adn|reference]
 
 A "step" is one pass of the hot path over one batch of B synthetic chunks per GPU.
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field's definition.
@@ -292,7 +292,106 @@ class Mf2seWorkload:
         }
 
 
-WORKLOADS = {"gtcrn": GtcrnWorkload, "mbr": MbrWorkload, "mf2se": Mf2seWorkload}
+class Mf2ssWorkload:
+    """MossFormer2-SS-16K (BASELINE.json configs[4], the separation half of the mixed stream): 24 FLASH + dilated-FSMN
+    layers, 1 s windows at 16 kHz (16000 samples, 1999 encoder frames = 8 FLASH groups), two separated outputs."""
+    name = "mf2ss"
+    default_batch = 64
+    chunk, sr, channels, t_frames, layers = 16000, 16000, 1, 1999, 24
+    cpu_chunks, ref_chunks = 4, 2
+    in_name = "mix_audio"
+    cpu_desc = "oracle/mf2ss_oracle.py (PyTorch-eager restatement, pinned to the executed reference wrapper)"
+    tc3_kernels = ("front_gemm", "fl_in", "att_qk", "att_pv", "att_kv", "fl_out", "fsmn_conv1", "fsmn_uv",
+                   "fsmn_linear", "fsmn_project", "fsmn_conv2", "tail_gate_gemm", "mask_gemm")
+
+    def describe(self, B):
+        return (f"MossFormer2-SS-16K, {self.layers} layers, {B} x 1 s windows (16000 samples, 1999 frames, 8 FLASH groups) "
+                f"per GPU per step, 2 speakers out, F32 in (int16 scale) / F32 out")
+
+    def audio_seconds(self, B):
+        return B * self.chunk / self.sr
+
+    def weights(self):
+        import mf2ss_oracle as so
+        return so.random_state_dict(so.SsConfig(layers=self.layers), 0)
+
+    def build(self, sd, device):
+        from adn import export, mf2ss_params
+        return export.mf2ss_model(sd, mf2ss_params.SsHyper(layers=self.layers), self.chunk, "F32", "F32", device_id=device)
+
+    def export(self, sd, path):
+        from adn import export, mf2ss_params
+        export.export_mf2ss(sd, path, mf2ss_params.SsHyper(layers=self.layers), self.chunk, "F32", "F32")
+
+    def inputs(self, B, n_sets, seed):
+        sets = []
+        for s in range(n_sets):
+            g = torch.Generator().manual_seed(seed + s)
+            x = 0.2 * torch.randn(B, 1, self.chunk, generator=g)
+            t = torch.arange(self.chunk, dtype=torch.float32) / self.sr
+            x = x + 0.3 * torch.sin(2 * torch.pi * (220.0 + 10 * s) * t).reshape(1, 1, -1)
+            sets.append((x / x.abs().amax() * 0.5 * 32767.0).contiguous())     # int16-scale samples (:411)
+        return sets
+
+    def cpu_rate(self, sd, n_chunks, threads):
+        import mf2ss_oracle as so
+        cfg = so.SsConfig(layers=self.layers)
+        P = so.fold(sd, cfg, self.t_frames)
+        torch.set_num_threads(threads)
+        g = torch.Generator().manual_seed(7)
+        x = (torch.rand(1, 1, self.chunk, generator=g) * 2 - 1) * 0.3 * 32767.0
+        with torch.inference_mode():
+            so.mf2ss_forward(sd, x, cfg, folded=P)
+            t0 = time.perf_counter()
+            for _ in range(n_chunks):
+                so.mf2ss_forward(sd, x, cfg, folded=P)
+            dt = time.perf_counter() - t0
+        return n_chunks * self.chunk / self.sr / dt, dt
+
+    def kernel_work(self):
+        """Algorithmic (bytes, flops) per window and per LAUNCH of each kernel."""
+        T, L, Tg, G = self.t_frames, self.chunk, 2048, 8
+
+        def gemm(m, k, n, outs=1):          # A planes (hi+lo) in, `outs` fp32-sized outputs
+            return (4 * (2 * m * k + outs * m * n), 2 * m * k * n)
+
+        return {
+            "norm_audio": (3 * L * 4, 6 * L),
+            "encoder": (L * 4 + T * 512 * 4, 2 * 16 * T * 512),
+            "encnorm": (4 * T * 512 * 4, 4 * T * 512),
+            "front_gemm": gemm(T, 512, 512, 2),
+            "shiftnorm": (3 * T * 512 * 4, 3 * T * 512),
+            "fl_in": gemm(T, 512, 2176),
+            "dwconv_in": (T * 2176 * 4 + T * 2048 * 4 + 2 * 2048 * T * 4 + 8 * T * 128 * 4, 2 * 17 * T * 2176),
+            "att_qk": (4 * Tg * 128 * 4 + 2 * Tg * 256 * 4, 2 * G * 256 * 256 * 128),
+            "att_kv": (2 * 2048 * Tg * 4 + 2 * 128 * Tg * 4 + 2 * 2048 * 128 * 4, 2 * 2048 * Tg * 128),
+            # quadratic value product with the linear-attention product riding along as 128 extra K columns
+            "att_pv": (2 * Tg * 384 * 4 + 2 * 2048 * Tg * 4 + 2 * 2048 * 128 * 4 + Tg * 2048 * 4, 2 * G * 256 * (256 + 128) * 2048),
+            "gate": (2 * T * 2048 * 4 + 2 * T * 1024 * 4, 8 * T * 1024),
+            "fl_out": gemm(T, 1024, 512),
+            "dwconv_out": (5 * T * 512 * 4, 2 * 17 * T * 512),
+            "fsmn_conv1": gemm(T, 512, 256),
+            "ln2": (4 * T * 256 * 4, 16 * T * 256),
+            "fsmn_uv": gemm(T, 256, 512),
+            "dwconv_uv": (2 * T * 512 * 4 + 2 * T * 256 * 4, 2 * 17 * T * 512),
+            "fsmn_linear": gemm(T, 256, 256, 2),
+            "fsmn_project": gemm(T, 256, 256),
+            "fsmn_mem1": (2 * T * 256 * 4, 2 * 39 * T * 256),
+            "fsmn_stats1": (32 * 256 * 8, 0),
+            "fsmn_mem2": (3 * T * 256 * 4, 4 * 39 * T * 256),
+            "fsmn_stats2": (32 * 256 * 8, 0),
+            "fsmn_out": (6 * T * 256 * 4, 24 * T * 256),
+            "fsmn_conv2": gemm(T, 256, 512, 2),
+            "tail_norm": (6 * T * 512 * 4, 20 * T * 512),
+            "tail_gate_gemm": gemm(T, 512, 2048),
+            "tail_gate": (4 * T * 1024 * 4, 16 * T * 512),
+            "mask_gemm": gemm(2 * T, 512, 512),
+            "decoder": (3 * T * 512 * 4 + 2 * T * 16 * 4, 2 * 2 * T * 512 * 17),
+            "ola_out": (2 * T * 16 * 4 + 3 * 2 * L * 4, 6 * L),
+        }
+
+
+WORKLOADS = {"gtcrn": GtcrnWorkload, "mbr": MbrWorkload, "mf2se": Mf2seWorkload, "mf2ss": Mf2ssWorkload}
 
 
 class ClockSampler:
@@ -388,7 +487,7 @@ def main():
     args.warmup = max(args.warmup, 3)
     wl = WORKLOADS[args.model]()
     if args.steps <= 0:
-        args.steps = 100 if args.model == "gtcrn" else 10
+        args.steps = 100 if args.model == "gtcrn" else (5 if args.model == "mf2ss" else 10)
     if args.impl == "reference":
         args.steps = min(args.steps, 20)
         run_reference(args, wl)
@@ -415,12 +514,15 @@ def main():
     sd = wl.weights()                      # seeded synthetic weights (no compute from oracle/ on the GPU path)
     model = wl.build(sd, local_rank)
     out_info = model.outputs[0]
+    n_out = len(model.outputs)                                         # 2 for MossFormer2-SS (one waveform per speaker)
     out_shape = (B, out_info.channels, out_info.length)
     in_bytes = B * wl.channels * wl.chunk * 4
     n_sets = max(2, min(8, int(np.ceil(160 * 2**20 / in_bytes))))      # rotated inputs exceed the 126 MB L2
     host_sets = wl.inputs(B, n_sets, seed=1234 + rank)
     dev_sets = [x.to(dev) for x in host_sets]
     out = torch.empty(out_shape, dtype=torch.float32, device=dev)
+    if n_out > 1:
+        out = tuple(torch.empty(out_shape, dtype=torch.float32, device=dev) for _ in range(n_out))
     stream = torch.cuda.current_stream(dev)
 
     def barrier():
@@ -501,21 +603,22 @@ def main():
     sess = onnxruntime.InferenceSession(str(mpath), providers=["CPUExecutionProvider"], device_id=local_rank)
     mpath.unlink(missing_ok=True)
     pin_in = [x.pin_memory() for x in host_sets]
-    pin_out = torch.empty(out_shape, dtype=torch.float32).pin_memory()
-    vout = onnxruntime.OrtValue.ortvalue_from_numpy(pin_out.numpy())
+    pin_outs = [torch.empty(out_shape, dtype=torch.float32).pin_memory() for _ in range(n_out)]
     vins = [onnxruntime.OrtValue.ortvalue_from_numpy(p.numpy()) for p in pin_in]
     bind = sess.io_binding()
-    bind.bind_ortvalue_output("denoised_audio", vout)
+    for o, p in zip(sess.get_outputs(), pin_outs):
+        bind.bind_ortvalue_output(o.name, onnxruntime.OrtValue.ortvalue_from_numpy(p.numpy()))
+    in_name = sess.get_inputs()[0].name
     checksum = 0.0
     for i in range(args.warmup):
-        bind.bind_ortvalue_input("noisy_audio", vins[i % n_sets])
+        bind.bind_ortvalue_input(in_name, vins[i % n_sets])
         sess.run_with_iobinding(bind)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        bind.bind_ortvalue_input("noisy_audio", vins[i % n_sets])
+        bind.bind_ortvalue_input(in_name, vins[i % n_sets])
         sess.run_with_iobinding(bind)                           # synchronous, result is in host memory
-        checksum += float(pin_out[0, 0, 0])
+        checksum += float(pin_outs[0][0, 0, 0])
     barrier()
     e2e_ms = allmax((time.perf_counter() - t0) * 1e3)
     e2e_value = audio_s / (e2e_ms * 1e-3)
@@ -542,7 +645,7 @@ def main():
             "rtf": 1.0 / value,
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
-                    "d2h_bytes_per_step": int(np.prod(out_shape)) * 4, "ms_per_step": e2e_ms / args.steps,
+                    "d2h_bytes_per_step": n_out * int(np.prod(out_shape)) * 4, "ms_per_step": e2e_ms / args.steps,
                     "api": "adn.ort_shim.InferenceSession.run_with_iobinding -> adn_run_host (pinned host buffers)"},
             "gpu_launches": launches * args.steps,
             "roofline": roof,
