@@ -179,40 +179,43 @@ inorm_stats_kernel(const float* __restrict__ part, int tiles, float* __restrict_
 }
 
 // Memory conv 2 (:532-537, j = 1): input = cat(PReLU(IN(conv1)), xp) (512 channels), groups = 256 (output c reads
-// input channels 2c, 2c+1), k = 39, dilation 2, zero padding 38.  blockIdx.z = 0: outputs 0..127 from the
-// normalised conv-1 branch (normalised while the tile is loaded), 1: outputs 128..255 from xp.
-// Thread = (output channel, half of the 64 frames).  taps: (2, 39, 256) = [input slot][tap][output channel].
-static __global__ void __launch_bounds__(256)
+// input channels 2c, 2c+1), k = 39, dilation 2, zero padding 38.  blockIdx.z = 2*half + sub: half 0 -> outputs 0..127
+// from the normalised conv-1 branch (normalised while the tile is loaded), half 1 -> outputs 128..255 from xp; sub picks
+// 64 of those outputs (128 input columns).  Thread = (output channel, quarter of the 64 frames).
+// taps: (2, 39, 256) = [input slot][tap][output channel].
+constexpr int MEM2_CH = 64;
+static __global__ void __launch_bounds__(256, 2)
 mem2_kernel(const float* __restrict__ m1, const float* __restrict__ stats1, const float* __restrict__ nw,
             const float* __restrict__ nb, const float* __restrict__ alpha, const float* __restrict__ xp,
             const float* __restrict__ taps, float* __restrict__ out, float* __restrict__ part, int T) {
   extern __shared__ float msm[];
-  float (*tile)[FI] = reinterpret_cast<float (*)[FI]>(msm);                 // [MEM2_ROWS][256 input channels]
-  __shared__ float red[2][2][FI / 2];
-  const int t0 = blockIdx.x * MEM_TT, b = blockIdx.y, half = blockIdx.z, tid = threadIdx.x;
+  float (*tile)[2 * MEM2_CH] = reinterpret_cast<float (*)[2 * MEM2_CH]>(msm);   // [MEM2_ROWS][128 input channels]
+  __shared__ float red[4][2][MEM2_CH];
+  const int t0 = blockIdx.x * MEM_TT, b = blockIdx.y, half = blockIdx.z >> 1, sub = blockIdx.z & 1, tid = threadIdx.x;
   const long long base = (long long)b * T;
-  if (half == 0) {
-    const float mean = stats1[((long long)b * FI + tid) * 2], rstd = stats1[((long long)b * FI + tid) * 2 + 1];
-    const float g = __ldg(nw + tid) * rstd, sh = __ldg(nb + tid) - mean * g, a = __ldg(alpha + tid);
-    for (int r = 0; r < MEM2_ROWS; ++r) {
+  {
+    const int col = tid & (2 * MEM2_CH - 1), ch = sub * 2 * MEM2_CH + col;          // input channel of this branch
+    float g = 1.f, sh = 0.f, a = 1.f;
+    const float* src = xp;
+    if (half == 0) {
+      const float mean = stats1[((long long)b * FI + ch) * 2], rstd = stats1[((long long)b * FI + ch) * 2 + 1];
+      g = __ldg(nw + ch) * rstd; sh = __ldg(nb + ch) - mean * g; a = __ldg(alpha + ch);
+      src = m1;
+    }
+    for (int r = tid >> 7; r < MEM2_ROWS; r += 2) {
       const int t = t0 + r - 2 * MEMH;
       float v = 0.f;                                                        // zero padding applies AFTER norm + PReLU
-      if (t >= 0 && t < T) v = adn_prelu(__ldg(m1 + (base + t) * FI + tid) * g + sh, a);
-      tile[r][tid] = v;
-    }
-  } else {
-    for (int r = 0; r < MEM2_ROWS; ++r) {
-      const int t = t0 + r - 2 * MEMH;
-      tile[r][tid] = (t >= 0 && t < T) ? __ldg(xp + (base + t) * FI + tid) : 0.f;
+      if (t >= 0 && t < T) v = adn_prelu(__ldg(src + (base + t) * FI + ch) * g + sh, a);
+      tile[r][col] = v;
     }
   }
-  const int j = tid & 127, th = tid >> 7, c = half * 128 + j;
+  const int j = tid & (MEM2_CH - 1), th = tid >> 6, c = half * 128 + sub * MEM2_CH + j;
   float k0[MEMK], k1[MEMK];
 #pragma unroll
   for (int i = 0; i < MEMK; ++i) { k0[i] = __ldg(taps + i * FI + c); k1[i] = __ldg(taps + (MEMK + i) * FI + c); }
   __syncthreads();
   float su = 0.f, sq = 0.f;
-  for (int tt = th * (MEM_TT / 2); tt < (th + 1) * (MEM_TT / 2); tt += 8) {
+  for (int tt = th * (MEM_TT / 4); tt < (th + 1) * (MEM_TT / 4); tt += 8) {
     // 8 outputs per pass: output tt + q reads rows tt + q + 2i, so the four even (odd) outputs share the 42 rows
     // tt (+1) + 2r -- one 64-bit shared load feeds up to 8 FMAs
     float a[8];
@@ -245,8 +248,8 @@ mem2_kernel(const float* __restrict__ m1, const float* __restrict__ stats1, cons
   __syncthreads();
   if (th == 0) {
     float* p = part + (((long long)b * gridDim.x + blockIdx.x) * FI + c) * 2;
-    p[0] = red[0][0][j] + red[1][0][j];
-    p[1] = red[0][1][j] + red[1][1][j];
+    p[0] = (red[0][0][j] + red[1][0][j]) + (red[2][0][j] + red[3][0][j]);
+    p[1] = (red[0][1][j] + red[1][1][j]) + (red[2][1][j] + red[3][1][j]);
   }
 }
 
@@ -594,7 +597,7 @@ class SsModel : public Base {
     static bool cfg = false;
     if (!cfg) {
       cudaFuncSetAttribute(mem1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MEM1_ROWS * FI * 4);
-      cudaFuncSetAttribute(mem2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MEM2_ROWS * FI * 4);
+      cudaFuncSetAttribute(mem2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MEM2_ROWS * 2 * MEM2_CH * 4);
       cfg = true;
     }
 
@@ -642,7 +645,7 @@ class SsModel : public Base {
       SS_TICK("fsmn_mem1");
       inorm_stats_kernel<<<B, 256, 0, st>>>(part, mem_tiles, stats, T);
       SS_TICK("fsmn_stats1");
-      mem2_kernel<<<dim3(mem_tiles, B, 2), 256, MEM2_ROWS * FI * sizeof(float), st>>>(m1, stats, Y.mem0_nw, Y.mem0_nb, Y.mem0_a, xp2,
+      mem2_kernel<<<dim3(mem_tiles, B, 4), 256, MEM2_ROWS * 2 * MEM2_CH * sizeof(float), st>>>(m1, stats, Y.mem0_nw, Y.mem0_nb, Y.mem0_a, xp2,
                                                                                     Y.mem1_c, m2, part2, T);
       SS_TICK("fsmn_mem2");
       inorm_stats_kernel<<<B, 256, 0, st>>>(part2, mem_tiles, stats2, T);
