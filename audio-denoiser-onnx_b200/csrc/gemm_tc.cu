@@ -375,7 +375,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 for (int j = 0; j < 4; ++j) x[j] = tanhf(x[j]);
               } else if (g.act == ACT_SILU) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) x[j] = x[j] / (1.0f + expf(-x[j]));
+                for (int j = 0; j < 4; ++j) x[j] = x[j] * __fdividef(1.0f, 1.0f + __expf(-x[j]));   // ex2.approx / rcp.approx: ~2 ulp,
+                                                                                                     // a third of the epilogue's instructions
               } else if (g.act == ACT_RELU) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.f);

@@ -290,42 +290,79 @@ fsmn_out_kernel(const float* __restrict__ m2, const float* __restrict__ stats2, 
   split4(make_float4(v[4], v[5], v[6], v[7]), yhi, ylo, m * FI + 128 + lane * 4);
 }
 
-// One warp per (token, speaker): sep = x_enc * mask, then the 16 ConvTranspose1d taps of that frame.
+// One warp per 2 tokens x 2 speakers: sep = x_enc * mask, then the 16 ConvTranspose1d taps of each frame.  The four
+// rows share every decoder-weight load (register tile 4 rows x 16 taps per lane; lanes split the 512 channels).
 // dec_w: (512, 16).  fo: (window, speaker, frame, 16).
+constexpr int DEC_TOK = 2;
 static __global__ void __launch_bounds__(256)
 dec_kernel(const float* __restrict__ xenc, const float* __restrict__ mask, const float* __restrict__ dw,
            float* __restrict__ fo, long long M, int n) {
-  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);        // r = m*SPK + s
-  if (r >= M * SPK) return;
+  const long long m0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * DEC_TOK;
+  if (m0 >= M) return;
   const int lane = threadIdx.x & 31;
-  const long long m = r / SPK;
-  const int s = (int)(r - m * SPK);
-  float acc[ENC_K];
+  float acc[DEC_TOK * SPK][ENC_K];
 #pragma unroll
-  for (int k = 0; k < ENC_K; ++k) acc[k] = 0.f;
+  for (int r = 0; r < DEC_TOK * SPK; ++r)
+#pragma unroll
+    for (int k = 0; k < ENC_K; ++k) acc[r][k] = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int c = (i * 32 + lane) * 4;
-    const float4 e = ld4(xenc + m * D + c), mk = ld4(mask + r * D + c);
-    const float p[4] = {e.x * mk.x, e.y * mk.y, e.z * mk.z, e.w * mk.w};
+    float p[DEC_TOK * SPK][4];
+#pragma unroll
+    for (int tk = 0; tk < DEC_TOK; ++tk) {
+      const long long m = m0 + tk < M ? m0 + tk : M - 1;
+      const float4 e = ld4(xenc + m * D + c);
+#pragma unroll
+      for (int sp = 0; sp < SPK; ++sp) {
+        const float4 mk = ld4(mask + (m * SPK + sp) * D + c);
+        p[tk * SPK + sp][0] = e.x * mk.x; p[tk * SPK + sp][1] = e.y * mk.y;
+        p[tk * SPK + sp][2] = e.z * mk.z; p[tk * SPK + sp][3] = e.w * mk.w;
+      }
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
 #pragma unroll
       for (int k4 = 0; k4 < ENC_K / 4; ++k4) {
         const float4 wv = __ldg(reinterpret_cast<const float4*>(dw + (c + q) * ENC_K) + k4);
-        acc[4 * k4] += p[q] * wv.x; acc[4 * k4 + 1] += p[q] * wv.y; acc[4 * k4 + 2] += p[q] * wv.z; acc[4 * k4 + 3] += p[q] * wv.w;
+#pragma unroll
+        for (int r = 0; r < DEC_TOK * SPK; ++r) {
+          acc[r][4 * k4] += p[r][q] * wv.x; acc[r][4 * k4 + 1] += p[r][q] * wv.y;
+          acc[r][4 * k4 + 2] += p[r][q] * wv.z; acc[r][4 * k4 + 3] += p[r][q] * wv.w;
+        }
       }
     }
   }
+  // 64 lane-partial sums -> lane l keeps (row l / 16, tap l % 16) of each half: fold the 32 lanes pairwise so that
+  // every shuffle halves the number of live values (63 shuffles instead of 64 x 5)
+  float v[DEC_TOK * SPK * ENC_K];
 #pragma unroll
-  for (int k = 0; k < ENC_K; ++k) acc[k] = warp_sum(acc[k]);
-  const long long b = m / n;
-  const int t = (int)(m - b * n);
-  if (lane < ENC_K) {
-    float v = acc[0];
+  for (int r = 0; r < DEC_TOK * SPK; ++r)
 #pragma unroll
-    for (int k = 1; k < ENC_K; ++k) v = lane == k ? acc[k] : v;
-    fo[((b * SPK + s) * n + t) * ENC_K + lane] = v;
+    for (int k = 0; k < ENC_K; ++k) v[r * ENC_K + k] = acc[r][k];
+#pragma unroll
+  for (int step = 0; step < 5; ++step) {
+    const int half = (DEC_TOK * SPK * ENC_K) >> (step + 1);          // 32, 16, 8, 4, 2 values kept
+    const bool up = (lane >> step) & 1;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float mine = up ? v[j + half] : v[j], other = up ? v[j] : v[j + half];
+      v[j] = mine + __shfl_xor_sync(0xffffffffu, other, 1 << step);
+    }
+  }
+  // lane bits (b0..b4) selected value index bit (5 - step): lane l now holds values idx0 = bitrev-style index, 2 values
+  int idx = 0;
+#pragma unroll
+  for (int step = 0; step < 5; ++step) idx |= ((lane >> step) & 1) << (5 - step);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int e = idx + j, r = e / ENC_K, k = e % ENC_K;
+    const long long m = m0 + r / SPK;
+    if (m < M) {
+      const long long b = m / n;
+      const int t = (int)(m - b * n);
+      fo[((b * SPK + (r % SPK)) * n + t) * ENC_K + k] = v[j];
+    }
   }
 }
 
@@ -661,7 +698,7 @@ class SsModel : public Base {
     tail_gate_kernel<<<(unsigned)((M * SPK * (D / 4) + 255) / 256), 256, 0, st>>>(gbuf, tg, tg + M * SPK * D, M * SPK);
     SS_TICK("tail_gate");
     SS_GEMM(g_mask, "mask_gemm");
-    dec_kernel<<<(unsigned)((M * SPK + 7) / 8), 256, 0, st>>>(xenc, mask, dec_w, fo, M, T);
+    dec_kernel<<<(unsigned)((M + 8 * DEC_TOK - 1) / (8 * DEC_TOK)), 256, 0, st>>>(xenc, mask, dec_w, fo, M, T);
     SS_TICK("decoder");
     ola_out_kernel<<<B * SPK, 512, 0, st>>>(fo, dec_b, rms_in, wav, d_outs[0], d_outs[1], out_dtype, T, Lout);
     SS_TICK("ola_out");
