@@ -301,6 +301,10 @@ class Mf2ssWorkload:
     cpu_chunks, ref_chunks = 4, 2
     in_name = "mix_audio"
     cpu_desc = "oracle/mf2ss_oracle.py (PyTorch-eager restatement, pinned to the executed reference wrapper)"
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch at B = 64 (ncu --set full, profiles/r1f_mf2ss_b64_ncu_raw.csv)
+    ncu_traffic = (64, {"fl_in": 1698158000, "dwconv_in": 4984556000, "att_pv": 3799065000, "fl_out": 1341530000,
+                        "gate": 3115241000, "fsmn_mem2": 374409000, "dwconv_out": 1287108000, "att_kv": 2413219000},
+                   "profiles/r1f_mf2ss_b64_ncu_raw.csv")
     tc3_kernels = ("front_gemm", "fl_in", "att_qk", "att_pv", "att_kv", "fl_out", "fsmn_conv1", "fsmn_uv",
                    "fsmn_linear", "fsmn_project", "fsmn_conv2", "tail_gate_gemm", "mask_gemm")
 
@@ -584,7 +588,12 @@ def main():
     if tc3 and roof["bound"] == "tensor":
         roof["tf32x3_ceiling"] = pk["bf16_tflops_sustained"] / 6.0
         roof["frac_of_tf32x3_ceiling"] = roof["achieved"] / roof["tf32x3_ceiling"]
-    roof.update({"traffic": None, "kernel": top, "kernel_ms_per_launch": launch_ms, "launches_per_step": n_l,
+    traffic = None
+    nt = getattr(wl, "ncu_traffic", None)
+    if nt and nt[0] == B and top in nt[1]:
+        traffic = nt[1][top]
+        roof["traffic_source"] = nt[2]
+    roof.update({"traffic": traffic, "kernel": top, "kernel_ms_per_launch": launch_ms, "launches_per_step": n_l,
                  "kernel_share_of_step": top_ms / step_ms_prof, "peak_source": pk["src"],
                  "algorithmic_bytes_per_launch": lb, "algorithmic_flops_per_launch": lf,
                  "note": "3xTF32 kernels issue 3 tf32 MMAs per algorithmic MAC: their ceiling is bf16 peak / 6"})

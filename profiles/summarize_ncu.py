@@ -41,7 +41,12 @@ def launches(path, out):
 
 
 def raw(rep, out):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """rep: an .ncu-rep, or the CSV of its raw page already exported on the GPU box (reports of a full-set capture are
+    tens of MB and do not travel back)."""
+    if str(rep).endswith(".csv"):
+        txt = open(rep).read()
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     h, units = rows[0], rows[1]
     cols = [h.index("Kernel Name")] + [h.index(m) for m in RAW if m in h]

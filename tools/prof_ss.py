@@ -13,8 +13,9 @@ from adn import export, mf2ss_params
 layers, B, reps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 cfg = so.SsConfig(layers=layers)
 sd = so.random_state_dict(cfg, 0)
-m = export.mf2ss_model(sd, mf2ss_params.SsHyper(layers=layers), 16000)
-x = ((torch.rand(B, 1, 16000) - 0.5) * 20000.0).cuda()
+L = int(sys.argv[4]) if len(sys.argv) > 4 else 16000
+m = export.mf2ss_model(sd, mf2ss_params.SsHyper(layers=layers), L)
+x = ((torch.rand(B, 1, L) - 0.5) * 20000.0).cuda()
 for _ in range(reps):
     y = m.run(x)
 torch.cuda.synchronize()
