@@ -116,6 +116,19 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// erf for the GELU epilogue: Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7) on rcp.approx / ex2.approx -- about half the
+// instructions of erff; the epilogue, not the tensor pipe, limits the small-K GEMMs that use it.
+__device__ __forceinline__ float fast_erf(float x) {
+  const float a = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, a, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float r = 1.0f - p * t * __expf(-a * a);
+  return copysignf(r, x);
+}
+
 __device__ __forceinline__ int16_t to_i16(float y, int mode) {
   if (mode == 1) return (int16_t)(int)(fminf(fmaxf(y, -1.0f), 32767.0f / 32768.0f) * 32768.0f);
   return (int16_t)(int)fminf(fmaxf(y * 32767.0f, -32768.0f), 32767.0f);
@@ -369,7 +382,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               float x[4] = {a4.x * rs + bias4.x, a4.y * rs + bias4.y, a4.z * rs + bias4.z, a4.w * rs + bias4.w};
               if (g.act == ACT_GELU) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) x[j] = 0.5f * x[j] * (1.0f + erff(x[j] * 0.70710678118654752440f));
+                for (int j = 0; j < 4; ++j) x[j] = 0.5f * x[j] * (1.0f + fast_erf(x[j] * 0.70710678118654752440f));
               } else if (g.act == ACT_TANH) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) x[j] = tanhf(x[j]);
