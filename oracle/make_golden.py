@@ -203,8 +203,34 @@ def main_mf2ss():
             print(f"mf2ss {dt} L{L}: {tuple(xin.shape)} -> 2 x {tuple(ys[0].shape)} max|y| {ys[0].float().abs().max().item():.4f}")
 
 
+def main_mfgan():
+    """MossFormerGAN-SE-16K fixtures: the reference wrapper (`MOSSFORMER_SE` of MossFormerGAN_SE_16K) executed around
+    `mfgan_oracle.skeleton()` on seeded weights, 2 SyncANet blocks (the block count is the only reduced
+    hyper-parameter); 3150 samples (wrap-around pad to 3200, 33 frames) in F32 and 2400 samples (25 frames) in INT16;
+    one all-zero window."""
+    import mfgan_oracle as go
+
+    assert ref_loader.reference_available()
+    cfg = go.GanConfig(layers=2)
+    sd = go.random_state_dict(cfg, 0)
+    hold = go.skeleton(cfg)
+    hold.load_state_dict(sd)
+    with torch.inference_mode():
+        for L, dt in ((3150, "F32"), (2400, "INT16")):
+            _, build = ref_loader.load_mfgan(L, dt)
+            w = build(hold)
+            x = synth_audio(L, 4321, batch=3)
+            x[2] = 0.0
+            xin = x if dt == "F32" else torch.round(x * 32767.0).to(torch.int16)
+            y = torch.cat([w(xin[i:i + 1].clone()) for i in range(3)], dim=0)
+            np.savez_compressed(GOLDEN / f"mfgan_{dt.lower()}_L{L}_l2.npz", x=xin.numpy(), y=y.numpy(), seed=0, layers=2)
+            print(f"mfgan {dt} L{L}: {tuple(xin.shape)} -> {tuple(y.shape)} max|y| {y.float().abs().max().item():.4f}")
+
+
 if __name__ == "__main__":
-    if "--mf2ss" in sys.argv:
+    if "--mfgan" in sys.argv:
+        main_mfgan()
+    elif "--mf2ss" in sys.argv:
         main_mf2ss()
     elif "--mbr" in sys.argv:
         main_mbr()

@@ -236,3 +236,45 @@ def load_mf2ss(input_audio_length: int, io_dtype: str = "F32"):
                                        ns["OUT_SAMPLE_RATE"], False, ns["FOLD_WINDOW_LENGTH"]).eval()
 
     return ns, build
+
+
+def load_mfgan(input_audio_length: int, io_dtype: str = "F32"):
+    """Reference MossFormerGAN-SE-16K wrapper (`MOSSFORMER_SE` of MossFormerGAN_SE_16K/Export_MossFormer_SE.py)
+    for one un-folded window.  The wrapper's forward is made of leaf ops; its constructor and forward read
+    parameters off the absent `clearvoice` generator.  Returns (namespace, build) with
+    build(holder) -> wrapper, where `holder` is `mfgan_oracle.skeleton()` carrying the weights."""
+    import torch
+
+    for name in ("clearvoice", "clearvoice.models", "clearvoice.models.mossformer_gan_se",
+                 "clearvoice.models.mossformer_gan_se.generator"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["clearvoice.models.mossformer_gan_se.generator"].MossFormerGAN_SE_16K = object
+    if "Rewrite_ONNX_Asymmetric_Padding" not in sys.modules:
+        mod = types.ModuleType("Rewrite_ONNX_Asymmetric_Padding")
+        mod.rewrite_asymmetric_causal_convs = lambda *a, **k: None
+        sys.modules["Rewrite_ONNX_Asymmetric_Padding"] = mod
+
+    ns = load_export_namespace(
+        "MossFormerGAN_SE_16K",
+        "Export_MossFormer_SE.py",
+        {
+            "INPUT_AUDIO_LENGTH   = 32000": f"INPUT_AUDIO_LENGTH   = {int(input_audio_length)}",
+            "IN_AUDIO_DTYPE       = 'INT16'": f"IN_AUDIO_DTYPE       = '{io_dtype}'",
+            "OUT_AUDIO_DTYPE      = 'INT16'": f"OUT_AUDIO_DTYPE      = '{io_dtype}'",
+            "USE_BATCH_FOLD       = True": "USE_BATCH_FOLD       = False",
+        },
+    )
+
+    def build(holder):
+        with torch.inference_mode():
+            S = ns["STFT_Process"]
+            stft = S(model_type="stft_C", n_fft=ns["NFFT"], hop_len=ns["HOP_LENGTH"], win_length=ns["WINDOW_LENGTH"],
+                     max_frames=0, window_type=ns["WINDOW_TYPE"], center_pad=True, pad_mode="reflect").eval()
+            istft = S(model_type="istft_C", n_fft=ns["NFFT"], hop_len=ns["HOP_LENGTH"], win_length=ns["WINDOW_LENGTH"],
+                      max_frames=ns["MAX_SIGNAL_LENGTH"], window_type=ns["WINDOW_TYPE"], center_pad=True, pad_mode="reflect",
+                      precompute_window_sum=True).eval()
+            return ns["MOSSFORMER_SE"](holder.eval().float(), stft, istft, ns["IN_SAMPLE_RATE"], ns["OUT_SAMPLE_RATE"],
+                                       False, ns["FOLD_WINDOW_LENGTH"]).eval()
+
+    return ns, build

@@ -242,7 +242,7 @@ def test_mf2se_oracle_matches_reference_module():
         yr = w(x.clone())
         yo = mo.mf2se_forward(sd, x, cfg)
     assert yr.shape == yo.shape == (1, 1, L)
-    assert (yr - yo).abs().max() <= 2e-6
+    assert (yr - yo).abs().max() <= 5e-6 * max(1.0, float(yr.abs().max()))     # fp32 re-association only (max|y| 0.69)
 
 
 # ----------------------------------------------------------------------------- MossFormer2-SS-16K
@@ -298,3 +298,60 @@ def test_mf2ss_oracle_matches_reference_module():
     for a, b in zip(yr, yo):
         assert a.shape == b.shape == (1, 1, L)
         assert (a - b).abs().max() <= 5e-6
+
+
+# ----------------------------------------------------------------------------- MossFormerGAN-SE-16K (oracle only: no CUDA path yet)
+@pytest.mark.parametrize("fixture,dt", [("mfgan_f32_L3150_l2", "F32"), ("mfgan_int16_L2400_l2", "INT16")])
+def test_mfgan_oracle_matches_golden(fixture, dt, golden_dir):
+    import mfgan_oracle as go
+
+    g = np.load(golden_dir / f"{fixture}.npz")
+    cfg = go.GanConfig(layers=int(g["layers"]))
+    sd = go.random_state_dict(cfg, int(g["seed"]))
+    with torch.inference_mode():
+        y = go.mfgan_forward_batch(sd, torch.from_numpy(g["x"]), cfg, dt, dt, chunk=1).numpy()
+    assert y.shape == g["y"].shape and y.dtype == g["y"].dtype
+    if dt == "INT16":
+        assert np.abs(y.astype(np.int32) - g["y"].astype(np.int32)).max() <= 1
+    else:
+        assert np.abs(y - g["y"]).max() <= 2e-6
+
+
+@needs_ref
+def test_mfgan_oracle_matches_reference_module():
+    """Restated folds + forward vs the reference's own MOSSFORMER_SE (MossFormerGAN) executed around the parameter
+    skeleton: fused buffers bit-equal, waveform <= 5e-6; the wrap-around pad (length not a hop multiple) included."""
+    import mfgan_oracle as go
+
+    cfg = go.GanConfig(layers=2)
+    L = 2750
+    sd = go.random_state_dict(cfg, 7)
+    hold = go.skeleton(cfg)
+    hold.load_state_dict(sd)
+    _, build = ref_loader.load_mfgan(L, "F32")
+    w = build(hold)
+    T = cfg.n_frames(L)
+    assert w.frames_static == T == 29 and w.n_freqs == cfg.n_freqs and w.intra_steps == 100
+    P = go.fold(sd, cfg, T)
+    assert torch.equal(P["rot_cos"][:cfg.n_freqs], w.rotary_cos_intra[0, :, 0]) and torch.equal(P["rot_sin"][:T], w.rotary_sin_inter[0, :, 0])
+    for i in range(cfg.layers):
+        pb = w.blk_params[i]
+        assert torch.equal(P[f"B{i}.intra.fconv_w"], pb["intra_fconv_w"]) and torch.equal(P[f"B{i}.intra.fconv_b"], pb["intra_fconv_b"])
+        assert torch.equal(P[f"B{i}.inter.unfold_w"], pb["inter_unfold_w"]) and torch.equal(P[f"B{i}.inter.unfold_b"], pb["inter_unfold_b"])
+        for p in ("intra", "inter"):
+            assert torch.equal(P[f"B{i}.{p}.uv_w"], pb[f"{p}_uv_w"]) and torch.equal(P[f"B{i}.{p}.uv_b"], pb[f"{p}_uv_b"])
+            assert torch.equal(P[f"B{i}.{p}.uv_c"], pb[f"{p}_uv_cw"][:, 0])
+            mf = pb[f"{p}_mf"]
+            for mine, theirs in (("in_w", "in_w"), ("in_b", "in_b"), ("out_w", "out_w"), ("out_b", "out_b"), ("gamma", "gamma"), ("beta", "beta")):
+                assert torch.equal(P[f"B{i}.{p}.mf.{mine}"], mf[theirs]), (p, mine)
+            assert float(P[f"B{i}.{p}.mf.cross_scale"]) == mf["cross_scale"]
+        ap = pb["attn"]
+        assert torch.equal(P[f"B{i}.att.w"], ap["w"][:, :, 0, 0]) and torch.equal(P[f"B{i}.att.a"], ap["prelu"])
+        assert torch.equal(P[f"B{i}.att.q_g"], ap["qk_gamma"][0, 0, :, 0]) and torch.equal(P[f"B{i}.att.k_b"], ap["qk_beta"][0, 1, :, 0])
+        assert torch.equal(P[f"B{i}.att.v_g"], ap["v_gamma"][0, :, 0])
+    x = synth_audio(L, 11)
+    with torch.inference_mode():
+        yr = w(x.clone())
+        yo = go.mfgan_forward(sd, x, cfg)
+    assert yr.shape == yo.shape == (1, 1, L)
+    assert (yr - yo).abs().max() <= 5e-6 * max(1.0, float(yr.abs().max()))     # fp32 re-association only (max|y| 0.69)
