@@ -99,6 +99,45 @@ def denoise(session, audio: np.ndarray, max_batch: int = 4096, tail: str = "zero
     return y.reshape(-1) if (mono_in and y.shape[0] == 1) else y
 
 
+def separate(session, audio: np.ndarray, pad_head: int | None = None, max_batch: int = 4096, tail: str = "zeros",
+             rng=None) -> list[np.ndarray]:
+    """Whole-file drop-in for the run section of `MossFormer2_SS_16K/Inference_MossFormer_SS_ONNX.py:269-340`:
+    `pad_head` zeros are prepended (`:273`; default: the model file's `pad_head` metadata key), the padded signal is cut
+    into fixed windows (stride = window, `:286-305`), ALL windows run as one batch with every output bound
+    (`:312-317`), and each output is concatenated and trimmed to `[pad_head : pad_head + len(audio)]` (`:339-340`).
+    Works for any number of outputs (one list entry per `session.get_outputs()` element).  tail: 'zeros' (fold mode)
+    or 'noise' (the un-folded script's RMS-matched gaussian tail)."""
+    from .ort_shim import OrtValue
+
+    i = session.get_inputs()[0]
+    outs_meta = session.get_outputs()
+    in_len, out_len = i.shape[-1], outs_meta[0].shape[-1]
+    if pad_head is None:
+        pad_head = int(session.get_modelmeta().custom_metadata_map.get("pad_head", "0"))
+    a = np.asarray(audio).reshape(-1)
+    a = np.concatenate([np.zeros(pad_head, dtype=a.dtype), a])
+    n = a.shape[0]
+    stride, num, total = plan_windows(n, in_len, in_len)            # SS strides by the input window (:285)
+    a = tail_pad(a.reshape(1, -1), total - n, tail, rng)
+    idx = np.arange(num)[:, None] * stride + np.arange(in_len)[None, :]
+    windows = np.ascontiguousarray(a[:, idx].transpose(1, 0, 2))     # (num, 1, in_len)
+    results = [[] for _ in outs_meta]
+    for s in range(0, num, max_batch):
+        w = np.ascontiguousarray(windows[s:s + max_batch])
+        b = session.io_binding()
+        b.bind_ortvalue_input(i.name, OrtValue.ortvalue_from_numpy(w))
+        vouts = []
+        for o in outs_meta:
+            v = OrtValue.ortvalue_from_numpy(np.zeros((w.shape[0], o.shape[-2], out_len), dtype=_np_dtype(o.type)))
+            b.bind_ortvalue_output(o.name, v)
+            vouts.append(v)
+        session.run_with_iobinding(b)
+        for r, v in zip(results, vouts):
+            r.append(v.numpy())
+    # windows whose output is shorter than their input (length not 16 + 8k) are concatenated as produced, like the script
+    return [np.concatenate(r, axis=0).reshape(-1)[pad_head:n] for r in results]
+
+
 def _np_dtype(ort_type: str):
     if "int16" in ort_type:
         return np.int16

@@ -261,3 +261,21 @@ def test_mf2ss_packing_matches_oracle_fold():
     assert h.n_frames(16000) == 1999 and h.out_len(16000) == 16000 and h.out_len(16005) == 16000
     with pytest.raises(ValueError):
         sp.pack(sd, h, 8)
+
+
+def test_wavio_roundtrip_and_reference_examples(tmp_path):
+    """stdlib-wave PCM16 reader / writer: round trip, stereo layout, mono fold."""
+    from adn import wavio
+
+    rng = np.random.default_rng(0)
+    st = rng.integers(-30000, 30000, size=(2, 4411), dtype=np.int16)
+    wavio.write_wav(tmp_path / "s.wav", st, 44100)
+    back, sr = wavio.read_wav(tmp_path / "s.wav")
+    assert sr == 44100 and back.dtype == np.int16 and np.array_equal(back, st)
+    mono = wavio.to_mono(st)
+    assert mono.shape == (4411,) and np.array_equal(mono, (st.astype(np.int32).sum(0) // 2).astype(np.int16))
+    wavio.write_wav(tmp_path / "m.wav", mono, 16000)
+    back, sr = wavio.read_wav(tmp_path / "m.wav")
+    assert back.shape == (1, 4411) and sr == 16000
+    with pytest.raises(ValueError):
+        wavio.write_wav(tmp_path / "f.wav", mono.astype(np.float32), 16000)
