@@ -163,7 +163,8 @@ def pack(sd: dict, h: Mf2Hyper, input_audio_length: int) -> dict[str, np.ndarray
     return blob
 
 
-def metadata(h: Mf2Hyper, input_audio_length: int, in_dtype: str = "INT16", out_dtype: str = "INT16") -> dict[str, str]:
+def metadata(h: Mf2Hyper, input_audio_length: int, in_dtype: str = "INT16", out_dtype: str = "INT16",
+             matmul_dtype: str = "F32") -> dict[str, str]:
     """Metadata keys of `Export_MossFormer_SE.py:557-561` + the hyper-parameters the reference
     reads off the live upstream modules."""
     g = stft_tables.GEOMETRY[GEOM_KEY]
@@ -181,5 +182,9 @@ def metadata(h: Mf2Hyper, input_audio_length: int, in_dtype: str = "INT16", out_
         "max_signal_length": g.n_frames(input_audio_length), "center_pad": "0", "pad_mode": "constant",
         "feature_kind": "kaldi_fbank_stft", "input_channels": 1, "output_channels": 1, "num_audio_inputs": 1,
         "n_mels": h.n_mels, "mf2_layers": h.layers,
+        # F32 = 3xTF32 tensor-core GEMMs with fp32-class accuracy (default, the 1e-4 parity path); BF16 = the 24 layers'
+        # GEMMs on bf16 operands with fp32 accumulation (BASELINE.json configs[2] "bf16 matmuls"; frontend, log-mel,
+        # norms, gates and the ISTFT stay fp32, cf. MossFormer2_SE_48K/Optimize_ONNX.py:27-108)
+        "matmul_dtype": matmul_dtype,
     }
     return {k: str(v) for k, v in md.items()}

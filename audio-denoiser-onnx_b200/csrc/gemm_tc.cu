@@ -11,11 +11,16 @@
 // * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
 //   warps 2..5 = epilogue (TMEM -> registers -> global).  Persistent over output tiles with
 //   two TMEM accumulator buffers so the epilogue of tile i overlaps the main loop of i+1.
+//
+// bf16 variant (TcPlan::bf16, licensed only where the workload spec says "bf16 matmuls": MossFormer2-SE-48K,
+// BASELINE.json configs[2]): one bf16 plane per operand, 64-element K blocks (the same 128-byte swizzled rows),
+// tcgen05.mma kind::f16 with fp32 accumulation -- 1 MMA per K step instead of 3 and half the operand bytes.
 #include "adn.h"
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 namespace tc {
 
@@ -80,6 +85,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -115,6 +130,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// kind::f16 with BF16 operands: A=BF16 [7,10)=1, B=BF16 [10,13)=1, D=F32
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 // erf for the GELU epilogue: Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7) on rcp.approx / ex2.approx -- about half the
 // instructions of erff; the epilogue, not the tensor pipe, limits the small-K GEMMs that use it.
@@ -134,22 +153,24 @@ __device__ __forceinline__ int16_t to_i16(float y, int mode) {
   return (int16_t)(int)fminf(fmaxf(y * 32767.0f, -32768.0f), 32767.0f);
 }
 
-template <int BN>
+template <int BN, bool BF = false>
 struct Smem {
-  static constexpr uint32_t W_TILE_BYTES = BN * BK * 4;
-  static constexpr uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * W_TILE_BYTES;
-  static constexpr int STAGES = (BN <= 128) ? 3 : 2;
+  static constexpr uint32_t W_TILE_BYTES = BN * BK * 4;           // BN rows of 128 bytes (32 tf32 or 64 bf16)
+  static constexpr int PLANES = BF ? 1 : 2;
+  static constexpr uint32_t STAGE_BYTES = PLANES * (A_TILE_BYTES + W_TILE_BYTES);
+  static constexpr int STAGES = BF ? 4 : ((BN <= 128) ? 3 : 2);
   static constexpr uint32_t EPI_STAGE_BYTES = 8 * 16 * 36 * 4;      // per-warp 16x36 transpose tiles of the epilogue
   static constexpr uint32_t TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool BF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
                const TcArgs g) {
-  using S = Smem<BN>;
+  using S = Smem<BN, BF>;
+  constexpr int BKE = BF ? 2 * BK : BK;          // K elements per 128-byte row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + S::STAGES * S::STAGE_BYTES);
@@ -163,7 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles_n = (g.N + BN - 1) / BN;
   const int n_tiles = g.m_tiles * n_tiles_n;
-  const int k_blocks = (g.K + BK - 1) / BK;
+  const int k_blocks = (g.K + BKE - 1) / BKE;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a_hi);
@@ -207,18 +228,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * S::STAGE_BYTES;
-          mbar_expect_tx(&full[stage], (uint32_t)(2 * g.bt * g.bb * BK * 4) + 2 * S::W_TILE_BYTES);
-          tma_load_3d(st, &map_a_hi, &full[stage], kb * BK, t0, b0);
-          tma_load_3d(st + A_TILE_BYTES, &map_a_lo, &full[stage], kb * BK, t0, b0);
+          mbar_expect_tx(&full[stage], (uint32_t)S::PLANES * ((uint32_t)(g.bt * g.bb * BK * 4) + S::W_TILE_BYTES));
           int wb = g.w_batched ? b0 : 0;            // per-batch weights (mask-estimator bands, attention operands)
-          int wk = kb * BK;
+          int wk = kb * BKE;
           if (g.w_group > 1) { wk += (b0 % g.w_group) * g.w_kstep; wb = b0 / g.w_group; }   // FLASH group of a window
-          if (g.k_split > 0 && kb * BK >= g.k_split) {        // second operand of a K-concatenated product
-            tma_load_3d(st + 2 * A_TILE_BYTES, &map_w2_hi, &full[stage], kb * BK - g.k_split, nt * BN, wb);
-            tma_load_3d(st + 2 * A_TILE_BYTES + S::W_TILE_BYTES, &map_w2_lo, &full[stage], kb * BK - g.k_split, nt * BN, wb);
+          const bool second = g.k_split > 0 && kb * BKE >= g.k_split;   // second operand of a K-concatenated product
+          if (second) wk = kb * BKE - g.k_split;
+          if (BF) {
+            tma_load_3d(st, &map_a_hi, &full[stage], kb * BKE, t0, b0);
+            tma_load_3d(st + A_TILE_BYTES, second ? &map_w2_hi : &map_w_hi, &full[stage], wk, nt * BN, wb);
           } else {
-            tma_load_3d(st + 2 * A_TILE_BYTES, &map_w_hi, &full[stage], wk, nt * BN, wb);
-            tma_load_3d(st + 2 * A_TILE_BYTES + S::W_TILE_BYTES, &map_w_lo, &full[stage], wk, nt * BN, wb);
+            tma_load_3d(st, &map_a_hi, &full[stage], kb * BKE, t0, b0);
+            tma_load_3d(st + A_TILE_BYTES, &map_a_lo, &full[stage], kb * BKE, t0, b0);
+            tma_load_3d(st + 2 * A_TILE_BYTES, second ? &map_w2_hi : &map_w_hi, &full[stage], wk, nt * BN, wb);
+            tma_load_3d(st + 2 * A_TILE_BYTES + S::W_TILE_BYTES, second ? &map_w2_lo : &map_w_lo, &full[stage], wk, nt * BN, wb);
           }
           if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -227,7 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+      constexpr uint32_t idesc = BF ? make_idesc_bf16(BM, BN) : make_idesc(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -241,15 +264,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
-          const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_TILE_BYTES);
-          const uint64_t w_hi = make_desc(sa + 2 * A_TILE_BYTES);
-          const uint64_t w_lo = make_desc(sa + 2 * A_TILE_BYTES + S::W_TILE_BYTES);
+          if (BF) {
+            const uint64_t a_d = make_desc(sa), w_d = make_desc(sa + A_TILE_BYTES);
 #pragma unroll
-          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-            const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);   // +32 B inside the swizzle row
-            umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, (kb | kk) ? 1u : 0u);
-            umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1u);
-            umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1u);
+            for (int kk = 0; kk < 4; ++kk) {       // 4 x 16 bf16 = one 128-byte row
+              const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+              umma_bf16(d_tmem, a_d + adv, w_d + adv, idesc, (kb | kk) ? 1u : 0u);
+            }
+          } else {
+            const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_TILE_BYTES);
+            const uint64_t w_hi = make_desc(sa + 2 * A_TILE_BYTES);
+            const uint64_t w_lo = make_desc(sa + 2 * A_TILE_BYTES + S::W_TILE_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+              const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);   // +32 B inside the swizzle row
+              umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, (kb | kk) ? 1u : 0u);
+              umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1u);
+              umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1u);
+            }
           }
           umma_commit(&empty[stage]);              // smem slot free once these MMAs retire
           if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
@@ -407,7 +439,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 x[0] += r4.x; x[1] += r4.y; x[2] += r4.z; x[3] += r4.w;
               }
               if (g.C) *reinterpret_cast<float4*>(g.C + o) = make_float4(x[0], x[1], x[2], x[3]);
-              if (g.Chi) {
+              if (g.Chi && !g.Clo) {                 // bf16 operand plane for a bf16 consumer
+                __nv_bfloat162 p01 = __floats2bfloat162_rn(x[0], x[1]), p23 = __floats2bfloat162_rn(x[2], x[3]);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&p01);
+                pk.y = *reinterpret_cast<uint32_t*>(&p23);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.Chi) + o) = pk;
+              } else if (g.Chi) {
                 float h[4], l[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -484,18 +522,19 @@ static EncodeTiledFn encode_fn() {
 }
 
 bool make_row_map(CUtensorMap* map, const float* base, int k_extent, int rows, long long row_stride, int batches,
-                  long long batch_stride, int box_rows, int box_batches, std::string& err) {
+                  long long batch_stride, int box_rows, int box_batches, std::string& err, bool bf16) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { err = "cuTensorMapEncodeTiled entry point not available"; return false; }
-  if ((row_stride * 4) % 16 || (batch_stride * 4) % 16 || ((uintptr_t)base) % 16) {
+  const int esz = bf16 ? 2 : 4;                  // bf16: `base` holds 2-byte elements, strides are in elements
+  if ((row_stride * esz) % 16 || (batch_stride * esz) % 16 || ((uintptr_t)base) % 16) {
     err = "TMA needs 16-byte aligned base and strides";
     return false;
   }
   cuuint64_t dims[3] = {(cuuint64_t)k_extent, (cuuint64_t)rows, (cuuint64_t)batches};
-  cuuint64_t strides[2] = {(cuuint64_t)row_stride * 4, (cuuint64_t)batch_stride * 4};
-  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, (cuuint32_t)box_batches};
+  cuuint64_t strides[2] = {(cuuint64_t)row_stride * esz, (cuuint64_t)batch_stride * esz};
+  cuuint32_t box[3] = {(cuuint32_t)(bf16 ? 2 * BK : BK), (cuuint32_t)box_rows, (cuuint32_t)box_batches};
   cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, es,
+  CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r); return false; }
@@ -503,25 +542,26 @@ bool make_row_map(CUtensorMap* map, const float* base, int k_extent, int rows, l
 }
 
 bool make_weight_map(CUtensorMap* map, const float* base, int k_pad, int n_pad, int box_n, std::string& err,
-                     int batches) {
+                     int batches, bool bf16) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { err = "cuTensorMapEncodeTiled entry point not available"; return false; }
+  const cuuint64_t esz = bf16 ? 2 : 4;
   cuuint64_t dims[3] = {(cuuint64_t)k_pad, (cuuint64_t)n_pad, (cuuint64_t)batches};
-  cuuint64_t strides[2] = {(cuuint64_t)k_pad * 4, (cuuint64_t)k_pad * 4 * (cuuint64_t)n_pad};
-  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_n, 1};
+  cuuint64_t strides[2] = {(cuuint64_t)k_pad * esz, (cuuint64_t)k_pad * esz * (cuuint64_t)n_pad};
+  cuuint32_t box[3] = {(cuuint32_t)(bf16 ? 2 * BK : BK), (cuuint32_t)box_n, 1};
   cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, es,
+  CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(W) failed: " + std::to_string((int)r); return false; }
   return true;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool BF>
 static cudaError_t launch_t(const TcPlan& p, const TcArgs& a, int sms, cudaStream_t st) {
-  using S = Smem<BN>;
+  using S = Smem<BN, BF>;
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, EPI>;
+  auto kern = gemm_tc_kernel<BN, EPI, BF>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
     if (e != cudaSuccess) return e;
@@ -535,14 +575,15 @@ static cudaError_t launch_t(const TcPlan& p, const TcArgs& a, int sms, cudaStrea
 
 template <int BN>
 static cudaError_t launch_bn(const TcPlan& p, const TcArgs& a, int epi, int sms, cudaStream_t st) {
-  if (epi == EPI_STORE) return launch_t<BN, EPI_STORE>(p, a, sms, st);
-  if (epi == EPI_ISTFT) return launch_t<BN, EPI_ISTFT>(p, a, sms, st);
-  if (epi == EPI_LIN) return launch_t<BN, EPI_LIN>(p, a, sms, st);
+  if (p.bf16) return epi == EPI_LIN ? launch_t<BN, EPI_LIN, true>(p, a, sms, st) : cudaErrorInvalidValue;
+  if (epi == EPI_STORE) return launch_t<BN, EPI_STORE, false>(p, a, sms, st);
+  if (epi == EPI_ISTFT) return launch_t<BN, EPI_ISTFT, false>(p, a, sms, st);
+  if (epi == EPI_LIN) return launch_t<BN, EPI_LIN, false>(p, a, sms, st);
   return cudaErrorInvalidValue;
 }
 
 cudaError_t launch(const TcPlan& p, const TcArgs& a, int epi, int sms, cudaStream_t st) {
-  if (p.bn == 176) return launch_bn<176>(p, a, epi, sms, st);
+  if (p.bn == 176) return p.bf16 ? cudaErrorInvalidValue : launch_bn<176>(p, a, epi, sms, st);
   if (p.bn == 256) return launch_bn<256>(p, a, epi, sms, st);
   if (p.bn == 128) return launch_bn<128>(p, a, epi, sms, st);
   return cudaErrorInvalidValue;

@@ -32,7 +32,7 @@ struct TcArgs {
   const float* bias;
   long long bias_bstride; // bias of chunk b starts at bias + b*bias_bstride (batched weights)
   const float* resid;
-  float* Chi;
+  float* Chi;            // with Clo == nullptr: ONE bf16 plane (2-byte elements at the same element offsets)
   float* Clo;
   long long ldc;
   int act;               // ACT_*
@@ -47,14 +47,15 @@ struct TcPlan {
   CUtensorMap map_a_hi, map_a_lo, map_w_hi, map_w_lo;
   CUtensorMap map_w2_hi, map_w2_lo;   // only read when args.k_split > 0
   int bn = 0;            // N tile: 128 | 176 | 256
+  bool bf16 = false;     // operands are single bf16 planes (maps built with bf16 = true); EPI_LIN only, bn 128 | 256
 };
 
 // A planes: element (b, t, k) at base[b*batch_stride + t*row_stride + k]; rows may overlap.
 bool make_row_map(CUtensorMap* map, const float* base, int k_extent, int rows, long long row_stride, int batches,
-                  long long batch_stride, int box_rows, int box_batches, std::string& err);
+                  long long batch_stride, int box_rows, int box_batches, std::string& err, bool bf16 = false);
 // W planes: (n_pad, k_pad) row-major, zero padded.
 bool make_weight_map(CUtensorMap* map, const float* base, int k_pad, int n_pad, int box_n, std::string& err,
-                     int batches = 1);
+                     int batches = 1, bool bf16 = false);
 
 cudaError_t launch(const TcPlan& p, const TcArgs& a, int epi, int sms, cudaStream_t st);
 

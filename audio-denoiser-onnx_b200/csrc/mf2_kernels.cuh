@@ -9,6 +9,8 @@
 #include "gtcrn.cuh"
 #include "model_impl.h"
 
+#include <cuda_bf16.h>
+
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -17,7 +19,17 @@
 
 namespace mf2 {
 
-using gtcrn::split_tf32_store;
+// GEMM operand stores.  3xTF32 (default): value -> tf32 hi / lo planes.  bf16 matmul mode (lo == nullptr; only where
+// the workload spec licenses bf16 matmuls): ONE bf16 plane living in the hi buffer at the same element offsets.
+__device__ __forceinline__ void split_tf32_store(float v, float* hi, float* lo, long long i) {
+  if (lo == nullptr) {
+    reinterpret_cast<__nv_bfloat16*>(hi)[i] = __float2bfloat16_rn(v);
+    return;
+  }
+  const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  hi[i] = h;
+  lo[i] = v - h;
+}
 
 constexpr int D = 512, VU = 1024, VU2 = 2048, QK = 128, PROJ = 2176, FI = 256;
 constexpr int DW = 17, DWH = 8, MEMK = 39, MEMH = 19;
@@ -31,6 +43,14 @@ constexpr float EPS_OUT = 1e-5f * 32.0f;                 // eps / 1024^-0.5  (:1
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void split4(float4 v, float* hi, float* lo, long long i) {
+  if (lo == nullptr) {                        // bf16 plane: 4 values = 8 bytes
+    __nv_bfloat162 p01 = __floats2bfloat162_rn(v.x, v.y), p23 = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&p01);
+    pk.y = *reinterpret_cast<uint32_t*>(&p23);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(hi) + i) = pk;
+    return;
+  }
   float4 h, l;
   h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
   h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
@@ -382,6 +402,7 @@ static int choose_bn(int N) {
 struct Lin {
   int N = 0, K = 0, n_pad = 0, k_pad = 0, bn = 0, batches = 1;
   float* planes = nullptr;       // owned (weights) or null (activation operand)
+  bool bf16 = false;             // one bf16 plane instead of tf32 hi / lo (w_lo unused)
   CUtensorMap w_hi, w_lo;
 };
 struct Gemm {
@@ -417,20 +438,24 @@ struct Base : public ModelImpl {
   }
 
   // weights (N, K) fp32 on the device -> zero-padded tf32 planes; n_valid_pad: N rounded to 4 for the epilogue
-  bool make_lin(Lin& l, const float* src, int N, int K) {
-    l.N = N; l.K = K; l.batches = 1;
+  bool make_lin(Lin& l, const float* src, int N, int K, bool bf16 = false) {
+    l.N = N; l.K = K; l.batches = 1; l.bf16 = bf16;
     l.bn = choose_bn(N);
+    if (bf16 && l.bn == 176) l.bn = 128;
     l.n_pad = round_up(N, l.bn);
-    l.k_pad = round_up(K, 32);
+    l.k_pad = round_up(K, bf16 ? 64 : 32);
     const long long plane = (long long)l.n_pad * l.k_pad;
     if (cudaMalloc((void**)&l.planes, 2 * plane * sizeof(float)) != cudaSuccess) { err = "out of memory (weights)"; return false; }
-    pad_split_kernel<<<(unsigned)((plane + 255) / 256), 256>>>(src, l.planes, l.planes + plane, N, K, l.k_pad, plane);
+    pad_split_kernel<<<(unsigned)((plane + 255) / 256), 256>>>(src, l.planes, bf16 ? nullptr : l.planes + plane, N, K, l.k_pad, plane);
+    if (bf16) return tc::make_weight_map(&l.w_hi, l.planes, l.k_pad, l.n_pad, l.bn, err, 1, true);
     return tc::make_weight_map(&l.w_hi, l.planes, l.k_pad, l.n_pad, l.bn, err, 1) &&
            tc::make_weight_map(&l.w_lo, l.planes + plane, l.k_pad, l.n_pad, l.bn, err, 1);
   }
-  // activation planes used as the per-window W operand
+  // activation planes used as the per-window W operand (lo == nullptr: one bf16 plane in `hi`)
   bool make_act_lin(Lin& l, float* hi, float* lo, int N, int n_pad, int K, int k_pad, int bn, int batches) {
     l.N = N; l.K = K; l.n_pad = n_pad; l.k_pad = k_pad; l.bn = bn; l.batches = batches; l.planes = nullptr;
+    l.bf16 = lo == nullptr;
+    if (l.bf16) return tc::make_weight_map(&l.w_hi, hi, k_pad, n_pad, bn, err, batches, true);
     return tc::make_weight_map(&l.w_hi, hi, k_pad, n_pad, bn, err, batches) &&
            tc::make_weight_map(&l.w_lo, lo, k_pad, n_pad, bn, err, batches);
   }
@@ -443,14 +468,19 @@ struct Base : public ModelImpl {
     return true;
   }
 
+  // A operand: tf32 hi plane at a_planes, lo plane a_plane_stride floats later; bf16 weights (l.bf16): ONE bf16 plane at
+  // a_planes (2-byte elements, same element strides)
   bool plan_gemm(Gemm& g, const float* a_planes, long long a_plane_stride, int K, int rows, long long row_stride,
                  int batches, long long batch_stride, const Lin& l) {
     const int bt = rows >= 128 ? 128 : rows;
     g.plan.bn = l.bn;
+    g.plan.bf16 = l.bf16;
     g.plan.map_w_hi = l.w_hi;
     g.plan.map_w_lo = l.w_lo;
-    if (!tc::make_row_map(&g.plan.map_a_hi, a_planes, K, rows, row_stride, batches, batch_stride, bt, 1, err) ||
-        !tc::make_row_map(&g.plan.map_a_lo, a_planes + a_plane_stride, K, rows, row_stride, batches, batch_stride, bt, 1, err))
+    if (l.bf16) {
+      if (!tc::make_row_map(&g.plan.map_a_hi, a_planes, K, rows, row_stride, batches, batch_stride, bt, 1, err, true)) return false;
+    } else if (!tc::make_row_map(&g.plan.map_a_hi, a_planes, K, rows, row_stride, batches, batch_stride, bt, 1, err) ||
+               !tc::make_row_map(&g.plan.map_a_lo, a_planes + a_plane_stride, K, rows, row_stride, batches, batch_stride, bt, 1, err))
       return false;
     tc::TcArgs& a = g.args;
     a = tc::TcArgs{};

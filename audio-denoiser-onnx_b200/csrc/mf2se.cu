@@ -210,6 +210,8 @@ class Model : public Base {
   struct LayerG { Gemm in, out, c1, uv, ul, up, c2; };
   std::vector<LayerG> lg;
   int stop_after = 0, last_batch = 0;
+  bool bf = false;               // metadata matmul_dtype == BF16: the 24 layers' GEMMs run on bf16 operands (BASELINE configs[2])
+  float* LO(float* p) const { return bf ? nullptr : p; }      // lo plane of an operand, absent in bf16 mode
 
   ~Model() override {
     cudaSetDevice(device);
@@ -241,6 +243,13 @@ class Model : public Base {
     if (nfft != NFFT || hop != HOP || nmels != NM || L < NFFT || (L - NFFT) % HOP) {
       err = "mossformer2_se needs nfft=1920, hop=384, n_mels=60 and input_audio_length = 1920 + k*384";
       return false;
+    }
+    {
+      auto it = meta.find("matmul_dtype");
+      if (it != meta.end() && !it->second.empty() && it->second != "F32") {
+        if (it->second != "BF16") { err = "matmul_dtype must be F32 (3xTF32, default) or BF16"; return false; }
+        bf = true;
+      }
     }
     auto pdt = [&](const std::string& s, int& o) { if (s == "F32") o = ADN_F32; else if (s == "INT16") o = ADN_I16; else if (s == "F16") o = ADN_F16; else return false; return true; };
     if (!pdt(sin, in_dtype) || !pdt(sout, out_dtype)) { err = "bad audio dtype"; return false; }
@@ -286,13 +295,13 @@ class Model : public Base {
     for (int i = 0; i < layers && ok; ++i) {
       const std::string p = "L" + std::to_string(i) + ".";
       Layer& Y = lw[i];
-      w = dptr(p + "in_w", (size_t)PROJ * D, ok);  if (ok && !make_lin(Y.in, w, PROJ, D)) return false;
-      w = dptr(p + "out_w", (size_t)D * VU, ok);   if (ok && !make_lin(Y.out, w, D, VU)) return false;
-      w = dptr(p + "c1_w", (size_t)FI * D, ok);    if (ok && !make_lin(Y.c1, w, FI, D)) return false;
-      w = dptr(p + "uv_w", (size_t)2 * FI * FI, ok); if (ok && !make_lin(Y.uv, w, 2 * FI, FI)) return false;
-      w = dptr(p + "ul_w", (size_t)FI * FI, ok);   if (ok && !make_lin(Y.ul, w, FI, FI)) return false;
-      w = dptr(p + "up_w", (size_t)FI * FI, ok);   if (ok && !make_lin(Y.up, w, FI, FI)) return false;
-      w = dptr(p + "c2_w", (size_t)D * FI, ok);    if (ok && !make_lin(Y.c2, w, D, FI)) return false;
+      w = dptr(p + "in_w", (size_t)PROJ * D, ok);  if (ok && !make_lin(Y.in, w, PROJ, D, bf)) return false;
+      w = dptr(p + "out_w", (size_t)D * VU, ok);   if (ok && !make_lin(Y.out, w, D, VU, bf)) return false;
+      w = dptr(p + "c1_w", (size_t)FI * D, ok);    if (ok && !make_lin(Y.c1, w, FI, D, bf)) return false;
+      w = dptr(p + "uv_w", (size_t)2 * FI * FI, ok); if (ok && !make_lin(Y.uv, w, 2 * FI, FI, bf)) return false;
+      w = dptr(p + "ul_w", (size_t)FI * FI, ok);   if (ok && !make_lin(Y.ul, w, FI, FI, bf)) return false;
+      w = dptr(p + "up_w", (size_t)FI * FI, ok);   if (ok && !make_lin(Y.up, w, FI, FI, bf)) return false;
+      w = dptr(p + "c2_w", (size_t)D * FI, ok);    if (ok && !make_lin(Y.c2, w, D, FI, bf)) return false;
       Y.in_b = dptr(p + "in_b", PROJ, ok); Y.in_c = dptr(p + "in_c", (size_t)DW * PROJ, ok);
       Y.gamma = dptr(p + "qk_gamma", 4 * QK, ok); Y.beta = dptr(p + "qk_beta", 4 * QK, ok);
       Y.out_b = dptr(p + "out_b", D, ok); Y.out_c = dptr(p + "out_c", (size_t)DW * D, ok);
@@ -368,14 +377,14 @@ class Model : public Base {
 
     // attention operands that live in activations
     const int bn_qk = Tn;                    // 128 or 256 keys per tile
-    if (!make_act_lin(a_qk, qk, qk + (size_t)B * Tn * QK, T4, Tn, QK, QK, bn_qk, B) ||
-        !make_act_lin(a_lk, lk, lk + (size_t)B * Tn * QK, T4, Tn, QK, QK, bn_qk, B) ||
-        !make_act_lin(a_vuT, vuT, vuT + (size_t)B * VU2 * Tp, VU2, VU2, Tp, Tp, 256, B))
+    if (!make_act_lin(a_qk, qk, LO(qk + (size_t)B * Tn * QK), T4, Tn, QK, QK, bn_qk, B) ||
+        !make_act_lin(a_lk, lk, LO(lk + (size_t)B * Tn * QK), T4, Tn, QK, QK, bn_qk, B) ||
+        !make_act_lin(a_vuT, vuT, LO(vuT + (size_t)B * VU2 * Tp), VU2, VU2, Tp, Tp, 256, B))
       return false;
     if (!plan_gemm(g_lk, lq, M * QK, QK, T, QK, B, (long long)T * QK, a_lk)) return false;
     g_lk.args.C = s1; g_lk.args.ldc = Tp;
     if (!plan_gemm(g_qk, qq, M * QK, QK, T, QK, B, (long long)T * QK, a_qk)) return false;
-    g_qk.args.act = tc::ACT_RELU2; g_qk.args.resid = s1; g_qk.args.Chi = ppl; g_qk.args.Clo = ppl + M * Tp; g_qk.args.ldc = Tp;
+    g_qk.args.act = tc::ACT_RELU2; g_qk.args.resid = s1; g_qk.args.Chi = ppl; g_qk.args.Clo = LO(ppl + M * Tp); g_qk.args.ldc = Tp;
     if (!plan_gemm(g_pv, ppl, M * Tp, Tp, T, Tp, B, (long long)T * Tp, a_vuT)) return false;
     g_pv.args.C = att; g_pv.args.ldc = VU2;
 
@@ -392,7 +401,7 @@ class Model : public Base {
       if (!plan_gemm(G.uv, xn, M * FI, FI, (int)M, FI, 1, M * FI, Y.uv)) return false;
       G.uv.args.bias = Y.uv_b; G.uv.args.act = tc::ACT_SILU; G.uv.args.C = uvp; G.uv.args.ldc = 2 * FI;
       if (!plan_gemm(G.ul, xupl, M * FI, FI, (int)M, FI, 1, M * FI, Y.ul)) return false;
-      G.ul.args.bias = Y.ul_b; G.ul.args.act = tc::ACT_RELU; G.ul.args.Chi = f1; G.ul.args.Clo = f1 + M * FI; G.ul.args.ldc = FI;
+      G.ul.args.bias = Y.ul_b; G.ul.args.act = tc::ACT_RELU; G.ul.args.Chi = f1; G.ul.args.Clo = LO(f1 + M * FI); G.ul.args.ldc = FI;
       if (!plan_gemm(G.up, f1, M * FI, FI, (int)M, FI, 1, M * FI, Y.up)) return false;
       G.up.args.C = xp2; G.up.args.ldc = FI;
       if (!plan_gemm(G.c2, yn, M * FI, FI, (int)M, FI, 1, M * FI, Y.c2)) return false;
@@ -466,30 +475,30 @@ class Model : public Base {
       LayerG& G = lg[i];
       const Layer& Y = lw[i];
       const float* hin = i == 0 ? z : h;
-      shiftnorm_kernel<<<wtok, 256, 0, st>>>(hin, xs, xs + M * D, rs, M, T, 0);
+      shiftnorm_kernel<<<wtok, 256, 0, st>>>(hin, xs, LO(xs + M * D), rs, M, T, 0);
       MF_TICK("shiftnorm");
       MF_GEMM(G.in, EPI_LIN, "fl_in");
       dwconv_in_kernel<<<dim3(PROJ / 32 / DWI_WARPS, B, (T + DW_SEG - 1) / DW_SEG), DWI_WARPS * 32, 0, st>>>(
-          proj, Y.in_c, Y.gamma, Y.beta, rcos, rsin, vu, vuT, vuT + (size_t)B * VU2 * Tp, qq, qq + M * QK, lq, lq + M * QK,
-          qk, qk + (size_t)B * Tn * QK, lk, lk + (size_t)B * Tn * QK, nullptr, nullptr, T, Tp, Tn, T, QK);
+          proj, Y.in_c, Y.gamma, Y.beta, rcos, rsin, vu, vuT, LO(vuT + (size_t)B * VU2 * Tp), qq, LO(qq + M * QK), lq, LO(lq + M * QK),
+          qk, LO(qk + (size_t)B * Tn * QK), lk, LO(lk + (size_t)B * Tn * QK), nullptr, nullptr, T, Tp, Tn, T, QK);
       MF_TICK("dwconv_in");
       MF_GEMM(g_lk, EPI_LIN, "att_lk");
       MF_GEMM(g_qk, EPI_LIN, "att_qk");
       MF_GEMM(g_pv, EPI_LIN, "att_pv");
-      gate_kernel<<<wtok, 256, 0, st>>>(att, vu, gated, gated + M * VU, rs2, M, T, T, 0);
+      gate_kernel<<<wtok, 256, 0, st>>>(att, vu, gated, LO(gated + M * VU), rs2, M, T, T, 0);
       MF_TICK("gate");
       MF_GEMM(G.out, EPI_LIN, "fl_out");
-      dwconv_kernel<<<dim3(D / 32 / DWI_WARPS, B, (T + DW_SEG - 1) / DW_SEG), DWI_WARPS * 32, 0, st>>>(y, Y.out_c, hin, h, hpl, hpl + M * D, D, T, D);
+      dwconv_kernel<<<dim3(D / 32 / DWI_WARPS, B, (T + DW_SEG - 1) / DW_SEG), DWI_WARPS * 32, 0, st>>>(y, Y.out_c, hin, h, hpl, LO(hpl + M * D), D, T, D);
       MF_TICK("dwconv_out");
       MF_GEMM(G.c1, EPI_LIN, "fsmn_conv1");
-      ln2_kernel<<<wtok, 256, 0, st>>>(c1y, Y.n1_w, Y.n1_b, gin, xn, xn + M * FI, M);
+      ln2_kernel<<<wtok, 256, 0, st>>>(c1y, Y.n1_w, Y.n1_b, gin, xn, LO(xn + M * FI), M);
       MF_TICK("ln2");
       MF_GEMM(G.uv, EPI_LIN, "fsmn_uv");
-      dwconv_kernel<<<dim3(2 * FI / 32 / DWI_WARPS, B, (T + DW_SEG - 1) / DW_SEG), DWI_WARPS * 32, 0, st>>>(uvp, Y.uv_c, nullptr, uv, xupl, xupl + M * FI, FI, T, 2 * FI);
+      dwconv_kernel<<<dim3(2 * FI / 32 / DWI_WARPS, B, (T + DW_SEG - 1) / DW_SEG), DWI_WARPS * 32, 0, st>>>(uvp, Y.uv_c, nullptr, uv, xupl, LO(xupl + M * FI), FI, T, 2 * FI);
       MF_TICK("dwconv_uv");
       MF_GEMM(G.ul, EPI_LIN, "fsmn_linear");
       MF_GEMM(G.up, EPI_LIN, "fsmn_project");
-      fsmn_mem_kernel<<<dim3((T + FM_TOK - 1) / FM_TOK, B), 256, (2 * FM_TOK + 2 * MEMH) * FI * sizeof(float), st>>>(xp2, uv, gin, Y.mem_c, Y.n2_w, Y.n2_b, yn, yn + M * FI, T);
+      fsmn_mem_kernel<<<dim3((T + FM_TOK - 1) / FM_TOK, B), 256, (2 * FM_TOK + 2 * MEMH) * FI * sizeof(float), st>>>(xp2, uv, gin, Y.mem_c, Y.n2_w, Y.n2_b, yn, LO(yn + M * FI), T);
       MF_TICK("fsmn_mem");
       MF_GEMM(G.c2, EPI_LIN, "fsmn_conv2");
     }

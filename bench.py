@@ -202,6 +202,7 @@ class Mf2seWorkload:
     """MossFormer2-SE-48K (BASELINE.json configs[2]): 24 FLASH+FSMN layers, 1 s windows at 48 kHz
     (48000 samples, 121 frames), mono."""
     name = "mf2se"
+    matmul = "F32"
     default_batch = 256
     chunk, sr, channels, t_frames, layers = 48000, 48000, 1, 121, 24
     cpu_chunks, ref_chunks = 32, 8
@@ -210,8 +211,9 @@ class Mf2seWorkload:
                    "fsmn_linear", "fsmn_project", "fsmn_conv2", "tail_gate_gemm", "mask_gemm", "istft_gemm")
 
     def describe(self, B):
+        mm = "3xTF32 matmuls (fp32-class)" if self.matmul == "F32" else "bf16 matmuls (fp32 accumulate; frontend / norms / gates / ISTFT fp32)"
         return (f"MossFormer2-SE-48K, {self.layers} layers, {B} x 1 s windows (48000 samples, 121 frames) per GPU per "
-                f"step, F32 in / F32 out")
+                f"step, F32 in / F32 out, {mm}")
 
     def audio_seconds(self, B):
         return B * self.chunk / self.sr
@@ -222,11 +224,12 @@ class Mf2seWorkload:
 
     def build(self, sd, device):
         from adn import export, mf2se_params
-        return export.mf2se_model(sd, mf2se_params.Mf2Hyper(layers=self.layers), self.chunk, "F32", "F32", device_id=device)
+        return export.mf2se_model(sd, mf2se_params.Mf2Hyper(layers=self.layers), self.chunk, "F32", "F32", device_id=device,
+                                  matmul_dtype=self.matmul)
 
     def export(self, sd, path):
         from adn import export, mf2se_params
-        export.export_mf2se(sd, path, mf2se_params.Mf2Hyper(layers=self.layers), self.chunk, "F32", "F32")
+        export.export_mf2se(sd, path, mf2se_params.Mf2Hyper(layers=self.layers), self.chunk, "F32", "F32", self.matmul)
 
     def inputs(self, B, n_sets, seed):
         sets = []
@@ -484,12 +487,19 @@ def main():
     ap.add_argument("--model", default="gtcrn", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="chunks per GPU per step (default: per model)")
     ap.add_argument("--impl", default="adn", choices=["adn", "reference"])
+    ap.add_argument("--matmul", default="f32", choices=["f32", "bf16"],
+                    help="mf2se only: bf16 = the layers' GEMMs on bf16 operands (BASELINE.json configs[2] 'bf16 matmuls'); "
+                         "default f32 = 3xTF32, the 1e-4 parity path")
     ap.add_argument("--ref-chunks", type=int, default=0, help="CPU chunks per step for --impl reference")
     ap.add_argument("--cpu-baseline-chunks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     wl = WORKLOADS[args.model]()
+    if args.matmul == "bf16":
+        if args.model != "mf2se":
+            raise SystemExit("--matmul bf16 is only licensed for MossFormer2-SE-48K (BASELINE.json configs[2])")
+        wl.matmul = "BF16"
     if args.steps <= 0:
         args.steps = 100 if args.model == "gtcrn" else (5 if args.model == "mf2ss" else 10)
     if args.impl == "reference":
@@ -578,6 +588,9 @@ def main():
     lb, lf = wb * B, wf * B
     t_hbm = lb / (pk["hbm_gbs"] * 1e9)
     tc3 = top in getattr(wl, "tc3_kernels", ())           # 3xTF32 tcgen05 GEMM: 3 tf32 MMAs per MAC, tf32 = bf16 rate / 2
+    bf_layers = ("fl_in", "att_lk", "att_qk", "att_pv", "fl_out", "fsmn_conv1", "fsmn_uv", "fsmn_linear", "fsmn_project", "fsmn_conv2")
+    if getattr(wl, "matmul", "F32") == "BF16" and top in bf_layers:
+        tc3 = False                                       # bf16 operands: one MMA per MAC at the bf16 rate
     t_tc = lf * (6.0 if tc3 else 1.0) / (pk["bf16_tflops_sustained"] * 1e12)
     if t_hbm >= t_tc:
         roof = {"bound": "hbm", "achieved": lb / (launch_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s"}
@@ -646,7 +659,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "bf16" if getattr(wl, "matmul", "F32") == "BF16" else "f32", "data": "synthetic",
             "config": {"workload": wl.describe(B), "model": wl.name, "batch_per_gpu": B, "chunk_samples": wl.chunk,
                        "l2_policy": f"{n_sets} distinct input batches rotated ({n_sets * in_bytes / 2**20:.0f} MiB) "
                                     f"+ {ws_mib:.0f} MiB workspace streamed per step, both > 126 MB L2",
