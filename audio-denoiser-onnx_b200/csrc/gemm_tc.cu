@@ -27,7 +27,9 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 32;                 // 32 fp32 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 8;              // tf32: 32 bytes of K per instruction
-constexpr int NTHREADS = 320;           // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int NEPI = 16;                // epilogue warps: four per TMEM lane quarter (the epilogue, not the tensor pipe, limits
+                                        // small-K and bf16 GEMMs: 8 warps could not issue fast enough)
+constexpr int NTHREADS = 64 + 32 * NEPI; // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 constexpr uint32_t A_TILE_BYTES = BM * BK * 4;   // 16 KiB
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -159,7 +161,7 @@ struct Smem {
   static constexpr int PLANES = BF ? 1 : 2;
   static constexpr uint32_t STAGE_BYTES = PLANES * (A_TILE_BYTES + W_TILE_BYTES);
   static constexpr int STAGES = BF ? 4 : ((BN <= 128) ? 3 : 2);
-  static constexpr uint32_t EPI_STAGE_BYTES = 8 * 16 * 36 * 4;      // per-warp 16x36 transpose tiles of the epilogue
+  static constexpr uint32_t EPI_STAGE_BYTES = NEPI * 8 * 36 * 4;    // per-warp 8x36 transpose tiles of the epilogue
   static constexpr uint32_t TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 };
 
@@ -200,7 +202,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 8);
+      mbar_init(&tempty[i], NEPI);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -290,9 +292,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..17) =====================
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
-    const int chalf = (warp - 2) >> 2;             // the two warps of a quarter take alternate 32-column chunks
+    const int cidx = (warp - 2) >> 2;              // the four warps of a quarter take every fourth 32-column chunk
     const int r = q * 32 + lane;                   // row of the tile
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -309,7 +311,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       tc_fence_after();
       const uint32_t taddr = tmem_base + ab * 256 + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c0 = chalf * 32; c0 < BN; c0 += 64) {
+      for (int c0 = cidx * 32; c0 < BN; c0 += 32 * (NEPI / 4)) {
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait();
@@ -318,25 +320,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           // Linear layer: v = act(acc * rowscale[m] + bias[n]) (+ residual) -> fp32 and/or tf32 planes.
           // The TMEM load gives lane = row; a per-warp smem transpose turns that into lane = column
           // quad so every global access is a full 128-byte row segment (8 lanes x 16 B, 4 rows/instr).
-          float* stg = stage + (warp - 2) * (16 * 36);
+          float* stg = stage + (warp - 2) * (8 * 36);
           const int cq = lane & 7;
           const bool col_ok = (c0 + 4 * cq < BN) && (n0 + 4 * cq < g.N);      // N, BN, ldc multiples of 4
           float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
           bool have_bias = false;
           // residual / row-scale operands of this 32x32 chunk are fetched up front (8 independent loads
           // in flight) instead of one dependent DRAM round trip per 4-row step
-          float4 res4[2][4];
-          float rsc[2][4];
+          float4 res4[4][2];
+          float rsc[4][2];
 #pragma unroll
-          for (int hrow = 0; hrow < 2; ++hrow)
+          for (int hrow = 0; hrow < 4; ++hrow)
 #pragma unroll
-            for (int it = 0; it < 4; ++it) { res4[hrow][it] = make_float4(0.f, 0.f, 0.f, 0.f); rsc[hrow][it] = 1.0f; }
+            for (int it = 0; it < 2; ++it) { res4[hrow][it] = make_float4(0.f, 0.f, 0.f, 0.f); rsc[hrow][it] = 1.0f; }
           if (EPI == EPI_LIN && (g.resid || g.rowscale)) {
 #pragma unroll
-            for (int hrow = 0; hrow < 2; ++hrow)
+            for (int hrow = 0; hrow < 4; ++hrow)
 #pragma unroll
-              for (int it = 0; it < 4; ++it) {
-                const int r2 = q * 32 + hrow * 16 + it * 4 + (lane >> 3);
+              for (int it = 0; it < 2; ++it) {
+                const int r2 = q * 32 + hrow * 8 + it * 4 + (lane >> 3);
                 int b2, t2;
                 if (g.bb > 1) { int bi = r2 / g.bt; b2 = mt * g.bb + bi; t2 = r2 - bi * g.bt; if (bi >= g.bb) b2 = g.B; }
                 else { b2 = tile_b; t2 = tile_t + r2; }
@@ -348,19 +350,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               }
           }
 #pragma unroll
-          for (int hrow = 0; hrow < 2; ++hrow) {             // 16 rows at a time through a 16x36 tile
-            if ((lane >> 4) == hrow) {
+          for (int hrow = 0; hrow < 4; ++hrow) {             // 8 rows at a time through an 8x36 tile
+            if ((lane >> 3) == hrow) {
 #pragma unroll
               for (int j0 = 0; j0 < 8; ++j0)
-                *reinterpret_cast<float4*>(stg + (lane & 15) * 36 + 4 * j0) =
+                *reinterpret_cast<float4*>(stg + (lane & 7) * 36 + 4 * j0) =
                     make_float4(__uint_as_float(v[4 * j0]), __uint_as_float(v[4 * j0 + 1]),
                                 __uint_as_float(v[4 * j0 + 2]), __uint_as_float(v[4 * j0 + 3]));
             }
             __syncwarp();
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
+            for (int it = 0; it < 2; ++it) {
               const int rl = it * 4 + (lane >> 3);
-              const int r2 = q * 32 + hrow * 16 + rl;
+              const int r2 = q * 32 + hrow * 8 + rl;
               int b2, t2;
               if (g.bb > 1) { int bi = r2 / g.bt; b2 = mt * g.bb + bi; t2 = r2 - bi * g.bt; if (bi >= g.bb) b2 = g.B; }
               else { b2 = tile_b; t2 = tile_t + r2; }
