@@ -57,6 +57,11 @@ bool make_row_map(CUtensorMap* map, const float* base, int k_extent, int rows, l
 bool make_weight_map(CUtensorMap* map, const float* base, int k_pad, int n_pad, int box_n, std::string& err,
                      int batches = 1, bool bf16 = false);
 
+// Plain (un-swizzled) 3-D tile map over fp32 rows: element (b, r, c) at base[b*batch_stride + r*row_stride + c]; boxes of
+// box_rows x box_cols; out-of-range rows / columns (negative start coordinates included) read as zeros.
+bool make_tile_map(CUtensorMap* map, const float* base, int cols, int rows, long long row_stride, int batches,
+                   long long batch_stride, int box_cols, int box_rows, std::string& err);
+
 cudaError_t launch(const TcPlan& p, const TcArgs& a, int epi, int sms, cudaStream_t st);
 
 void split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t st);

@@ -8,6 +8,7 @@
 #include "gemm_tc.cuh"
 #include "gtcrn.cuh"
 #include "model_impl.h"
+#include "tma_utils.cuh"
 
 #include <cuda_bf16.h>
 
@@ -199,6 +200,127 @@ dwconv_in_kernel(const float* __restrict__ proj, const float* __restrict__ taps,
                     }
                     __syncwarp();
                   });
+  }
+}
+
+// TMA-fed, double-buffered form of dwconv_in_kernel.  CTA = 128 channels x up to DP_TILES consecutive 64-frame tiles
+// of one window.  Each (64 + 16) x 128 input tile arrives as ONE bulk tensor copy (512-byte row segments; rows before
+// the window start or past its end are zero-filled by the TMA unit, which is the conv's zero padding) into one of two
+// shared-memory buffers, so tile i+1 is in flight while tile i is processed.  Every thread owns one channel and 32
+// frames (48-value register window, 17 FMAs per output); the transposed operands ([v|u]^T, lin_k^T) leave through a
+// 128 x 65 tile that aliases the buffer just consumed, as 128-byte row segments.  Same arguments and arithmetic order
+// as the streamed kernel; `map` is a tile map over proj: dims (2176, T, windows), box (128, 80, 1).
+constexpr int DP_F = 64, DP_C = 128, DP_ROWS = DP_F + 2 * DWH, DP_TILES = 4;
+constexpr size_t DP_SMEM = 2 * DP_ROWS * DP_C * sizeof(float) + 64;
+static __global__ void __launch_bounds__(256, 2)
+dwconv_in_tma_kernel(const __grid_constant__ CUtensorMap map, const float* __restrict__ taps, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, const float* __restrict__ rcos, const float* __restrict__ rsin,
+                     float* __restrict__ vu, float* __restrict__ vuT_hi, float* __restrict__ vuT_lo,
+                     float* __restrict__ qq_hi, float* __restrict__ qq_lo, float* __restrict__ lq_hi,
+                     float* __restrict__ lq_lo, float* __restrict__ qk_hi, float* __restrict__ qk_lo,
+                     float* __restrict__ lk_hi, float* __restrict__ lk_lo, float* __restrict__ lkT_hi,
+                     float* __restrict__ lkT_lo, int T, int Tp, int Tn, int Tq, int lq_ld) {
+  extern __shared__ __align__(128) float dsm[];
+  float* buf[2] = {dsm, dsm + DP_ROWS * DP_C};
+  uint64_t* full = reinterpret_cast<uint64_t*>(dsm + 2 * DP_ROWS * DP_C);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c0 = blockIdx.x * DP_C, b = blockIdx.y, seg = blockIdx.z * (DP_TILES * DP_F);
+  const int ntiles = min(DP_TILES, (T - seg + DP_F - 1) / DP_F);
+  if (tid == 0) {
+    tc::mbar_init(&full[0], 1);
+    tc::mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 0; i < 2 && i < ntiles; ++i) {
+      tc::mbar_expect_tx(&full[i], DP_ROWS * DP_C * 4);
+      tc::tma_load_3d(buf[i], &map, &full[i], c0, seg + i * DP_F - DWH, b);
+    }
+  }
+  const int ch = tid & (DP_C - 1), f0 = (tid >> 7) * (DP_F / 2), c = c0 + ch;
+  float w[DW];
+#pragma unroll
+  for (int k = 0; k < DW; ++k) w[k] = __ldg(taps + k * PROJ + c);
+  float g4[4], b4[4];
+  if (c0 >= VU2) {
+#pragma unroll
+    for (int hd = 0; hd < 4; ++hd) { g4[hd] = __ldg(gamma + hd * QK + ch); b4[hd] = __ldg(beta + hd * QK + ch); }
+  }
+  for (int i = 0; i < ntiles; ++i) {
+    const int s = i & 1, t0 = seg + i * DP_F;
+    tc::mbar_wait(&full[s], (i >> 1) & 1);
+    float x[DP_F / 2 + 2 * DWH];
+#pragma unroll
+    for (int k = 0; k < DP_F / 2 + 2 * DWH; ++k) x[k] = buf[s][(f0 + k) * DP_C + ch];
+    __syncthreads();                             // every column of buffer s is in registers: it can be reused
+    float y[DP_F / 2];
+#pragma unroll
+    for (int j = 0; j < DP_F / 2; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < DW; ++k) acc += w[k] * x[j + k];
+      y[j] = acc + x[j + DWH];
+    }
+    float* tt = buf[s];                          // [DP_C][DP_F + 1]
+    if (c0 < VU2) {
+#pragma unroll
+      for (int j = 0; j < DP_F / 2; ++j) {
+        const int t = t0 + f0 + j;
+        if (t < T) vu[((long long)b * T + t) * VU2 + c] = y[j];
+        tt[ch * (DP_F + 1) + f0 + j] = y[j];
+      }
+      __syncthreads();
+      for (int cc = warp * (DP_C / 8); cc < (warp + 1) * (DP_C / 8); ++cc) {
+#pragma unroll
+        for (int h = 0; h < DP_F / 32; ++h) {
+          const int f = lane + 32 * h, t = t0 + f;
+          if (t < T) split_tf32_store(tt[cc * (DP_F + 1) + f], vuT_hi, vuT_lo, ((long long)b * VU2 + c0 + cc) * Tp + t);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < DP_F / 2; ++j) {
+        const int t = t0 + f0 + j;
+        const int tc_ = t < T ? t : T - 1;       // (whole warps stay converged for the shuffles)
+        float sv[4];
+#pragma unroll
+        for (int hd = 0; hd < 4; ++hd) sv[hd] = y[j] * g4[hd] + b4[hd];
+        if (ch < ROT) {                          // rotary on the first 32 qk channels, interleaved pairs (warp-uniform)
+          const float cs = __ldg(rcos + tc_ * ROT + lane), sn = __ldg(rsin + tc_ * ROT + lane);
+#pragma unroll
+          for (int hd = 0; hd < 4; ++hd) {
+            const float other = __shfl_xor_sync(0xffffffffu, sv[hd], 1);
+            const float rot = (lane & 1) ? other : -other;
+            sv[hd] = sv[hd] * cs + rot * sn;
+          }
+        }
+        if (lkT_hi) tt[ch * (DP_F + 1) + f0 + j] = sv[3];
+        if (t < T) {
+          const long long m = (long long)b * Tq + t;
+          split_tf32_store(sv[0], qq_hi, qq_lo, m * QK + ch);
+          split_tf32_store(sv[1], lq_hi, lq_lo, m * lq_ld + ch);
+          split_tf32_store(sv[2], qk_hi, qk_lo, ((long long)b * Tn + t) * QK + ch);
+          if (!lkT_hi) split_tf32_store(sv[3], lk_hi, lk_lo, ((long long)b * Tn + t) * QK + ch);
+        }
+      }
+      __syncthreads();
+      if (lkT_hi) {                              // multi-group windows: lin_k^T (SS)
+        for (int cc = warp * (DP_C / 8); cc < (warp + 1) * (DP_C / 8); ++cc) {
+#pragma unroll
+          for (int h = 0; h < DP_F / 32; ++h) {
+            const int f = lane + 32 * h, t = t0 + f;
+            if (t < T) split_tf32_store(tt[cc * (DP_F + 1) + f], lkT_hi, lkT_lo, ((long long)b * QK + cc) * Tp + t);
+          }
+        }
+      }
+    }
+    __syncthreads();                             // transpose tile drained: buffer s may be overwritten
+    if (tid == 0 && i + 2 < ntiles) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc::mbar_expect_tx(&full[s], DP_ROWS * DP_C * 4);
+      tc::tma_load_3d(buf[s], &map, &full[s], c0, seg + (i + 2) * DP_F - DWH, b);
+    }
   }
 }
 

@@ -209,6 +209,7 @@ class Model : public Base {
   Gemm g_front, g_enc, g_lk, g_qk, g_pv, g_gate, g_dec, g_istft;
   struct LayerG { Gemm in, out, c1, uv, ul, up, c2; };
   std::vector<LayerG> lg;
+  CUtensorMap map_proj;          // tile map over `proj` for the TMA-fed dwconv_in
   int stop_after = 0, last_batch = 0;
   bool bf = false;               // metadata matmul_dtype == BF16: the 24 layers' GEMMs run on bf16 operands (BASELINE configs[2])
   float* LO(float* p) const { return bf ? nullptr : p; }      // lo plane of an operand, absent in bf16 mode
@@ -426,6 +427,7 @@ class Model : public Base {
           !tc::make_row_map(&g_istft.plan.map_a_lo, enh + enh_plane, ola.k_pad, rows, SPEC_LD, B, (long long)rows * SPEC_LD, bt, 1, err))
         return false;
     }
+    if (!tc::make_tile_map(&map_proj, proj, PROJ, T, PROJ, B, (long long)T * PROJ, DP_C, DP_ROWS, err)) return false;
     planned = B;
     return true;
   }
@@ -455,6 +457,7 @@ class Model : public Base {
     const unsigned wtok = (unsigned)((M + 7) / 8);
     static bool cfg = false;
     if (!cfg) {
+      cudaFuncSetAttribute(dwconv_in_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DP_SMEM);
       cudaFuncSetAttribute(featnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 2 * NM * 4);
       cudaFuncSetAttribute(fsmn_mem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * FM_TOK + 2 * MEMH) * FI * 4);
       cfg = true;
@@ -478,8 +481,8 @@ class Model : public Base {
       shiftnorm_kernel<<<wtok, 256, 0, st>>>(hin, xs, LO(xs + M * D), rs, M, T, 0);
       MF_TICK("shiftnorm");
       MF_GEMM(G.in, EPI_LIN, "fl_in");
-      dwconv_in_kernel<<<dim3(PROJ / 32 / DWI_WARPS, B, (T + DW_SEG - 1) / DW_SEG), DWI_WARPS * 32, 0, st>>>(
-          proj, Y.in_c, Y.gamma, Y.beta, rcos, rsin, vu, vuT, LO(vuT + (size_t)B * VU2 * Tp), qq, LO(qq + M * QK), lq, LO(lq + M * QK),
+      dwconv_in_tma_kernel<<<dim3(PROJ / DP_C, B, (T + DP_TILES * DP_F - 1) / (DP_TILES * DP_F)), 256, DP_SMEM, st>>>(
+          map_proj, Y.in_c, Y.gamma, Y.beta, rcos, rsin, vu, vuT, LO(vuT + (size_t)B * VU2 * Tp), qq, LO(qq + M * QK), lq, LO(lq + M * QK),
           qk, LO(qk + (size_t)B * Tn * QK), lk, LO(lk + (size_t)B * Tn * QK), nullptr, nullptr, T, Tp, Tn, T, QK);
       MF_TICK("dwconv_in");
       MF_GEMM(g_lk, EPI_LIN, "att_lk");

@@ -656,6 +656,8 @@ class SsModel : public Base {
       shiftnorm_kernel<<<wtok, 256, 0, st>>>(hin, xs, xs + M * D, rs, M, T, 1);
       SS_TICK("shiftnorm");
       SS_GEMM(Gm.in, "fl_in");
+      // (the TMA-fed tile form, dwconv_in_tma_kernel, wins for one-group windows -- MossFormer2-SE 7.96 -> 6.84 ms -- but
+      // loses here, 1.31 -> 1.51 ms: with Tg = 2048 every 256-byte piece of [v|u]^T lands in its own 8 KB-strided row)
       dwconv_in_kernel<<<dim3(PROJ / 32 / DWI_WARPS, B, (T + DW_SEG - 1) / DW_SEG), DWI_WARPS * 32, 0, st>>>(
           proj, Y.in_c, Y.gamma, Y.beta, rcos, rsin, vu, vuT, vuT + (size_t)B * VU2 * Tg, qq, qq + Mg * QK, spl + GROUP, spl + Mg * SQ + GROUP,
           qk, qk + Mg * QK, nullptr, nullptr, lkT, lkT + (size_t)B * QK * Tg, T, Tg, Tg, Tg, SQ);

@@ -13,7 +13,8 @@ from adn import export, mf2se_params
 layers, B, reps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 cfg = mo.Mf2Config(layers=layers)
 sd = mo.random_state_dict(cfg, 0)
-m = export.mf2se_model(sd, mf2se_params.Mf2Hyper(layers=layers), 48000)
+mm = "BF16" if len(sys.argv) > 4 and sys.argv[4] == "bf16" else "F32"
+m = export.mf2se_model(sd, mf2se_params.Mf2Hyper(layers=layers), 48000, matmul_dtype=mm)
 x = (torch.rand(B, 1, 48000) - 0.5).cuda()
 for _ in range(reps):
     y = m.run(x)
