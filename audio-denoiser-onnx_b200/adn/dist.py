@@ -62,6 +62,43 @@ def run_sharded(run_fn, audio: torch.Tensor | None, n: int, shape_tail: tuple, d
     if local.shape[0] > 0:
         out = run_fn(local.contiguous())
     else:
-        probe = run_fn(torch.zeros((1, *shape_tail), dtype=dtype, device=device))
-        out = probe[:0]
+        out = run_fn(torch.zeros((1, *shape_tail), dtype=dtype, device=device))
+        out = tuple(o[:0] for o in out) if isinstance(out, (tuple, list)) else out[:0]
+    if isinstance(out, (tuple, list)):                    # several outputs (MossFormer2-SS: one per speaker)
+        parts = [gather_batch(o, n, group=group) for o in out]
+        return None if parts[0] is None else tuple(parts)
     return gather_batch(out, n, group=group)
+
+
+def run_mixed_stream(run_fns: dict, requests: list | None, specs: dict, device, group=None):
+    """Mixed-model stream (BASELINE.json configs[4]: MossFormerGAN-SE + MossFormer2-SS chunks interleaved in one
+    stream).  Every rank holds every model's weights (they all fit on one GPU), so routing is: group the
+    requests by model tag, shard EACH model's batch over all ranks (scatter -> run -> gather, no other collective),
+    and put the results back in request order.
+
+    run_fns:  tag -> callable (b, C, L) -> tensor or tuple of tensors (Model.run on the GPU box)
+    requests: on rank 0 a list of (tag, tensor (C, L)); None elsewhere
+    specs:    tag -> ((C, L), dtype) of that model's input, known on every rank
+    Returns on rank 0 a list, one entry per request (tensor (C', L') or tuple of them); None elsewhere."""
+    rank = dist.get_rank(group)
+    tags = sorted(run_fns)
+    counts = torch.zeros(len(tags), dtype=torch.int64, device=device)      # (NCCL moves device tensors only)
+    if rank == 0:
+        for t, _ in requests:
+            counts[tags.index(t)] += 1
+    dist.broadcast(counts, src=0, group=group)
+    results = [None] * (len(requests) if rank == 0 else 0)
+    for ti, tag in enumerate(tags):
+        n = int(counts[ti])
+        if n == 0:
+            continue
+        shape_tail, dtype = specs[tag]
+        batch, where = None, []
+        if rank == 0:
+            where = [i for i, (t, _) in enumerate(requests) if t == tag]
+            batch = torch.stack([requests[i][1] for i in where], dim=0)
+        out = run_sharded(run_fns[tag], batch, n, tuple(shape_tail), dtype, device, group=group)
+        if rank == 0:
+            for j, i in enumerate(where):
+                results[i] = tuple(o[j] for o in out) if isinstance(out, tuple) else out[j]
+    return results if rank == 0 else None
