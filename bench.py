@@ -203,6 +203,11 @@ class Mf2seWorkload:
     (48000 samples, 121 frames), mono."""
     name = "mf2se"
     matmul = "F32"
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch at B = 256, 3xTF32 mode (ncu --set full,
+    # profiles/r1j_mf2se_b256_ncu_raw.csv; the 126 MB L2 keeps part of each producer's output on chip)
+    ncu_traffic = (256, {"fl_in": 357846096, "dwconv_in": 1156369104, "fl_out": 315620360, "att_pv": 788668592,
+                         "gate": 726862880, "dwconv_out": 264326960, "frontend_gemm": 2207932864},
+                   "profiles/r1j_mf2se_b256_ncu_raw.csv")
     default_batch = 256
     chunk, sr, channels, t_frames, layers = 48000, 48000, 1, 121, 24
     cpu_chunks, ref_chunks = 32, 8
@@ -606,7 +611,7 @@ def main():
         roof["frac_of_tf32x3_ceiling"] = roof["achieved"] / roof["tf32x3_ceiling"]
     traffic = None
     nt = getattr(wl, "ncu_traffic", None)
-    if nt and nt[0] == B and top in nt[1]:
+    if nt and nt[0] == B and top in nt[1] and getattr(wl, "matmul", "F32") == "F32":
         traffic = nt[1][top]
         roof["traffic_source"] = nt[2]
     roof.update({"traffic": traffic, "kernel": top, "kernel_ms_per_launch": launch_ms, "launches_per_step": n_l,
