@@ -67,19 +67,25 @@ typedef struct {
 } adn_tensor_info;
 
 /* Replaces onnxruntime.InferenceSession(path, ...) (Inference_GTCRN_ONNX.py:213-214,237):
- * builds a model of desc["model_family"] on CUDA device `device_id` from a host blob of
- * `nfloats` fp32 values.  On failure *out is NULL and adn_last_error(NULL) has the reason. */
+ * builds a model of desc["model_family"] (gtcrn | mel_band_roformer | mossformer2_se | mossformer2_ss)
+ * on CUDA device `device_id` from a host blob of `nfloats` fp32 values.  The keys are the reference's
+ * metadata keys (audio_onnx_metadata.py:115-205) plus, for mossformer2_se, the optional
+ * "matmul_dtype" = F32 (default: 3xTF32 tensor-core GEMMs, fp32-class) | BF16 (the layers' GEMMs on bf16
+ * operands -- BASELINE.json configs[2] "bf16 matmuls").  On failure *out is NULL and adn_last_error(NULL) has the reason. */
 adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weights,
                       size_t nfloats, int device_id);
 
-/* Replaces session.get_inputs()/get_outputs()/_inputs_meta (…:262-267,276-277). */
+/* Replaces session.get_inputs()/get_outputs()/_inputs_meta (…:262-267,276-277).  `outs` must have
+ * room for 4 entries; *n_out receives how many the model has: 1 (`denoised_audio`) for every family except
+ * mossformer2_ss, which reports 2 (`separated_0`, `separated_1`;
+ * MossFormer2_SS_16K/Export_MossFormer2_SS_16K.py:689-690, Inference_MossFormer_SS_ONNX.py:312-317). */
 adn_status adn_io_info(const adn_model* m, adn_tensor_info* in, adn_tensor_info* outs,
                        int32_t* n_out);
 
 /* Replaces session.run_with_iobinding(binding) for a batch of `batch` independent
  * (1,C,L) chunks resident on the device (…:209-210, 314-317).  d_in is (batch,C,L)
- * contiguous in the input dtype, d_outs[i] is (batch,C,L_out).  Asynchronous on
- * `stream` (a cudaStream_t passed as void*). */
+ * contiguous in the input dtype, d_outs[i] (i < n_out of adn_io_info) is (batch,C,L_out).
+ * Asynchronous on `stream` (a cudaStream_t passed as void*). */
 adn_status adn_run(adn_model* m, const void* d_in, void* const* d_outs, int32_t batch,
                    void* stream);
 
