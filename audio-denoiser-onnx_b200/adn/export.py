@@ -68,22 +68,22 @@ def mf2se_model(state_dict: dict, hyper=None, input_audio_length: int = 48000, i
 
 
 def export_mf2ss(state_dict: dict, path, hyper=None, input_audio_length: int = 16000, in_dtype: str = "INT16",
-                 out_dtype: str = "INT16") -> dict[str, str]:
+                 out_dtype: str = "INT16", in_rate: int | None = None, out_rate: int | None = None) -> dict[str, str]:
     """MossFormer2-SS-16K `.adn` for one static window length (counterpart of
     MossFormer2_SS_16K/Export_MossFormer2_SS_16K.py:672-709).  `state_dict` keys: see adn/mf2ss_params.py."""
     from . import mf2ss_params
 
     hyper = hyper or mf2ss_params.SsHyper()
-    md = mf2ss_params.metadata(hyper, input_audio_length, in_dtype, out_dtype)
-    modelfile.save(path, md, mf2ss_params.pack(state_dict, hyper, input_audio_length))
+    md = mf2ss_params.metadata(hyper, input_audio_length, in_dtype, out_dtype, in_rate, out_rate)
+    modelfile.save(path, md, mf2ss_params.pack(state_dict, hyper, input_audio_length, in_rate))
     return md
 
 
 def mf2ss_model(state_dict: dict, hyper=None, input_audio_length: int = 16000, in_dtype: str = "F32",
-                out_dtype: str = "F32", device_id: int = 0):
+                out_dtype: str = "F32", device_id: int = 0, in_rate: int | None = None, out_rate: int | None = None):
     from . import mf2ss_params
     from .model import Model
 
     hyper = hyper or mf2ss_params.SsHyper()
-    md = mf2ss_params.metadata(hyper, input_audio_length, in_dtype, out_dtype)
-    return Model.from_tensors(md, mf2ss_params.pack(state_dict, hyper, input_audio_length), device_id)
+    md = mf2ss_params.metadata(hyper, input_audio_length, in_dtype, out_dtype, in_rate, out_rate)
+    return Model.from_tensors(md, mf2ss_params.pack(state_dict, hyper, input_audio_length, in_rate), device_id)

@@ -55,7 +55,15 @@ def _f(t) -> np.ndarray:
     return np.ascontiguousarray(t.detach().cpu().numpy().astype(np.float32, copy=False))
 
 
-def pack(sd: dict, h: SsHyper, input_audio_length: int) -> dict[str, np.ndarray]:
+def model_length(h: SsHyper, input_audio_length: int, in_rate: int | None = None) -> int:
+    """MODEL_AUDIO_LENGTH (Export_MossFormer2_SS_16K.py:36): the window length at the 16 kHz model rate."""
+    in_rate = in_rate or h.sample_rate
+    return int(round(input_audio_length * h.sample_rate / in_rate))
+
+
+def pack(sd: dict, h: SsHyper, input_audio_length: int, in_rate: int | None = None) -> dict[str, np.ndarray]:
+    """input_audio_length is at `in_rate` (default: the model rate); tables are sized for the model-rate window."""
+    input_audio_length = model_length(h, input_audio_length, in_rate)
     if input_audio_length < h.enc_kernel:
         raise ValueError("input_audio_length must cover one encoder kernel (16 samples)")
     if h.mem_depth != 2:
@@ -149,18 +157,22 @@ def pack(sd: dict, h: SsHyper, input_audio_length: int) -> dict[str, np.ndarray]
     return blob
 
 
-def metadata(h: SsHyper, input_audio_length: int, in_dtype: str = "INT16", out_dtype: str = "INT16") -> dict[str, str]:
+def metadata(h: SsHyper, input_audio_length: int, in_dtype: str = "INT16", out_dtype: str = "INT16",
+             in_rate: int | None = None, out_rate: int | None = None) -> dict[str, str]:
     """Metadata keys of `Export_MossFormer2_SS_16K.py:703-708` (no STFT keys: learned encoder / decoder)
-    + the layer count the reference reads off the live upstream module."""
-    out_len = h.out_len(input_audio_length)
+    + the layer count the reference reads off the live upstream module.  in_rate / out_rate != 16000: the model
+    resamples linearly either side (`:564-579`, `:633-648`); input_audio_length is at in_rate."""
+    in_rate, out_rate = in_rate or h.sample_rate, out_rate or h.sample_rate
+    mlen = model_length(h, input_audio_length, in_rate)
+    out_len = h.out_len(mlen) if out_rate == h.sample_rate else int(round(input_audio_length * out_rate / in_rate))
     md = {
         "audio_metadata_version": 1, "producer": "adn.mf2ss_params", "model_name": "MossFormer2_SS_16K",
         "task": "source_separation", "model_family": FAMILY, "dynamic_axes": "0", "opset": 20,
         "input_audio_dtype": in_dtype, "output_audio_dtype": out_dtype,
-        "in_sample_rate": h.sample_rate, "out_sample_rate": h.sample_rate, "model_sample_rate": h.sample_rate,
+        "in_sample_rate": in_rate, "out_sample_rate": out_rate, "model_sample_rate": h.sample_rate,
         "input_audio_length": input_audio_length, "export_audio_length": input_audio_length,
-        "model_audio_length": input_audio_length, "output_audio_length": out_len,
-        "input_to_output_scale": 1.0, "batch_window_seconds": 1.5, "use_batch_fold": "0",
+        "model_audio_length": mlen, "output_audio_length": out_len,
+        "input_to_output_scale": float(out_rate / in_rate), "batch_window_seconds": 1.5, "use_batch_fold": "0",
         "batch_fold_inference_default": "0", "fold_window_length": 24000, "fold_input_length": 24000,
         "max_dynamic_audio_seconds": 6, "normalize_audio_default": "0", "normalize_target_rms": 4096.0,
         "feature_kind": "conv_encoder_decoder", "center_pad": "0", "input_channels": 1, "output_channels": 1,

@@ -617,6 +617,11 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
                   : is_ss ? mf2ss_create(m->meta, m->index, weights, m->d_blob, device_id, m->sms, m->err)
                           : mbr_create(m->meta, m->index, weights, m->d_blob, device_id, m->sms, m->err);
     if (!m->impl) s = ADN_ERR_INVALID;
+    else {                                          // host staging follows the family's own I/O description
+      adn_tensor_info tin, touts[4];
+      m->impl->io_info(&tin, touts);
+      m->L = tin.length; m->chans = tin.channels; m->Lout = touts[0].length; m->n_out = m->impl->n_outputs();
+    }
   }
   if (s != ADN_OK) return fail(s);
   if (cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) != cudaSuccess) {

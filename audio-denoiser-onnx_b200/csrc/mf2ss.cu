@@ -368,6 +368,27 @@ dec_kernel(const float* __restrict__ xenc, const float* __restrict__ mask, const
 
 // One CTA per (window, speaker): overlap-add of the frame products (+ bias), RMS of the separated waveform,
 // gain = rms_in / rms_out (0 for a silent output, :631), output conversion (:649-657).
+__device__ __forceinline__ void ss_store(void* out, long long i, float v, int out_dtype) {
+  if (out_dtype == ADN_I16) {
+    const int q = max(-32768, min(32767, (int)fminf(fmaxf(v, -2147483648.f), 2147483520.f)));
+    reinterpret_cast<int16_t*>(out)[i] = (int16_t)q;
+  } else if (out_dtype == ADN_F32) {
+    reinterpret_cast<float*>(out)[i] = v * (1.0f / 32768.0f);
+  } else {
+    reinterpret_cast<__half*>(out)[i] = __float2half_rn(v * (1.0f / 32768.0f));
+  }
+}
+
+// Output conversion behind the output resampler (:649-657): rows = (window, speaker) of the resampled, gain-restored signal.
+static __global__ void __launch_bounds__(256)
+ss_convert_kernel(const float* __restrict__ src, void* __restrict__ out0, void* __restrict__ out1, int out_dtype, int len) {
+  const int b = blockIdx.y / SPK, s = blockIdx.y % SPK;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= len) return;
+  ss_store(s == 0 ? out0 : out1, (long long)b * len + i, src[(long long)blockIdx.y * len + i], out_dtype);
+}
+
+// out_dtype < 0: keep the gain-restored fp32 signal in `wav` (int16 scale) for the output resampler instead of converting.
 static __global__ void __launch_bounds__(512)
 ola_out_kernel(const float* __restrict__ fo, const float* __restrict__ dbias, const float* __restrict__ rms_in,
                float* __restrict__ wav, void* __restrict__ out0, void* __restrict__ out1, int out_dtype, int n, int Lout) {
@@ -393,14 +414,8 @@ ola_out_kernel(const float* __restrict__ fo, const float* __restrict__ dbias, co
   const long long ob = (long long)b * Lout;
   for (int i = tid; i < Lout; i += 512) {
     const float v = wv[i] * g;
-    if (out_dtype == ADN_I16) {
-      const int q = max(-32768, min(32767, (int)fminf(fmaxf(v, -2147483648.f), 2147483520.f)));
-      reinterpret_cast<int16_t*>(out)[ob + i] = (int16_t)q;
-    } else if (out_dtype == ADN_F32) {
-      reinterpret_cast<float*>(out)[ob + i] = v * (1.0f / 32768.0f);
-    } else {
-      reinterpret_cast<__half*>(out)[ob + i] = __float2half_rn(v * (1.0f / 32768.0f));
-    }
+    if (out_dtype < 0) wv[i] = v;
+    else ss_store(out, ob + i, v, out_dtype);
   }
 }
 
@@ -408,6 +423,9 @@ class SsModel : public Base {
  public:
   int in_dtype = ADN_F32, out_dtype = ADN_F32;
   int L = 0, Lout = 0, T = 0, G = 1, Tg = 256, layers = 24;
+  int L_in = 0, L_final = 0;      // window length at the input rate / output length at the output rate (== L, Lout at 16 kHz)
+  bool rs_in = false, rs_out = false;
+  float *xr = nullptr, *wres = nullptr;
   int enc_tiles = 0, mem_tiles = 0;
 
   const float *enc_w = nullptr, *enc_b = nullptr, *dec_w = nullptr, *dec_b = nullptr, *front_b = nullptr, *emb = nullptr;
@@ -461,14 +479,26 @@ class SsModel : public Base {
     if (!geti("input_audio_length", L) || !geti("enc_stride", stride) || !geti("output_sources", sources) ||
         !geti("mf2_layers", layers) || !gets("input_audio_dtype", sin) || !gets("output_audio_dtype", sout))
       return false;
+    // optional linear resampling either side of the model (:564-579, :633-648): input_audio_length is at in_sample_rate
+    int in_sr = 16000, out_sr = 16000, model_sr = 16000;
+    {
+      auto opt = [&](const char* k, int& v) { auto it = meta.find(k); if (it != meta.end() && !it->second.empty()) v = atoi(it->second.c_str()); };
+      opt("in_sample_rate", in_sr); opt("out_sample_rate", out_sr); opt("model_sample_rate", model_sr);
+    }
+    if (model_sr != 16000 || in_sr <= 0 || out_sr <= 0) { err = "mossformer2_ss runs at model_sample_rate 16000"; return false; }
+    L_in = L;
+    rs_in = in_sr != model_sr;
+    rs_out = out_sr != model_sr;
+    if (rs_in) L = (int)llround((double)L_in * model_sr / in_sr);          // MODEL_AUDIO_LENGTH (:36)
     if (stride != ENC_S || sources != SPK || L < ENC_K) {
-      err = "mossformer2_ss needs enc_stride=8, output_sources=2 and input_audio_length >= 16";
+      err = "mossformer2_ss needs enc_stride=8, output_sources=2 and a window of at least 16 model-rate samples";
       return false;
     }
     auto pdt = [&](const std::string& s, int& o) { if (s == "F32") o = ADN_F32; else if (s == "INT16") o = ADN_I16; else if (s == "F16") o = ADN_F16; else return false; return true; };
     if (!pdt(sin, in_dtype) || !pdt(sout, out_dtype)) { err = "bad audio dtype"; return false; }
     T = (L - ENC_K) / ENC_S + 1;
     Lout = (T - 1) * ENC_S + ENC_K;
+    L_final = rs_out ? (int)llround((double)L_in * out_sr / in_sr) : Lout;   // OUTPUT_AUDIO_LENGTH (:37)
     G = (T + GROUP - 1) / GROUP;
     Tg = G * GROUP;
     enc_tiles = (T + ENC_TT - 1) / ENC_TT;
@@ -520,7 +550,7 @@ class SsModel : public Base {
 
   size_t floats_needed(size_t B) const {
     const size_t M = B * T, Mg = B * Tg;
-    return B * L + B + 3 * M * D + 2 * M * D + M + M * PROJ + M * VU2 + 2 * B * VU2 * Tg + 4 * Mg * QK + 2 * B * QK * Tg +
+    return B * L + B + (rs_in ? B * L : 0) + (rs_out ? B * SPK * L_final : 0) + 3 * M * D + 2 * M * D + M + M * PROJ + M * VU2 + 2 * B * VU2 * Tg + 4 * Mg * QK + 2 * B * QK * Tg +
            2 * Mg * SQ + 2 * B * VU2 * QK + Mg * VU2 + 2 * M * VU + M + M * D + 2 * M * D + 2 * M * FI + 2 * M * FI +
            2 * M * 2 * FI + 4 * M * FI + 3 * M * FI + 2 * B * mem_tiles * FI * 2 + 2 * B * FI * 2 + 2 * M * FI + M * D +
            2 * M * D + M * SPK * 2 * D + 2 * M * SPK * D + M * SPK * D + M * SPK * ENC_K + B * SPK * Lout + B * enc_tiles * 4;
@@ -532,6 +562,7 @@ class SsModel : public Base {
     free_ws();
     const size_t M = (size_t)B * T, Mg = (size_t)B * Tg;
     float* ep = nullptr;
+    if ((rs_in && !alloc(xr, (size_t)B * L, false)) || (rs_out && !alloc(wres, (size_t)B * SPK * L_final, false))) return false;
     if (!alloc(xn, (size_t)B * L, false) || !alloc(rms_in, B, false) || !alloc(xenc, M * D, false) || !alloc(z, M * D, false) ||
         !alloc(h, M * D, false) || !alloc(xs, 2 * M * D, false) || !alloc(rs, M, false) || !alloc(proj, M * PROJ, false) ||
         !alloc(vu, M * VU2, false) || !alloc(vuT, 2 * (size_t)B * VU2 * Tg, true) || !alloc(qq, 2 * Mg * QK, true) ||
@@ -603,15 +634,15 @@ class SsModel : public Base {
   void io_info(adn_tensor_info* in, adn_tensor_info* out) override {
     memset(in, 0, sizeof(*in));
     strncpy(in->name, "mix_audio", sizeof(in->name) - 1);              // Export_MossFormer2_SS_16K.py:689
-    in->dtype = in_dtype; in->channels = 1; in->length = L;
+    in->dtype = in_dtype; in->channels = 1; in->length = L_in;
     for (int s = 0; s < SPK; ++s) {
       memset(out + s, 0, sizeof(*out));
       snprintf(out[s].name, sizeof(out[s].name), "separated_%d", s);   // :690
-      out[s].dtype = out_dtype; out[s].channels = 1; out[s].length = Lout;
+      out[s].dtype = out_dtype; out[s].channels = 1; out[s].length = L_final;
     }
   }
   size_t workspace_bytes(int batch) override { return floats_needed((size_t)batch) * sizeof(float); }
-  int launches(int) override { return 4 + layers * 21 + 6; }
+  int launches(int) override { return 4 + layers * 21 + 6 + (rs_in ? 1 : 0) + (rs_out ? 2 : 0); }
   void set_stop_after(int n) override { stop_after = n; }
 
 #define SS_TICK(name) do { ++n; if (tick) tick(tick_ctx, name); if (stop_after > 0 && n >= stop_after) return ADN_OK; } while (0)
@@ -638,7 +669,15 @@ class SsModel : public Base {
       cfg = true;
     }
 
-    if (adn_two_stage_rms(d_in, in_dtype, 0.05623413251903491f, 1e-6f, xn, rms_in, B, L, st) != ADN_OK) {
+    const void* src = d_in;
+    int src_dtype = in_dtype;
+    if (rs_in) {                                   // F.interpolate(size=MODEL_AUDIO_LENGTH, mode='linear') (:564-579)
+      if (adn_resample_linear(d_in, in_dtype, xr, B, L_in, L, 0.0, st) != ADN_OK) { err = "input resampler launch failed"; return ADN_ERR_CUDA; }
+      SS_TICK("resample_in");
+      src = xr;
+      src_dtype = ADN_F32;
+    }
+    if (adn_two_stage_rms(src, src_dtype, 0.05623413251903491f, 1e-6f, xn, rms_in, B, L, st) != ADN_OK) {
       err = "two-stage RMS launch failed";
       return ADN_ERR_CUDA;
     }
@@ -702,8 +741,14 @@ class SsModel : public Base {
     SS_GEMM(g_mask, "mask_gemm");
     dec_kernel<<<(unsigned)((M + 8 * DEC_TOK - 1) / (8 * DEC_TOK)), 256, 0, st>>>(xenc, mask, dec_w, fo, M, T);
     SS_TICK("decoder");
-    ola_out_kernel<<<B * SPK, 512, 0, st>>>(fo, dec_b, rms_in, wav, d_outs[0], d_outs[1], out_dtype, T, Lout);
+    ola_out_kernel<<<B * SPK, 512, 0, st>>>(fo, dec_b, rms_in, wav, d_outs[0], d_outs[1], rs_out ? -1 : out_dtype, T, Lout);
     SS_TICK("ola_out");
+    if (rs_out) {                                  // F.interpolate(size=OUTPUT_AUDIO_LENGTH) on the gain-restored rows (:633-648)
+      if (adn_resample_linear(wav, ADN_F32, wres, B * SPK, Lout, L_final, 0.0, st) != ADN_OK) { err = "output resampler launch failed"; return ADN_ERR_CUDA; }
+      SS_TICK("resample_out");
+      ss_convert_kernel<<<dim3((L_final + 255) / 256, B * SPK), 256, 0, st>>>(wres, d_outs[0], d_outs[1], out_dtype, L_final);
+      SS_TICK("convert_out");
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("mf2ss run: ") + cudaGetErrorString(e); return ADN_ERR_CUDA; }
     return ADN_OK;

@@ -330,14 +330,25 @@ def fsmn_layer(P: dict, c: SsConfig, i: int, h: torch.Tensor, dbg=None) -> torch
     return F.linear(y, P[f"L{i}.c2_w"], P[f"L{i}.c2_b"]) + h
 
 
+def model_len(length: int, in_rate: int, c: SsConfig = SsConfig()) -> int:
+    """MODEL_AUDIO_LENGTH (:36): the window length at the model rate."""
+    return int(round(length * c.sample_rate / in_rate))
+
+
 def mf2ss_forward(sd: dict, audio: torch.Tensor, c: SsConfig = SsConfig(), in_dtype: str = "F32", out_dtype: str = "F32",
-                  dbg=None, folded: dict | None = None):
+                  dbg=None, folded: dict | None = None, in_rate: int | None = None, out_rate: int | None = None):
     """audio (B,1,L) int16-SCALE samples in `in_dtype` (:411 scales by 1/32768 whatever the dtype) ->
-    tuple of `num_spks` tensors (B,1,L_out); every window independent."""
-    B, _, L = audio.shape
+    tuple of `num_spks` tensors (B,1,L_out); every window independent.  in_rate / out_rate != 16 kHz: linear
+    resampling to MODEL_AUDIO_LENGTH in front (:564-579) and to OUTPUT_AUDIO_LENGTH behind the gain (:633-648)."""
+    B, _, L_in = audio.shape
+    in_rate, out_rate = in_rate or c.sample_rate, out_rate or c.sample_rate
+    x = audio.float()
+    if in_rate != c.sample_rate:
+        x = F.interpolate(x, size=model_len(L_in, in_rate, c), mode="linear", align_corners=False)
+    L = x.shape[-1]
     n = c.n_frames(L)
     P = folded if folded is not None else fold(sd, c, n)
-    x, rms_in = norm_audio(audio.float())
+    x, rms_in = norm_audio(x)
     x_enc = F.relu(F.conv1d(x, P["enc_w"].unsqueeze(1), P["enc_b"], stride=c.enc_stride))          # (B, dim, n)
     z = F.group_norm(x_enc, 1, None, None, 1e-8)
     z = (F.conv1d(z, P["front_w"].unsqueeze(-1), P["front_b"]).transpose(1, 2) + P["emb_pos"][None, :n]).contiguous()
@@ -362,6 +373,9 @@ def mf2ss_forward(sd: dict, audio: torch.Tensor, c: SsConfig = SsConfig(), in_dt
     rms_out = torch.sqrt((wav * wav).mean(dim=2, keepdim=True))
     gain = torch.where(rms_out > 0.0, rms_in / rms_out, torch.zeros_like(rms_out))
     out = wav * gain
+    if out_rate != c.sample_rate:
+        size = int(round(L_in * out_rate / in_rate))                                                  # OUTPUT_AUDIO_LENGTH (:37)
+        out = F.interpolate(out.reshape(1, B * c.num_spks, -1), size=size, mode="linear", align_corners=False).reshape(B, c.num_spks, -1)
     if dbg is not None:
         dbg["tail"], dbg["mask"], dbg["wav"] = t, mask, wav
     if "int" in out_dtype.lower():
@@ -373,9 +387,11 @@ def mf2ss_forward(sd: dict, audio: torch.Tensor, c: SsConfig = SsConfig(), in_dt
     return tuple(out[:, s:s + 1].contiguous() for s in range(c.num_spks))
 
 
-def mf2ss_forward_batch(sd, audio, c: SsConfig = SsConfig(), in_dtype="F32", out_dtype="F32", chunk: int = 2):
-    P = fold(sd, c, c.n_frames(audio.shape[-1]))
-    outs = [mf2ss_forward(sd, audio[s:s + chunk], c, in_dtype, out_dtype, folded=P) for s in range(0, audio.shape[0], chunk)]
+def mf2ss_forward_batch(sd, audio, c: SsConfig = SsConfig(), in_dtype="F32", out_dtype="F32", chunk: int = 2,
+                        in_rate: int | None = None, out_rate: int | None = None):
+    P = fold(sd, c, c.n_frames(model_len(audio.shape[-1], in_rate or c.sample_rate, c)))
+    outs = [mf2ss_forward(sd, audio[s:s + chunk], c, in_dtype, out_dtype, folded=P, in_rate=in_rate, out_rate=out_rate)
+            for s in range(0, audio.shape[0], chunk)]
     return tuple(torch.cat([o[s] for o in outs], dim=0) for s in range(c.num_spks))
 
 

@@ -205,7 +205,7 @@ def load_mf2se(input_audio_length: int, io_dtype: str = "F32"):
     return ns, build
 
 
-def load_mf2ss(input_audio_length: int, io_dtype: str = "F32"):
+def load_mf2ss(input_audio_length: int, io_dtype: str = "F32", in_rate: int = 16000, out_rate: int = 16000):
     """Reference MossFormer2-SS-16K wrapper (`MOSSFORMER_SS`) for one un-folded window.
 
     The wrapper's forward is made of leaf ops on packed buffers; only its constructor reads the
@@ -227,6 +227,8 @@ def load_mf2ss(input_audio_length: int, io_dtype: str = "F32"):
             "IN_AUDIO_DTYPE          = 'INT16'": f"IN_AUDIO_DTYPE          = '{io_dtype}'",
             "OUT_AUDIO_DTYPE         = 'INT16'": f"OUT_AUDIO_DTYPE         = '{io_dtype}'",
             "USE_BATCH_FOLD          = True": "USE_BATCH_FOLD          = False",
+            "IN_SAMPLE_RATE          = 16000": f"IN_SAMPLE_RATE          = {int(in_rate)}",
+            "OUT_SAMPLE_RATE         = 16000": f"OUT_SAMPLE_RATE         = {int(out_rate)}",
         },
     )
 

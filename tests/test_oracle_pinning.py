@@ -355,3 +355,26 @@ def test_mfgan_oracle_matches_reference_module():
         yo = go.mfgan_forward(sd, x, cfg)
     assert yr.shape == yo.shape == (1, 1, L)
     assert (yr - yo).abs().max() <= 5e-6 * max(1.0, float(yr.abs().max()))     # fp32 re-association only (max|y| 0.69)
+
+
+@needs_ref
+@pytest.mark.parametrize("L,in_rate,out_rate", [(2400, 8000, 48000), (7205, 48000, 8000), (3300, 22500, 16000)])
+def test_mf2ss_oracle_resampling_matches_reference_module(L, in_rate, out_rate):
+    """IN / OUT_SAMPLE_RATE != 16 kHz: the wrapper's linear resamplers either side of the model
+    (Export_MossFormer2_SS_16K.py:564-579, :633-648) -- executed reference vs the restatement."""
+    import mf2ss_oracle as so
+
+    cfg = so.SsConfig(layers=2)
+    sd = so.random_state_dict(cfg, 3)
+    hold = so.skeleton(cfg)
+    hold.load_state_dict(sd)
+    _, build = ref_loader.load_mf2ss(L, "F32", in_rate, out_rate)
+    w = build(hold)
+    x = synth_audio(L, 17) * 32767.0
+    with torch.inference_mode():
+        yr = w(x.clone())
+        yo = so.mf2ss_forward(sd, x, cfg, in_rate=in_rate, out_rate=out_rate)
+    want = int(round(L * out_rate / in_rate)) if out_rate != 16000 else cfg.out_len(so.model_len(L, in_rate, cfg))
+    for a, b in zip(yr, yo):
+        assert a.shape == b.shape == (1, 1, want)
+        assert (a - b).abs().max() <= 5e-6
