@@ -20,6 +20,16 @@ struct AdnError {
     }                                                                                \
   } while (0)
 
+// cudaFuncSetAttribute is per device: true the first time `mask` (one static per call site) sees the current device.
+inline bool adn_first_use_on_device(unsigned long long& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 __device__ __forceinline__ float adn_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float adn_prelu(float x, float a) { return x >= 0.f ? x : a * x; }
 

@@ -544,12 +544,11 @@ bool make_tile_map(CUtensorMap* map, const float* base, int cols, int rows, long
 template <int BN, int EPI, bool BF>
 static cudaError_t launch_t(const TcPlan& p, const TcArgs& a, int sms, cudaStream_t st) {
   using S = Smem<BN, BF>;
-  static bool configured = false;
+  static unsigned long long configured = 0;      // per device
   auto kern = gemm_tc_kernel<BN, EPI, BF>;
-  if (!configured) {
+  if (adn_first_use_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const int n_tiles = a.m_tiles * ((a.N + BN - 1) / BN);
   const int grid = n_tiles < sms ? n_tiles : sms;

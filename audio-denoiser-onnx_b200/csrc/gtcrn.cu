@@ -356,11 +356,9 @@ template <int KT>
 static void launch_gt_main_t(const GTW& w, const float* xin, float* h1, float* zt, int B, int T, int dil,
                              cudaStream_t st) {
   using C = GtCfg<KT>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;      // per device
+  if (adn_first_use_on_device(configured))
     cudaFuncSetAttribute(gt_main_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    configured = true;
-  }
   const int nkmax = (T + dil - 1) / dil;
   dim3 grid((nkmax + KT - 1) / KT, dil, B);
   gt_main_kernel<KT><<<grid, C::THREADS, C::SMEM, st>>>(w, xin, h1, zt, T, dil);

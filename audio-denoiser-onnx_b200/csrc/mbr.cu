@@ -738,11 +738,10 @@ class Model : public ModelImpl {
       {
         const int nseq = freq ? nb : T;
         const long long nq = freq ? Mf : (long long)nb * B;
-        static bool cfg = false;
-        if (!cfg) {
+        static unsigned long long cfg = 0;             // per device
+        if (adn_first_use_on_device(cfg)) {
           cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
           cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-          cfg = true;
         }
         const size_t smem2 = att2_smem_floats(nseq) * sizeof(float);
         if (smem2 <= 220 * 1024) {

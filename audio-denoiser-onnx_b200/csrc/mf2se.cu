@@ -455,12 +455,11 @@ class Model : public Base {
     int n = 0;
     const long long M = (long long)B * T;
     const unsigned wtok = (unsigned)((M + 7) / 8);
-    static bool cfg = false;
-    if (!cfg) {
+    static unsigned long long cfg = 0;             // per device
+    if (adn_first_use_on_device(cfg)) {
       cudaFuncSetAttribute(dwconv_in_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DP_SMEM);
       cudaFuncSetAttribute(featnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 2 * NM * 4);
       cudaFuncSetAttribute(fsmn_mem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * FM_TOK + 2 * MEMH) * FI * 4);
-      cfg = true;
     }
 
     // 1-3: cast (+1/32768 for int16, :315-317), fused Kaldi||STFT frontend (:335), log-mel (:337-341)

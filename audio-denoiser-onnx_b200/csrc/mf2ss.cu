@@ -662,11 +662,10 @@ class SsModel : public Base {
     int n = 0;
     const long long M = (long long)B * T, Mg = (long long)B * Tg;
     const unsigned wtok = (unsigned)((M + 7) / 8);
-    static bool cfg = false;
-    if (!cfg) {
+    static unsigned long long cfg = 0;             // per device
+    if (adn_first_use_on_device(cfg)) {
       cudaFuncSetAttribute(mem1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MEM1_ROWS * FI * 4);
       cudaFuncSetAttribute(mem2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MEM2_ROWS * 2 * MEM2_CH * 4);
-      cfg = true;
     }
 
     const void* src = d_in;
