@@ -114,8 +114,10 @@ featnorm_kernel(const float* __restrict__ mel, const float* __restrict__ gw, con
   for (int i = tid; i < T * D / 4; i += 256) st4(zb + 4 * i, __ldg(reinterpret_cast<const float4*>(emb) + i));
 }
 
-// CTA = (8 frames, window), thread = channel: memory conv (k = 39, zero padded) on the projected
-// branch, gate with xv, residual g_in, norm2 -> operand planes of conv2.
+// CTA = (8 frames, window), thread = channel: memory conv (k = 39, zero padded) on the projected branch, gate with xv,
+// residual g_in, norm2 -> operand planes of conv2.  Each thread keeps its own shared-memory column (no barrier before
+// the taps) and produces 4 outputs per pass so that 42 shared loads feed 156 FMAs (8 frames per CTA: with 121-frame
+// windows more, smaller CTAs beat a smaller halo: 32-frame tiles measured 2.1 -> 3.2 ms).
 constexpr int FM_TOK = 8;
 __global__ void __launch_bounds__(256)
 fsmn_mem_kernel(const float* __restrict__ xp, const float* __restrict__ uv, const float* __restrict__ gin,
@@ -134,37 +136,48 @@ fsmn_mem_kernel(const float* __restrict__ xp, const float* __restrict__ uv, cons
 #pragma unroll
   for (int i = 0; i < MEMK; ++i) k[i] = __ldg(taps + i * FI + c);
   // own column only: no barrier needed between the tile fill and the taps
+  for (int tt = 0; tt < FM_TOK; tt += 4) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-  for (int tt = 0; tt < FM_TOK; ++tt) {
-    const int t = t0 + tt;
-    float y = 0.f;
-    if (t < T) {
-      float conv = 0.f;
-#pragma unroll
-      for (int i = 0; i < MEMK; ++i) conv += k[i] * tile[tt + i][c];
-      const long long m = base + t;
-      const float xu = __ldg(uv + m * (2 * FI) + c) + (tile[tt + MEMH][c] + conv);
-      y = __ldg(uv + m * (2 * FI) + FI + c) * xu + __ldg(gin + m * FI + c);
+    for (int i = 0; i < MEMK + 3; ++i) {
+      const float v = tile[tt + i][c];
+      if (i < MEMK) a0 += k[i] * v;
+      if (i >= 1 && i < MEMK + 1) a1 += k[i - 1] * v;
+      if (i >= 2 && i < MEMK + 2) a2 += k[i - 2] * v;
+      if (i >= 3) a3 += k[i - 3] * v;
     }
-    ys[tt][c] = y;
+    const float conv[4] = {a0, a1, a2, a3};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t = t0 + tt + j;
+      float y = 0.f;
+      if (t < T) {
+        const long long m = base + t;
+        const float xu = __ldg(uv + m * (2 * FI) + c) + (tile[tt + j + MEMH][c] + conv[j]);
+        y = __ldg(uv + m * (2 * FI) + FI + c) * xu + __ldg(gin + m * FI + c);
+      }
+      ys[tt + j][c] = y;
+    }
   }
   __syncthreads();
   const int warp = c >> 5, lane = c & 31;
-  const int t = t0 + warp;
-  if (t >= T) return;
-  float v[8];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { v[i] = ys[warp][lane * 4 + i]; v[4 + i] = ys[warp][128 + lane * 4 + i]; }
-  float mean, rstd;
-  ln256(v, mean, rstd);
   const float4 w0 = ld4(w + lane * 4), w1 = ld4(w + 128 + lane * 4), b0 = ld4(bvec + lane * 4), b1 = ld4(bvec + 128 + lane * 4);
   const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
   const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  for (int tok = warp; tok < FM_TOK; tok += 8) {
+    const int t = t0 + tok;
+    if (t >= T) break;
+    float v[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * ww[i] + bb[i];
-  const long long m = base + t;
-  split4(make_float4(v[0], v[1], v[2], v[3]), yhi, ylo, m * FI + lane * 4);
-  split4(make_float4(v[4], v[5], v[6], v[7]), yhi, ylo, m * FI + 128 + lane * 4);
+    for (int i = 0; i < 4; ++i) { v[i] = ys[tok][lane * 4 + i]; v[4 + i] = ys[tok][128 + lane * 4 + i]; }
+    float mean, rstd;
+    ln256(v, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * ww[i] + bb[i];
+    const long long m = base + t;
+    split4(make_float4(v[0], v[1], v[2], v[3]), yhi, ylo, m * FI + lane * 4);
+    split4(make_float4(v[4], v[5], v[6], v[7]), yhi, ylo, m * FI + 128 + lane * 4);
+  }
 }
 
 // One CTA per frame: real mask on both STFT row blocks, written into the zero-framed ISTFT operand.
