@@ -279,3 +279,82 @@ def test_wavio_roundtrip_and_reference_examples(tmp_path):
     assert back.shape == (1, 4411) and sr == 16000
     with pytest.raises(ValueError):
         wavio.write_wav(tmp_path / "f.wav", mono.astype(np.float32), 16000)
+
+
+class _FakeSession:
+    """Stand-in with the slice of the ORT session surface `chunker` touches: a per-window function in place of the GPU."""
+
+    class _Arg:
+        def __init__(self, name, shape):
+            self.name, self.type, self.shape = name, "tensor(int16)", shape
+
+    class _Meta:
+        def __init__(self, md):
+            self.custom_metadata_map = md
+
+    class _Binding:
+        def __init__(self):
+            self.inputs, self.outputs = {}, {}
+
+        def bind_ortvalue_input(self, n, v):
+            self.inputs[n] = v
+
+        def bind_ortvalue_output(self, n, v):
+            self.outputs[n] = v
+
+    def __init__(self, in_len, out_len, fns, md):
+        self._in = [self._Arg("mix_audio", [1, 1, in_len])]
+        self._out = [self._Arg(f"separated_{i}", [1, 1, out_len]) for i in range(len(fns))]
+        self._fns, self._md, self.calls = fns, md, []
+
+    def get_inputs(self):
+        return self._in
+
+    def get_outputs(self):
+        return self._out
+
+    def get_modelmeta(self):
+        return self._Meta(self._md)
+
+    def io_binding(self):
+        return self._Binding()
+
+    def run_with_iobinding(self, b, run_options=None):
+        x = b.inputs["mix_audio"].numpy()
+        self.calls.append(x.shape[0])
+        for arg, fn in zip(self._out, self._fns):
+            np.copyto(b.outputs[arg.name].numpy(), fn(x)[..., :arg.shape[-1]])
+
+
+@pytest.mark.parametrize("n,win,out_len", [(10000, 4808, 4808), (3000, 4808, 4808), (9616, 4808, 4808), (7000, 2411, 2408)])
+def test_separate_is_the_reference_ss_loop(n, win, out_len):
+    """`chunker.separate` == the run section of Inference_MossFormer_SS_ONNX.py:269-340 transcribed as a batch-1 loop:
+    PAD_HEAD zeros in front, stride = window, zero tail (fold mode), every output concatenated and cut to
+    [pad_head : pad_head + len(audio)] -- but issued as ONE batched run."""
+    from adn import chunker
+
+    pad_head = 800
+    rng = np.random.default_rng(n)
+    audio = rng.integers(-20000, 20000, size=n, dtype=np.int16)
+    fns = [lambda x: (x // 2).astype(np.int16), lambda x: (-(x // 3) + np.arange(x.shape[-1], dtype=np.int16) % 7).astype(np.int16)]
+    sess = _FakeSession(win, out_len, fns, {"pad_head": str(pad_head)})
+    got = chunker.separate(sess, audio)
+    assert len(sess.calls) == 1                                  # one batched run, not a loop
+    # the reference's loop, one window at a time
+    a = np.concatenate([np.zeros(pad_head, np.int16), audio])
+    audio_len = len(a)
+    if audio_len > win:
+        num = int(np.ceil((audio_len - win) / win)) + 1
+        total = (num - 1) * win + win
+    else:
+        num, total = 1, win
+    a = np.concatenate([a, np.zeros(total - audio_len, np.int16)])
+    assert sess.calls[0] == num
+    for k, fn in enumerate(fns):
+        saved, s, e = [], 0, win
+        while e <= total:
+            saved.append(fn(a[s:e].reshape(1, 1, -1))[..., :out_len])
+            s += win
+            e = s + win
+        want = np.concatenate(saved, axis=-1).reshape(-1)[pad_head:audio_len]
+        assert got[k].dtype == np.int16 and np.array_equal(got[k], want)
