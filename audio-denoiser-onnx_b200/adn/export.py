@@ -46,25 +46,27 @@ def mbr_model(state_dict: dict, hyper=None, input_audio_length: int = 66150, in_
 
 
 def export_mf2se(state_dict: dict, path, hyper=None, input_audio_length: int = 48000, in_dtype: str = "INT16",
-                 out_dtype: str = "INT16", matmul_dtype: str = "F32") -> dict[str, str]:
+                 out_dtype: str = "INT16", matmul_dtype: str = "F32", in_rate: int | None = None,
+                 out_rate: int | None = None) -> dict[str, str]:
     """MossFormer2-SE-48K `.adn` for one static window length (counterpart of
     MossFormer2_SE_48K/Export_MossFormer_SE.py:519-563).  `state_dict` keys: see adn/mf2se_params.py."""
     from . import mf2se_params
 
     hyper = hyper or mf2se_params.Mf2Hyper()
-    md = mf2se_params.metadata(hyper, input_audio_length, in_dtype, out_dtype, matmul_dtype)
-    modelfile.save(path, md, mf2se_params.pack(state_dict, hyper, input_audio_length))
+    md = mf2se_params.metadata(hyper, input_audio_length, in_dtype, out_dtype, matmul_dtype, in_rate, out_rate)
+    modelfile.save(path, md, mf2se_params.pack(state_dict, hyper, input_audio_length, in_rate))
     return md
 
 
 def mf2se_model(state_dict: dict, hyper=None, input_audio_length: int = 48000, in_dtype: str = "F32",
-                out_dtype: str = "F32", device_id: int = 0, matmul_dtype: str = "F32"):
+                out_dtype: str = "F32", device_id: int = 0, matmul_dtype: str = "F32", in_rate: int | None = None,
+                out_rate: int | None = None):
     from . import mf2se_params
     from .model import Model
 
     hyper = hyper or mf2se_params.Mf2Hyper()
-    md = mf2se_params.metadata(hyper, input_audio_length, in_dtype, out_dtype, matmul_dtype)
-    return Model.from_tensors(md, mf2se_params.pack(state_dict, hyper, input_audio_length), device_id)
+    md = mf2se_params.metadata(hyper, input_audio_length, in_dtype, out_dtype, matmul_dtype, in_rate, out_rate)
+    return Model.from_tensors(md, mf2se_params.pack(state_dict, hyper, input_audio_length, in_rate), device_id)
 
 
 def export_mf2ss(state_dict: dict, path, hyper=None, input_audio_length: int = 16000, in_dtype: str = "INT16",

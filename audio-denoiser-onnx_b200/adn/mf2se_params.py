@@ -82,7 +82,15 @@ def mel_matrix(n_mels: int, P: int, fs: float, f_lo: float = 20.0) -> torch.Tens
     return torch.cat([tri, torch.zeros(n_mels, 1, dtype=torch.float64)], dim=1).float()
 
 
-def pack(sd: dict, h: Mf2Hyper, input_audio_length: int) -> dict[str, np.ndarray]:
+def model_length(h: Mf2Hyper, input_audio_length: int, in_rate: int | None = None) -> int:
+    """MODEL_AUDIO_LENGTH (Export_MossFormer_SE.py:48): the window length at the 48 kHz model rate."""
+    in_rate = in_rate or h.sample_rate
+    return int(round(input_audio_length * h.sample_rate / in_rate))
+
+
+def pack(sd: dict, h: Mf2Hyper, input_audio_length: int, in_rate: int | None = None) -> dict[str, np.ndarray]:
+    """input_audio_length is at `in_rate` (default: the model rate); tables are sized for the model-rate window."""
+    input_audio_length = model_length(h, input_audio_length, in_rate)
     geom = stft_tables.GEOMETRY[GEOM_KEY]
     if input_audio_length < geom.nfft or (input_audio_length - geom.nfft) % geom.hop:
         raise ValueError("input_audio_length must be nfft + k*hop (1920 + k*384): snip-edges framing, no centre padding")
@@ -164,22 +172,25 @@ def pack(sd: dict, h: Mf2Hyper, input_audio_length: int) -> dict[str, np.ndarray
 
 
 def metadata(h: Mf2Hyper, input_audio_length: int, in_dtype: str = "INT16", out_dtype: str = "INT16",
-             matmul_dtype: str = "F32") -> dict[str, str]:
+             matmul_dtype: str = "F32", in_rate: int | None = None, out_rate: int | None = None) -> dict[str, str]:
     """Metadata keys of `Export_MossFormer_SE.py:557-561` + the hyper-parameters the reference
     reads off the live upstream modules."""
     g = stft_tables.GEOMETRY[GEOM_KEY]
+    in_rate, out_rate = in_rate or h.sample_rate, out_rate or h.sample_rate
+    mlen = model_length(h, input_audio_length, in_rate)
+    olen = mlen if out_rate == h.sample_rate else int(round(input_audio_length * out_rate / in_rate))
     md = {
         "audio_metadata_version": 1, "producer": "adn.mf2se_params", "model_name": "MossFormer2_SE_48K",
         "task": "denoise", "model_family": FAMILY, "dynamic_axes": "0", "opset": 20,
         "input_audio_dtype": in_dtype, "output_audio_dtype": out_dtype,
-        "in_sample_rate": h.sample_rate, "out_sample_rate": h.sample_rate, "model_sample_rate": h.sample_rate,
+        "in_sample_rate": in_rate, "out_sample_rate": out_rate, "model_sample_rate": h.sample_rate,
         "input_audio_length": input_audio_length, "export_audio_length": input_audio_length,
-        "model_audio_length": input_audio_length, "output_audio_length": input_audio_length,
-        "input_to_output_scale": 1.0, "batch_window_seconds": 1.5, "use_batch_fold": "0",
+        "model_audio_length": mlen, "output_audio_length": olen,
+        "input_to_output_scale": float(out_rate / in_rate), "batch_window_seconds": 1.5, "use_batch_fold": "0",
         "batch_fold_inference_default": "0", "fold_window_length": 72192, "fold_input_length": 72192,
         "max_dynamic_audio_seconds": 6, "normalize_audio_default": "0", "normalize_target_rms": 4096.0,
         "window_type": "hamming", "nfft": g.nfft, "window_length": g.win_length, "hop_length": g.hop,
-        "max_signal_length": g.n_frames(input_audio_length), "center_pad": "0", "pad_mode": "constant",
+        "max_signal_length": g.n_frames(mlen), "center_pad": "0", "pad_mode": "constant",
         "feature_kind": "kaldi_fbank_stft", "input_channels": 1, "output_channels": 1, "num_audio_inputs": 1,
         "n_mels": h.n_mels, "mf2_layers": h.layers,
         # F32 = 3xTF32 tensor-core GEMMs with fp32-class accuracy (default, the 1e-4 parity path); BF16 = the 24 layers'

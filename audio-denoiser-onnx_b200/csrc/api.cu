@@ -572,7 +572,7 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
     m->err = "gtcrn requires nfft=512, hop_length=256";
     return fail(ADN_ERR_INVALID);
   }
-  if (m->L < nfft) {
+  if (is_gtcrn && m->L < nfft) {                   // (the other families validate their own model-rate window)
     m->err = "input_audio_length must be >= nfft";
     return fail(ADN_ERR_INVALID);
   }

@@ -180,6 +180,23 @@ fsmn_mem_kernel(const float* __restrict__ xp, const float* __restrict__ uv, cons
   }
 }
 
+// In-place x *= s (the int16 PCM scale of a resampled input; 2^-15 commutes exactly with the linear interpolation).
+__global__ void scale_kernel(float* __restrict__ x, long long n, float s) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) x[i] *= s;
+}
+
+// Output conversion behind the output resampler (:499-507): int16 = clamp(x, -1, 32767/32768) * 32768 through int32.
+__global__ void se_convert_kernel(const float* __restrict__ src, void* __restrict__ out, int out_dtype, long long n) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float v = src[i];
+  if (out_dtype == ADN_I16)
+    reinterpret_cast<int16_t*>(out)[i] = (int16_t)max(-32768, min(32767, (int)(fminf(fmaxf(v, -1.0f), 32767.0f / 32768.0f) * 32768.0f)));
+  else if (out_dtype == ADN_F32) reinterpret_cast<float*>(out)[i] = v;
+  else reinterpret_cast<__half*>(out)[i] = __float2half_rn(v);
+}
+
 // One CTA per frame: real mask on both STFT row blocks, written into the zero-framed ISTFT operand.
 __global__ void __launch_bounds__(256)
 mask_apply_kernel(const float* __restrict__ fr, const float* __restrict__ mask, float* __restrict__ ehi,
@@ -198,6 +215,9 @@ class Model : public Base {
  public:
   int in_dtype = ADN_F32, out_dtype = ADN_F32;
   int L = 0, Lp = 0, T = 0, Tp = 0, T4 = 0, Tn = 0, layers = 24;
+  int L_in = 0, L_final = 0;     // window length at the input rate / output length at the output rate (== L at 48 kHz)
+  bool rs_in = false, rs_out = false;
+  float *xr = nullptr, *yres = nullptr, *yout = nullptr;
 
   int *d_mel_lo = nullptr, *d_mel_hi = nullptr;
   const float *banks = nullptr, *norm_w = nullptr, *norm_b = nullptr, *emb = nullptr, *rcos = nullptr, *rsin = nullptr;
@@ -254,8 +274,20 @@ class Model : public Base {
     if (!geti("input_audio_length", L) || !geti("nfft", nfft) || !geti("hop_length", hop) || !geti("n_mels", nmels) ||
         !geti("mf2_layers", layers) || !gets("input_audio_dtype", sin) || !gets("output_audio_dtype", sout))
       return false;
+    // optional linear resampling either side of the model (:318-325, :491-498): input_audio_length is at in_sample_rate
+    int in_sr = 48000, out_sr = 48000, model_sr = 48000;
+    {
+      auto opt = [&](const char* k, int& v) { auto it = meta.find(k); if (it != meta.end() && !it->second.empty()) v = atoi(it->second.c_str()); };
+      opt("in_sample_rate", in_sr); opt("out_sample_rate", out_sr); opt("model_sample_rate", model_sr);
+    }
+    if (model_sr != 48000 || in_sr <= 0 || out_sr <= 0) { err = "mossformer2_se runs at model_sample_rate 48000"; return false; }
+    L_in = L;
+    rs_in = in_sr != model_sr;
+    rs_out = out_sr != model_sr;
+    if (rs_in) L = (int)llround((double)L_in * model_sr / in_sr);          // MODEL_AUDIO_LENGTH (:48)
+    L_final = rs_out ? (int)llround((double)L_in * out_sr / in_sr) : L;    // OUTPUT_AUDIO_LENGTH (:49)
     if (nfft != NFFT || hop != HOP || nmels != NM || L < NFFT || (L - NFFT) % HOP) {
-      err = "mossformer2_se needs nfft=1920, hop=384, n_mels=60 and input_audio_length = 1920 + k*384";
+      err = "mossformer2_se needs nfft=1920, hop=384, n_mels=60 and a model-rate window of 1920 + k*384 samples";
       return false;
     }
     {
@@ -353,7 +385,7 @@ class Model : public Base {
 
   size_t floats_needed(size_t B) const {
     const size_t M = B * T;
-    return B * Lp * 3 + M * FRONT + M * NM + 2 * M * FEATP + 2 * M * D + 2 * M * D + 2 * M + M * PROJ + M * VU2 +
+    return (rs_in ? B * L : 0) + (rs_out ? B * (L + L_final) : 0) + B * Lp * 3 + M * FRONT + M * NM + 2 * M * FEATP + 2 * M * D + 2 * M * D + 2 * M + M * PROJ + M * VU2 +
            2 * B * VU2 * Tp + 4 * M * QK + 4 * B * Tn * QK + 3 * M * Tp + M * VU2 +
            2 * M * VU + M * D + 2 * M * D + 2 * M * FI + 2 * M * FI + 2 * M * D + 2 * M * FI + 2 * M * FI + M * FI +
            2 * M * FI + M * D + 2 * M * D + M * 2 * D + 2 * M * D + M * BINSP + 2 * (B * (T + 2 * PADF) * SPEC_LD + 9664);
@@ -365,6 +397,9 @@ class Model : public Base {
     free_ws();
     const long long M = (long long)B * T;
     const size_t xplane = (size_t)B * Lp;
+    if ((rs_in && !alloc(xr, (size_t)B * L, false)) ||
+        (rs_out && (!alloc(yres, (size_t)B * L, false) || !alloc(yout, (size_t)B * L_final, false))))
+      return false;
     enh_plane = (size_t)B * (T + 2 * PADF) * SPEC_LD + ola.k_pad;       // + slack for the K overrun of the last block
     if (!alloc(xp, xplane, false) || !alloc(xpl, 2 * xplane, false) || !alloc(fr, (size_t)M * FRONT, false) ||
         !alloc(mel, (size_t)M * NM, false) || !alloc(featpl, 2 * (size_t)M * FEATP, true) || !alloc(z, (size_t)M * D, false) ||
@@ -434,7 +469,7 @@ class Model : public Base {
       const int bt = TM >= 128 ? 128 : TM;
       c.bt = bt; c.tiles_per_chunk = (TM + 127) / 128; c.m_tiles = B * c.tiles_per_chunk; c.TM = TM; c.t0 = 0;
       c.N = HOP; c.K = R_OLA * SPEC_LD;
-      c.norm = d_norm; c.norm_mul = 0; c.hop = HOP; c.shift = 0; c.out_len = L; c.out_dtype = out_dtype; c.i16_mode = 1;
+      c.norm = d_norm; c.norm_mul = 0; c.hop = HOP; c.shift = 0; c.out_len = L; c.out_dtype = rs_out ? ADN_F32 : out_dtype; c.i16_mode = 1;
       // the A box must match bt rows
       if (!tc::make_row_map(&g_istft.plan.map_a_hi, enh, ola.k_pad, rows, SPEC_LD, B, (long long)rows * SPEC_LD, bt, 1, err) ||
           !tc::make_row_map(&g_istft.plan.map_a_lo, enh + enh_plane, ola.k_pad, rows, SPEC_LD, B, (long long)rows * SPEC_LD, bt, 1, err))
@@ -450,12 +485,12 @@ class Model : public Base {
     memset(in, 0, sizeof(*in));
     memset(out, 0, sizeof(*out));
     strncpy(in->name, "noisy_audio", sizeof(in->name) - 1);        // Export_MossFormer_SE.py:537
-    in->dtype = in_dtype; in->channels = 1; in->length = L;
+    in->dtype = in_dtype; in->channels = 1; in->length = L_in;
     strncpy(out->name, "denoised_audio", sizeof(out->name) - 1);   // :538
-    out->dtype = out_dtype; out->channels = 1; out->length = L;
+    out->dtype = out_dtype; out->channels = 1; out->length = L_final;
   }
   size_t workspace_bytes(int batch) override { return floats_needed((size_t)batch) * sizeof(float); }
-  int launches(int) override { return 5 + layers * 17 + 6; }
+  int launches(int) override { return 5 + layers * 17 + 6 + (rs_in ? (in_dtype == ADN_I16 ? 2 : 1) : 0) + (rs_out ? 2 : 0); }
   void set_stop_after(int n) override { stop_after = n; }
 
 #define MF_TICK(name) do { ++n; if (tick) tick(tick_ctx, name); if (stop_after > 0 && n >= stop_after) return ADN_OK; } while (0)
@@ -476,7 +511,19 @@ class Model : public Base {
     }
 
     // 1-3: cast (+1/32768 for int16, :315-317), fused Kaldi||STFT frontend (:335), log-mel (:337-341)
-    gtcrn::launch_prep(d_in, in_dtype, xp, xpl, xpl + (size_t)B * Lp, B, L, Lp, 0, 0, 0, st);
+    const void* src = d_in;
+    int src_dtype = in_dtype;
+    if (rs_in) {                                   // x * 1/32768 (int16), then F.interpolate(size=MODEL_AUDIO_LENGTH) (:315-325)
+      if (adn_resample_linear(d_in, in_dtype, xr, B, L_in, L, 0.0, st) != ADN_OK) { err = "input resampler launch failed"; return ADN_ERR_CUDA; }
+      MF_TICK("resample_in");
+      if (in_dtype == ADN_I16) {
+        scale_kernel<<<(unsigned)(((long long)B * L + 255) / 256), 256, 0, st>>>(xr, (long long)B * L, 1.0f / 32768.0f);
+        MF_TICK("pcm_scale");
+      }
+      src = xr;
+      src_dtype = ADN_F32;
+    }
+    gtcrn::launch_prep(src, src_dtype, xp, xpl, xpl + (size_t)B * Lp, B, L, Lp, 0, 0, 0, st);
     MF_TICK("prep");
     MF_GEMM(g_front, EPI_LIN, "frontend_gemm");
     feat_kernel<<<(unsigned)M, 256, 0, st>>>(fr, banks, d_mel_lo, d_mel_hi, mel, 1.1920929e-07f * (1.0f / 32768.0f) * (1.0f / 32768.0f),
@@ -526,8 +573,14 @@ class Model : public Base {
     MF_GEMM(g_dec, EPI_LIN, "mask_gemm");
     mask_apply_kernel<<<(unsigned)M, 256, 0, st>>>(fr, mask, enh, enh + enh_plane, T);
     MF_TICK("mask_apply");
-    g_istft.args.out = d_out;
+    g_istft.args.out = rs_out ? (void*)yres : d_out;
     MF_GEMM(g_istft, EPI_ISTFT, "istft_gemm");
+    if (rs_out) {                                  // F.interpolate(size=OUTPUT_AUDIO_LENGTH), then the output rule (:491-507)
+      if (adn_resample_linear(yres, ADN_F32, yout, B, L, L_final, 0.0, st) != ADN_OK) { err = "output resampler launch failed"; return ADN_ERR_CUDA; }
+      MF_TICK("resample_out");
+      se_convert_kernel<<<(unsigned)(((long long)B * L_final + 255) / 256), 256, 0, st>>>(yout, d_out, out_dtype, (long long)B * L_final);
+      MF_TICK("convert_out");
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("mf2se run: ") + cudaGetErrorString(e); return ADN_ERR_CUDA; }
     return ADN_OK;

@@ -417,23 +417,37 @@ def mf2se_core(P: dict, c: Mf2Config, feats: torch.Tensor, dbg=None) -> torch.Te
     return F.relu(F.linear(t, P["dec_w"]))
 
 
+def model_len(length: int, in_rate: int, c: Mf2Config = Mf2Config()) -> int:
+    """MODEL_AUDIO_LENGTH (:48): the window length at the 48 kHz model rate."""
+    return int(round(length * c.sample_rate / in_rate))
+
+
 def mf2se_forward(sd: dict, audio: torch.Tensor, c: Mf2Config = Mf2Config(), in_dtype: str = "F32",
-                  out_dtype: str = "F32", dbg=None, folded: dict | None = None) -> torch.Tensor:
-    """audio (B,1,L) in `in_dtype` -> (B,1,L) in `out_dtype`; every window independent."""
-    B, _, L = audio.shape
+                  out_dtype: str = "F32", dbg=None, folded: dict | None = None, in_rate: int | None = None,
+                  out_rate: int | None = None) -> torch.Tensor:
+    """audio (B,1,L) in `in_dtype` -> (B,1,L_out) in `out_dtype`; every window independent.  in_rate / out_rate != 48 kHz:
+    linear resampling to MODEL_AUDIO_LENGTH behind the PCM scale (:318-325) and to OUTPUT_AUDIO_LENGTH behind the
+    ISTFT (:491-498)."""
+    B, _, L_in = audio.shape
+    in_rate, out_rate = in_rate or c.sample_rate, out_rate or c.sample_rate
+    x = audio.float()
+    if "int" in in_dtype.lower():
+        x = x * INV_INT16
+    if in_rate != c.sample_rate:
+        x = F.interpolate(x, size=model_len(L_in, in_rate, c), mode="linear", align_corners=False)
+    L = x.shape[-1]
     T = c.n_frames(L)
     if T > c.group:
         raise ValueError("restatement covers one FLASH group (frames <= group_size)")
     P = folded if folded is not None else fold(sd, c, T)
-    x = audio.float()
-    if "int" in in_dtype.lower():
-        x = x * INV_INT16
     feats, st = features(P, c, x)
     mask = mf2se_core(P, c, feats, dbg)                                             # (B,T,bins)
     masked = (st.reshape(B, 2, c.out_bins, T) * mask.transpose(1, 2).unsqueeze(1)).reshape(B, 2 * c.out_bins, T)
     if dbg is not None:
         dbg["feats"], dbg["stft"], dbg["mask"] = feats, st, mask
     y = istft_packed(SPECS["mossformer2_se_48k"], masked)
+    if out_rate != c.sample_rate:
+        y = F.interpolate(y, size=int(round(L_in * out_rate / in_rate)), mode="linear", align_corners=False)
     if "int" in out_dtype.lower():
         y = y.clamp(min=-1.0, max=32767.0 / 32768.0) * 32768.0                     # int32 staging cast (:499-504)
         return y.to(torch.int32).clamp(min=-32768, max=32767).to(torch.int16)

@@ -166,7 +166,7 @@ def load_mbr(input_audio_length: int, io_dtype: str = "F32"):
     return ns, build
 
 
-def load_mf2se(input_audio_length: int, io_dtype: str = "F32"):
+def load_mf2se(input_audio_length: int, io_dtype: str = "F32", in_rate: int = 48000, out_rate: int = 48000):
     """Reference MossFormer2-SE-48K wrapper (`MOSSFORMER_SE`) for one un-folded window.
 
     The wrapper's forward is made of leaf ops; only its constructor reads the absent
@@ -187,6 +187,8 @@ def load_mf2se(input_audio_length: int, io_dtype: str = "F32"):
             "INPUT_AUDIO_LENGTH = 96000": f"INPUT_AUDIO_LENGTH = {int(input_audio_length)}",
             "IN_AUDIO_DTYPE     = 'INT16'": f"IN_AUDIO_DTYPE     = '{io_dtype}'",
             "OUT_AUDIO_DTYPE    = 'INT16'": f"OUT_AUDIO_DTYPE    = '{io_dtype}'",
+            "IN_SAMPLE_RATE     = 48000": f"IN_SAMPLE_RATE     = {int(in_rate)}",
+            "OUT_SAMPLE_RATE    = 48000": f"OUT_SAMPLE_RATE    = {int(out_rate)}",
         },
     )
 

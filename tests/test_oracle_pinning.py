@@ -378,3 +378,25 @@ def test_mf2ss_oracle_resampling_matches_reference_module(L, in_rate, out_rate):
     for a, b in zip(yr, yo):
         assert a.shape == b.shape == (1, 1, want)
         assert (a - b).abs().max() <= 5e-6
+
+
+@needs_ref
+@pytest.mark.parametrize("L,in_rate,out_rate", [(3200, 16000, 48000), (9600, 48000, 16000)])
+def test_mf2se_oracle_resampling_matches_reference_module(L, in_rate, out_rate):
+    """IN / OUT_SAMPLE_RATE != 48 kHz: the wrapper's linear resamplers (MossFormer2_SE_48K/Export_MossFormer_SE.py
+    :318-325, :491-498) -- executed reference vs the restatement."""
+    import mf2se_oracle as mo
+
+    cfg = mo.Mf2Config(layers=2)
+    sd = mo.random_state_dict(cfg, 3)
+    hold = mo.skeleton(cfg)
+    hold.load_state_dict(sd)
+    _, build = ref_loader.load_mf2se(L, "F32", in_rate, out_rate)
+    w = build(hold)
+    x = synth_audio(L, 17)
+    with torch.inference_mode():
+        yr = w(x.clone())
+        yo = mo.mf2se_forward(sd, x, cfg, in_rate=in_rate, out_rate=out_rate)
+    want = int(round(L * out_rate / in_rate)) if out_rate != 48000 else mo.model_len(L, in_rate, cfg)
+    assert yr.shape == yo.shape == (1, 1, want)
+    assert (yr - yo).abs().max() <= 2e-6
