@@ -6,21 +6,21 @@ from . import gtcrn_params, modelfile
 
 
 def export_gtcrn(state_dict: dict, path, input_audio_length: int = 16000, in_dtype: str = "INT16",
-                 out_dtype: str = "INT16") -> dict[str, str]:
+                 out_dtype: str = "INT16", in_rate: int = 16000, out_rate: int = 16000) -> dict[str, str]:
     """Writes `path` (.adn) for one static chunk length; returns the metadata stamped."""
-    md = gtcrn_params.metadata(input_audio_length, in_dtype, out_dtype)
-    tensors = gtcrn_params.pack(state_dict, input_audio_length)
+    md = gtcrn_params.metadata(input_audio_length, in_dtype, out_dtype, in_rate, out_rate)
+    tensors = gtcrn_params.pack(state_dict, input_audio_length, in_rate)
     modelfile.save(path, md, tensors)
     return md
 
 
 def gtcrn_model(state_dict: dict, input_audio_length: int = 16000, in_dtype: str = "F32",
-                out_dtype: str = "F32", device_id: int = 0):
+                out_dtype: str = "F32", device_id: int = 0, in_rate: int = 16000, out_rate: int = 16000):
     """In-memory shortcut: build a `Model` without touching the file system."""
     from .model import Model
 
-    md = gtcrn_params.metadata(input_audio_length, in_dtype, out_dtype)
-    return Model.from_tensors(md, gtcrn_params.pack(state_dict, input_audio_length), device_id)
+    md = gtcrn_params.metadata(input_audio_length, in_dtype, out_dtype, in_rate, out_rate)
+    return Model.from_tensors(md, gtcrn_params.pack(state_dict, input_audio_length, in_rate), device_id)
 
 
 def export_mbr(state_dict: dict, path, hyper=None, input_audio_length: int = 66150, in_dtype: str = "INT16",

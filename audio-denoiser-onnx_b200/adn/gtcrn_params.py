@@ -82,8 +82,23 @@ def _nonzero_ranges(mat: torch.Tensor):
     return lo, hi
 
 
-def pack(state_dict: dict, input_audio_length: int) -> dict[str, np.ndarray]:
-    """Returns {tensor name: fp32 array} for one static chunk length."""
+def model_length(input_audio_length: int, in_rate: int = 16000) -> int:
+    """Window length at the 16 kHz model rate: F.interpolate(scale_factor=16000/in_rate) yields floor(L * scale)
+    samples (Export_GTCRN.py:626, :638-654)."""
+    if in_rate == 16000:
+        return int(input_audio_length)
+    return int(np.floor(float(input_audio_length) * (1.0 / (in_rate / 16000.0))))
+
+
+def output_length(model_out_length: int, out_rate: int = 16000) -> int:
+    if out_rate == 16000:
+        return int(model_out_length)
+    return int(np.floor(float(model_out_length) * (out_rate / 16000.0)))
+
+
+def pack(state_dict: dict, input_audio_length: int, in_rate: int = 16000) -> dict[str, np.ndarray]:
+    """Returns {tensor name: fp32 array} for one static chunk length (given at `in_rate`)."""
+    input_audio_length = model_length(input_audio_length, in_rate)
     sd = {k: v for k, v in state_dict.items()}
     geom = stft_tables.GEOMETRY["gtcrn"]
     blob: dict[str, np.ndarray] = {}
@@ -148,19 +163,22 @@ def pack(state_dict: dict, input_audio_length: int) -> dict[str, np.ndarray]:
     return blob
 
 
-def metadata(input_audio_length: int, in_dtype: str = "INT16", out_dtype: str = "INT16") -> dict[str, str]:
+def metadata(input_audio_length: int, in_dtype: str = "INT16", out_dtype: str = "INT16", in_rate: int = 16000,
+             out_rate: int = 16000) -> dict[str, str]:
     """The metadata keys `Export_GTCRN.py:784-788` stamps (via
-    audio_onnx_metadata.build_audio_metadata_from_globals), as strings."""
+    audio_onnx_metadata.build_audio_metadata_from_globals), as strings.  in_rate / out_rate != 16000: the model resamples
+    linearly either side; input_audio_length is at in_rate."""
     g = stft_tables.GEOMETRY["gtcrn"]
-    t = g.n_frames(input_audio_length)
+    mlen = model_length(input_audio_length, in_rate)
+    t = g.n_frames(mlen)
     md = {
         "audio_metadata_version": 1, "producer": "adn.gtcrn_params", "model_name": "GTCRN", "task": "denoise",
         "model_family": FAMILY, "dynamic_axes": "0", "opset": 20,
         "input_audio_dtype": in_dtype, "output_audio_dtype": out_dtype,
-        "in_sample_rate": 16000, "out_sample_rate": 16000, "model_sample_rate": 16000,
+        "in_sample_rate": in_rate, "out_sample_rate": out_rate, "model_sample_rate": 16000,
         "input_audio_length": input_audio_length, "export_audio_length": input_audio_length,
-        "model_audio_length": input_audio_length, "output_audio_length": g.out_length(t),
-        "input_to_output_scale": 1.0, "batch_window_seconds": 1.5, "use_batch_fold": "0",
+        "model_audio_length": mlen, "output_audio_length": output_length(g.out_length(t), out_rate),
+        "input_to_output_scale": float(out_rate / in_rate), "batch_window_seconds": 1.5, "use_batch_fold": "0",
         "batch_fold_inference_default": "0", "fold_window_length": 24064, "fold_input_length": 24064,
         "max_dynamic_audio_seconds": 30, "normalize_audio_default": "0", "normalize_target_rms": 4096.0,
         "window_type": g.window_type, "nfft": g.nfft, "window_length": g.win_length, "hop_length": g.hop,

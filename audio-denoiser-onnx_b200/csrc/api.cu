@@ -134,7 +134,15 @@ struct adn_model {
   size_t nfloats = 0;
 
   int in_dtype = ADN_F32, out_dtype = ADN_F32;
-  int L = 0, T = 0, Lp = 0, Lout = 0, chans = 1;
+  int L = 0, T = 0, Lp = 0, Lout = 0, chans = 1;   // GTCRN: L / Lout are the MODEL-rate window and its ISTFT length
+  // GTCRN linear resampling (Export_GTCRN.py:619-632, :638-654, :671-688): the caller's window is io_L samples at
+  // in_sample_rate, the output io_Lout samples at out_sample_rate; the inner run works on fp32 model-rate buffers
+  bool rs_in = false, rs_out = false;
+  int io_L = 0, io_Lout = 0, in_sr = 16000, out_sr = 16000;
+  double in_scale_factor = 1.0, out_scale_factor = 1.0;
+  int run_in_dtype = ADN_F32, run_out_dtype = ADN_F32, run_remove_dc = 1;
+  float *rs_xc = nullptr, *rs_xm = nullptr, *rs_ym = nullptr, *rs_yr = nullptr;
+  int rs_cap = 0;
   StftPlan stft;
   const float* d_fwd = nullptr;
   float* d_ola = nullptr;
@@ -253,7 +261,7 @@ size_t workspace_bytes_for(const adn_model* m, int B) {
   f += (size_t)3 * B * T * FRAME16;             // xa, xb, inter
   f += (size_t)B * (T + 2 * m->stft.pad_frames()) * SPEC_LD;   // enh
   size_t bytes = f * sizeof(float);
-  bytes += (size_t)B * m->L * dtype_size(m->in_dtype) + (size_t)B * m->Lout * dtype_size(m->out_dtype);
+  bytes += (size_t)B * m->io_L * dtype_size(m->in_dtype) + (size_t)B * m->io_Lout * dtype_size(m->out_dtype);
   return bytes;
 }
 
@@ -309,15 +317,15 @@ adn_status ensure_capacity(adn_model* m, int B) {
     c.bb = bb; c.bt = bt; c.tiles_per_chunk = tpc; c.t0 = lo; c.TM = TM;
     c.N = p.hop; c.K = p.R * p.ld;
     c.norm = m->d_norm; c.norm_mul = p.norm_mul; c.hop = p.hop; c.shift = p.center ? p.half : 0;
-    c.out_len = m->Lout; c.out_dtype = m->out_dtype;
+    c.out_len = m->Lout; c.out_dtype = m->run_out_dtype;
     const int rows = (int)T + 2 * p.pad_frames();
     if (!tc::make_row_map(&m->istft_plan.map_a_hi, m->enh_hl, m->wo_kpad, rows, p.ld, B, (long long)rows * p.ld, bt, bb, m->err) ||
         !tc::make_row_map(&m->istft_plan.map_a_lo, m->enh_hl + m->enh_plane, m->wo_kpad, rows, p.ld, B,
                           (long long)rows * p.ld, bt, bb, m->err))
       return ADN_ERR_CUDA;
   }
-  if ((s = dev_alloc(m, &m->d_in, (size_t)B * m->L * dtype_size(m->in_dtype), false)) != ADN_OK) return s;
-  if ((s = dev_alloc(m, &m->d_out, (size_t)B * m->Lout * dtype_size(m->out_dtype), false)) != ADN_OK) return s;
+  if ((s = dev_alloc(m, &m->d_in, (size_t)B * m->io_L * dtype_size(m->in_dtype), false)) != ADN_OK) return s;
+  if ((s = dev_alloc(m, &m->d_out, (size_t)B * m->io_Lout * dtype_size(m->out_dtype), false)) != ADN_OK) return s;
 #undef A
   m->capacity = B;
   return ADN_OK;
@@ -441,16 +449,16 @@ adn_status gtcrn_run(adn_model* m, const void* d_in, void* d_out, int batch, cud
   tick_cb(m, "start");
   const int nr = ps ? 2 : 1;
   const int lo[2] = {0, ps ? ps->mid : 0}, hi[2] = {ps ? ps->mid : batch, batch};
-  const size_t in_row = (size_t)m->L * dtype_size(m->in_dtype);
+  const size_t in_row = (size_t)m->L * dtype_size(m->run_in_dtype);
   GemmArgs g;
 
   for (int r = 0; r < nr; ++r) {
     const int b0 = lo[r], nb = hi[r] - lo[r];
     if (ps) ADN_CUDA_TRY(cudaStreamWaitEvent(st, ps->h2d_done[r], 0), m->err);
-    gtcrn::launch_prep((const char*)d_in + b0 * in_row, m->in_dtype, m->buf.xp + (size_t)b0 * m->Lp,
+    gtcrn::launch_prep((const char*)d_in + b0 * in_row, m->run_in_dtype, m->buf.xp + (size_t)b0 * m->Lp,
                        m->buf.xp_hi ? m->buf.xp_hi + (size_t)b0 * m->Lp : nullptr,
                        m->buf.xp_lo ? m->buf.xp_lo + (size_t)b0 * m->Lp : nullptr, nb, m->L, m->Lp, m->stft.half,
-                       /*remove_dc=*/1, m->stft.reflect, st);
+                       /*remove_dc=*/m->run_remove_dc, m->stft.reflect, st);
     if (r == 0) { ++n; tick_cb(m, "prep"); }
     if (m->use_tc) {
       tc::TcArgs a = m->stft_args;
@@ -478,7 +486,7 @@ adn_status gtcrn_run(adn_model* m, const void* d_in, void* d_out, int batch, cud
     return ADN_OK;
   }
 
-  const size_t out_row = (size_t)m->Lout * dtype_size(m->out_dtype);
+  const size_t out_row = (size_t)m->Lout * dtype_size(m->run_out_dtype);
   for (int r = 0; r < nr; ++r) {
     const int b0 = lo[r], nb = hi[r] - lo[r];
     if (m->use_tc) {
@@ -491,7 +499,7 @@ adn_status gtcrn_run(adn_model* m, const void* d_in, void* d_out, int batch, cud
       if (r == 0) { ++n; tick_cb(m, "istft_gemm_tc"); }
     } else {
       fill_istft_gemm(g, m->stft, m->buf.enh + (size_t)b0 * (m->T + 2 * m->stft.pad_frames()) * gtcrn::SPEC_LD,
-                      m->d_ola, m->d_norm, nb, m->T, (char*)d_out + b0 * out_row, m->out_dtype);
+                      m->d_ola, m->d_norm, nb, m->T, (char*)d_out + b0 * out_row, m->run_out_dtype);
       launch_gemm_ffma(g, EPI_ISTFT, st);
       if (r == 0) { ++n; tick_cb(m, "istft_gemm"); }
     }
@@ -499,6 +507,62 @@ adn_status gtcrn_run(adn_model* m, const void* d_in, void* d_out, int batch, cud
   }
   m->last_launches = n;
   m->last_batch = batch;
+  ADN_CUDA_TRY(cudaGetLastError(), m->err);
+  return ADN_OK;
+}
+
+__global__ void rs_scale_kernel(float* __restrict__ x, long long n, float s) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) x[i] *= s;
+}
+
+// clamp / truncate to int16, fp32 copy or fp16 cast (Export_GTCRN.py:689-693)
+__global__ void rs_convert_kernel(const float* __restrict__ src, void* __restrict__ out, int out_dtype, long long n) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float v = src[i];
+  if (out_dtype == ADN_I16) reinterpret_cast<int16_t*>(out)[i] = (int16_t)(int)fminf(fmaxf(v, -32768.0f), 32767.0f);
+  else if (out_dtype == ADN_F32) reinterpret_cast<float*>(out)[i] = v;
+  else reinterpret_cast<__half*>(out)[i] = __float2half_rn(v);
+}
+
+// GTCRN with in / out sample rates other than 16 kHz (Export_GTCRN.py:636-693).  Input: down-sampling resamples the raw
+// samples first and then applies the PCM scale and the DC removal (inside the model's prep kernel); up-sampling scales and
+// removes the mean at the INPUT rate, then resamples (:638-654).  Output: down-sampling resamples before the x32767 PCM
+// scale, up-sampling after it (:671-688).  The 2^-15 input scale commutes exactly with the linear interpolation.
+adn_status gtcrn_run_resampled(adn_model* m, const void* d_in, void* d_out, int batch, cudaStream_t st) {
+  if (batch > m->rs_cap) {
+    ADN_CUDA_TRY(cudaDeviceSynchronize(), m->err);
+    if (m->rs_cap) { cudaFree(m->rs_xc); cudaFree(m->rs_xm); cudaFree(m->rs_ym); cudaFree(m->rs_yr); }
+    m->rs_cap = 0;
+    ADN_CUDA_TRY(cudaMalloc((void**)&m->rs_xc, (size_t)batch * m->io_L * 4), m->err);
+    ADN_CUDA_TRY(cudaMalloc((void**)&m->rs_xm, (size_t)batch * m->L * 4), m->err);
+    ADN_CUDA_TRY(cudaMalloc((void**)&m->rs_ym, (size_t)batch * m->Lout * 4), m->err);
+    ADN_CUDA_TRY(cudaMalloc((void**)&m->rs_yr, (size_t)batch * m->io_Lout * 4), m->err);
+    m->rs_cap = batch;
+  }
+  auto blocks = [](long long n) { return (unsigned)((n + 255) / 256); };
+  const void* run_in = d_in;
+  if (m->rs_in) {
+    const long long nm = (long long)batch * m->L;
+    if (m->in_sr > 16000) {
+      if (adn_resample_linear(d_in, m->in_dtype, m->rs_xm, batch, m->io_L, m->L, m->in_scale_factor, st) != ADN_OK) return ADN_ERR_CUDA;
+      if (m->in_dtype == ADN_I16) rs_scale_kernel<<<blocks(nm), 256, 0, st>>>(m->rs_xm, nm, 1.0f / 32768.0f);
+    } else {
+      // cast, PCM scale and DC removal at the input rate (the prep kernel without padding), then the resampler
+      gtcrn::launch_prep(d_in, m->in_dtype, m->rs_xc, nullptr, nullptr, batch, m->io_L, m->io_L, 0, 1, 0, st);
+      if (adn_resample_linear(m->rs_xc, ADN_F32, m->rs_xm, batch, m->io_L, m->L, m->in_scale_factor, st) != ADN_OK) return ADN_ERR_CUDA;
+    }
+    run_in = m->rs_xm;
+  }
+  adn_status s = gtcrn_run(m, run_in, m->rs_out ? (void*)m->rs_ym : d_out, batch, st, nullptr);
+  if (s != ADN_OK || !m->rs_out || (m->stop_after > 0 && m->last_launches >= m->stop_after)) return s;
+  const long long no = (long long)batch * m->io_Lout, nmo = (long long)batch * m->Lout;
+  const bool pcm = m->out_dtype == ADN_I16;
+  if (m->out_sr > 16000 && pcm) rs_scale_kernel<<<blocks(nmo), 256, 0, st>>>(m->rs_ym, nmo, 32767.0f);
+  if (adn_resample_linear(m->rs_ym, ADN_F32, m->rs_yr, batch, m->Lout, m->io_Lout, m->out_scale_factor, st) != ADN_OK) return ADN_ERR_CUDA;
+  if (m->out_sr < 16000 && pcm) rs_scale_kernel<<<blocks(no), 256, 0, st>>>(m->rs_yr, no, 32767.0f);
+  rs_convert_kernel<<<blocks(no), 256, 0, st>>>(m->rs_yr, d_out, m->out_dtype, no);
   ADN_CUDA_TRY(cudaGetLastError(), m->err);
   return ADN_OK;
 }
@@ -572,6 +636,28 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
     m->err = "gtcrn requires nfft=512, hop_length=256";
     return fail(ADN_ERR_INVALID);
   }
+  m->io_L = m->L;
+  m->run_in_dtype = m->in_dtype;
+  m->run_out_dtype = m->out_dtype;
+  if (is_gtcrn) {                                  // optional linear resampling (Export_GTCRN.py:619-632)
+    auto opt = [&](const char* k, int& v) { auto it = m->meta.find(k); if (it != m->meta.end() && !it->second.empty()) v = atoi(it->second.c_str()); };
+    int model_sr = 16000;
+    opt("in_sample_rate", m->in_sr); opt("out_sample_rate", m->out_sr); opt("model_sample_rate", model_sr);
+    if (model_sr != 16000 || m->in_sr <= 0 || m->out_sr <= 0) {
+      m->err = "gtcrn runs at model_sample_rate 16000";
+      return fail(ADN_ERR_INVALID);
+    }
+    m->rs_in = m->in_sr != 16000;
+    m->rs_out = m->out_sr != 16000;
+    m->in_scale_factor = 1.0 / ((double)m->in_sr / 16000.0);       // model_rate_scale (:626)
+    m->out_scale_factor = (double)m->out_sr / 16000.0;             // out_sample_rate_scale (:625)
+    if (m->rs_in) {
+      m->L = (int)floor((double)m->io_L * m->in_scale_factor);     // F.interpolate(scale_factor=...) output size
+      m->run_in_dtype = ADN_F32;
+      m->run_remove_dc = m->in_sr > 16000 ? 1 : 0;                 // up-sampling: the mean is removed BEFORE the resampler (:627-628)
+    }
+    if (m->rs_out) m->run_out_dtype = ADN_F32;
+  }
   if (is_gtcrn && m->L < nfft) {                   // (the other families validate their own model-rate window)
     m->err = "input_audio_length must be >= nfft";
     return fail(ADN_ERR_INVALID);
@@ -585,6 +671,7 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
     m->Lout = (m->T - 1) * hop + nfft;
     m->n_out = 2;
   }
+  m->io_Lout = m->rs_out ? (int)floor((double)m->Lout * m->out_scale_factor) : m->Lout;
   m->chans = fam == "mel_band_roformer" ? 2 : 1;
 
   int ndev = 0;
@@ -621,6 +708,7 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
       adn_tensor_info tin, touts[4];
       m->impl->io_info(&tin, touts);
       m->L = tin.length; m->chans = tin.channels; m->Lout = touts[0].length; m->n_out = m->impl->n_outputs();
+      m->io_L = m->L; m->io_Lout = m->Lout;
     }
   }
   if (s != ADN_OK) return fail(s);
@@ -639,6 +727,7 @@ void adn_destroy(adn_model* m) {
   delete m->impl;
   free_workspace(m);
   if (m->d_blob) cudaFree(m->d_blob);
+  if (m->rs_cap) { cudaFree(m->rs_xc); cudaFree(m->rs_xm); cudaFree(m->rs_ym); cudaFree(m->rs_yr); }
   if (m->d_ola) cudaFree(m->d_ola);
   if (m->d_wf_hl) cudaFree(m->d_wf_hl);
   if (m->d_wo_hl) cudaFree(m->d_wo_hl);
@@ -664,9 +753,9 @@ adn_status adn_io_info(const adn_model* m, adn_tensor_info* in, adn_tensor_info*
   memset(in, 0, sizeof(*in));
   memset(outs, 0, sizeof(*outs));
   strncpy(in->name, "noisy_audio", sizeof(in->name) - 1);       // Export_GTCRN.py:768
-  in->dtype = m->in_dtype; in->channels = 1; in->length = m->L;
+  in->dtype = m->in_dtype; in->channels = 1; in->length = m->io_L;
   strncpy(outs->name, "denoised_audio", sizeof(outs->name) - 1); // Export_GTCRN.py:769
-  outs->dtype = m->out_dtype; outs->channels = 1; outs->length = m->Lout;
+  outs->dtype = m->out_dtype; outs->channels = 1; outs->length = m->io_Lout;
   *n_out = 1;
   return ADN_OK;
 }
@@ -702,7 +791,8 @@ adn_status adn_run(adn_model* m, const void* d_in, void* const* d_outs, int32_t 
     m->last_batch = batch;
     return r;
   }
-  return gtcrn_run(m, d_in, d_outs[0], batch, (cudaStream_t)stream, nullptr);
+  if (!m->rs_in && !m->rs_out) return gtcrn_run(m, d_in, d_outs[0], batch, (cudaStream_t)stream, nullptr);
+  return gtcrn_run_resampled(m, d_in, d_outs[0], batch, (cudaStream_t)stream);
 }
 
 adn_status adn_run_host(adn_model* m, const void* h_in, void* const* h_outs, int32_t batch) {
@@ -717,16 +807,16 @@ adn_status adn_run_host(adn_model* m, const void* h_in, void* const* h_outs, int
     if (batch > m->io_cap) {     // staging buffers for families that own their workspace
       ADN_CUDA_TRY(cudaDeviceSynchronize(), m->err);
       if (m->io_cap) { cudaFree(m->d_in); cudaFree(m->d_out); }
-      ADN_CUDA_TRY(cudaMalloc(&m->d_in, (size_t)batch * m->chans * m->L * dtype_size(m->in_dtype)), m->err);
-      ADN_CUDA_TRY(cudaMalloc(&m->d_out, (size_t)m->n_out * batch * m->chans * m->Lout * dtype_size(m->out_dtype)), m->err);
+      ADN_CUDA_TRY(cudaMalloc(&m->d_in, (size_t)batch * m->chans * m->io_L * dtype_size(m->in_dtype)), m->err);
+      ADN_CUDA_TRY(cudaMalloc(&m->d_out, (size_t)m->n_out * batch * m->chans * m->io_Lout * dtype_size(m->out_dtype)), m->err);
       m->io_cap = batch;
     }
   } else {
     s = ensure_capacity(m, batch);
     if (s != ADN_OK) return s;
   }
-  const size_t in_row = (size_t)m->chans * m->L * dtype_size(m->in_dtype);
-  const size_t out_row = (size_t)m->chans * m->Lout * dtype_size(m->out_dtype);
+  const size_t in_row = (size_t)m->chans * m->io_L * dtype_size(m->in_dtype);
+  const size_t out_row = (size_t)m->chans * m->io_Lout * dtype_size(m->out_dtype);
   if (!m->ev_h2d[0]) {
     ADN_CUDA_TRY(cudaStreamCreateWithFlags(&m->st_in, cudaStreamNonBlocking), m->err);
     ADN_CUDA_TRY(cudaStreamCreateWithFlags(&m->st_out, cudaStreamNonBlocking), m->err);
@@ -736,7 +826,7 @@ adn_status adn_run_host(adn_model* m, const void* h_in, void* const* h_outs, int
     }
   }
   cudaStream_t st = m->own_stream;
-  if (!m->impl && batch >= 64 && m->stop_after == 0) {
+  if (!m->impl && batch >= 64 && m->stop_after == 0 && !m->rs_in && !m->rs_out) {
     // Two ranges: the second half's H2D overlaps the first half's conditioning + STFT, the first
     // half's D2H overlaps the second half's ISTFT.  The backbone runs once over the whole batch
     // (its GRU kernels are latency-bound, so slicing it would cost more than the copies).

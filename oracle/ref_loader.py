@@ -82,7 +82,7 @@ def load_export_namespace(model_dir: str, script: str, patches: dict[str, str]) 
     return ns
 
 
-def load_gtcrn(input_audio_length: int = 16000, io_dtype: str = "F32"):
+def load_gtcrn(input_audio_length: int = 16000, io_dtype: str = "F32", in_rate: int = 16000, out_rate: int = 16000):
     """Build the reference GTCRN_CUSTOM wrapper (random init, eval) for one chunk length.
 
     Returns (namespace, build) where build(state_dict|None) -> wrapper module.
@@ -96,6 +96,8 @@ def load_gtcrn(input_audio_length: int = 16000, io_dtype: str = "F32"):
             "INPUT_AUDIO_LENGTH   = 32000": f"INPUT_AUDIO_LENGTH   = {int(input_audio_length)}",
             "IN_AUDIO_DTYPE       = 'INT16'": f"IN_AUDIO_DTYPE       = '{io_dtype}'",
             "OUT_AUDIO_DTYPE      = 'INT16'": f"OUT_AUDIO_DTYPE      = '{io_dtype}'",
+            "IN_SAMPLE_RATE       = 16000": f"IN_SAMPLE_RATE       = {int(in_rate)}",
+            "OUT_SAMPLE_RATE      = 16000": f"OUT_SAMPLE_RATE      = {int(out_rate)}",
         },
     )
 

@@ -400,3 +400,27 @@ def test_mf2se_oracle_resampling_matches_reference_module(L, in_rate, out_rate):
     want = int(round(L * out_rate / in_rate)) if out_rate != 48000 else mo.model_len(L, in_rate, cfg)
     assert yr.shape == yo.shape == (1, 1, want)
     assert (yr - yo).abs().max() <= 2e-6
+
+
+@needs_ref
+@pytest.mark.parametrize("L,out_rate,dt", [(16000, 44000, "INT16"), (16000, 8000, "F32"), (8000, 48000, "F32")])
+def test_gtcrn_oracle_output_resampling_matches_reference_module(L, out_rate, dt):
+    """OUT_SAMPLE_RATE != 16 kHz (Export_GTCRN.py:629-632, :671-688): down-sampling before the x32767 PCM scale,
+    up-sampling after it -- executed reference (static export) vs the restatement.  The INPUT-side resampler of the
+    restatement (:638-654) has no runnable reference configuration: the static export sizes its frame count from the
+    input-rate length (:45), the dynamic one changes the ISTFT length contract; it is restated from the forward only."""
+    import gtcrn_oracle as go
+
+    sd = go.random_state_dict(0)
+    _, build = ref_loader.load_gtcrn(L, dt, 16000, out_rate)
+    w = build(sd)
+    x = synth_audio(L, 3)
+    xin = x if dt == "F32" else torch.round(x * 32767).to(torch.int16)
+    with torch.inference_mode():
+        r = w(xin.clone())
+        o = go.gtcrn_forward(sd, xin, dt, dt, out_rate=out_rate)
+    assert r.shape == o.shape and r.dtype == o.dtype
+    if dt == "INT16":
+        assert int((r.int() - o.int()).abs().max()) <= 1
+    else:
+        assert float((r - o).abs().max()) <= 2e-6
