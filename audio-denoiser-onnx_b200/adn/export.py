@@ -24,25 +24,25 @@ def gtcrn_model(state_dict: dict, input_audio_length: int = 16000, in_dtype: str
 
 
 def export_mbr(state_dict: dict, path, hyper=None, input_audio_length: int = 66150, in_dtype: str = "INT16",
-               out_dtype: str = "INT16") -> dict[str, str]:
+               out_dtype: str = "INT16", in_rate: int = 44100, out_rate: int = 44100) -> dict[str, str]:
     """Mel-Band-Roformer (stereo) `.adn` for one static window length (counterpart of
     Mel_Band_Roformer/Stereo/Export_MelBandRoformer.py:690-735)."""
     from . import mbr_params
 
     hyper = hyper or mbr_params.MbrHyper()
-    md = mbr_params.metadata(hyper, input_audio_length, in_dtype, out_dtype)
-    modelfile.save(path, md, mbr_params.pack(state_dict, hyper, input_audio_length))
+    md = mbr_params.metadata(hyper, input_audio_length, in_dtype, out_dtype, in_rate, out_rate)
+    modelfile.save(path, md, mbr_params.pack(state_dict, hyper, input_audio_length, in_rate))
     return md
 
 
 def mbr_model(state_dict: dict, hyper=None, input_audio_length: int = 66150, in_dtype: str = "F32",
-              out_dtype: str = "F32", device_id: int = 0):
+              out_dtype: str = "F32", device_id: int = 0, in_rate: int = 44100, out_rate: int = 44100):
     from . import mbr_params
     from .model import Model
 
     hyper = hyper or mbr_params.MbrHyper()
-    md = mbr_params.metadata(hyper, input_audio_length, in_dtype, out_dtype)
-    return Model.from_tensors(md, mbr_params.pack(state_dict, hyper, input_audio_length), device_id)
+    md = mbr_params.metadata(hyper, input_audio_length, in_dtype, out_dtype, in_rate, out_rate)
+    return Model.from_tensors(md, mbr_params.pack(state_dict, hyper, input_audio_length, in_rate), device_id)
 
 
 def export_mf2se(state_dict: dict, path, hyper=None, input_audio_length: int = 48000, in_dtype: str = "INT16",

@@ -84,7 +84,15 @@ def band_layout(h: MbrHyper):
     return idx.to(torch.int64), widths, denom
 
 
-def pack(sd: dict, h: MbrHyper, input_audio_length: int) -> dict[str, np.ndarray]:
+def model_length(input_audio_length: int, in_rate: int = 44100) -> int:
+    """Window length at the 44.1 kHz model rate: F.interpolate(scale_factor=44100/in_rate) yields floor(L * scale)."""
+    if in_rate == 44100:
+        return int(input_audio_length)
+    return int(np.floor(float(input_audio_length) * float(44100 / in_rate)))
+
+
+def pack(sd: dict, h: MbrHyper, input_audio_length: int, in_rate: int = 44100) -> dict[str, np.ndarray]:
+    input_audio_length = model_length(input_audio_length, in_rate)
     if input_audio_length % h.hop:
         raise ValueError("input_audio_length must be a multiple of hop_length (441)")
     idx, widths, denom = band_layout(h)
@@ -156,22 +164,25 @@ def pack(sd: dict, h: MbrHyper, input_audio_length: int) -> dict[str, np.ndarray
     return blob
 
 
-def metadata(h: MbrHyper, input_audio_length: int, in_dtype: str = "INT16", out_dtype: str = "INT16") -> dict[str, str]:
+def metadata(h: MbrHyper, input_audio_length: int, in_dtype: str = "INT16", out_dtype: str = "INT16",
+             in_rate: int = 44100, out_rate: int = 44100) -> dict[str, str]:
     """Metadata keys of `Export_MelBandRoformer.py:728-733` + the model hyper-parameters the
     reference reads from the (absent) YAML."""
     g = stft_tables.GEOMETRY["mel_band_roformer"]
+    mlen = model_length(input_audio_length, in_rate)
+    olen = mlen if out_rate == 44100 else int(np.floor(float(mlen) * float(out_rate / 44100)))
     md = {
         "audio_metadata_version": 1, "producer": "adn.mbr_params", "model_name": "MelBandRoformer_Stereo",
         "task": "denoise", "model_family": FAMILY, "dynamic_axes": "0", "opset": 20,
         "input_audio_dtype": in_dtype, "output_audio_dtype": out_dtype,
-        "in_sample_rate": h.sample_rate, "out_sample_rate": h.sample_rate, "model_sample_rate": h.sample_rate,
+        "in_sample_rate": in_rate, "out_sample_rate": out_rate, "model_sample_rate": h.sample_rate,
         "input_audio_length": input_audio_length, "export_audio_length": input_audio_length,
-        "model_audio_length": input_audio_length, "output_audio_length": input_audio_length,
-        "input_to_output_scale": 1.0, "batch_window_seconds": 1.5, "use_batch_fold": "0",
+        "model_audio_length": mlen, "output_audio_length": olen,
+        "input_to_output_scale": float(out_rate / in_rate), "batch_window_seconds": 1.5, "use_batch_fold": "0",
         "batch_fold_inference_default": "0", "fold_window_length": 66150, "fold_input_length": 66150,
         "max_dynamic_audio_seconds": 6, "normalize_audio_default": "0", "normalize_target_rms": 4096.0,
         "window_type": g.window_type, "nfft": g.nfft, "window_length": g.win_length, "hop_length": g.hop,
-        "max_signal_length": g.n_frames(input_audio_length), "center_pad": "1", "pad_mode": "reflect",
+        "max_signal_length": g.n_frames(mlen), "center_pad": "1", "pad_mode": "reflect",
         "feature_kind": "stft_mel_band", "input_channels": 2, "output_channels": 2, "num_audio_inputs": 1,
         "mbr_dim": h.dim, "mbr_depth": h.depth, "mbr_heads": h.heads, "mbr_dim_head": h.dim_head,
         "mbr_num_bands": h.num_bands,

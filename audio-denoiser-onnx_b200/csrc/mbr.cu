@@ -193,6 +193,20 @@ attention_kernel(const float* __restrict__ qkvg, int ldq, const float* __restric
 // ---------------------------------------------------------------------------------
 constexpr int ATT2_THREADS = 1024;
 
+// helpers of the optional linear resampling either side of the model (Export_MelBandRoformer.py:631-644, :662-675)
+__global__ void rs_scale_kernel(float* __restrict__ x, long long n, float sc) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) x[i] *= sc;
+}
+__global__ void rs_convert_kernel(const float* __restrict__ src, void* __restrict__ out, int out_dtype, long long n) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float v = src[i];
+  if (out_dtype == ADN_I16) reinterpret_cast<int16_t*>(out)[i] = (int16_t)(int)fminf(fmaxf(v, -32768.0f), 32767.0f);
+  else if (out_dtype == ADN_F32) reinterpret_cast<float*>(out)[i] = v;
+  else reinterpret_cast<__half*>(out)[i] = __float2half_rn(v);
+}
+
 __host__ __device__ inline size_t att2_smem_floats(int n) {
   const int np = (n + 3) & ~3;
   size_t s_region = (size_t)n * (np + 1);
@@ -406,6 +420,10 @@ class Model : public ModelImpl {
   int device = 0, sms = 148;
   int in_dtype = ADN_F32, out_dtype = ADN_F32;
   int W = 0, T = 0, Lp = 0, pad = 4, R = 5;
+  int W_in = 0, W_final = 0, in_sr = 44100, out_sr = 44100;   // I/O window at the in / out sample rates (== W at 44.1 kHz)
+  bool rs_in = false, rs_out = false;
+  double in_scale = 1.0, out_scale = 1.0;
+  float *xr = nullptr, *yres = nullptr, *yout = nullptr;
   int D = 384, depth = 6, heads = 8, nb = 60, DI = 512, DQ = 1544, DHID = 1536, NSEL = 0, SD = 0;
   std::vector<int> din, off;     // per band input width / offset into SD
   float* d_blob = nullptr;
@@ -501,8 +519,21 @@ class Model : public ModelImpl {
         !geti("mbr_depth", depth) || !geti("mbr_heads", heads) || !geti("mbr_dim_head", dh) ||
         !geti("mbr_num_bands", nb) || !gets("input_audio_dtype", sin) || !gets("output_audio_dtype", sout))
       return false;
+    {
+      auto opt = [&](const char* k, int& v) { auto it = meta.find(k); if (it != meta.end() && !it->second.empty()) v = atoi(it->second.c_str()); };
+      int model_sr = 44100;
+      opt("in_sample_rate", in_sr); opt("out_sample_rate", out_sr); opt("model_sample_rate", model_sr);
+      if (model_sr != 44100 || in_sr <= 0 || out_sr <= 0) { err = "mel_band_roformer runs at model_sample_rate 44100"; return false; }
+    }
+    W_in = W;
+    rs_in = in_sr != 44100;
+    rs_out = out_sr != 44100;
+    in_scale = 44100.0 / (double)in_sr;            // INPUT_TO_MODEL_SCALE (:56)
+    out_scale = (double)out_sr / 44100.0;          // MODEL_TO_OUTPUT_SCALE (:57)
+    if (rs_in) W = (int)floor((double)W_in * in_scale);            // F.interpolate(scale_factor=...) output size
+    W_final = rs_out ? (int)floor((double)W * out_scale) : W;
     if (nfft != NFFT || hop != HOP || dh != DHEAD || D % 32 || W % hop) {
-      err = "mel_band_roformer needs nfft=2048, hop=441, dim_head=64, dim % 32 == 0, length % hop == 0";
+      err = "mel_band_roformer needs nfft=2048, hop=441, dim_head=64, dim % 32 == 0, model-rate length % hop == 0";
       return false;
     }
     auto pdt = [&](const std::string& s, int& o) { if (s == "F32") o = ADN_F32; else if (s == "INT16") o = ADN_I16; else if (s == "F16") o = ADN_F16; else return false; return true; };
@@ -640,6 +671,9 @@ class Model : public ModelImpl {
     free_ws();
     const long long Mf = (long long)B * T, M = (long long)nb * Mf;
     const int B2 = B * CH;
+    if ((rs_in && !alloc(xr, (size_t)B2 * W, false)) ||
+        (rs_out && (!alloc(yres, (size_t)B2 * W, false) || !alloc(yout, (size_t)B2 * W_final, false))))
+      return false;
     if (!alloc(xp, (size_t)B2 * Lp, false) || !alloc(spec, (size_t)B2 * T * LD, true) ||
         !alloc(xg, (size_t)2 * Mf * SD, false) || !alloc(rs_bs, (size_t)M, false) || !alloc(x, (size_t)M * D, false) ||
         !alloc(xpl, (size_t)2 * M * D, false) || !alloc(rn, (size_t)M, false) || !alloc(qkvg, (size_t)M * DQ, false) ||
@@ -689,14 +723,16 @@ class Model : public ModelImpl {
     memset(in, 0, sizeof(*in));
     memset(out, 0, sizeof(*out));
     strncpy(in->name, "noisy_audio", sizeof(in->name) - 1);        // Export_MelBandRoformer.py:715
-    in->dtype = in_dtype; in->channels = CH; in->length = W;
+    in->dtype = in_dtype; in->channels = CH; in->length = W_in;
     strncpy(out->name, "denoised_audio", sizeof(out->name) - 1);   // :716
-    out->dtype = out_dtype; out->channels = CH; out->length = W;
+    out->dtype = out_dtype; out->channels = CH; out->length = W_final;
   }
   size_t workspace_bytes(int batch) override {
     const size_t Mf = (size_t)batch * T, M = (size_t)nb * Mf;
     size_t f = (size_t)batch * CH * Lp + (size_t)batch * CH * T * LD + 2 * Mf * SD + 2 * M + 3 * M * D + M * DQ +
                2 * M * DI + 4 * M * DHID + Mf * 2 * SD + (size_t)batch * CH * (T + 2 * pad) * LD;
+    if (rs_in) f += (size_t)batch * CH * W;
+    if (rs_out) f += (size_t)batch * CH * ((size_t)W + W_final);
     return f * sizeof(float);
   }
   int launches(int) override { return 3 + nb + 1 + 2 * depth * 7 + 2 + nb + 2; }
@@ -713,7 +749,15 @@ class Model : public ModelImpl {
     const long long Mf = (long long)B * T, M = (long long)nb * Mf;
     const int B2 = B * CH;
     // 1-2: conditioning + STFT (reference kernel pre-scaled by 1/32768 for int16 input, :327-328)
-    gtcrn::launch_prep(d_in, in_dtype, xp, nullptr, nullptr, B2, W, Lp, NFFT / 2, 0, 1, st);
+    const void* src = d_in;
+    int src_dtype = in_dtype;
+    if (rs_in) {                                   // F.interpolate on the raw samples, then the 1/32768 the STFT kernel carries (:327-328)
+      if (adn_resample_linear(d_in, in_dtype, xr, B2, W_in, W, in_scale, st) != ADN_OK) { err = "input resampler launch failed"; return ADN_ERR_CUDA; }
+      if (in_dtype == ADN_I16) rs_scale_kernel<<<(unsigned)(((long long)B2 * W + 255) / 256), 256, 0, st>>>(xr, (long long)B2 * W, 1.0f / 32768.0f);
+      src = xr;
+      src_dtype = ADN_F32;
+    }
+    gtcrn::launch_prep(src, src_dtype, xp, nullptr, nullptr, B2, W, Lp, NFFT / 2, 0, 1, st);
     MBR_TICK("prep");
     {
       GemmArgs g;
@@ -777,9 +821,17 @@ class Model : public ModelImpl {
       const int lo = half / HOP, hi = (raw - half - 1) / HOP;
       g.A = enh; g.a_sB = (long long)(T + 2 * pad) * LD; g.a_sT = LD; g.a_t0 = lo; g.TM = hi - lo + 1;
       g.W = d_ola; g.ldw = R * LD; g.M = B2 * g.TM; g.N = HOP; g.K = R * LD;
-      g.norm = d_norm; g.norm_mul = 0; g.hop = HOP; g.shift = half; g.out_len = W; g.out_dtype = out_dtype; g.out = d_out;
+      g.norm = d_norm; g.norm_mul = 0; g.hop = HOP; g.shift = half; g.out_len = W; g.out_dtype = rs_out ? ADN_F32 : out_dtype; g.out = rs_out ? (void*)yres : d_out;
       launch_gemm_ffma(g, EPI_ISTFT, st);
       MBR_TICK("istft_gemm");
+      if (rs_out) {                                // down-sampling before the x32767 PCM scale, up-sampling after it (:662-678)
+        const long long nm = (long long)B2 * W, no = (long long)B2 * W_final;
+        const bool pcm = out_dtype == ADN_I16;
+        if (out_sr > 44100 && pcm) rs_scale_kernel<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(yres, nm, 32767.0f);
+        if (adn_resample_linear(yres, ADN_F32, yout, B2, W, W_final, out_scale, st) != ADN_OK) { err = "output resampler launch failed"; return ADN_ERR_CUDA; }
+        if (out_sr < 44100 && pcm) rs_scale_kernel<<<(unsigned)((no + 255) / 256), 256, 0, st>>>(yout, no, 32767.0f);
+        rs_convert_kernel<<<(unsigned)((no + 255) / 256), 256, 0, st>>>(yout, d_out, out_dtype, no);
+      }
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("mbr run: ") + cudaGetErrorString(e); return ADN_ERR_CUDA; }

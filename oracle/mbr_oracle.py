@@ -320,11 +320,15 @@ def mbr_core(cfg: MbrConfig, fw: dict, stft_repr: torch.Tensor, dbg: dict | None
 
 
 def mbr_forward(cfg: MbrConfig, fw: dict, audio: torch.Tensor, in_dtype="F32", out_dtype="F32",
-                dbg: dict | None = None) -> torch.Tensor:
-    """`MelBandRoformer.forward` for ONE window at native rate, no fold (:629-680).
-    audio (1, chan, W) -> (1, chan, W)."""
+                dbg: dict | None = None, in_rate: int = 44100, out_rate: int = 44100) -> torch.Tensor:
+    """`MelBandRoformer.forward` for ONE window, no fold (:629-680).  audio (1, chan, W) -> (1, chan, W_out).
+    in_rate / out_rate != 44.1 kHz: F.interpolate(scale_factor=...) on the raw input (:631-644); on the output before the
+    x32767 PCM scale when down-sampling and after it when up-sampling (:662-675)."""
     spec = SPECS["mel_band_roformer"]
-    x = audio.float().squeeze(0).unsqueeze(1).contiguous()                     # (chan,1,W)
+    x = audio.float()
+    if in_rate != 44100:
+        x = F.interpolate(x, scale_factor=float(44100 / in_rate), mode="linear", align_corners=False)
+    x = x.squeeze(0).unsqueeze(1).contiguous()                                 # (chan,1,W)
     s = stft_packed(spec, x, input_scale=(1.0 / 32768.0) if "int" in in_dtype.lower() else 1.0)
     nf = cfg.num_freqs
     rep = torch.stack((s[:, :nf], s[:, nf:]), dim=-1)                          # (chan,F,T,2)
@@ -332,10 +336,18 @@ def mbr_forward(cfg: MbrConfig, fw: dict, audio: torch.Tensor, in_dtype="F32", o
         dbg["stft"] = rep
     real, imag = mbr_core(cfg, fw, rep, dbg)
     y = istft_packed(spec, torch.cat((real, imag), dim=1)).transpose(0, 1).contiguous()
+    scale = float(out_rate / 44100)
+    if out_rate < 44100:
+        y = F.interpolate(y, scale_factor=scale, mode="linear", align_corners=False)
     if "int" in out_dtype.lower():
-        return (y * 32767.0).clamp(min=-32768.0, max=32767.0).to(torch.int16)
+        y = y * 32767.0
+    if out_rate > 44100:
+        y = F.interpolate(y, scale_factor=scale, mode="linear", align_corners=False)
+    if "int" in out_dtype.lower():
+        return y.clamp(min=-32768.0, max=32767.0).to(torch.int16)
     return y
 
 
-def mbr_forward_batch(cfg, fw, audio, in_dtype="F32", out_dtype="F32"):
-    return torch.cat([mbr_forward(cfg, fw, audio[i:i + 1], in_dtype, out_dtype) for i in range(audio.shape[0])], dim=0)
+def mbr_forward_batch(cfg, fw, audio, in_dtype="F32", out_dtype="F32", in_rate: int = 44100, out_rate: int = 44100):
+    return torch.cat([mbr_forward(cfg, fw, audio[i:i + 1], in_dtype, out_dtype, in_rate=in_rate, out_rate=out_rate)
+                      for i in range(audio.shape[0])], dim=0)

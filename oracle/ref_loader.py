@@ -129,7 +129,7 @@ def load_gtcrn(input_audio_length: int = 16000, io_dtype: str = "F32", in_rate: 
     return ns, build
 
 
-def load_mbr(input_audio_length: int, io_dtype: str = "F32"):
+def load_mbr(input_audio_length: int, io_dtype: str = "F32", out_rate: int = 44100):
     """Reference Mel-Band-Roformer (stereo) wrapper for one un-folded window.
 
     Returns (namespace, build) with build(state_dict, **model_kwargs) -> module.  The
@@ -145,6 +145,7 @@ def load_mbr(input_audio_length: int, io_dtype: str = "F32"):
             "USE_BATCH_FOLD       = True": "USE_BATCH_FOLD       = False",
             "IN_AUDIO_DTYPE        = 'INT16'": f"IN_AUDIO_DTYPE        = '{io_dtype}'",
             "OUT_AUDIO_DTYPE       = 'INT16'": f"OUT_AUDIO_DTYPE       = '{io_dtype}'",
+            "OUT_SAMPLE_RATE   = 44100": f"OUT_SAMPLE_RATE   = {int(out_rate)}",
         },
     )
 

@@ -198,6 +198,33 @@ def test_mbr_oracle_matches_reference_module():
     assert (yr - yo).abs().max() <= 1e-6
 
 
+@needs_ref
+@pytest.mark.parametrize("L,out_rate,dt", [(4410, 48000, "INT16"), (4410, 16000, "F32"), (4410, 22050, "INT16")])
+def test_mbr_oracle_output_resampling_matches_reference_module(L, out_rate, dt):
+    """OUT_SAMPLE_RATE != 44.1 kHz (Export_MelBandRoformer.py:662-678): down-sampling before the x32767 PCM scale,
+    up-sampling after it -- executed reference vs the restatement.  The INPUT-side resampler (:631-644) has no runnable
+    reference configuration (MAX_SIGNAL_LENGTH is sized from the input-rate length, :50): restated from the forward only."""
+    import mbr_oracle as mo
+    from make_golden import mbr_kwargs
+
+    cfg = mo.MbrConfig(depth=1)
+    sd = mo.random_state_dict(cfg, 3)
+    _, build = ref_loader.load_mbr(L, dt, out_rate)
+    m = build(sd, **mbr_kwargs(cfg))
+    fw = mo.fuse(sd, cfg)
+    g = torch.Generator().manual_seed(1)
+    x = (torch.rand(1, 2, L, generator=g) * 2 - 1) * 0.5
+    xin = x if dt == "F32" else torch.round(x * 32767).to(torch.int16)
+    with torch.inference_mode():
+        yr = m(xin.clone())
+        yo = mo.mbr_forward(cfg, fw, xin, dt, dt, out_rate=out_rate)
+    assert yr.shape == yo.shape == (1, 2, int(np.floor(L * float(out_rate / 44100)))) and yr.dtype == yo.dtype
+    if dt == "INT16":
+        assert int((yr.int() - yo.int()).abs().max()) <= 1
+    else:
+        assert float((yr - yo).abs().max()) <= 1e-6
+
+
 # ----------------------------------------------------------------------------- MossFormer2-SE-48K
 @pytest.mark.parametrize("fixture,dt", [("mf2se_f32_L13440_l2", "F32"), ("mf2se_int16_L11520_l2", "INT16")])
 def test_mf2se_oracle_matches_golden(fixture, dt, golden_dir):
