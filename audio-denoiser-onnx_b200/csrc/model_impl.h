@@ -42,3 +42,7 @@ ModelImpl* mf2se_create(const std::map<std::string, std::string>& meta, const st
 // MossFormer2-SS-16K: csrc/mf2ss.cu
 ModelImpl* mf2ss_create(const std::map<std::string, std::string>& meta, const std::map<std::string, TensorRef>& index,
                         const float* h_blob, float* d_blob, int device, int sms, std::string& err);
+
+// MossFormerGAN-SE-16K: csrc/mfgan.cu
+ModelImpl* mfgan_create(const std::map<std::string, std::string>& meta, const std::map<std::string, TensorRef>& index,
+                        const float* h_blob, float* d_blob, int device, int sms, std::string& err);

@@ -1,0 +1,56 @@
+// TEST INFRASTRUCTURE ONLY -- host executor for the MossFormerGAN-SE-16K launch sequence.
+// Instantiates gan::forward (csrc/mfgan_ops.cuh, the sequence libadn runs on the GPU) with a plain loop per
+// operator, so every functor's index arithmetic and the buffer plumbing are checked against the oracle on a
+// machine without a GPU (tests/test_mfgan_host.py).  Never linked into libadn.so.
+#include "mfgan_ops.cuh"
+
+#include <map>
+#include <string>
+#include <vector>
+
+typedef void (*dump_fn)(const char* name, const float* data, long long count);
+
+struct HostExec {
+  dump_fn dump = nullptr;
+  int launches = 0;
+  template <class F>
+  void run(long long n, const F& f) {
+    ++launches;
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < n; ++i) f(i);
+  }
+  void mark(const char* tag, const char* name, const float* p, long long count) {
+    if (!dump) return;
+    std::string key = tag[0] ? std::string(tag) + "." + name : std::string(name);
+    dump(key.c_str(), p, count);
+  }
+};
+
+extern "C" int mfgan_host_forward(const char* const* names, const unsigned long long* offsets, const unsigned long long* counts,
+                                  int n_tensors, const float* blob, int layers, int B, int T, const float* feat, float* mask,
+                                  float* cplx, dump_fn dump, char* errbuf, int errlen) {
+  std::map<std::string, std::pair<unsigned long long, unsigned long long>> index;
+  for (int i = 0; i < n_tensors; ++i) index[names[i]] = {offsets[i], counts[i]};
+  std::string err;
+  auto lk = [&](const char* name, size_t expect) -> const float* {
+    auto it = index.find(name);
+    if (it == index.end() || (expect && it->second.second != expect)) {
+      if (err.empty()) err = std::string("tensor '") + name + "' missing or wrong size";
+      return nullptr;
+    }
+    return blob + it->second.first;
+  };
+  gan::Weights W;
+  if (!gan::bind(W, layers, T, lk)) {
+    snprintf(errbuf, errlen, "%s", err.c_str());
+    return -1;
+  }
+  std::vector<std::vector<float>> bufs;
+  auto alloc = [&](size_t n) { bufs.emplace_back(n ? n : 1, 0.0f); return bufs.back().data(); };
+  gan::Workspace ws;
+  if (!gan::alloc_ws(ws, B, T, alloc)) return -2;
+  HostExec ex;
+  ex.dump = dump;
+  gan::forward(ex, ws, W, feat, mask, cplx, B, T);
+  return ex.launches;
+}
