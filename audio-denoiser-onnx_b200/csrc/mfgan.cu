@@ -4,7 +4,7 @@
 //   -> dense encoder, 6 x (intra path, inter path, triple attention), mask / complex decoders           [mfgan_ops.cuh]
 //   -> mask * compressed + complex, decompress (:863-868) -> ISTFT -> x norm factor, output rule (:880-897) [ends.cu]
 // First-correct implementation: one grid per operator (fp32 FFMA, one output per thread), all intermediates in HBM.
-#include "mfgan_ops.cuh"
+#include "mfgan_gemm.cuh"
 
 #include "common.cuh"
 #include "model_impl.h"
@@ -35,6 +35,25 @@ struct CudaExec {
     ++launches;
     if (tick) tick(tick_ctx, op_name(f));
   }
+  // contractions run on the shared-memory tiled GEMM (mfgan_gemm.cuh) instead of the one-output-per-thread functor
+  template <class F>
+  void run_gemm(long long n, const F& f) {
+    if (n <= 0) return;
+    GemmOp ops[3];
+    const int k = translate(f, n, ops);
+    for (int i = 0; i < k; ++i) launch_gemm(ops[i], st);
+    launches += k;
+    if (tick) tick(tick_ctx, op_name(f));
+  }
+  void run(long long n, const Linear& f) { run_gemm(n, f); }
+  void run(long long n, const SimLocal& f) { run_gemm(n, f); }
+  void run(long long n, const SimCross& f) { run_gemm(n, f); }
+  void run(long long n, const LinKV& f) { run_gemm(n, f); }
+  void run(long long n, const Att& f) { run_gemm(n, f); }
+  void run(long long n, const Conv2d& f) {
+    if (f.Cout >= 16 && f.Cin % GK == 0) run_gemm(n, f);
+    else run<Conv2d>(n, f);
+  }
   void mark(const char* tag, const char* name, const float* p, long long count) {
     if (!capture || !dumps) return;
     std::string key = tag[0] ? std::string(tag) + "." + name : std::string(name);
@@ -46,14 +65,34 @@ struct CudaExec {
   template <class F> static const char* op_name(const F&) { return "gan_op"; }
   static const char* op_name(const Linear&) { return "gan_linear"; }
   static const char* op_name(const Conv2d&) { return "gan_conv2d"; }
-  static const char* op_name(const DwConv&) { return "gan_dwconv"; }
+  static const char* op_name(const DwConv&) { return "gan_dw_conv"; }
   static const char* op_name(const Att&) { return "gan_att"; }
   static const char* op_name(const SimLocal&) { return "gan_sim_local"; }
   static const char* op_name(const SimCross&) { return "gan_sim_cross"; }
-  static const char* op_name(const LinKV&) { return "gan_lin_kv"; }
+  static const char* op_name(const LinKV&) { return "gan_lin_k_v"; }
   static const char* op_name(const TaScores&) { return "gan_ta_scores"; }
-  static const char* op_name(const TaAV&) { return "gan_ta_av"; }
-  static const char* op_name(const GateConvT&) { return "gan_gate_convt"; }
+  static const char* op_name(const TaAV&) { return "gan_ta_a_v"; }
+  static const char* op_name(const GateConvT&) { return "gan_gate_conv_t"; }
+  static const char* op_name(const RowStats&) { return "gan_row_stats"; }
+  static const char* op_name(const Gather&) { return "gan_gather"; }
+  static const char* op_name(const Shift&) { return "gan_shift"; }
+  static const char* op_name(const OffsetRot&) { return "gan_offset_rot"; }
+  static const char* op_name(const GateOut&) { return "gan_gate_out"; }
+  static const char* op_name(const SePool1&) { return "gan_se_pool1"; }
+  static const char* op_name(const SePool2&) { return "gan_se_pool2"; }
+  static const char* op_name(const SeMlp&) { return "gan_se_mlp"; }
+  static const char* op_name(const ScaleRes&) { return "gan_scale_res"; }
+  static const char* op_name(const GroupPart&) { return "gan_group_part"; }
+  static const char* op_name(const GroupFin&) { return "gan_group_fin"; }
+  static const char* op_name(const GroupNorm&) { return "gan_group_norm"; }
+  static const char* op_name(const Softmax&) { return "gan_softmax"; }
+  static const char* op_name(const InPart&) { return "gan_in_part"; }
+  static const char* op_name(const InFin&) { return "gan_in_fin"; }
+  static const char* op_name(const InApply&) { return "gan_in_apply"; }
+  static const char* op_name(const FeatConv&) { return "gan_feat_conv"; }
+  static const char* op_name(const CopyCh&) { return "gan_copy_ch"; }
+  static const char* op_name(const MaskTail&) { return "gan_mask_tail"; }
+  static const char* op_name(const CplxTail&) { return "gan_cplx_tail"; }
 };
 
 class Model : public ModelImpl {
@@ -180,7 +219,7 @@ class Model : public ModelImpl {
     return f * sizeof(float);
   }
   int launches(int batch) override {
-    const int per_dense = DEPTH * 7, per_path = 26, per_ta = 9;
+    const int per_dense = DEPTH * 7, per_path = 28, per_ta = 11;   // Att is three GEMM launches
     const int bb = 8 + per_dense + layers * (2 * per_path + per_ta) + 2 * (6 + per_dense);
     return 6 + ((batch + SUB - 1) / SUB) * bb;
   }

@@ -71,16 +71,23 @@ struct Linear {
   }
 };
 
-// (mean, rstd) of each row over K values: LayerNorm without affine / the per-pixel channel norm
+// (mean, rstd) of each row over K values: LayerNorm without affine / the per-pixel channel norm (K % 4 == 0, 16-byte rows)
+struct alignas(16) F4 { float x, y, z, w; };
 struct RowStats {
   const float* in; int ldi; int K; float* stat;
   GAN_HD void operator()(long long r) const {
-    const float* x = in + r * ldi;
+    const F4* x = reinterpret_cast<const F4*>(in + r * ldi);
     float s = 0.f;
-    for (int k = 0; k < K; ++k) s += x[k];
+    for (int k = 0; k < K / 4; ++k) { const F4 v = x[k]; s += v.x; s += v.y; s += v.z; s += v.w; }
     const float mu = s / (float)K;
     float v = 0.f;
-    for (int k = 0; k < K; ++k) { const float d = x[k] - mu; v += d * d; }
+    for (int k = 0; k < K / 4; ++k) {
+      const F4 q = x[k];
+      float d = q.x - mu; v += d * d;
+      d = q.y - mu; v += d * d;
+      d = q.z - mu; v += d * d;
+      d = q.w - mu; v += d * d;
+    }
     stat[2 * r] = mu;
     stat[2 * r + 1] = 1.0f / sqrtf(v / (float)K + EPS);
   }
@@ -102,19 +109,28 @@ struct Gather {
 };
 
 // dst[n, s, c] = res[n, s, c] + src[n, s, c] + sum_k taps[k, c] * src[n, s + k - padl, c]   (zero outside 0..S-1)
+// Thread order: 32 channels x 8 positions per 256 threads, so a block reads (8 + k - 1) rows of 128 bytes once from L2
+// and re-uses them from L1 (count = dw_count(N, S, Cn); Cn % 32 == 0).
+constexpr int DWS = 8;
+GAN_HD long long dw_count(long long N, int S, int Cn) { return N * ((S + DWS - 1) / DWS) * DWS * Cn; }
 struct DwConv {
   const float* src; int lds; const float* res; int ldr; const float* taps; int k, padl; float* dst; int ldd; int use_pm;
   PixMap pm; int S, Cn;
   GAN_HD void operator()(long long i) const {
-    const int c = (int)(i % Cn); const long long r = i / Cn; const int s = (int)(r % S); const long long n = r / S;
-    float acc = src[r * lds + c];
-    if (res) acc += res[r * ldr + c];
+    const int cl = (int)(i % 32); long long r = i / 32; const int sl = (int)(r % DWS); r /= DWS;
+    const int cg = Cn / 32, ch = (int)(r % cg); r /= cg;
+    const int sg = (S + DWS - 1) / DWS, sh = (int)(r % sg); const long long n = r / sg;
+    const int c = ch * 32 + cl, s = sh * DWS + sl;
+    if (s >= S) return;
+    const long long row = n * S + s;
+    float acc = src[row * lds + c];
+    if (res) acc += res[row * ldr + c];
     float m = 0.f;
     for (int j = 0; j < k; ++j) {
       const int sj = s + j - padl;
       if (sj >= 0 && sj < S) m += taps[j * Cn + c] * src[(n * S + sj) * lds + c];
     }
-    const long long d = use_pm ? pm.pix(n, s) * ldd : r * ldd;
+    const long long d = use_pm ? pm.pix(n, s) * ldd : row * ldd;
     dst[d + c] = acc + m;
   }
 };
@@ -283,20 +299,28 @@ struct ScaleRes {
 
 // LayerNorm over (channel group, sub-band) per (window, frame) (:751-784): stats, then affine (+ residual)
 struct GroupBounds { int n; int lo[13]; };
-struct GroupStats {
-  const float* x; int ld; GroupBounds g; float* stat; int Fw;
+// stats in two steps: per (window, frame, sub-band, group) double sums over the group's channels, then over sub-bands
+struct GroupPart {
+  const float* x; int ld; GroupBounds g; double* part; 
+  GAN_HD void operator()(long long i) const {
+    const int gi = (int)(i % g.n); const long long p = i / g.n;
+    const float* v = x + p * ld;
+    double s = 0.0, s2 = 0.0;
+    for (int c = g.lo[gi]; c < g.lo[gi + 1]; ++c) { const double d = (double)v[c]; s += d; s2 += d * d; }
+    part[2 * i] = s; part[2 * i + 1] = s2;
+  }
+};
+struct GroupFin {
+  const double* part; GroupBounds g; float* stat; int Fw;
   GAN_HD void operator()(long long i) const {
     const int gi = (int)(i % g.n); const long long bt = i / g.n;
-    const int lo = g.lo[gi], hi = g.lo[gi + 1];
-    const float* p = x + bt * Fw * ld;
-    double s = 0.0;
-    for (int f = 0; f < Fw; ++f) for (int c = lo; c < hi; ++c) s += (double)p[f * ld + c];
-    const double cnt = (double)Fw * (hi - lo);
-    const float mu = (float)(s / cnt);
-    double v = 0.0;
-    for (int f = 0; f < Fw; ++f) for (int c = lo; c < hi; ++c) { const float d = p[f * ld + c] - mu; v += (double)(d * d); }
-    stat[2 * i] = mu;
-    stat[2 * i + 1] = 1.0f / sqrtf((float)(v / cnt) + EPS);
+    double s = 0.0, s2 = 0.0;
+    for (int f = 0; f < Fw; ++f) { const double* p = part + 2 * ((bt * Fw + f) * g.n + gi); s += p[0]; s2 += p[1]; }
+    const double cnt = (double)Fw * (g.lo[gi + 1] - g.lo[gi]), mu = s / cnt;
+    double var = s2 / cnt - mu * mu;
+    var = var > 0.0 ? var : 0.0;
+    stat[2 * i] = (float)mu;
+    stat[2 * i + 1] = (float)(1.0 / sqrt(var + (double)EPS));
   }
 };
 struct GroupNorm {
@@ -548,7 +572,7 @@ bool bind(Weights& W, int layers, int T, Lookup& lk) {
 struct Workspace {
   float *skip, *o201, *h201, *p201, *x, *xa, *xb, *pst, *seq, *huv, *fh, *fp, *iu, *t0, *sh, *rst, *mhuv, *heads, *A, *Ac, *kv,
       *att, *go, *ho, *separt, *sepool, *sescale, *qkv, *gst, *sc, *av, *pr, *ist, *xm;
-  double* dpart;
+  double *dpart, *gpart;
 };
 template <class Alloc>
 bool alloc_ws(Workspace& w, int B, int T, Alloc& alloc) {
@@ -568,6 +592,9 @@ bool alloc_ws(Workspace& w, int B, int T, Alloc& alloc) {
   float* d = alloc((size_t)B * T * C * 2 * 2);     // doubles
   ok = ok && d;
   w.dpart = reinterpret_cast<double*>(d);
+  float* d2 = alloc((size_t)px * 12 * 2 * 2);      // doubles
+  ok = ok && d2;
+  w.gpart = reinterpret_cast<double*>(d2);
   return ok;
 }
 
@@ -592,7 +619,7 @@ void dense_block(Exec& ex, const Workspace& w, const DenseW& d, int B, int T, in
     ex.run(px * C, Linear{w.o201, C, nullptr, d.fl_w[i], d.fl_b[i], w.h201, C, C, C, ACT_RELU, nullptr});
     ex.run(px * C, Linear{w.h201, C, nullptr, d.fp_w[i], nullptr, w.p201, C, C, C, ACT_NONE, nullptr});
     float* dst = i + 1 < DEPTH ? w.skip + (DEPTH - 1 - i) * C : out;
-    ex.run(px * C, DwConv{w.p201, C, w.o201, C, d.fm_w[i], 2 * DLORDER - 1, DLORDER - 1, dst, i + 1 < DEPTH ? SKIPC : C, 0, PixMap{1, 0, 0, 0},
+    ex.run(dw_count((long long)B * T, Fw, C), DwConv{w.p201, C, w.o201, C, d.fm_w[i], 2 * DLORDER - 1, DLORDER - 1, dst, i + 1 < DEPTH ? SKIPC : C, 0, PixMap{1, 0, 0, 0},
                           Fw, C});
   }
 }
@@ -608,18 +635,18 @@ void path(Exec& ex, const Workspace& w, const Weights& W, const PathW& p, const 
   ex.run(N * S * PI, Gather{xin, w.pst, pm, p.gw, p.gb, w.seq, S});
   ex.run(N * S, RowStats{w.seq, PI, PI, w.rst});
   ex.run(N * S * 2 * UV, Linear{w.seq, PI, w.rst, p.uv_w, p.uv_b, w.att, 2 * UV, PI, 2 * UV, ACT_SILU, nullptr});
-  ex.run(N * S * 2 * UV, DwConv{w.att, 2 * UV, nullptr, 0, p.uv_c, DW, DW / 2, w.huv, 2 * UV, 0, pm, S, 2 * UV});
+  ex.run(dw_count(N, S, 2 * UV), DwConv{w.att, 2 * UV, nullptr, 0, p.uv_c, DW, DW / 2, w.huv, 2 * UV, 0, pm, S, 2 * UV});
   ex.mark(tag, "huv", w.huv, N * S * 2 * UV);
   ex.run(N * S * UV, Linear{w.huv, 2 * UV, nullptr, p.rl_w, p.rl_b, w.fh, UV, UV, UV, ACT_RELU, nullptr});
   ex.run(N * S * UV, Linear{w.fh, UV, nullptr, p.rp_w, nullptr, w.fp, UV, UV, UV, ACT_NONE, nullptr});
-  ex.run(N * S * UV, DwConv{w.fp, UV, w.huv, 2 * UV, p.rm_w, 2 * LORDER - 1, LORDER - 1, w.iu, UV, 0, pm, S, UV});
+  ex.run(dw_count(N, S, UV), DwConv{w.fp, UV, w.huv, 2 * UV, p.rm_w, 2 * LORDER - 1, LORDER - 1, w.iu, UV, 0, pm, S, UV});
   ex.run(N * Q * C, GateConvT{w.iu, UV, w.huv + UV, 2 * UV, p.lin_w, p.lin_b, w.t0, S, Q});
   ex.mark(tag, "lin", w.t0, N * Q * C);
   // MossFormer block on t0 (N, Q, 64)
   ex.run(N * Q * C, Shift{w.t0, w.sh, Q});
   ex.run(N * Q, RowStats{w.sh, C, C, w.rst});
   ex.run(N * Q * HUV, Linear{w.sh, C, w.rst, p.mf.in_w, p.mf.in_b, w.heads, HUV, C, HUV, ACT_SILU, nullptr});
-  ex.run(N * Q * HUV, DwConv{w.heads, HUV, nullptr, 0, p.mf.in_c, DW, DW / 2, w.mhuv, HUV, 0, pm, Q, HUV});
+  ex.run(dw_count(N, Q, HUV), DwConv{w.heads, HUV, nullptr, 0, p.mf.in_c, DW, DW / 2, w.mhuv, HUV, 0, pm, Q, HUV});
   ex.mark(tag, "mf.huv", w.mhuv, N * Q * HUV);
   ex.run(N * Q * 4 * QK, OffsetRot{w.mhuv, p.mf.gamma, p.mf.beta, W.rot_cos, W.rot_sin, w.heads, Q});
   ex.run(N * Q * Q, SimLocal{w.heads, w.A, Q});
@@ -630,7 +657,7 @@ void path(Exec& ex, const Workspace& w, const Weights& W, const PathW& p, const 
   ex.run(N * Q * (HID / 2), GateOut{w.att, w.mhuv, w.go});
   ex.run(N * Q, RowStats{w.go, HID / 2, HID / 2, w.rst});
   ex.run(N * Q * C, Linear{w.go, HID / 2, w.rst, p.mf.out_w, p.mf.out_b, w.ho, C, HID / 2, C, ACT_SILU, nullptr});
-  ex.run(N * Q * C, DwConv{w.ho, C, w.t0, C, p.mf.out_c, DW, DW / 2, w.pr, C, 1, pm, Q, C});     // back to the channel-last map
+  ex.run(dw_count(N, Q, C), DwConv{w.ho, C, w.t0, C, p.mf.out_c, DW, DW / 2, w.pr, C, 1, pm, Q, C});     // back to the channel-last map
   // SE (:689-696) + residual
   ex.run((long long)B * T * C, SePool1{w.pr, w.separt, FQ});
   ex.run((long long)B * C, SePool2{w.separt, w.sepool, T, FQ});
@@ -644,13 +671,15 @@ void triple_attention(Exec& ex, const Workspace& w, const AttW& a, const float* 
   const long long px = (long long)B * T * FQ;
   GroupBounds g12{12, {0, 6, 12, 18, 24, 30, 36, 42, 48, 64, 80, 96, 112}}, g1{1, {0, 64}};
   ex.run(px * QKV, Linear{xin, C, nullptr, a.w, a.b, w.qkv, QKV, C, QKV, ACT_PRELU, a.a});
-  ex.run((long long)B * T * 12, GroupStats{w.qkv, QKV, g12, w.gst, FQ});
+  ex.run(px * 12, GroupPart{w.qkv, QKV, g12, w.gpart});
+  ex.run((long long)B * T * 12, GroupFin{w.gpart, g12, w.gst, FQ});
   ex.run(px * QKV, GroupNorm{w.qkv, QKV, g12, w.gst, a.g, a.beta, nullptr, w.qkv, FQ});
   ex.run((long long)B * HEADS * T * T, TaScores{w.qkv, w.sc, T, FQ});
   ex.run((long long)B * HEADS * T, Softmax{w.sc, T});
   ex.run(px * C, TaAV{w.sc, w.qkv, w.av, T, FQ});
   ex.run(px * C, Linear{w.av, C, nullptr, a.p_w, a.p_b, w.pr, C, C, C, ACT_PRELU, a.p_a});
-  ex.run((long long)B * T, GroupStats{w.pr, C, g1, w.gst, FQ});
+  ex.run(px, GroupPart{w.pr, C, g1, w.gpart});
+  ex.run((long long)B * T, GroupFin{w.gpart, g1, w.gst, FQ});
   ex.run(px * C, GroupNorm{w.pr, C, g1, w.gst, a.p_g, a.p_beta, xin, xout, FQ});
 }
 

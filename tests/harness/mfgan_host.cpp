@@ -2,7 +2,7 @@
 // Instantiates gan::forward (csrc/mfgan_ops.cuh, the sequence libadn runs on the GPU) with a plain loop per
 // operator, so every functor's index arithmetic and the buffer plumbing are checked against the oracle on a
 // machine without a GPU (tests/test_mfgan_host.py).  Never linked into libadn.so.
-#include "mfgan_ops.cuh"
+#include "mfgan_gemm.cuh"
 
 #include <map>
 #include <string>
@@ -19,6 +19,25 @@ struct HostExec {
 #pragma omp parallel for schedule(static)
     for (long long i = 0; i < n; ++i) f(i);
   }
+  // use_gemm: the contractions go through translate() + gemm_ref, i.e. the GemmOp the CUDA executor launches
+  bool use_gemm = false;
+  template <class F>
+  void run_gemm(long long n, const F& f) {
+    if (!use_gemm) { run<F>(n, f); return; }
+    ++launches;
+    gan::GemmOp ops[3];
+    const int k = gan::translate(f, n, ops);
+    for (int i = 0; i < k; ++i) gan::gemm_ref(ops[i]);
+  }
+  void run(long long n, const gan::Linear& f) { run_gemm(n, f); }
+  void run(long long n, const gan::SimLocal& f) { run_gemm(n, f); }
+  void run(long long n, const gan::SimCross& f) { run_gemm(n, f); }
+  void run(long long n, const gan::LinKV& f) { run_gemm(n, f); }
+  void run(long long n, const gan::Att& f) { run_gemm(n, f); }
+  void run(long long n, const gan::Conv2d& f) {
+    if (f.Cout >= 16 && f.Cin % 16 == 0) run_gemm(n, f);
+    else run<gan::Conv2d>(n, f);
+  }
   void mark(const char* tag, const char* name, const float* p, long long count) {
     if (!dump) return;
     std::string key = tag[0] ? std::string(tag) + "." + name : std::string(name);
@@ -28,7 +47,7 @@ struct HostExec {
 
 extern "C" int mfgan_host_forward(const char* const* names, const unsigned long long* offsets, const unsigned long long* counts,
                                   int n_tensors, const float* blob, int layers, int B, int T, const float* feat, float* mask,
-                                  float* cplx, dump_fn dump, char* errbuf, int errlen) {
+                                  float* cplx, dump_fn dump, char* errbuf, int errlen, int use_gemm) {
   std::map<std::string, std::pair<unsigned long long, unsigned long long>> index;
   for (int i = 0; i < n_tensors; ++i) index[names[i]] = {offsets[i], counts[i]};
   std::string err;
@@ -51,6 +70,7 @@ extern "C" int mfgan_host_forward(const char* const* names, const unsigned long 
   if (!gan::alloc_ws(ws, B, T, alloc)) return -2;
   HostExec ex;
   ex.dump = dump;
+  ex.use_gemm = use_gemm != 0;
   gan::forward(ex, ws, W, feat, mask, cplx, B, T);
   return ex.launches;
 }

@@ -15,6 +15,7 @@ import mfgan_oracle as go
 ROOT = Path(__file__).resolve().parent.parent
 SRC = ROOT / "tests" / "harness" / "mfgan_host.cpp"
 HDR = ROOT / "audio-denoiser-onnx_b200" / "csrc" / "mfgan_ops.cuh"
+HDR2 = HDR.parent / "mfgan_gemm.cuh"
 LIB = ROOT / "tests" / "_build" / "libmfgan_host.so"
 DUMP = C.CFUNCTYPE(None, C.c_char_p, C.POINTER(C.c_float), C.c_longlong)
 
@@ -22,7 +23,7 @@ DUMP = C.CFUNCTYPE(None, C.c_char_p, C.POINTER(C.c_float), C.c_longlong)
 @pytest.fixture(scope="module")
 def host_lib():
     LIB.parent.mkdir(exist_ok=True)
-    if not LIB.exists() or LIB.stat().st_mtime < max(SRC.stat().st_mtime, HDR.stat().st_mtime):
+    if not LIB.exists() or LIB.stat().st_mtime < max(SRC.stat().st_mtime, HDR.stat().st_mtime, HDR2.stat().st_mtime):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-fopenmp", "-shared", "-I", str(HDR.parent), str(SRC), "-o", str(LIB)],
                        check=True)
     lib = C.CDLL(str(LIB))
@@ -30,7 +31,7 @@ def host_lib():
     return lib
 
 
-def run_host(lib, blob: dict, layers: int, feat: torch.Tensor, T: int):
+def run_host(lib, blob: dict, layers: int, feat: torch.Tensor, T: int, use_gemm: bool = False):
     from adn import modelfile
 
     index, payload = modelfile.flatten(blob)
@@ -49,13 +50,15 @@ def run_host(lib, blob: dict, layers: int, feat: torch.Tensor, T: int):
 
     err = C.create_string_buffer(256)
     fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
-    rc = lib.mfgan_host_forward(names, offs, cnts, n, fp(payload), layers, B, T, fp(f), fp(mask), fp(cplx), DUMP(cb), err, 256)
+    rc = lib.mfgan_host_forward(names, offs, cnts, n, fp(payload), layers, B, T, fp(f), fp(mask), fp(cplx), DUMP(cb), err, 256, int(use_gemm))
     assert rc > 0, err.value.decode()
     return mask, cplx, dumps, rc
 
 
-@pytest.mark.parametrize("L,B", [(2400, 2), (1250, 1)])
-def test_host_sequence_matches_oracle(L, B, host_lib):
+@pytest.mark.parametrize("L,B,use_gemm", [(2400, 2, False), (1250, 1, False), (2400, 2, True), (850, 1, True)])
+def test_host_sequence_matches_oracle(L, B, use_gemm, host_lib):
+    """use_gemm: the contractions (Linear, the three attention branches, the convs) run as the GemmOps that
+    csrc/mfgan_gemm.cuh `translate()` hands to the tiled CUDA GEMM, evaluated by plain loops."""
     from adn import mfgan_params
 
     cfg = go.GanConfig(layers=2)
@@ -70,7 +73,7 @@ def test_host_sequence_matches_oracle(L, B, host_lib):
     assert T == cfg.n_frames(L)
     blob = mfgan_params.pack(sd, h, L)
     feat = dbg["feat"].transpose(-1, -2).contiguous()                  # (B, 3, T, 201)
-    mask, cplx, d, launches = run_host(host_lib, blob, 2, feat, T)
+    mask, cplx, d, launches = run_host(host_lib, blob, 2, feat, T, use_gemm)
     Fq, E = 101, 64
     rows = []
 
@@ -109,4 +112,4 @@ def test_launch_count_matches_model_claim(host_lib):
     feat = torch.zeros(1, 3, T, 201)
     feat[:, 0] = 1.0
     _, _, _, launches = run_host(host_lib, mfgan_params.pack(sd, h, L), 1, feat, T)
-    assert launches == 8 + 28 + 1 * (2 * 26 + 9) + 2 * (6 + 28)
+    assert launches == 8 + 28 + 1 * (2 * 26 + 11) + 2 * (6 + 28)      # + 2 per path on the GPU: Att is three GEMMs
