@@ -50,6 +50,9 @@ struct CudaExec {
   void run(long long n, const SimCross& f) { run_gemm(n, f); }
   void run(long long n, const LinKV& f) { run_gemm(n, f); }
   void run(long long n, const Att& f) { run_gemm(n, f); }
+  void run(long long n, const GateConvT& f) { run_gemm(n, f); }
+  void run(long long n, const TaScores& f) { run_gemm(n, f); }
+  void run(long long n, const TaAV& f) { run_gemm(n, f); }
   void run(long long n, const Conv2d& f) {
     if (f.Cout >= 16 && f.Cin % GK == 0) run_gemm(n, f);
     else run<Conv2d>(n, f);
@@ -65,7 +68,7 @@ struct CudaExec {
   template <class F> static const char* op_name(const F&) { return "gan_op"; }
   static const char* op_name(const Linear&) { return "gan_linear"; }
   static const char* op_name(const Conv2d&) { return "gan_conv2d"; }
-  static const char* op_name(const DwConv&) { return "gan_dw_conv"; }
+  template <int KT> static const char* op_name(const DwConv<KT>&) { return "gan_dw_conv"; }
   static const char* op_name(const Att&) { return "gan_att"; }
   static const char* op_name(const SimLocal&) { return "gan_sim_local"; }
   static const char* op_name(const SimCross&) { return "gan_sim_cross"; }

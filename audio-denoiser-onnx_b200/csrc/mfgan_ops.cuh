@@ -109,29 +109,40 @@ struct Gather {
 };
 
 // dst[n, s, c] = res[n, s, c] + src[n, s, c] + sum_k taps[k, c] * src[n, s + k - padl, c]   (zero outside 0..S-1)
-// Thread order: 32 channels x 8 positions per 256 threads, so a block reads (8 + k - 1) rows of 128 bytes once from L2
-// and re-uses them from L1 (count = dw_count(N, S, Cn); Cn % 32 == 0).
+// One thread = one channel x DWS consecutive positions: the KT taps and the DWS + KT - 1 inputs sit in registers
+// (KT * DWS FMAs for DWS + 2 KT - 1 loads); adjacent threads = adjacent channels (count = dw_count(N, S, Cn)).
 constexpr int DWS = 8;
-GAN_HD long long dw_count(long long N, int S, int Cn) { return N * ((S + DWS - 1) / DWS) * DWS * Cn; }
+GAN_HD long long dw_count(long long N, int S, int Cn) { return N * ((S + DWS - 1) / DWS) * Cn; }
+template <int KT>
 struct DwConv {
-  const float* src; int lds; const float* res; int ldr; const float* taps; int k, padl; float* dst; int ldd; int use_pm;
+  const float* src; int lds; const float* res; int ldr; const float* taps; float* dst; int ldd; int use_pm;
   PixMap pm; int S, Cn;
   GAN_HD void operator()(long long i) const {
-    const int cl = (int)(i % 32); long long r = i / 32; const int sl = (int)(r % DWS); r /= DWS;
-    const int cg = Cn / 32, ch = (int)(r % cg); r /= cg;
-    const int sg = (S + DWS - 1) / DWS, sh = (int)(r % sg); const long long n = r / sg;
-    const int c = ch * 32 + cl, s = sh * DWS + sl;
-    if (s >= S) return;
-    const long long row = n * S + s;
-    float acc = src[row * lds + c];
-    if (res) acc += res[row * ldr + c];
-    float m = 0.f;
-    for (int j = 0; j < k; ++j) {
-      const int sj = s + j - padl;
-      if (sj >= 0 && sj < S) m += taps[j * Cn + c] * src[(n * S + sj) * lds + c];
+    constexpr int padl = (KT - 1) / 2;             // 'same' padding of every depthwise conv of the model
+    const int c = (int)(i % Cn); const long long r = i / Cn;
+    const int sg = (S + DWS - 1) / DWS; const int s0 = (int)(r % sg) * DWS; const long long n = r / sg;
+    float t[KT], x[DWS + KT - 1];
+#pragma unroll
+    for (int j = 0; j < KT; ++j) t[j] = taps[j * Cn + c];
+#pragma unroll
+    for (int j = 0; j < DWS + KT - 1; ++j) {
+      const int sj = s0 + j - padl;
+      x[j] = (sj >= 0 && sj < S) ? src[(n * S + sj) * lds + c] : 0.f;
     }
-    const long long d = use_pm ? pm.pix(n, s) * ldd : row * ldd;
-    dst[d + c] = acc + m;
+#pragma unroll
+    for (int o = 0; o < DWS; ++o) {
+      const int s = s0 + o;
+      if (s < S) {
+        const long long row = n * S + s;
+        float acc = x[o + padl];
+        if (res) acc += res[row * ldr + c];
+        float m = 0.f;
+#pragma unroll
+        for (int j = 0; j < KT; ++j) m += t[j] * x[o + j];
+        const long long d = use_pm ? pm.pix(n, s) * ldd : row * ldd;
+        dst[d + c] = acc + m;
+      }
+    }
   }
 };
 
@@ -619,7 +630,7 @@ void dense_block(Exec& ex, const Workspace& w, const DenseW& d, int B, int T, in
     ex.run(px * C, Linear{w.o201, C, nullptr, d.fl_w[i], d.fl_b[i], w.h201, C, C, C, ACT_RELU, nullptr});
     ex.run(px * C, Linear{w.h201, C, nullptr, d.fp_w[i], nullptr, w.p201, C, C, C, ACT_NONE, nullptr});
     float* dst = i + 1 < DEPTH ? w.skip + (DEPTH - 1 - i) * C : out;
-    ex.run(dw_count((long long)B * T, Fw, C), DwConv{w.p201, C, w.o201, C, d.fm_w[i], 2 * DLORDER - 1, DLORDER - 1, dst, i + 1 < DEPTH ? SKIPC : C, 0, PixMap{1, 0, 0, 0},
+    ex.run(dw_count((long long)B * T, Fw, C), DwConv<2 * DLORDER - 1>{w.p201, C, w.o201, C, d.fm_w[i], dst, i + 1 < DEPTH ? SKIPC : C, 0, PixMap{1, 0, 0, 0},
                           Fw, C});
   }
 }
@@ -635,18 +646,18 @@ void path(Exec& ex, const Workspace& w, const Weights& W, const PathW& p, const 
   ex.run(N * S * PI, Gather{xin, w.pst, pm, p.gw, p.gb, w.seq, S});
   ex.run(N * S, RowStats{w.seq, PI, PI, w.rst});
   ex.run(N * S * 2 * UV, Linear{w.seq, PI, w.rst, p.uv_w, p.uv_b, w.att, 2 * UV, PI, 2 * UV, ACT_SILU, nullptr});
-  ex.run(dw_count(N, S, 2 * UV), DwConv{w.att, 2 * UV, nullptr, 0, p.uv_c, DW, DW / 2, w.huv, 2 * UV, 0, pm, S, 2 * UV});
+  ex.run(dw_count(N, S, 2 * UV), DwConv<DW>{w.att, 2 * UV, nullptr, 0, p.uv_c, w.huv, 2 * UV, 0, pm, S, 2 * UV});
   ex.mark(tag, "huv", w.huv, N * S * 2 * UV);
   ex.run(N * S * UV, Linear{w.huv, 2 * UV, nullptr, p.rl_w, p.rl_b, w.fh, UV, UV, UV, ACT_RELU, nullptr});
   ex.run(N * S * UV, Linear{w.fh, UV, nullptr, p.rp_w, nullptr, w.fp, UV, UV, UV, ACT_NONE, nullptr});
-  ex.run(dw_count(N, S, UV), DwConv{w.fp, UV, w.huv, 2 * UV, p.rm_w, 2 * LORDER - 1, LORDER - 1, w.iu, UV, 0, pm, S, UV});
+  ex.run(dw_count(N, S, UV), DwConv<2 * LORDER - 1>{w.fp, UV, w.huv, 2 * UV, p.rm_w, w.iu, UV, 0, pm, S, UV});
   ex.run(N * Q * C, GateConvT{w.iu, UV, w.huv + UV, 2 * UV, p.lin_w, p.lin_b, w.t0, S, Q});
   ex.mark(tag, "lin", w.t0, N * Q * C);
   // MossFormer block on t0 (N, Q, 64)
   ex.run(N * Q * C, Shift{w.t0, w.sh, Q});
   ex.run(N * Q, RowStats{w.sh, C, C, w.rst});
   ex.run(N * Q * HUV, Linear{w.sh, C, w.rst, p.mf.in_w, p.mf.in_b, w.heads, HUV, C, HUV, ACT_SILU, nullptr});
-  ex.run(dw_count(N, Q, HUV), DwConv{w.heads, HUV, nullptr, 0, p.mf.in_c, DW, DW / 2, w.mhuv, HUV, 0, pm, Q, HUV});
+  ex.run(dw_count(N, Q, HUV), DwConv<DW>{w.heads, HUV, nullptr, 0, p.mf.in_c, w.mhuv, HUV, 0, pm, Q, HUV});
   ex.mark(tag, "mf.huv", w.mhuv, N * Q * HUV);
   ex.run(N * Q * 4 * QK, OffsetRot{w.mhuv, p.mf.gamma, p.mf.beta, W.rot_cos, W.rot_sin, w.heads, Q});
   ex.run(N * Q * Q, SimLocal{w.heads, w.A, Q});
@@ -657,7 +668,7 @@ void path(Exec& ex, const Workspace& w, const Weights& W, const PathW& p, const 
   ex.run(N * Q * (HID / 2), GateOut{w.att, w.mhuv, w.go});
   ex.run(N * Q, RowStats{w.go, HID / 2, HID / 2, w.rst});
   ex.run(N * Q * C, Linear{w.go, HID / 2, w.rst, p.mf.out_w, p.mf.out_b, w.ho, C, HID / 2, C, ACT_SILU, nullptr});
-  ex.run(dw_count(N, Q, C), DwConv{w.ho, C, w.t0, C, p.mf.out_c, DW, DW / 2, w.pr, C, 1, pm, Q, C});     // back to the channel-last map
+  ex.run(dw_count(N, Q, C), DwConv<DW>{w.ho, C, w.t0, C, p.mf.out_c, w.pr, C, 1, pm, Q, C});     // back to the channel-last map
   // SE (:689-696) + residual
   ex.run((long long)B * T * C, SePool1{w.pr, w.separt, FQ});
   ex.run((long long)B * C, SePool2{w.separt, w.sepool, T, FQ});

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the north-star path: noisy chunk in -> clean chunk out (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--model gtcrn|mbr|mf2se|mf2ss] [--batch B] [--impl adn|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model gtcrn|mbr|mf2se|mf2ss|mfgan] [--batch B] [--impl adn|reference]
 
 A "step" is one pass of the hot path over one batch of B synthetic chunks per GPU.
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field's definition.
@@ -403,7 +403,105 @@ class Mf2ssWorkload:
         }
 
 
-WORKLOADS = {"gtcrn": GtcrnWorkload, "mbr": MbrWorkload, "mf2se": Mf2seWorkload, "mf2ss": Mf2ssWorkload}
+class _Work(dict):
+    def __missing__(self, key):          # operators with negligible work: never the top kernel in practice
+        return (1, 0)
+
+
+class MfganWorkload:
+    """MossFormerGAN-SE-16K (BASELINE.json configs[4], the enhancement half of the mixed stream): dense encoder, 6 x (intra
+    path, inter path, triple attention), mask + complex decoders; 1 s windows at 16 kHz (161 frames x 101 sub-bands x 64)."""
+    name = "mfgan"
+    default_batch = 64
+    chunk, sr, channels, t_frames, layers = 16000, 16000, 1, 161, 6
+    cpu_chunks, ref_chunks = 6, 3
+    in_name = "noisy_audio"
+    cpu_desc = "oracle/mfgan_oracle.py (PyTorch-eager restatement, pinned to the executed reference wrapper)"
+
+    def describe(self, B):
+        return (f"MossFormerGAN-SE-16K, {self.layers} blocks, {B} x 1 s windows (16000 samples, 161 frames x 101 sub-bands) "
+                f"per GPU per step, F32 in / F32 out")
+
+    def audio_seconds(self, B):
+        return B * self.chunk / self.sr
+
+    def weights(self):
+        import mfgan_oracle as go
+        return go.random_state_dict(go.GanConfig(layers=self.layers), 0)
+
+    def build(self, sd, device):
+        from adn import export, mfgan_params
+        return export.mfgan_model(sd, mfgan_params.GanHyper(layers=self.layers), self.chunk, "F32", "F32", device_id=device)
+
+    def export(self, sd, path):
+        from adn import export, mfgan_params
+        export.export_mfgan(sd, path, mfgan_params.GanHyper(layers=self.layers), self.chunk, "F32", "F32")
+
+    def inputs(self, B, n_sets, seed):
+        sets = []
+        for s in range(n_sets):
+            g = torch.Generator().manual_seed(seed + s)
+            x = 0.2 * torch.randn(B, 1, self.chunk, generator=g)
+            t = torch.arange(self.chunk, dtype=torch.float32) / self.sr
+            x = x + 0.3 * torch.sin(2 * torch.pi * (220.0 + 10 * s) * t).reshape(1, 1, -1)
+            sets.append((x / x.abs().amax() * 0.5).contiguous())
+        return sets
+
+    def cpu_rate(self, sd, n_chunks, threads):
+        import mfgan_oracle as go
+        cfg = go.GanConfig(layers=self.layers)
+        P = go.fold(sd, cfg, self.t_frames)
+        torch.set_num_threads(threads)
+        g = torch.Generator().manual_seed(7)
+        x = (torch.rand(1, 1, self.chunk, generator=g) * 2 - 1) * 0.3
+        with torch.inference_mode():
+            go.mfgan_forward(sd, x, cfg, folded=P)
+            t0 = time.perf_counter()
+            for _ in range(n_chunks):
+                go.mfgan_forward(sd, x, cfg, folded=P)
+            dt = time.perf_counter() - t0
+        return n_chunks * self.chunk / self.sr / dt, dt
+
+    def kernel_work(self):
+        """Algorithmic (bytes, flops) per window, averaged per LAUNCH over the launches that share an operator name."""
+        T, F, FB, nl = self.t_frames, 101, 201, self.layers
+        px, pxb = T * F, T * FB
+        rows = {"intra": (T, F), "inter": (F, T)}                      # (sequences, positions) per window
+
+        def gemm(m, k, n, batch=1):
+            return (4 * batch * (m * k + k * n + m * n), 2 * batch * m * k * n)
+
+        def avg(items):
+            return (sum(b for b, _ in items) / len(items), sum(f for _, f in items) / len(items))
+
+        lin, att, dw, simL, simC, kv, gct = [], [], [], [], [], [], []
+        for w in (pxb, px, px):                                         # dense blocks: encoder (201 bins), two decoders
+            for _ in range(4):
+                lin += [gemm(w, 64, 64), gemm(w, 64, 64)]
+                dw.append((4 * 3 * w * 64, 2 * 9 * w * 64))
+        for _ in range(nl):
+            for n, q in rows.values():
+                s, bt = q - 1, n
+                lin += [gemm(n * s, 128, 256), gemm(n * s, 128, 128), gemm(n * s, 128, 128), gemm(n * q, 64, 384), gemm(n * q, 128, 64)]
+                dw += [(4 * 2 * n * s * 256, 2 * 31 * n * s * 256), (4 * 3 * n * s * 128, 2 * 39 * n * s * 128),
+                       (4 * 2 * n * q * 384, 2 * 31 * n * q * 384), (4 * 3 * n * q * 64, 2 * 31 * n * q * 64)]
+                simL.append(gemm(q, 128, q, n))
+                simC.append(gemm(bt, 128, bt, q))
+                kv.append(gemm(128, q, 256, n))
+                a = [gemm(q, q, 256, n), gemm(bt, bt, 256, q), gemm(q, 128, 256, n)]
+                att.append((sum(b for b, _ in a), sum(f for _, f in a)))
+                gct.append(gemm(n * q, 256, 64))
+            lin += [gemm(px, 64, 112), gemm(px, 64, 64)]
+        conv = [gemm(pxb, 6 * 64 * (i + 1), 64) for i in range(4)] + [gemm(px, 192, 64)]
+        conv += [gemm(px, 6 * 64 * (i + 1), 64) for i in range(4)] * 2 + [gemm(px, 192, 128)] * 2 + [gemm(pxb, 128, 1)]
+        return _Work({
+            "gan_linear": avg(lin), "gan_att": avg(att), "gan_dw_conv": avg(dw), "gan_sim_local": avg(simL),
+            "gan_sim_cross": avg(simC), "gan_lin_k_v": avg(kv), "gan_gate_conv_t": avg(gct), "gan_conv2d": avg(conv),
+            "gan_ta_scores": gemm(T, F * 6, T, 4), "gan_ta_a_v": gemm(T, T, F * 16, 4),
+        })
+
+
+WORKLOADS = {"gtcrn": GtcrnWorkload, "mbr": MbrWorkload, "mf2se": Mf2seWorkload, "mf2ss": Mf2ssWorkload, "mfgan": MfganWorkload}
 
 
 class ClockSampler:
@@ -509,7 +607,7 @@ def main():
             raise SystemExit("--matmul bf16 is only licensed for MossFormer2-SE-48K (BASELINE.json configs[2])")
         wl.matmul = "BF16"
     if args.steps <= 0:
-        args.steps = 100 if args.model == "gtcrn" else (5 if args.model == "mf2ss" else 20)
+        args.steps = 100 if args.model == "gtcrn" else (5 if args.model in ("mf2ss", "mfgan") else 20)
     if args.impl == "reference":
         args.steps = min(args.steps, 20)
         run_reference(args, wl)

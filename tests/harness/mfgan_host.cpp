@@ -34,6 +34,9 @@ struct HostExec {
   void run(long long n, const gan::SimCross& f) { run_gemm(n, f); }
   void run(long long n, const gan::LinKV& f) { run_gemm(n, f); }
   void run(long long n, const gan::Att& f) { run_gemm(n, f); }
+  void run(long long n, const gan::GateConvT& f) { run_gemm(n, f); }
+  void run(long long n, const gan::TaScores& f) { run_gemm(n, f); }
+  void run(long long n, const gan::TaAV& f) { run_gemm(n, f); }
   void run(long long n, const gan::Conv2d& f) {
     if (f.Cout >= 16 && f.Cin % 16 == 0) run_gemm(n, f);
     else run<gan::Conv2d>(n, f);

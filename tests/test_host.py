@@ -263,6 +263,62 @@ def test_mf2ss_packing_matches_oracle_fold():
         sp.pack(sd, h, 8)
 
 
+def test_mfgan_pack_matches_oracle_fold():
+    """adn/mfgan_params.py (product-side folds + kernel layouts) vs the oracle's `fold` (pinned bit-equal to the executed
+    reference wrapper's fused buffers): every folded tensor is found in the blob, transposed as csrc/mfgan_ops.cuh reads it."""
+    import mfgan_oracle as go
+    from adn import mfgan_params as gp
+
+    cfg = go.GanConfig(layers=2)
+    sd = go.random_state_dict(cfg, 5)
+    L = 2450
+    h = gp.GanHyper(layers=2)
+    T = h.n_frames(L)
+    assert T == cfg.n_frames(L) == 26 and h.padded(L) == 2500
+    P = go.fold(sd, cfg, T)
+    blob = gp.pack(sd, h, L)
+    lin_t = {"fl_w", "fp_w", "uv_w", "rl_w", "rp_w", "in_w", "out_w", "p_w"}
+    taps_t = {"fm_w", "uv_c", "rm_w", "in_c", "out_c"}
+    conv = {"conv_w", "c2_w", "sp_w", "c1_w", "c_w"}
+    seen = set()
+    for k, v in P.items():
+        leaf, ref, name = k.split(".")[-1], v.numpy(), k
+        if leaf == "cross_scale":
+            continue                                   # recomputed in csrc/mfgan_ops.cuh bind() as float(Q / BT)
+        if leaf in ("fconv_w", "unfold_w"):
+            ref, name = ref.reshape(128, 2), k.rsplit(".", 1)[0] + ".gw"
+        elif leaf in ("fconv_b", "unfold_b"):
+            name = k.rsplit(".", 1)[0] + ".gb"
+        elif k.startswith("enc.c1_w"):
+            ref = ref[:, :, 0, 0]
+        elif leaf in conv:
+            ref = ref.transpose(2, 3, 1, 0)
+        elif leaf == "w" and ".att." in k:
+            ref = ref.T
+        elif leaf in lin_t or leaf in taps_t:
+            ref = ref.T
+        elif leaf == "lin_w":
+            ref = ref.transpose(2, 0, 1)
+        elif leaf in ("q_g", "k_g", "v_g", "q_b", "k_b", "v_b"):
+            continue                                   # checked below as one (112, n_freqs) table
+        elif leaf == "p_a":
+            ref = np.broadcast_to(ref, (64,))
+        elif leaf == "fin_w":
+            ref = ref.reshape(-1)
+        assert np.array_equal(blob[name].reshape(ref.shape), ref), k
+        seen.add(name)
+    for i in range(2):
+        g = np.concatenate([P[f"B{i}.att.{t}_g"].numpy().reshape(-1, 101) for t in "qkv"], 0)
+        b = np.concatenate([P[f"B{i}.att.{t}_b"].numpy().reshape(-1, 101) for t in "qkv"], 0)
+        assert np.array_equal(blob[f"B{i}.att.g"], g) and np.array_equal(blob[f"B{i}.att.beta"], b)
+        seen |= {f"B{i}.att.g", f"B{i}.att.beta"}
+    assert set(blob) - seen == {"stft.fwd", "stft.inv", "stft.norm"}
+    md = gp.metadata(h, L)
+    assert md["model_family"] == "mossformergan_se" and md["gan_layers"] == "2" and md["max_signal_length"] == "26"
+    with pytest.raises(ValueError):
+        gp.pack(sd, h, 399)
+
+
 def test_wavio_roundtrip_and_reference_examples(tmp_path):
     """stdlib-wave PCM16 reader / writer: round trip, stereo layout, mono fold."""
     from adn import wavio
