@@ -67,7 +67,8 @@ typedef struct {
 } adn_tensor_info;
 
 /* Replaces onnxruntime.InferenceSession(path, ...) (Inference_GTCRN_ONNX.py:213-214,237):
- * builds a model of desc["model_family"] (gtcrn | mel_band_roformer | mossformer2_se | mossformer2_ss)
+ * builds a model of desc["model_family"] (gtcrn | mel_band_roformer | mossformer2_se | mossformer2_ss |
+ * mossformergan_se)
  * on CUDA device `device_id` from a host blob of `nfloats` fp32 values.  The keys are the reference's
  * metadata keys (audio_onnx_metadata.py:115-205) plus, for mossformer2_se, the optional
  * "matmul_dtype" = F32 (default: 3xTF32 tensor-core GEMMs, fp32-class) | BF16 (the layers' GEMMs on bf16
@@ -148,9 +149,9 @@ adn_status adn_stft_inverse(adn_stft* s, const float* d_spec, float* d_y, int32_
 void adn_stft_destroy(adn_stft* s);
 
 /* ---- stand-alone conditioning / feature / recombine / output operators ------------------------
- * The wrapper-forward steps either side of the backbones that are not built in this library
- * (ZipEnhancer, MossFormerGAN-SE-16K, MossFormer2-SS-16K) and the linear resampler every wrapper
- * shares.  With adn_stft_forward / adn_stft_inverse they form the complete front and back ends
+ * The wrapper-forward steps either side of the ZipEnhancer, MossFormerGAN-SE-16K and MossFormer2-SS-16K
+ * backbones (ZipEnhancer's backbone is not built in this library; the mossformergan_se model runs the
+ * MossFormerGAN operators internally) and the linear resampler every wrapper shares.  With adn_stft_forward / adn_stft_inverse they form the complete front and back ends
  * around those backbones.  All pointers are DEVICE pointers, rows are contiguous, `stream` is a
  * cudaStream_t (NULL = default stream); errors go to adn_last_error(NULL). */
 enum { ADN_FAMILY_ZIPENHANCER = 1, ADN_FAMILY_MOSSFORMERGAN = 2, ADN_FAMILY_MOSSFORMER2_SS = 3 };

@@ -64,9 +64,10 @@ def load_export_namespace(model_dir: str, script: str, patches: dict[str, str]) 
     to its replacement text."""
     _install_stubs()
     mdir = REFERENCE_ROOT / model_dir
-    for p in (str(mdir), str(REFERENCE_ROOT)):
-        if p not in sys.path:
-            sys.path.insert(0, p)
+    for p in (str(REFERENCE_ROOT), str(mdir)):          # the model folder must come FIRST: every folder has its own STFT_Process.py
+        while p in sys.path:
+            sys.path.remove(p)
+        sys.path.insert(0, p)
     # the per-model STFT_Process must win over a previously imported sibling variant
     sys.modules.pop("STFT_Process", None)
     src = (mdir / script).read_text()
