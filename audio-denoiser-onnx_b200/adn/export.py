@@ -111,3 +111,25 @@ def mfgan_model(state_dict: dict, hyper=None, input_audio_length: int = 16000, i
     hyper = hyper or mfgan_params.GanHyper()
     md = mfgan_params.metadata(hyper, input_audio_length, in_dtype, out_dtype)
     return Model.from_tensors(md, mfgan_params.pack(state_dict, hyper, input_audio_length), device_id)
+
+
+def export_dfsmn(state_dict: dict, path, hyper=None, input_audio_length: int = 96000, in_dtype: str = "INT16",
+                 out_dtype: str = "INT16") -> dict[str, str]:
+    """DFSMN (48 kHz) `.adn` for one static window length (counterpart of DFSMN/Export_DFSMN.py:252-324).
+    `state_dict` keys: see adn/dfsmn_params.py."""
+    from . import dfsmn_params
+
+    hyper = hyper or dfsmn_params.DfsmnHyper()
+    md = dfsmn_params.metadata(hyper, input_audio_length, in_dtype, out_dtype)
+    modelfile.save(path, md, dfsmn_params.pack(state_dict, hyper, input_audio_length))
+    return md
+
+
+def dfsmn_model(state_dict: dict, hyper=None, input_audio_length: int = 96000, in_dtype: str = "F32",
+                out_dtype: str = "F32", device_id: int = 0):
+    from . import dfsmn_params
+    from .model import Model
+
+    hyper = hyper or dfsmn_params.DfsmnHyper()
+    md = dfsmn_params.metadata(hyper, input_audio_length, in_dtype, out_dtype)
+    return Model.from_tensors(md, dfsmn_params.pack(state_dict, hyper, input_audio_length), device_id)

@@ -4,7 +4,7 @@
 //   -> dense encoder, 6 x (intra path, inter path, triple attention), mask / complex decoders           [mfgan_ops.cuh]
 //   -> mask * compressed + complex, decompress (:863-868) -> ISTFT -> x norm factor, output rule (:880-897) [ends.cu]
 // First-correct implementation: one grid per operator (fp32 FFMA, one output per thread), all intermediates in HBM.
-#include "mfgan_gemm.cuh"
+#include "gan_exec.cuh"
 
 #include "common.cuh"
 #include "model_impl.h"
@@ -14,89 +14,6 @@
 #include <vector>
 
 namespace gan {
-
-template <class F>
-__global__ void __launch_bounds__(256) op_kernel(long long n, F f) {
-  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (i < n) f(i);
-}
-
-struct CudaExec {
-  cudaStream_t st = nullptr;
-  int launches = 0;
-  ImplTickFn tick = nullptr;
-  void* tick_ctx = nullptr;
-  bool capture = false;
-  std::map<std::string, std::vector<float>>* dumps = nullptr;
-  template <class F>
-  void run(long long n, const F& f) {
-    if (n <= 0) return;
-    op_kernel<F><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, f);
-    ++launches;
-    if (tick) tick(tick_ctx, op_name(f));
-  }
-  // contractions run on the shared-memory tiled GEMM (mfgan_gemm.cuh) instead of the one-output-per-thread functor
-  template <class F>
-  void run_gemm(long long n, const F& f) {
-    if (n <= 0) return;
-    GemmOp ops[3];
-    const int k = translate(f, n, ops);
-    for (int i = 0; i < k; ++i) launch_gemm(ops[i], st);
-    launches += k;
-    if (tick) tick(tick_ctx, op_name(f));
-  }
-  void run(long long n, const Linear& f) { run_gemm(n, f); }
-  void run(long long n, const SimLocal& f) { run_gemm(n, f); }
-  void run(long long n, const SimCross& f) { run_gemm(n, f); }
-  void run(long long n, const LinKV& f) { run_gemm(n, f); }
-  void run(long long n, const Att& f) { run_gemm(n, f); }
-  void run(long long n, const GateConvT& f) { run_gemm(n, f); }
-  void run(long long n, const TaScores& f) { run_gemm(n, f); }
-  void run(long long n, const TaAV& f) { run_gemm(n, f); }
-  void run(long long n, const Conv2d& f) {
-    if (f.Cout >= 16 && f.Cin % GK == 0) run_gemm(n, f);
-    else run<Conv2d>(n, f);
-  }
-  void mark(const char* tag, const char* name, const float* p, long long count) {
-    if (!capture || !dumps) return;
-    std::string key = tag[0] ? std::string(tag) + "." + name : std::string(name);
-    std::vector<float>& v = (*dumps)[key];
-    v.resize((size_t)count);
-    cudaStreamSynchronize(st);
-    cudaMemcpy(v.data(), p, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost);
-  }
-  template <class F> static const char* op_name(const F&) { return "gan_op"; }
-  static const char* op_name(const Linear&) { return "gan_linear"; }
-  static const char* op_name(const Conv2d&) { return "gan_conv2d"; }
-  template <int KT> static const char* op_name(const DwConv<KT>&) { return "gan_dw_conv"; }
-  static const char* op_name(const Att&) { return "gan_att"; }
-  static const char* op_name(const SimLocal&) { return "gan_sim_local"; }
-  static const char* op_name(const SimCross&) { return "gan_sim_cross"; }
-  static const char* op_name(const LinKV&) { return "gan_lin_k_v"; }
-  static const char* op_name(const TaScores&) { return "gan_ta_scores"; }
-  static const char* op_name(const TaAV&) { return "gan_ta_a_v"; }
-  static const char* op_name(const GateConvT&) { return "gan_gate_conv_t"; }
-  static const char* op_name(const RowStats&) { return "gan_row_stats"; }
-  static const char* op_name(const Gather&) { return "gan_gather"; }
-  static const char* op_name(const Shift&) { return "gan_shift"; }
-  static const char* op_name(const OffsetRot&) { return "gan_offset_rot"; }
-  static const char* op_name(const GateOut&) { return "gan_gate_out"; }
-  static const char* op_name(const SePool1&) { return "gan_se_pool1"; }
-  static const char* op_name(const SePool2&) { return "gan_se_pool2"; }
-  static const char* op_name(const SeMlp&) { return "gan_se_mlp"; }
-  static const char* op_name(const ScaleRes&) { return "gan_scale_res"; }
-  static const char* op_name(const GroupPart&) { return "gan_group_part"; }
-  static const char* op_name(const GroupFin&) { return "gan_group_fin"; }
-  static const char* op_name(const GroupNorm&) { return "gan_group_norm"; }
-  static const char* op_name(const Softmax&) { return "gan_softmax"; }
-  static const char* op_name(const InPart&) { return "gan_in_part"; }
-  static const char* op_name(const InFin&) { return "gan_in_fin"; }
-  static const char* op_name(const InApply&) { return "gan_in_apply"; }
-  static const char* op_name(const FeatConv&) { return "gan_feat_conv"; }
-  static const char* op_name(const CopyCh&) { return "gan_copy_ch"; }
-  static const char* op_name(const MaskTail&) { return "gan_mask_tail"; }
-  static const char* op_name(const CplxTail&) { return "gan_cplx_tail"; }
-};
 
 class Model : public ModelImpl {
  public:

@@ -226,7 +226,7 @@ inline void gemm_ref(const GemmOp& g) {
 #if defined(__CUDACC__)
 constexpr int GT = 64, GK = 16, GLD = GT + 4;
 
-__global__ void __launch_bounds__(256) gemm_kernel(const GemmOp g, const int tiles_n) {
+static __global__ void __launch_bounds__(256) gemm_kernel(const GemmOp g, const int tiles_n) {
   __shared__ __align__(16) float As[2][GK][GLD];
   __shared__ __align__(16) float Bs[2][GK][GLD];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;

@@ -18,7 +18,7 @@
 
 namespace gan {
 
-enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_PRELU = 3 };
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_PRELU = 3, ACT_LOGCLAMP = 4, ACT_SIGMOID = 5 };
 
 constexpr int C = 64;        // emb
 constexpr int KS = 2;        // emb_ks
@@ -42,6 +42,8 @@ GAN_HD float act(float v, int a, const float* slope, int n) {
   if (a == ACT_RELU) return v > 0.f ? v : 0.f;
   if (a == ACT_SILU) return v * sigmoidf_(v);
   if (a == ACT_PRELU) return v >= 0.f ? v : slope[n] * v;
+  if (a == ACT_LOGCLAMP) return logf(v > 1.1920928955078125e-07f ? v : 1.1920928955078125e-07f);   // log(max(v, fp32 eps)), Kaldi log floor
+  if (a == ACT_SIGMOID) return sigmoidf_(v);
   return v;
 }
 

@@ -46,3 +46,7 @@ ModelImpl* mf2ss_create(const std::map<std::string, std::string>& meta, const st
 // MossFormerGAN-SE-16K: csrc/mfgan.cu
 ModelImpl* mfgan_create(const std::map<std::string, std::string>& meta, const std::map<std::string, TensorRef>& index,
                         const float* h_blob, float* d_blob, int device, int sms, std::string& err);
+
+// DFSMN 48 kHz: csrc/dfsmn.cu
+ModelImpl* dfsmn_create(const std::map<std::string, std::string>& meta, const std::map<std::string, TensorRef>& index,
+                        const float* h_blob, float* d_blob, int device, int sms, std::string& err);

@@ -227,8 +227,33 @@ def main_mfgan():
             print(f"mfgan {dt} L{L}: {tuple(xin.shape)} -> {tuple(y.shape)} max|y| {y.float().abs().max().item():.4f}")
 
 
+def main_dfsmn():
+    """DFSMN (48 kHz) fixtures: the reference wrapper (`DFSMN` of DFSMN/Export_DFSMN.py) executed around
+    `dfsmn_oracle.skeleton()` on seeded weights, 3 FSMN layers (the depth is the only reduced hyper-parameter);
+    1920 + 960 * 8 samples (9 frames) in F32 and 1920 + 960 * 5 (6 frames) in INT16; one all-zero window."""
+    import dfsmn_oracle as do
+
+    assert ref_loader.reference_available()
+    cfg = do.DfsmnConfig(layers=3)
+    sd = do.random_state_dict(cfg, 0)
+    hold = do.skeleton(cfg)
+    hold.load_state_dict(sd)
+    with torch.inference_mode():
+        for L, dt in ((1920 + 960 * 8, "F32"), (1920 + 960 * 5, "INT16")):
+            _, build = ref_loader.load_dfsmn(L, dt)
+            w = build(hold)
+            x = synth_audio(L, 2468, batch=3)
+            x[2] = 0.0
+            xin = x if dt == "F32" else torch.round(x * 32767.0).to(torch.int16)
+            y = torch.cat([w(xin[i:i + 1].clone()) for i in range(3)], dim=0)
+            np.savez_compressed(GOLDEN / f"dfsmn_{dt.lower()}_L{L}_l3.npz", x=xin.numpy(), y=y.numpy(), seed=0, layers=3)
+            print(f"dfsmn {dt} L{L}: {tuple(xin.shape)} -> {tuple(y.shape)} max|y| {y.float().abs().max().item():.4f}")
+
+
 if __name__ == "__main__":
-    if "--mfgan" in sys.argv:
+    if "--dfsmn" in sys.argv:
+        main_dfsmn()
+    elif "--mfgan" in sys.argv:
         main_mfgan()
     elif "--mf2ss" in sys.argv:
         main_mf2ss()

@@ -286,3 +286,43 @@ def load_mfgan(input_audio_length: int, io_dtype: str = "F32"):
                                        False, ns["FOLD_WINDOW_LENGTH"]).eval()
 
     return ns, build
+
+
+def load_dfsmn(input_audio_length: int, io_dtype: str = "F32"):
+    """Reference DFSMN wrapper (`DFSMN` of DFSMN/Export_DFSMN.py) for one un-folded window at 48 kHz.  The wrapper's
+    forward is made of leaf ops; its constructor reads the weights off the absent `modelscope` pipeline model.
+    Returns (namespace, build) with build(holder) -> wrapper, where `holder` is `dfsmn_oracle.skeleton()`."""
+    import torch
+
+    for name in ("modelscope", "modelscope.pipelines", "modelscope.utils", "modelscope.utils.constant"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["modelscope.pipelines"].pipeline = lambda *a, **k: None
+    sys.modules["modelscope.utils.constant"].Tasks = types.SimpleNamespace(acoustic_noise_suppression="ans")
+    if "Rewrite_ONNX_Causal_Padding" not in sys.modules:
+        mod = types.ModuleType("Rewrite_ONNX_Causal_Padding")
+        mod.rewrite_causal_fsmn_padding = lambda *a, **k: None
+        sys.modules["Rewrite_ONNX_Causal_Padding"] = mod
+
+    ns = load_export_namespace(
+        "DFSMN",
+        "Export_DFSMN.py",
+        {
+            "INPUT_AUDIO_LENGTH    = 96000": f"INPUT_AUDIO_LENGTH    = {int(input_audio_length)}",
+            "IN_AUDIO_DTYPE        = 'INT16'": f"IN_AUDIO_DTYPE        = '{io_dtype}'",
+            "OUT_AUDIO_DTYPE       = 'INT16'": f"OUT_AUDIO_DTYPE       = '{io_dtype}'",
+        },
+    )
+
+    def build(holder):
+        with torch.inference_mode():
+            S = ns["STFT_Process"]
+            stft = S(model_type="stft_B", n_fft=ns["NFFT_STFT"], win_length=ns["WINDOW_LENGTH"], hop_len=ns["HOP_LENGTH"],
+                     max_frames=0, window_type=ns["WINDOW_TYPE"], center_pad=False, pad_mode="constant").eval()
+            istft = S(model_type="istft_B", n_fft=ns["NFFT_STFT"], win_length=ns["WINDOW_LENGTH"], hop_len=ns["HOP_LENGTH"],
+                      max_frames=ns["MAX_SIGNAL_LENGTH"], window_type=ns["ISTFT_WINDOW_TYPE"], center_pad=False,
+                      pad_mode="constant", static_norm=True).eval()
+            return ns["DFSMN"](holder.eval().float(), stft, istft, ns["NFFT_STFT"], ns["N_MELS"], ns["IN_SAMPLE_RATE"],
+                               ns["OUT_SAMPLE_RATE"], use_batch_fold=False, fold_window=ns["FOLD_WINDOW_LENGTH"], static_batch=1).eval()
+
+    return ns, build

@@ -327,7 +327,7 @@ def test_mf2ss_oracle_matches_reference_module():
         assert (a - b).abs().max() <= 5e-6
 
 
-# ----------------------------------------------------------------------------- MossFormerGAN-SE-16K (oracle only: no CUDA path yet)
+# ----------------------------------------------------------------------------- MossFormerGAN-SE-16K
 @pytest.mark.parametrize("fixture,dt", [("mfgan_f32_L3150_l2", "F32"), ("mfgan_int16_L2400_l2", "INT16")])
 def test_mfgan_oracle_matches_golden(fixture, dt, golden_dir):
     import mfgan_oracle as go
@@ -451,3 +451,51 @@ def test_gtcrn_oracle_output_resampling_matches_reference_module(L, out_rate, dt
         assert int((r.int() - o.int()).abs().max()) <= 1
     else:
         assert float((r - o).abs().max()) <= 2e-6
+
+
+# ----------------------------------------------------------------------------- DFSMN (48 kHz)
+@pytest.mark.parametrize("fixture,dt", [("dfsmn_f32_L9600_l3", "F32"), ("dfsmn_int16_L6720_l3", "INT16")])
+def test_dfsmn_oracle_matches_golden(fixture, dt, golden_dir):
+    import dfsmn_oracle as do
+
+    g = np.load(golden_dir / f"{fixture}.npz")
+    cfg = do.DfsmnConfig(layers=int(g["layers"]))
+    sd = do.random_state_dict(cfg, int(g["seed"]))
+    with torch.inference_mode():
+        y = do.dfsmn_forward_batch(sd, torch.from_numpy(g["x"]), cfg, dt, dt).numpy()
+    assert y.shape == g["y"].shape and y.dtype == g["y"].dtype
+    if dt == "INT16":
+        assert np.abs(y.astype(np.int32) - g["y"].astype(np.int32)).max() <= 1
+    else:
+        assert np.abs(y - g["y"]).max() <= 2e-6
+
+
+@needs_ref
+@pytest.mark.parametrize("dt", ["F32", "INT16"])
+def test_dfsmn_oracle_matches_reference_module(dt):
+    """Restated folds + forward vs the reference's own DFSMN wrapper (DFSMN/Export_DFSMN.py:71-250) executed around the
+    parameter skeleton: fused analysis kernel, Kaldi mel banks and FSMN buffers bit-equal, waveform <= 2e-6."""
+    import dfsmn_oracle as do
+
+    cfg = do.DfsmnConfig(layers=2)
+    sd = do.random_state_dict(cfg, 4)
+    L = 1920 + 960 * 7
+    _, build = ref_loader.load_dfsmn(L, dt)
+    hold = do.skeleton(cfg)
+    hold.load_state_dict(sd)
+    w = build(hold)
+    P = do.fold(sd, cfg)
+    assert torch.equal(P["analysis_w"], w.analysis_conv_weight[:, 0, :]) and torch.equal(P["mel_banks"], w.mel_banks[0])
+    for i in range(cfg.layers):
+        assert torch.equal(P[f"uf{i}.conv_w"], getattr(w, f"uf_conv_w_{i}")[:, 0, :])
+        assert torch.equal(P[f"uf{i}.lin_w"], getattr(w, f"uf_lin_w_{i}")[:, :, 0])
+    x = synth_audio(L, 5, batch=2)
+    xin = x if dt == "F32" else torch.round(x * 32767).to(torch.int16)
+    with torch.inference_mode():
+        yr = torch.cat([w(xin[i:i + 1].clone()) for i in range(2)], dim=0)
+        yo = do.dfsmn_forward_batch(sd, xin, cfg, dt, dt)
+    assert yr.shape == yo.shape == (2, 1, L) and yr.dtype == yo.dtype
+    if dt == "INT16":
+        assert int((yr.int() - yo.int()).abs().max()) <= 1
+    else:
+        assert float((yr - yo).abs().max()) <= 2e-6
