@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the north-star path: noisy chunk in -> clean chunk out (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--model gtcrn|mbr|mf2se|mf2ss|mfgan] [--batch B] [--impl adn|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model gtcrn|mbr|mf2se|mf2ss|mfgan|dfsmn] [--batch B] [--impl adn|reference]
 
 A "step" is one pass of the hot path over one batch of B synthetic chunks per GPU.
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field's definition.
@@ -501,7 +501,67 @@ class MfganWorkload:
         })
 
 
-WORKLOADS = {"gtcrn": GtcrnWorkload, "mbr": MbrWorkload, "mf2se": Mf2seWorkload, "mf2ss": Mf2ssWorkload, "mfgan": MfganWorkload}
+class DfsmnWorkload:
+    """DFSMN 48 kHz causal denoiser: fused Kaldi-fbank | STFT analysis, 9 FSMN layers, 1 s windows."""
+    name = "dfsmn"
+    default_batch = 256
+    chunk, sr, channels, t_frames, layers = 48000, 48000, 1, 49, 9
+    cpu_chunks, ref_chunks = 64, 16
+    in_name = "noisy_audio"
+    cpu_desc = "oracle/dfsmn_oracle.py (PyTorch-eager restatement, bit-equal to the executed reference wrapper)"
+
+    def describe(self, B):
+        return f"DFSMN 48 kHz, {self.layers} FSMN layers, {B} x 1 s windows (48000 samples, 49 frames) per GPU per step, F32 in / F32 out"
+
+    def audio_seconds(self, B):
+        return B * self.chunk / self.sr
+
+    def weights(self):
+        import dfsmn_oracle as do
+        return do.random_state_dict(do.DfsmnConfig(layers=self.layers), 0)
+
+    def build(self, sd, device):
+        from adn import dfsmn_params, export
+        return export.dfsmn_model(sd, dfsmn_params.DfsmnHyper(layers=self.layers), self.chunk, "F32", "F32", device_id=device)
+
+    def export(self, sd, path):
+        from adn import dfsmn_params, export
+        export.export_dfsmn(sd, path, dfsmn_params.DfsmnHyper(layers=self.layers), self.chunk, "F32", "F32")
+
+    inputs = MfganWorkload.inputs
+
+    def cpu_rate(self, sd, n_chunks, threads):
+        import dfsmn_oracle as do
+        cfg = do.DfsmnConfig(layers=self.layers)
+        P = do.fold(sd, cfg)
+        torch.set_num_threads(threads)
+        g = torch.Generator().manual_seed(7)
+        x = (torch.rand(1, 1, self.chunk, generator=g) * 2 - 1) * 0.3
+        with torch.inference_mode():
+            do.dfsmn_forward(sd, x, cfg, folded=P)
+            t0 = time.perf_counter()
+            for _ in range(n_chunks):
+                do.dfsmn_forward(sd, x, cfg, folded=P)
+            dt = time.perf_counter() - t0
+        return n_chunks * self.chunk / self.sr / dt, dt
+
+    def kernel_work(self):
+        T, L = self.t_frames, self.chunk
+
+        def gemm(m, k, n):
+            return (4 * (m * k + k * n + m * n), 2 * m * k * n)
+
+        lin = [gemm(T, 1025, 120), gemm(T, 120, 256), gemm(T, 256, 961)] + [gemm(T, 256, 256)] * (2 * self.layers)
+        return _Work({
+            "gemm": (4 * (L + 3972 * 1920 + T * 3972), 2 * T * 1920 * 3972),       # fused analysis conv
+            "gan_linear": (sum(b for b, _ in lin) / len(lin), sum(f for _, f in lin) / len(lin)),
+            "dfsmn_memory": (4 * 3 * T * 256, 2 * 20 * T * 256),
+            "istft": (4 * (1922 * T + L), 2 * T * 1920 * 1922),
+        })
+
+
+WORKLOADS = {"gtcrn": GtcrnWorkload, "mbr": MbrWorkload, "mf2se": Mf2seWorkload, "mf2ss": Mf2ssWorkload, "mfgan": MfganWorkload,
+             "dfsmn": DfsmnWorkload}
 
 
 class ClockSampler:
