@@ -92,25 +92,25 @@ def mf2ss_model(state_dict: dict, hyper=None, input_audio_length: int = 16000, i
 
 
 def export_mfgan(state_dict: dict, path, hyper=None, input_audio_length: int = 16000, in_dtype: str = "INT16",
-                 out_dtype: str = "INT16") -> dict[str, str]:
+                 out_dtype: str = "INT16", in_rate: int | None = None, out_rate: int | None = None) -> dict[str, str]:
     """MossFormerGAN-SE-16K `.adn` for one static window length (counterpart of
     MossFormerGAN_SE_16K/Export_MossFormer_SE.py:900-950).  `state_dict` keys: see adn/mfgan_params.py."""
     from . import mfgan_params
 
     hyper = hyper or mfgan_params.GanHyper()
-    md = mfgan_params.metadata(hyper, input_audio_length, in_dtype, out_dtype)
-    modelfile.save(path, md, mfgan_params.pack(state_dict, hyper, input_audio_length))
+    md = mfgan_params.metadata(hyper, input_audio_length, in_dtype, out_dtype, in_rate, out_rate)
+    modelfile.save(path, md, mfgan_params.pack(state_dict, hyper, input_audio_length, in_rate))
     return md
 
 
 def mfgan_model(state_dict: dict, hyper=None, input_audio_length: int = 16000, in_dtype: str = "F32",
-                out_dtype: str = "F32", device_id: int = 0):
+                out_dtype: str = "F32", device_id: int = 0, in_rate: int | None = None, out_rate: int | None = None):
     from . import mfgan_params
     from .model import Model
 
     hyper = hyper or mfgan_params.GanHyper()
-    md = mfgan_params.metadata(hyper, input_audio_length, in_dtype, out_dtype)
-    return Model.from_tensors(md, mfgan_params.pack(state_dict, hyper, input_audio_length), device_id)
+    md = mfgan_params.metadata(hyper, input_audio_length, in_dtype, out_dtype, in_rate, out_rate)
+    return Model.from_tensors(md, mfgan_params.pack(state_dict, hyper, input_audio_length, in_rate), device_id)
 
 
 def export_dfsmn(state_dict: dict, path, hyper=None, input_audio_length: int = 96000, in_dtype: str = "INT16",

@@ -85,7 +85,14 @@ def _dense(sd, pre: str, h: GanHyper, blob: dict, out: str):
         blob[f"{out}{i}.fm_w"] = _f(sd[f"{f}.conv1.weight"][:, 0, :, 0].t())                               # (2*lorder-1, C)
 
 
-def pack(sd: dict, h: GanHyper, input_audio_length: int) -> dict[str, np.ndarray]:
+def model_length(h: GanHyper, input_audio_length: int, in_rate: int | None = None) -> int:
+    """MODEL_AUDIO_LENGTH (Export_MossFormer_SE.py:37): the window length at the 16 kHz model rate."""
+    return int(round(input_audio_length * h.sample_rate / (in_rate or h.sample_rate)))
+
+
+def pack(sd: dict, h: GanHyper, input_audio_length: int, in_rate: int | None = None) -> dict[str, np.ndarray]:
+    """input_audio_length is at `in_rate` (default: the model rate); tables are sized for the model-rate window."""
+    input_audio_length = model_length(h, input_audio_length, in_rate)
     if input_audio_length < 400:
         raise ValueError("input_audio_length must cover one STFT frame (400 samples)")
     T = h.n_frames(input_audio_length)
@@ -178,22 +185,27 @@ def pack(sd: dict, h: GanHyper, input_audio_length: int) -> dict[str, np.ndarray
     return blob
 
 
-def metadata(h: GanHyper, input_audio_length: int, in_dtype: str = "INT16", out_dtype: str = "INT16") -> dict[str, str]:
+def metadata(h: GanHyper, input_audio_length: int, in_dtype: str = "INT16", out_dtype: str = "INT16",
+             in_rate: int | None = None, out_rate: int | None = None) -> dict[str, str]:
     """Metadata keys of `MossFormerGAN_SE_16K/Export_MossFormer_SE.py:941-947` + the block count the reference
     reads off the live upstream module."""
     g = stft_tables.GEOMETRY[GEOM_KEY]
+    in_rate, out_rate = in_rate or h.sample_rate, out_rate or h.sample_rate
+    mlen = model_length(h, input_audio_length, in_rate)
+    # OUTPUT_AUDIO_LENGTH (:38): the reference scales the INPUT length by out / model rate
+    olen = mlen if out_rate == h.sample_rate else int(round(input_audio_length * out_rate / h.sample_rate))
     md = {
         "audio_metadata_version": 1, "producer": "adn.mfgan_params", "model_name": "MossFormerGAN_SE_16K",
         "task": "denoise", "model_family": FAMILY, "dynamic_axes": "0", "opset": 20,
         "input_audio_dtype": in_dtype, "output_audio_dtype": out_dtype,
-        "in_sample_rate": h.sample_rate, "out_sample_rate": h.sample_rate, "model_sample_rate": h.sample_rate,
+        "in_sample_rate": in_rate, "out_sample_rate": out_rate, "model_sample_rate": h.sample_rate,
         "input_audio_length": input_audio_length, "export_audio_length": input_audio_length,
-        "model_audio_length": input_audio_length, "output_audio_length": input_audio_length,
-        "input_to_output_scale": 1.0, "batch_window_seconds": 1.0, "use_batch_fold": "0",
+        "model_audio_length": mlen, "output_audio_length": olen,
+        "input_to_output_scale": float(out_rate / in_rate), "batch_window_seconds": 1.0, "use_batch_fold": "0",
         "batch_fold_inference_default": "0", "fold_window_length": 16000, "fold_input_length": 16000,
         "max_dynamic_audio_seconds": 6, "normalize_audio_default": "0", "normalize_target_rms": 4096.0,
         "window_type": "hamming", "nfft": g.nfft, "window_length": g.win_length, "hop_length": g.hop,
-        "max_signal_length": h.n_frames(input_audio_length), "center_pad": "1", "pad_mode": "reflect",
+        "max_signal_length": h.n_frames(mlen), "center_pad": "1", "pad_mode": "reflect",
         "feature_kind": "stft_power_compressed", "input_channels": 1, "output_channels": 1, "num_audio_inputs": 1,
         "gan_layers": h.layers,
     }

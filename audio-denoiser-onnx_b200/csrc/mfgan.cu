@@ -7,6 +7,7 @@
 #include "gan_exec.cuh"
 
 #include "common.cuh"
+#include "dfsmn_ops.cuh"
 #include "model_impl.h"
 
 #include <stdio.h>
@@ -15,11 +16,19 @@
 
 namespace gan {
 
+struct CastF16 {
+  const float* w; __half* out;
+  __device__ void operator()(long long i) const { out[i] = __float2half_rn(w[i]); }
+};
+
 class Model : public ModelImpl {
  public:
   int device = 0, sms = 148;
   int in_dtype = ADN_F32, out_dtype = ADN_F32;
   int L = 0, Lpad = 0, T = 0, layers = 6, Lsrc = 0;
+  int L_in = 0, L_final = 0;     // I/O window lengths at the in / out sample rates (== L at 16 kHz)
+  bool rs_in = false, rs_out = false;
+  float *xr = nullptr, *ymod = nullptr, *yout = nullptr;
   float* d_blob = nullptr;
   std::map<std::string, TensorRef> index;
   Weights W;
@@ -68,15 +77,21 @@ class Model : public ModelImpl {
     if (!geti("input_audio_length", L) || !geti("nfft", nfft) || !geti("hop_length", hop) || !geti("gan_layers", layers) ||
         !gets("input_audio_dtype", sin) || !gets("output_audio_dtype", sout))
       return false;
-    if (nfft != 400 || hop != 100 || L < 400 || layers < 1 || layers > 8) {
+    if (nfft != 400 || hop != 100 || L < 1 || layers < 1 || layers > 8) {
       err = "mossformergan_se needs nfft=400, hop_length=100, input_audio_length >= 400, 1..8 layers";
       return false;
     }
-    {
-      int in_sr = 16000, out_sr = 16000;
+    {   // optional linear resampling either side of the model (:542-549, :884-891): input_audio_length is at in_sample_rate
+      int in_sr = 16000, out_sr = 16000, model_sr = 16000;
       auto opt = [&](const char* k, int& v) { auto it = meta.find(k); if (it != meta.end() && !it->second.empty()) v = atoi(it->second.c_str()); };
-      opt("in_sample_rate", in_sr); opt("out_sample_rate", out_sr);
-      if (in_sr != 16000 || out_sr != 16000) { err = "mossformergan_se runs at 16 kHz I/O only"; return false; }
+      opt("in_sample_rate", in_sr); opt("out_sample_rate", out_sr); opt("model_sample_rate", model_sr);
+      if (model_sr != 16000 || in_sr <= 0 || out_sr <= 0) { err = "mossformergan_se runs at model_sample_rate 16000"; return false; }
+      L_in = L;
+      rs_in = in_sr != 16000;
+      rs_out = out_sr != 16000;
+      if (rs_in) L = (int)llround((double)L_in * 16000.0 / in_sr);                 // MODEL_AUDIO_LENGTH (:37)
+      L_final = rs_out ? (int)llround((double)L_in * out_sr / 16000.0) : L;        // OUTPUT_AUDIO_LENGTH (:38): input length x out / model rate
+      if (L < 400 || L_final < 1) { err = "mossformergan_se: the model-rate window must cover one STFT frame (400 samples)"; return false; }
     }
     auto pdt = [&](const std::string& s, int& o) { if (s == "F32") o = ADN_F32; else if (s == "INT16") o = ADN_I16; else if (s == "F16") o = ADN_F16; else return false; return true; };
     if (!pdt(sin, in_dtype) || !pdt(sout, out_dtype)) { err = "bad audio dtype"; return false; }
@@ -120,6 +135,7 @@ class Model : public ModelImpl {
         !(keep = dalloc(b * 2 * FB * T)) || !(mask = dalloc(b * FB * T)) || !(cplx = dalloc(b * 2 * FB * T)) ||
         !(spec2 = dalloc(b * 2 * FB * T)) || !(wave = dalloc(b * Lsrc)))
       return false;
+    if ((rs_in && !(xr = dalloc(b * L))) || (rs_out && (!(ymod = dalloc(b * L)) || !(yout = dalloc(b * L_final))))) return false;
     cap = B;
     return true;
   }
@@ -127,21 +143,23 @@ class Model : public ModelImpl {
     memset(in, 0, sizeof(*in));
     memset(out, 0, sizeof(*out));
     strncpy(in->name, "noisy_audio", sizeof(in->name) - 1);
-    in->dtype = in_dtype; in->channels = 1; in->length = L;
+    in->dtype = in_dtype; in->channels = 1; in->length = L_in;
     strncpy(out->name, "denoised_audio", sizeof(out->name) - 1);
-    out->dtype = out_dtype; out->channels = 1; out->length = L;
+    out->dtype = out_dtype; out->channels = 1; out->length = L_final;
   }
   size_t workspace_bytes(int batch) override {
     const size_t sub = batch < SUB ? batch : SUB, S = T > FQ ? T : FQ, rows = sub * T * FQ, px2 = sub * T * (FB + 1);
     size_t f = px2 * (SKIPC + 3 * C + 1) + rows * (3 * C + 2 + PI + 2 * UV + 3 * UV + 2 * C + 2 + HUV + 4 * QK + 2 * S + HID + HID / 2 + C + QKV + 2 * C) +
                sub * S * QK * HID + sub * HEADS * T * T;
     f += (size_t)batch * (Lpad + 1 + 9 * FB * T + Lsrc);
+    if (rs_in) f += (size_t)batch * L;
+    if (rs_out) f += (size_t)batch * ((size_t)L + L_final);
     return f * sizeof(float);
   }
   int launches(int batch) override {
     const int per_dense = DEPTH * 7, per_path = 28, per_ta = 11;   // Att is three GEMM launches
     const int bb = 8 + per_dense + layers * (2 * per_path + per_ta) + 2 * (6 + per_dense);
-    return 6 + ((batch + SUB - 1) / SUB) * bb;
+    return 6 + (rs_in ? 1 : 0) + (rs_out ? (out_dtype == ADN_F32 ? 1 : 2) : 0) + ((batch + SUB - 1) / SUB) * bb;
   }
   void set_stop_after(int n) override { stop_after = n; }
 
@@ -153,8 +171,17 @@ class Model : public ModelImpl {
       return s == ADN_OK;
     };
     auto tk = [&](const char* name) { if (tick) tick(tick_ctx, name); };
-    // F32 / F16 inputs are in [-1, 1]: x32768 (:540-541)
-    if (!chk(adn_rms_normalize(d_in, in_dtype, in_dtype == ADN_I16 ? 1.0f : 32768.0f, 1e-6f, xn, nf, B, L, Lpad, st), "rms_normalize")) return ADN_ERR_CUDA;
+    // F32 / F16 inputs are in [-1, 1]: x32768 (:540-541).  With a resampled input the reference lifts, then interpolates
+    // (:542-549); the lift is a power of two, so interpolating the raw samples and lifting inside the RMS pass is bit-identical.
+    const void* src = d_in;
+    int src_dtype = in_dtype;
+    int extra = 0;
+    if (rs_in) {
+      if (!chk(adn_resample_linear(d_in, in_dtype, xr, B, L_in, L, 0.0, st), "input resampler")) return ADN_ERR_CUDA;
+      tk("resample_in");
+      src = xr; src_dtype = ADN_F32; ++extra;
+    }
+    if (!chk(adn_rms_normalize(src, src_dtype, in_dtype == ADN_I16 ? 1.0f : 32768.0f, 1e-6f, xn, nf, B, L, Lpad, st), "rms_normalize")) return ADN_ERR_CUDA;
     tk("rms_normalize");
     if (!chk(adn_stft_forward(stft, xn, spec, B, Lpad, st), "stft")) return ADN_ERR_CUDA;
     tk("stft");
@@ -169,13 +196,28 @@ class Model : public ModelImpl {
       forward(ex, ws, W, feat + (size_t)b0 * 3 * T * FB, mask + (size_t)b0 * FB * T, cplx + (size_t)b0 * 2 * FB * T, nb, T);
       ex.capture = false;                          // stage dumps cover the first pass only
     }
-    last_launches = ex.launches + 6;
+    last_launches = ex.launches + 6 + extra;
     if (!chk(adn_spec_recombine(ADN_FAMILY_MOSSFORMERGAN, mask, cplx, keep, spec2, B, FB, T, st), "spec_recombine")) return ADN_ERR_CUDA;
     tk("spec_recombine");
     if (!chk(adn_stft_inverse(stft, spec2, wave, B, T, st), "istft")) return ADN_ERR_CUDA;
     tk("istft");
-    if (!chk(adn_condition_output(ADN_FAMILY_MOSSFORMERGAN, wave, Lsrc, nf, 1, d_out, out_dtype, B, L, st), "condition_output")) return ADN_ERR_CUDA;
-    tk("condition_output");
+    if (!rs_out) {
+      if (!chk(adn_condition_output(ADN_FAMILY_MOSSFORMERGAN, wave, Lsrc, nf, 1, d_out, out_dtype, B, L, st), "condition_output")) return ADN_ERR_CUDA;
+      tk("condition_output");
+    } else {
+      // x norm_factor -> interpolate -> output rule (:877-897).  The F32 rule of adn_condition_output (x nf x 2^-15) commutes
+      // exactly with the interpolation (power-of-two scale), so: condition to fp32, resample, then restore x 2^15 / clamp /
+      // truncate for int16.
+      if (!chk(adn_condition_output(ADN_FAMILY_MOSSFORMERGAN, wave, Lsrc, nf, 1, ymod, ADN_F32, B, L, st), "condition_output")) return ADN_ERR_CUDA;
+      tk("condition_output");
+      float* dst = out_dtype == ADN_F32 ? (float*)d_out : yout;
+      if (!chk(adn_resample_linear(ymod, ADN_F32, dst, B, L, L_final, 0.0, st), "output resampler")) return ADN_ERR_CUDA;
+      tk("resample_out");
+      const long long no = (long long)B * L_final;
+      if (out_dtype == ADN_I16) ex.run(no, dfs::OutI16{yout, (int16_t*)d_out});
+      else if (out_dtype == ADN_F16) ex.run(no, CastF16{yout, (__half*)d_out});
+      last_launches += out_dtype == ADN_F32 ? 1 : 2;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("mossformergan_se run: ") + cudaGetErrorString(e); return ADN_ERR_CUDA; }
     return ADN_OK;

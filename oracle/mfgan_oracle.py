@@ -444,14 +444,29 @@ def _triple_attention(P: dict, pre: str, c: GanConfig, x: torch.Tensor) -> torch
     return o * P[f"{pre}.p_g"][None, :, None, :] + P[f"{pre}.p_beta"][None, :, None, :]
 
 
+def model_len(length: int, in_rate: int = 16000) -> int:
+    """MODEL_AUDIO_LENGTH (:37)."""
+    return int(round(length * 16000 / in_rate))
+
+
+def out_len(length: int, out_rate: int = 16000, in_rate: int = 16000) -> int:
+    """OUTPUT_AUDIO_LENGTH (:38) -- the reference scales the INPUT length by out / model rate."""
+    return model_len(length, in_rate) if out_rate == 16000 else int(round(length * out_rate / 16000))
+
+
 def mfgan_forward(sd: dict, audio: torch.Tensor, c: GanConfig = GanConfig(), in_dtype: str = "F32", out_dtype: str = "F32",
-                  dbg=None, folded: dict | None = None) -> torch.Tensor:
-    """audio (B,1,L) in `in_dtype` ([-1,1] for float dtypes, :540-541) -> (B,1,L) in `out_dtype`; windows independent."""
-    B, _, L = audio.shape
+                  dbg=None, folded: dict | None = None, in_rate: int = 16000, out_rate: int = 16000) -> torch.Tensor:
+    """audio (B,1,L) in `in_dtype` ([-1,1] for float dtypes, :540-541) -> (B,1,L_out) in `out_dtype`; windows independent.
+    in_rate / out_rate != 16 kHz: `F.interpolate(size=...)` behind the int16 lift (:542-549) and behind the x norm_factor
+    (:884-891)."""
+    L_in = audio.shape[-1]
     spec = SPECS["mossformergan_se_16k"]
     x = audio.float()
     if "int" not in in_dtype.lower():
         x = x * 32768.0
+    if in_rate != 16000:
+        x = F.interpolate(x, size=model_len(L_in, in_rate), mode="linear", align_corners=False)
+    B, _, L = x.shape
     nf = torch.sqrt(torch.mean(x * x, dim=-1, keepdim=True) + 1e-6)
     x = x / nf
     pad = (c.hop - L % c.hop) % c.hop
@@ -512,12 +527,16 @@ def mfgan_forward(sd: dict, audio: torch.Tensor, c: GanConfig = GanConfig(), in_
     if dbg is not None:
         dbg["mask"], dbg["complex"], dbg["spec_out"] = mask, cplx, fin
     y = istft_packed(spec, fin.reshape(B, 2 * c.n_bins, T))[..., :L] * nf
+    if out_rate != 16000:
+        y = F.interpolate(y, size=out_len(L_in, out_rate, in_rate), mode="linear", align_corners=False)
     if "int" in out_dtype.lower():
         return y.clamp(min=-32768.0, max=32767.0).to(torch.int16)
     y = y * INV_INT16
     return y if "32" in out_dtype else y.to(torch.float16)
 
 
-def mfgan_forward_batch(sd, audio, c: GanConfig = GanConfig(), in_dtype="F32", out_dtype="F32", chunk: int = 4):
-    outs = [mfgan_forward(sd, audio[s:s + chunk], c, in_dtype, out_dtype) for s in range(0, audio.shape[0], chunk)]
+def mfgan_forward_batch(sd, audio, c: GanConfig = GanConfig(), in_dtype="F32", out_dtype="F32", chunk: int = 4,
+                        in_rate: int = 16000, out_rate: int = 16000):
+    outs = [mfgan_forward(sd, audio[s:s + chunk], c, in_dtype, out_dtype, in_rate=in_rate, out_rate=out_rate)
+            for s in range(0, audio.shape[0], chunk)]
     return torch.cat(outs, dim=0)

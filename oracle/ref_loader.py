@@ -246,7 +246,7 @@ def load_mf2ss(input_audio_length: int, io_dtype: str = "F32", in_rate: int = 16
     return ns, build
 
 
-def load_mfgan(input_audio_length: int, io_dtype: str = "F32"):
+def load_mfgan(input_audio_length: int, io_dtype: str = "F32", in_rate: int = 16000, out_rate: int = 16000):
     """Reference MossFormerGAN-SE-16K wrapper (`MOSSFORMER_SE` of MossFormerGAN_SE_16K/Export_MossFormer_SE.py)
     for one un-folded window.  The wrapper's forward is made of leaf ops; its constructor and forward read
     parameters off the absent `clearvoice` generator.  Returns (namespace, build) with
@@ -271,6 +271,8 @@ def load_mfgan(input_audio_length: int, io_dtype: str = "F32"):
             "IN_AUDIO_DTYPE       = 'INT16'": f"IN_AUDIO_DTYPE       = '{io_dtype}'",
             "OUT_AUDIO_DTYPE      = 'INT16'": f"OUT_AUDIO_DTYPE      = '{io_dtype}'",
             "USE_BATCH_FOLD       = True": "USE_BATCH_FOLD       = False",
+            "IN_SAMPLE_RATE       = 16000": f"IN_SAMPLE_RATE       = {int(in_rate)}",
+            "OUT_SAMPLE_RATE      = 16000": f"OUT_SAMPLE_RATE      = {int(out_rate)}",
         },
     )
 

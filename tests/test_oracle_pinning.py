@@ -453,6 +453,33 @@ def test_gtcrn_oracle_output_resampling_matches_reference_module(L, out_rate, dt
         assert float((r - o).abs().max()) <= 2e-6
 
 
+@needs_ref
+@pytest.mark.parametrize("L,in_rate,out_rate,dt", [(1200, 8000, 48000, "F32"), (7200, 48000, 8000, "INT16"), (3300, 22500, 16000, "F32"),
+                                                   (2400, 16000, 24000, "INT16")])
+def test_mfgan_oracle_resampling_matches_reference_module(L, in_rate, out_rate, dt):
+    """IN / OUT_SAMPLE_RATE != 16 kHz: the wrapper's linear resamplers (MossFormerGAN_SE_16K/Export_MossFormer_SE.py:542-549,
+    :884-891; OUTPUT_AUDIO_LENGTH scales the INPUT length by out / model rate, :38) -- executed reference vs the restatement."""
+    import mfgan_oracle as go
+
+    cfg = go.GanConfig(layers=1)
+    sd = go.random_state_dict(cfg, 2)
+    _, build = ref_loader.load_mfgan(L, dt, in_rate, out_rate)
+    hold = go.skeleton(cfg)
+    hold.load_state_dict(sd)
+    w = build(hold)
+    g = torch.Generator().manual_seed(1)
+    x = (torch.rand(1, 1, L, generator=g) * 2 - 1) * 0.5
+    xin = x if dt == "F32" else torch.round(x * 32767).to(torch.int16)
+    with torch.inference_mode():
+        yr = w(xin.clone())
+        yo = go.mfgan_forward(sd, xin, cfg, dt, dt, in_rate=in_rate, out_rate=out_rate)
+    assert yr.shape == yo.shape == (1, 1, go.out_len(L, out_rate, in_rate)) and yr.dtype == yo.dtype
+    if dt == "INT16":
+        assert int((yr.int() - yo.int()).abs().max()) <= 1
+    else:
+        assert float((yr - yo).abs().max()) <= 2e-6
+
+
 # ----------------------------------------------------------------------------- DFSMN (48 kHz)
 @pytest.mark.parametrize("fixture,dt", [("dfsmn_f32_L9600_l3", "F32"), ("dfsmn_int16_L6720_l3", "INT16")])
 def test_dfsmn_oracle_matches_golden(fixture, dt, golden_dir):
