@@ -250,8 +250,29 @@ def main_dfsmn():
             print(f"dfsmn {dt} L{L}: {tuple(xin.shape)} -> {tuple(y.shape)} max|y| {y.float().abs().max().item():.4f}")
 
 
+def main_ulunas():
+    """UL-UNAS fixtures (no CUDA path and no restatement yet): the reference `ULUNAS_CUSTOM` executed on
+    seeded default-init weights with randomised BatchNorm statistics.  The RAW (pre-fold) state_dict travels in the fixture
+    (`sd/<key>`), because the model class itself cannot run on the GPU box; 16000 samples -> 15872 (63 frames), F32 and INT16,
+    one all-zero window."""
+    assert ref_loader.reference_available()
+    for dt in ("F32", "INT16"):
+        _, build = ref_loader.load_ulunas(16000, dt)
+        w, raw = build(None, 0)
+        x = synth_audio(16000, 1357, batch=3)
+        x[2] = 0.0
+        xin = x if dt == "F32" else torch.round(x * 32767.0).to(torch.int16)
+        with torch.inference_mode():
+            y = torch.cat([w(xin[i:i + 1].clone()) for i in range(3)], dim=0)
+        np.savez_compressed(GOLDEN / f"ulunas_{dt.lower()}_L16000.npz", x=xin.numpy(), y=y.numpy(), seed=0,
+                            **{f"sd/{k}": v.numpy() for k, v in raw.items()})
+        print(f"ulunas {dt}: {tuple(xin.shape)} -> {tuple(y.shape)} max|y| {y.float().abs().max().item():.4f}")
+
+
 if __name__ == "__main__":
-    if "--dfsmn" in sys.argv:
+    if "--ulunas" in sys.argv:
+        main_ulunas()
+    elif "--dfsmn" in sys.argv:
         main_dfsmn()
     elif "--mfgan" in sys.argv:
         main_mfgan()

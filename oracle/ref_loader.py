@@ -328,3 +328,55 @@ def load_dfsmn(input_audio_length: int, io_dtype: str = "F32"):
                                ns["OUT_SAMPLE_RATE"], use_batch_fold=False, fold_window=ns["FOLD_WINDOW_LENGTH"], static_batch=1).eval()
 
     return ns, build
+
+
+def load_ulunas(input_audio_length: int = 16000, io_dtype: str = "F32"):
+    """Reference UL-UNAS wrapper (`ULUNAS_CUSTOM` of UL-UNAS/Export_UL_UNAS.py) for one un-folded window at 16 kHz.
+    The model definition is self-contained in the script (like GTCRN's).  Returns (namespace, build) with
+    build(state_dict | None, seed) -> (wrapper, raw_state_dict): `ULUNAS()` with seeded default init and randomised BatchNorm
+    statistics (so the BN fold is exercised) unless a raw state_dict is given, then `prepare_for_export_` and the wrapper exactly
+    as the script's main does (:938-975)."""
+    import torch
+
+    ns = load_export_namespace(
+        "UL-UNAS",
+        "Export_UL_UNAS.py",
+        {
+            "INPUT_AUDIO_LENGTH    = 32000": f"INPUT_AUDIO_LENGTH    = {int(input_audio_length)}",
+            "IN_AUDIO_DTYPE        = 'INT16'": f"IN_AUDIO_DTYPE        = '{io_dtype}'",
+            "OUT_AUDIO_DTYPE       = 'INT16'": f"OUT_AUDIO_DTYPE       = '{io_dtype}'",
+        },
+    )
+
+    def build(state_dict=None, seed: int = 0):
+        is_int = "int" in io_dtype.lower()
+        with torch.inference_mode():
+            S = ns["STFT_Process"]
+            stft = S(model_type="stft_B", n_fft=ns["NFFT"], hop_len=ns["HOP_LENGTH"], win_length=ns["WINDOW_LENGTH"], max_frames=0,
+                     window_type=ns["WINDOW_TYPE"], center_pad=True, pad_mode=ns["STFT_PAD_MODE"],
+                     input_scale=ns["INV_INT16"] if is_int else 1.0).eval()
+            istft = S(model_type="istft_B", n_fft=ns["NFFT"], hop_len=ns["HOP_LENGTH"], win_length=ns["WINDOW_LENGTH"],
+                      max_frames=ns["MAX_SIGNAL_LENGTH"], window_type=ns["WINDOW_TYPE"], center_pad=True,
+                      pad_mode=ns["STFT_PAD_MODE"], output_scale=32767.0 if is_int else 1.0, static_norm=True).eval()
+            torch.manual_seed(seed)
+            net = ns["ULUNAS"]().eval()
+            if state_dict is None:
+                g = torch.Generator().manual_seed(seed + 1)
+                for m in net.modules():
+                    if isinstance(m, torch.nn.BatchNorm2d):
+                        m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=g))
+                        m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+                        m.weight.copy_(1.0 + 0.2 * torch.randn(m.weight.shape, generator=g))
+                        m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+            else:
+                missing, unexpected = net.load_state_dict(state_dict, strict=False)
+                assert not unexpected, unexpected
+            raw = {k: v.clone() for k, v in net.state_dict().items()}
+            net.prepare_for_export_()
+            wrapper = ns["ULUNAS_CUSTOM"](net.float(), stft, istft, ns["IN_SAMPLE_RATE"], ns["OUT_SAMPLE_RATE"],
+                                          remove_dc_offset=ns["REMOVE_DC_OFFSET"], use_batch_fold=False,
+                                          fold_window=ns["FOLD_WINDOW_LENGTH"], input_scale_folded=is_int,
+                                          output_scale_folded=is_int).eval()
+        return wrapper, raw
+
+    return ns, build

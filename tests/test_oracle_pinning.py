@@ -526,3 +526,21 @@ def test_dfsmn_oracle_matches_reference_module(dt):
         assert int((yr.int() - yo.int()).abs().max()) <= 1
     else:
         assert float((yr - yo).abs().max()) <= 2e-6
+
+
+# ----------------------------------------------------------------------------- UL-UNAS (fixtures only: no restatement, no CUDA path yet)
+@needs_ref
+@pytest.mark.parametrize("dt", ["F32", "INT16"])
+def test_ulunas_fixture_reproduces_from_reference(dt, golden_dir):
+    """tests/golden/ulunas_*.npz carry the raw state_dict, input and output of the reference `ULUNAS_CUSTOM`
+    (UL-UNAS/Export_UL_UNAS.py:654-912) executed here: re-executing the reference on the stored weights reproduces the stored
+    output bit for bit (the fixture is what a future CUDA path for this family will be held to)."""
+    g = np.load(golden_dir / f"ulunas_{dt.lower()}_L16000.npz")
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")}
+    _, build = ref_loader.load_ulunas(16000, dt)
+    w, raw = build(sd, 0)
+    assert set(raw) == set(sd) and all(torch.equal(raw[k], sd[k]) for k in sd)
+    x = torch.from_numpy(g["x"])
+    with torch.inference_mode():
+        y = torch.cat([w(x[i:i + 1].clone()) for i in range(x.shape[0])], dim=0)
+    assert y.shape == (3, 1, 15872) and np.array_equal(y.numpy(), g["y"])
