@@ -528,7 +528,7 @@ def test_dfsmn_oracle_matches_reference_module(dt):
         assert float((yr - yo).abs().max()) <= 2e-6
 
 
-# ----------------------------------------------------------------------------- UL-UNAS (fixtures only: no restatement, no CUDA path yet)
+# ----------------------------------------------------------------------------- UL-UNAS (oracle half: no CUDA path yet)
 @needs_ref
 @pytest.mark.parametrize("dt", ["F32", "INT16"])
 def test_ulunas_fixture_reproduces_from_reference(dt, golden_dir):
@@ -544,3 +544,47 @@ def test_ulunas_fixture_reproduces_from_reference(dt, golden_dir):
     with torch.inference_mode():
         y = torch.cat([w(x[i:i + 1].clone()) for i in range(x.shape[0])], dim=0)
     assert y.shape == (3, 1, 15872) and np.array_equal(y.numpy(), g["y"])
+
+
+@pytest.mark.parametrize("dt", ["F32", "INT16"])
+def test_ulunas_oracle_matches_golden(dt, golden_dir):
+    """oracle/ulunas_oracle.py (restated folds + forward over the RAW state_dict) vs the outputs of the executed reference."""
+    import ulunas_oracle as uo
+
+    g = np.load(golden_dir / f"ulunas_{dt.lower()}_L16000.npz")
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")}
+    with torch.inference_mode():
+        y = uo.ulunas_forward(sd, torch.from_numpy(g["x"]), dt, dt).numpy()
+    assert y.shape == g["y"].shape and y.dtype == g["y"].dtype
+    if dt == "INT16":
+        assert np.abs(y.astype(np.int32) - g["y"].astype(np.int32)).max() <= 1
+    else:
+        assert np.abs(y - g["y"]).max() <= 2e-6
+
+
+@needs_ref
+def test_ulunas_oracle_matches_reference_module_stage_by_stage():
+    """Fresh seed, a different window length: every encoder / dual-path / decoder block output of the restatement vs forward
+    hooks on the executed reference (after `prepare_for_export_`), and the waveform."""
+    import ulunas_oracle as uo
+
+    L = 8192
+    _, build = ref_loader.load_ulunas(L, "F32")
+    w, raw = build(None, 7)
+    got = {}
+    net = w.ulunas
+    hooks = [m.register_forward_hook(lambda _m, _i, o, k=f"enc{i}": got.__setitem__(k, o)) for i, m in enumerate(net.encoder.en_convs)]
+    hooks += [m.register_forward_hook(lambda _m, _i, o, k=f"dp{i}": got.__setitem__(k, o)) for i, m in enumerate(net.dpgrnn)]
+    hooks += [m.register_forward_hook(lambda _m, _i, o, k=f"dec{i}": got.__setitem__(k, o)) for i, m in enumerate(net.decoder.de_convs)]
+    x = synth_audio(L, 11, batch=1)
+    dbg = {}
+    with torch.inference_mode():
+        yr = w(x.clone())
+        yo = uo.ulunas_forward(raw, x, dbg=dbg)
+    for h in hooks:
+        h.remove()
+    assert set(got) == set(dbg) and len(got) == 12
+    for k in sorted(got):
+        assert got[k].shape == dbg[k].shape, k
+        assert float((got[k] - dbg[k]).abs().max()) <= 2e-5 * max(1.0, float(got[k].abs().max())), k
+    assert yr.shape == yo.shape == (1, 1, 256 * (L // 256)) and float((yr - yo).abs().max()) <= 2e-6
