@@ -133,3 +133,21 @@ def dfsmn_model(state_dict: dict, hyper=None, input_audio_length: int = 96000, i
     hyper = hyper or dfsmn_params.DfsmnHyper()
     md = dfsmn_params.metadata(hyper, input_audio_length, in_dtype, out_dtype)
     return Model.from_tensors(md, dfsmn_params.pack(state_dict, hyper, input_audio_length), device_id)
+
+
+def export_ulunas(state_dict: dict, path, input_audio_length: int = 32000, in_dtype: str = "INT16", out_dtype: str = "INT16") -> dict[str, str]:
+    """UL-UNAS `.adn` for one static window length (counterpart of UL-UNAS/Export_UL_UNAS.py:918-1012).  `state_dict`: the raw
+    `ULUNAS().state_dict()` (the checkpoint after the reference's own `convert_state_dict`), see adn/ulunas_params.py."""
+    from . import ulunas_params
+
+    md = ulunas_params.metadata(input_audio_length, in_dtype, out_dtype)
+    modelfile.save(path, md, ulunas_params.pack(state_dict, input_audio_length, in_dtype, out_dtype))
+    return md
+
+
+def ulunas_model(state_dict: dict, input_audio_length: int = 32000, in_dtype: str = "F32", out_dtype: str = "F32", device_id: int = 0):
+    from . import ulunas_params
+    from .model import Model
+
+    md = ulunas_params.metadata(input_audio_length, in_dtype, out_dtype)
+    return Model.from_tensors(md, ulunas_params.pack(state_dict, input_audio_length, in_dtype, out_dtype), device_id)

@@ -50,3 +50,7 @@ ModelImpl* mfgan_create(const std::map<std::string, std::string>& meta, const st
 // DFSMN 48 kHz: csrc/dfsmn.cu
 ModelImpl* dfsmn_create(const std::map<std::string, std::string>& meta, const std::map<std::string, TensorRef>& index,
                         const float* h_blob, float* d_blob, int device, int sms, std::string& err);
+
+// UL-UNAS 16 kHz: csrc/ulunas.cu
+ModelImpl* ulunas_create(const std::map<std::string, std::string>& meta, const std::map<std::string, TensorRef>& index,
+                         const float* h_blob, float* d_blob, int device, int sms, std::string& err);
