@@ -68,7 +68,7 @@ typedef struct {
 
 /* Replaces onnxruntime.InferenceSession(path, ...) (Inference_GTCRN_ONNX.py:213-214,237):
  * builds a model of desc["model_family"] (gtcrn | mel_band_roformer | mossformer2_se | mossformer2_ss |
- * mossformergan_se | dfsmn)
+ * mossformergan_se | dfsmn | ulunas)
  * on CUDA device `device_id` from a host blob of `nfloats` fp32 values.  The keys are the reference's
  * metadata keys (audio_onnx_metadata.py:115-205) plus, for mossformer2_se, the optional
  * "matmul_dtype" = F32 (default: 3xTF32 tensor-core GEMMs, fp32-class) | BF16 (the layers' GEMMs on bf16
