@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the north-star path: noisy chunk in -> clean chunk out (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--model gtcrn|mbr|mf2se|mf2ss|mfgan|dfsmn] [--batch B] [--impl adn|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model gtcrn|mbr|mf2se|mf2ss|mfgan|dfsmn|ulunas] [--batch B] [--impl adn|reference]
 
 A "step" is one pass of the hot path over one batch of B synthetic chunks per GPU.
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field's definition.
@@ -560,8 +560,58 @@ class DfsmnWorkload:
         })
 
 
+class UlunasWorkload:
+    """UL-UNAS 16 kHz: ERB features, 5 + 5 X-blocks with cTFA, 2 grouped dual-path GRU blocks; 1 s windows.
+    Weights: the raw state_dict stored in tests/golden/ulunas_f32_L16000.npz (seeded init of the reference class, which cannot
+    run on the GPU box)."""
+    name = "ulunas"
+    default_batch = 64
+    chunk, sr, channels, t_frames = 16000, 16000, 1, 63
+    cpu_chunks, ref_chunks = 32, 8
+    in_name = "noisy_audio"
+    cpu_desc = "oracle/ulunas_oracle.py (PyTorch-eager restatement, pinned stage by stage to the executed reference)"
+
+    def describe(self, B):
+        return f"UL-UNAS 16 kHz, {B} x 1 s windows (16000 samples, 63 frames x 129 ERB bands) per GPU per step, F32 in / F32 out"
+
+    def audio_seconds(self, B):
+        return B * self.chunk / self.sr
+
+    def weights(self):
+        g = np.load(ROOT / "tests" / "golden" / "ulunas_f32_L16000.npz")
+        return {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")}
+
+    def build(self, sd, device):
+        from adn import export
+        return export.ulunas_model(sd, self.chunk, "F32", "F32", device_id=device)
+
+    def export(self, sd, path):
+        from adn import export
+        export.export_ulunas(sd, path, self.chunk, "F32", "F32")
+
+    inputs = MfganWorkload.inputs
+
+    def cpu_rate(self, sd, n_chunks, threads):
+        import ulunas_oracle as uo
+        torch.set_num_threads(threads)
+        g = torch.Generator().manual_seed(7)
+        x = (torch.rand(1, 1, self.chunk, generator=g) * 2 - 1) * 0.3
+        with torch.inference_mode():
+            uo.ulunas_forward(sd, x)
+            t0 = time.perf_counter()
+            for _ in range(n_chunks):
+                uo.ulunas_forward(sd, x)
+            dt = time.perf_counter() - t0
+        return n_chunks * self.chunk / self.sr / dt, dt
+
+    def kernel_work(self):
+        T = self.t_frames
+        return _Work({"ulunas_gru": (4 * 2 * T * 64, 2 * 3 * T * 64 * 96), "stft": (4 * (16000 + 514 * T), 2 * 514 * 512 * T),
+                      "istft": (4 * (514 * T + 15872), 2 * 514 * 512 * T)})
+
+
 WORKLOADS = {"gtcrn": GtcrnWorkload, "mbr": MbrWorkload, "mf2se": Mf2seWorkload, "mf2ss": Mf2ssWorkload, "mfgan": MfganWorkload,
-             "dfsmn": DfsmnWorkload}
+             "dfsmn": DfsmnWorkload, "ulunas": UlunasWorkload}
 
 
 class ClockSampler:
