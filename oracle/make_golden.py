@@ -269,8 +269,31 @@ def main_ulunas():
         print(f"ulunas {dt}: {tuple(xin.shape)} -> {tuple(y.shape)} max|y| {y.float().abs().max().item():.4f}")
 
 
+def main_hgtcrn():
+    """H-GTCRN fixtures (no restatement and no CUDA path yet): the reference `H_GTCRN_CUSTOM` (2-channel
+    STFT -> WPE -> AuxIVA -> GTCRN_IVA -> ISTFT) executed on seeded default-init weights with randomised BatchNorm statistics;
+    the RAW state_dict of `GTCRN_IVA` travels in the fixture (`sd/<key>`).  Stereo windows of 16128 samples (64 frames), F32 and
+    INT16; correlated channels (a delayed, attenuated copy plus independent noise), as a two-microphone pickup would give."""
+    assert ref_loader.reference_available()
+    L = 16128
+    for dt in ("F32", "INT16"):
+        _, build = ref_loader.load_hgtcrn(L, dt)
+        w, raw = build(None, 0)
+        a = synth_audio(L, 97, batch=2)[:, 0]
+        n = synth_audio(L, 98, batch=2)[:, 0]
+        x = torch.stack((a, 0.7 * torch.roll(a, 3, dims=-1) + 0.3 * n), dim=1)           # (2 windows, 2 channels, L)
+        xin = x if dt == "F32" else torch.round(x * 32767.0).to(torch.int16)
+        with torch.inference_mode():
+            y = torch.cat([w(xin[i:i + 1].clone()) for i in range(2)], dim=0)
+        np.savez_compressed(GOLDEN / f"hgtcrn_{dt.lower()}_L{L}.npz", x=xin.numpy(), y=y.numpy(), seed=0,
+                            **{f"sd/{k}": v.numpy() for k, v in raw.items()})
+        print(f"hgtcrn {dt}: {tuple(xin.shape)} -> {tuple(y.shape)} max|y| {y.float().abs().max().item():.4f}")
+
+
 if __name__ == "__main__":
-    if "--ulunas" in sys.argv:
+    if "--hgtcrn" in sys.argv:
+        main_hgtcrn()
+    elif "--ulunas" in sys.argv:
         main_ulunas()
     elif "--dfsmn" in sys.argv:
         main_dfsmn()

@@ -380,3 +380,56 @@ def load_ulunas(input_audio_length: int = 16000, io_dtype: str = "F32"):
         return wrapper, raw
 
     return ns, build
+
+
+def load_hgtcrn(input_audio_length: int = 16128, io_dtype: str = "F32"):
+    """Reference H-GTCRN wrapper (`H_GTCRN_CUSTOM` of H-GTCRN/Export_H_GTCRN.py: 2-channel STFT -> WPE -> AuxIVA -> GTCRN_IVA ->
+    ISTFT) for one un-folded stereo window at 16 kHz; the model definition is self-contained in the script.  Returns
+    (namespace, build) with build(state_dict | None, seed) -> (wrapper, raw_state_dict), constructed as the script's main does
+    (:1075-1140) around `GTCRN_IVA()` with seeded default init and randomised BatchNorm statistics."""
+    import torch
+
+    ns = load_export_namespace(
+        "H-GTCRN",
+        "Export_H_GTCRN.py",
+        {
+            "INPUT_AUDIO_LENGTH   = 32000": f"INPUT_AUDIO_LENGTH   = {int(input_audio_length)}",
+            "IN_AUDIO_DTYPE       = 'INT16'": f"IN_AUDIO_DTYPE       = '{io_dtype}'",
+            "OUT_AUDIO_DTYPE      = 'INT16'": f"OUT_AUDIO_DTYPE      = '{io_dtype}'",
+        },
+    )
+
+    def build(state_dict=None, seed: int = 0):
+        with torch.inference_mode():
+            S = ns["STFT_Process"]
+            T = ns["MAX_SIGNAL_LENGTH"]
+            stft = S(model_type="stft_B", n_fft=ns["NFFT"], hop_len=ns["HOP_LENGTH"], win_length=ns["WINDOW_LENGTH"], max_frames=0,
+                     window_type=ns["WINDOW_TYPE"], center_pad=True, pad_mode=ns["PAD_MODE"], input_scale=1.0).eval()
+            istft = S(model_type="istft_B", n_fft=ns["NFFT"], hop_len=ns["HOP_LENGTH"], win_length=ns["WINDOW_LENGTH"], max_frames=T,
+                      window_type=ns["WINDOW_TYPE"], center_pad=True, pad_mode=ns["PAD_MODE"], output_scale=1.0, static_cola=True).eval()
+            wpe = ns["OnnxFriendlyWPE"](n_channels=2, rt60=ns["WPE_RT60"], hop_length=ns["HOP_LENGTH"], delay=ns["WPE_DELAY"],
+                                        sample_rate=16000, num_iter=ns["WPE_ITER"], ns_iter=ns["CG_SOLVE_ITER"], n_freq_bins=257,
+                                        max_frames=T, batch_size=1, dynamic_frames=False).eval()
+            iva = ns["OnnxFriendlyAuxIVA"](n_iter=ns["IVA_ITER"], n_channels=2, batch_size=1, n_frames=T).eval()
+            torch.manual_seed(seed)
+            net = ns["GTCRN_IVA"](batch_size=1, n_frames=T).eval()
+            if state_dict is None:
+                g = torch.Generator().manual_seed(seed + 1)
+                for m in net.modules():
+                    if isinstance(m, torch.nn.BatchNorm2d):
+                        m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=g))
+                        m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+                        m.weight.copy_(1.0 + 0.2 * torch.randn(m.weight.shape, generator=g))
+                        m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+            else:
+                missing, unexpected = net.load_state_dict(state_dict, strict=False)
+                assert not unexpected, unexpected
+            raw = {k: v.clone() for k, v in net.state_dict().items()}
+            net.fuse_bn_()
+            wrapper = ns["H_GTCRN_CUSTOM"](net, stft, istft, wpe, iva, n_fft=512, in_sample_rate=16000, out_sample_rate=16000,
+                                           use_batch_fold=False, fold_window=ns["FOLD_WINDOW_LENGTH"],
+                                           model_audio_length=ns["MODEL_AUDIO_LENGTH"], n_frames=T, frontend_batch=1,
+                                           fold_input_pcm_scale=False, fold_output_pcm_scale=False).eval()
+        return wrapper, raw
+
+    return ns, build

@@ -588,3 +588,21 @@ def test_ulunas_oracle_matches_reference_module_stage_by_stage():
         assert got[k].shape == dbg[k].shape, k
         assert float((got[k] - dbg[k]).abs().max()) <= 2e-5 * max(1.0, float(got[k].abs().max())), k
     assert yr.shape == yo.shape == (1, 1, 256 * (L // 256)) and float((yr - yo).abs().max()) <= 2e-6
+
+
+# ----------------------------------------------------------------------------- H-GTCRN (fixtures only: no restatement, no CUDA path yet)
+@needs_ref
+@pytest.mark.parametrize("dt", ["F32", "INT16"])
+def test_hgtcrn_fixture_reproduces_from_reference(dt, golden_dir):
+    """tests/golden/hgtcrn_*.npz carry the raw `GTCRN_IVA` state_dict, stereo input and mono output of the reference
+    `H_GTCRN_CUSTOM` (H-GTCRN/Export_H_GTCRN.py:903-1063) executed here; re-executing the reference on the stored weights
+    reproduces the stored output bit for bit (the target a restatement / CUDA path for this family will be held to)."""
+    g = np.load(golden_dir / f"hgtcrn_{dt.lower()}_L16128.npz")
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")}
+    _, build = ref_loader.load_hgtcrn(16128, dt)
+    w, raw = build(sd, 0)
+    assert set(raw) == set(sd)
+    x = torch.from_numpy(g["x"])
+    with torch.inference_mode():
+        y = torch.cat([w(x[i:i + 1].clone()) for i in range(x.shape[0])], dim=0)
+    assert y.shape == (2, 1, 16128) and np.array_equal(y.numpy(), g["y"])
