@@ -2,6 +2,7 @@
 // the GPU): plain loops per functor, the contractions through translate() + gemm_ref.  Never linked into libadn.so.
 #include "dfsmn_ops.cuh"
 
+#include <cmath>
 #include <map>
 #include <string>
 #include <vector>
@@ -53,7 +54,7 @@ extern "C" int dfsmn_host_forward(const char* const* names, const unsigned long 
   }
   const int T = (L - dfs::FRAME) / dfs::HOP + 1;
   std::vector<std::vector<float>> bufs;
-  auto alloc = [&](size_t n) { bufs.emplace_back(n ? n : 1, 0.0f); return bufs.back().data(); };
+  auto alloc = [&](size_t n) { bufs.emplace_back(n ? n : 1, std::nanf("")); return bufs.back().data(); };   // NaN poison: cudaMalloc does not zero either
   dfs::Workspace ws;
   if (!dfs::alloc_ws(ws, B, T, alloc)) return -2;
   std::vector<float> x((size_t)B * L);

@@ -4,6 +4,7 @@
 // machine without a GPU (tests/test_mfgan_host.py).  Never linked into libadn.so.
 #include "mfgan_gemm.cuh"
 
+#include <cmath>
 #include <map>
 #include <string>
 #include <vector>
@@ -68,7 +69,7 @@ extern "C" int mfgan_host_forward(const char* const* names, const unsigned long 
     return -1;
   }
   std::vector<std::vector<float>> bufs;
-  auto alloc = [&](size_t n) { bufs.emplace_back(n ? n : 1, 0.0f); return bufs.back().data(); };
+  auto alloc = [&](size_t n) { bufs.emplace_back(n ? n : 1, std::nanf("")); return bufs.back().data(); };   // NaN poison: cudaMalloc does not zero either
   gan::Workspace ws;
   if (!gan::alloc_ws(ws, B, T, alloc)) return -2;
   HostExec ex;

@@ -2,6 +2,7 @@
 // GPU): plain loops per functor, Linear through translate() + gemm_ref as on the GPU.  Never linked into libadn.so.
 #include "ulunas_ops.cuh"
 
+#include <cmath>
 #include <map>
 #include <string>
 #include <vector>
@@ -52,7 +53,7 @@ extern "C" int ulunas_host_forward(const char* const* names, const unsigned long
     return -1;
   }
   std::vector<std::vector<float>> bufs;
-  auto alloc = [&](size_t n) { bufs.emplace_back(n ? n : 1, 0.0f); return bufs.back().data(); };
+  auto alloc = [&](size_t n) { bufs.emplace_back(n ? n : 1, std::nanf("")); return bufs.back().data(); };   // NaN poison: cudaMalloc does not zero either
   uln::Workspace ws;
   if (!uln::alloc_ws(ws, B, T, alloc)) return -2;
   HostExec ex;
