@@ -119,3 +119,19 @@ def test_pack_matches_oracle_fold():
     assert md["model_family"] == "dfsmn" and md["max_signal_length"] == "5" and md["dfsmn_lorder"] == "20"
     with pytest.raises(ValueError):
         dp.pack(sd, h, 1920 + 100)
+
+
+def test_host_sequence_matches_reference_fixture(host_lib, golden_dir):
+    """The same launch sequence vs the output of the EXECUTED reference (tests/golden/dfsmn_f32_L9600_l3.npz, one all-zero window)."""
+    from adn import dfsmn_params as dp
+
+    g = np.load(golden_dir / "dfsmn_f32_L9600_l3.npz")
+    cfg = do.DfsmnConfig(layers=int(g["layers"]))
+    sd = do.random_state_dict(cfg, int(g["seed"]))
+    h = dp.DfsmnHyper(layers=cfg.layers)
+    x = torch.from_numpy(g["x"])
+    spec, _, _ = run_host(host_lib, dp.pack(sd, h, x.shape[-1]), h, x)
+    with torch.inference_mode():
+        y = istft_packed(do.SYNTHESIS, torch.from_numpy(spec))
+    assert y.shape == tuple(g["y"].shape) and float((y - torch.from_numpy(g["y"])).abs().max()) <= 1e-5
+    assert not y[2].any()

@@ -91,3 +91,21 @@ def test_host_sequence_matches_oracle(L, B, dt, host_lib, golden_dir):
         print(f"wave   {e:11.3e} {float(y_ref.abs().max()):11.3e}")
         assert e <= 2e-6
     assert not bad, f"stages out of tolerance: {bad}"
+
+
+def test_host_sequence_matches_reference_fixture(host_lib, golden_dir):
+    """The same launch sequence vs the output of the EXECUTED reference (tests/golden/ulunas_f32_L16000.npz: 63 frames, one
+    all-zero window) -- no oracle in between except its STFT / ISTFT tables, which are pinned bit-equal to the reference's."""
+    from adn import ulunas_params as up
+
+    g = np.load(golden_dir / "ulunas_f32_L16000.npz")
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")}
+    x = torch.from_numpy(g["x"])
+    blob = up.pack(sd, x.shape[-1], "F32", "F32")
+    with torch.inference_mode():
+        spec = F.conv1d(pad_signal(uo.SPEC, x), torch.from_numpy(blob["stft.fwd"]).unsqueeze(1), stride=256)
+        out, _, _ = run_host(host_lib, blob, spec)
+        inv = F.conv_transpose1d(torch.from_numpy(out), inverse_basis(uo.SPEC).unsqueeze(1), stride=256)
+        y = inv[..., 256:inv.shape[-1] - 256] * torch.from_numpy(blob["stft.norm"])
+    assert y.shape == tuple(g["y"].shape) and float((y - torch.from_numpy(g["y"])).abs().max()) <= 2e-6
+    assert not y[2].any()                                   # the all-zero window stays exactly zero
