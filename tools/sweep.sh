@@ -7,6 +7,10 @@ run gtcrn 1 200; run gtcrn 64 100; run gtcrn 512 100
 run mf2se 1 20; run mf2se 64 10; run mf2se 512 5
 run mf2ss 1 10; run mf2ss 64 5; run mf2ss 512 3
 run mbr 1 10; run mbr 64 5; run mbr 256 3
+# families added late in round 1 (first-correct designs: small step counts; dfsmn / ulunas have not run on a GPU yet)
+run mfgan 1 5; run mfgan 64 3; run mfgan 512 1
+run dfsmn 1 20; run dfsmn 64 10; run dfsmn 512 5
+run ulunas 1 5; run ulunas 64 3; run ulunas 512 1
 python - <<PY
 import json
 for l in open("$out"):
