@@ -36,3 +36,24 @@ def test_resampled_io(L, in_rate, out_rate, dt, libadn):
         assert err <= 1e-4
     assert int(m.debug_read("launches")[0]) == m.launches_per_run(2)
     m.close()
+
+
+def test_window_independence_at_the_bench_size(libadn):
+    """BASELINE configs[4] shape: 6 blocks, 64 x 1 s windows in one run (four backbone passes of 16): every probed window equals
+    its own single-window run bit for bit, an all-zero window stays finite, and the batch is finite."""
+    from adn import export, mfgan_params
+
+    cfg = go.GanConfig(layers=6)
+    sd = go.random_state_dict(cfg, 0)
+    L, B = 16000, 64
+    g = torch.Generator().manual_seed(21)
+    x = (torch.rand(B, 1, L, generator=g) * 2 - 1) * 0.4
+    x[17] = 0.0
+    m = export.mfgan_model(sd, mfgan_params.GanHyper(layers=6), L)
+    xc = x.cuda()
+    yb = m.run(xc).cpu()
+    assert torch.isfinite(yb).all()
+    for i in (0, 15, 16, 17, 47, 63):
+        yi = m.run(xc[i:i + 1].contiguous()).cpu()
+        assert torch.equal(yi[0], yb[i]), i
+    m.close()
