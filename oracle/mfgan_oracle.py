@@ -3,9 +3,9 @@
 
 Restates `MOSSFORMER_SE.__init__` (weight folds) and `forward` / `_mossformer_block` (reference
 `MossFormerGAN_SE_16K/Export_MossFormer_SE.py:83-897`) as plain functions over a flat `state_dict`.
-Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline legs may import it.  No CUDA
-path exists for this family yet: this file, its parameter skeleton and the fixtures under
-tests/golden/mfgan_*.npz are the oracle half of row a9.
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline legs may import it.  The CUDA
+path it checks is csrc/mfgan_ops.cuh + csrc/mfgan.cu (model family `mossformergan_se`); `dbg` collects the
+stage dumps the host-harness test and the GPU stage test compare against.
 
 The reference wrapper reads its parameters from the un-vendored `clearvoice` package
 (`clearvoice.models.mossformer_gan_se.generator`, no pinned version).  The wrapper's

@@ -1,5 +1,5 @@
-"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference UL-UNAS path.  No CUDA path consumes it
-yet: this file and tests/golden/ulunas_*.npz are the oracle half of that row.
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference UL-UNAS path; the oracle of the CUDA path
+csrc/ulunas_ops.cuh + csrc/ulunas.cu (model family `ulunas`), whose launch sequence tests/test_ulunas_host.py checks on the CPU.
 
 Restates `ULUNAS` + `ULUNAS_CUSTOM.forward` (reference `UL-UNAS/Export_UL_UNAS.py:51-912`) as plain functions over the RAW
 (pre-fold) `state_dict` of `ULUNAS()`: BatchNorm folds (`fuse_bn_`, :240-262), AffinePReLU slopes (:122-129), the
