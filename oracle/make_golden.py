@@ -251,7 +251,7 @@ def main_dfsmn():
 
 
 def main_ulunas():
-    """UL-UNAS fixtures (no CUDA path and no restatement yet): the reference `ULUNAS_CUSTOM` executed on
+    """UL-UNAS fixtures: the reference `ULUNAS_CUSTOM` executed on
     seeded default-init weights with randomised BatchNorm statistics.  The RAW (pre-fold) state_dict travels in the fixture
     (`sd/<key>`), because the model class itself cannot run on the GPU box; 16000 samples -> 15872 (63 frames), F32 and INT16,
     one all-zero window."""

@@ -528,7 +528,7 @@ def test_dfsmn_oracle_matches_reference_module(dt):
         assert float((yr - yo).abs().max()) <= 2e-6
 
 
-# ----------------------------------------------------------------------------- UL-UNAS (oracle half: no CUDA path yet)
+# ----------------------------------------------------------------------------- UL-UNAS
 @needs_ref
 @pytest.mark.parametrize("dt", ["F32", "INT16"])
 def test_ulunas_fixture_reproduces_from_reference(dt, golden_dir):
