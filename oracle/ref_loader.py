@@ -433,3 +433,58 @@ def load_hgtcrn(input_audio_length: int = 16128, io_dtype: str = "F32"):
         return wrapper, raw
 
     return ns, build
+
+
+def load_zipenh(input_audio_length: int = 16000, io_dtype: str = "F32"):
+    """Reference ZipEnhancer wrapper (`ZipEnhancer` of ZipEnhancer/Export_ZipEnhancer.py) for one un-folded window at 16 kHz.
+    The wrapper drives the un-vendored `modelscope` Zipformer2 modules; every forward with arithmetic in it is overridden in the
+    reference file itself (`apply_onnx_export_patches`, :341-355).  The skeleton classes of `zipenh_oracle` (shapes only) are
+    registered under the modelscope module names, the reference installs ITS forwards on them, and the reference wrapper runs
+    around the holder.  Returns (namespace, build) with build(holder) -> wrapper."""
+    import torch
+
+    import zipenh_oracle as zo
+
+    base = "modelscope.models.audio.ans.zipenhancer_layers"
+    for name in ("modelscope", "modelscope.models", "modelscope.models.base", "modelscope.models.audio", "modelscope.models.audio.ans",
+                 base, base + ".scaling", base + ".zipformer"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["modelscope.models.base"].Model = object
+    scaling, zipformer = sys.modules[base + ".scaling"], sys.modules[base + ".zipformer"]
+    sys.modules[base].scaling, sys.modules[base].zipformer = scaling, zipformer
+    for cls in ("BiasNorm", "ActivationDropoutAndLinear"):
+        setattr(scaling, cls, getattr(zo, cls))
+    for cls in ("Zipformer2EncoderLayer", "BypassModule", "SimpleDownsample", "SimpleUpsample", "RelPositionMultiheadAttentionWeights",
+                "SelfAttention", "NonlinAttention", "ConvolutionModule", "CompactRelPositionalEncoding"):
+        setattr(zipformer, cls, getattr(zo, cls))
+    if "Rewrite_ONNX_Asymmetric_Padding" not in sys.modules:
+        mod = types.ModuleType("Rewrite_ONNX_Asymmetric_Padding")
+        mod.rewrite_asymmetric_causal_convs = lambda *a, **k: None
+        sys.modules["Rewrite_ONNX_Asymmetric_Padding"] = mod
+
+    ns = load_export_namespace(
+        "ZipEnhancer",
+        "Export_ZipEnhancer.py",
+        {
+            "INPUT_AUDIO_LENGTH = 32000": f"INPUT_AUDIO_LENGTH = {int(input_audio_length)}",
+            "IN_AUDIO_DTYPE  = 'INT16'": f"IN_AUDIO_DTYPE  = '{io_dtype}'",
+            "OUT_AUDIO_DTYPE = 'INT16'": f"OUT_AUDIO_DTYPE = '{io_dtype}'",
+            "USE_BATCH_FOLD        = True": "USE_BATCH_FOLD        = False",
+        },
+    )
+    ns["apply_onnx_export_patches"]()
+
+    def build(holder):
+        with torch.inference_mode():
+            S = ns["STFT_Process"]
+            stft = S(model_type="stft_B", n_fft=ns["NFFT"], hop_len=ns["HOP_LENGTH"], win_length=ns["WINDOW_LENGTH"], max_frames=0,
+                     window_type=ns["WINDOW_TYPE"], center_pad=True, pad_mode="reflect").eval()
+            istft = S(model_type="istft_B", n_fft=ns["NFFT"], hop_len=ns["HOP_LENGTH"], win_length=ns["WINDOW_LENGTH"],
+                      max_frames=ns["MAX_SIGNAL_LENGTH"], window_type=ns["WINDOW_TYPE"], center_pad=True, pad_mode="reflect",
+                      static_norm=ns["STATIC_SHAPE"]).eval()
+            return ns["ZipEnhancer"](holder.eval().float(), stft, istft, ns["IN_SAMPLE_RATE"], ns["OUT_SAMPLE_RATE"],
+                                     use_batch_fold=False, fold_window=ns["FOLD_WINDOW_LENGTH"],
+                                     use_rectangular_istft=ns["USE_RECTANGULAR_ISTFT"]).eval()
+
+    return ns, build
