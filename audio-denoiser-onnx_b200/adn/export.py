@@ -113,6 +113,28 @@ def mfgan_model(state_dict: dict, hyper=None, input_audio_length: int = 16000, i
     return Model.from_tensors(md, mfgan_params.pack(state_dict, hyper, input_audio_length, in_rate), device_id)
 
 
+def export_zipenh(state_dict: dict, path, hyper=None, input_audio_length: int = 16000, in_dtype: str = "INT16",
+                  out_dtype: str = "INT16") -> dict[str, str]:
+    """ZipEnhancer `.adn` for one static window length at 16 kHz (counterpart of ZipEnhancer/Export_ZipEnhancer.py:938-1001).
+    `state_dict` keys: see adn/zipenh_params.py."""
+    from . import zipenh_params
+
+    hyper = hyper or zipenh_params.ZipHyper()
+    md = zipenh_params.metadata(hyper, input_audio_length, in_dtype, out_dtype)
+    modelfile.save(path, md, zipenh_params.pack(state_dict, hyper, input_audio_length))
+    return md
+
+
+def zipenh_model(state_dict: dict, hyper=None, input_audio_length: int = 16000, in_dtype: str = "F32", out_dtype: str = "F32",
+                 device_id: int = 0):
+    from . import zipenh_params
+    from .model import Model
+
+    hyper = hyper or zipenh_params.ZipHyper()
+    md = zipenh_params.metadata(hyper, input_audio_length, in_dtype, out_dtype)
+    return Model.from_tensors(md, zipenh_params.pack(state_dict, hyper, input_audio_length), device_id)
+
+
 def export_dfsmn(state_dict: dict, path, hyper=None, input_audio_length: int = 96000, in_dtype: str = "INT16",
                  out_dtype: str = "INT16") -> dict[str, str]:
     """DFSMN (48 kHz) `.adn` for one static window length (counterpart of DFSMN/Export_DFSMN.py:252-324).

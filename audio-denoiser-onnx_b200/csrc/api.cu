@@ -621,7 +621,7 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
   if (!is_ss && (!need("nfft", snfft) || !need("hop_length", shop))) return fail(ADN_ERR_INVALID);
   if (is_ss) { snfft = "16"; shop = "8"; }          // Conv1d(k16, s8) framing, snip-edges
   m->family = fam;
-  if (fam != "gtcrn" && fam != "mel_band_roformer" && fam != "mossformer2_se" && fam != "mossformergan_se" && fam != "dfsmn" && fam != "ulunas" && !is_ss) {
+  if (fam != "gtcrn" && fam != "mel_band_roformer" && fam != "mossformer2_se" && fam != "mossformergan_se" && fam != "dfsmn" && fam != "ulunas" && fam != "zipenhancer" && !is_ss) {
     m->err = "unsupported model_family '" + fam + "'";
     return fail(ADN_ERR_UNSUPPORTED);
   }
@@ -705,6 +705,7 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
                   : fam == "mossformergan_se" ? mfgan_create(m->meta, m->index, weights, m->d_blob, device_id, m->sms, m->err)
                   : fam == "dfsmn" ? dfsmn_create(m->meta, m->index, weights, m->d_blob, device_id, m->sms, m->err)
                   : fam == "ulunas" ? ulunas_create(m->meta, m->index, weights, m->d_blob, device_id, m->sms, m->err)
+                  : fam == "zipenhancer" ? zipenh_create(m->meta, m->index, weights, m->d_blob, device_id, m->sms, m->err)
                           : mbr_create(m->meta, m->index, weights, m->d_blob, device_id, m->sms, m->err);
     if (!m->impl) s = ADN_ERR_INVALID;
     else {                                          // host staging follows the family's own I/O description

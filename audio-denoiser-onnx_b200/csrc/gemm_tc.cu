@@ -123,7 +123,7 @@ struct Smem {
   static constexpr uint32_t W_TILE_BYTES = BN * BK * 4;           // BN rows of 128 bytes (32 tf32 or 64 bf16)
   static constexpr int PLANES = BF ? 1 : 2;
   static constexpr uint32_t STAGE_BYTES = PLANES * (A_TILE_BYTES + W_TILE_BYTES);
-  static constexpr int STAGES = BF ? 4 : ((BN <= 128) ? 3 : 2);
+  static constexpr int STAGES = BF ? 4 : ((BN <= 64) ? 4 : (BN <= 128) ? 3 : 2);
   static constexpr uint32_t EPI_STAGE_BYTES = NEPI * 8 * 36 * 4;    // per-warp 8x36 transpose tiles of the epilogue
   static constexpr uint32_t TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 };
@@ -199,12 +199,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           if (g.w_group > 1) { wk += (b0 % g.w_group) * g.w_kstep; wb = b0 / g.w_group; }   // FLASH group of a window
           const bool second = g.k_split > 0 && kb * BKE >= g.k_split;   // second operand of a K-concatenated product
           if (second) wk = kb * BKE - g.k_split;
+          int ak = kb * BKE, at = t0;
+          if (g.taps > 0) { const int tap = kb / g.tap_kb; ak = g.tap_k0 + (kb - tap * g.tap_kb) * BKE; at = t0 + g.tap_shift[tap]; }
           if (BF) {
-            tma_load_3d(st, &map_a_hi, &full[stage], kb * BKE, t0, b0);
+            tma_load_3d(st, &map_a_hi, &full[stage], ak, at, b0);
             tma_load_3d(st + A_TILE_BYTES, second ? &map_w2_hi : &map_w_hi, &full[stage], wk, nt * BN, wb);
           } else {
-            tma_load_3d(st, &map_a_hi, &full[stage], kb * BKE, t0, b0);
-            tma_load_3d(st + A_TILE_BYTES, &map_a_lo, &full[stage], kb * BKE, t0, b0);
+            tma_load_3d(st, &map_a_hi, &full[stage], ak, at, b0);
+            tma_load_3d(st + A_TILE_BYTES, &map_a_lo, &full[stage], ak, at, b0);
             tma_load_3d(st + 2 * A_TILE_BYTES, second ? &map_w2_hi : &map_w_hi, &full[stage], wk, nt * BN, wb);
             tma_load_3d(st + 2 * A_TILE_BYTES + S::W_TILE_BYTES, second ? &map_w2_lo : &map_w_lo, &full[stage], wk, nt * BN, wb);
           }
@@ -397,11 +399,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const float slope = __ldg(g.act_param);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) x[j] = x[j] >= 0.f ? x[j] : slope * x[j];
+              } else if (g.act == ACT_SWOOSH_L || g.act == ACT_SWOOSH_R) {
+                const float off = g.act == ACT_SWOOSH_L ? 4.0f : 1.0f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float y = x[j] - off;
+                  x[j] = (y > 20.f ? y : log1pf(expf(y))) - 0.08f * x[j];
+                }
               }
               const long long o = m * g.ldc + n0 + 4 * cq;
               {
                 const float4 r4 = res4[hrow][it];
                 x[0] += r4.x; x[1] += r4.y; x[2] += r4.z; x[3] += r4.w;
+              }
+              if (g.resid2) {
+                const float4 o4 = *reinterpret_cast<const float4*>(g.resid2 + o);
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(g.colscale + n0) + cq);
+                x[0] = o4.x + (x[0] - o4.x) * s4.x; x[1] = o4.y + (x[1] - o4.y) * s4.y;
+                x[2] = o4.z + (x[2] - o4.z) * s4.z; x[3] = o4.w + (x[3] - o4.w) * s4.w;
               }
               if (g.C) *reinterpret_cast<float4*>(g.C + o) = make_float4(x[0], x[1], x[2], x[3]);
               if (g.Chi && !g.Clo) {                 // bf16 operand plane for a bf16 consumer
@@ -569,6 +584,7 @@ cudaError_t launch(const TcPlan& p, const TcArgs& a, int epi, int sms, cudaStrea
   if (p.bn == 176) return p.bf16 ? cudaErrorInvalidValue : launch_bn<176>(p, a, epi, sms, st);
   if (p.bn == 256) return launch_bn<256>(p, a, epi, sms, st);
   if (p.bn == 128) return launch_bn<128>(p, a, epi, sms, st);
+  if (p.bn == 64) return p.bf16 ? cudaErrorInvalidValue : launch_bn<64>(p, a, epi, sms, st);
   return cudaErrorInvalidValue;
 }
 

@@ -37,16 +37,25 @@ struct TcArgs {
   long long ldc;
   int act;               // ACT_*
   const float* act_param; // ACT_PRELU: device scalar slope
+  // conv-as-GEMM (ZipEnhancer dense blocks): taps > 0 turns K into a concatenation of `taps` channel windows of tap_kb K blocks
+  // each; K block kb reads A-map columns tap_k0 + (kb % tap_kb)*32 of row t + tap_shift[kb / tap_kb] (rows outside the
+  // chunk read as zeros: the causal / sub-band zero padding of the conv).  The W operand keeps its plain K axis.
+  int taps, tap_kb, tap_k0;
+  int tap_shift[6];
+  // EPI_LIN: after the residual, v = resid2[m*ldc+n] + (v - resid2[m*ldc+n]) * colscale[n]   (Zipformer2 BypassModule)
+  const float* resid2;
+  const float* colscale;
   int i16_mode;          // EPI_ISTFT int16 output: 0 = x*32767, clamp, truncate (GTCRN, Export_GTCRN.py:680-693)
                          //   1 = clamp(x,-1,32767/32768)*32768, truncate (MossFormer2_SE_48K/Export_MossFormer_SE.py:499-504)
 };
 
-enum { ACT_NONE = 0, ACT_GELU = 1, ACT_TANH = 2, ACT_SILU = 3, ACT_RELU = 4, ACT_RELU2 = 5, ACT_PRELU = 6 };
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_TANH = 2, ACT_SILU = 3, ACT_RELU = 4, ACT_RELU2 = 5, ACT_PRELU = 6,
+       ACT_SWOOSH_L = 7, ACT_SWOOSH_R = 8 };   // softplus(x - 4 | 1) - 0.08 x (Export_ZipEnhancer.py:131-140)
 
 struct TcPlan {
   CUtensorMap map_a_hi, map_a_lo, map_w_hi, map_w_lo;
   CUtensorMap map_w2_hi, map_w2_lo;   // only read when args.k_split > 0
-  int bn = 0;            // N tile: 128 | 176 | 256
+  int bn = 0;            // N tile: 64 | 128 | 176 | 256
   bool bf16 = false;     // operands are single bf16 planes (maps built with bf16 = true); EPI_LIN only, bn 128 | 256
 };
 

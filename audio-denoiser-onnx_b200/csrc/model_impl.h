@@ -54,3 +54,7 @@ ModelImpl* dfsmn_create(const std::map<std::string, std::string>& meta, const st
 // UL-UNAS 16 kHz: csrc/ulunas.cu
 ModelImpl* ulunas_create(const std::map<std::string, std::string>& meta, const std::map<std::string, TensorRef>& index,
                          const float* h_blob, float* d_blob, int device, int sms, std::string& err);
+
+// ZipEnhancer 16 kHz: csrc/zipenh.cu
+ModelImpl* zipenh_create(const std::map<std::string, std::string>& meta, const std::map<std::string, TensorRef>& index,
+                         const float* h_blob, float* d_blob, int device, int sms, std::string& err);

@@ -1,0 +1,718 @@
+// ZipEnhancer 16 kHz (BASELINE configs[1]) behind the C ABI: model family `zipenhancer`.
+// Reference: ZipEnhancer/Export_ZipEnhancer.py `ZipEnhancer.forward` (:818-927).
+//   RMS norm (:839-840) -> STFT 400/100 hann (:841) -> compressed magnitude + phase (:843-844)                [ends.cu operators]
+//   -> DenseEncoder, 4 dual-path Zipformer2 encoders, mask / phase decoders                                 [zipenh_ops.cuh sequence]
+//   -> magnitude decompress x unit phase (:882-892) -> ISTFT x 1/sum w^2 (:893) -> x norm factor, output rule (:899-926) [ends.cu]
+// The sequence's LinOps (every Linear, the (2,3) dilated causal convs, the stride-2 and sub-pixel convs) run on the tcgen05
+// 3xTF32 GEMM (gemm_tc.cu: TMA-fed, TMEM accumulators), planned once per batch size; attention weights, the two attention
+// value products, the gated depthwise conv and the final BiasNorm are cooperative kernels below; the remaining element-wise
+// functors run one thread per output.
+#include "zipenh_ops.cuh"
+
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "model_impl.h"
+
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+namespace zip {
+
+template <class F>
+__global__ void __launch_bounds__(256) op_kernel(long long n, F f) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) f(i);
+}
+
+template <class F> struct OpName { static const char* get() { return "zip_op"; } };
+#define ZIP_OP_NAME(T, s) template <> struct OpName<T> { static const char* get() { return s; } }
+ZIP_OP_NAME(FeatConv, "zip_feat_conv");
+ZIP_OP_NAME(InPart, "zip_in_part");
+ZIP_OP_NAME(InFin, "zip_in_fin");
+ZIP_OP_NAME(InApply, "zip_in_apply");
+ZIP_OP_NAME(PadCopy, "zip_pad_copy");
+ZIP_OP_NAME(AttnW, "zip_attn_w");
+ZIP_OP_NAME(SaApply, "zip_sa_apply");
+ZIP_OP_NAME(NlApply, "zip_nl_apply");
+ZIP_OP_NAME(GluDwConv, "zip_glu_dwconv");
+ZIP_OP_NAME(NormBypass, "zip_norm_bypass");
+ZIP_OP_NAME(Down, "zip_down");
+ZIP_OP_NAME(UpCombine, "zip_up_combine");
+ZIP_OP_NAME(Head, "zip_head");
+
+// ------------------------------------------------------------------------------------------------ attention weights
+// One CTA = one (sequence, head): q | p rows, k^T and the head's relative-position table staged in shared memory; one warp
+// = four query rows at a time, lanes over the keys; softmax in registers; rows written coalesced.
+template <int JJ>
+__global__ void __launch_bounds__(256) attn_w_kernel(const float* __restrict__ ap, SeqMap sm, const float* __restrict__ pos,
+                                                    float* __restrict__ aw) {
+  extern __shared__ float sh[];
+  const int S = sm.S, SP = (S + 31) & ~31, RP = 2 * S;
+  float* kT = sh;                  // [QD][SP]
+  float* qp = kT + QD * SP;        // [S][16]: q[12] | p[4]
+  float* R = qp + S * 16;          // [PD][RP]
+  const long long n = blockIdx.x / HEADS;
+  const int h = blockIdx.x % HEADS;
+  for (int idx = threadIdx.x; idx < S * 7; idx += 256) {
+    const int s = idx / 7, e = idx - s * 7;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(ap + sm.tok(n, s) * AP + h * HB) + e);
+    if (e < 3) *reinterpret_cast<float4*>(qp + s * 16 + 4 * e) = v;
+    else if (e < 6) {
+      const int d = 4 * (e - 3);
+      kT[(d + 0) * SP + s] = v.x; kT[(d + 1) * SP + s] = v.y; kT[(d + 2) * SP + s] = v.z; kT[(d + 3) * SP + s] = v.w;
+    } else *reinterpret_cast<float4*>(qp + s * 16 + 12) = v;
+  }
+  const int RL = 2 * S - 1;
+  for (int idx = threadIdx.x; idx < PD * RL; idx += 256) {
+    const int d = idx / RL, r = idx - d * RL;
+    R[d * RP + r] = __ldg(pos + (long long)h * PD * RL + idx);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i0 = warp * 4; i0 < S; i0 += 32) {
+    float q[4][16];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int ii = min(i0 + r, S - 1);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 v = *reinterpret_cast<const float4*>(qp + ii * 16 + 4 * e);
+        q[r][4 * e] = v.x; q[r][4 * e + 1] = v.y; q[r][4 * e + 2] = v.z; q[r][4 * e + 3] = v.w;
+      }
+    }
+    float sc[4][JJ];
+#pragma unroll
+    for (int jj = 0; jj < JJ; ++jj) {
+      const int j = lane + 32 * jj;
+      if (j < S) {
+        float k[QD];
+#pragma unroll
+        for (int d = 0; d < QD; ++d) k[d] = kT[d * SP + j];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int ii = min(i0 + r, S - 1);
+          float a = 0.f;
+#pragma unroll
+          for (int d = 0; d < QD; ++d) a += q[r][d] * k[d];
+          float e = 0.f;
+#pragma unroll
+          for (int d = 0; d < PD; ++d) e += q[r][QD + d] * R[d * RP + (S - 1 - ii + j)];
+          sc[r][jj] = a + e;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) sc[r][jj] = -INFINITY;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float mx = sc[r][0];
+#pragma unroll
+      for (int jj = 1; jj < JJ; ++jj) mx = fmaxf(mx, sc[r][jj]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < JJ; ++jj) { sc[r][jj] = expf(sc[r][jj] - mx); sum += sc[r][jj]; }
+      sum = warp_sum(sum);
+      const float inv = 1.0f / sum;
+      if (i0 + r < S) {
+        float* row = aw + ((n * HEADS + h) * S + i0 + r) * (long long)S;
+#pragma unroll
+        for (int jj = 0; jj < JJ; ++jj) {
+          const int j = lane + 32 * jj;
+          if (j < S) row[j] = sc[r][jj] * inv;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ attention value products
+// 48 partial sums per lane -> lane pair (2p, 2p+1) holds the complete sums base .. base+2 in v[0..2]
+template <int MASK, int N>
+__device__ __forceinline__ void fold_step(float (&v)[48], int lane) {
+  const bool up = lane & MASK;
+#pragma unroll
+  for (int k = 0; k < N / 2; ++k) {
+    const float send = up ? v[k] : v[k + N / 2];
+    const float keep = up ? v[k + N / 2] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, MASK);
+  }
+}
+__device__ __forceinline__ int fold48(float (&v)[48], int lane) {
+  fold_step<16, 48>(v, lane);
+  fold_step<8, 24>(v, lane);
+  fold_step<4, 12>(v, lane);
+  fold_step<2, 6>(v, lane);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], 1);
+  return ((lane & 16) ? 24 : 0) + ((lane & 8) ? 12 : 0) + ((lane & 4) ? 6 : 0) + ((lane & 2) ? 3 : 0);
+}
+
+constexpr int VST = 52;            // value-row stride in shared memory: conflict-free 128-bit loads at lane stride 52 floats
+// One CTA = one sequence; the 48-wide value rows staged in shared memory (NonlinAttention: x_mid * tanh(s) formed while
+// staging).  One warp = one task, lanes over the keys, 48 accumulators per lane, folded across the warp at the end:
+//   SelfAttention (NL = false): task = (head, four query rows) -> 4 x 12 outputs;
+//   NonlinAttention (NL = true): task = one query row -> 48 outputs of head 0, times the y gate.
+template <bool NL, int JJ>
+__global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict__ aw, SeqMap sm, const float* __restrict__ src,
+                                                        float* __restrict__ ohi, float* __restrict__ olo) {
+  extern __shared__ float sh[];
+  const int S = sm.S;
+  const long long n = blockIdx.x;
+  for (int idx = threadIdx.x; idx < S * 12; idx += 256) {
+    const int s = idx / 12, e = idx - s * 12;
+    float4 v;
+    if (NL) {
+      const float4* pj = reinterpret_cast<const float4*>(src + sm.tok(n, s) * (3 * NH));
+      const float4 g = __ldg(pj + e), m = __ldg(pj + NH / 4 + e);
+      v = make_float4(m.x * tanhf(g.x), m.y * tanhf(g.y), m.z * tanhf(g.z), m.w * tanhf(g.w));
+    } else {
+      v = __ldg(reinterpret_cast<const float4*>(src + sm.tok(n, s) * SV) + e);
+    }
+    *reinterpret_cast<float4*>(sh + s * VST + 4 * e) = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntask = NL ? S : HEADS * ((S + 3) / 4);
+  for (int task = warp; task < ntask; task += 8) {
+    const int h = NL ? 0 : task % HEADS;
+    const int i0 = NL ? task : (task / HEADS) * 4;
+    float acc[48];
+#pragma unroll
+    for (int k = 0; k < 48; ++k) acc[k] = 0.f;
+    const float* arow = aw + ((n * HEADS + h) * S) * (long long)S;
+#pragma unroll
+    for (int jj = 0; jj < JJ; ++jj) {
+      const int j = lane + 32 * jj;
+      if (j < S) {
+        if (NL) {
+          const float a = __ldg(arow + (long long)i0 * S + j);
+#pragma unroll
+          for (int e = 0; e < 12; ++e) {
+            const float4 v = *reinterpret_cast<const float4*>(sh + j * VST + 4 * e);
+            acc[4 * e] += a * v.x; acc[4 * e + 1] += a * v.y; acc[4 * e + 2] += a * v.z; acc[4 * e + 3] += a * v.w;
+          }
+        } else {
+          float v[12];
+#pragma unroll
+          for (int e = 0; e < 3; ++e) {
+            const float4 t = *reinterpret_cast<const float4*>(sh + j * VST + h * VD + 4 * e);
+            v[4 * e] = t.x; v[4 * e + 1] = t.y; v[4 * e + 2] = t.z; v[4 * e + 3] = t.w;
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const float a = __ldg(arow + (long long)min(i0 + r, S - 1) * S + j);
+#pragma unroll
+            for (int c = 0; c < 12; ++c) acc[r * 12 + c] += a * v[c];
+          }
+        }
+      }
+    }
+    const int base = fold48(acc, lane);
+    if (!(lane & 1)) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int idx = base + k;
+        int i, c;
+        if (NL) { i = i0; c = idx; }
+        else { i = i0 + idx / 12; c = h * VD + idx % 12; }
+        if (i < S) {
+          const long long t = sm.tok(n, i);
+          float v = acc[k];
+          if (NL) v *= __ldg(src + t * (3 * NH) + 2 * NH + c);
+          float hi, lo;
+          split_tf32(v, hi, lo);
+          ohi[t * SV + c] = hi; olo[t * SV + c] = lo;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ gated depthwise conv
+// One thread = one (sequence, channel) strip walking the sequence: u = x_mid * sigmoid(gate) computed once per position and
+// kept in a 15-deep register ring, so the fused projection is read once and only the tf32 planes of the SwooshR output are
+// written.  Adjacent threads = adjacent channels (coalesced rows of 64 floats).
+__global__ void __launch_bounds__(256) glu_dwconv_kernel(const float* __restrict__ cp, SeqMap sm, long long nseq,
+                                                        const float* __restrict__ w, const float* __restrict__ b,
+                                                        float* __restrict__ ohi, float* __restrict__ olo) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int c = (int)(idx % C);
+  const long long n = idx / C;
+  if (n >= nseq) return;
+  const int S = sm.S;
+  float wk[DWK], ring[DWK];
+#pragma unroll
+  for (int k = 0; k < DWK; ++k) wk[k] = __ldg(w + c * DWK + k);
+  const float bias = __ldg(b + c);
+  auto u_at = [&](int sj) -> float {
+    if (sj < 0 || sj >= S) return 0.f;
+    const float* pj = cp + sm.tok(n, sj) * (2 * C);
+    return __ldg(pj + c) * sigmoidf_(__ldg(pj + C + c));
+  };
+  // slot (sj + 7) % 15 holds u[sj]; at step s the taps k read slots (s + k) % 15
+#pragma unroll
+  for (int k = 0; k < DWK; ++k) ring[k] = u_at(k - DWK / 2);
+  for (int s0 = 0; s0 < S; s0 += DWK) {
+#pragma unroll
+    for (int d = 0; d < DWK; ++d) {
+      const int s = s0 + d;
+      if (s < S) {
+        const float nxt = u_at(s + DWK / 2 + 1);
+        float acc = bias;
+#pragma unroll
+        for (int k = 0; k < DWK; ++k) acc += wk[k] * ring[(d + k) % DWK];
+        const long long o = sm.tok(n, s) * C + c;
+        float hi, lo;
+        split_tf32(swoosh(acc, 1.0f), hi, lo);
+        ohi[o] = hi; olo[o] = lo;
+        ring[d] = nxt;
+      }
+    }
+  }
+}
+
+// final BiasNorm + bypasses: half a warp per token row (float4 per lane)
+__global__ void __launch_bounds__(256) norm_bypass_kernel(const float* __restrict__ x, float* __restrict__ x0, long long M,
+                                                         const float* __restrict__ nbias, const float* __restrict__ nscale,
+                                                         const float* __restrict__ rscale, float* __restrict__ ohi,
+                                                         float* __restrict__ olo) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long row = idx >> 4;
+  const int l = (int)(idx & 15);
+  const long long rr = row < M ? row : M - 1;
+  const float4 xv = *reinterpret_cast<const float4*>(x + rr * C + 4 * l);
+  const float4 nb = __ldg(reinterpret_cast<const float4*>(nbias) + l);
+  float ss = (xv.x - nb.x) * (xv.x - nb.x) + (xv.y - nb.y) * (xv.y - nb.y) + (xv.z - nb.z) * (xv.z - nb.z) + (xv.w - nb.w) * (xv.w - nb.w);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (row >= M) return;
+  const float nrm = sqrtf(ss);
+  const float4 ns = __ldg(reinterpret_cast<const float4*>(nscale) + l), rs = __ldg(reinterpret_cast<const float4*>(rscale) + l);
+  const float4 o0 = *reinterpret_cast<const float4*>(x0 + row * C + 4 * l);
+  float v[4] = {(xv.x / nrm) * ns.x + o0.x * rs.x, (xv.y / nrm) * ns.y + o0.y * rs.y, (xv.z / nrm) * ns.z + o0.z * rs.z,
+                (xv.w / nrm) * ns.w + o0.w * rs.w};
+  float h[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_tf32(v[j], h[j], lo[j]);
+  *reinterpret_cast<float4*>(x0 + row * C + 4 * l) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(ohi + row * C + 4 * l) = make_float4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<float4*>(olo + row * C + 4 * l) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+__global__ void pad_split_w_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) split_tf32(src[i], hi[i], lo[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ executor
+struct PlanEntry {
+  bool valid = false;
+  LinOp key;
+  tc::TcPlan plan;
+  tc::TcArgs args;
+};
+
+static bool same_op(const LinOp& a, const LinOp& b) {
+  bool s = a.a_hi == b.a_hi && a.a_lo == b.a_lo && a.a_sB == b.a_sB && a.a_sR == b.a_sR && a.a_r0 == b.a_r0 && a.a_ke == b.a_ke &&
+           a.a_rows == b.a_rows && a.chunks == b.chunks && a.rows == b.rows && a.K == b.K && a.N == b.N && a.taps == b.taps &&
+           a.tap_c == b.tap_c && a.a_k0 == b.a_k0 && a.W.w == b.W.w && a.W.b == b.W.b && a.act == b.act && a.resid == b.resid &&
+           a.resid2 == b.resid2 && a.colscale == b.colscale && a.Cf == b.Cf && a.c_hi == b.c_hi && a.c_lo == b.c_lo && a.ldc == b.ldc;
+  for (int i = 0; s && i < 6; ++i) s = a.tap_shift[i] == b.tap_shift[i];
+  return s;
+}
+
+struct WPlanes { float *hi = nullptr, *lo = nullptr; };
+
+struct CudaExec {
+  cudaStream_t st = nullptr;
+  int sms = 148;
+  int launches = 0, gemms = 0;
+  bool functors_only = false;       // ADN_ZIP_FUNCTORS=1: run the plain functors instead of the cooperative kernels (debugging)
+  ImplTickFn tick = nullptr;
+  void* tick_ctx = nullptr;
+  bool capture = false;
+  std::map<std::string, std::vector<float>>* dumps = nullptr;
+  std::vector<PlanEntry>* plans = nullptr;
+  std::map<const float*, WPlanes>* wplanes = nullptr;
+  std::string* err = nullptr;
+  bool failed = false;
+
+  void done(const char* name) {
+    ++launches;
+    if (tick) tick(tick_ctx, name);
+  }
+  template <class F>
+  void run_functor(long long n, const F& f) {
+    if (n <= 0) return;
+    op_kernel<F><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, f);
+    done(OpName<F>::get());
+  }
+  template <class F>
+  void run(long long n, const F& f) { run_functor(n, f); }
+
+  static int jj_of(int S) { return S <= 64 ? 2 : S <= 128 ? 4 : S <= 192 ? 6 : S <= 256 ? 8 : 0; }
+
+  void run(long long n, const AttnW& f) {
+    const int S = f.sm.S, jj = jj_of(S);
+    if (functors_only || !jj) { run_functor(n, f); return; }
+    const long long nseq = n / ((long long)HEADS * S);
+    const size_t smem = ((size_t)QD * ((S + 31) & ~31) + 16 * S + (size_t)PD * 2 * S) * sizeof(float);
+    const unsigned grid = (unsigned)(nseq * HEADS);
+    if (jj == 2) attn_w_kernel<2><<<grid, 256, smem, st>>>(f.ap, f.sm, f.pos, f.aw);
+    else if (jj == 4) attn_w_kernel<4><<<grid, 256, smem, st>>>(f.ap, f.sm, f.pos, f.aw);
+    else if (jj == 6) attn_w_kernel<6><<<grid, 256, smem, st>>>(f.ap, f.sm, f.pos, f.aw);
+    else attn_w_kernel<8><<<grid, 256, smem, st>>>(f.ap, f.sm, f.pos, f.aw);
+    done("zip_attn_w");
+  }
+  template <bool NL>
+  void apply(long long nseq, const SeqMap& sm, const float* aw, const float* src, float* ohi, float* olo, int jj) {
+    const size_t smem = (size_t)sm.S * VST * sizeof(float);     // <= 256 * 52 * 4 = 53 248 B
+    static unsigned long long configured[4] = {0, 0, 0, 0};
+#define ZIP_APPLY(J, slot)                                                                                                    \
+  {                                                                                                                           \
+    auto k = attn_apply_kernel<NL, J>;                                                                                        \
+    if (adn_first_use_on_device(configured[slot])) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * VST * 4); \
+    k<<<(unsigned)nseq, 256, smem, st>>>(aw, sm, src, ohi, olo);                                                              \
+  }
+    if (jj == 2) ZIP_APPLY(2, 0) else if (jj == 4) ZIP_APPLY(4, 1) else if (jj == 6) ZIP_APPLY(6, 2) else ZIP_APPLY(8, 3)
+#undef ZIP_APPLY
+  }
+  void run(long long n, const SaApply& f) {
+    const int S = f.sm.S, jj = jj_of(S);
+    if (functors_only || !jj) { run_functor(n, f); return; }
+    apply<false>(n / ((long long)SV * S), f.sm, f.aw, f.v, f.ohi, f.olo, jj);
+    done("zip_sa_apply");
+  }
+  void run(long long n, const NlApply& f) {
+    const int S = f.sm.S, jj = jj_of(S);
+    if (functors_only || !jj) { run_functor(n, f); return; }
+    apply<true>(n / ((long long)NH * S), f.sm, f.aw, f.np, f.ohi, f.olo, jj);
+    done("zip_nl_apply");
+  }
+  void run(long long n, const GluDwConv& f) {
+    if (functors_only) { run_functor(n, f); return; }
+    const long long nseq = n / ((long long)C * f.sm.S);
+    glu_dwconv_kernel<<<(unsigned)((nseq * C + 255) / 256), 256, 0, st>>>(f.cp, f.sm, nseq, f.w, f.b, f.ohi, f.olo);
+    done("zip_glu_dwconv");
+  }
+  void run(long long n, const NormBypass& f) {
+    if (functors_only) { run_functor(n, f); return; }
+    const long long M = n / C;
+    norm_bypass_kernel<<<(unsigned)((M * 16 + 255) / 256), 256, 0, st>>>(f.x, f.x0, M, f.nbias, f.nscale, f.rscale, f.ohi, f.olo);
+    done("zip_norm_bypass");
+  }
+
+  bool build(PlanEntry& e, const LinOp& g) {
+    auto it = wplanes->find(g.W.w);
+    if (it == wplanes->end()) { *err = "zipenhancer: LinOp weight without operand planes"; return false; }
+    const int bn = g.N <= 64 ? 64 : g.N <= 128 ? 128 : (g.N <= 176 || g.N > 256) ? 176 : 256;
+    const int bt = g.rows >= 128 ? 128 : g.rows;
+    e.plan = tc::TcPlan{};
+    e.plan.bn = bn;
+    const int batches = g.chunks;
+    const long long sB = g.a_sB ? g.a_sB : (long long)g.a_rows * g.a_sR;
+    if (!tc::make_row_map(&e.plan.map_a_hi, g.a_hi, g.a_ke, g.a_rows, g.a_sR, batches, sB, bt, 1, *err) ||
+        !tc::make_row_map(&e.plan.map_a_lo, g.a_lo, g.a_ke, g.a_rows, g.a_sR, batches, sB, bt, 1, *err) ||
+        !tc::make_weight_map(&e.plan.map_w_hi, it->second.hi, g.W.k_pad, g.W.n_pad, bn, *err) ||
+        !tc::make_weight_map(&e.plan.map_w_lo, it->second.lo, g.W.k_pad, g.W.n_pad, bn, *err))
+      return false;
+    e.plan.map_w2_hi = e.plan.map_w_hi;
+    e.plan.map_w2_lo = e.plan.map_w_lo;
+    tc::TcArgs& a = e.args;
+    a = tc::TcArgs{};
+    a.bb = 1; a.bt = bt; a.tiles_per_chunk = (g.rows + 127) / 128; a.t0 = g.a_r0;
+    a.B = g.chunks; a.TM = g.rows; a.N = g.N; a.K = g.K;
+    a.m_tiles = g.chunks * a.tiles_per_chunk;
+    a.taps = g.taps;
+    if (g.taps > 0) {
+      a.tap_kb = g.tap_c / 32; a.tap_k0 = g.a_k0;
+      for (int i = 0; i < 6; ++i) a.tap_shift[i] = g.tap_shift[i];
+    }
+    a.C = g.Cf; a.Chi = g.c_hi; a.Clo = g.c_lo; a.ldc = g.ldc;
+    a.bias = g.W.b; a.resid = g.resid; a.resid2 = g.resid2; a.colscale = g.colscale; a.act = g.act;
+    e.key = g;
+    e.valid = true;
+    return true;
+  }
+  void gemm(const LinOp& g, const char* name) {
+    if (failed) return;
+    const size_t idx = (size_t)gemms++;
+    if (plans->size() <= idx) plans->resize(idx + 1);
+    PlanEntry& e = (*plans)[idx];
+    if (!e.valid || !same_op(e.key, g)) {
+      if (!build(e, g)) { failed = true; return; }
+    }
+    cudaError_t ce = tc::launch(e.plan, e.args, EPI_LIN, sms, st);
+    if (ce != cudaSuccess) { *err = std::string("zipenhancer gemm launch: ") + cudaGetErrorString(ce); failed = true; return; }
+    done(name);
+  }
+  void mark(const char* name, const float* p, long long count) {
+    if (!capture || !dumps) return;
+    std::vector<float>& v = (*dumps)[name];
+    v.resize((size_t)count);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(v.data(), p, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost);
+  }
+  void mark_planes(const char* name, Planes pl, long long pixels, int ld, int coff, int width) {
+    if (!capture || !dumps) return;
+    std::vector<float> hi((size_t)pixels * ld), lo((size_t)pixels * ld);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hi.data(), pl.hi, hi.size() * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaMemcpy(lo.data(), pl.lo, lo.size() * sizeof(float), cudaMemcpyDeviceToHost);
+    std::vector<float>& v = (*dumps)[name];
+    v.resize((size_t)pixels * width);
+    for (long long p = 0; p < pixels; ++p)
+      for (int c = 0; c < width; ++c) v[p * width + c] = hi[p * ld + coff + c] + lo[p * ld + coff + c];
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ model
+class Model : public ModelImpl {
+ public:
+  int device = 0, sms = 148;
+  int in_dtype = ADN_F32, out_dtype = ADN_F32;
+  int L = 0, T = 0, Lout = 0;
+  int ds[NENC] = {1, 2, 2, 1};
+  float* d_blob = nullptr;
+  std::map<std::string, TensorRef> index;
+  Weights W;
+  Workspace ws;
+  adn_stft* stft = nullptr;
+  std::vector<void*> allocs, wallocs;
+  std::map<const float*, WPlanes> wplanes;
+  std::map<int, std::vector<PlanEntry>> plans;      // per windows-in-pass
+  int cap = 0, cap_sub = 0;
+  float *xn = nullptr, *nf = nullptr, *spec = nullptr, *feat = nullptr, *mx = nullptr, *ri = nullptr, *spec2 = nullptr, *wave = nullptr;
+  int stop_after = 0, last_launches = 0, last_batch = 0;
+  bool functors_only = false;
+  std::map<std::string, std::vector<float>> dumps;
+  static constexpr int SUB = 64;    // windows per pass of the backbone (bounds the workspace: ~0.3 GB per window)
+
+  ~Model() override {
+    cudaSetDevice(device);
+    cudaDeviceSynchronize();
+    free_ws();
+    for (void* p : wallocs) cudaFree(p);
+    if (stft) adn_stft_destroy(stft);
+  }
+  void free_ws() {
+    for (void* p : allocs) cudaFree(p);
+    allocs.clear();
+    plans.clear();
+    cap = cap_sub = 0;
+  }
+  float* dalloc(size_t n) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, (n ? n : 1) * sizeof(float)) != cudaSuccess) { err = "zipenhancer: out of device memory for the workspace"; return nullptr; }
+    allocs.push_back(p);
+    return (float*)p;
+  }
+  bool add_planes(const LinW& w) {
+    if (!w.w || wplanes.count(w.w)) return true;
+    const long long n = (long long)w.n_pad * w.k_pad;
+    float* p = nullptr;
+    if (cudaMalloc((void**)&p, 2 * n * sizeof(float)) != cudaSuccess) { err = "zipenhancer: out of device memory (weights)"; return false; }
+    wallocs.push_back(p);
+    pad_split_w_kernel<<<(unsigned)((n + 255) / 256), 256>>>(w.w, p, p + n, n);
+    wplanes[w.w] = WPlanes{p, p + n};
+    return true;
+  }
+  bool init(const std::map<std::string, std::string>& meta, const float* h_blob) {
+    auto geti = [&](const char* k, int& v) {
+      auto it = meta.find(k);
+      if (it == meta.end() || it->second.empty()) { err = std::string("Required metadata key ") + k + " is missing."; return false; }
+      v = atoi(it->second.c_str());
+      return true;
+    };
+    auto gets = [&](const char* k, std::string& v) {
+      auto it = meta.find(k);
+      if (it == meta.end()) { err = std::string("Required metadata key ") + k + " is missing."; return false; }
+      v = it->second;
+      return true;
+    };
+    int nfft = 0, hop = 0;
+    std::string sin, sout;
+    if (!geti("input_audio_length", L) || !geti("nfft", nfft) || !geti("hop_length", hop) || !gets("input_audio_dtype", sin) ||
+        !gets("output_audio_dtype", sout))
+      return false;
+    if (nfft != 400 || hop != 100 || L < 400) { err = "zipenhancer needs nfft=400, hop_length=100, input_audio_length >= 400"; return false; }
+    {   // the dimensions compiled into zipenh_ops.cuh; resampled I/O is not built for this family
+      struct { const char* k; int v; } dims[] = {{"zip_channels", C}, {"zip_heads", HEADS}, {"zip_query_head_dim", QD}, {"zip_pos_head_dim", PD},
+                                                 {"zip_value_head_dim", VD}, {"zip_ff_dim", FF2}, {"zip_conv_kernel", DWK}};
+      for (auto& d : dims) {
+        auto it = meta.find(d.k);
+        if (it != meta.end() && !it->second.empty() && atoi(it->second.c_str()) != d.v) {
+          err = std::string("zipenhancer: ") + d.k + " = " + it->second + " differs from the compiled value " + std::to_string(d.v);
+          return false;
+        }
+      }
+      for (const char* k : {"in_sample_rate", "out_sample_rate", "model_sample_rate"}) {
+        auto it = meta.find(k);
+        if (it != meta.end() && !it->second.empty() && atoi(it->second.c_str()) != 16000) { err = "zipenhancer runs at 16 kHz in, model and out sample rates"; return false; }
+      }
+      auto it = meta.find("zip_downsample");
+      if (it != meta.end() && !it->second.empty()) {
+        int k = 0;
+        const char* p = it->second.c_str();
+        while (*p && k < NENC) { ds[k++] = atoi(p); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
+        if (k != NENC) { err = "zipenhancer: zip_downsample needs four factors"; return false; }
+      }
+      for (int k = 0; k < NENC; ++k)
+        if (ds[k] < 1 || ds[k] > 2) { err = "zipenhancer: down-sampling factors must be 1 or 2"; return false; }
+    }
+    auto pdt = [&](const std::string& s, int& o) { if (s == "F32") o = ADN_F32; else if (s == "INT16") o = ADN_I16; else if (s == "F16") o = ADN_F16; else return false; return true; };
+    if (!pdt(sin, in_dtype) || !pdt(sout, out_dtype)) { err = "bad audio dtype"; return false; }
+    T = L / hop + 1;
+    Lout = hop * (T - 1);
+    auto lk = [&](const char* name, size_t expect) -> const float* {
+      auto it = index.find(name);
+      if (it == index.end() || (expect && it->second.count != expect)) {
+        if (err.empty()) err = std::string("weight blob: tensor '") + name + "' missing or wrong size";
+        return nullptr;
+      }
+      return d_blob + it->second.offset;
+    };
+    err.clear();
+    if (!bind(W, T, ds, lk)) { if (err.empty()) err = "zipenhancer: weight binding failed"; return false; }
+    auto dense = [&](const DenseW& d) { for (int i = 0; i < DEPTH; ++i) if (!add_planes(d.conv[i])) return false; return true; };
+    bool ok = dense(W.enc_dense) && dense(W.mask_dense) && dense(W.phase_dense) && add_planes(W.c2) && add_planes(W.mask_up) && add_planes(W.phase_up);
+    for (int k = 0; ok && k < NENC; ++k)
+      for (int dir = 0; ok && dir < 2; ++dir) {
+        const LayerW& l = dir ? W.enc[k].t : W.enc[k].f;
+        const LinW* all[] = {&l.attn_in, &l.ff1_in, &l.ff1_out, &l.nl_in, &l.nl_out, &l.sa1_in, &l.sa1_out, &l.cv1_in, &l.cv1_out,
+                             &l.ff2_in, &l.ff2_out, &l.sa2_in, &l.sa2_out, &l.cv2_in, &l.cv2_out, &l.ff3_in, &l.ff3_out};
+        for (const LinW* w : all) ok = ok && add_planes(*w);
+      }
+    if (!ok) return false;
+    if (cudaDeviceSynchronize() != cudaSuccess) { err = "zipenhancer: weight operand split failed"; return false; }
+    auto host = [&](const char* name, size_t expect) -> const float* {
+      auto it = index.find(name);
+      if (it == index.end() || it->second.count != expect) { err = std::string("weight blob: tensor '") + name + "' missing or wrong size"; return nullptr; }
+      return h_blob + it->second.offset;
+    };
+    const float* fwd = host("stft.fwd", (size_t)2 * FB * 400);
+    const float* inv = host("stft.inv", (size_t)2 * FB * 400);
+    const float* nrm = host("stft.norm", (size_t)Lout);
+    if (!fwd || !inv || !nrm) return false;
+    adn_stft_geom g;
+    memset(&g, 0, sizeof(g));
+    g.nfft = 400; g.hop = 100; g.center = 1; g.pad_reflect = 1; g.norm_multiply = 1;      // ZipEnhancer/STFT_Process.py:243-248, :294-295
+    if (adn_stft_create(&stft, &g, fwd, inv, nrm, T, device) != ADN_OK) { err = std::string("zipenhancer: ") + adn_last_error(nullptr); return false; }
+    const char* fo = getenv("ADN_ZIP_FUNCTORS");
+    functors_only = fo && fo[0] == '1';
+    return true;
+  }
+  bool ensure(int B) {
+    if (B <= cap) return true;
+    cudaDeviceSynchronize();
+    free_ws();
+    const int sub = B < SUB ? B : SUB;
+    auto a = [&](size_t n) { return dalloc(n); };
+    if (!alloc_ws(ws, sub, T, a)) return false;
+    const size_t b = (size_t)B;
+    if (!(xn = dalloc(b * L)) || !(nf = dalloc(b)) || !(spec = dalloc(b * 2 * FB * T)) || !(feat = dalloc(b * 2 * T * FB)) ||
+        !(mx = dalloc(b * T * FB)) || !(ri = dalloc(b * 2 * T * FB)) || !(spec2 = dalloc(b * 2 * FB * T)) || !(wave = dalloc(b * Lout)))
+      return false;
+    cap = B;
+    cap_sub = sub;
+    return true;
+  }
+  void io_info(adn_tensor_info* in, adn_tensor_info* out) override {
+    memset(in, 0, sizeof(*in));
+    memset(out, 0, sizeof(*out));
+    strncpy(in->name, "noisy_audio", sizeof(in->name) - 1);          // Export_ZipEnhancer.py:964-965
+    in->dtype = in_dtype; in->channels = 1; in->length = L;
+    strncpy(out->name, "denoised_audio", sizeof(out->name) - 1);
+    out->dtype = out_dtype; out->channels = 1; out->length = Lout;
+  }
+  size_t workspace_bytes(int batch) override {
+    const int sub = batch < SUB ? batch : SUB;
+    return (ws_floats(sub, T) + (size_t)batch * (L + 1 + 9 * FB * T + Lout)) * sizeof(float);
+  }
+  int per_pass() const {
+    int n = 1 + 3 + DEPTH * 4 + 4 + 1 + 2 * (DEPTH * 4 + 4 + 1);      // encoder, pad copy, two decoders
+    for (int k = 0; k < NENC; ++k) n += 2 * 24 + (ds[k] > 1 ? 2 : 0);
+    return n;
+  }
+  int launches(int batch) override { return 6 + ((batch + SUB - 1) / SUB) * per_pass(); }
+  void set_stop_after(int n) override { stop_after = n; }
+
+  adn_status run(const void* d_in, void* d_out, int B, cudaStream_t st) override {
+    if (!ensure(B)) return ADN_ERR_CUDA;
+    last_batch = B;
+    auto chk = [&](adn_status s, const char* what) {
+      if (s != ADN_OK) err = std::string("zipenhancer ") + what + ": " + adn_last_error(nullptr);
+      return s == ADN_OK;
+    };
+    auto tk = [&](const char* name) { if (tick) tick(tick_ctx, name); };
+    // F32 / F16 inputs are in [-1, 1]: x 32768 (:820-821), folded into the RMS pass
+    if (!chk(adn_rms_normalize(d_in, in_dtype, in_dtype == ADN_I16 ? 1.0f : 32768.0f, 1e-6f, xn, nf, B, L, L, st), "rms_normalize")) return ADN_ERR_CUDA;
+    tk("rms_normalize");
+    if (!chk(adn_stft_forward(stft, xn, spec, B, L, st), "stft")) return ADN_ERR_CUDA;
+    tk("stft");
+    if (!chk(adn_spec_features(ADN_FAMILY_ZIPENHANCER, spec, feat, nullptr, B, FB, T, st), "spec_features")) return ADN_ERR_CUDA;
+    tk("spec_features");
+    CudaExec ex;
+    ex.st = st; ex.sms = sms; ex.tick = tick; ex.tick_ctx = tick_ctx; ex.functors_only = functors_only;
+    ex.capture = stop_after != 0; ex.dumps = &dumps; ex.wplanes = &wplanes; ex.err = &err;
+    if (ex.capture) {
+      dumps.clear();
+      ex.mark("feat", feat, (long long)B * 2 * T * FB);      // the phase branch-cut decisions of this run (see the oracle's zipenh_forward)
+    }
+    for (int b0 = 0; b0 < B; b0 += cap_sub) {
+      const int nb = B - b0 < cap_sub ? B - b0 : cap_sub;
+      ex.plans = &plans[nb];
+      ex.gemms = 0;
+      forward(ex, ws, W, feat + (size_t)b0 * 2 * T * FB, mx + (size_t)b0 * T * FB, ri + (size_t)b0 * 2 * T * FB, nb, T);
+      if (ex.failed) return ADN_ERR_CUDA;
+      ex.capture = false;                          // stage dumps cover the first pass only
+    }
+    last_launches = ex.launches + 6;
+    if (!chk(adn_spec_recombine(ADN_FAMILY_ZIPENHANCER, mx, ri, nullptr, spec2, B, FB, T, st), "spec_recombine")) return ADN_ERR_CUDA;
+    tk("spec_recombine");
+    if (!chk(adn_stft_inverse(stft, spec2, wave, B, T, st), "istft")) return ADN_ERR_CUDA;
+    tk("istft");
+    if (!chk(adn_condition_output(ADN_FAMILY_ZIPENHANCER, wave, Lout, nf, 1, d_out, out_dtype, B, Lout, st), "condition_output")) return ADN_ERR_CUDA;
+    tk("condition_output");
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("zipenhancer run: ") + cudaGetErrorString(e); return ADN_ERR_CUDA; }
+    return ADN_OK;
+  }
+
+  adn_status debug_read(const char* name, float* h_dst, size_t count, size_t* actual) override {
+    if (!last_batch) { err = "adn_debug_read: no run yet"; return ADN_ERR_INVALID; }
+    if (!strcmp(name, "launches")) {
+      if (actual) *actual = 1;
+      if (h_dst && count) h_dst[0] = (float)last_launches;
+      return ADN_OK;
+    }
+    auto it = dumps.find(name);
+    if (it == dumps.end()) { err = std::string("adn_debug_read: unknown tensor '") + name + "' (stage dumps need adn_debug_stop_after(m, -1) before the run)"; return ADN_ERR_INVALID; }
+    if (actual) *actual = it->second.size();
+    if (!h_dst) return ADN_OK;
+    const size_t nc = count < it->second.size() ? count : it->second.size();
+    memcpy(h_dst, it->second.data(), nc * sizeof(float));
+    return ADN_OK;
+  }
+};
+
+}  // namespace zip
+
+ModelImpl* zipenh_create(const std::map<std::string, std::string>& meta, const std::map<std::string, TensorRef>& index,
+                         const float* h_blob, float* d_blob, int device, int sms, std::string& err) {
+  zip::Model* m = new zip::Model();
+  m->device = device;
+  m->sms = sms;
+  m->d_blob = d_blob;
+  m->index = index;
+  if (!m->init(meta, h_blob)) {
+    err = m->err;
+    delete m;
+    return nullptr;
+  }
+  return m;
+}

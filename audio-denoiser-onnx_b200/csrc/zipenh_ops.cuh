@@ -9,7 +9,7 @@
 //   implicit GEMMs: no im2col buffer).  libadn runs them on the tcgen05 3xTF32 GEMM (csrc/gemm_tc.cu); the host harness
 //   (tests/harness/zipenh_host.cpp) runs the same LinOps with plain loops, so the addressing is checked without a GPU.
 // * Everything else is a one-output-per-thread functor (`ex.run(count, functor)`); the CUDA executor replaces the
-//   attention functors (AttnW, AttnApply) and the depthwise conv by cooperative kernels (csrc/zipenh.cu), which the GPU
+//   attention functors (AttnW, SaApply, NlApply), the gated depthwise conv and the final norm by cooperative kernels (csrc/zipenh.cu), which the GPU
 //   tests compare against the same stage dumps.
 // * Layout: tokens are channel-last rows of 64 floats in (window, frame, sub-band) order for BOTH path directions; a layer
 //   over sub-bands and a layer over frames differ only in the `SeqMap` that turns (sequence, position) into a token row --
@@ -241,50 +241,51 @@ struct AttnW {
   }
 };
 
-// NonlinAttention value path (:319-322): v = x_mid * tanh(s)
-struct NlGate {
-  const float* np; float* nv;
-  ZIP_HD void operator()(long long i) const {
-    const int c = (int)(i % NH); const long long r = i / NH;
-    nv[i] = np[r * (3 * NH) + NH + c] * tanhf(np[r * (3 * NH) + c]);
-  }
-};
-
-// out[tok(n,i), c] = (sum_j aw[n, head(c), i, j] * v[tok(n,j), c]) * (y ? y[tok(n,i)*ldy + c] : 1) as tf32 planes (width SV == NH == 48);
-// heads == 1: every channel uses head 0 (NonlinAttention :161, :323-324); heads == HEADS: SelfAttention (:298-308)
-struct AttnApply {
-  const float* aw; SeqMap sm; const float* v; int heads; const float* y; int ldy; float *ohi, *olo;
+// SelfAttention value product (:298-308): out[tok(n,i), c] = sum_j aw[n, c / VD, i, j] * v[tok(n,j), c]  -> tf32 planes (width SV)
+struct SaApply {
+  const float* aw; SeqMap sm; const float* v; float *ohi, *olo;
   ZIP_HD void operator()(long long idx) const {
     const int S = sm.S;
     const int c = (int)(idx % SV); long long r = idx / SV; const int i = (int)(r % S); const long long n = r / S;
-    const int h = heads == 1 ? 0 : c / VD;
-    const float* a = aw + ((n * HEADS + h) * S + i) * (long long)S;
+    const float* a = aw + ((n * HEADS + c / VD) * S + i) * (long long)S;
     float acc = 0.f;
     for (int j = 0; j < S; ++j) acc += a[j] * v[sm.tok(n, j) * SV + c];
+    const long long o = sm.tok(n, i) * SV + c;
+    split_tf32(acc, ohi[o], olo[o]);
+  }
+};
+// NonlinAttention core (:310-326) on the fused projection np = [s | x_mid | y] (width 3 NH): head 0 of the attention weights
+// mixes x_mid * tanh(s) over the sequence, then the y gate  -> tf32 planes (width NH)
+struct NlApply {
+  const float* aw; SeqMap sm; const float* np; float *ohi, *olo;
+  ZIP_HD void operator()(long long idx) const {
+    const int S = sm.S;
+    const int c = (int)(idx % NH); long long r = idx / NH; const int i = (int)(r % S); const long long n = r / S;
+    const float* a = aw + ((n * HEADS) * S + i) * (long long)S;
+    float acc = 0.f;
+    for (int j = 0; j < S; ++j) {
+      const float* pj = np + sm.tok(n, j) * (3 * NH);
+      acc += a[j] * (pj[NH + c] * tanhf(pj[c]));
+    }
     const long long o = sm.tok(n, i);
-    if (y) acc *= y[o * ldy + c];
-    split_tf32(acc, ohi[o * SV + c], olo[o * SV + c]);
+    acc *= np[o * (3 * NH) + 2 * NH + c];
+    split_tf32(acc, ohi[o * NH + c], olo[o * NH + c]);
   }
 };
 
-// ConvolutionModule gate (:331-334): u = x_mid * sigmoid(gate)
-struct Glu {
-  const float* cp; float* u;
-  ZIP_HD void operator()(long long i) const {
-    const int c = (int)(i % C); const long long r = i / C;
-    u[i] = cp[r * 2 * C + c] * sigmoidf_(cp[r * 2 * C + C + c]);
-  }
-};
-// depthwise Conv1d(k 15, 'same') along the sequence + the SwooshR of the out projection (:336-339, :131-140) -> tf32 planes
-struct DwConvAct {
-  const float* u; SeqMap sm; const float* w; const float* b; float *ohi, *olo;     // w (C, DWK)
+// ConvolutionModule core (:328-339) on the fused projection cp = [x_mid | gate] (width 2 C): u = x_mid * sigmoid(gate),
+// depthwise Conv1d(k 15, 'same') along the sequence, then the SwooshR of the out projection (:131-140) -> tf32 planes
+struct GluDwConv {
+  const float* cp; SeqMap sm; const float* w; const float* b; float *ohi, *olo;     // w (C, DWK)
   ZIP_HD void operator()(long long idx) const {
     const int S = sm.S;
     const int c = (int)(idx % C); long long r = idx / C; const int s = (int)(r % S); const long long n = r / S;
     float acc = b[c];
     for (int k = 0; k < DWK; ++k) {
       const int sj = s + k - DWK / 2;
-      if (sj >= 0 && sj < S) acc += w[c * DWK + k] * u[sm.tok(n, sj) * C + c];
+      if (sj < 0 || sj >= S) continue;
+      const float* pj = cp + sm.tok(n, sj) * (2 * C);
+      acc += w[c * DWK + k] * (pj[c] * sigmoidf_(pj[C + c]));
     }
     const long long o = sm.tok(n, s) * C + c;
     split_tf32(swoosh(acc, 1.0f), ohi[o], olo[o]);
@@ -557,8 +558,7 @@ void zip_layer(Exec& ex, Workspace& w, const LayerW& L, float* x0, float* x, Pla
   g = lin_rows(xp.hi, xp.lo, C, C, M, L.nl_in, 3 * NH);
   g.Cf = w.t1; g.ldc = 3 * NH;
   ex.gemm(g, "zip_nl_in");
-  ex.run(M * NH, NlGate{w.t1, w.t2});
-  ex.run(M * SV, AttnApply{w.aw, sm, w.t2, 1, w.t1 + 2 * NH, 3 * NH, w.p64.hi, w.p64.lo});
+  ex.run(M * NH, NlApply{w.aw, sm, w.t1, w.p64.hi, w.p64.lo});
   g = lin_rows(w.p64.hi, w.p64.lo, NH, NH, M, L.nl_out, C);
   g.resid = x; g.Cf = x; g.c_hi = xp.hi; g.c_lo = xp.lo; g.ldc = C;
   ex.gemm(g, "zip_nl_out");
@@ -567,7 +567,7 @@ void zip_layer(Exec& ex, Workspace& w, const LayerW& L, float* x0, float* x, Pla
     LinOp a = lin_rows(xp.hi, xp.lo, C, C, M, win, SV);
     a.Cf = w.t2; a.ldc = SV;
     ex.gemm(a, "zip_sa_in");
-    ex.run(M * SV, AttnApply{w.aw, sm, w.t2, HEADS, nullptr, 0, w.p64.hi, w.p64.lo});
+    ex.run(M * SV, SaApply{w.aw, sm, w.t2, w.p64.hi, w.p64.lo});
     LinOp o = lin_rows(w.p64.hi, w.p64.lo, SV, SV, M, wout, C);
     o.resid = x; o.Cf = x; o.c_hi = xp.hi; o.c_lo = xp.lo; o.ldc = C;
     ex.gemm(o, "zip_sa_out");
@@ -576,8 +576,7 @@ void zip_layer(Exec& ex, Workspace& w, const LayerW& L, float* x0, float* x, Pla
     LinOp a = lin_rows(xp.hi, xp.lo, C, C, M, win, 2 * C);
     a.Cf = w.t1; a.ldc = 2 * C;
     ex.gemm(a, "zip_cv_in");
-    ex.run(M * C, Glu{w.t1, w.t2});
-    ex.run(nseq * S * C, DwConvAct{w.t2, sm, dw_w, dw_b, w.p64.hi, w.p64.lo});
+    ex.run(nseq * S * C, GluDwConv{w.t1, sm, dw_w, dw_b, w.p64.hi, w.p64.lo});
     LinOp o = lin_rows(w.p64.hi, w.p64.lo, C, C, M, wout, C);
     o.resid = x; o.Cf = x; o.c_hi = xp.hi; o.c_lo = xp.lo; o.ldc = C;
     ex.gemm(o, "zip_cv_out");

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the north-star path: noisy chunk in -> clean chunk out (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--model gtcrn|mbr|mf2se|mf2ss|mfgan|dfsmn|ulunas] [--batch B] [--impl adn|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model zipenh|gtcrn|mbr|mf2se|mf2ss|mfgan|dfsmn|ulunas] [--batch B] [--impl adn|reference]
 
 A "step" is one pass of the hot path over one batch of B synthetic chunks per GPU.
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field's definition.
@@ -610,8 +610,96 @@ class UlunasWorkload:
                       "istft": (4 * (514 * T + 15872), 2 * 514 * 512 * T)})
 
 
+class ZipenhWorkload:
+    """ZipEnhancer 16 kHz (BASELINE.json configs[1]: 64 x 1 s chunks, fp32, one B200): dense encoder, four dual-path Zipformer2
+    encoders (the middle two down-sampled x2 in time and frequency), mask + phase decoders; 161 frames x 101 sub-bands x 64."""
+    name = "zipenh"
+    default_batch = 64
+    chunk, sr, channels, t_frames = 16000, 16000, 1, 161
+    cpu_chunks, ref_chunks = 16, 8
+    in_name = "noisy_audio"
+    cpu_desc = "oracle/zipenh_oracle.py (PyTorch-eager restatement, pinned to the executed reference wrapper)"
+    tc3_kernels = ("zip_dense_conv", "zip_stride_conv", "zip_up_conv", "zip_attn_in", "zip_ff_in", "zip_ff_out", "zip_nl_in",
+                   "zip_nl_out", "zip_sa_in", "zip_sa_out", "zip_cv_in", "zip_cv_out")
+
+    def describe(self, B):
+        return (f"ZipEnhancer 16 kHz, {B} x 1 s windows (16000 samples, 161 frames x 201 bins -> 101 sub-bands x 64 channels) "
+                f"per GPU per step, F32 in / F32 out, 3xTF32 contractions")
+
+    def audio_seconds(self, B):
+        return B * self.chunk / self.sr
+
+    def weights(self):
+        import zipenh_oracle as zo
+        return zo.random_state_dict(zo.ZipConfig(), 0)
+
+    def build(self, sd, device):
+        from adn import export
+        return export.zipenh_model(sd, None, self.chunk, "F32", "F32", device_id=device)
+
+    def export(self, sd, path):
+        from adn import export
+        export.export_zipenh(sd, path, None, self.chunk, "F32", "F32")
+
+    inputs = MfganWorkload.inputs
+
+    def cpu_rate(self, sd, n_chunks, threads):
+        import zipenh_oracle as zo
+        cfg = zo.ZipConfig()
+        torch.set_num_threads(threads)
+        g = torch.Generator().manual_seed(7)
+        x = (torch.rand(1, 1, self.chunk, generator=g) * 2 - 1) * 0.3
+        with torch.inference_mode():
+            zo.zipenh_forward(sd, x, cfg)
+            t0 = time.perf_counter()
+            for _ in range(n_chunks):
+                zo.zipenh_forward(sd, x, cfg)
+            dt = time.perf_counter() - t0
+        return n_chunks * self.chunk / self.sr / dt, dt
+
+    def kernel_work(self):
+        """Algorithmic (bytes, flops) per window, averaged per LAUNCH over the launches that share an operator name.  Bytes of
+        a contraction: fp32 operands once (A, W, C); of an attention kernel: the weights it reads or writes + its value rows."""
+        T, F, FB = self.t_frames, 101, 201
+        Td, Fd = (T + 1) // 2, (F + 1) // 2
+        work: dict[str, list] = {}
+
+        def add(name, b, f):
+            work.setdefault(name, []).append((b, f))
+
+        def gemm(name, m, k, n):
+            add(name, 4 * (m * k + k * n + m * n), 2 * m * k * n)
+
+        for px in (T * FB, T * F, T * F):                               # dense blocks: encoder (201 bins), two decoders
+            for i in range(4):
+                add("zip_dense_conv", 4 * (px * 64 * (i + 1) + 6 * 64 * (i + 1) * 64 + px * 64), 2 * px * 6 * 64 * (i + 1) * 64)
+        gemm("zip_stride_conv", T * F, 192, 64)
+        gemm("zip_up_conv", T * F, 192, 128)
+        gemm("zip_up_conv", T * F, 192, 128)
+        for (t, f) in ((T, F), (Td, Fd), (Td, Fd), (T, F)):
+            m = t * f
+            for nseq, s in ((t, f), (f, t)):                            # layer over sub-bands, layer over frames
+                gemm("zip_attn_in", m, 64, 112)
+                for hdim in (192, 256, 320):
+                    gemm("zip_ff_in", m, 64, hdim)
+                    gemm("zip_ff_out", m, hdim, 64)
+                gemm("zip_nl_in", m, 64, 144)
+                gemm("zip_nl_out", m, 48, 64)
+                for _ in range(2):
+                    gemm("zip_sa_in", m, 64, 48)
+                    gemm("zip_sa_out", m, 48, 64)
+                    gemm("zip_cv_in", m, 64, 128)
+                    gemm("zip_cv_out", m, 64, 64)
+                    add("zip_sa_apply", 4 * (nseq * 4 * s * s + 2 * m * 48), 2 * nseq * s * s * 48)
+                    add("zip_glu_dwconv", 4 * (m * 128 + m * 64), 2 * m * 64 * 15)
+                add("zip_attn_w", 4 * (m * 112 + nseq * 4 * s * s), 2 * nseq * 4 * s * s * 16)
+                add("zip_nl_apply", 4 * (nseq * s * s + m * 144 + m * 48), 2 * nseq * s * s * 48)
+                add("zip_norm_bypass", 4 * 3 * m * 64, 4 * m * 64)
+        return _Work({k: (sum(b for b, _ in v) / len(v), sum(f for _, f in v) / len(v)) for k, v in work.items()})
+
+
 WORKLOADS = {"gtcrn": GtcrnWorkload, "mbr": MbrWorkload, "mf2se": Mf2seWorkload, "mf2ss": Mf2ssWorkload, "mfgan": MfganWorkload,
-             "dfsmn": DfsmnWorkload, "ulunas": UlunasWorkload}
+             "dfsmn": DfsmnWorkload, "ulunas": UlunasWorkload, "zipenh": ZipenhWorkload}
 
 
 class ClockSampler:

@@ -227,6 +227,39 @@ def main_mfgan():
             print(f"mfgan {dt} L{L}: {tuple(xin.shape)} -> {tuple(y.shape)} max|y| {y.float().abs().max().item():.4f}")
 
 
+def main_zipenh():
+    """ZipEnhancer fixtures (BASELINE configs[1]): the reference wrapper (`ZipEnhancer` of
+    ZipEnhancer/Export_ZipEnhancer.py, with the reference's own forward overrides installed on the skeleton classes) executed
+    around `zipenh_oracle.skeleton()` on seeded weights -- the full model (four dual-path encoders), 3200 samples (33 frames) in
+    F32 and 2400 samples (25 frames) in INT16; one all-zero window.  The weights are regenerated from the seed.  The inputs carry a
+    broadband noise floor (noisy speech does): in a bin without energy the phase feature atan2(im, re + 1e-5) (:844) is the angle of
+    rounding noise and the reference's own output is not reproducible from one BLAS to the next."""
+    import zipenh_oracle as zo
+
+    assert ref_loader.reference_available()
+    cfg = zo.ZipConfig()
+    with torch.inference_mode():
+        for L, dt in ((3200, "F32"), (2400, "INT16")):
+            _, build = ref_loader.load_zipenh(L, dt)
+            w = build(zo.skeleton(cfg, 0))
+            x = synth_audio(L, 1357, batch=4)
+            x = (x + 0.03 * torch.randn(x.shape, generator=torch.Generator().manual_seed(97))).clamp(-1.0, 1.0)
+            x[2] = 0.0
+            xin = x if dt == "F32" else torch.round(x * 32767.0).to(torch.int16)
+            y = torch.cat([w(xin[i:i + 1].clone()) for i in range(4)], dim=0)
+            # the phase feature the reference computed (:839-844, same modules, same machine): its +-pi branch-cut decisions in
+            # the edge frames are rounding noise, so an implementation can only be compared where it took the same ones
+            phas = []
+            for i in range(4):                                                     # one window per call, as the forward saw it
+                a = xin[i:i + 1].float() * (1.0 if dt == "INT16" else 32768.0)
+                a = a / torch.sqrt(torch.mean(a * a, dim=-1, keepdim=True) + 1e-6)
+                re, im = w.stft_model(a)
+                phas.append(torch.atan2(im, re + 1e-5).transpose(1, 2))
+            pha = torch.cat(phas, dim=0).contiguous()                              # (B, T, F)
+            np.savez_compressed(GOLDEN / f"zipenh_{dt.lower()}_L{L}.npz", x=xin.numpy(), y=y.numpy(), pha=pha.numpy(), seed=0)
+            print(f"zipenh {dt} L{L}: {tuple(xin.shape)} -> {tuple(y.shape)} max|y| {y.float().abs().max().item():.4f}")
+
+
 def main_dfsmn():
     """DFSMN (48 kHz) fixtures: the reference wrapper (`DFSMN` of DFSMN/Export_DFSMN.py) executed around
     `dfsmn_oracle.skeleton()` on seeded weights, 3 FSMN layers (the depth is the only reduced hyper-parameter);
@@ -297,6 +330,8 @@ if __name__ == "__main__":
         main_ulunas()
     elif "--dfsmn" in sys.argv:
         main_dfsmn()
+    elif "--zipenh" in sys.argv:
+        main_zipenh()
     elif "--mfgan" in sys.argv:
         main_mfgan()
     elif "--mf2ss" in sys.argv:

@@ -516,9 +516,17 @@ def backbone(sd, feat, cfg: ZipConfig = ZipConfig(), dbg=None):
     return m, ri
 
 
-def zipenh_forward(sd, audio, cfg: ZipConfig = ZipConfig(), in_dtype: str = "F32", out_dtype: str = "F32", dbg=None):
-    """audio (B, 1, L) -> (B, 1, hop * (L // hop)); `ZipEnhancer.forward` (:818-927) without batch fold, at the model rate."""
-    feat, nf = ends_oracle.zip_front(audio, in_dtype)
+def zipenh_forward(sd, audio, cfg: ZipConfig = ZipConfig(), in_dtype: str = "F32", out_dtype: str = "F32", dbg=None, feat=None):
+    """audio (B, 1, L) -> (B, 1, hop * (L // hop)); `ZipEnhancer.forward` (:818-927) without batch fold, at the model rate.
+
+    `feat` (B, 2, T, F), when given, replaces the features computed here.  The phase feature atan2(im, re + 1e-5) (:844) sits on
+    its branch cut wherever im is zero up to rounding and re < 0 -- structurally in the first frame and (for a hop-multiple
+    length) the last one, whose reflect-padded, symmetrically windowed samples have an exactly real spectrum up to a sign: there
+    the reference's own result is +pi or -pi by summation-order noise, and the backbone is not invariant to the flip.  Tests
+    that compare another implementation end to end pass its features in, so both sides take the same +-pi decisions, and
+    check separately that the features differ only by such flips."""
+    feat0, nf = ends_oracle.zip_front(audio, in_dtype)
+    feat = feat0 if feat is None else feat
     if dbg is not None:
         dbg["feat"], dbg["nf"] = feat, nf
     mx, ri = backbone(sd, feat, cfg, dbg)

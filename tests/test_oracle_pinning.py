@@ -606,3 +606,65 @@ def test_hgtcrn_fixture_reproduces_from_reference(dt, golden_dir):
     with torch.inference_mode():
         y = torch.cat([w(x[i:i + 1].clone()) for i in range(x.shape[0])], dim=0)
     assert y.shape == (2, 1, 16128) and np.array_equal(y.numpy(), g["y"])
+
+
+# ----------------------------------------------------------------------------- ZipEnhancer
+@pytest.mark.parametrize("fixture,dt", [("zipenh_f32_L3200", "F32"), ("zipenh_int16_L2400", "INT16")])
+def test_zipenh_oracle_matches_golden(fixture, dt, golden_dir):
+    import zipenh_oracle as zo
+
+    g = np.load(golden_dir / f"{fixture}.npz")
+    cfg = zo.ZipConfig()
+    sd = zo.random_state_dict(cfg, int(g["seed"]))
+    y = zo.zipenh_forward_batch(sd, torch.from_numpy(g["x"]), cfg, dt, dt).numpy()
+    assert y.shape == g["y"].shape and y.dtype == g["y"].dtype
+    if dt == "INT16":
+        assert np.abs(y.astype(np.int32) - g["y"].astype(np.int32)).max() <= 1
+    else:
+        assert np.abs(y - g["y"]).max() <= 5e-6
+
+
+@needs_ref
+def test_zipenh_oracle_and_folds_match_reference_module():
+    """Restated forward vs the reference's own `ZipEnhancer` wrapper executed (with ITS forward overrides installed on the
+    skeleton classes) around the parameter holder, one 1 s window: waveform <= 5e-6.  The product-side folds
+    (adn/zipenh_params.py) against the buffers the reference wrapper registers: bit-equal."""
+    import zipenh_oracle as zo
+    from adn import zipenh_params
+
+    cfg = zo.ZipConfig()
+    L = 16000
+    hold = zo.skeleton(cfg, 5)
+    sd = {k: v.detach().clone() for k, v in hold.state_dict().items()}
+    _, build = ref_loader.load_zipenh(L, "F32")
+    w = build(hold)
+    h = zipenh_params.ZipHyper()
+    T = h.n_frames(L)
+    blob = zipenh_params.pack(sd, h, L)
+    encs = w.zip_enhancer.TSConformer.encoders
+    for k, ds in enumerate(cfg.downsample):
+        e = encs[k]
+        inner = e if ds == 1 else e.encoder
+        if ds > 1:
+            assert np.array_equal(blob[f"ts{k}.down_t"], e.downsample_t.onnx_downsample_weights.reshape(-1).numpy())
+            assert np.array_equal(blob[f"ts{k}.comb_rscale"], e.out_combiner.onnx_residual_scale.numpy())
+        for d, layer in (("f", inner.f_layers[0]), ("t", inner.t_layers[0])):
+            o = f"ts{k}.{d}"
+            S = (-(-cfg.n_sub // ds)) if d == "f" else (-(-T // ds))
+            assert np.array_equal(blob[f"{o}.norm_scale"], layer.onnx_final_norm_scale.numpy())
+            assert np.array_equal(blob[f"{o}.res_scale"], layer.onnx_final_residual_scale.numpy())
+            pos = layer.self_attn_weights.onnx_linear_pos                     # (1, H, pos_head_dim, 2S-1)
+            assert tuple(pos.shape) == (1, cfg.heads, cfg.pos_head_dim, 2 * S - 1)
+            assert np.array_equal(blob[f"{o}.pos"], pos[0].numpy())
+            n_attn = layer.onnx_attn_projection_size
+            assert np.array_equal(blob[f"{o}.attn_in.w"][:n_attn, :64], layer.onnx_attn_ff1_weight[:n_attn].numpy())
+            assert np.array_equal(blob[f"{o}.ff1_in.w"][:192, :64], layer.onnx_attn_ff1_weight[n_attn:].numpy())
+            assert np.array_equal(blob[f"{o}.ff2_out.b"][:64], layer.feed_forward2.out_proj.onnx_bias.numpy())
+            assert np.array_equal(blob[f"{o}.cv1_out.b"][:64], layer.conv_module1.out_proj.onnx_bias.numpy())
+    x = synth_audio(L, 23)
+    with torch.inference_mode():
+        yr = w(x.clone())
+        yo = zo.zipenh_forward(sd, x, cfg)
+    assert yr.shape == yo.shape == (1, 1, L)
+    assert float(yr.abs().max()) > 0.1
+    assert (yr - yo).abs().max() <= 5e-6 * max(1.0, float(yr.abs().max()))

@@ -105,4 +105,4 @@ def test_host_sequence_matches_oracle(L, B, host_lib):
     cmp("phase_up", d["phase_up"], dbg["phase_up"], 5e-5)
     cmp("mx", mx, dbg["mx"], 5e-5)
     cmp("phase_ri", ri, dbg["phase_ri"], 5e-5)
-    assert launches == 287
+    assert launches == 263
