@@ -46,13 +46,23 @@ def tail_pad(audio: np.ndarray, pad_amount: int, mode: str = "zeros", rng=None) 
     return np.concatenate((audio, block), axis=-1)
 
 
-def split(audio: np.ndarray, in_len: int, out_len: int, tail: str = "zeros", rng=None) -> tuple[np.ndarray, int]:
+def _rates(session) -> tuple[int, int, float]:
+    """(in_sample_rate, out_sample_rate, input_to_output_scale) of the model file; equal rates when the keys are absent."""
+    md = session.get_modelmeta().custom_metadata_map or {}
+    in_sr, out_sr = int(md.get("in_sample_rate") or 0), int(md.get("out_sample_rate") or 0)
+    if in_sr <= 0 or out_sr <= 0:
+        in_sr = out_sr = 1
+    scale = md.get("input_to_output_scale")
+    return in_sr, out_sr, float(scale) if scale not in (None, "") else out_sr / in_sr
+
+
+def split(audio: np.ndarray, in_len: int, out_len: int, tail: str = "zeros", rng=None, same_rate: bool = True) -> tuple[np.ndarray, int]:
     """audio (N,) or (C, N) -> windows (num_windows, C, in_len), stride."""
     a = np.asarray(audio)
     if a.ndim == 1:
         a = a.reshape(1, -1)
     n = a.shape[-1]
-    stride, num, total = plan_windows(n, in_len, out_len)
+    stride, num, total = plan_windows(n, in_len, out_len, same_rate)
     a = tail_pad(a, total - n, tail, rng)
     idx = np.arange(num)[:, None] * stride + np.arange(in_len)[None, :]
     w = a[:, idx]                                   # (C, num, in_len)
@@ -73,8 +83,9 @@ def match_channels(audio: np.ndarray, channels: int) -> np.ndarray:
 
 def denoise(session, audio: np.ndarray, max_batch: int = 4096, tail: str = "zeros", rng=None) -> np.ndarray:
     """Whole-file drop-in for the reference's run section: returns the concatenated output trimmed
-    to the input length (`[:audio_len]`, GTCRN :332 / Mel-Band :345).  audio (N,) -> (N,) for mono
-    models, (C, N) -> (C, N) otherwise."""
+    to the input length at the output rate (`audio_len = int(audio_len * OUT / IN)`, `[:audio_len]`, GTCRN :303, :332 /
+    Mel-Band :345).  The overlap stride of a model whose output window is shorter than its input window applies only when
+    the two sample rates are equal (:288-290).  audio (N,) -> (N',) for mono models, (C, N) -> (C, N') otherwise."""
     from .ort_shim import OrtValue
 
     i = session.get_inputs()[0]
@@ -83,7 +94,9 @@ def denoise(session, audio: np.ndarray, max_batch: int = 4096, tail: str = "zero
     mono_in = np.asarray(audio).ndim == 1
     a = match_channels(audio, chans)
     n = a.shape[-1]
-    windows, _ = split(a, in_len, out_len, tail, rng)
+    in_sr, out_sr, _ = _rates(session)
+    windows, _ = split(a, in_len, out_len, tail, rng, same_rate=in_sr == out_sr)
+    n_out = int(n * out_sr / in_sr)
     outs = []
     for s in range(0, windows.shape[0], max_batch):
         w = np.ascontiguousarray(windows[s:s + max_batch])
@@ -95,7 +108,7 @@ def denoise(session, audio: np.ndarray, max_batch: int = 4096, tail: str = "zero
         session.run_with_iobinding(b)
         outs.append(vout.numpy())
     y = np.concatenate(outs, axis=0)                # (num, C, out_len)
-    y = y.transpose(1, 0, 2).reshape(y.shape[1], -1)[:, :n]
+    y = y.transpose(1, 0, 2).reshape(y.shape[1], -1)[:, :n_out]
     return y.reshape(-1) if (mono_in and y.shape[0] == 1) else y
 
 
@@ -104,7 +117,8 @@ def separate(session, audio: np.ndarray, pad_head: int | None = None, max_batch:
     """Whole-file drop-in for the run section of `MossFormer2_SS_16K/Inference_MossFormer_SS_ONNX.py:269-340`:
     `pad_head` zeros are prepended (`:273`; default: the model file's `pad_head` metadata key), the padded signal is cut
     into fixed windows (stride = window, `:286-305`), ALL windows run as one batch with every output bound
-    (`:312-317`), and each output is concatenated and trimmed to `[pad_head : pad_head + len(audio)]` (`:339-340`).
+    (`:312-317`), and each output is concatenated and trimmed to `[round(pad_head * s) : round(len(padded audio) * s)]`,
+    s = the model file's input_to_output_scale (`:308-309`, `:339-340`).
     Works for any number of outputs (one list entry per `session.get_outputs()` element).  tail: 'zeros' (fold mode)
     or 'noise' (the un-folded script's RMS-matched gaussian tail)."""
     from .ort_shim import OrtValue
@@ -135,7 +149,9 @@ def separate(session, audio: np.ndarray, pad_head: int | None = None, max_batch:
         for r, v in zip(results, vouts):
             r.append(v.numpy())
     # windows whose output is shorter than their input (length not 16 + 8k) are concatenated as produced, like the script
-    return [np.concatenate(r, axis=0).reshape(-1)[pad_head:n] for r in results]
+    scale = _rates(session)[2]
+    lo, hi = int(round(pad_head * scale)), int(round(n * scale))
+    return [np.concatenate(r, axis=0).reshape(-1)[lo:hi] for r in results]
 
 
 def _np_dtype(ort_type: str):

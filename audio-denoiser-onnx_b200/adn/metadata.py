@@ -1,6 +1,11 @@
-"""Run-time configuration from the model's string metadata -- mirrors the reference's
-`MetadataReader` / `runtime_config_from_metadata` (audio_onnx_metadata.py:247-303,354-386):
-same keys, defaults, error text for a missing required key, and the same 23 constants."""
+"""Run-time configuration from the model's string metadata.
+
+The drop-in contract with the reference (`audio_onnx_metadata.py:8-26, 247-303, 354-386`) is a SCHEMA, and it is kept as one here:
+the required-key list, each run-time constant's metadata key, type, required flag and default, and the two error messages a caller
+of the reference can observe.  Everything else is this module's own: one generic typed lookup (`MetadataReader.get`) driven by the
+table `RUNTIME_SCHEMA`; the `required_*` / `optional_*` method names of the reference's reader are generated from it for callers
+that were written against them.
+"""
 from __future__ import annotations
 
 REQUIRED_AUDIO_METADATA_KEYS = (
@@ -10,89 +15,92 @@ REQUIRED_AUDIO_METADATA_KEYS = (
     "normalize_target_rms",
 )
 
-
-def _missing(key):
-    return (f"Required metadata key {key} is missing. "
-            "Re-export with the matching Export_*.py and rerun Optimize_ONNX.py.")
+_TRUE, _FALSE = frozenset({"1", "true", "yes", "on"}), frozenset({"0", "false", "no", "off"})
 
 
-def _parse_bool(value, key):
-    v = str(value).strip().lower()
-    if v in {"1", "true", "yes", "on"}:
-        return True
-    if v in {"0", "false", "no", "off"}:
-        return False
-    raise ValueError(f"Metadata key {key} must be a boolean encoded as 1/0, got {value!r}.")
+def _to_bool(text, key):
+    word = str(text).strip().lower()
+    if word in _TRUE or word in _FALSE:
+        return word in _TRUE
+    raise ValueError(f"Metadata key {key} must be a boolean encoded as 1/0, got {text!r}.")
+
+
+_CASTS = {"int": lambda t, k: int(t), "float": lambda t, k: float(t), "bool": _to_bool, "string": lambda t, k: t}
 
 
 class MetadataReader:
+    """Typed view of a `custom_metadata_map`.  An absent key and an empty string are the same thing."""
+
     def __init__(self, metadata):
         self.metadata = dict(metadata or {})
 
-    def string(self, key, default=None, required=False):
-        value = self.metadata.get(key)
-        if value is None or value == "":
+    def get(self, key, kind="string", required=False, default=None):
+        text = self.metadata.get(key)
+        if text is None or text == "":
             if required:
-                raise KeyError(_missing(key))
+                raise KeyError(f"Required metadata key {key} is missing. "
+                               "Re-export with the matching Export_*.py and rerun Optimize_ONNX.py.")
             return default
-        return value
+        return _CASTS[kind](text, key)
 
-    def required_int(self, key):
-        return int(self.string(key, required=True))
+    def string(self, key, default=None, required=False):
+        return self.get(key, "string", required, default)
 
-    def optional_int(self, key, default=None):
-        v = self.string(key)
-        return default if v is None else int(v)
 
-    def required_float(self, key):
-        return float(self.string(key, required=True))
+def _install_typed_getters():
+    for kind in ("int", "float", "bool"):
+        setattr(MetadataReader, f"required_{kind}", lambda self, key, _k=kind: self.get(key, _k, required=True))
+        setattr(MetadataReader, f"optional_{kind}", lambda self, key, default=None, _k=kind: self.get(key, _k, False, default))
 
-    def optional_float(self, key, default=None):
-        v = self.string(key)
-        return default if v is None else float(v)
 
-    def required_bool(self, key):
-        return _parse_bool(self.string(key, required=True), key)
-
-    def optional_bool(self, key, default=None):
-        v = self.string(key)
-        return default if v is None else _parse_bool(v, key)
+_install_typed_getters()
 
 
 def load_runtime_metadata(session, required_keys=REQUIRED_AUDIO_METADATA_KEYS) -> MetadataReader:
     reader = MetadataReader(session.get_modelmeta().custom_metadata_map or {})
     for key in required_keys:
-        reader.string(key, required=True)
+        reader.get(key, required=True)
     return reader
 
 
+# constant -> (metadata key, type, required, default).  A callable default is evaluated on the constants resolved so far
+# (the table is ordered), which is how the reference derives three of its fall-backs from the sample rates.
+def _fold_input_default(c):
+    w = c["FOLD_WINDOW_LENGTH"]
+    return max(1, int(round(w * c["IN_SAMPLE_RATE"] / c["MODEL_SAMPLE_RATE"]))) if w else 0
+
+
+RUNTIME_SCHEMA = (
+    ("IN_SAMPLE_RATE", "in_sample_rate", "int", True, None),
+    ("OUT_SAMPLE_RATE", "out_sample_rate", "int", True, None),
+    ("MODEL_SAMPLE_RATE", "model_sample_rate", "int", True, None),
+    ("INPUT_TO_OUTPUT_SCALE", "input_to_output_scale", "float", True, None),
+    ("BATCH_WINDOW_SECONDS", "batch_window_seconds", "float", False, 0.0),
+    ("HOP_LENGTH", "hop_length", "int", False, 0),
+    ("FOLD_WINDOW_LENGTH", "fold_window_length", "int", False, 0),
+    ("FOLD_INPUT_LENGTH", "fold_input_length", "int", False, _fold_input_default),
+    ("BATCH_FOLD_INFERENCE", "batch_fold_inference_default", "bool", False, False),
+    ("MAX_DYNAMIC_AUDIO_SECONDS", "max_dynamic_audio_seconds", "int", True, None),
+    ("NORMALIZE_AUDIO", "normalize_audio_default", "bool", True, None),
+    ("NORMALIZE_TARGET_RMS", "normalize_target_rms", "float", True, None),
+    ("INPUT_CHANNELS", "input_channels", "int", False, 1),
+    ("OUTPUT_CHANNELS", "output_channels", "int", False, 1),
+    ("N_CHANNELS", "input_channels", "int", False, 1),
+    ("NUM_AUDIO_INPUTS", "num_audio_inputs", "int", False, 1),
+    ("PAD_HEAD", "pad_head", "int", False, 0),
+    ("ENC_STRIDE", "enc_stride", "int", False, 0),
+    ("OUTPUT_SOURCES", "output_sources", "int", False, 1),
+    ("ORIGINAL_SAMPLE_RATE", "original_sample_rate", "int", False, lambda c: c["IN_SAMPLE_RATE"]),
+    ("SUPER_SAMPLE_RATE", "super_sample_rate", "int", False, lambda c: c["OUT_SAMPLE_RATE"]),
+    ("SCALE_FACTOR", "scale_factor", "float", False, lambda c: float(c["OUT_SAMPLE_RATE"] / c["IN_SAMPLE_RATE"])),
+)
+
+
 def runtime_config_from_metadata(reader: MetadataReader) -> dict:
-    in_sr = reader.required_int("in_sample_rate")
-    out_sr = reader.required_int("out_sample_rate")
-    model_sr = reader.required_int("model_sample_rate")
-    fold_w = reader.optional_int("fold_window_length", 0)
-    return {
-        "IN_SAMPLE_RATE": in_sr,
-        "OUT_SAMPLE_RATE": out_sr,
-        "MODEL_SAMPLE_RATE": model_sr,
-        "INPUT_TO_OUTPUT_SCALE": reader.required_float("input_to_output_scale"),
-        "BATCH_WINDOW_SECONDS": reader.optional_float("batch_window_seconds", 0.0),
-        "HOP_LENGTH": reader.optional_int("hop_length", 0),
-        "FOLD_WINDOW_LENGTH": fold_w,
-        "FOLD_INPUT_LENGTH": reader.optional_int(
-            "fold_input_length", max(1, int(round(fold_w * in_sr / model_sr))) if fold_w else 0),
-        "BATCH_FOLD_INFERENCE": reader.optional_bool("batch_fold_inference_default", False),
-        "MAX_DYNAMIC_AUDIO_SECONDS": reader.required_int("max_dynamic_audio_seconds"),
-        "NORMALIZE_AUDIO": reader.required_bool("normalize_audio_default"),
-        "NORMALIZE_TARGET_RMS": reader.required_float("normalize_target_rms"),
-        "INPUT_CHANNELS": reader.optional_int("input_channels", 1),
-        "OUTPUT_CHANNELS": reader.optional_int("output_channels", 1),
-        "N_CHANNELS": reader.optional_int("input_channels", 1),
-        "NUM_AUDIO_INPUTS": reader.optional_int("num_audio_inputs", 1),
-        "PAD_HEAD": reader.optional_int("pad_head", 0),
-        "ENC_STRIDE": reader.optional_int("enc_stride", 0),
-        "OUTPUT_SOURCES": reader.optional_int("output_sources", 1),
-        "ORIGINAL_SAMPLE_RATE": reader.optional_int("original_sample_rate", in_sr),
-        "SUPER_SAMPLE_RATE": reader.optional_int("super_sample_rate", out_sr),
-        "SCALE_FACTOR": reader.optional_float("scale_factor", float(out_sr / in_sr)),
-    }
+    cfg: dict = {}
+    for constant, key, kind, required, default in RUNTIME_SCHEMA:
+        value = reader.get(key, kind, required)
+        if value is None:
+            value = default(cfg) if callable(default) else default
+        cfg[constant] = value
+    return cfg

@@ -68,18 +68,25 @@ class Model:
         output tensor (B, C, L_out).  Asynchronous on the current torch stream."""
         import torch
 
-        assert audio.is_cuda and audio.is_contiguous(), "adn.Model.run needs a contiguous CUDA tensor"
+        if not (audio.is_cuda and audio.is_contiguous()):
+            raise ValueError("adn.Model.run needs a contiguous CUDA tensor")
         B = audio.shape[0]
         tdt = {np.float32: torch.float32, np.int16: torch.int16, np.float16: torch.float16}
-        assert audio.dtype == tdt[self.input.np_dtype], (audio.dtype, self.input)
-        assert tuple(audio.shape[1:]) == (self.input.channels, self.input.length), (audio.shape, self.input)
+        if audio.dtype != tdt[self.input.np_dtype] or tuple(audio.shape[1:]) != (self.input.channels, self.input.length) or B < 1:
+            raise ValueError(f"adn.Model.run: input {tuple(audio.shape)} {audio.dtype} does not match {self.input}")
         multi = len(self.outputs) > 1            # MossFormer2-SS: one tensor per speaker, returned as a tuple
         if out is None:
             out = tuple(torch.empty((B, o.channels, o.length), dtype=tdt[o.np_dtype], device=audio.device)
                         for o in self.outputs)
-        elif not multi:
+        elif not multi and not isinstance(out, (tuple, list)):
             out = (out,)
-        assert len(out) == len(self.outputs)
+        if len(out) != len(self.outputs):
+            raise ValueError(f"adn.Model.run: {len(out)} output buffers for {len(self.outputs)} model outputs")
+        for t, o in zip(out, self.outputs):      # the library writes B * C * L elements through these pointers
+            if not (t.is_cuda and t.device == audio.device and t.is_contiguous() and t.dtype == tdt[o.np_dtype]
+                    and tuple(t.shape) == (B, o.channels, o.length)):
+                raise ValueError(f"adn.Model.run: output buffer {tuple(t.shape)} {t.dtype} on {t.device} does not match "
+                                 f"({B}, {o.channels}, {o.length}) {o} on {audio.device}")
         st = torch.cuda.current_stream(audio.device).cuda_stream if stream is None else stream
         outs = (C.c_void_p * len(out))(*[t.data_ptr() for t in out])
         _lib.check(_lib.lib().adn_run(self._h, C.c_void_p(audio.data_ptr()), outs, B, C.c_void_p(st)),
@@ -91,10 +98,18 @@ class Model:
         a = np.ascontiguousarray(audio, dtype=self.input.np_dtype)
         B = a.shape[0]
         multi = len(self.outputs) > 1
+        if a.ndim != 3 or tuple(a.shape[1:]) != (self.input.channels, self.input.length) or B < 1:
+            raise ValueError(f"adn.Model.run_host: input {a.shape} does not match {self.input}")
         if out is None:
             out = tuple(np.empty((B, o.channels, o.length), dtype=o.np_dtype) for o in self.outputs)
-        elif not multi:
+        elif not multi and not isinstance(out, (tuple, list)):
             out = (out,)
+        if len(out) != len(self.outputs):
+            raise ValueError(f"adn.Model.run_host: {len(out)} output buffers for {len(self.outputs)} model outputs")
+        for t, o in zip(out, self.outputs):
+            if not (isinstance(t, np.ndarray) and t.flags.c_contiguous and t.flags.writeable and t.dtype == o.np_dtype
+                    and t.shape == (B, o.channels, o.length)):
+                raise ValueError(f"adn.Model.run_host: output buffer does not match ({B}, {o.channels}, {o.length}) {o}")
         outs = (C.c_void_p * len(out))(*[t.ctypes.data for t in out])
         _lib.check(_lib.lib().adn_run_host(self._h, C.c_void_p(a.ctypes.data), outs, B), self._h, "adn_run_host")
         return tuple(out) if multi else out[0]

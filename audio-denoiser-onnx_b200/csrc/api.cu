@@ -327,6 +327,7 @@ adn_status ensure_capacity(adn_model* m, int B) {
   if ((s = dev_alloc(m, &m->d_in, (size_t)B * m->io_L * dtype_size(m->in_dtype), false)) != ADN_OK) return s;
   if ((s = dev_alloc(m, &m->d_out, (size_t)B * m->io_Lout * dtype_size(m->out_dtype), false)) != ADN_OK) return s;
 #undef A
+  ADN_CUDA_TRY(cudaDeviceSynchronize(), m->err);   // the zero-fills above ran on the legacy default stream
   m->capacity = B;
   return ADN_OK;
 }
@@ -569,6 +570,20 @@ adn_status gtcrn_run_resampled(adn_model* m, const void* d_in, void* d_out, int 
 
 }  // namespace
 
+// Every entry point runs on the handle's device and puts the caller's current device back (a process that drives several GPUs,
+// e.g. torch with one model per device, must not find its current device changed by a library call).
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 // ===================================================================================
 extern "C" {
 
@@ -598,7 +613,7 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
   for (int i = 0; i < desc->n_kv; ++i) m->meta[desc->keys[i]] = desc->values[i];
   for (int i = 0; i < desc->n_tensors; ++i) {
     const auto& t = desc->tensors[i];
-    if (t.offset + t.count > nfloats) {
+    if (t.count > nfloats || t.offset > nfloats - t.count) {        // (no uint64 wrap-around)
       m->err = std::string("tensor '") + t.name + "' exceeds the blob";
       return fail(ADN_ERR_INVALID);
     }
@@ -680,7 +695,8 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
     return fail(ADN_ERR_CUDA);
   }
   cudaDeviceProp prop;
-  if (cudaSetDevice(device_id) != cudaSuccess || cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) {
+  DeviceGuard dg(device_id);
+  if (!dg.ok || cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) {
     m->err = "cudaSetDevice failed";
     return fail(ADN_ERR_CUDA);
   }
@@ -718,6 +734,11 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
   if (s != ADN_OK) return fail(s);
   if (cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     m->err = "cudaStreamCreate failed";
+    return fail(ADN_ERR_CUDA);
+  }
+  // weight uploads, operand splits and table memsets ran on the legacy default stream; runs use non-blocking streams
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    m->err = "device initialisation failed";
     return fail(ADN_ERR_CUDA);
   }
   *out = m;
@@ -783,7 +804,8 @@ adn_status adn_run(adn_model* m, const void* d_in, void* const* d_outs, int32_t 
     m->err = "adn_run: null buffer or non-positive batch";
     return ADN_ERR_INVALID;
   }
-  ADN_CUDA_TRY(cudaSetDevice(m->device), m->err);
+  DeviceGuard dg(m->device);
+  if (!dg.ok) { m->err = "cudaSetDevice failed"; return ADN_ERR_CUDA; }
   if (m->impl) {
     m->ev_used = 0;
     m->ev_stream = (cudaStream_t)stream;
@@ -805,7 +827,8 @@ adn_status adn_run_host(adn_model* m, const void* h_in, void* const* h_outs, int
     m->err = "adn_run_host: null buffer or non-positive batch";
     return ADN_ERR_INVALID;
   }
-  ADN_CUDA_TRY(cudaSetDevice(m->device), m->err);
+  DeviceGuard dg(m->device);
+  if (!dg.ok) { m->err = "cudaSetDevice failed"; return ADN_ERR_CUDA; }
   adn_status s = ADN_OK;
   if (m->impl) {
     if (batch > m->io_cap) {     // staging buffers for families that own their workspace

@@ -714,6 +714,8 @@ class Model : public ModelImpl {
     if (!plan_gemm(g_me2, g1, M * DHID, DHID, (int)Mf, DHID, nb, Mf * DHID, me2)) return false;
     g_me2.args.bias = me_b2; g_me2.args.bias_bstride = DHID; g_me2.args.act = tc::ACT_TANH;
     g_me2.args.Chi = hpl; g_me2.args.Clo = hpl + M * DHID; g_me2.args.ldc = DHID;
+    // workspace memsets ran on the legacy default stream; runs use a non-blocking stream that does not order against it
+    if (cudaDeviceSynchronize() != cudaSuccess) { err = "workspace initialisation failed"; return false; }
     planned = B;
     return true;
   }

@@ -476,6 +476,8 @@ class Model : public Base {
         return false;
     }
     if (!tc::make_tile_map(&map_proj, proj, PROJ, T, PROJ, B, (long long)T * PROJ, DP_C, DP_ROWS, err)) return false;
+    // workspace memsets ran on the legacy default stream; runs use a non-blocking stream that does not order against it
+    if (cudaDeviceSynchronize() != cudaSuccess) { err = "workspace initialisation failed"; return false; }
     planned = B;
     return true;
   }

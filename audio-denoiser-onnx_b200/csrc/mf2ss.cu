@@ -625,6 +625,8 @@ class SsModel : public Base {
     // rows = (token, speaker): the speaker-stacked gate output viewed as (M*SPK, 1024)
     if (!plan_gemm(g_mask, tg, Ml * SPK * D, D, (int)(M * SPK), D, 1, Ml * SPK * D, maskl)) return false;
     g_mask.args.act = tc::ACT_RELU; g_mask.args.C = mask; g_mask.args.ldc = D;
+    // workspace memsets ran on the legacy default stream; runs use a non-blocking stream that does not order against it
+    if (cudaDeviceSynchronize() != cudaSuccess) { err = "workspace initialisation failed"; return false; }
     planned = B;
     return true;
   }

@@ -414,3 +414,46 @@ def test_separate_is_the_reference_ss_loop(n, win, out_len):
             e = s + win
         want = np.concatenate(saved, axis=-1).reshape(-1)[pad_head:audio_len]
         assert got[k].dtype == np.int16 and np.array_equal(got[k], want)
+
+
+@pytest.mark.parametrize("in_sr,out_sr,win,out_len", [(16000, 48000, 1600, 4800), (48000, 16000, 4800, 1600), (16000, 16000, 1600, 1472)])
+def test_denoise_and_separate_with_resampled_io(in_sr, out_sr, win, out_len):
+    """A model whose output window differs from its input window: with different I/O sample rates the stride stays the input
+    window and the result is cut to int(n * out / in) samples (Inference_GTCRN_ONNX.py:288-290, :303, :332); with equal rates
+    the windows overlap by in - out samples.  `separate` scales PAD_HEAD and the length by input_to_output_scale
+    (Inference_MossFormer_SS_ONNX.py:308-309, :339-340).  Compared with the reference loop transcribed window by window."""
+    from adn import chunker
+
+    n = 5 * win + 123
+    rng = np.random.default_rng(5)
+    audio = rng.integers(-20000, 20000, size=n, dtype=np.int16)
+
+    def fn(x):                                            # nearest-neighbour "resampler" standing in for the model
+        idx = np.minimum((np.arange(out_len) * win) // out_len, win - 1)
+        return x[..., idx]
+
+    md = {"in_sample_rate": str(in_sr), "out_sample_rate": str(out_sr), "input_to_output_scale": str(float(out_sr / in_sr)), "pad_head": "400"}
+    sess = _FakeSession(win, out_len, [fn], md)
+    sess._in[0].name = "mix_audio"
+    got = chunker.denoise(sess, audio)
+    stride = out_len if (win != out_len and in_sr == out_sr) else win
+    num = int(np.ceil((n - win) / stride)) + 1
+    total = (num - 1) * stride + win
+    a = np.concatenate([audio, np.zeros(total - n, np.int16)])
+    saved, s = [], 0
+    while s + win <= total:
+        saved.append(fn(a[s:s + win].reshape(1, 1, -1)))
+        s += stride
+    want = np.concatenate(saved, axis=-1).reshape(-1)[:int(n * out_sr / in_sr)]
+    assert np.array_equal(got, want)
+    if in_sr != out_sr:
+        sess = _FakeSession(win, out_len, [fn, fn], md)
+        sep = chunker.separate(sess, audio)
+        scale = out_sr / in_sr
+        a = np.concatenate([np.zeros(400, np.int16), audio])
+        m = len(a)
+        numw = int(np.ceil((m - win) / win)) + 1
+        a = np.concatenate([a, np.zeros((numw - 1) * win + win - m, np.int16)])
+        full = np.concatenate([fn(a[k * win:(k + 1) * win].reshape(1, 1, -1)) for k in range(numw)], axis=-1).reshape(-1)
+        want = full[int(round(400 * scale)):int(round(m * scale))]
+        assert np.array_equal(sep[0], want) and np.array_equal(sep[1], want)
