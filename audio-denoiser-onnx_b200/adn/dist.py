@@ -16,54 +16,69 @@ def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def _exchange(ops):
+    """One grouped launch of point-to-point transfers (ncclGroupStart / ncclSend / ncclRecv / ncclGroupEnd on the GPU box)."""
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
 def scatter_batch(audio: torch.Tensor | None, n: int, shape_tail: tuple, dtype, device, src: int = 0, group=None):
-    """Rank `src` holds audio (n, *shape_tail); every rank receives its block."""
+    """Rank `src` holds audio (n, *shape_tail) on `device`; every rank receives exactly its block: grouped sends of the
+    contiguous row ranges, no padding and no staging copies (rank `src` keeps a view of its own rows)."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = shard_bounds(n, world, rank)
-    cap = shard_bounds(n, world, 0)[1]                       # largest block
-    recv = torch.zeros((max(cap, 1), *shape_tail), dtype=dtype, device=device)
     if rank == src:
-        parts = []
+        audio = audio.to(device).contiguous()
+        ops = []
         for r in range(world):
             a, b = shard_bounds(n, world, r)
-            p = torch.zeros((max(cap, 1), *shape_tail), dtype=dtype, device=device)
-            if b > a:
-                p[: b - a] = audio[a:b].to(device)
-            parts.append(p)
-        dist.scatter(recv, parts, src=src, group=group)
-    else:
-        dist.scatter(recv, None, src=src, group=group)
-    return recv[: hi - lo]
+            if r != src and b > a:
+                ops.append(dist.P2POp(dist.isend, audio[a:b], r, group))
+        _exchange(ops)
+        return audio[lo:hi]
+    recv = torch.empty((hi - lo, *shape_tail), dtype=dtype, device=device)
+    if hi > lo:
+        _exchange([dist.P2POp(dist.irecv, recv, src, group)])
+    return recv
 
 
-def gather_batch(out_local: torch.Tensor, n: int, dst: int = 0, group=None):
-    """Inverse of scatter_batch: rank `dst` gets the (n, ...) concatenation, others None."""
+def gather_batch(out_local: torch.Tensor, n: int, dst: int = 0, group=None, out: torch.Tensor | None = None):
+    """Inverse of scatter_batch: rank `dst` gets the (n, ...) concatenation (written straight into `out` when given), others
+    None.  Every rank's block lands in its row range of the result: grouped receives, no padding, no concatenation copy."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    cap = max(shard_bounds(n, world, 0)[1], 1)
-    pad = torch.zeros((cap, *out_local.shape[1:]), dtype=out_local.dtype, device=out_local.device)
-    pad[: out_local.shape[0]] = out_local
+    lo, hi = shard_bounds(n, world, rank)
     if rank == dst:
-        bufs = [torch.empty_like(pad) for _ in range(world)]
-        dist.gather(pad, bufs, dst=dst, group=group)
-        parts = []
+        if out is None:
+            out = torch.empty((n, *out_local.shape[1:]), dtype=out_local.dtype, device=out_local.device)
+        out[lo:hi].copy_(out_local)
+        ops = []
         for r in range(world):
             a, b = shard_bounds(n, world, r)
-            parts.append(bufs[r][: b - a])
-        return torch.cat(parts, dim=0)
-    dist.gather(pad, None, dst=dst, group=group)
+            if r != dst and b > a:
+                ops.append(dist.P2POp(dist.irecv, out[a:b], r, group))
+        _exchange(ops)
+        return out
+    if hi > lo:
+        _exchange([dist.P2POp(dist.isend, out_local.contiguous(), dst, group)])
     return None
 
 
-def run_sharded(run_fn, audio: torch.Tensor | None, n: int, shape_tail: tuple, dtype, device, group=None):
+def run_sharded(run_fn, audio: torch.Tensor | None, n: int, shape_tail: tuple, dtype, device, group=None, marks=None):
     """scatter -> run_fn(local block) -> gather.  `run_fn` maps (b, C, L) -> (b, C, L_out) on
     `device` (Model.run on the GPU box).  Ranks whose block is empty skip the run (B=1 => one
-    GPU active)."""
+    GPU active).  `marks`, when given, is called with "scattered" and "ran" between the three phases (bench.py records
+    CUDA events there to report the exchange's share of the step)."""
     local = scatter_batch(audio, n, shape_tail, dtype, device, group=group)
+    if marks:
+        marks("scattered")
     if local.shape[0] > 0:
         out = run_fn(local.contiguous())
     else:
         out = run_fn(torch.zeros((1, *shape_tail), dtype=dtype, device=device))
         out = tuple(o[:0] for o in out) if isinstance(out, (tuple, list)) else out[:0]
+    if marks:
+        marks("ran")
     if isinstance(out, (tuple, list)):                    # several outputs (MossFormer2-SS: one per speaker)
         parts = [gather_batch(o, n, group=group) for o in out]
         return None if parts[0] is None else tuple(parts)

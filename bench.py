@@ -780,6 +780,102 @@ def run_reference(args, wl):
     print(json.dumps(line))
 
 
+def run_strong(args, wl, model, B, n_sets, dev, dist, rank, world, barrier, allmax):
+    """Strong scaling through the real multi-GPU data path (SURVEY 8e): B windows in total per step, owned by rank 0;
+    every step is adn.dist.run_sharded = NCCL grouped send / recv of each rank's exact block -> Model.run -> NCCL gather into
+    rank 0's output tensor.  `value`: inputs resident in rank 0's HBM; `e2e`: rank 0's pinned host buffers, H2D and D2H
+    inside the timed region.  The scatter / run / gather split comes from CUDA events between the phases (max over ranks)."""
+    from adn import dist as adist
+    from adn import _lib
+
+    if dist is None:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29541")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+    tail = (wl.channels, wl.chunk)
+    host_sets = wl.inputs(B, n_sets, seed=1234) if rank == 0 else None
+    dev_sets = [x.to(dev) for x in host_sets] if rank == 0 else None
+    stream = torch.cuda.current_stream(dev)
+    marks: list = []
+
+    def mark(_):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        marks.append(e)
+
+    def step(i, timed=False):
+        if timed:
+            mark("start")
+        y = adist.run_sharded(model.run, dev_sets[i % n_sets] if rank == 0 else None, B, tail, torch.float32, dev,
+                              marks=mark if timed else None)
+        if timed:
+            mark("gathered")
+        return y
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        y = step(i, timed=True)
+    e1.record(stream)
+    barrier()
+    ms = allmax(e0.elapsed_time(e1))
+    ph = [0.0, 0.0, 0.0]
+    for k in range(args.steps):
+        a, b, c, d = marks[4 * k:4 * k + 4]
+        ph[0] += a.elapsed_time(b); ph[1] += b.elapsed_time(c); ph[2] += c.elapsed_time(d)
+    ph = [allmax(v) / args.steps for v in ph]
+    audio_s = wl.audio_seconds(B) * args.steps
+    value = audio_s / (ms * 1e-3)
+    n_out = len(model.outputs)
+    out_elems = B * model.outputs[0].channels * model.outputs[0].length
+    # end to end: pinned host buffers on rank 0
+    e2e_ms = None
+    if rank == 0:
+        pin_in = [x.pin_memory() for x in host_sets]
+        pin_out = [torch.empty((B, model.outputs[0].channels, model.outputs[0].length), dtype=torch.float32).pin_memory() for _ in range(n_out)]
+        stage = torch.empty((B, *tail), dtype=torch.float32, device=dev)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        if rank == 0:
+            stage.copy_(pin_in[i % n_sets], non_blocking=True)
+        y = adist.run_sharded(model.run, stage if rank == 0 else None, B, tail, torch.float32, dev)
+        if rank == 0:
+            for po, yo in zip(pin_out, y if isinstance(y, tuple) else (y,)):
+                po.copy_(yo, non_blocking=True)
+            torch.cuda.synchronize(dev)
+    barrier()
+    e2e_ms = allmax((time.perf_counter() - t0) * 1e3)
+    if rank == 0:
+        per_rank = -(-B // world)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16" if getattr(wl, "matmul", "F32") == "BF16" else "f32", "data": "synthetic",
+            "config": {"workload": wl.describe(B).replace("per GPU per step", f"in TOTAL per step, sharded over {world} GPU(s)"),
+                       "model": wl.name, "batch_total": B, "batch_per_gpu_max": per_rank, "chunk_samples": wl.chunk,
+                       "parallelism": f"rank 0 owns the batch; NCCL grouped send/recv scatter -> run -> gather (adn.dist.run_sharded), "
+                                      f"weights replicated x{world}"},
+            "rtf": 1.0 / value,
+            "exchange": {"scatter_ms_per_step": ph[0], "run_ms_per_step": ph[1], "gather_ms_per_step": ph[2],
+                         "share_of_step": (ph[0] + ph[2]) / max(ph[0] + ph[1] + ph[2], 1e-9),
+                         "scatter_bytes_per_step": (B - per_rank) * wl.channels * wl.chunk * 4 if world > 1 else 0,
+                         "gather_bytes_per_step": n_out * (out_elems - out_elems // B * per_rank) * 4 if world > 1 else 0},
+            "e2e": {"value": audio_s / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * wl.channels * wl.chunk * 4,
+                    "d2h_bytes_per_step": n_out * out_elems * 4, "ms_per_step": e2e_ms / args.steps,
+                    "api": "pinned host -> H2D -> adn.dist.run_sharded -> D2H, rank 0"},
+            "gpu_launches": model.launches_per_run(per_rank) * args.steps * world,
+            "roofline": None, "cpu_baseline": None,
+            "lib": _lib.lib().adn_version().decode(),
+        }
+        print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -794,6 +890,12 @@ def main():
     ap.add_argument("--matmul", default="f32", choices=["f32", "bf16"],
                     help="mf2se only: bf16 = the layers' GEMMs on bf16 operands (BASELINE.json configs[2] 'bf16 matmuls'); "
                          "default f32 = 3xTF32, the 1e-4 parity path")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's contract): --batch chunks per GPU, every rank's inputs resident in its own HBM; "
+                         "strong: --batch chunks in TOTAL, owned by rank 0, scattered / run / gathered through adn.dist.run_sharded "
+                         "(NCCL grouped send / recv) inside the timed region")
+    ap.add_argument("--segments", default="", help="NxSs, e.g. 128x8s (BASELINE.json configs[3]): N segments of S seconds, folded on the host "
+                                                   "into the model's fixed windows (stride = window, zero tail) -> --batch = N * ceil(S * sr / window)")
     ap.add_argument("--ref-chunks", type=int, default=0, help="CPU chunks per step for --impl reference")
     ap.add_argument("--cpu-baseline-chunks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -804,6 +906,14 @@ def main():
         if args.model != "mf2se":
             raise SystemExit("--matmul bf16 is only licensed for MossFormer2-SE-48K (BASELINE.json configs[2])")
         wl.matmul = "BF16"
+    if args.segments:
+        nseg, secs = args.segments.lower().rstrip("s").split("x")
+        per_seg = -(-int(float(secs) * wl.sr) // wl.chunk)
+        args.batch = int(nseg) * per_seg
+        seg_audio = int(nseg) * float(secs)
+        wl.audio_seconds = lambda B, _a=seg_audio: _a                      # the tail window of a segment is padding, not audio
+        _describe = wl.describe
+        wl.describe = lambda B: f"{nseg} x {secs} s segments folded into {per_seg} windows each: " + _describe(B)
     if args.steps <= 0:
         args.steps = 100 if args.model == "gtcrn" else (5 if args.model in ("mf2ss", "mfgan") else 20)
     if args.impl == "reference":
@@ -854,6 +964,14 @@ def main():
         t = torch.tensor([v], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    if args.scaling == "strong":
+        del dev_sets, out
+        run_strong(args, wl, model, B, n_sets, dev, dist, rank, world, barrier, allmax)
+        model.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     # ---------------- device-resident throughput ("value")
     for i in range(args.warmup):
