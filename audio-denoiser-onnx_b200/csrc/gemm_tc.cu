@@ -30,7 +30,9 @@ constexpr int BK = 32;                 // 32 fp32 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 8;              // tf32: 32 bytes of K per instruction
 constexpr int NEPI = 16;                // epilogue warps: four per TMEM lane quarter (the epilogue, not the tensor pipe, limits
                                         // small-K and bf16 GEMMs: 8 warps could not issue fast enough)
+constexpr int NCONV_AF = 3;             // fp32-A mode: converter warps behind the epilogue warps
 constexpr int NTHREADS = 64 + 32 * NEPI; // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
+constexpr int NTHREADS_AF = NTHREADS + 32 * NCONV_AF;
 constexpr uint32_t A_TILE_BYTES = BM * BK * 4;   // 16 KiB
 
 // (mbarrier / TMA wrappers: tma_utils.cuh)
@@ -128,8 +130,13 @@ struct Smem {
   static constexpr uint32_t TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 };
 
-template <int BN, int EPI, bool BF>
-__global__ void __launch_bounds__(NTHREADS, 1)
+// AF (fp32 A operand, ZipEnhancer): the A tensor map is over the fp32 activations themselves.  TMA lands the fp32 tile in the
+// hi slot of the stage; three converter warps (behind the sixteen epilogue warps) split every element in place into
+// hi = x & 0xFFFFE000 (kept where it is) and lo = x - hi (lo slot) -- the 128-byte swizzle is a permutation of 16-byte chunks,
+// so an element-wise pass needs no knowledge of it -- then fence.proxy.async and hand the stage to the MMA warp.  Activations
+// live in HBM once, as fp32: half the A bytes, and no producer writes operand planes.
+template <int BN, int EPI, bool BF, bool AF>
+__global__ void __launch_bounds__(AF ? NTHREADS_AF : NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
@@ -143,7 +150,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   uint64_t* empty = bars + S::STAGES;       // [STAGES]
   uint64_t* tfull = bars + 2 * S::STAGES;   // [2]
   uint64_t* tempty = tfull + 2;             // [2]
-  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  uint64_t* conv = tempty + 2;              // [STAGES] (AF only)
+  uint32_t* tmem_slot = (uint32_t*)(conv + S::STAGES);
+  constexpr int NE = NEPI;                  // epilogue warps 2 .. 2+NE-1; converter warps behind them
+  constexpr int NCONV = AF ? NCONV_AF : 0;
   float* stage = (float*)(smem + S::STAGES * S::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -162,10 +172,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     for (int i = 0; i < S::STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
+      if (AF) mbar_init(&conv[i], NCONV);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], NEPI);
+      mbar_init(&tempty[i], NE);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -193,7 +204,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * S::STAGE_BYTES;
-          mbar_expect_tx(&full[stage], (uint32_t)S::PLANES * ((uint32_t)(g.bt * g.bb * BK * 4) + S::W_TILE_BYTES));
+          mbar_expect_tx(&full[stage], (uint32_t)(AF ? 1 : S::PLANES) * (uint32_t)(g.bt * g.bb * BK * 4) + (uint32_t)S::PLANES * S::W_TILE_BYTES);
           int wb = g.w_batched ? b0 : 0;            // per-batch weights (mask-estimator bands, attention operands)
           int wk = kb * BKE;
           if (g.w_group > 1) { wk += (b0 % g.w_group) * g.w_kstep; wb = b0 / g.w_group; }   // FLASH group of a window
@@ -206,7 +217,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             tma_load_3d(st + A_TILE_BYTES, second ? &map_w2_hi : &map_w_hi, &full[stage], wk, nt * BN, wb);
           } else {
             tma_load_3d(st, &map_a_hi, &full[stage], ak, at, b0);
-            tma_load_3d(st + A_TILE_BYTES, &map_a_lo, &full[stage], ak, at, b0);
+            if (!AF) tma_load_3d(st + A_TILE_BYTES, &map_a_lo, &full[stage], ak, at, b0);
             tma_load_3d(st + 2 * A_TILE_BYTES, second ? &map_w2_hi : &map_w_hi, &full[stage], wk, nt * BN, wb);
             tma_load_3d(st + 2 * A_TILE_BYTES + S::W_TILE_BYTES, second ? &map_w2_lo : &map_w_lo, &full[stage], wk, nt * BN, wb);
           }
@@ -229,6 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const uint32_t d_tmem = tmem_base + ab * 256;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full[stage], phase);
+          if (AF) mbar_wait(&conv[stage], phase);  // operand tiles split by the converter warps
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
           if (BF) {
@@ -256,6 +268,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         umma_commit(&tfull[ab]);                   // accumulator complete
       }
     }
+  } else if (AF && warp >= 2 + NE) {
+    // ===================== fp32 -> tf32 hi / lo converters =====================
+    const int cw = warp - (2 + NE);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full[stage], phase);
+        float4* hi = reinterpret_cast<float4*>(smem + stage * S::STAGE_BYTES);
+        float4* lo = hi + A_TILE_BYTES / 16;
+#pragma unroll 4
+        for (int i = cw * 32 + lane; i < (int)(A_TILE_BYTES / 16); i += NCONV * 32) {
+          const float4 v = hi[i];
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+          hi[i] = h;
+          lo[i] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv[stage]);
+        if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
   } else {
     // ===================== epilogue (warps 2..17) =====================
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
@@ -276,11 +315,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       tc_fence_after();
       const uint32_t taddr = tmem_base + ab * 256 + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c0 = cidx * 32; c0 < BN; c0 += 32 * (NEPI / 4)) {
+      for (int c0 = cidx * 32; c0 < BN; c0 += 32 * (NE / 4)) {
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait();
         const int n0 = nt * BN + c0;
+        if (AF) {
+          // fp32-only outputs (no operand planes to write): the TMEM load already gives lane = row with 32 consecutive
+          // columns in registers, so every lane streams its own row as 16-byte stores -- the halves of a 32-byte sector
+          // come from back-to-back stores of one lane and merge in L2 -- with a fraction of the instructions of the
+          // transposing path below (which exists to write three coalesced planes per element).
+          if (!row_ok) continue;
+          const long long o = ((long long)b * g.TM + t) * g.ldc + n0;
+          float4 res4[8], org4[8];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const bool ok = c0 + 4 * j4 < BN && n0 + 4 * j4 < g.N;
+            res4[j4] = (ok && g.resid) ? *reinterpret_cast<const float4*>(g.resid + o + 4 * j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            org4[j4] = (ok && g.resid2) ? *reinterpret_cast<const float4*>(g.resid2 + o + 4 * j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            if (!(c0 + 4 * j4 < BN && n0 + 4 * j4 < g.N)) continue;
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g.bias) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j4);
+            float x[4] = {__uint_as_float(v[4 * j4]) + b4.x, __uint_as_float(v[4 * j4 + 1]) + b4.y,
+                          __uint_as_float(v[4 * j4 + 2]) + b4.z, __uint_as_float(v[4 * j4 + 3]) + b4.w};
+            if (g.act == ACT_SWOOSH_L || g.act == ACT_SWOOSH_R) {
+              const float off = g.act == ACT_SWOOSH_L ? 4.0f : 1.0f;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float y = x[j] - off;
+                x[j] = fmaxf(y, 0.f) + __logf(1.0f + __expf(-fabsf(y))) - 0.08f * x[j];
+              }
+            }
+            x[0] += res4[j4].x; x[1] += res4[j4].y; x[2] += res4[j4].z; x[3] += res4[j4].w;
+            if (g.resid2) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(g.colscale + n0) + j4);
+              x[0] = org4[j4].x + (x[0] - org4[j4].x) * s4.x; x[1] = org4[j4].y + (x[1] - org4[j4].y) * s4.y;
+              x[2] = org4[j4].z + (x[2] - org4[j4].z) * s4.z; x[3] = org4[j4].w + (x[3] - org4[j4].w) * s4.w;
+            }
+            *reinterpret_cast<float4*>(g.C + o + 4 * j4) = make_float4(x[0], x[1], x[2], x[3]);
+          }
+          continue;
+        }
         if (EPI == EPI_LIN || EPI == EPI_ISTFT) {
           // Linear layer: v = act(acc * rowscale[m] + bias[n]) (+ residual) -> fp32 and/or tf32 planes.
           // The TMEM load gives lane = row; a per-warp smem transpose turns that into lane = column
@@ -403,8 +481,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const float off = g.act == ACT_SWOOSH_L ? 4.0f : 1.0f;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
+                  // softplus(y) = max(y, 0) + log(1 + exp(-|y|)) on ex2.approx / lg2.approx: the argument of the log is in (1, 2],
+                  // absolute error ~1e-7 on values of order 1 (the accurate log1pf / expf pair was the epilogue's critical path)
                   const float y = x[j] - off;
-                  x[j] = (y > 20.f ? y : log1pf(expf(y))) - 0.08f * x[j];
+                  x[j] = fmaxf(y, 0.f) + __logf(1.0f + __expf(-fabsf(y))) - 0.08f * x[j];
                 }
               }
               const long long o = m * g.ldc + n0 + 4 * cq;
@@ -556,24 +636,25 @@ bool make_tile_map(CUtensorMap* map, const float* base, int cols, int rows, long
   return true;
 }
 
-template <int BN, int EPI, bool BF>
+template <int BN, int EPI, bool BF, bool AF = false>
 static cudaError_t launch_t(const TcPlan& p, const TcArgs& a, int sms, cudaStream_t st) {
   using S = Smem<BN, BF>;
   static unsigned long long configured = 0;      // per device
-  auto kern = gemm_tc_kernel<BN, EPI, BF>;
+  auto kern = gemm_tc_kernel<BN, EPI, BF, AF>;
   if (adn_first_use_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
     if (e != cudaSuccess) return e;
   }
   const int n_tiles = a.m_tiles * ((a.N + BN - 1) / BN);
   const int grid = n_tiles < sms ? n_tiles : sms;
-  kern<<<grid, NTHREADS, S::TOTAL, st>>>(p.map_a_hi, p.map_a_lo, p.map_w_hi, p.map_w_lo, p.map_w2_hi, p.map_w2_lo, a);
+  kern<<<grid, AF ? NTHREADS_AF : NTHREADS, S::TOTAL, st>>>(p.map_a_hi, p.map_a_lo, p.map_w_hi, p.map_w_lo, p.map_w2_hi, p.map_w2_lo, a);
   return cudaGetLastError();
 }
 
 template <int BN>
 static cudaError_t launch_bn(const TcPlan& p, const TcArgs& a, int epi, int sms, cudaStream_t st) {
   if (p.bf16) return epi == EPI_LIN ? launch_t<BN, EPI_LIN, true>(p, a, sms, st) : cudaErrorInvalidValue;
+  if (p.a_f32) return epi == EPI_LIN ? launch_t<BN, EPI_LIN, false, true>(p, a, sms, st) : cudaErrorInvalidValue;
   if (epi == EPI_STORE) return launch_t<BN, EPI_STORE, false>(p, a, sms, st);
   if (epi == EPI_ISTFT) return launch_t<BN, EPI_ISTFT, false>(p, a, sms, st);
   if (epi == EPI_LIN) return launch_t<BN, EPI_LIN, false>(p, a, sms, st);

@@ -56,6 +56,7 @@ struct TcPlan {
   CUtensorMap map_a_hi, map_a_lo, map_w_hi, map_w_lo;
   CUtensorMap map_w2_hi, map_w2_lo;   // only read when args.k_split > 0
   int bn = 0;            // N tile: 64 | 128 | 176 | 256
+  bool a_f32 = false;    // map_a_hi is over fp32 activations; the kernel splits them into tf32 hi / lo tiles itself (EPI_LIN only)
   bool bf16 = false;     // operands are single bf16 planes (maps built with bf16 = true); EPI_LIN only, bn 128 | 256
 };
 

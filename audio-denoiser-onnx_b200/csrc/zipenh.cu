@@ -4,7 +4,7 @@
 //   -> DenseEncoder, 4 dual-path Zipformer2 encoders, mask / phase decoders                                 [zipenh_ops.cuh sequence]
 //   -> magnitude decompress x unit phase (:882-892) -> ISTFT x 1/sum w^2 (:893) -> x norm factor, output rule (:899-926) [ends.cu]
 // The sequence's LinOps (every Linear, the (2,3) dilated causal convs, the stride-2 and sub-pixel convs) run on the tcgen05
-// 3xTF32 GEMM (gemm_tc.cu: TMA-fed, TMEM accumulators), planned once per batch size; attention weights, the two attention
+// 3xTF32 GEMM (gemm_tc.cu: TMA-fed fp32 activations split into tf32 hi / lo tiles in shared memory, TMEM accumulators), planned once per batch size; attention weights, the two attention
 // value products, the gated depthwise conv and the final BiasNorm are cooperative kernels below; the remaining element-wise
 // functors run one thread per output.
 #include "zipenh_ops.cuh"
@@ -158,7 +158,7 @@ constexpr int VST = 52;            // value-row stride in shared memory: conflic
 //   NonlinAttention (NL = true): task = one query row -> 48 outputs of head 0, times the y gate.
 template <bool NL, int JJ>
 __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict__ aw, SeqMap sm, const float* __restrict__ src,
-                                                        float* __restrict__ ohi, float* __restrict__ olo) {
+                                                        float* __restrict__ out) {
   extern __shared__ float sh[];
   const int S = sm.S;
   const long long n = blockIdx.x;
@@ -223,9 +223,7 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict
           const long long t = sm.tok(n, i);
           float v = acc[k];
           if (NL) v *= __ldg(src + t * (3 * NH) + 2 * NH + c);
-          float hi, lo;
-          split_tf32(v, hi, lo);
-          ohi[t * SV + c] = hi; olo[t * SV + c] = lo;
+          out[t * SV + c] = v;
         }
       }
     }
@@ -238,7 +236,7 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict
 // written.  Adjacent threads = adjacent channels (coalesced rows of 64 floats).
 __global__ void __launch_bounds__(256) glu_dwconv_kernel(const float* __restrict__ cp, SeqMap sm, long long nseq,
                                                         const float* __restrict__ w, const float* __restrict__ b,
-                                                        float* __restrict__ ohi, float* __restrict__ olo) {
+                                                        float* __restrict__ out) {
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   const int c = (int)(idx % C);
   const long long n = idx / C;
@@ -265,10 +263,7 @@ __global__ void __launch_bounds__(256) glu_dwconv_kernel(const float* __restrict
         float acc = bias;
 #pragma unroll
         for (int k = 0; k < DWK; ++k) acc += wk[k] * ring[(d + k) % DWK];
-        const long long o = sm.tok(n, s) * C + c;
-        float hi, lo;
-        split_tf32(swoosh(acc, 1.0f), hi, lo);
-        ohi[o] = hi; olo[o] = lo;
+        out[sm.tok(n, s) * C + c] = swoosh(acc, 1.0f);
         ring[d] = nxt;
       }
     }
@@ -278,8 +273,7 @@ __global__ void __launch_bounds__(256) glu_dwconv_kernel(const float* __restrict
 // final BiasNorm + bypasses: half a warp per token row (float4 per lane)
 __global__ void __launch_bounds__(256) norm_bypass_kernel(const float* __restrict__ x, float* __restrict__ x0, long long M,
                                                          const float* __restrict__ nbias, const float* __restrict__ nscale,
-                                                         const float* __restrict__ rscale, float* __restrict__ ohi,
-                                                         float* __restrict__ olo) {
+                                                         const float* __restrict__ rscale) {
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   const long long row = idx >> 4;
   const int l = (int)(idx & 15);
@@ -293,14 +287,54 @@ __global__ void __launch_bounds__(256) norm_bypass_kernel(const float* __restric
   const float nrm = sqrtf(ss);
   const float4 ns = __ldg(reinterpret_cast<const float4*>(nscale) + l), rs = __ldg(reinterpret_cast<const float4*>(rscale) + l);
   const float4 o0 = *reinterpret_cast<const float4*>(x0 + row * C + 4 * l);
-  float v[4] = {(xv.x / nrm) * ns.x + o0.x * rs.x, (xv.y / nrm) * ns.y + o0.y * rs.y, (xv.z / nrm) * ns.z + o0.z * rs.z,
-                (xv.w / nrm) * ns.w + o0.w * rs.w};
-  float h[4], lo[4];
+  *reinterpret_cast<float4*>(x0 + row * C + 4 * l) = make_float4((xv.x / nrm) * ns.x + o0.x * rs.x, (xv.y / nrm) * ns.y + o0.y * rs.y,
+                                                                  (xv.z / nrm) * ns.z + o0.z * rs.z, (xv.w / nrm) * ns.w + o0.w * rs.w);
+}
+
+// InstanceNorm2d apply + PReLU for pool == 1 (every launch but the two sub-pixel ones): 16 threads per destination pixel,
+// one float4 of channels each; pad columns of the destination grid are written as zeros
+__global__ void __launch_bounds__(256) in_apply_kernel(InApply f, int npix) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int c4 = idx & 15, pix = idx >> 4;
+  if (pix >= npix) return;
+  const int fd = pix % f.Wd, bt = pix / f.Wd, bb = bt / f.T;
+  const int k = fd - f.dst_lo;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (k >= 0 && k < f.nout) {
+    const float4 x = *reinterpret_cast<const float4*>(f.raw + ((long long)bt * f.Ws + f.src_lo + k) * f.ld + 4 * c4);
+    const float4* st = reinterpret_cast<const float4*>(f.stat + 2 * (bb * C + 4 * c4));
+    const float4 s0 = st[0], s1 = st[1];           // (mean, rstd) x 4 channels
+    const float4 w = __ldg(reinterpret_cast<const float4*>(f.w) + c4), b = __ldg(reinterpret_cast<const float4*>(f.b) + c4);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(f.slope) + c4);
+    v.x = (x.x - s0.x) * s0.y * w.x + b.x; v.y = (x.y - s0.z) * s0.w * w.y + b.y;
+    v.z = (x.z - s1.x) * s1.y * w.z + b.z; v.w = (x.w - s1.z) * s1.w * w.w + b.w;
+    v.x = v.x >= 0.f ? v.x : a.x * v.x; v.y = v.y >= 0.f ? v.y : a.y * v.y;
+    v.z = v.z >= 0.f ? v.z : a.z * v.z; v.w = v.w >= 0.f ? v.w : a.w * v.w;
+  }
+  *reinterpret_cast<float4*>(f.of + (long long)pix * f.ldd + f.coff + 4 * c4) = v;
+}
+
+// decoder heads: one thread = one (window, frame, bin) with both taps' 2 x 64 inputs read as float4 and all outputs of the head
+__global__ void __launch_bounds__(256) head_kernel(Head f, int npix) {
+  __shared__ float4 ws[2 * 2 * C / 4];
+  for (int i = threadIdx.x; i < f.nout * 2 * C / 4; i += 256) ws[i] = __ldg(reinterpret_cast<const float4*>(f.w) + i);
+  __syncthreads();
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= npix) return;
+  const int fb = idx % FB, bt = idx / FB, t = bt % f.T, bb = bt / f.T;
+  const float4* x = reinterpret_cast<const float4*>(f.up + ((long long)bt * FU + fb) * C);
+  float acc[2] = {__ldg(f.b), f.nout > 1 ? __ldg(f.b + 1) : 0.f};
+#pragma unroll 8
+  for (int k = 0; k < 2 * C / 4; ++k) {
+    const float4 v = x[k];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) split_tf32(v[j], h[j], lo[j]);
-  *reinterpret_cast<float4*>(x0 + row * C + 4 * l) = make_float4(v[0], v[1], v[2], v[3]);
-  *reinterpret_cast<float4*>(ohi + row * C + 4 * l) = make_float4(h[0], h[1], h[2], h[3]);
-  *reinterpret_cast<float4*>(olo + row * C + 4 * l) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    for (int o = 0; o < 2; ++o)
+      if (o < f.nout) {
+        const float4 w = ws[o * (2 * C / 4) + k];
+        acc[o] += v.x * w.x + v.y * w.y + v.z * w.z + v.w * w.w;
+      }
+  }
+  for (int o = 0; o < f.nout; ++o) f.out[(((long long)bb * f.nout + o) * f.T + t) * FB + fb] = acc[o];
 }
 
 __global__ void pad_split_w_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, long long n) {
@@ -317,10 +351,10 @@ struct PlanEntry {
 };
 
 static bool same_op(const LinOp& a, const LinOp& b) {
-  bool s = a.a_hi == b.a_hi && a.a_lo == b.a_lo && a.a_sB == b.a_sB && a.a_sR == b.a_sR && a.a_r0 == b.a_r0 && a.a_ke == b.a_ke &&
+  bool s = a.a == b.a && a.a_sB == b.a_sB && a.a_sR == b.a_sR && a.a_r0 == b.a_r0 && a.a_ke == b.a_ke &&
            a.a_rows == b.a_rows && a.chunks == b.chunks && a.rows == b.rows && a.K == b.K && a.N == b.N && a.taps == b.taps &&
            a.tap_c == b.tap_c && a.a_k0 == b.a_k0 && a.W.w == b.W.w && a.W.b == b.W.b && a.act == b.act && a.resid == b.resid &&
-           a.resid2 == b.resid2 && a.colscale == b.colscale && a.Cf == b.Cf && a.c_hi == b.c_hi && a.c_lo == b.c_lo && a.ldc == b.ldc;
+           a.resid2 == b.resid2 && a.colscale == b.colscale && a.Cf == b.Cf && a.ldc == b.ldc;
   for (int i = 0; s && i < 6; ++i) s = a.tap_shift[i] == b.tap_shift[i];
   return s;
 }
@@ -369,14 +403,14 @@ struct CudaExec {
     done("zip_attn_w");
   }
   template <bool NL>
-  void apply(long long nseq, const SeqMap& sm, const float* aw, const float* src, float* ohi, float* olo, int jj) {
+  void apply(long long nseq, const SeqMap& sm, const float* aw, const float* src, float* out, int jj) {
     const size_t smem = (size_t)sm.S * VST * sizeof(float);     // <= 256 * 52 * 4 = 53 248 B
     static unsigned long long configured[4] = {0, 0, 0, 0};
 #define ZIP_APPLY(J, slot)                                                                                                    \
   {                                                                                                                           \
     auto k = attn_apply_kernel<NL, J>;                                                                                        \
     if (adn_first_use_on_device(configured[slot])) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * VST * 4); \
-    k<<<(unsigned)nseq, 256, smem, st>>>(aw, sm, src, ohi, olo);                                                              \
+    k<<<(unsigned)nseq, 256, smem, st>>>(aw, sm, src, out);                                                              \
   }
     if (jj == 2) ZIP_APPLY(2, 0) else if (jj == 4) ZIP_APPLY(4, 1) else if (jj == 6) ZIP_APPLY(6, 2) else ZIP_APPLY(8, 3)
 #undef ZIP_APPLY
@@ -384,25 +418,37 @@ struct CudaExec {
   void run(long long n, const SaApply& f) {
     const int S = f.sm.S, jj = jj_of(S);
     if (functors_only || !jj) { run_functor(n, f); return; }
-    apply<false>(n / ((long long)SV * S), f.sm, f.aw, f.v, f.ohi, f.olo, jj);
+    apply<false>(n / ((long long)SV * S), f.sm, f.aw, f.v, f.out, jj);
     done("zip_sa_apply");
   }
   void run(long long n, const NlApply& f) {
     const int S = f.sm.S, jj = jj_of(S);
     if (functors_only || !jj) { run_functor(n, f); return; }
-    apply<true>(n / ((long long)NH * S), f.sm, f.aw, f.np, f.ohi, f.olo, jj);
+    apply<true>(n / ((long long)NH * S), f.sm, f.aw, f.np, f.out, jj);
     done("zip_nl_apply");
   }
   void run(long long n, const GluDwConv& f) {
     if (functors_only) { run_functor(n, f); return; }
     const long long nseq = n / ((long long)C * f.sm.S);
-    glu_dwconv_kernel<<<(unsigned)((nseq * C + 255) / 256), 256, 0, st>>>(f.cp, f.sm, nseq, f.w, f.b, f.ohi, f.olo);
+    glu_dwconv_kernel<<<(unsigned)((nseq * C + 255) / 256), 256, 0, st>>>(f.cp, f.sm, nseq, f.w, f.b, f.out);
     done("zip_glu_dwconv");
+  }
+  void run(long long n, const InApply& f) {
+    if (functors_only || f.pool != 1) { run_functor(n, f); return; }
+    const long long npix = n / C;
+    in_apply_kernel<<<(unsigned)((npix * 16 + 255) / 256), 256, 0, st>>>(f, (int)npix);
+    done("zip_in_apply");
+  }
+  void run(long long n, const Head& f) {
+    if (functors_only) { run_functor(n, f); return; }
+    const long long npix = n / f.nout;
+    head_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(f, (int)npix);
+    done("zip_head");
   }
   void run(long long n, const NormBypass& f) {
     if (functors_only) { run_functor(n, f); return; }
     const long long M = n / C;
-    norm_bypass_kernel<<<(unsigned)((M * 16 + 255) / 256), 256, 0, st>>>(f.x, f.x0, M, f.nbias, f.nscale, f.rscale, f.ohi, f.olo);
+    norm_bypass_kernel<<<(unsigned)((M * 16 + 255) / 256), 256, 0, st>>>(f.x, f.x0, M, f.nbias, f.nscale, f.rscale);
     done("zip_norm_bypass");
   }
 
@@ -413,13 +459,14 @@ struct CudaExec {
     const int bt = g.rows >= 128 ? 128 : g.rows;
     e.plan = tc::TcPlan{};
     e.plan.bn = bn;
+    e.plan.a_f32 = true;                     // fp32 activations, split into tf32 hi / lo tiles inside the GEMM
     const int batches = g.chunks;
     const long long sB = g.a_sB ? g.a_sB : (long long)g.a_rows * g.a_sR;
-    if (!tc::make_row_map(&e.plan.map_a_hi, g.a_hi, g.a_ke, g.a_rows, g.a_sR, batches, sB, bt, 1, *err) ||
-        !tc::make_row_map(&e.plan.map_a_lo, g.a_lo, g.a_ke, g.a_rows, g.a_sR, batches, sB, bt, 1, *err) ||
+    if (!tc::make_row_map(&e.plan.map_a_hi, g.a, g.a_ke, g.a_rows, g.a_sR, batches, sB, bt, 1, *err) ||
         !tc::make_weight_map(&e.plan.map_w_hi, it->second.hi, g.W.k_pad, g.W.n_pad, bn, *err) ||
         !tc::make_weight_map(&e.plan.map_w_lo, it->second.lo, g.W.k_pad, g.W.n_pad, bn, *err))
       return false;
+    e.plan.map_a_lo = e.plan.map_a_hi;
     e.plan.map_w2_hi = e.plan.map_w_hi;
     e.plan.map_w2_lo = e.plan.map_w_lo;
     tc::TcArgs& a = e.args;
@@ -432,7 +479,7 @@ struct CudaExec {
       a.tap_kb = g.tap_c / 32; a.tap_k0 = g.a_k0;
       for (int i = 0; i < 6; ++i) a.tap_shift[i] = g.tap_shift[i];
     }
-    a.C = g.Cf; a.Chi = g.c_hi; a.Clo = g.c_lo; a.ldc = g.ldc;
+    a.C = g.Cf; a.ldc = g.ldc;
     a.bias = g.W.b; a.resid = g.resid; a.resid2 = g.resid2; a.colscale = g.colscale; a.act = g.act;
     e.key = g;
     e.valid = true;
@@ -457,16 +504,15 @@ struct CudaExec {
     cudaStreamSynchronize(st);
     cudaMemcpy(v.data(), p, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost);
   }
-  void mark_planes(const char* name, Planes pl, long long pixels, int ld, int coff, int width) {
+  void mark_strided(const char* name, const float* src, long long pixels, int ld, int coff, int width) {
     if (!capture || !dumps) return;
-    std::vector<float> hi((size_t)pixels * ld), lo((size_t)pixels * ld);
+    std::vector<float> all((size_t)pixels * ld);
     cudaStreamSynchronize(st);
-    cudaMemcpy(hi.data(), pl.hi, hi.size() * sizeof(float), cudaMemcpyDeviceToHost);
-    cudaMemcpy(lo.data(), pl.lo, lo.size() * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaMemcpy(all.data(), src, all.size() * sizeof(float), cudaMemcpyDeviceToHost);
     std::vector<float>& v = (*dumps)[name];
     v.resize((size_t)pixels * width);
     for (long long p = 0; p < pixels; ++p)
-      for (int c = 0; c < width; ++c) v[p * width + c] = hi[p * ld + coff + c] + lo[p * ld + coff + c];
+      for (int c = 0; c < width; ++c) v[p * width + c] = all[p * ld + coff + c];
   }
 };
 

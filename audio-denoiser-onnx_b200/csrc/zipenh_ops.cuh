@@ -4,10 +4,12 @@
 // `_downsampled_encoder` :783-816, layer forward :143-187 with the overrides :118-339), mask / phase decoders
 // (:725-768, :866-880) -- templated on the executor.
 //
-// * Dense contractions are `LinOp`s: C = A W^T with A given as tf32 hi / lo planes (hi + lo == the fp32 value), either plain
-//   rows or a K-concatenation of shifted channel windows of a padded channel-last map (the (2,3) dilated causal convs as
-//   implicit GEMMs: no im2col buffer).  libadn runs them on the tcgen05 3xTF32 GEMM (csrc/gemm_tc.cu); the host harness
-//   (tests/harness/zipenh_host.cpp) runs the same LinOps with plain loops, so the addressing is checked without a GPU.
+// * Dense contractions are `LinOp`s: C = A W^T with A in fp32, either plain rows or a K-concatenation of shifted channel
+//   windows of a padded channel-last map (the (2,3) dilated causal convs as implicit GEMMs: no im2col buffer).  libadn runs
+//   them on the tcgen05 3xTF32 GEMM (csrc/gemm_tc.cu) in its fp32-A mode: TMA brings the fp32 tile into shared memory and
+//   converter warps split it into the tf32 hi / lo operand tiles in place, so activations exist in HBM once, as fp32.  The
+//   host harness (tests/harness/zipenh_host.cpp) runs the same LinOps with plain loops, so the addressing is checked
+//   without a GPU.
 // * Everything else is a one-output-per-thread functor (`ex.run(count, functor)`); the CUDA executor replaces the
 //   attention functors (AttnW, SaApply, NlApply), the gated depthwise conv and the final norm by cooperative kernels (csrc/zipenh.cu), which the GPU
 //   tests compare against the same stage dumps.
@@ -79,7 +81,7 @@ struct LinW {
   int n_pad, k_pad;
 };
 struct LinOp {
-  const float *a_hi, *a_lo;
+  const float* a;
   long long a_sB, a_sR;    // element (chunk b, row r, k) at a[b*a_sB + (r + a_r0)*a_sR + k]
   int a_r0;
   int a_ke;                // readable k extent of one A row (beyond it: zeros)
@@ -93,13 +95,12 @@ struct LinOp {
   const float* resid;      // v += resid[m*ldc + n]
   const float* resid2;     // v = resid2[m*ldc + n] + (v - resid2[m*ldc + n]) * colscale[n]
   const float* colscale;
-  float* Cf;               // fp32 output (optional)
-  float *c_hi, *c_lo;      // tf32 planes (optional)
+  float* Cf;               // fp32 output
   long long ldc;
 };
-inline LinOp lin_rows(const float* a_hi, const float* a_lo, long long lda, int K, long long M, const LinW& W, int N) {
+inline LinOp lin_rows(const float* a, long long lda, int K, long long M, const LinW& W, int N) {
   LinOp g{};
-  g.a_hi = a_hi; g.a_lo = a_lo; g.a_sB = 0; g.a_sR = lda; g.a_r0 = 0; g.a_ke = K; g.a_rows = (int)M;
+  g.a = a; g.a_sB = 0; g.a_sR = lda; g.a_r0 = 0; g.a_ke = K; g.a_rows = (int)M;
   g.chunks = 1; g.rows = (int)M; g.K = K; g.N = N; g.taps = 0; g.W = W; g.act = ACT_NONE; g.ldc = N;
   return g;
 }
@@ -117,13 +118,13 @@ inline void lin_ref(const LinOp& g) {
           const long long rr = (long long)r + g.a_r0 + g.tap_shift[tp];
           if (rr < 0 || rr >= g.a_rows) continue;
           const long long o = b * g.a_sB + rr * g.a_sR + g.a_k0;
-          for (int c = 0; c < g.tap_c; ++c) acc += ((double)g.a_hi[o + c] + (double)g.a_lo[o + c]) * (double)w[tp * g.tap_c + c];
+          for (int c = 0; c < g.tap_c; ++c) acc += (double)g.a[o + c] * (double)w[tp * g.tap_c + c];
         }
       } else {
         const long long rr = (long long)r + g.a_r0;
         if (rr >= 0 && rr < g.a_rows) {
           const long long o = b * g.a_sB + rr * g.a_sR;
-          for (int k = 0; k < g.K && k < g.a_ke; ++k) acc += ((double)g.a_hi[o + k] + (double)g.a_lo[o + k]) * (double)w[k];
+          for (int k = 0; k < g.K && k < g.a_ke; ++k) acc += (double)g.a[o + k] * (double)w[k];
         }
       }
       float v = (float)acc;
@@ -132,8 +133,7 @@ inline void lin_ref(const LinOp& g) {
       const long long oc = m * g.ldc + n;
       if (g.resid) v += g.resid[oc];
       if (g.resid2) v = g.resid2[oc] + (v - g.resid2[oc]) * g.colscale[n];
-      if (g.Cf) g.Cf[oc] = v;
-      if (g.c_hi) split_tf32(v, g.c_hi[oc], g.c_lo[oc]);
+      g.Cf[oc] = v;
     }
   }
 }
@@ -177,10 +177,10 @@ struct InFin {
 };
 // normalise + affine + PReLU; source grid (T, Ws) with valid columns from src_lo, `pool` raw channels per output channel
 // (output column = source column * pool + u); destination grid (T, Wd) with the outputs at columns dst_lo.., zeros elsewhere;
-// writes fp32 and / or tf32 planes at channel offset coff of ldd-wide pixels
+// written at channel offset coff of ldd-wide pixels
 struct InApply {
   const float* raw; int ld; int Ws; int src_lo; int pool; const float* stat; const float* w; const float* b; const float* slope;
-  float* of; float *ohi, *olo; int ldd; int coff; int Wd; int dst_lo; int nout; int T;
+  float* of; int ldd; int coff; int Wd; int dst_lo; int nout; int T;
   ZIP_HD void operator()(long long i) const {
     const int c = (int)(i % C); long long p = i / C; const int fd = (int)(p % Wd); p /= Wd; const int t = (int)(p % T); const long long bb = p / T;
     float v = 0.f;
@@ -191,23 +191,19 @@ struct InApply {
       v = (raw[((bb * T + t) * Ws + fs) * ld + c * pool + u] - st[0]) * st[1] * w[c] + b[c];
       v = v >= 0.f ? v : slope[c] * v;
     }
-    const long long o = ((bb * T + t) * Wd + fd) * ldd + coff + c;
-    if (of) of[o] = v;
-    if (ohi) split_tf32(v, ohi[o], olo[o]);
+    of[((bb * T + t) * Wd + fd) * ldd + coff + c] = v;
   }
 };
 
 // compact tokens (window, frame, FQ, C) -> the x slot of the two decoder dense-block buffers (padded grid, zero pad columns)
 struct PadCopy {
-  const float* x; float *ahi, *alo, *bhi, *blo; int T;
+  const float* x; float *da, *db; int T;
   ZIP_HD void operator()(long long i) const {
     const int c = (int)(i % C); long long p = i / C; const int fd = (int)(p % FPD); const long long bt = p / FPD;
     float v = 0.f;
     if (fd >= 1 && fd <= FQ) v = x[(bt * FQ + fd - 1) * C + c];
-    float h, l;
-    split_tf32(v, h, l);
     const long long o = (bt * FPD + fd) * SLOTC + (DEPTH - 1) * C + c;
-    ahi[o] = h; alo[o] = l; bhi[o] = h; blo[o] = l;
+    da[o] = v; db[o] = v;
   }
 };
 
@@ -241,23 +237,22 @@ struct AttnW {
   }
 };
 
-// SelfAttention value product (:298-308): out[tok(n,i), c] = sum_j aw[n, c / VD, i, j] * v[tok(n,j), c]  -> tf32 planes (width SV)
+// SelfAttention value product (:298-308): out[tok(n,i), c] = sum_j aw[n, c / VD, i, j] * v[tok(n,j), c]   (width SV)
 struct SaApply {
-  const float* aw; SeqMap sm; const float* v; float *ohi, *olo;
+  const float* aw; SeqMap sm; const float* v; float* out;
   ZIP_HD void operator()(long long idx) const {
     const int S = sm.S;
     const int c = (int)(idx % SV); long long r = idx / SV; const int i = (int)(r % S); const long long n = r / S;
     const float* a = aw + ((n * HEADS + c / VD) * S + i) * (long long)S;
     float acc = 0.f;
     for (int j = 0; j < S; ++j) acc += a[j] * v[sm.tok(n, j) * SV + c];
-    const long long o = sm.tok(n, i) * SV + c;
-    split_tf32(acc, ohi[o], olo[o]);
+    out[sm.tok(n, i) * SV + c] = acc;
   }
 };
 // NonlinAttention core (:310-326) on the fused projection np = [s | x_mid | y] (width 3 NH): head 0 of the attention weights
-// mixes x_mid * tanh(s) over the sequence, then the y gate  -> tf32 planes (width NH)
+// mixes x_mid * tanh(s) over the sequence, then the y gate   (width NH)
 struct NlApply {
-  const float* aw; SeqMap sm; const float* np; float *ohi, *olo;
+  const float* aw; SeqMap sm; const float* np; float* out;
   ZIP_HD void operator()(long long idx) const {
     const int S = sm.S;
     const int c = (int)(idx % NH); long long r = idx / NH; const int i = (int)(r % S); const long long n = r / S;
@@ -268,15 +263,14 @@ struct NlApply {
       acc += a[j] * (pj[NH + c] * tanhf(pj[c]));
     }
     const long long o = sm.tok(n, i);
-    acc *= np[o * (3 * NH) + 2 * NH + c];
-    split_tf32(acc, ohi[o * NH + c], olo[o * NH + c]);
+    out[o * NH + c] = acc * np[o * (3 * NH) + 2 * NH + c];
   }
 };
 
 // ConvolutionModule core (:328-339) on the fused projection cp = [x_mid | gate] (width 2 C): u = x_mid * sigmoid(gate),
-// depthwise Conv1d(k 15, 'same') along the sequence, then the SwooshR of the out projection (:131-140) -> tf32 planes
+// depthwise Conv1d(k 15, 'same') along the sequence, then the SwooshR of the out projection (:131-140)
 struct GluDwConv {
-  const float* cp; SeqMap sm; const float* w; const float* b; float *ohi, *olo;     // w (C, DWK)
+  const float* cp; SeqMap sm; const float* w; const float* b; float* out;     // w (C, DWK)
   ZIP_HD void operator()(long long idx) const {
     const int S = sm.S;
     const int c = (int)(idx % C); long long r = idx / C; const int s = (int)(r % S); const long long n = r / S;
@@ -287,29 +281,26 @@ struct GluDwConv {
       const float* pj = cp + sm.tok(n, sj) * (2 * C);
       acc += w[c * DWK + k] * (pj[c] * sigmoidf_(pj[C + c]));
     }
-    const long long o = sm.tok(n, s) * C + c;
-    split_tf32(swoosh(acc, 1.0f), ohi[o], olo[o]);
+    out[sm.tok(n, s) * C + c] = swoosh(acc, 1.0f);
   }
 };
 
 // final BiasNorm + layer bypass + dual-path bypass, fused as the reference fuses them (:176-184, :659-676):
-// x0 <- x / ||x - bias||_2 * nscale + x0 * rscale   (in place on the layer input; also its tf32 planes)
+// x0 <- x / ||x - bias||_2 * nscale + x0 * rscale   (in place on the layer input)
 struct NormBypass {
-  const float* x; float* x0; const float* nbias; const float* nscale; const float* rscale; float *ohi, *olo;
+  const float* x; float* x0; const float* nbias; const float* nscale; const float* rscale;
   ZIP_HD void operator()(long long i) const {
     const int c = (int)(i % C); const long long r = i / C;
     const float* xr = x + r * C;
     float ss = 0.f;
     for (int k = 0; k < C; ++k) { const float d = xr[k] - nbias[k]; ss += d * d; }
-    const float v = (xr[c] / sqrtf(ss)) * nscale[c] + x0[i] * rscale[c];
-    x0[i] = v;
-    split_tf32(v, ohi[i], olo[i]);
+    x0[i] = (xr[c] / sqrtf(ss)) * nscale[c] + x0[i] * rscale[c];
   }
 };
 
 // SimpleDownsample over frames then sub-bands (:194-220, :788-791): last position repeated up to a multiple of ds
 struct Down {
-  const float* x; const float* wt; const float* wf; int ds; int T, F, Td, Fd; float* of; float *ohi, *olo;
+  const float* x; const float* wt; const float* wf; int ds; int T, F, Td, Fd; float* of;
   ZIP_HD void operator()(long long i) const {
     const int c = (int)(i % C); long long p = i / C; const int fj = (int)(p % Fd); p /= Fd; const int ti = (int)(p % Td); const long long bb = p / Td;
     float acc = 0.f;
@@ -323,17 +314,14 @@ struct Down {
       acc += a * wf[e];
     }
     of[i] = acc;
-    split_tf32(acc, ohi[i], olo[i]);
   }
 };
 // out-combiner (:806-816): x0 <- x0 * (1 - scale) + up(y) * scale, nearest-neighbour upsampling of both axes
 struct UpCombine {
-  const float* y; const float* scale; const float* rscale; int ds; int T, F, Td, Fd; float* x0; float *ohi, *olo;
+  const float* y; const float* scale; const float* rscale; int ds; int T, F, Td, Fd; float* x0;
   ZIP_HD void operator()(long long i) const {
     const int c = (int)(i % C); long long p = i / C; const int f = (int)(p % F); p /= F; const int t = (int)(p % T); const long long bb = p / T;
-    const float v = x0[i] * rscale[c] + (y[((bb * Td + t / ds) * Fd + f / ds) * C + c] * scale[c]);
-    x0[i] = v;
-    split_tf32(v, ohi[i], olo[i]);
+    x0[i] = x0[i] * rscale[c] + (y[((bb * Td + t / ds) * Fd + f / ds) * C + c] * scale[c]);
   }
 };
 
@@ -455,9 +443,8 @@ bool bind(Weights& W, int T, const int* ds, Lookup& lk) {
 }
 
 // ------------------------------------------------------------------------------------------------ workspace
-struct Planes { float *hi, *lo; };
 struct Workspace {
-  Planes encbuf, d3, xp, hp, p64, xpd, decm, decp;
+  float *encbuf, *d3, *hp, *p64, *decm, *decp;
   float *raw, *stat, *x0, *x, *t1, *t2, *aw, *x0d, *xd, *up;
   double* part;
 };
@@ -471,9 +458,9 @@ template <class Alloc>
 bool alloc_ws(Workspace& w, int B, int T, Alloc& alloc) {
   const size_t b = (size_t)B, pxE = b * T * FPE, pxD = b * T * FPD, M = b * T * FQ, Md = b * ceil_div(T, 2) * ceil_div(FQ, 2);
   const size_t slack = 4096;
-  auto pl = [&](Planes& p, size_t n) { p.hi = alloc(n + slack); p.lo = alloc(n + slack); return p.hi && p.lo; };
-  bool ok = pl(w.encbuf, pxE * SLOTC) && pl(w.d3, pxE * C) && pl(w.xp, M * C) && pl(w.hp, M * FF3) && pl(w.p64, M * C) &&
-            pl(w.xpd, Md * C) && pl(w.decm, pxD * SLOTC) && pl(w.decp, pxD * SLOTC);
+  auto pl = [&](float*& p, size_t n) { p = alloc(n + slack); return p != nullptr; };
+  bool ok = pl(w.encbuf, pxE * SLOTC) && pl(w.d3, pxE * C) && pl(w.hp, M * FF3) && pl(w.p64, M * C) && pl(w.decm, pxD * SLOTC) &&
+            pl(w.decp, pxD * SLOTC);
   if (!ok) return false;
   const size_t raw_n = pxE * C > pxD * UPF * C ? pxE * C : pxD * UPF * C;
   w.raw = alloc(raw_n + slack);
@@ -488,48 +475,46 @@ bool alloc_ws(Workspace& w, int B, int T, Alloc& alloc) {
 inline size_t ws_floats(int B, int T) {
   const size_t b = (size_t)B, pxE = b * T * FPE, pxD = b * T * FPD, M = b * T * FQ, Md = b * ceil_div(T, 2) * ceil_div(FQ, 2);
   const size_t raw_n = pxE * C > pxD * UPF * C ? pxE * C : pxD * UPF * C;
-  return 2 * (pxE * SLOTC + pxE * C + M * C + M * FF3 + M * C + Md * C + 2 * pxD * SLOTC) + raw_n + b * C * 2 + b * T * UPF * C * 4 +
+  return pxE * SLOTC + pxE * C + M * FF3 + M * C + 2 * pxD * SLOTC + raw_n + b * C * 2 + b * T * UPF * C * 4 +
          M * (2 * C + 3 * NH + C) + aw_floats(B, T) + 2 * Md * C + b * T * FU * C;
 }
 
 // ------------------------------------------------------------------------------------------------ launch sequence
 // InstanceNorm2d + PReLU of a raw conv output (see InPart / InFin / InApply)
 template <class Exec>
-void inorm(Exec& ex, Workspace& w, int B, int T, int ld, int Ws, int src_lo, int nsrc, int pool, const NormAct& na, float* of, Planes op,
+void inorm(Exec& ex, Workspace& w, int B, int T, int ld, int Ws, int src_lo, int nsrc, int pool, const NormAct& na, float* of,
            int ldd, int coff, int Wd, int dst_lo) {
   ex.run((long long)B * T * ld, InPart{w.raw, ld, Ws, src_lo, src_lo + nsrc, w.part});
   ex.run((long long)B * (ld / pool), InFin{w.part, ld, T, nsrc, pool, w.stat});
-  ex.run((long long)B * T * Wd * C, InApply{w.raw, ld, Ws, src_lo, pool, w.stat, na.w, na.b, na.slope, of, op.hi, op.lo, ldd, coff, Wd, dst_lo,
-                                           nsrc * pool, T});
+  ex.run((long long)B * T * Wd * C, InApply{w.raw, ld, Ws, src_lo, pool, w.stat, na.w, na.b, na.slope, of, ldd, coff, Wd, dst_lo, nsrc * pool, T});
 }
 
 // DenseBlockV2 on a padded grid of width Wp (valid columns 1..nvalid): layer i reads the last C*(i+1) channels of `buf`
 // and writes slot DEPTH-2-i, the last layer writes `last` (C-wide pixels)
 template <class Exec>
-void dense_block(Exec& ex, Workspace& w, const DenseW& d, Planes buf, Planes last, int B, int T, int Wp, int nvalid, const char* tag) {
+void dense_block(Exec& ex, Workspace& w, const DenseW& d, float* buf, float* last, int B, int T, int Wp, int nvalid, const char* tag) {
   for (int i = 0; i < DEPTH; ++i) {
     const int dil = 1 << i, cin = C * (i + 1);
     LinOp g{};
-    g.a_hi = buf.hi; g.a_lo = buf.lo; g.a_sB = (long long)T * Wp * SLOTC; g.a_sR = SLOTC; g.a_r0 = 0; g.a_ke = SLOTC; g.a_rows = T * Wp;
+    g.a = buf; g.a_sB = (long long)T * Wp * SLOTC; g.a_sR = SLOTC; g.a_r0 = 0; g.a_ke = SLOTC; g.a_rows = T * Wp;
     g.chunks = B; g.rows = T * Wp; g.K = 6 * cin; g.N = C;
     g.taps = 6; g.tap_c = cin; g.a_k0 = SLOTC - cin;
     for (int kt = 0; kt < 2; ++kt)
       for (int kf = 0; kf < 3; ++kf) g.tap_shift[kt * 3 + kf] = (kt - 1) * dil * Wp + (kf - 1);
     g.W = d.conv[i]; g.act = ACT_NONE; g.Cf = w.raw; g.ldc = C;
     ex.gemm(g, "zip_dense_conv");
-    if (i + 1 < DEPTH) inorm(ex, w, B, T, C, Wp, 1, nvalid, 1, d.na[i], nullptr, buf, SLOTC, (DEPTH - 2 - i) * C, Wp, 1);
-    else inorm(ex, w, B, T, C, Wp, 1, nvalid, 1, d.na[i], nullptr, last, C, 0, Wp, 1);
+    if (i + 1 < DEPTH) inorm(ex, w, B, T, C, Wp, 1, nvalid, 1, d.na[i], buf, SLOTC, (DEPTH - 2 - i) * C, Wp, 1);
+    else inorm(ex, w, B, T, C, Wp, 1, nvalid, 1, d.na[i], last, C, 0, Wp, 1);
     char nm[32];
     snprintf(nm, sizeof(nm), "%s.d%d", tag, i);
-    ex.mark_planes(nm, i + 1 < DEPTH ? buf : last, (long long)B * T * Wp, i + 1 < DEPTH ? SLOTC : C, i + 1 < DEPTH ? (DEPTH - 2 - i) * C : 0, C);
+    ex.mark_strided(nm, i + 1 < DEPTH ? buf : last, (long long)B * T * Wp, i + 1 < DEPTH ? SLOTC : C, i + 1 < DEPTH ? (DEPTH - 2 - i) * C : 0, C);
   }
 }
 
-// one Zipformer2EncoderLayer over M tokens with the sequence structure `sm` (:143-187); x0 / xp hold the layer input on
-// entry and the layer output on exit
+// one Zipformer2EncoderLayer over M tokens with the sequence structure `sm` (:143-187); x0 holds the layer input on entry and
+// the layer output on exit, x is the running residual stream
 template <class Exec>
-void zip_layer(Exec& ex, Workspace& w, const LayerW& L, float* x0, float* x, Planes xp, long long M, const SeqMap& sm, long long nseq,
-               const char* tag) {
+void zip_layer(Exec& ex, Workspace& w, const LayerW& L, float* x0, float* x, long long M, const SeqMap& sm, long long nseq, const char* tag) {
   const int S = sm.S;
   char nm[48];
   auto mark = [&](const char* leaf, const float* p, int width) {
@@ -537,73 +522,73 @@ void zip_layer(Exec& ex, Workspace& w, const LayerW& L, float* x0, float* x, Pla
     ex.mark(nm, p, M * width);
   };
   // attention projection and weights
-  LinOp g = lin_rows(xp.hi, xp.lo, C, C, M, L.attn_in, AP);
+  LinOp g = lin_rows(x0, C, C, M, L.attn_in, AP);
   g.Cf = w.t1; g.ldc = AP;
   ex.gemm(g, "zip_attn_in");
   ex.run(nseq * HEADS * S, AttnW{w.t1, sm, L.pos, w.aw});
   snprintf(nm, sizeof(nm), "%s.aw", tag);
   ex.mark(nm, w.aw, nseq * HEADS * S * S);
-  // feed_forward1
-  auto ff = [&](const LinW& win, const LinW& wout, int hidden, const float* resid, const float* resid2, const float* cs) {
-    LinOp a = lin_rows(xp.hi, xp.lo, C, C, M, win, hidden);
-    a.act = ACT_SWOOSH_L; a.c_hi = w.hp.hi; a.c_lo = w.hp.lo; a.ldc = hidden;
+  // feed-forward modules: in projection + SwooshL, out projection + residual (+ bypass_mid)
+  auto ff = [&](const float* in, const LinW& win, const LinW& wout, int hidden, const float* resid, const float* resid2, const float* cs) {
+    LinOp a = lin_rows(in, C, C, M, win, hidden);
+    a.act = ACT_SWOOSH_L; a.Cf = w.hp; a.ldc = hidden;
     ex.gemm(a, "zip_ff_in");
-    LinOp o = lin_rows(w.hp.hi, w.hp.lo, hidden, hidden, M, wout, C);
-    o.resid = resid; o.resid2 = resid2; o.colscale = cs; o.Cf = x; o.c_hi = xp.hi; o.c_lo = xp.lo; o.ldc = C;
+    LinOp o = lin_rows(w.hp, hidden, hidden, M, wout, C);
+    o.resid = resid; o.resid2 = resid2; o.colscale = cs; o.Cf = x; o.ldc = C;
     ex.gemm(o, "zip_ff_out");
   };
-  ff(L.ff1_in, L.ff1_out, FF1, x0, nullptr, nullptr);
+  ff(x0, L.ff1_in, L.ff1_out, FF1, x0, nullptr, nullptr);
   mark("ff1", x, C);
   // NonlinAttention
-  g = lin_rows(xp.hi, xp.lo, C, C, M, L.nl_in, 3 * NH);
+  g = lin_rows(x, C, C, M, L.nl_in, 3 * NH);
   g.Cf = w.t1; g.ldc = 3 * NH;
   ex.gemm(g, "zip_nl_in");
-  ex.run(M * NH, NlApply{w.aw, sm, w.t1, w.p64.hi, w.p64.lo});
-  g = lin_rows(w.p64.hi, w.p64.lo, NH, NH, M, L.nl_out, C);
-  g.resid = x; g.Cf = x; g.c_hi = xp.hi; g.c_lo = xp.lo; g.ldc = C;
+  ex.run(M * NH, NlApply{w.aw, sm, w.t1, w.p64});
+  g = lin_rows(w.p64, NH, NH, M, L.nl_out, C);
+  g.resid = x; g.Cf = x; g.ldc = C;
   ex.gemm(g, "zip_nl_out");
   mark("nla", x, C);
   auto self_attn = [&](const LinW& win, const LinW& wout) {
-    LinOp a = lin_rows(xp.hi, xp.lo, C, C, M, win, SV);
+    LinOp a = lin_rows(x, C, C, M, win, SV);
     a.Cf = w.t2; a.ldc = SV;
     ex.gemm(a, "zip_sa_in");
-    ex.run(M * SV, SaApply{w.aw, sm, w.t2, w.p64.hi, w.p64.lo});
-    LinOp o = lin_rows(w.p64.hi, w.p64.lo, SV, SV, M, wout, C);
-    o.resid = x; o.Cf = x; o.c_hi = xp.hi; o.c_lo = xp.lo; o.ldc = C;
+    ex.run(M * SV, SaApply{w.aw, sm, w.t2, w.p64});
+    LinOp o = lin_rows(w.p64, SV, SV, M, wout, C);
+    o.resid = x; o.Cf = x; o.ldc = C;
     ex.gemm(o, "zip_sa_out");
   };
   auto conv_module = [&](const LinW& win, const LinW& wout, const float* dw_w, const float* dw_b) {
-    LinOp a = lin_rows(xp.hi, xp.lo, C, C, M, win, 2 * C);
+    LinOp a = lin_rows(x, C, C, M, win, 2 * C);
     a.Cf = w.t1; a.ldc = 2 * C;
     ex.gemm(a, "zip_cv_in");
-    ex.run(nseq * S * C, GluDwConv{w.t1, sm, dw_w, dw_b, w.p64.hi, w.p64.lo});
-    LinOp o = lin_rows(w.p64.hi, w.p64.lo, C, C, M, wout, C);
-    o.resid = x; o.Cf = x; o.c_hi = xp.hi; o.c_lo = xp.lo; o.ldc = C;
+    ex.run(nseq * S * C, GluDwConv{w.t1, sm, dw_w, dw_b, w.p64});
+    LinOp o = lin_rows(w.p64, C, C, M, wout, C);
+    o.resid = x; o.Cf = x; o.ldc = C;
     ex.gemm(o, "zip_cv_out");
   };
   self_attn(L.sa1_in, L.sa1_out);
   mark("sa1", x, C);
   conv_module(L.cv1_in, L.cv1_out, L.dw1_w, L.dw1_b);
   mark("cv1", x, C);
-  ff(L.ff2_in, L.ff2_out, FF2, x, x0, L.mid_scale);      // + bypass_mid against the layer input
+  ff(x, L.ff2_in, L.ff2_out, FF2, x, x0, L.mid_scale);      // + bypass_mid against the layer input
   mark("mid", x, C);
   self_attn(L.sa2_in, L.sa2_out);
   conv_module(L.cv2_in, L.cv2_out, L.dw2_w, L.dw2_b);
-  ff(L.ff3_in, L.ff3_out, FF3, x, nullptr, nullptr);
+  ff(x, L.ff3_in, L.ff3_out, FF3, x, nullptr, nullptr);
   mark("ff3", x, C);
-  ex.run(M * C, NormBypass{x, x0, L.norm_bias, L.norm_scale, L.res_scale, xp.hi, xp.lo});
+  ex.run(M * C, NormBypass{x, x0, L.norm_bias, L.norm_scale, L.res_scale});
 }
 
 template <class Exec>
-void dual_path(Exec& ex, Workspace& w, const EncW& e, float* x0, float* x, Planes xp, int B, int T, int F, const char* tag) {
+void dual_path(Exec& ex, Workspace& w, const EncW& e, float* x0, float* x, int B, int T, int F, const char* tag) {
   const long long M = (long long)B * T * F;
   char nm[32];
   snprintf(nm, sizeof(nm), "%s.f", tag);
-  zip_layer(ex, w, e.f, x0, x, xp, M, seq_over_f(T, F), (long long)B * T, nm);
+  zip_layer(ex, w, e.f, x0, x, M, seq_over_f(T, F), (long long)B * T, nm);
   snprintf(nm, sizeof(nm), "%s.f.out", tag);
   ex.mark(nm, x0, M * C);
   snprintf(nm, sizeof(nm), "%s.t", tag);
-  zip_layer(ex, w, e.t, x0, x, xp, M, seq_over_t(T, F), (long long)B * F, nm);
+  zip_layer(ex, w, e.t, x0, x, M, seq_over_t(T, F), (long long)B * F, nm);
 }
 
 // feat (B, 2, T, FB) planar -> mx (B, 1, T, FB) (mask-decoder output before the ReLU), ri (B, 2, T, FB)
@@ -611,15 +596,15 @@ template <class Exec>
 void forward(Exec& ex, Workspace& w, const Weights& W, const float* feat, float* mx, float* ri, int B, int T) {
   // ---- DenseEncoder (:851-853)
   ex.run((long long)B * T * FB * C, FeatConv{feat, W.c1_w, W.c1_b, w.raw, T});
-  inorm(ex, w, B, T, C, FPE, 1, FB, 1, W.c1_na, nullptr, w.encbuf, SLOTC, (DEPTH - 1) * C, FPE, 1);
-  ex.mark_planes("enc0", w.encbuf, (long long)B * T * FPE, SLOTC, (DEPTH - 1) * C, C);
+  inorm(ex, w, B, T, C, FPE, 1, FB, 1, W.c1_na, w.encbuf, SLOTC, (DEPTH - 1) * C, FPE, 1);
+  ex.mark_strided("enc0", w.encbuf, (long long)B * T * FPE, SLOTC, (DEPTH - 1) * C, C);
   dense_block(ex, w, W.enc_dense, w.encbuf, w.d3, B, T, FPE, FB, "enc");
   {   // dense_conv_2: (1,3) stride (1,2) pad (0,1): row (t, f') starts at padded pixel t*FPE + 2f' and spans 3 pixels of C channels
     LinOp g{};
-    g.a_hi = w.d3.hi; g.a_lo = w.d3.lo; g.a_sB = (long long)T * FPE * C; g.a_sR = 2 * C; g.a_r0 = 0; g.a_ke = 3 * C; g.a_rows = T * FH;
+    g.a = w.d3; g.a_sB = (long long)T * FPE * C; g.a_sR = 2 * C; g.a_r0 = 0; g.a_ke = 3 * C; g.a_rows = T * FH;
     g.chunks = B; g.rows = T * FH; g.K = 3 * C; g.N = C; g.taps = 0; g.W = W.c2; g.act = ACT_NONE; g.Cf = w.raw; g.ldc = C;
     ex.gemm(g, "zip_stride_conv");
-    inorm(ex, w, B, T, C, FH, 0, FQ, 1, W.c2_na, w.x0, w.xp, C, 0, FQ, 0);
+    inorm(ex, w, B, T, C, FH, 0, FQ, 1, W.c2_na, w.x0, C, 0, FQ, 0);
   }
   ex.mark("enc", w.x0, (long long)B * T * FQ * C);
   // ---- four dual-path encoders (:863-867)
@@ -628,31 +613,30 @@ void forward(Exec& ex, Workspace& w, const Weights& W, const float* feat, float*
     char tag[16];
     snprintf(tag, sizeof(tag), "ts%d", k);
     if (e.ds == 1) {
-      dual_path(ex, w, e, w.x0, w.x, w.xp, B, T, FQ, tag);
+      dual_path(ex, w, e, w.x0, w.x, B, T, FQ, tag);
     } else {
       const int Td = ceil_div(T, e.ds), Fd = ceil_div(FQ, e.ds);
-      ex.run((long long)B * Td * Fd * C, Down{w.x0, e.down_t, e.down_f, e.ds, T, FQ, Td, Fd, w.x0d, w.xpd.hi, w.xpd.lo});
+      ex.run((long long)B * Td * Fd * C, Down{w.x0, e.down_t, e.down_f, e.ds, T, FQ, Td, Fd, w.x0d});
       char nm[32];
       snprintf(nm, sizeof(nm), "%s.down", tag);
       ex.mark(nm, w.x0d, (long long)B * Td * Fd * C);
-      dual_path(ex, w, e, w.x0d, w.xd, w.xpd, B, Td, Fd, tag);
-      ex.run((long long)B * T * FQ * C, UpCombine{w.x0d, e.comb_scale, e.comb_rscale, e.ds, T, FQ, Td, Fd, w.x0, w.xp.hi, w.xp.lo});
+      dual_path(ex, w, e, w.x0d, w.xd, B, Td, Fd, tag);
+      ex.run((long long)B * T * FQ * C, UpCombine{w.x0d, e.comb_scale, e.comb_rscale, e.ds, T, FQ, Td, Fd, w.x0});
     }
     ex.mark(tag, w.x0, (long long)B * T * FQ * C);
   }
   // ---- decoders (:868-880): the two dense blocks share their input
-  ex.run((long long)B * T * FPD * C, PadCopy{w.x0, w.decm.hi, w.decm.lo, w.decp.hi, w.decp.lo, T});
+  ex.run((long long)B * T * FPD * C, PadCopy{w.x0, w.decm, w.decp, T});
   for (int dec = 0; dec < 2; ++dec) {
     const DenseW& dw = dec ? W.phase_dense : W.mask_dense;
-    Planes buf = dec ? w.decp : w.decm;
-    dense_block(ex, w, dw, buf, w.d3, B, T, FPD, FQ, dec ? "phase" : "mask");
+    dense_block(ex, w, dw, dec ? w.decp : w.decm, w.d3, B, T, FPD, FQ, dec ? "phase" : "mask");
     // sub-pixel conv (1,3) pad (0,1) to UPF*C channels: row of pixel p starts at pixel p-1 and spans 3 pixels
     LinOp g{};
-    g.a_hi = w.d3.hi; g.a_lo = w.d3.lo; g.a_sB = (long long)T * FPD * C; g.a_sR = C; g.a_r0 = -1; g.a_ke = 3 * C; g.a_rows = T * FPD;
+    g.a = w.d3; g.a_sB = (long long)T * FPD * C; g.a_sR = C; g.a_r0 = -1; g.a_ke = 3 * C; g.a_rows = T * FPD;
     g.chunks = B; g.rows = T * FPD; g.K = 3 * C; g.N = UPF * C; g.taps = 0; g.W = dec ? W.phase_up : W.mask_up; g.act = ACT_NONE;
     g.Cf = w.raw; g.ldc = UPF * C;
     ex.gemm(g, "zip_up_conv");
-    inorm(ex, w, B, T, UPF * C, FPD, 1, FQ, UPF, dec ? W.phase_up_na : W.mask_up_na, w.up, Planes{nullptr, nullptr}, C, 0, FU, 0);
+    inorm(ex, w, B, T, UPF * C, FPD, 1, FQ, UPF, dec ? W.phase_up_na : W.mask_up_na, w.up, C, 0, FU, 0);
     ex.mark(dec ? "phase_up" : "mask_up", w.up, (long long)B * T * FU * C);
     if (dec) ex.run((long long)B * 2 * T * FB, Head{w.up, W.phase_out_w, W.phase_out_b, 2, ri, T});
     else ex.run((long long)B * T * FB, Head{w.up, W.mask_out_w, W.mask_out_b, 1, mx, T});

@@ -28,11 +28,11 @@ struct HostExec {
   void mark(const char* name, const float* p, long long count) {
     if (dump) dump(name, p, count);
   }
-  void mark_planes(const char* name, zip::Planes pl, long long pixels, int ld, int coff, int width) {
+  void mark_strided(const char* name, const float* src, long long pixels, int ld, int coff, int width) {
     if (!dump) return;
     std::vector<float> v((size_t)pixels * width);
     for (long long p = 0; p < pixels; ++p)
-      for (int c = 0; c < width; ++c) v[p * width + c] = pl.hi[p * ld + coff + c] + pl.lo[p * ld + coff + c];
+      for (int c = 0; c < width; ++c) v[p * width + c] = src[p * ld + coff + c];
     dump(name, v.data(), (long long)v.size());
   }
 };
