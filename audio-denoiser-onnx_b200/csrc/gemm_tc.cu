@@ -30,7 +30,7 @@ constexpr int BK = 32;                 // 32 fp32 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 8;              // tf32: 32 bytes of K per instruction
 constexpr int NEPI = 16;                // epilogue warps: four per TMEM lane quarter (the epilogue, not the tensor pipe, limits
                                         // small-K and bf16 GEMMs: 8 warps could not issue fast enough)
-constexpr int NCONV_AF = 3;             // fp32-A mode: converter warps behind the epilogue warps
+constexpr int NCONV_AF = 2;             // fp32-A mode: converter warps behind the epilogue warps
 constexpr int NTHREADS = 64 + 32 * NEPI; // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 constexpr int NTHREADS_AF = NTHREADS + 32 * NCONV_AF;
 constexpr uint32_t A_TILE_BYTES = BM * BK * 4;   // 16 KiB
@@ -131,7 +131,7 @@ struct Smem {
 };
 
 // AF (fp32 A operand, ZipEnhancer): the A tensor map is over the fp32 activations themselves.  TMA lands the fp32 tile in the
-// hi slot of the stage; three converter warps (behind the sixteen epilogue warps) split every element in place into
+// hi slot of the stage; two converter warps (behind the sixteen epilogue warps; 640 threads keep the 96-register budget) split every element in place into
 // hi = x & 0xFFFFE000 (kept where it is) and lo = x - hi (lo slot) -- the 128-byte swizzle is a permutation of 16-byte chunks,
 // so an element-wise pass needs no knowledge of it -- then fence.proxy.async and hand the stage to the MMA warp.  Activations
 // live in HBM once, as fp32: half the A bytes, and no producer writes operand planes.
