@@ -8,6 +8,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -183,6 +184,16 @@ struct adn_model {
   int last_launches = 0;
   int last_batch = 0;
   int stop_after = 0;       // diagnostics: stop the launch sequence after N kernels
+
+  // CUDA graphs of whole runs (adn_run): one executable graph per (input, outputs, batch, stream); the first run of a batch
+  // size is eager (workspace allocation, GEMM planning), the second is captured, later ones are one cudaGraphLaunch
+  struct GraphEntry {
+    const void* in; void* outs[4]; int batch; cudaStream_t st; cudaGraphExec_t exec; unsigned long long epoch;
+  };
+  std::vector<GraphEntry> graphs;
+  std::map<int, int> eager_runs;
+  bool use_graphs = true;
+  unsigned long long graph_launches = 0;
 };
 
 namespace {
@@ -242,6 +253,7 @@ adn_status dev_alloc(adn_model* m, void** p, size_t bytes, bool zero) {
 }
 
 void free_workspace(adn_model* m) {
+  adn_note_free();
   for (void* p : m->allocs) cudaFree(p);
   m->allocs.clear();
   m->ws_bytes = 0;
@@ -534,6 +546,7 @@ __global__ void rs_convert_kernel(const float* __restrict__ src, void* __restric
 adn_status gtcrn_run_resampled(adn_model* m, const void* d_in, void* d_out, int batch, cudaStream_t st) {
   if (batch > m->rs_cap) {
     ADN_CUDA_TRY(cudaDeviceSynchronize(), m->err);
+    adn_note_free();
     if (m->rs_cap) { cudaFree(m->rs_xc); cudaFree(m->rs_xm); cudaFree(m->rs_ym); cudaFree(m->rs_yr); }
     m->rs_cap = 0;
     ADN_CUDA_TRY(cudaMalloc((void**)&m->rs_xc, (size_t)batch * m->io_L * 4), m->err);
@@ -569,6 +582,10 @@ adn_status gtcrn_run_resampled(adn_model* m, const void* d_in, void* d_out, int 
 }
 
 }  // namespace
+
+static std::atomic<unsigned long long> g_alloc_epoch{1};
+void adn_note_free() { g_alloc_epoch.fetch_add(1, std::memory_order_relaxed); }
+unsigned long long adn_alloc_epoch() { return g_alloc_epoch.load(std::memory_order_relaxed); }
 
 // Every entry point runs on the handle's device and puts the caller's current device back (a process that drives several GPUs,
 // e.g. torch with one model per device, must not find its current device changed by a library call).
@@ -736,6 +753,10 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
     m->err = "cudaStreamCreate failed";
     return fail(ADN_ERR_CUDA);
   }
+  {
+    const char* ge = getenv("ADN_GRAPHS");             // ADN_GRAPHS=0: never replay runs as CUDA graphs
+    m->use_graphs = !(ge && ge[0] == '0');
+  }
   // weight uploads, operand splits and table memsets ran on the legacy default stream; runs use non-blocking streams
   if (cudaDeviceSynchronize() != cudaSuccess) {
     m->err = "device initialisation failed";
@@ -749,6 +770,7 @@ void adn_destroy(adn_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   cudaDeviceSynchronize();
+  for (auto& ge : m->graphs) cudaGraphExecDestroy(ge.exec);
   delete m->impl;
   free_workspace(m);
   if (m->d_blob) cudaFree(m->d_blob);
@@ -806,19 +828,74 @@ adn_status adn_run(adn_model* m, const void* d_in, void* const* d_outs, int32_t 
   }
   DeviceGuard dg(m->device);
   if (!dg.ok) { m->err = "cudaSetDevice failed"; return ADN_ERR_CUDA; }
-  if (m->impl) {
-    m->ev_used = 0;
-    m->ev_stream = (cudaStream_t)stream;
-    m->impl->tick = tick_cb;
-    m->impl->tick_ctx = m;
-    tick_cb(m, "start");
-    adn_status r = m->impl->run_multi(d_in, d_outs, batch, (cudaStream_t)stream);
-    if (r != ADN_OK) m->err = m->impl->err;
-    m->last_batch = batch;
-    return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  auto eager = [&]() -> adn_status {
+    if (m->impl) {
+      m->ev_used = 0;
+      m->ev_stream = st;
+      m->impl->tick = tick_cb;
+      m->impl->tick_ctx = m;
+      tick_cb(m, "start");
+      adn_status r = m->impl->run_multi(d_in, d_outs, batch, st);
+      if (r != ADN_OK) m->err = m->impl->err;
+      m->last_batch = batch;
+      return r;
+    }
+    if (!m->rs_in && !m->rs_out) return gtcrn_run(m, d_in, d_outs[0], batch, st, nullptr);
+    return gtcrn_run_resampled(m, d_in, d_outs[0], batch, st);
+  };
+  // Launch-bound regime (batch 1: 28 ... 514 dependent launches per run): replay the run as one CUDA graph.  Not on the legacy
+  // default stream (it cannot be captured), not while profiling or dumping stages, not inside a caller's own capture.
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  const bool graphable = m->use_graphs && !m->profiling && m->stop_after == 0 && st != nullptr && st != cudaStreamLegacy &&
+                         st != cudaStreamPerThread && cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone;
+  if (!graphable) return eager();
+  const int n_out = m->impl ? m->impl->n_outputs() : 1;
+  const unsigned long long ep = adn_alloc_epoch();
+  if (!m->graphs.empty() && m->graphs[0].epoch != ep) {        // some workspace was re-allocated since: addresses are stale
+    for (auto& ge : m->graphs) cudaGraphExecDestroy(ge.exec);
+    m->graphs.clear();
   }
-  if (!m->rs_in && !m->rs_out) return gtcrn_run(m, d_in, d_outs[0], batch, (cudaStream_t)stream, nullptr);
-  return gtcrn_run_resampled(m, d_in, d_outs[0], batch, (cudaStream_t)stream);
+  for (auto& ge : m->graphs) {
+    bool same = ge.in == d_in && ge.batch == batch && ge.st == st;
+    for (int o = 0; same && o < n_out; ++o) same = ge.outs[o] == d_outs[o];
+    if (!same) continue;
+    ADN_CUDA_TRY(cudaGraphLaunch(ge.exec, st), m->err);
+    ++m->graph_launches;
+    m->last_batch = batch;
+    return ADN_OK;
+  }
+  int& seen = m->eager_runs[batch];
+  if (seen < 1) { ++seen; return eager(); }
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    m->use_graphs = false;
+    return eager();
+  }
+  adn_status r = eager();
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  cudaGraphExec_t exec = nullptr;
+  if (r == ADN_OK && ce == cudaSuccess && graph && adn_alloc_epoch() == ep) ce = cudaGraphInstantiate(&exec, graph, 0);
+  else if (ce == cudaSuccess) ce = cudaErrorUnknown;
+  if (graph) cudaGraphDestroy(graph);
+  if (r != ADN_OK) return r;
+  if (ce != cudaSuccess || !exec) {             // (a prohibited call inside the run, or an allocation: stay eager from now on)
+    cudaGetLastError();
+    m->use_graphs = false;
+    return eager();
+  }
+  if (m->graphs.size() >= 32) {
+    cudaGraphExecDestroy(m->graphs.front().exec);
+    m->graphs.erase(m->graphs.begin());
+  }
+  adn_model::GraphEntry ge{};
+  ge.in = d_in; ge.batch = batch; ge.st = st; ge.exec = exec; ge.epoch = ep;
+  for (int o = 0; o < n_out && o < 4; ++o) ge.outs[o] = d_outs[o];
+  m->graphs.push_back(ge);
+  ADN_CUDA_TRY(cudaGraphLaunch(exec, st), m->err);
+  ++m->graph_launches;
+  return ADN_OK;
 }
 
 adn_status adn_run_host(adn_model* m, const void* h_in, void* const* h_outs, int32_t batch) {
@@ -833,6 +910,7 @@ adn_status adn_run_host(adn_model* m, const void* h_in, void* const* h_outs, int
   if (m->impl) {
     if (batch > m->io_cap) {     // staging buffers for families that own their workspace
       ADN_CUDA_TRY(cudaDeviceSynchronize(), m->err);
+      adn_note_free();
       if (m->io_cap) { cudaFree(m->d_in); cudaFree(m->d_out); }
       ADN_CUDA_TRY(cudaMalloc(&m->d_in, (size_t)batch * m->chans * m->io_L * dtype_size(m->in_dtype)), m->err);
       ADN_CUDA_TRY(cudaMalloc(&m->d_out, (size_t)m->n_out * batch * m->chans * m->io_Lout * dtype_size(m->out_dtype)), m->err);
@@ -922,6 +1000,11 @@ adn_status adn_last_kernel_times(adn_model* m, const char** names, float* ms, in
 
 adn_status adn_debug_read(adn_model* m, const char* name, float* h_dst, size_t count, size_t* actual) {
   if (!m || !name) return ADN_ERR_INVALID;
+  if (!strcmp(name, "graph_launches")) {          // runs of this handle that were replayed as a CUDA graph
+    if (actual) *actual = 1;
+    if (h_dst && count) h_dst[0] = (float)m->graph_launches;
+    return ADN_OK;
+  }
   if (m->impl) {
     adn_status r = m->impl->debug_read(name, h_dst, count, actual);
     if (r != ADN_OK) m->err = m->impl->err;
@@ -1064,6 +1147,7 @@ adn_status adn_stft_forward(adn_stft* s, const float* d_x, float* d_spec, int32_
   size_t need = (size_t)batch * Lp;
   if (need > s->xp_cap) {
     cudaDeviceSynchronize();
+    adn_note_free();
     cudaFree(s->d_xp);
     if (cudaMalloc((void**)&s->d_xp, need * 4) != cudaSuccess) {
       set_global_error("adn_stft_forward: out of memory");
@@ -1097,6 +1181,7 @@ adn_status adn_stft_inverse(adn_stft* s, const float* d_spec, float* d_y, int32_
   size_t need = (size_t)batch * (T + 2 * pad) * ld;
   if (need > s->fm_cap) {
     cudaDeviceSynchronize();
+    adn_note_free();
     cudaFree(s->d_fm);
     if (cudaMalloc((void**)&s->d_fm, need * 4) != cudaSuccess) {
       set_global_error("adn_stft_inverse: out of memory");

@@ -30,6 +30,11 @@ inline bool adn_first_use_on_device(unsigned long long& mask) {
   return true;
 }
 
+// Run-time workspaces are raw cudaMalloc blocks; a captured CUDA graph (adn_run, api.cu) holds their addresses.  Every path that
+// frees one calls adn_note_free(); adn_run drops the graphs captured before the epoch changed.
+void adn_note_free();
+unsigned long long adn_alloc_epoch();
+
 __device__ __forceinline__ float adn_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float adn_prelu(float x, float a) { return x >= 0.f ? x : a * x; }
 

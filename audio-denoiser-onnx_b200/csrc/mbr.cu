@@ -468,6 +468,7 @@ class Model : public ModelImpl {
   }
 
   void free_ws() {
+    adn_note_free();
     for (void* p : allocs) cudaFree(p);
     allocs.clear();
     ws_bytes = 0;

@@ -543,6 +543,7 @@ struct Base : public ModelImpl {
   int planned = 0;
 
   void free_ws() {
+    adn_note_free();
     for (void* p : allocs) cudaFree(p);
     allocs.clear();
     ws_bytes = 0;

@@ -546,6 +546,7 @@ class Model : public ModelImpl {
     if (stft) adn_stft_destroy(stft);
   }
   void free_ws() {
+    adn_note_free();
     for (void* p : allocs) cudaFree(p);
     allocs.clear();
     plans.clear();

@@ -780,6 +780,77 @@ def run_reference(args, wl):
     print(json.dumps(line))
 
 
+def run_sweep(args):
+    """BASELINE.json `metric`: RTF and audio-seconds per second per model at batch 1 / 64 / 512 on one B200.  Per (model, batch):
+    device-resident throughput (CUDA events on a non-default stream, so batch 1 runs as a CUDA graph) and the end-to-end figure
+    through adn_run_host with pinned host buffers.  Steps are bounded by time (about 2 s per cell) so the table finishes in minutes."""
+    from adn import _lib, build
+
+    build.build()
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    side = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(side)
+    table = []
+    for name in [m for m in args.sweep_models.split(",") if m]:
+        wl = WORKLOADS[name]()
+        sd = wl.weights()
+        model = wl.build(sd, 0)
+        for B in [int(b) for b in args.sweep_batches.split(",") if b]:
+            n_sets = 2
+            sub = B                                                         # windows per launch: the workspace must fit the GPU
+            while sub > 1 and model.workspace_bytes(sub) > 100 * 2**30:
+                sub //= 2
+            host = wl.inputs(B, n_sets, seed=1234)
+            devs = [x.to(dev) for x in host]
+            cuts = [(a, min(a + sub, B)) for a in range(0, B, sub)]
+            outs = [None] * len(cuts)
+
+            def step(i):
+                for k, (a, b) in enumerate(cuts):
+                    outs[k] = model.run(devs[i % n_sets][a:b], out=outs[k])
+
+            for i in range(3):
+                step(i)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            step(0)
+            torch.cuda.synchronize(dev)
+            est = time.perf_counter() - t0
+            steps = int(max(3, min(200, 2.0 / max(est, 1e-4))))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(side)
+            for i in range(steps):
+                step(i)
+            e1.record(side)
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / steps
+            pins = [x.pin_memory().numpy() for x in host]
+            houts = [tuple(torch.empty((b - a, o.channels, o.length), dtype=torch.float32).pin_memory().numpy() for o in model.outputs) for a, b in cuts]
+
+            def host_step(i):
+                for (a, b), ho in zip(cuts, houts):
+                    model.run_host(pins[i % n_sets][a:b], out=ho if len(ho) > 1 else ho[0])
+
+            for i in range(2):
+                host_step(i)
+            t0 = time.perf_counter()
+            for i in range(steps):
+                host_step(i)
+            e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
+            a = wl.audio_seconds(B)
+            table.append({"model": name, "batch": B, "windows_per_launch": sub, "ms_per_step": round(ms, 4),
+                          "audio_s_per_s": round(a / (ms * 1e-3), 2), "rtf": ms * 1e-3 / a, "e2e_ms_per_step": round(e2e_ms, 4),
+                          "e2e_audio_s_per_s": round(a / (e2e_ms * 1e-3), 2), "steps": steps,
+                          "graph_replays": int(model.debug_read("graph_launches")[0]),
+                          "workspace_gib": round(model.workspace_bytes(sub) / 2**30, 2)})
+            del devs, outs, houts, pins
+            torch.cuda.empty_cache()
+        model.close()
+    print(json.dumps({"metric": "RTF & audio-sec/s per model @ batch 1/64/512", "unit": UNIT, "n_gpus": 1, "data": "synthetic",
+                      "dtype": "f32", "table": table, "lib": _lib.lib().adn_version().decode()}))
+
+
 def run_strong(args, wl, model, B, n_sets, dev, dist, rank, world, barrier, allmax):
     """Strong scaling through the real multi-GPU data path (SURVEY 8e): B windows in total per step, owned by rank 0;
     every step is adn.dist.run_sharded = NCCL grouped send / recv of each rank's exact block -> Model.run -> NCCL gather into
@@ -894,6 +965,11 @@ def main():
                     help="weak (default, the driver's contract): --batch chunks per GPU, every rank's inputs resident in its own HBM; "
                          "strong: --batch chunks in TOTAL, owned by rank 0, scattered / run / gathered through adn.dist.run_sharded "
                          "(NCCL grouped send / recv) inside the timed region")
+    ap.add_argument("--sweep", action="store_true",
+                    help="BASELINE.json's metric table in one JSON line: RTF and audio-s/s per model at batch 1 / 64 / 512 on one GPU "
+                         "(device-resident and end to end through adn_run_host); --sweep-models / --sweep-batches narrow it")
+    ap.add_argument("--sweep-models", default="gtcrn,zipenh,mf2se,mbr,mfgan,mf2ss,dfsmn,ulunas")
+    ap.add_argument("--sweep-batches", default="1,64,512")
     ap.add_argument("--segments", default="", help="NxSs, e.g. 128x8s (BASELINE.json configs[3]): N segments of S seconds, folded on the host "
                                                    "into the model's fixed windows (stride = window, zero tail) -> --batch = N * ceil(S * sr / window)")
     ap.add_argument("--ref-chunks", type=int, default=0, help="CPU chunks per step for --impl reference")
@@ -901,6 +977,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.sweep:
+        run_sweep(args)
+        return
     wl = WORKLOADS[args.model]()
     if args.matmul == "bf16":
         if args.model != "mf2se":
@@ -951,6 +1030,9 @@ def main():
     out = torch.empty(out_shape, dtype=torch.float32, device=dev)
     if n_out > 1:
         out = tuple(torch.empty(out_shape, dtype=torch.float32, device=dev) for _ in range(n_out))
+    # a non-default stream: adn_run replays repeated runs as CUDA graphs there (the legacy default stream cannot be captured)
+    side = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(side)
     stream = torch.cuda.current_stream(dev)
 
     def barrier():

@@ -86,7 +86,10 @@ adn_status adn_io_info(const adn_model* m, adn_tensor_info* in, adn_tensor_info*
 /* Replaces session.run_with_iobinding(binding) for a batch of `batch` independent
  * (1,C,L) chunks resident on the device (…:209-210, 314-317).  d_in is (batch,C,L)
  * contiguous in the input dtype, d_outs[i] (i < n_out of adn_io_info) is (batch,C,L_out).
- * Asynchronous on `stream` (a cudaStream_t passed as void*). */
+ * Asynchronous on `stream` (a cudaStream_t passed as void*).  On a non-default stream the launch sequence of a
+ * (buffers, batch) combination seen before is replayed as one CUDA graph (captured on its second run; environment
+ * ADN_GRAPHS=0 disables this); the legacy default stream always runs the kernels one by one.  Families: gtcrn,
+ * zipenhancer, mel_band_roformer, mossformer2_se, mossformer2_ss, mossformergan_se, dfsmn, ulunas. */
 adn_status adn_run(adn_model* m, const void* d_in, void* const* d_outs, int32_t batch,
                    void* stream);
 
@@ -150,8 +153,7 @@ void adn_stft_destroy(adn_stft* s);
 
 /* ---- stand-alone conditioning / feature / recombine / output operators ------------------------
  * The wrapper-forward steps either side of the ZipEnhancer, MossFormerGAN-SE-16K and MossFormer2-SS-16K
- * backbones (ZipEnhancer's backbone is not built in this library; the mossformergan_se model runs the
- * MossFormerGAN operators internally) and the linear resampler every wrapper shares.  With adn_stft_forward / adn_stft_inverse they form the complete front and back ends
+ * backbones (the zipenhancer and mossformergan_se models run these operators internally) and the linear resampler every wrapper shares.  With adn_stft_forward / adn_stft_inverse they form the complete front and back ends
  * around those backbones.  All pointers are DEVICE pointers, rows are contiguous, `stream` is a
  * cudaStream_t (NULL = default stream); errors go to adn_last_error(NULL). */
 enum { ADN_FAMILY_ZIPENHANCER = 1, ADN_FAMILY_MOSSFORMERGAN = 2, ADN_FAMILY_MOSSFORMER2_SS = 3 };
