@@ -952,10 +952,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=0)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--model", default="mf2se", choices=sorted(WORKLOADS),
-                    help="default mf2se = BASELINE.json configs[2] (MossFormer2-SE-48K, 256 x 1 s windows per GPU): the largest "
-                         "single-GPU configuration that is built (configs[1], ZipEnhancer, is not: its backbone source is absent "
-                         "from the reference)")
+    ap.add_argument("--model", default="zipenh", choices=sorted(WORKLOADS),
+                    help="default zipenh = BASELINE.json configs[1] (ZipEnhancer 16 kHz, 64 x 1 s chunks, fp32, one B200), the "
+                         "configuration the metric is quoted on; mf2se = configs[2] (256 x 1 s @48 kHz per GPU), gtcrn = configs[0]'s "
+                         "model batched, mbr = configs[3]'s model, mfgan / mf2ss = the two halves of configs[4]")
     ap.add_argument("--batch", type=int, default=0, help="chunks per GPU per step (default: per model)")
     ap.add_argument("--impl", default="adn", choices=["adn", "reference"])
     ap.add_argument("--matmul", default="f32", choices=["f32", "bf16"],
@@ -994,7 +994,7 @@ def main():
         _describe = wl.describe
         wl.describe = lambda B: f"{nseg} x {secs} s segments folded into {per_seg} windows each: " + _describe(B)
     if args.steps <= 0:
-        args.steps = 100 if args.model == "gtcrn" else (5 if args.model in ("mf2ss", "mfgan") else 20)
+        args.steps = 100 if args.model == "gtcrn" else (5 if args.model in ("mf2ss", "mfgan") else 10 if args.model == "zipenh" else 20)
     if args.impl == "reference":
         args.steps = min(args.steps, 20)
         run_reference(args, wl)
