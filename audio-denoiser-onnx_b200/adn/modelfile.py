@@ -21,7 +21,19 @@ import numpy as np
 MAGIC = b"ADN1"
 
 
-def save(path, metadata: dict[str, str], tensors: dict[str, np.ndarray]) -> None:
+def metadata_path_for_model(path) -> Path:
+    """`<Model>_Metadata.onnx` beside the model file, whatever the model's own suffix: the sidecar the reference's
+    `load_runtime_metadata` opens and requires to exist (audio_onnx_metadata.py:37-39, :290-297).  The container is
+    recognised by its magic, not by its name."""
+    p = Path(path)
+    return p.with_name(f"{p.stem}_Metadata.onnx")
+
+
+def save(path, metadata: dict[str, str], tensors: dict[str, np.ndarray], sidecar: bool = True) -> None:
+    """Writes the model file and, beside it, the metadata-only sidecar (same container, no tensors) -- the counterpart of the
+    reference's `stamp_export_metadata` (Export_GTCRN.py:780-790)."""
+    if sidecar and tensors:
+        save(metadata_path_for_model(path), metadata, {}, sidecar=False)
     index, chunks, off = [], [], 0
     for name, arr in tensors.items():
         a = np.ascontiguousarray(arr, dtype=np.float32)

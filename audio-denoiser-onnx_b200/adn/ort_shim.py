@@ -173,9 +173,10 @@ class InferenceSession:
     """`onnxruntime.InferenceSession(path, sess_options=, providers=, provider_options=,
     disabled_optimizers=)` (Inference_GTCRN_ONNX.py:213-214,230-237).
 
-    `path` is a `.adn` model file.  A path ending in `_Metadata.onnx` / `_Metadata.adn`
-    resolves to the main model (the reference opens the sidecar only to read
-    `custom_metadata_map`, audio_onnx_metadata.py:290-303); no device work is done for it."""
+    `path` is a `.adn` model file (any file name: the container is recognised by its magic).  A path ending in
+    `_Metadata.<ext>` is the metadata sidecar `adn.modelfile.save` writes beside every model (the reference opens it only to
+    read `custom_metadata_map`, audio_onnx_metadata.py:290-303); if it is absent the main model's header is read instead.
+    No device work is done for a sidecar session."""
 
     def __init__(self, path, sess_options=None, providers=None, provider_options=None,
                  disabled_optimizers=None, device_id: int | None = None, **_ignored):
@@ -183,7 +184,8 @@ class InferenceSession:
         self._metadata_only = False
         if p.stem.endswith("_Metadata"):
             self._metadata_only = True
-            p = p.with_name(p.stem[: -len("_Metadata")] + p.suffix)
+            if not (p.exists() and p.stat().st_size > 8):      # no sidecar written: read the main file's header instead
+                p = p.with_name(p.stem[: -len("_Metadata")] + p.suffix)
         if p.suffix == ".onnx" and not p.exists():
             p = p.with_suffix(".adn")
         if not p.exists():

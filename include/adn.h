@@ -67,12 +67,18 @@ typedef struct {
 } adn_tensor_info;
 
 /* Replaces onnxruntime.InferenceSession(path, ...) (Inference_GTCRN_ONNX.py:213-214,237):
- * builds a model of desc["model_family"] (gtcrn | mel_band_roformer | mossformer2_se | mossformer2_ss |
- * mossformergan_se | dfsmn | ulunas)
+ * builds a model of desc["model_family"] (gtcrn | zipenhancer | mel_band_roformer | mossformer2_se |
+ * mossformer2_ss | mossformergan_se | dfsmn | ulunas)
  * on CUDA device `device_id` from a host blob of `nfloats` fp32 values.  The keys are the reference's
  * metadata keys (audio_onnx_metadata.py:115-205) plus, for mossformer2_se, the optional
  * "matmul_dtype" = F32 (default: 3xTF32 tensor-core GEMMs, fp32-class) | BF16 (the layers' GEMMs on bf16
- * operands -- BASELINE.json configs[2] "bf16 matmuls").  On failure *out is NULL and adn_last_error(NULL) has the reason. */
+ * operands -- BASELINE.json configs[2] "bf16 matmuls").  On failure *out is NULL and adn_last_error(NULL) has the reason.
+ * Window limits: `input_audio_length` is ONE window of the model (the reference's static export length; its in-graph batch
+ * fold is the leading batch dimension here).  mel_band_roformer accepts windows of at most 255 hops (112 455 samples, 2.55 s
+ * at 44.1 kHz: the reference's 1.5 s fold window, Mel_Band_Roformer/Stereo/Export_MelBandRoformer.py:46-50) -- a longer
+ * un-folded static length (Inference_MelBandRoformer_ONNX.py:301-313) is rejected at adn_create and must be folded on the
+ * host (adn.chunker.denoise does); zipenhancer sequences (frames, sub-bands) of more than 256 positions run on the
+ * slower one-thread-per-row attention path; every other family takes any window its STFT geometry allows. */
 adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weights,
                       size_t nfloats, int device_id);
 
