@@ -41,6 +41,82 @@ struct CountExec {                      // dry run of the sequence: how many lau
   void mark(const char*, const char*, const float*, long long) {}
 };
 
+// nn.GRU with a hidden state wide enough to share (the cTFA time-attention GRUs: hidden 2C = 24 ... 64 over the 63 frames, ONE
+// sequence per window): one CTA = one (sequence, group, direction), thread j = hidden unit j, both weight matrices transposed in
+// shared memory ([input][3H]: thread j reads consecutive words), h double-buffered in shared memory, two barriers per step.
+// Summation order = the GruSeq functor's (bias first, inputs in order), so the two paths give identical bits.
+__global__ void gru_coop_kernel(GruSeq f) {
+  extern __shared__ float sh[];
+  const int H = f.H, I = f.I, H3 = 3 * f.H;
+  float* wiT = sh;                  // [I][3H]
+  float* whT = wiT + I * H3;        // [H][3H]
+  float* hs = whT + H * H3;         // [2][H]
+  float* xv = hs + 2 * H;           // [I]
+  const long long idx = blockIdx.x;
+  const int d = (int)(idx % f.dirs);
+  long long r = idx / f.dirs;
+  const int g = (int)(r % f.ngroups);
+  const long long n = r / f.ngroups;
+  const long long gd = (long long)g * f.dirs + d;
+  const float* wi = f.w_ih + gd * H3 * I;
+  const float* wh = f.w_hh + gd * H3 * H;
+  for (int e = threadIdx.x; e < H3 * I; e += blockDim.x) wiT[(e % I) * H3 + e / I] = __ldg(wi + e);
+  for (int e = threadIdx.x; e < H3 * H; e += blockDim.x) whT[(e % H) * H3 + e / H] = __ldg(wh + e);
+  const int j = threadIdx.x;
+  float bir = 0.f, biz = 0.f, bin = 0.f, bhr = 0.f, bhz = 0.f, bhn = 0.f;
+  if (j < H) {
+    const float* bi = f.b_ih + gd * H3;
+    const float* bh = f.b_hh + gd * H3;
+    bir = bi[j]; biz = bi[H + j]; bin = bi[2 * H + j];
+    bhr = bh[j]; bhz = bh[H + j]; bhn = bh[2 * H + j];
+    hs[j] = 0.f;
+  }
+  const float* xs = f.x + (n / f.n2) * f.x_sA + (n % f.n2) * f.x_sB + (long long)g * f.x_grp;
+  float* os = f.out + (n / f.n2) * f.o_sA + (n % f.n2) * f.o_sB + (long long)g * f.o_grp + (long long)d * H;
+  int cur = 0;
+  for (int k = 0; k < f.steps; ++k) {
+    const int s = d ? f.steps - 1 - k : k;
+    if (j < I) xv[j] = (f.x_limit > 0 && s * I + j >= f.x_limit) ? 0.f : xs[(long long)s * f.x_step + j];
+    __syncthreads();
+    if (j < H) {
+      float ir = bir, iz = biz, in_ = bin;
+      for (int q = 0; q < I; ++q) {
+        const float v = xv[q];
+        ir += wiT[q * H3 + j] * v; iz += wiT[q * H3 + H + j] * v; in_ += wiT[q * H3 + 2 * H + j] * v;
+      }
+      float hr = bhr, hz = bhz, hh = bhn;
+      const float* hc = hs + cur * H;
+      for (int q = 0; q < H; ++q) {
+        const float v = hc[q];
+        hr += whT[q * H3 + j] * v; hz += whT[q * H3 + H + j] * v; hh += whT[q * H3 + 2 * H + j] * v;
+      }
+      const float rg = gan::sigmoidf_(ir + hr), zg = gan::sigmoidf_(iz + hz);
+      const float ng = tanhf(in_ + rg * hh);
+      const float hn = (1.f - zg) * ng + zg * hc[j];
+      hs[(cur ^ 1) * H + j] = hn;
+      os[(long long)s * f.o_step + j] = hn;
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+}
+
+// the functor executor + the cooperative GRU for wide hidden states
+struct UlExec : gan::CudaExec {
+  using gan::CudaExec::run;
+  void run(long long n, const GruSeq& f) {
+    if (f.H < 16 || n <= 0) { gan::CudaExec::run<GruSeq>(n, f); return; }
+    const int threads = ((f.H > f.I ? f.H : f.I) + 31) / 32 * 32;
+    const size_t smem = ((size_t)(f.I + f.H) * 3 * f.H + 2 * f.H + f.I) * sizeof(float);
+    static unsigned long long configured = 0;
+    if (adn_first_use_on_device(configured))
+      cudaFuncSetAttribute(gru_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)(GRU_HMAX + GRU_HMAX) * 3 * GRU_HMAX + 3 * GRU_HMAX) * sizeof(float)));
+    gru_coop_kernel<<<(unsigned)n, threads, smem, st>>>(f);
+    ++launches;
+    if (tick) tick(tick_ctx, "ulunas_gru");
+  }
+};
+
 class Model : public ModelImpl {
  public:
   int device = 0, sms = 148;
@@ -167,7 +243,7 @@ class Model : public ModelImpl {
   adn_status run(const void* d_in, void* d_out, int B, cudaStream_t st) override {
     if (!ensure(B)) return ADN_ERR_CUDA;
     last_batch = B;
-    gan::CudaExec ex;
+    UlExec ex;
     ex.st = st; ex.tick = tick; ex.tick_ctx = tick_ctx;
     ex.capture = stop_after != 0; ex.dumps = &dumps;
     if (ex.capture) dumps.clear();
