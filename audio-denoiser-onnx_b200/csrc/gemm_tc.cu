@@ -66,6 +66,11 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(smem_u32(src)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -120,13 +125,15 @@ __device__ __forceinline__ int16_t to_i16(float y, int mode) {
   return (int16_t)(int)fminf(fmaxf(y * 32767.0f, -32768.0f), 32767.0f);
 }
 
-template <int BN, bool BF = false>
+template <int BN, bool BF = false, bool AF = false>
 struct Smem {
   static constexpr uint32_t W_TILE_BYTES = BN * BK * 4;           // BN rows of 128 bytes (32 tf32 or 64 bf16)
   static constexpr int PLANES = BF ? 1 : 2;
   static constexpr uint32_t STAGE_BYTES = PLANES * (A_TILE_BYTES + W_TILE_BYTES);
   static constexpr int STAGES = BF ? 4 : ((BN <= 64) ? 4 : (BN <= 128) ? 3 : 2);
-  static constexpr uint32_t EPI_STAGE_BYTES = NEPI * 8 * 36 * 4;    // per-warp 8x36 transpose tiles of the epilogue
+  // epilogue staging behind the pipeline stages (1024-byte aligned): per-warp 8x36 transpose tiles, or, in fp32-A mode, one
+  // 16-row x 128-byte swizzled tile per warp that a TMA store drains
+  static constexpr uint32_t EPI_STAGE_BYTES = AF ? NEPI * 2048 : 19456 /* >= NEPI * 8 * 36 * 4, multiple of 1024 */;
   static constexpr uint32_t TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 };
 
@@ -140,12 +147,12 @@ __global__ void __launch_bounds__(AF ? NTHREADS_AF : NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
-               const TcArgs g) {
-  using S = Smem<BN, BF>;
+               const __grid_constant__ CUtensorMap map_c, const TcArgs g) {
+  using S = Smem<BN, BF, AF>;
   constexpr int BKE = BF ? 2 * BK : BK;          // K elements per 128-byte row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + S::STAGES * S::STAGE_BYTES);
+  uint64_t* bars = (uint64_t*)(smem + S::STAGES * S::STAGE_BYTES + S::EPI_STAGE_BYTES);
   uint64_t* full = bars;                    // [STAGES]
   uint64_t* empty = bars + S::STAGES;       // [STAGES]
   uint64_t* tfull = bars + 2 * S::STAGES;   // [2]
@@ -154,7 +161,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   uint32_t* tmem_slot = (uint32_t*)(conv + S::STAGES);
   constexpr int NE = NEPI;                  // epilogue warps 2 .. 2+NE-1; converter warps behind them
   constexpr int NCONV = AF ? NCONV_AF : 0;
-  float* stage = (float*)(smem + S::STAGES * S::STAGE_BYTES + 256);
+  float* stage = (float*)(smem + S::STAGES * S::STAGE_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles_n = (g.N + BN - 1) / BN;
@@ -167,6 +174,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     prefetch_tmap(&map_w_hi);
     prefetch_tmap(&map_w_lo);
     if (g.k_split > 0) { prefetch_tmap(&map_w2_hi); prefetch_tmap(&map_w2_lo); }
+    if (AF) prefetch_tmap(&map_c);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S::STAGES; ++i) {
@@ -204,7 +212,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * S::STAGE_BYTES;
-          mbar_expect_tx(&full[stage], (uint32_t)(AF ? 1 : S::PLANES) * (uint32_t)(g.bt * g.bb * BK * 4) + (uint32_t)S::PLANES * S::W_TILE_BYTES);
+          const bool skip_w = AF && (g.probe & 4) && !(tile == (int)blockIdx.x && kb < S::STAGES);
+          mbar_expect_tx(&full[stage], (uint32_t)(AF ? 1 : S::PLANES) * (uint32_t)(g.bt * g.bb * BK * 4) + (skip_w ? 0u : (uint32_t)S::PLANES * S::W_TILE_BYTES));
           int wb = g.w_batched ? b0 : 0;            // per-batch weights (mask-estimator bands, attention operands)
           int wk = kb * BKE;
           if (g.w_group > 1) { wk += (b0 % g.w_group) * g.w_kstep; wb = b0 / g.w_group; }   // FLASH group of a window
@@ -218,8 +227,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           } else {
             tma_load_3d(st, &map_a_hi, &full[stage], ak, at, b0);
             if (!AF) tma_load_3d(st + A_TILE_BYTES, &map_a_lo, &full[stage], ak, at, b0);
+            if (!skip_w) {
             tma_load_3d(st + 2 * A_TILE_BYTES, second ? &map_w2_hi : &map_w_hi, &full[stage], wk, nt * BN, wb);
             tma_load_3d(st + 2 * A_TILE_BYTES + S::W_TILE_BYTES, second ? &map_w2_lo : &map_w_lo, &full[stage], wk, nt * BN, wb);
+            }
           }
           if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -279,7 +290,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         float4* hi = reinterpret_cast<float4*>(smem + stage * S::STAGE_BYTES);
         float4* lo = hi + A_TILE_BYTES / 16;
 #pragma unroll 4
-        for (int i = cw * 32 + lane; i < (int)(A_TILE_BYTES / 16); i += NCONV * 32) {
+        for (int i = cw * 32 + lane; i < ((g.probe & 1) ? 0 : (int)(A_TILE_BYTES / 16)); i += NCONV * 32) {
           const float4 v = hi[i];
           float4 h, l;
           h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
@@ -321,41 +332,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         tmem_ld_wait();
         const int n0 = nt * BN + c0;
         if (AF) {
-          // fp32-only outputs (no operand planes to write): the TMEM load already gives lane = row with 32 consecutive
-          // columns in registers, so every lane streams its own row as 16-byte stores -- the halves of a 32-byte sector
-          // come from back-to-back stores of one lane and merge in L2 -- with a fraction of the instructions of the
-          // transposing path below (which exists to write three coalesced planes per element).
-          if (!row_ok) continue;
+          // fp32-only outputs through a TMA store.  The TMEM load gives lane = row with 32 consecutive columns in registers;
+          // bias / activation / residuals are applied there, the 32 x 32 block goes -- 16 rows at a time -- into this warp's
+          // swizzled 16 x 128-byte staging tile (conflict-free 16-byte writes), and one lane issues cp.async.bulk.tensor
+          // (shared -> global): full 128-byte row segments leave the SM asynchronously, rows >= TM and columns >= N are
+          // clipped by the tensor map, and the LSU sees no global store at all.  (Measured with ADN_TC_PROBE=2: per-lane
+          // st.global epilogues -- row-streaming or transposed -- were 70 % of the time of every small-K GEMM.)
+          const bool dead = (g.probe & 2) != 0;
           const long long o = ((long long)b * g.TM + t) * g.ldc + n0;
-          float4 res4[8], org4[8];
+          float x[32];
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const bool ok = c0 + 4 * j4 < BN && n0 + 4 * j4 < g.N;
-            res4[j4] = (ok && g.resid) ? *reinterpret_cast<const float4*>(g.resid + o + 4 * j4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            org4[j4] = (ok && g.resid2) ? *reinterpret_cast<const float4*>(g.resid2 + o + 4 * j4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+          if (row_ok && !dead) {
+            float4 res4[8];
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            if (!(c0 + 4 * j4 < BN && n0 + 4 * j4 < g.N)) continue;
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (g.bias) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j4);
-            float x[4] = {__uint_as_float(v[4 * j4]) + b4.x, __uint_as_float(v[4 * j4 + 1]) + b4.y,
-                          __uint_as_float(v[4 * j4 + 2]) + b4.z, __uint_as_float(v[4 * j4 + 3]) + b4.w};
-            if (g.act == ACT_SWOOSH_L || g.act == ACT_SWOOSH_R) {
-              const float off = g.act == ACT_SWOOSH_L ? 4.0f : 1.0f;
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const bool ok = c0 + 4 * j4 < BN && n0 + 4 * j4 < g.N;
+              res4[j4] = (ok && g.resid) ? *reinterpret_cast<const float4*>(g.resid + o + 4 * j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float y = x[j] - off;
-                x[j] = fmaxf(y, 0.f) + __logf(1.0f + __expf(-fabsf(y))) - 0.08f * x[j];
+            for (int j4 = 0; j4 < 8; ++j4) {
+              if (!(c0 + 4 * j4 < BN && n0 + 4 * j4 < g.N)) continue;
+              if (g.bias) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j4);
+                x[4 * j4] += b4.x; x[4 * j4 + 1] += b4.y; x[4 * j4 + 2] += b4.z; x[4 * j4 + 3] += b4.w;
+              }
+              if (g.act == ACT_SWOOSH_L || g.act == ACT_SWOOSH_R) {
+                const float off = g.act == ACT_SWOOSH_L ? 4.0f : 1.0f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float y = x[4 * j4 + j] - off;
+                  x[4 * j4 + j] = fmaxf(y, 0.f) + __logf(1.0f + __expf(-fabsf(y))) - 0.08f * x[4 * j4 + j];
+                }
+              }
+              x[4 * j4] += res4[j4].x; x[4 * j4 + 1] += res4[j4].y; x[4 * j4 + 2] += res4[j4].z; x[4 * j4 + 3] += res4[j4].w;
+              if (g.resid2) {
+                const float4 o4 = *reinterpret_cast<const float4*>(g.resid2 + o + 4 * j4);
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(g.colscale + n0) + j4);
+                x[4 * j4] = o4.x + (x[4 * j4] - o4.x) * s4.x; x[4 * j4 + 1] = o4.y + (x[4 * j4 + 1] - o4.y) * s4.y;
+                x[4 * j4 + 2] = o4.z + (x[4 * j4 + 2] - o4.z) * s4.z; x[4 * j4 + 3] = o4.w + (x[4 * j4 + 3] - o4.w) * s4.w;
               }
             }
-            x[0] += res4[j4].x; x[1] += res4[j4].y; x[2] += res4[j4].z; x[3] += res4[j4].w;
-            if (g.resid2) {
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(g.colscale + n0) + j4);
-              x[0] = org4[j4].x + (x[0] - org4[j4].x) * s4.x; x[1] = org4[j4].y + (x[1] - org4[j4].y) * s4.y;
-              x[2] = org4[j4].z + (x[2] - org4[j4].z) * s4.z; x[3] = org4[j4].w + (x[3] - org4[j4].w) * s4.w;
+          }
+          if (n0 >= g.N || dead) continue;
+          uint8_t* stg = reinterpret_cast<uint8_t*>(stage) + (warp - 2) * 2048;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            if ((lane >> 4) == half) {
+              const int rr = lane & 15;
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4)
+                *reinterpret_cast<float4*>(stg + rr * 128 + ((j4 ^ (rr & 7)) << 4)) = make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
             }
-            *reinterpret_cast<float4*>(g.C + o + 4 * j4) = make_float4(x[0], x[1], x[2], x[3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&map_c, stg, n0, tile_t + q * 32 + half * 16, tile_b + g.b_off);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the staging tile may be overwritten
+            }
+            __syncwarp();
           }
           continue;
         }
@@ -555,6 +591,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[ab]);
     }
+    if (AF && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this warp's bulk stores have completed
   }
 
   tc_fence_before();
@@ -636,9 +673,27 @@ bool make_tile_map(CUtensorMap* map, const float* base, int cols, int rows, long
   return true;
 }
 
+bool make_store_map(CUtensorMap* map, float* base, int cols, int rows, long long row_stride, int batches, long long batch_stride,
+                    std::string& err) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { err = "cuTensorMapEncodeTiled entry point not available"; return false; }
+  if ((row_stride * 4) % 16 || (batch_stride * 4) % 16 || ((uintptr_t)base) % 16) {
+    err = "TMA store map needs a 16-byte aligned base and strides";
+    return false;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batches};
+  cuuint64_t strides[2] = {(cuuint64_t)row_stride * 4, (cuuint64_t)batch_stride * 4};
+  cuuint32_t box[3] = {32, 16, 1};                   // the per-warp staging tile of the fp32-A epilogue
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(C) failed: " + std::to_string((int)r); return false; }
+  return true;
+}
+
 template <int BN, int EPI, bool BF, bool AF = false>
 static cudaError_t launch_t(const TcPlan& p, const TcArgs& a, int sms, cudaStream_t st) {
-  using S = Smem<BN, BF>;
+  using S = Smem<BN, BF, AF>;
   static unsigned long long configured = 0;      // per device
   auto kern = gemm_tc_kernel<BN, EPI, BF, AF>;
   if (adn_first_use_on_device(configured)) {
@@ -647,7 +702,7 @@ static cudaError_t launch_t(const TcPlan& p, const TcArgs& a, int sms, cudaStrea
   }
   const int n_tiles = a.m_tiles * ((a.N + BN - 1) / BN);
   const int grid = n_tiles < sms ? n_tiles : sms;
-  kern<<<grid, AF ? NTHREADS_AF : NTHREADS, S::TOTAL, st>>>(p.map_a_hi, p.map_a_lo, p.map_w_hi, p.map_w_lo, p.map_w2_hi, p.map_w2_lo, a);
+  kern<<<grid, AF ? NTHREADS_AF : NTHREADS, S::TOTAL, st>>>(p.map_a_hi, p.map_a_lo, p.map_w_hi, p.map_w_lo, p.map_w2_hi, p.map_w2_lo, AF ? p.map_c : p.map_a_hi, a);
   return cudaGetLastError();
 }
 

@@ -45,6 +45,7 @@ struct TcArgs {
   // EPI_LIN: after the residual, v = resid2[m*ldc+n] + (v - resid2[m*ldc+n]) * colscale[n]   (Zipformer2 BypassModule)
   const float* resid2;
   const float* colscale;
+  int probe;             // diagnostics (ADN_TC_PROBE): 1 = converters do not convert, 2 = epilogue does not load / store, 4 = W loaded once per CTA
   int i16_mode;          // EPI_ISTFT int16 output: 0 = x*32767, clamp, truncate (GTCRN, Export_GTCRN.py:680-693)
                          //   1 = clamp(x,-1,32767/32768)*32768, truncate (MossFormer2_SE_48K/Export_MossFormer_SE.py:499-504)
 };
@@ -55,6 +56,7 @@ enum { ACT_NONE = 0, ACT_GELU = 1, ACT_TANH = 2, ACT_SILU = 3, ACT_RELU = 4, ACT
 struct TcPlan {
   CUtensorMap map_a_hi, map_a_lo, map_w_hi, map_w_lo;
   CUtensorMap map_w2_hi, map_w2_lo;   // only read when args.k_split > 0
+  CUtensorMap map_c;                  // a_f32 only: the fp32 output, written by TMA stores (make_store_map)
   int bn = 0;            // N tile: 64 | 128 | 176 | 256
   bool a_f32 = false;    // map_a_hi is over fp32 activations; the kernel splits them into tf32 hi / lo tiles itself (EPI_LIN only)
   bool bf16 = false;     // operands are single bf16 planes (maps built with bf16 = true); EPI_LIN only, bn 128 | 256
@@ -71,6 +73,11 @@ bool make_weight_map(CUtensorMap* map, const float* base, int k_pad, int n_pad, 
 // box_rows x box_cols; out-of-range rows / columns (negative start coordinates included) read as zeros.
 bool make_tile_map(CUtensorMap* map, const float* base, int cols, int rows, long long row_stride, int batches,
                    long long batch_stride, int box_cols, int box_rows, std::string& err);
+
+// fp32 output of an a_f32 plan: element (b, r, n) at base[b*batch_stride + r*row_stride + n]; rows >= `rows` and columns >= `cols`
+// are never written.
+bool make_store_map(CUtensorMap* map, float* base, int cols, int rows, long long row_stride, int batches, long long batch_stride,
+                    std::string& err);
 
 cudaError_t launch(const TcPlan& p, const TcArgs& a, int epi, int sms, cudaStream_t st);
 

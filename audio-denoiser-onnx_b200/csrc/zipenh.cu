@@ -455,7 +455,8 @@ struct CudaExec {
   bool build(PlanEntry& e, const LinOp& g) {
     auto it = wplanes->find(g.W.w);
     if (it == wplanes->end()) { *err = "zipenhancer: LinOp weight without operand planes"; return false; }
-    const int bn = g.N <= 64 ? 64 : g.N <= 128 ? 128 : (g.N <= 176 || g.N > 256) ? 176 : 256;
+    // (no 176-wide tile here: the TMA-store epilogue writes 32-column boxes, so N tiles must be multiples of 32 columns)
+    const int bn = g.N <= 64 ? 64 : g.N <= 128 ? 128 : 256;
     const int bt = g.rows >= 128 ? 128 : g.rows;
     e.plan = tc::TcPlan{};
     e.plan.bn = bn;
@@ -466,6 +467,7 @@ struct CudaExec {
         !tc::make_weight_map(&e.plan.map_w_hi, it->second.hi, g.W.k_pad, g.W.n_pad, bn, *err) ||
         !tc::make_weight_map(&e.plan.map_w_lo, it->second.lo, g.W.k_pad, g.W.n_pad, bn, *err))
       return false;
+    if (!tc::make_store_map(&e.plan.map_c, g.Cf, g.N, g.rows, g.ldc, g.chunks, (long long)g.rows * g.ldc, *err)) return false;
     e.plan.map_a_lo = e.plan.map_a_hi;
     e.plan.map_w2_hi = e.plan.map_w_hi;
     e.plan.map_w2_lo = e.plan.map_w_lo;
@@ -481,6 +483,7 @@ struct CudaExec {
     }
     a.C = g.Cf; a.ldc = g.ldc;
     a.bias = g.W.b; a.resid = g.resid; a.resid2 = g.resid2; a.colscale = g.colscale; a.act = g.act;
+    { const char* pr = getenv("ADN_TC_PROBE"); a.probe = pr ? atoi(pr) : 0; }
     e.key = g;
     e.valid = true;
     return true;
