@@ -30,7 +30,7 @@ constexpr int BK = 32;                 // 32 fp32 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 8;              // tf32: 32 bytes of K per instruction
 constexpr int NEPI = 16;                // epilogue warps: four per TMEM lane quarter (the epilogue, not the tensor pipe, limits
                                         // small-K and bf16 GEMMs: 8 warps could not issue fast enough)
-constexpr int NCONV_AF = 2;             // fp32-A mode: converter warps behind the epilogue warps
+constexpr int NCONV_AF = 2;             // fp32-A mode: 2 + NEPI + NCONV_AF warps in all; the epilogue needs fewer (TMA stores), the rest convert
 constexpr int NTHREADS = 64 + 32 * NEPI; // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 constexpr int NTHREADS_AF = NTHREADS + 32 * NCONV_AF;
 constexpr uint32_t A_TILE_BYTES = BM * BK * 4;   // 16 KiB
@@ -138,7 +138,7 @@ struct Smem {
 };
 
 // AF (fp32 A operand, ZipEnhancer): the A tensor map is over the fp32 activations themselves.  TMA lands the fp32 tile in the
-// hi slot of the stage; two converter warps (behind the sixteen epilogue warps; 640 threads keep the 96-register budget) split every element in place into
+// hi slot of the stage; the converter warps (6 or 10 of the 20 warps; 640 threads keep the 96-register budget) split every element in place into
 // hi = x & 0xFFFFE000 (kept where it is) and lo = x - hi (lo slot) -- the 128-byte swizzle is a permutation of 16-byte chunks,
 // so an element-wise pass needs no knowledge of it -- then fence.proxy.async and hand the stage to the MMA warp.  Activations
 // live in HBM once, as fp32: half the A bytes, and no producer writes operand planes.
@@ -159,8 +159,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   uint64_t* tempty = tfull + 2;             // [2]
   uint64_t* conv = tempty + 2;              // [STAGES] (AF only)
   uint32_t* tmem_slot = (uint32_t*)(conv + S::STAGES);
-  constexpr int NE = NEPI;                  // epilogue warps 2 .. 2+NE-1; converter warps behind them
-  constexpr int NCONV = AF ? NCONV_AF : 0;
+  // epilogue warps 2 .. 2+NE-1, converter warps behind them.  fp32-A mode: a 64-wide tile has only 2 column chunks x 4 lane
+  // quarters = 8 epilogue tasks, so 10 warps convert operands there (what bounds the deep-K implicit-GEMM convolutions: 19.7 ->
+  // 16.1 ms per step); wider tiles keep all 16 epilogue warps (12 measured slower: ff_in 8.2 -> 10.0 ms) and 2 converters.
+  constexpr int NE = AF ? (BN <= 64 ? 8 : NEPI) : NEPI;
+  constexpr int NCONV = AF ? NEPI + NCONV_AF - NE : 0;
   float* stage = (float*)(smem + S::STAGES * S::STAGE_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
