@@ -44,7 +44,7 @@ ZIP_OP_NAME(Head, "zip_head");
 // ------------------------------------------------------------------------------------------------ attention weights
 // One CTA = one (sequence, head): q | p rows, k^T and the head's relative-position table staged in shared memory; one warp
 // = four query rows at a time, lanes over the keys; softmax in registers; rows written coalesced.
-template <int JJ>
+template <int JJ, int NR>
 __global__ void __launch_bounds__(256) attn_w_kernel(const float* __restrict__ ap, SeqMap sm, const float* __restrict__ pos,
                                                     float* __restrict__ aw) {
   extern __shared__ float sh[];
@@ -70,10 +70,10 @@ __global__ void __launch_bounds__(256) attn_w_kernel(const float* __restrict__ a
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i0 = warp * 4; i0 < S; i0 += 32) {
-    float q[4][16];
+  for (int i0 = warp * NR; i0 < S; i0 += 8 * NR) {
+    float q[NR][16];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < NR; ++r) {
       const int ii = min(i0 + r, S - 1);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) attn_w_kernel(const float* __restrict__ a
         q[r][4 * e] = v.x; q[r][4 * e + 1] = v.y; q[r][4 * e + 2] = v.z; q[r][4 * e + 3] = v.w;
       }
     }
-    float sc[4][JJ];
+    float sc[NR][JJ];
 #pragma unroll
     for (int jj = 0; jj < JJ; ++jj) {
       const int j = lane + 32 * jj;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) attn_w_kernel(const float* __restrict__ a
 #pragma unroll
         for (int d = 0; d < QD; ++d) k[d] = kT[d * SP + j];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < NR; ++r) {
           const int ii = min(i0 + r, S - 1);
           float a = 0.f;
 #pragma unroll
@@ -102,11 +102,11 @@ __global__ void __launch_bounds__(256) attn_w_kernel(const float* __restrict__ a
         }
       } else {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) sc[r][jj] = -INFINITY;
+        for (int r = 0; r < NR; ++r) sc[r][jj] = -INFINITY;
       }
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < NR; ++r) {
       float mx = sc[r][0];
 #pragma unroll
       for (int jj = 1; jj < JJ; ++jj) mx = fmaxf(mx, sc[r][jj]);
@@ -131,8 +131,8 @@ __global__ void __launch_bounds__(256) attn_w_kernel(const float* __restrict__ a
 
 // ------------------------------------------------------------------------------------------------ attention value products
 // 48 partial sums per lane -> lane pair (2p, 2p+1) holds the complete sums base .. base+2 in v[0..2]
-template <int MASK, int N>
-__device__ __forceinline__ void fold_step(float (&v)[48], int lane) {
+template <int MASK, int N, int SZ>
+__device__ __forceinline__ void fold_step(float (&v)[SZ], int lane) {
   const bool up = lane & MASK;
 #pragma unroll
   for (int k = 0; k < N / 2; ++k) {
@@ -141,14 +141,26 @@ __device__ __forceinline__ void fold_step(float (&v)[48], int lane) {
     v[k] = keep + __shfl_xor_sync(0xffffffffu, send, MASK);
   }
 }
+// SZ = 48: lane pair (2p, 2p+1) ends with the complete sums base .. base+2 in v[0..2]; SZ = 24: lane quad (4p .. 4p+3) does
 __device__ __forceinline__ int fold48(float (&v)[48], int lane) {
-  fold_step<16, 48>(v, lane);
-  fold_step<8, 24>(v, lane);
-  fold_step<4, 12>(v, lane);
-  fold_step<2, 6>(v, lane);
+  fold_step<16, 48, 48>(v, lane);
+  fold_step<8, 24, 48>(v, lane);
+  fold_step<4, 12, 48>(v, lane);
+  fold_step<2, 6, 48>(v, lane);
 #pragma unroll
   for (int k = 0; k < 3; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], 1);
   return ((lane & 16) ? 24 : 0) + ((lane & 8) ? 12 : 0) + ((lane & 4) ? 6 : 0) + ((lane & 2) ? 3 : 0);
+}
+__device__ __forceinline__ int fold24(float (&v)[24], int lane) {
+  fold_step<16, 24, 24>(v, lane);
+  fold_step<8, 12, 24>(v, lane);
+  fold_step<4, 6, 24>(v, lane);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    v[k] += __shfl_xor_sync(0xffffffffu, v[k], 2);
+    v[k] += __shfl_xor_sync(0xffffffffu, v[k], 1);
+  }
+  return ((lane & 16) ? 12 : 0) + ((lane & 8) ? 6 : 0) + ((lane & 4) ? 3 : 0);
 }
 
 constexpr int VST = 52;            // value-row stride in shared memory: conflict-free 128-bit loads at lane stride 52 floats
@@ -176,13 +188,15 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ntask = NL ? S : HEADS * ((S + 3) / 4);
+  constexpr int NRS = 4;                         // SelfAttention rows per task (2 rows / 24 accumulators raised occupancy but measured slower: 13.4 -> 14.8 ms)
+  constexpr int NACC = NL ? 48 : NRS * 12;
+  const int ntask = NL ? S : HEADS * ((S + NRS - 1) / NRS);
   for (int task = warp; task < ntask; task += 8) {
     const int h = NL ? 0 : task % HEADS;
-    const int i0 = NL ? task : (task / HEADS) * 4;
-    float acc[48];
+    const int i0 = NL ? task : (task / HEADS) * NRS;
+    float acc[NACC];
 #pragma unroll
-    for (int k = 0; k < 48; ++k) acc[k] = 0.f;
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
     const float* arow = aw + ((n * HEADS + h) * S) * (long long)S;
 #pragma unroll
     for (int jj = 0; jj < JJ; ++jj) {
@@ -203,7 +217,7 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict
             v[4 * e] = t.x; v[4 * e + 1] = t.y; v[4 * e + 2] = t.z; v[4 * e + 3] = t.w;
           }
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
+          for (int r = 0; r < NRS; ++r) {
             const float a = __ldg(arow + (long long)min(i0 + r, S - 1) * S + j);
 #pragma unroll
             for (int c = 0; c < 12; ++c) acc[r * 12 + c] += a * v[c];
@@ -211,8 +225,11 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict
         }
       }
     }
-    const int base = fold48(acc, lane);
-    if (!(lane & 1)) {
+    int base;
+    bool writer;
+    if constexpr (NACC == 48) { base = fold48(acc, lane); writer = !(lane & 1); }
+    else { base = fold24(acc, lane); writer = !(lane & 3); }
+    if (writer) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const int idx = base + k;
@@ -396,10 +413,18 @@ struct CudaExec {
     const long long nseq = n / ((long long)HEADS * S);
     const size_t smem = ((size_t)QD * ((S + 31) & ~31) + 16 * S + (size_t)PD * 2 * S) * sizeof(float);
     const unsigned grid = (unsigned)(nseq * HEADS);
-    if (jj == 2) attn_w_kernel<2><<<grid, 256, smem, st>>>(f.ap, f.sm, f.pos, f.aw);
-    else if (jj == 4) attn_w_kernel<4><<<grid, 256, smem, st>>>(f.ap, f.sm, f.pos, f.aw);
-    else if (jj == 6) attn_w_kernel<6><<<grid, 256, smem, st>>>(f.ap, f.sm, f.pos, f.aw);
-    else attn_w_kernel<8><<<grid, 256, smem, st>>>(f.ap, f.sm, f.pos, f.aw);
+    static const int nr = getenv("ADN_ZIP_AW_ROWS") ? atoi(getenv("ADN_ZIP_AW_ROWS")) : 2;   // 2 rows per pass: 64-80 registers, 3-4 CTAs per SM (9.8 -> 7.7 ms per step vs 4 rows)
+    if (nr == 2) {
+      if (jj == 2) attn_w_kernel<2, 2><<<grid, 256, smem, st>>>(f.ap, f.sm, f.pos, f.aw);
+      else if (jj == 4) attn_w_kernel<4, 2><<<grid, 256, smem, st>>>(f.ap, f.sm, f.pos, f.aw);
+      else if (jj == 6) attn_w_kernel<6, 2><<<grid, 256, smem, st>>>(f.ap, f.sm, f.pos, f.aw);
+      else attn_w_kernel<8, 2><<<grid, 256, smem, st>>>(f.ap, f.sm, f.pos, f.aw);
+    } else {
+      if (jj == 2) attn_w_kernel<2, 4><<<grid, 256, smem, st>>>(f.ap, f.sm, f.pos, f.aw);
+      else if (jj == 4) attn_w_kernel<4, 4><<<grid, 256, smem, st>>>(f.ap, f.sm, f.pos, f.aw);
+      else if (jj == 6) attn_w_kernel<6, 4><<<grid, 256, smem, st>>>(f.ap, f.sm, f.pos, f.aw);
+      else attn_w_kernel<8, 4><<<grid, 256, smem, st>>>(f.ap, f.sm, f.pos, f.aw);
+    }
     done("zip_attn_w");
   }
   template <bool NL>
