@@ -118,11 +118,13 @@ __global__ void __launch_bounds__(256) attn_w_kernel(const float* __restrict__ a
       sum = warp_sum(sum);
       const float inv = 1.0f / sum;
       if (i0 + r < S) {
-        float* row = aw + ((n * HEADS + h) * S + i0 + r) * (long long)S;
+        const int ld = aw_ld(S);
+        float* row = aw + ((n * HEADS + h) * S + i0 + r) * (long long)ld;
 #pragma unroll
         for (int jj = 0; jj < JJ; ++jj) {
           const int j = lane + 32 * jj;
           if (j < S) row[j] = sc[r][jj] * inv;
+          else if (j < ld) row[j] = 0.f;
         }
       }
     }
@@ -197,13 +199,14 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict
     float acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
-    const float* arow = aw + ((n * HEADS + h) * S) * (long long)S;
+    const int ld = aw_ld(S);
+    const float* arow = aw + ((n * HEADS + h) * S) * (long long)ld;
 #pragma unroll
     for (int jj = 0; jj < JJ; ++jj) {
       const int j = lane + 32 * jj;
       if (j < S) {
         if (NL) {
-          const float a = __ldg(arow + (long long)i0 * S + j);
+          const float a = __ldg(arow + (long long)i0 * ld + j);
 #pragma unroll
           for (int e = 0; e < 12; ++e) {
             const float4 v = *reinterpret_cast<const float4*>(sh + j * VST + 4 * e);
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict
           }
 #pragma unroll
           for (int r = 0; r < NRS; ++r) {
-            const float a = __ldg(arow + (long long)min(i0 + r, S - 1) * S + j);
+            const float a = __ldg(arow + (long long)min(i0 + r, S - 1) * ld + j);
 #pragma unroll
             for (int c = 0; c < 12; ++c) acc[r * 12 + c] += a * v[c];
           }
@@ -244,6 +247,109 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict
         }
       }
     }
+  }
+}
+
+// Tensor-core variant of the two value products: out = AW (S x S, fp32 in HBM) . V (S x 8 per n-tile) with mma.sync m16n8k8 on
+// tf32 operands, 3xTF32 (hi.hi + lo.hi + hi.lo) for fp32-class accuracy.  The products are bound by streaming the attention weights,
+// not by math, so the legacy warp-level MMA is the right tool: the A fragments are loaded straight from global memory in the
+// fragment layout (rows g / g+8, columns t / t+4 of the 16 x 8 block) and split in registers; V sits in shared memory as tf32 hi / lo
+// planes with a row stride of 56 floats (bank = 24 t + g: conflict-free B-fragment loads).  About a quarter of the instructions of
+// the FFMA kernel above (no 48-value warp fold).  One CTA = one sequence, one warp task = (head, 16 query rows) for SelfAttention
+// (two 8-column tiles: 12 of 16 columns used) or (16 query rows, half of the 48 channels) for NonlinAttention.
+constexpr int VSM = 56;
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <bool NL>
+__global__ void __launch_bounds__(256) attn_apply_mma_kernel(const float* __restrict__ aw, SeqMap sm, const float* __restrict__ src,
+                                                            float* __restrict__ out) {
+  extern __shared__ float sh[];
+  const int S = sm.S, SP16 = (S + 15) & ~15, ld = aw_ld(S);
+  float* vhi = sh;                    // [SP16][VSM], rows permuted inside every block of 16 (see below)
+  float* vlo = sh + SP16 * VSM;
+  const long long n = blockIdx.x;
+  for (int idx = threadIdx.x; idx < SP16 * (VSM / 4); idx += 256) {
+    const int s = idx / (VSM / 4), e = idx - s * (VSM / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s < S && e < 12) {
+      if (NL) {
+        const float4* pj = reinterpret_cast<const float4*>(src + sm.tok(n, s) * (3 * NH));
+        const float4 g = __ldg(pj + e), m = __ldg(pj + NH / 4 + e);
+        v = make_float4(m.x * tanhf(g.x), m.y * tanhf(g.y), m.z * tanhf(g.z), m.w * tanhf(g.w));
+      } else {
+        v = __ldg(reinterpret_cast<const float4*>(src + sm.tok(n, s) * SV) + e);
+      }
+    }
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+    // key j = 16 b + 4 t + e lives in row 16 b + 4 e + t: lane t of an MMA reads keys 4t .. 4t+3 of a 16-key block (one 16-byte
+    // load of the weights), and this placement keeps its four B-fragment loads on bank 24 t + g
+    const int ps = (s & ~15) + ((s & 3) << 2) + ((s >> 2) & 3);
+    *reinterpret_cast<float4*>(vhi + ps * VSM + 4 * e) = h;
+    *reinterpret_cast<float4*>(vlo + ps * VSM + 4 * e) = l;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int row_tiles = (S + 15) / 16;
+  constexpr int NT = NL ? 3 : 2;                 // 8-column tiles per task
+  const int ntask = (NL ? 2 : HEADS) * row_tiles;
+  for (int task = warp; task < ntask; task += 8) {
+    const int part = task % (NL ? 2 : HEADS);    // head (SelfAttention) or channel half (NonlinAttention)
+    const int i0 = (task / (NL ? 2 : HEADS)) * 16;
+    const int h = NL ? 0 : part;
+    const int c0 = NL ? part * 24 : part * VD;   // first channel of this task
+    const float* a_lo_row = aw + ((n * HEADS + h) * S + min(i0 + g, S - 1)) * (long long)ld;
+    const float* a_hi_row = aw + ((n * HEADS + h) * S + min(i0 + g + 8, S - 1)) * (long long)ld;
+    float acc[NT][4];
+#pragma unroll
+    for (int q = 0; q < NT; ++q)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[q][e] = 0.f;
+#pragma unroll 2
+    for (int k16 = 0; k16 < SP16; k16 += 16) {
+      // the sum over keys may take them in any order: MMA step s of this block uses keys 4t + 2s (k index t) and 4t + 2s + 1
+      // (k index t + 4), so each lane's share of the weights is ONE aligned 16-byte load per row (pad columns hold zeros)
+      const bool in = k16 + 4 * t < ld;
+      const float4 r0 = in ? __ldg(reinterpret_cast<const float4*>(a_lo_row + k16) + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 r1 = in ? __ldg(reinterpret_cast<const float4*>(a_hi_row + k16) + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float av[2][4] = {{r0.x, r1.x, r0.y, r1.y}, {r0.z, r1.z, r0.w, r1.w}};
+#pragma unroll
+      for (int st = 0; st < 2; ++st) {
+        uint32_t ah[4], al[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float hh, ll;
+          split_tf32(av[st][e], hh, ll);
+          ah[e] = __float_as_uint(hh); al[e] = __float_as_uint(ll);
+        }
+        const int p0 = (k16 + 8 * st + t) * VSM, p1 = p0 + 4 * VSM;      // rows of keys 4t + 2 st and 4t + 2 st + 1
+#pragma unroll
+        for (int q = 0; q < NT; ++q) {
+          const int col = c0 + 8 * q + g;
+          const uint32_t bh0 = __float_as_uint(vhi[p0 + col]), bh1 = __float_as_uint(vhi[p1 + col]);
+          const uint32_t bl0 = __float_as_uint(vlo[p0 + col]), bl1 = __float_as_uint(vlo[p1 + col]);
+          mma_tf32(acc[q], al, bh0, bh1);
+          mma_tf32(acc[q], ah, bl0, bl1);
+          mma_tf32(acc[q], ah, bh0, bh1);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NT; ++q)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = i0 + g + (e >> 1) * 8;
+        const int cc = 8 * q + 2 * t + (e & 1);          // column within the task
+        if (i >= S || (!NL && cc >= VD)) continue;
+        const int c = c0 + cc;
+        const long long tk = sm.tok(n, i);
+        float v = acc[q][e];
+        if (NL) v *= __ldg(src + tk * (3 * NH) + 2 * NH + c);
+        out[tk * SV + c] = v;
+      }
   }
 }
 
@@ -429,6 +535,15 @@ struct CudaExec {
   }
   template <bool NL>
   void apply(long long nseq, const SeqMap& sm, const float* aw, const float* src, float* out, int jj) {
+    static const bool use_mma = !(getenv("ADN_ZIP_APPLY") && !strcmp(getenv("ADN_ZIP_APPLY"), "ffma"));
+    if (use_mma) {
+      const size_t smem_m = (size_t)2 * ((sm.S + 15) & ~15) * VSM * sizeof(float);   // <= 2 * 256 * 56 * 4 = 114 688 B
+      static unsigned long long conf_m = 0;
+      auto km = attn_apply_mma_kernel<NL>;
+      if (adn_first_use_on_device(conf_m)) cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * VSM * 4);
+      km<<<(unsigned)nseq, 256, smem_m, st>>>(aw, sm, src, out);
+      return;
+    }
     const size_t smem = (size_t)sm.S * VST * sizeof(float);     // <= 256 * 52 * 4 = 53 248 B
     static unsigned long long configured[4] = {0, 0, 0, 0};
 #define ZIP_APPLY(J, slot)                                                                                                    \

@@ -207,9 +207,12 @@ struct PadCopy {
   }
 };
 
+// rows of the attention-weight tensor are padded to a multiple of 4 floats (16-byte aligned rows for vector loads); pad = 0
+ZIP_HD int aw_ld(int S) { return (S + 3) & ~3; }
+
 // RelPositionMultiheadAttentionWeights (:232-296): one thread = one (sequence, head, query) row of softmax(q.k + p.R[j - i])
 struct AttnW {
-  const float* ap; SeqMap sm; const float* pos; float* aw;      // pos (HEADS, PD, 2S-1); aw (sequence, head, S, S)
+  const float* ap; SeqMap sm; const float* pos; float* aw;      // pos (HEADS, PD, 2S-1); aw (sequence, head, S, aw_ld(S))
   ZIP_HD void operator()(long long idx) const {
     const int S = sm.S;
     const int i = (int)(idx % S); long long r = idx / S; const int h = (int)(r % HEADS); const long long n = r / HEADS;
@@ -217,7 +220,8 @@ struct AttnW {
     float q[QD], p[PD];
     for (int d = 0; d < QD; ++d) q[d] = qi[d];
     for (int d = 0; d < PD; ++d) p[d] = qi[2 * QD + d];
-    float* row = aw + ((n * HEADS + h) * S + i) * (long long)S;
+    float* row = aw + ((n * HEADS + h) * S + i) * (long long)aw_ld(S);
+    for (int j = S; j < aw_ld(S); ++j) row[j] = 0.f;
     const float* ph = pos + (long long)h * PD * (2 * S - 1) + (S - 1 - i);
     float mx = -INFINITY;
     for (int j = 0; j < S; ++j) {
@@ -243,7 +247,7 @@ struct SaApply {
   ZIP_HD void operator()(long long idx) const {
     const int S = sm.S;
     const int c = (int)(idx % SV); long long r = idx / SV; const int i = (int)(r % S); const long long n = r / S;
-    const float* a = aw + ((n * HEADS + c / VD) * S + i) * (long long)S;
+    const float* a = aw + ((n * HEADS + c / VD) * S + i) * (long long)aw_ld(S);
     float acc = 0.f;
     for (int j = 0; j < S; ++j) acc += a[j] * v[sm.tok(n, j) * SV + c];
     out[sm.tok(n, i) * SV + c] = acc;
@@ -256,7 +260,7 @@ struct NlApply {
   ZIP_HD void operator()(long long idx) const {
     const int S = sm.S;
     const int c = (int)(idx % NH); long long r = idx / NH; const int i = (int)(r % S); const long long n = r / S;
-    const float* a = aw + ((n * HEADS) * S + i) * (long long)S;
+    const float* a = aw + ((n * HEADS) * S + i) * (long long)aw_ld(S);
     float acc = 0.f;
     for (int j = 0; j < S; ++j) {
       const float* pj = np + sm.tok(n, j) * (3 * NH);
@@ -449,7 +453,7 @@ struct Workspace {
   double* part;
 };
 inline size_t aw_floats(int B, int T) {
-  const size_t a = (size_t)B * FQ * HEADS * T * T, b = (size_t)B * T * HEADS * FQ * FQ;
+  const size_t a = (size_t)B * FQ * HEADS * T * aw_ld(T), b = (size_t)B * T * HEADS * FQ * aw_ld(FQ);
   return a > b ? a : b;
 }
 // Alloc: float* alloc(size_t n_floats)  (null on failure).  Every buffer of the dense-block / stride-conv A operands gets
@@ -527,7 +531,7 @@ void zip_layer(Exec& ex, Workspace& w, const LayerW& L, float* x0, float* x, lon
   ex.gemm(g, "zip_attn_in");
   ex.run(nseq * HEADS * S, AttnW{w.t1, sm, L.pos, w.aw});
   snprintf(nm, sizeof(nm), "%s.aw", tag);
-  ex.mark(nm, w.aw, nseq * HEADS * S * S);
+  ex.mark_strided(nm, w.aw, nseq * HEADS * S, aw_ld(S), 0, S);
   // feed-forward modules: in projection + SwooshL, out projection + residual (+ bypass_mid)
   auto ff = [&](const float* in, const LinW& win, const LinW& wout, int hidden, const float* resid, const float* resid2, const float* cs) {
     LinOp a = lin_rows(in, C, C, M, win, hidden);
