@@ -142,7 +142,7 @@ struct Smem {
 // hi = x & 0xFFFFE000 (kept where it is) and lo = x - hi (lo slot) -- the 128-byte swizzle is a permutation of 16-byte chunks,
 // so an element-wise pass needs no knowledge of it -- then fence.proxy.async and hand the stage to the MMA warp.  Activations
 // live in HBM once, as fp32: half the A bytes, and no producer writes operand planes.
-template <int BN, int EPI, bool BF, bool AF>
+template <int BN, int EPI, bool BF, bool AF, bool DK = false>
 __global__ void __launch_bounds__(AF ? NTHREADS_AF : NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -162,7 +162,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   // epilogue warps 2 .. 2+NE-1, converter warps behind them.  fp32-A mode: a 64-wide tile has only 2 column chunks x 4 lane
   // quarters = 8 epilogue tasks, so 10 warps convert operands there (what bounds the deep-K implicit-GEMM convolutions: 19.7 ->
   // 16.1 ms per step); wider tiles keep all 16 epilogue warps (12 measured slower: ff_in 8.2 -> 10.0 ms) and 2 converters.
-  constexpr int NE = AF ? (BN <= 64 ? 8 : NEPI) : NEPI;
+  // DK (deep K, >= 512: MossFormer2 fl_in): the epilogue is amortised over many K blocks, conversion is not: 12 epilogue + 6
+  // converter warps (fl_in 8.3 -> 7.6 ms per step; at K = 256 the 16-warp epilogue still wins).
+  constexpr int NE = AF ? (BN <= 64 ? 8 : DK ? 12 : NEPI) : NEPI;
   constexpr int NCONV = AF ? NEPI + NCONV_AF - NE : 0;
   float* stage = (float*)(smem + S::STAGES * S::STAGE_BYTES);
 
@@ -347,6 +349,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
           if (row_ok && !dead) {
+            const float rsc_row = g.rowscale ? __ldg(g.rowscale + (long long)b * g.TM + t) : 1.0f;
             float4 res4[8];
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
@@ -356,6 +359,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               if (!(c0 + 4 * j4 < BN && n0 + 4 * j4 < g.N)) continue;
+              if (g.rowscale) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[4 * j4 + j] *= rsc_row;
+              }
               if (g.bias) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j4);
                 x[4 * j4] += b4.x; x[4 * j4 + 1] += b4.y; x[4 * j4 + 2] += b4.z; x[4 * j4 + 3] += b4.w;
@@ -367,6 +374,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                   const float y = x[4 * j4 + j] - off;
                   x[4 * j4 + j] = fmaxf(y, 0.f) + __logf(1.0f + __expf(-fabsf(y))) - 0.08f * x[4 * j4 + j];
                 }
+              } else if (g.act == ACT_SILU) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[4 * j4 + j] = x[4 * j4 + j] * __fdividef(1.0f, 1.0f + __expf(-x[4 * j4 + j]));
+              } else if (g.act == ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[4 * j4 + j] = fmaxf(x[4 * j4 + j], 0.f);
+              } else if (g.act == ACT_RELU2) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float r = fmaxf(x[4 * j4 + j], 0.f); x[4 * j4 + j] = r * r; }
+              } else if (g.act == ACT_PRELU) {
+                const float slope = __ldg(g.act_param);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[4 * j4 + j] = x[4 * j4 + j] >= 0.f ? x[4 * j4 + j] : slope * x[4 * j4 + j];
+              } else if (g.act == ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[4 * j4 + j] = 0.5f * x[4 * j4 + j] * (1.0f + fast_erf(x[4 * j4 + j] * 0.70710678118654752440f));
+              } else if (g.act == ACT_TANH) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[4 * j4 + j] = tanhf(x[4 * j4 + j]);
               }
               x[4 * j4] += res4[j4].x; x[4 * j4 + 1] += res4[j4].y; x[4 * j4 + 2] += res4[j4].z; x[4 * j4 + 3] += res4[j4].w;
               if (g.resid2) {
@@ -694,11 +720,11 @@ bool make_store_map(CUtensorMap* map, float* base, int cols, int rows, long long
   return true;
 }
 
-template <int BN, int EPI, bool BF, bool AF = false>
+template <int BN, int EPI, bool BF, bool AF = false, bool DK = false>
 static cudaError_t launch_t(const TcPlan& p, const TcArgs& a, int sms, cudaStream_t st) {
   using S = Smem<BN, BF, AF>;
   static unsigned long long configured = 0;      // per device
-  auto kern = gemm_tc_kernel<BN, EPI, BF, AF>;
+  auto kern = gemm_tc_kernel<BN, EPI, BF, AF, DK>;
   if (adn_first_use_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
     if (e != cudaSuccess) return e;
@@ -712,7 +738,11 @@ static cudaError_t launch_t(const TcPlan& p, const TcArgs& a, int sms, cudaStrea
 template <int BN>
 static cudaError_t launch_bn(const TcPlan& p, const TcArgs& a, int epi, int sms, cudaStream_t st) {
   if (p.bf16) return epi == EPI_LIN ? launch_t<BN, EPI_LIN, true>(p, a, sms, st) : cudaErrorInvalidValue;
-  if (p.a_f32) return epi == EPI_LIN ? launch_t<BN, EPI_LIN, false, true>(p, a, sms, st) : cudaErrorInvalidValue;
+  if (p.a_f32) {
+    if (epi != EPI_LIN) return cudaErrorInvalidValue;
+    if (BN > 64 && a.K >= 512 && a.taps == 0) return launch_t<BN, EPI_LIN, false, true, true>(p, a, sms, st);
+    return launch_t<BN, EPI_LIN, false, true>(p, a, sms, st);
+  }
   if (epi == EPI_STORE) return launch_t<BN, EPI_STORE, false>(p, a, sms, st);
   if (epi == EPI_ISTFT) return launch_t<BN, EPI_ISTFT, false>(p, a, sms, st);
   if (epi == EPI_LIN) return launch_t<BN, EPI_LIN, false>(p, a, sms, st);

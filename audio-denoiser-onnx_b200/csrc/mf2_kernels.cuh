@@ -20,9 +20,11 @@
 
 namespace mf2 {
 
-// GEMM operand stores.  3xTF32 (default): value -> tf32 hi / lo planes.  bf16 matmul mode (lo == nullptr; only where
-// the workload spec licenses bf16 matmuls): ONE bf16 plane living in the hi buffer at the same element offsets.
+// GEMM operand stores.  3xTF32 W-side operands: value -> tf32 hi / lo planes.  bf16 matmul mode (lo == nullptr; only where
+// the workload spec licenses bf16 matmuls): ONE bf16 plane living in the hi buffer at the same element offsets.  fp32-A mode
+// (lo == hi): the consumer is a GEMM that splits its A tile itself (gemm_tc.cu, TcPlan::a_f32), so the value is stored once, as fp32.
 __device__ __forceinline__ void split_tf32_store(float v, float* hi, float* lo, long long i) {
+  if (lo == hi) { hi[i] = v; return; }
   if (lo == nullptr) {
     reinterpret_cast<__nv_bfloat16*>(hi)[i] = __float2bfloat16_rn(v);
     return;
@@ -44,6 +46,7 @@ constexpr float EPS_OUT = 1e-5f * 32.0f;                 // eps / 1024^-0.5  (:1
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void split4(float4 v, float* hi, float* lo, long long i) {
+  if (lo == hi) { st4(hi + i, v); return; }   // fp32-A mode
   if (lo == nullptr) {                        // bf16 plane: 4 values = 8 bytes
     __nv_bfloat162 p01 = __floats2bfloat162_rn(v.x, v.y), p23 = __floats2bfloat162_rn(v.z, v.w);
     uint2 pk;
@@ -541,6 +544,7 @@ struct Base : public ModelImpl {
   std::vector<void*> allocs;
   size_t ws_bytes = 0;
   int planned = 0;
+  bool af = false;               // fp32-A GEMMs: activations are stored once as fp32, the GEMM splits its A tile in shared memory
 
   void free_ws() {
     adn_note_free();
@@ -565,6 +569,7 @@ struct Base : public ModelImpl {
     l.N = N; l.K = K; l.batches = 1; l.bf16 = bf16;
     l.bn = choose_bn(N);
     if (bf16 && l.bn == 176) l.bn = 128;
+    if (af && !bf16 && l.bn == 176) l.bn = 256;     // the TMA-store epilogue writes 32-column boxes: tiles are multiples of 32
     l.n_pad = round_up(N, l.bn);
     l.k_pad = round_up(K, bf16 ? 64 : 32);
     const long long plane = (long long)l.n_pad * l.k_pad;
@@ -594,13 +599,18 @@ struct Base : public ModelImpl {
   // A operand: tf32 hi plane at a_planes, lo plane a_plane_stride floats later; bf16 weights (l.bf16): ONE bf16 plane at
   // a_planes (2-byte elements, same element strides)
   bool plan_gemm(Gemm& g, const float* a_planes, long long a_plane_stride, int K, int rows, long long row_stride,
-                 int batches, long long batch_stride, const Lin& l) {
+                 int batches, long long batch_stride, const Lin& l, bool allow_af = true) {
     const int bt = rows >= 128 ? 128 : rows;
+    g.plan = tc::TcPlan{};
     g.plan.bn = l.bn;
     g.plan.bf16 = l.bf16;
     g.plan.map_w_hi = l.w_hi;
     g.plan.map_w_lo = l.w_lo;
-    if (l.bf16) {
+    g.plan.a_f32 = af && allow_af && !l.bf16;
+    if (g.plan.a_f32) {                          // a_planes is the fp32 tensor itself
+      if (!tc::make_row_map(&g.plan.map_a_hi, a_planes, K, rows, row_stride, batches, batch_stride, bt, 1, err)) return false;
+      g.plan.map_a_lo = g.plan.map_a_hi;
+    } else if (l.bf16) {
       if (!tc::make_row_map(&g.plan.map_a_hi, a_planes, K, rows, row_stride, batches, batch_stride, bt, 1, err, true)) return false;
     } else if (!tc::make_row_map(&g.plan.map_a_hi, a_planes, K, rows, row_stride, batches, batch_stride, bt, 1, err) ||
                !tc::make_row_map(&g.plan.map_a_lo, a_planes + a_plane_stride, K, rows, row_stride, batches, batch_stride, bt, 1, err))
@@ -612,6 +622,16 @@ struct Base : public ModelImpl {
     a.m_tiles = batches * a.tiles_per_chunk;
     a.w_batched = l.batches > 1;
     return true;
+  }
+  // fp32-A plans write their output through a TMA store: call once the caller has set args.C / Chi / ldc / N.  An operand-plane
+  // output (Chi / Clo) becomes the fp32 output.
+  bool finish_af(Gemm& g) {
+    if (!g.plan.a_f32) return true;
+    tc::TcArgs& a = g.args;
+    if (!a.C && a.Chi) { a.C = a.Chi; }
+    a.Chi = a.Clo = nullptr;
+    if (!a.C) { err = "fp32-A GEMM without an fp32 output"; return false; }
+    return tc::make_store_map(&g.plan.map_c, a.C, a.N, a.TM, a.ldc, a.B, (long long)a.TM * a.ldc, err);
   }
 };
 

@@ -246,6 +246,7 @@ class Model : public Base {
   int stop_after = 0, last_batch = 0;
   bool bf = false;               // metadata matmul_dtype == BF16: the 24 layers' GEMMs run on bf16 operands (BASELINE configs[2])
   float* LO(float* p) const { return bf ? nullptr : p; }      // lo plane of an operand, absent in bf16 mode
+  float* LOA(float* hi, float* lo) const { return af ? hi : LO(lo); }   // A-side operand: fp32-A mode stores fp32 in the hi buffer only
 
   ~Model() override {
     cudaSetDevice(device);
@@ -296,6 +297,9 @@ class Model : public Base {
         if (it->second != "BF16") { err = "matmul_dtype must be F32 (3xTF32, default) or BF16"; return false; }
         bf = true;
       }
+      // 3xTF32 mode: fp32 activations + in-kernel operand split + TMA-store epilogues (ADN_MF2_AF=0: the round-1 operand planes)
+      const char* e = getenv("ADN_MF2_AF");
+      af = !bf && !(e && e[0] == '0');
     }
     auto pdt = [&](const std::string& s, int& o) { if (s == "F32") o = ADN_F32; else if (s == "INT16") o = ADN_I16; else if (s == "F16") o = ADN_F16; else return false; return true; };
     if (!pdt(sin, in_dtype) || !pdt(sout, out_dtype)) { err = "bad audio dtype"; return false; }
@@ -419,7 +423,7 @@ class Model : public Base {
       return false;
 
     // frontend: rows = frames (stride hop) of the raw window
-    if (!plan_gemm(g_front, xpl, (long long)xplane, NFFT, T, HOP, B, Lp, front)) return false;
+    if (!plan_gemm(g_front, af ? xp : xpl, (long long)xplane, NFFT, T, HOP, B, Lp, front)) return false;
     g_front.args.C = fr; g_front.args.ldc = FRONT;
     if (!plan_gemm(g_enc, featpl, M * FEATP, FEATP, (int)M, FEATP, 1, M * FEATP, enc)) return false;
     g_enc.args.K = FEATP; g_enc.args.resid = z; g_enc.args.C = z; g_enc.args.ldc = D;
@@ -433,7 +437,7 @@ class Model : public Base {
     if (!plan_gemm(g_lk, lq, M * QK, QK, T, QK, B, (long long)T * QK, a_lk)) return false;
     g_lk.args.C = s1; g_lk.args.ldc = Tp;
     if (!plan_gemm(g_qk, qq, M * QK, QK, T, QK, B, (long long)T * QK, a_qk)) return false;
-    g_qk.args.act = tc::ACT_RELU2; g_qk.args.resid = s1; g_qk.args.Chi = ppl; g_qk.args.Clo = LO(ppl + M * Tp); g_qk.args.ldc = Tp;
+    g_qk.args.act = tc::ACT_RELU2; g_qk.args.resid = s1; g_qk.args.Chi = ppl; g_qk.args.Clo = LOA(ppl, ppl + M * Tp); g_qk.args.ldc = Tp;
     if (!plan_gemm(g_pv, ppl, M * Tp, Tp, T, Tp, B, (long long)T * Tp, a_vuT)) return false;
     g_pv.args.C = att; g_pv.args.ldc = VU2;
 
@@ -445,12 +449,12 @@ class Model : public Base {
       G.in.args.rowscale = rs; G.in.args.bias = Y.in_b; G.in.args.act = tc::ACT_SILU; G.in.args.C = proj; G.in.args.ldc = PROJ;
       if (!plan_gemm(G.out, gated, M * VU, VU, (int)M, VU, 1, M * VU, Y.out)) return false;
       G.out.args.rowscale = rs2; G.out.args.bias = Y.out_b; G.out.args.act = tc::ACT_SILU; G.out.args.C = y; G.out.args.ldc = D;
-      if (!plan_gemm(G.c1, hpl, M * D, D, (int)M, D, 1, M * D, Y.c1)) return false;
+      if (!plan_gemm(G.c1, af ? h : hpl, M * D, D, (int)M, D, 1, M * D, Y.c1)) return false;
       G.c1.args.bias = Y.c1_b; G.c1.args.act = tc::ACT_PRELU; G.c1.args.act_param = Y.c1_a; G.c1.args.C = c1y; G.c1.args.ldc = FI;
       if (!plan_gemm(G.uv, xn, M * FI, FI, (int)M, FI, 1, M * FI, Y.uv)) return false;
       G.uv.args.bias = Y.uv_b; G.uv.args.act = tc::ACT_SILU; G.uv.args.C = uvp; G.uv.args.ldc = 2 * FI;
-      if (!plan_gemm(G.ul, xupl, M * FI, FI, (int)M, FI, 1, M * FI, Y.ul)) return false;
-      G.ul.args.bias = Y.ul_b; G.ul.args.act = tc::ACT_RELU; G.ul.args.Chi = f1; G.ul.args.Clo = LO(f1 + M * FI); G.ul.args.ldc = FI;
+      if (!plan_gemm(G.ul, af ? uv : xupl, M * FI, FI, (int)M, af ? 2 * FI : FI, 1, af ? M * 2 * FI : M * FI, Y.ul)) return false;
+      G.ul.args.bias = Y.ul_b; G.ul.args.act = tc::ACT_RELU; G.ul.args.Chi = f1; G.ul.args.Clo = LOA(f1, f1 + M * FI); G.ul.args.ldc = FI;
       if (!plan_gemm(G.up, f1, M * FI, FI, (int)M, FI, 1, M * FI, Y.up)) return false;
       G.up.args.C = xp2; G.up.args.ldc = FI;
       if (!plan_gemm(G.c2, yn, M * FI, FI, (int)M, FI, 1, M * FI, Y.c2)) return false;
@@ -461,10 +465,15 @@ class Model : public Base {
     if (!plan_gemm(g_dec, tg, M * D, D, (int)M, D, 1, M * D, dec)) return false;
     g_dec.args.N = BINSP; g_dec.args.act = tc::ACT_RELU; g_dec.args.C = mask; g_dec.args.ldc = BINSP;
 
+    {   // fp32-A plans: output tensor maps (TMA-store epilogue)
+      std::vector<Gemm*> all = {&g_front, &g_enc, &g_lk, &g_qk, &g_pv, &g_gate, &g_dec};
+      for (auto& G : lg) for (Gemm* q : {&G.in, &G.out, &G.c1, &G.uv, &G.ul, &G.up, &G.c2}) all.push_back(q);
+      for (Gemm* q : all) if (!finish_af(*q)) return false;
+    }
     {   // inverse: rows = raw hop blocks, each a run of R consecutive zero-framed spectrum frames
       const int rows = T + 2 * PADF;
       const int TM = T + R_OLA - 1;          // blocks 0 .. (raw-1)/hop
-      if (!plan_gemm(g_istft, enh, (long long)enh_plane, ola.k_pad, rows, SPEC_LD, B, (long long)rows * SPEC_LD, ola)) return false;
+      if (!plan_gemm(g_istft, enh, (long long)enh_plane, ola.k_pad, rows, SPEC_LD, B, (long long)rows * SPEC_LD, ola, false)) return false;
       tc::TcArgs& c = g_istft.args;
       const int bt = TM >= 128 ? 128 : TM;
       c.bt = bt; c.tiles_per_chunk = (TM + 127) / 128; c.m_tiles = B * c.tiles_per_chunk; c.TM = TM; c.t0 = 0;
@@ -531,7 +540,7 @@ class Model : public Base {
     feat_kernel<<<(unsigned)M, 256, 0, st>>>(fr, banks, d_mel_lo, d_mel_hi, mel, 1.1920929e-07f * (1.0f / 32768.0f) * (1.0f / 32768.0f),
                                             20.794415416798357f);
     MF_TICK("feat");
-    featnorm_kernel<<<B, 256, (size_t)T * 2 * NM * sizeof(float), st>>>(mel, norm_w, norm_b, emb, featpl, featpl + M * FEATP, z, T);
+    featnorm_kernel<<<B, 256, (size_t)T * 2 * NM * sizeof(float), st>>>(mel, norm_w, norm_b, emb, featpl, af ? featpl : featpl + M * FEATP, z, T);
     MF_TICK("featnorm");
     MF_GEMM(g_enc, EPI_LIN, "enc_gemm");
 
@@ -539,38 +548,38 @@ class Model : public Base {
       LayerG& G = lg[i];
       const Layer& Y = lw[i];
       const float* hin = i == 0 ? z : h;
-      shiftnorm_kernel<<<wtok, 256, 0, st>>>(hin, xs, LO(xs + M * D), rs, M, T, 0);
+      shiftnorm_kernel<<<wtok, 256, 0, st>>>(hin, xs, LOA(xs, xs + M * D), rs, M, T, 0);
       MF_TICK("shiftnorm");
       MF_GEMM(G.in, EPI_LIN, "fl_in");
       dwconv_in_tma_kernel<<<dim3(PROJ / DP_C, B, (T + DP_TILES * DP_F - 1) / (DP_TILES * DP_F)), 256, DP_SMEM, st>>>(
-          map_proj, Y.in_c, Y.gamma, Y.beta, rcos, rsin, vu, vuT, LO(vuT + (size_t)B * VU2 * Tp), qq, LO(qq + M * QK), lq, LO(lq + M * QK),
+          map_proj, Y.in_c, Y.gamma, Y.beta, rcos, rsin, vu, vuT, LO(vuT + (size_t)B * VU2 * Tp), qq, LOA(qq, qq + M * QK), lq, LOA(lq, lq + M * QK),
           qk, LO(qk + (size_t)B * Tn * QK), lk, LO(lk + (size_t)B * Tn * QK), nullptr, nullptr, T, Tp, Tn, T, QK);
       MF_TICK("dwconv_in");
       MF_GEMM(g_lk, EPI_LIN, "att_lk");
       MF_GEMM(g_qk, EPI_LIN, "att_qk");
       MF_GEMM(g_pv, EPI_LIN, "att_pv");
-      gate_kernel<<<wtok, 256, 0, st>>>(att, vu, gated, LO(gated + M * VU), rs2, M, T, T, 0);
+      gate_kernel<<<wtok, 256, 0, st>>>(att, vu, gated, LOA(gated, gated + M * VU), rs2, M, T, T, 0);
       MF_TICK("gate");
       MF_GEMM(G.out, EPI_LIN, "fl_out");
-      dwconv_kernel<<<dim3(D / 32 / DWI_WARPS, B, (T + DW_SEG - 1) / DW_SEG), DWI_WARPS * 32, 0, st>>>(y, Y.out_c, hin, h, hpl, LO(hpl + M * D), D, T, D);
+      dwconv_kernel<<<dim3(D / 32 / DWI_WARPS, B, (T + DW_SEG - 1) / DW_SEG), DWI_WARPS * 32, 0, st>>>(y, Y.out_c, hin, h, af ? nullptr : hpl, LO(hpl + M * D), D, T, D);      // fp32-A: fsmn_conv1 reads h itself
       MF_TICK("dwconv_out");
       MF_GEMM(G.c1, EPI_LIN, "fsmn_conv1");
-      ln2_kernel<<<wtok, 256, 0, st>>>(c1y, Y.n1_w, Y.n1_b, gin, xn, LO(xn + M * FI), M);
+      ln2_kernel<<<wtok, 256, 0, st>>>(c1y, Y.n1_w, Y.n1_b, gin, xn, LOA(xn, xn + M * FI), M);
       MF_TICK("ln2");
       MF_GEMM(G.uv, EPI_LIN, "fsmn_uv");
-      dwconv_kernel<<<dim3(2 * FI / 32 / DWI_WARPS, B, (T + DW_SEG - 1) / DW_SEG), DWI_WARPS * 32, 0, st>>>(uvp, Y.uv_c, nullptr, uv, xupl, LO(xupl + M * FI), FI, T, 2 * FI);
+      dwconv_kernel<<<dim3(2 * FI / 32 / DWI_WARPS, B, (T + DW_SEG - 1) / DW_SEG), DWI_WARPS * 32, 0, st>>>(uvp, Y.uv_c, nullptr, uv, af ? nullptr : xupl, LO(xupl + M * FI), FI, T, 2 * FI);   // fp32-A: fsmn_linear reads uv's first FI columns
       MF_TICK("dwconv_uv");
       MF_GEMM(G.ul, EPI_LIN, "fsmn_linear");
       MF_GEMM(G.up, EPI_LIN, "fsmn_project");
-      fsmn_mem_kernel<<<dim3((T + FM_TOK - 1) / FM_TOK, B), 256, (2 * FM_TOK + 2 * MEMH) * FI * sizeof(float), st>>>(xp2, uv, gin, Y.mem_c, Y.n2_w, Y.n2_b, yn, LO(yn + M * FI), T);
+      fsmn_mem_kernel<<<dim3((T + FM_TOK - 1) / FM_TOK, B), 256, (2 * FM_TOK + 2 * MEMH) * FI * sizeof(float), st>>>(xp2, uv, gin, Y.mem_c, Y.n2_w, Y.n2_b, yn, LOA(yn, yn + M * FI), T);
       MF_TICK("fsmn_mem");
       MF_GEMM(G.c2, EPI_LIN, "fsmn_conv2");
     }
 
-    tail_norm_kernel<<<B, 512, 0, st>>>(layers ? h : z, z, mm_w, mm_b, in_w, in_b, prelu_a, hn, tpl, tpl + M * D, T);
+    tail_norm_kernel<<<B, 512, 0, st>>>(layers ? h : z, z, mm_w, mm_b, in_w, in_b, prelu_a, hn, tpl, af ? tpl : tpl + M * D, T);
     MF_TICK("tail_norm");
     MF_GEMM(g_gate, EPI_LIN, "tail_gate_gemm");
-    tail_gate_kernel<<<(unsigned)((M * (D / 4) + 255) / 256), 256, 0, st>>>(gbuf, tg, tg + M * D, M);
+    tail_gate_kernel<<<(unsigned)((M * (D / 4) + 255) / 256), 256, 0, st>>>(gbuf, tg, af ? tg : tg + M * D, M);
     MF_TICK("tail_gate");
     MF_GEMM(g_dec, EPI_LIN, "mask_gemm");
     mask_apply_kernel<<<(unsigned)M, 256, 0, st>>>(fr, mask, enh, enh + enh_plane, T);
