@@ -3,6 +3,8 @@
 #pragma once
 #include "mfgan_gemm.cuh"
 
+#include "common.cuh"
+#include "gemm_tc.cuh"
 #include "model_impl.h"
 
 #include <map>
@@ -10,6 +12,53 @@
 #include <vector>
 
 namespace gan {
+
+// ---- tcgen05 path for the operators that are plain contractions (Linear; Conv2d with unit stride): the fp32-A mode of
+// csrc/gemm_tc.cu -- fp32 activations through TMA, operand split + LayerNorm-on-load + conv edge masking in the converter warps,
+// TMA-store epilogue.  Weights arrive as (K, N) matrices (adjacent threads of the functor read adjacent outputs); their
+// transposed, zero-padded tf32 hi / lo planes are built on first use and kept in the model's TcCache together with the plans.
+static __global__ void transpose_split_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int K, int N,
+                                              int k_pad, long long total) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int n = (int)(i / k_pad), k = (int)(i % k_pad);
+  const float v = (n < N && k < K) ? w[(long long)k * N + n] : 0.f;
+  const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  hi[i] = h;
+  lo[i] = v - h;
+}
+
+struct TcEntry {
+  bool valid = false;
+  const float *in = nullptr, *w = nullptr; float* out = nullptr; const float* stat = nullptr;
+  long long rows = 0; int chunks = 0, K = 0, N = 0, lda = 0, ldc = 0, kind = 0, dil = 0;
+  tc::TcPlan plan;
+  tc::TcArgs args;
+};
+struct TcWeight { float* planes = nullptr; int n_pad = 0, k_pad = 0; };
+struct TcCache {
+  int sms = 148;
+  bool enabled = true;
+  std::map<int, std::vector<TcEntry>> plans;           // per windows-in-pass
+  std::map<const float*, TcWeight> weights;
+  std::string err;
+  ~TcCache() { clear(); }
+  void clear() {
+    for (auto& kv : weights) cudaFree(kv.second.planes);
+    weights.clear();
+    plans.clear();
+  }
+  const TcWeight* weight(const float* w, int K, int N, cudaStream_t st) {
+    auto it = weights.find(w);
+    if (it != weights.end()) return &it->second;
+    TcWeight t;
+    t.n_pad = (N + 63) / 64 * 64; t.k_pad = (K + 31) / 32 * 32;
+    const long long total = (long long)t.n_pad * t.k_pad;
+    if (cudaMalloc((void**)&t.planes, 2 * total * sizeof(float)) != cudaSuccess) { err = "out of device memory (operand planes)"; return nullptr; }
+    transpose_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, t.planes, t.planes + total, K, N, t.k_pad, total);
+    return &(weights[w] = t);
+  }
+};
 
 template <class F>
 __global__ void __launch_bounds__(256) op_kernel(long long n, F f) {
@@ -79,7 +128,104 @@ struct CudaExec {
     ++launches;
     if (tick) tick(tick_ctx, name);
   }
-  void run(long long n, const Linear& f) { run_gemm(n, f); }
+  // ---- tcgen05 dispatch
+  TcCache* tc = nullptr;
+  int tc_pass = 0, tc_idx = 0;       // plans are cached per (windows in this pass, position in the launch sequence)
+  static int tc_act(int a) {
+    return a == ACT_NONE ? tc::ACT_NONE : a == ACT_RELU ? tc::ACT_RELU : a == ACT_SILU ? tc::ACT_SILU : a == ACT_PRELU ? tc::ACT_PRELU_VEC
+           : a == ACT_SIGMOID ? tc::ACT_SIGMOID : -1;
+  }
+  bool tc_launch(TcEntry& e, const char* name) {
+    if (tc::launch(e.plan, e.args, EPI_LIN, tc->sms, st) != cudaSuccess) { cudaGetLastError(); return false; }
+    ++launches;
+    if (tick) tick(tick_ctx, name);
+    return true;
+  }
+  TcEntry& tc_slot() {
+    std::vector<TcEntry>& v = tc->plans[tc_pass];
+    if ((int)v.size() <= tc_idx) v.resize(tc_idx + 1);
+    return v[tc_idx++];
+  }
+  bool tc_plan(TcEntry& e, const float* a, int a_ke, long long rows, long long a_sr, int chunks, long long a_sb, const TcWeight* w, int N, int K,
+               float* out, int ldc) {
+    const int bn = N <= 64 ? 64 : N <= 128 ? 128 : 256;
+    const int bt = rows >= 128 ? 128 : (int)rows;
+    e.plan = tc::TcPlan{};
+    e.plan.bn = bn;
+    e.plan.a_f32 = true;
+    const long long plane = (long long)w->n_pad * w->k_pad;
+    std::string& err = tc->err;
+    if (!tc::make_row_map(&e.plan.map_a_hi, a, a_ke, (int)rows, a_sr, chunks, a_sb, bt, 1, err) ||
+        !tc::make_weight_map(&e.plan.map_w_hi, w->planes, w->k_pad, w->n_pad, bn, err) ||
+        !tc::make_weight_map(&e.plan.map_w_lo, w->planes + plane, w->k_pad, w->n_pad, bn, err) ||
+        !tc::make_store_map(&e.plan.map_c, out, N, (int)rows, ldc, chunks, rows * ldc, err))
+      return false;
+    e.plan.map_a_lo = e.plan.map_a_hi;
+    e.plan.map_w2_hi = e.plan.map_w_hi;
+    e.plan.map_w2_lo = e.plan.map_w_lo;
+    tc::TcArgs& g = e.args;
+    g = tc::TcArgs{};
+    g.bb = 1; g.bt = bt; g.tiles_per_chunk = (int)((rows + 127) / 128); g.t0 = 0;
+    g.B = chunks; g.TM = (int)rows; g.N = N; g.K = K;
+    g.m_tiles = chunks * g.tiles_per_chunk;
+    g.C = out; g.ldc = ldc;
+    return true;
+  }
+  bool try_tc(long long n, const Linear& f) {
+    if (!tc || !tc->enabled || tc_act(f.a) < 0 || f.N % 4 || f.ldo % 4 || f.ldi % 4 || f.K % 4 || f.N < 16 || ((uintptr_t)f.in & 15) || ((uintptr_t)f.out & 15))
+      return false;
+    const long long M = n / f.N;
+    if (M < 128) return false;
+    const TcWeight* w = tc->weight(f.Wt, f.K, f.N, st);
+    if (!w) return false;
+    TcEntry& e = tc_slot();
+    if (!(e.valid && e.kind == 1 && e.in == f.in && e.out == f.out && e.w == f.Wt && e.stat == f.stat && e.rows == M && e.K == f.K && e.N == f.N &&
+          e.lda == f.ldi && e.ldc == f.ldo)) {
+      e.valid = false;
+      if (!tc_plan(e, f.in, f.K, M, f.ldi, 1, M * f.ldi, w, f.N, f.K, f.out, f.ldo)) return false;
+      e.args.bias = f.bias; e.args.act = tc_act(f.a); e.args.act_vec = f.slope; e.args.a_rowstat = f.stat;
+      e.kind = 1; e.in = f.in; e.out = f.out; e.w = f.Wt; e.stat = f.stat; e.rows = M; e.chunks = 1; e.K = f.K; e.N = f.N; e.lda = f.ldi; e.ldc = f.ldo;
+      e.valid = true;
+    }
+    return tc_launch(e, "gan_linear_tc");
+  }
+  // unit-stride channel-last conv as an implicit GEMM over the UN-padded map: K = taps x Cin, tap (kt, kf) reads the rows shifted by
+  // (kt - (KT-1)) * dil * F + (kf - pf); rows before the window start read as zeros (TMA), rows whose sub-band leaves [0, F) are zeroed
+  // by the converter warps
+  bool try_tc(long long n, const Conv2d& f) {
+    if (!tc || !tc->enabled || f.sf != 1 || f.Fin != f.Fout || f.Cin % 32 || f.Cout % 4 || f.Cout < 16 || f.KT * f.KF > 6 || f.ldi % 4 || f.ldo % 4 ||
+        ((uintptr_t)f.in & 15) || ((uintptr_t)f.out & 15))
+      return false;
+    const long long px = n / f.Cout;                       // B * T * F
+    const long long rows = (long long)f.T * f.Fin;
+    const int B = (int)(px / rows);
+    if (rows < 128) return false;
+    const int K = f.KT * f.KF * f.Cin;
+    const TcWeight* w = tc->weight(f.W, K, f.Cout, st);
+    if (!w) return false;
+    TcEntry& e = tc_slot();
+    if (!(e.valid && e.kind == 2 && e.in == f.in && e.out == f.out && e.w == f.W && e.rows == rows && e.chunks == B && e.K == K && e.N == f.Cout &&
+          e.lda == f.ldi && e.ldc == f.ldo && e.dil == f.dil)) {
+      e.valid = false;
+      if (!tc_plan(e, f.in, f.Cin, rows, f.ldi, B, rows * f.ldi, w, f.Cout, K, f.out, f.ldo)) return false;
+      tc::TcArgs& g = e.args;
+      g.bias = f.bias;
+      g.taps = f.KT * f.KF; g.tap_kb = f.Cin / 32; g.tap_k0 = 0; g.tap_w = f.Fin;
+      for (int kt = 0; kt < f.KT; ++kt)
+        for (int kf = 0; kf < f.KF; ++kf) {
+          g.tap_shift[kt * f.KF + kf] = (kt - (f.KT - 1)) * f.dil * f.Fin + (kf - f.pf);
+          g.tap_df[kt * f.KF + kf] = kf - f.pf;
+        }
+      e.kind = 2; e.in = f.in; e.out = f.out; e.w = f.W; e.stat = nullptr; e.rows = rows; e.chunks = B; e.K = K; e.N = f.Cout; e.lda = f.ldi;
+      e.ldc = f.ldo; e.dil = f.dil;
+      e.valid = true;
+    }
+    return tc_launch(e, "gan_conv2d_tc");
+  }
+  void run(long long n, const Linear& f) {
+    if (try_tc(n, f)) return;
+    run_gemm(n, f);
+  }
   void run(long long n, const SimLocal& f) { run_gemm(n, f); }
   void run(long long n, const SimCross& f) { run_gemm(n, f); }
   void run(long long n, const LinKV& f) { run_gemm(n, f); }
@@ -88,6 +234,7 @@ struct CudaExec {
   void run(long long n, const TaScores& f) { run_gemm(n, f); }
   void run(long long n, const TaAV& f) { run_gemm(n, f); }
   void run(long long n, const Conv2d& f) {
+    if (try_tc(n, f)) return;
     if (f.Cout >= 16 && f.Cin % GK == 0) run_gemm(n, f);
     else run<Conv2d>(n, f);
   }

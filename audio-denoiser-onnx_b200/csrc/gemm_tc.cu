@@ -290,13 +290,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int mt = tile / n_tiles_n;
+      const int cb = mt / g.tiles_per_chunk, ct = (mt - cb * g.tiles_per_chunk) * BM;     // chunk and first row of this tile
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(&full[stage], phase);
         float4* hi = reinterpret_cast<float4*>(smem + stage * S::STAGE_BYTES);
         float4* lo = hi + A_TILE_BYTES / 16;
+        const int df = (g.taps > 0 && g.tap_w > 0) ? g.tap_df[kb / g.tap_kb] : 0;
 #pragma unroll 4
         for (int i = cw * 32 + lane; i < ((g.probe & 1) ? 0 : (int)(A_TILE_BYTES / 16)); i += NCONV * 32) {
-          const float4 v = hi[i];
+          float4 v = hi[i];
+          if (g.a_rowstat || df) {                 // per-row work: the swizzle permutes 16-byte chunks inside a row only
+            const int t = ct + (i >> 3);
+            if (g.a_rowstat && t < g.TM) {
+              const float2 ms = __ldg(reinterpret_cast<const float2*>(g.a_rowstat) + ((long long)(cb + g.b_off) * g.TM + t));
+              v.x = (v.x - ms.x) * ms.y; v.y = (v.y - ms.x) * ms.y; v.z = (v.z - ms.x) * ms.y; v.w = (v.w - ms.x) * ms.y;
+            }
+            if (df) {
+              const int col = t % g.tap_w + df;
+              if (col < 0 || col >= g.tap_w) v = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
           float4 h, l;
           h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
           h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
@@ -387,6 +401,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const float slope = __ldg(g.act_param);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) x[4 * j4 + j] = x[4 * j4 + j] >= 0.f ? x[4 * j4 + j] : slope * x[4 * j4 + j];
+              } else if (g.act == ACT_PRELU_VEC) {
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(g.act_vec + n0) + j4);
+                const float sl[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[4 * j4 + j] = x[4 * j4 + j] >= 0.f ? x[4 * j4 + j] : sl[j] * x[4 * j4 + j];
+              } else if (g.act == ACT_SIGMOID) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[4 * j4 + j] = 1.0f / (1.0f + expf(-x[4 * j4 + j]));
               } else if (g.act == ACT_GELU) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) x[4 * j4 + j] = 0.5f * x[4 * j4 + j] * (1.0f + fast_erf(x[4 * j4 + j] * 0.70710678118654752440f));

@@ -45,13 +45,18 @@ struct TcArgs {
   // EPI_LIN: after the residual, v = resid2[m*ldc+n] + (v - resid2[m*ldc+n]) * colscale[n]   (Zipformer2 BypassModule)
   const float* resid2;
   const float* colscale;
+  // fp32-A mode extras (MossFormerGAN / DFSMN operators on this GEMM):
+  const float* a_rowstat;  // (mean, rstd) per output row m: the converter warps normalise the A row while splitting it (LayerNorm on load)
+  int tap_w;               // taps > 0 on an UN-padded map of row width tap_w: rows whose column + tap_df[tap] leaves [0, tap_w) are zeroed
+  int tap_df[6];           //   by the converter (the conv's zero padding along the row axis)
+  const float* act_vec;    // ACT_PRELU_VEC: slope per output column
   int probe;             // diagnostics (ADN_TC_PROBE): 1 = converters do not convert, 2 = epilogue does not load / store, 4 = W loaded once per CTA
   int i16_mode;          // EPI_ISTFT int16 output: 0 = x*32767, clamp, truncate (GTCRN, Export_GTCRN.py:680-693)
                          //   1 = clamp(x,-1,32767/32768)*32768, truncate (MossFormer2_SE_48K/Export_MossFormer_SE.py:499-504)
 };
 
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_TANH = 2, ACT_SILU = 3, ACT_RELU = 4, ACT_RELU2 = 5, ACT_PRELU = 6,
-       ACT_SWOOSH_L = 7, ACT_SWOOSH_R = 8 };   // softplus(x - 4 | 1) - 0.08 x (Export_ZipEnhancer.py:131-140)
+       ACT_SWOOSH_L = 7, ACT_SWOOSH_R = 8, ACT_PRELU_VEC = 9, ACT_SIGMOID = 10 };   // softplus(x - 4 | 1) - 0.08 x (Export_ZipEnhancer.py:131-140)
 
 struct TcPlan {
   CUtensorMap map_a_hi, map_a_lo, map_w_hi, map_w_lo;

@@ -11,6 +11,7 @@
 #include "model_impl.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -40,6 +41,7 @@ class Model : public ModelImpl {
         *spec2 = nullptr, *wave = nullptr;
   int stop_after = 0, last_launches = 0, last_batch = 0;
   std::map<std::string, std::vector<float>> dumps;
+  TcCache tcc;                     // tcgen05 plans + weight operand planes of the Linear / Conv2d operators (gan_exec.cuh)
   static constexpr int SUB = 16;   // windows per pass of the backbone (bounds the workspace)
 
   ~Model() override {
@@ -52,6 +54,7 @@ class Model : public ModelImpl {
     adn_note_free();
     for (void* p : allocs) cudaFree(p);
     allocs.clear();
+    tcc.plans.clear();             // the plans hold workspace addresses
     cap = 0;
   }
   float* dalloc(size_t n) {
@@ -192,8 +195,12 @@ class Model : public ModelImpl {
     ex.st = st; ex.tick = tick; ex.tick_ctx = tick_ctx;
     ex.capture = stop_after != 0; ex.dumps = &dumps;
     if (ex.capture) dumps.clear();
+    tcc.sms = sms;
+    { const char* e = getenv("ADN_GAN_TC"); tcc.enabled = !(e && e[0] == '0'); }     // ADN_GAN_TC=0: the round-1 FFMA tiles
+    ex.tc = &tcc;
     for (int b0 = 0; b0 < B; b0 += SUB) {
       const int nb = B - b0 < SUB ? B - b0 : SUB;
+      ex.tc_pass = nb; ex.tc_idx = 0;
       forward(ex, ws, W, feat + (size_t)b0 * 3 * T * FB, mask + (size_t)b0 * FB * T, cplx + (size_t)b0 * 2 * FB * T, nb, T);
       ex.capture = false;                          // stage dumps cover the first pass only
     }
