@@ -8,6 +8,7 @@
 #include "gan_exec.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace gan {
@@ -49,10 +50,12 @@ class Model : public ModelImpl {
     free_ws();
     if (stft) adn_stft_destroy(stft);
   }
+  gan::TcCache tcc;               // tcgen05 plans + weight operand planes of the analysis transform and the Linear layers (gan_exec.cuh)
   void free_ws() {
     adn_note_free();
     for (void* p : allocs) cudaFree(p);
     allocs.clear();
+    tcc.plans.clear();
     cap = 0;
   }
   float* dalloc(size_t n) {
@@ -155,6 +158,9 @@ class Model : public ModelImpl {
     ex.st = st; ex.tick = tick; ex.tick_ctx = tick_ctx;
     ex.capture = stop_after != 0; ex.dumps = &dumps;
     if (ex.capture) dumps.clear();
+    tcc.sms = sms; tcc.min_rows = 1;
+    { const char* e = getenv("ADN_GAN_TC"); tcc.enabled = !(e && e[0] == '0'); }
+    ex.tc = &tcc; ex.tc_pass = B; ex.tc_idx = 0;
     const long long n = (long long)B * L;
     if (in_dtype == ADN_I16) ex.run(n, Prep<int16_t>{(const int16_t*)d_in, 1.0f / 32768.0f, x});
     else if (in_dtype == ADN_F16) ex.run(n, Prep<__half>{(const __half*)d_in, 1.0f, x});

@@ -18,11 +18,11 @@ namespace gan {
 // TMA-store epilogue.  Weights arrive as (K, N) matrices (adjacent threads of the functor read adjacent outputs); their
 // transposed, zero-padded tf32 hi / lo planes are built on first use and kept in the model's TcCache together with the plans.
 static __global__ void transpose_split_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int K, int N,
-                                              int k_pad, long long total) {
+                                              int k_pad, long long total, int kmajor) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= total) return;
   const int n = (int)(i / k_pad), k = (int)(i % k_pad);
-  const float v = (n < N && k < K) ? w[(long long)k * N + n] : 0.f;
+  const float v = (n < N && k < K) ? (kmajor ? w[(long long)n * K + k] : w[(long long)k * N + n]) : 0.f;
   const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
   hi[i] = h;
   lo[i] = v - h;
@@ -37,6 +37,7 @@ struct TcEntry {
 };
 struct TcWeight { float* planes = nullptr; int n_pad = 0, k_pad = 0; };
 struct TcCache {
+  int min_rows = 128;             // Linear layers with fewer rows stay on the FFMA tiles (DFSMN sets 1: a window's result must not depend on the batch it rides in)
   int sms = 148;
   bool enabled = true;
   std::map<int, std::vector<TcEntry>> plans;           // per windows-in-pass
@@ -48,14 +49,15 @@ struct TcCache {
     weights.clear();
     plans.clear();
   }
-  const TcWeight* weight(const float* w, int K, int N, cudaStream_t st) {
+  // kmajor: w is (N, K) row-major already; otherwise (K, N)
+  const TcWeight* weight(const float* w, int K, int N, cudaStream_t st, bool kmajor = false) {
     auto it = weights.find(w);
     if (it != weights.end()) return &it->second;
     TcWeight t;
     t.n_pad = (N + 63) / 64 * 64; t.k_pad = (K + 31) / 32 * 32;
     const long long total = (long long)t.n_pad * t.k_pad;
     if (cudaMalloc((void**)&t.planes, 2 * total * sizeof(float)) != cudaSuccess) { err = "out of device memory (operand planes)"; return nullptr; }
-    transpose_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, t.planes, t.planes + total, K, N, t.k_pad, total);
+    transpose_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, t.planes, t.planes + total, K, N, t.k_pad, total, kmajor ? 1 : 0);
     return &(weights[w] = t);
   }
 };
@@ -124,6 +126,7 @@ struct CudaExec {
     if (tick) tick(tick_ctx, OpName<F>::get());
   }
   void gemm(const GemmOp& g, const char* name = "gemm") {
+    if (try_tc(g, name)) return;
     launch_gemm(g, st);
     ++launches;
     if (tick) tick(tick_ctx, name);
@@ -175,7 +178,7 @@ struct CudaExec {
     if (!tc || !tc->enabled || tc_act(f.a) < 0 || f.N % 4 || f.ldo % 4 || f.ldi % 4 || f.K % 4 || f.N < 16 || ((uintptr_t)f.in & 15) || ((uintptr_t)f.out & 15))
       return false;
     const long long M = n / f.N;
-    if (M < 128) return false;
+    if (M < tc->min_rows) return false;
     const TcWeight* w = tc->weight(f.Wt, f.K, f.N, st);
     if (!w) return false;
     TcEntry& e = tc_slot();
@@ -221,6 +224,25 @@ struct CudaExec {
       e.valid = true;
     }
     return tc_launch(e, "gan_conv2d_tc");
+  }
+  // a plain GemmOp whose operands are K-contiguous (the DFSMN analysis transform: frames as overlapping rows of the waveform)
+  bool try_tc(const GemmOp& g, const char* name) {
+    if (!tc || !tc->enabled || g.a_k != 1 || g.b_k != 1 || g.c_n != 1 || g.stat || g.cv.on || g.gt.on || g.epi != GEPI_ACT || g.act != ACT_NONE ||
+        g.bias || g.nb2 != 1 || g.a_kin || g.b_kin || g.b_nin || g.c_nin || g.b_b1 || g.a_m % 4 || g.a_b1 % 4 || g.c_m % 4 || g.K % 4 || g.N % 4 ||
+        g.b_n != g.K || g.c_b1 != (long long)g.M * g.c_m || ((uintptr_t)g.A & 15) || ((uintptr_t)g.C & 15))
+      return false;
+    const TcWeight* w = tc->weight(g.B, g.K, g.N, st, true);
+    if (!w) return false;
+    TcEntry& e = tc_slot();
+    if (!(e.valid && e.kind == 3 && e.in == g.A && e.out == g.C && e.w == g.B && e.rows == g.M && e.chunks == g.batch && e.K == g.K && e.N == g.N &&
+          e.lda == (int)g.a_m && e.ldc == (int)g.c_m)) {
+      e.valid = false;
+      if (!tc_plan(e, g.A, g.K, g.M, g.a_m, g.batch, g.a_b1, w, g.N, g.K, g.C, (int)g.c_m)) return false;
+      e.kind = 3; e.in = g.A; e.out = g.C; e.w = g.B; e.stat = nullptr; e.rows = g.M; e.chunks = g.batch; e.K = g.K; e.N = g.N;
+      e.lda = (int)g.a_m; e.ldc = (int)g.c_m;
+      e.valid = true;
+    }
+    return tc_launch(e, name);
   }
   void run(long long n, const Linear& f) {
     if (try_tc(n, f)) return;

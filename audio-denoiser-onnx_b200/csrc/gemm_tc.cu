@@ -297,10 +297,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         float4* hi = reinterpret_cast<float4*>(smem + stage * S::STAGE_BYTES);
         float4* lo = hi + A_TILE_BYTES / 16;
         const int df = (g.taps > 0 && g.tap_w > 0) ? g.tap_df[kb / g.tap_kb] : 0;
+        const int n16 = (g.probe & 1) ? 0 : (int)(A_TILE_BYTES / 16);
+        if (!(g.a_rowstat || df)) {                // the common case: split only
 #pragma unroll 4
-        for (int i = cw * 32 + lane; i < ((g.probe & 1) ? 0 : (int)(A_TILE_BYTES / 16)); i += NCONV * 32) {
-          float4 v = hi[i];
-          if (g.a_rowstat || df) {                 // per-row work: the swizzle permutes 16-byte chunks inside a row only
+          for (int i = cw * 32 + lane; i < n16; i += NCONV * 32) {
+            const float4 v = hi[i];
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+            hi[i] = h;
+            lo[i] = l;
+          }
+        } else {                                   // per-row work: the swizzle permutes 16-byte chunks inside a row only
+#pragma unroll 2
+          for (int i = cw * 32 + lane; i < n16; i += NCONV * 32) {
+            float4 v = hi[i];
             const int t = ct + (i >> 3);
             if (g.a_rowstat && t < g.TM) {
               const float2 ms = __ldg(reinterpret_cast<const float2*>(g.a_rowstat) + ((long long)(cb + g.b_off) * g.TM + t));
@@ -310,14 +323,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               const int col = t % g.tap_w + df;
               if (col < 0 || col >= g.tap_w) v = make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+            hi[i] = h;
+            lo[i] = l;
           }
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-          hi[i] = h;
-          lo[i] = l;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
         __syncwarp();
