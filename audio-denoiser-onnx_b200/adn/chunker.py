@@ -28,8 +28,10 @@ def plan_windows(audio_len: int, in_len: int, out_len: int, same_rate: bool = Tr
 
 
 def tail_pad(audio: np.ndarray, pad_amount: int, mode: str = "zeros", rng=None) -> np.ndarray:
-    """audio (C, N) -> (C, N+pad).  'zeros' (GTCRN :291-298, folded Mel-Band :298-300) or 'noise':
-    RMS-matched gaussian tail of the un-folded Mel-Band script (:301-303, :309-311)."""
+    """audio (C, N) -> (C, N+pad).  'zeros' (GTCRN :291-298, folded Mel-Band :298-300), 'noise': RMS-matched gaussian
+    tail of the un-folded Mel-Band script (:301-303, :309-311), or 'reflect': the signal mirrored about its last sample,
+    a single sample repeated, nothing -> zeros (`pad_audio_tail_with_context`, H-GTCRN/Inference_H_GTCRN_ONNX.py:138-153,
+    the un-folded H-GTCRN script)."""
     if pad_amount <= 0:
         return audio
     c = audio.shape[0]
@@ -41,6 +43,14 @@ def tail_pad(audio: np.ndarray, pad_amount: int, mode: str = "zeros", rng=None) 
         ref = ref.astype(np.float32)
         rms = np.sqrt(np.mean(ref * ref, dtype=np.float32), dtype=np.float32)
         block = (rms * rng.normal(loc=0.0, scale=1.0, size=(c, pad_amount))).astype(audio.dtype)
+    elif mode == "reflect":
+        n = audio.shape[1]
+        if n == 0:
+            block = np.zeros((c, pad_amount), dtype=audio.dtype)
+        elif n == 1:
+            block = np.repeat(audio[:, -1:], pad_amount, axis=-1)
+        else:
+            block = np.pad(audio, ((0, 0), (0, pad_amount)), mode="reflect")[:, n:]
     else:
         raise ValueError(f"unknown tail pad mode {mode!r}")
     return np.concatenate((audio, block), axis=-1)

@@ -173,3 +173,21 @@ def ulunas_model(state_dict: dict, input_audio_length: int = 32000, in_dtype: st
 
     md = ulunas_params.metadata(input_audio_length, in_dtype, out_dtype)
     return Model.from_tensors(md, ulunas_params.pack(state_dict, input_audio_length, in_dtype, out_dtype), device_id)
+
+
+def export_hgtcrn(state_dict: dict, path, input_audio_length: int = 16128, in_dtype: str = "INT16", out_dtype: str = "INT16") -> dict[str, str]:
+    """H-GTCRN (two microphones, WPE + AuxIVA front end) `.adn` for one static window of k * 256 samples at 16 kHz (counterpart of
+    H-GTCRN/Export_H_GTCRN.py:1075-1186).  `state_dict`: the raw `GTCRN_IVA` state_dict (reference key names)."""
+    from . import hgtcrn_params
+
+    md = hgtcrn_params.metadata(input_audio_length, in_dtype, out_dtype)
+    modelfile.save(path, md, hgtcrn_params.pack(state_dict, input_audio_length))
+    return md
+
+
+def hgtcrn_model(state_dict: dict, input_audio_length: int = 16128, in_dtype: str = "F32", out_dtype: str = "F32", device_id: int = 0):
+    from . import hgtcrn_params
+    from .model import Model
+
+    md = hgtcrn_params.metadata(input_audio_length, in_dtype, out_dtype)
+    return Model.from_tensors(md, hgtcrn_params.pack(state_dict, input_audio_length), device_id)

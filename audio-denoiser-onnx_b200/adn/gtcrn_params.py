@@ -96,23 +96,9 @@ def output_length(model_out_length: int, out_rate: int = 16000) -> int:
     return int(np.floor(float(model_out_length) * (out_rate / 16000.0)))
 
 
-def pack(state_dict: dict, input_audio_length: int, in_rate: int = 16000) -> dict[str, np.ndarray]:
-    """Returns {tensor name: fp32 array} for one static chunk length (given at `in_rate`)."""
-    input_audio_length = model_length(input_audio_length, in_rate)
-    sd = {k: v for k, v in state_dict.items()}
-    geom = stft_tables.GEOMETRY["gtcrn"]
-    blob: dict[str, np.ndarray] = {}
-
-    # encoder front: en_convs.0 (16,9,1,5) and en_convs.1 (16,8,1,5, groups 2)
-    w0, b0 = _fold(sd, "encoder.en_convs.0.conv", "encoder.en_convs.0.bn")
-    w1, b1 = _fold(sd, "encoder.en_convs.1.conv", "encoder.en_convs.1.bn")
-    w0p = w0[:, :, 0, :].permute(2, 1, 0).contiguous()                       # (o,ci,k) -> [k][ci][o]
-    w1p = w1[:, :, 0, :].reshape(2, 8, 8, 5).permute(0, 2, 3, 1).contiguous()  # (grp,ol,ci,k) -> [grp][ci][k][ol]
-    blob["enc_front"] = _f(torch.cat([
-        w0p.reshape(-1), b0, w1p.reshape(-1), b1,
-        sd["encoder.en_convs.0.act.weight"].reshape(-1), sd["encoder.en_convs.1.act.weight"].reshape(-1)]))
-    assert blob["enc_front"].size == 720 + 16 + 640 + 16 + 2
-
+def pack_backbone(sd: dict, blob: dict, dec_deconv: bool) -> None:
+    """Everything between en_convs.1 and the band synthesis: the six GTConv blocks with their TRA GRUs, the two DPGRNNs,
+    de_convs.3 / .4 and the ERB matrices.  dec_deconv: GTCRN's decoder blocks are transposed convolutions, H-GTCRN's plain."""
     for i in range(3):
         pe = f"encoder.en_convs.{i + 2}"
         blob[f"enc_gt.{i}"] = _gt_block(sd, pe, False)
@@ -120,7 +106,7 @@ def pack(state_dict: dict, input_audio_length: int, in_rate: int = 16000) -> dic
         blob[f"enc_tra.{i}.fc_w"] = _f(sd[f"{pe}.tra.att_fc.weight"])
         blob[f"enc_tra.{i}.fc_b"] = _f(sd[f"{pe}.tra.att_fc.bias"])
         pd = f"decoder.de_convs.{i}"
-        blob[f"dec_gt.{i}"] = _gt_block(sd, pd, True)
+        blob[f"dec_gt.{i}"] = _gt_block(sd, pd, dec_deconv)
         _gru(blob, f"dec_tra.{i}", sd, f"{pd}.tra.att_gru")
         blob[f"dec_tra.{i}.fc_w"] = _f(sd[f"{pd}.tra.att_fc.weight"])
         blob[f"dec_tra.{i}.fc_b"] = _f(sd[f"{pd}.tra.att_fc.bias"])
@@ -155,6 +141,27 @@ def pack(state_dict: dict, input_audio_length: int, in_rate: int = 16000) -> dic
     blob["erb.bs"] = _f(bs)
     lo, hi = _nonzero_ranges(bs)
     blob["erb.bs_lo"], blob["erb.bs_hi"] = _f(lo), _f(hi)
+
+
+
+def pack(state_dict: dict, input_audio_length: int, in_rate: int = 16000) -> dict[str, np.ndarray]:
+    """Returns {tensor name: fp32 array} for one static chunk length (given at `in_rate`)."""
+    input_audio_length = model_length(input_audio_length, in_rate)
+    sd = {k: v for k, v in state_dict.items()}
+    geom = stft_tables.GEOMETRY["gtcrn"]
+    blob: dict[str, np.ndarray] = {}
+
+    # encoder front: en_convs.0 (16,9,1,5) and en_convs.1 (16,8,1,5, groups 2)
+    w0, b0 = _fold(sd, "encoder.en_convs.0.conv", "encoder.en_convs.0.bn")
+    w1, b1 = _fold(sd, "encoder.en_convs.1.conv", "encoder.en_convs.1.bn")
+    w0p = w0[:, :, 0, :].permute(2, 1, 0).contiguous()                       # (o,ci,k) -> [k][ci][o]
+    w1p = w1[:, :, 0, :].reshape(2, 8, 8, 5).permute(0, 2, 3, 1).contiguous()  # (grp,ol,ci,k) -> [grp][ci][k][ol]
+    blob["enc_front"] = _f(torch.cat([
+        w0p.reshape(-1), b0, w1p.reshape(-1), b1,
+        sd["encoder.en_convs.0.act.weight"].reshape(-1), sd["encoder.en_convs.1.act.weight"].reshape(-1)]))
+    assert blob["enc_front"].size == 720 + 16 + 640 + 16 + 2
+
+    pack_backbone(sd, blob, True)
 
     n_frames = geom.n_frames(input_audio_length)
     blob["stft.fwd"] = _f(stft_tables.forward_basis(geom))

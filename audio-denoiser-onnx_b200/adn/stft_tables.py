@@ -43,6 +43,7 @@ GEOMETRY = {
     "mossformer2_se_48k": StftGeometry(1920, 1920, 384, "hamming_sym", False, "constant", "divide"),
     "mel_band_roformer": StftGeometry(2048, 2048, 441, "hann", True, "reflect", "divide"),
     "mossformergan_se_16k": StftGeometry(400, 400, 100, "hamming", True, "reflect", "divide"),
+    "h_gtcrn": StftGeometry(512, 512, 256, "hann", True, "reflect", "divide"),          # H-GTCRN/Export_H_GTCRN.py:34-39
 }
 
 

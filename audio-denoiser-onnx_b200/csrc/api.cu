@@ -135,7 +135,7 @@ struct adn_model {
   size_t nfloats = 0;
 
   int in_dtype = ADN_F32, out_dtype = ADN_F32;
-  int L = 0, T = 0, Lp = 0, Lout = 0, chans = 1;   // GTCRN: L / Lout are the MODEL-rate window and its ISTFT length
+  int L = 0, T = 0, Lp = 0, Lout = 0, chans = 1, out_chans = 1;   // (H-GTCRN: two microphones in, one channel out)  // GTCRN: L / Lout are the MODEL-rate window and its ISTFT length
   // GTCRN linear resampling (Export_GTCRN.py:619-632, :638-654, :671-688): the caller's window is io_L samples at
   // in_sample_rate, the output io_Lout samples at out_sample_rate; the inner run works on fp32 model-rate buffers
   bool rs_in = false, rs_out = false;
@@ -653,7 +653,7 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
   if (!is_ss && (!need("nfft", snfft) || !need("hop_length", shop))) return fail(ADN_ERR_INVALID);
   if (is_ss) { snfft = "16"; shop = "8"; }          // Conv1d(k16, s8) framing, snip-edges
   m->family = fam;
-  if (fam != "gtcrn" && fam != "mel_band_roformer" && fam != "mossformer2_se" && fam != "mossformergan_se" && fam != "dfsmn" && fam != "ulunas" && fam != "zipenhancer" && !is_ss) {
+  if (fam != "gtcrn" && fam != "mel_band_roformer" && fam != "mossformer2_se" && fam != "mossformergan_se" && fam != "dfsmn" && fam != "ulunas" && fam != "zipenhancer" && fam != "h_gtcrn" && !is_ss) {
     m->err = "unsupported model_family '" + fam + "'";
     return fail(ADN_ERR_UNSUPPORTED);
   }
@@ -705,6 +705,7 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
   }
   m->io_Lout = m->rs_out ? (int)floor((double)m->Lout * m->out_scale_factor) : m->Lout;
   m->chans = fam == "mel_band_roformer" ? 2 : 1;
+  m->out_chans = m->chans;
 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device_id) {
@@ -739,12 +740,13 @@ adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weight
                   : fam == "dfsmn" ? dfsmn_create(m->meta, m->index, weights, m->d_blob, device_id, m->sms, m->err)
                   : fam == "ulunas" ? ulunas_create(m->meta, m->index, weights, m->d_blob, device_id, m->sms, m->err)
                   : fam == "zipenhancer" ? zipenh_create(m->meta, m->index, weights, m->d_blob, device_id, m->sms, m->err)
+                  : fam == "h_gtcrn" ? hgtcrn_create(m->meta, m->index, weights, m->d_blob, device_id, m->sms, m->err)
                           : mbr_create(m->meta, m->index, weights, m->d_blob, device_id, m->sms, m->err);
     if (!m->impl) s = ADN_ERR_INVALID;
     else {                                          // host staging follows the family's own I/O description
       adn_tensor_info tin, touts[4];
       m->impl->io_info(&tin, touts);
-      m->L = tin.length; m->chans = tin.channels; m->Lout = touts[0].length; m->n_out = m->impl->n_outputs();
+      m->L = tin.length; m->chans = tin.channels; m->out_chans = touts[0].channels; m->Lout = touts[0].length; m->n_out = m->impl->n_outputs();
       m->io_L = m->L; m->io_Lout = m->Lout;
     }
   }
@@ -913,7 +915,7 @@ adn_status adn_run_host(adn_model* m, const void* h_in, void* const* h_outs, int
       adn_note_free();
       if (m->io_cap) { cudaFree(m->d_in); cudaFree(m->d_out); }
       ADN_CUDA_TRY(cudaMalloc(&m->d_in, (size_t)batch * m->chans * m->io_L * dtype_size(m->in_dtype)), m->err);
-      ADN_CUDA_TRY(cudaMalloc(&m->d_out, (size_t)m->n_out * batch * m->chans * m->io_Lout * dtype_size(m->out_dtype)), m->err);
+      ADN_CUDA_TRY(cudaMalloc(&m->d_out, (size_t)m->n_out * batch * m->out_chans * m->io_Lout * dtype_size(m->out_dtype)), m->err);
       m->io_cap = batch;
     }
   } else {
@@ -921,7 +923,7 @@ adn_status adn_run_host(adn_model* m, const void* h_in, void* const* h_outs, int
     if (s != ADN_OK) return s;
   }
   const size_t in_row = (size_t)m->chans * m->io_L * dtype_size(m->in_dtype);
-  const size_t out_row = (size_t)m->chans * m->io_Lout * dtype_size(m->out_dtype);
+  const size_t out_row = (size_t)m->out_chans * m->io_Lout * dtype_size(m->out_dtype);
   if (!m->ev_h2d[0]) {
     ADN_CUDA_TRY(cudaStreamCreateWithFlags(&m->st_in, cudaStreamNonBlocking), m->err);
     ADN_CUDA_TRY(cudaStreamCreateWithFlags(&m->st_out, cudaStreamNonBlocking), m->err);
@@ -1167,6 +1169,30 @@ adn_status adn_stft_forward(adn_stft* s, const float* d_x, float* d_spec, int32_
   }
   return ADN_OK;
 }
+
+}  // extern "C"
+
+// Frame-major variants (internal, model_impl.h) for model families that keep GTCRN's (rows, T, ld) spectrum layout: the
+// forward takes an already padded waveform (rows, Lp) and writes (rows, T, ld) [Re | Im | pad]; the inverse takes the
+// zero-framed (rows, T + 2 * pad_frames, ld) enhanced spectrum as the overlap-add GEMM's A operand directly.
+int adn_stft_ld(const adn_stft* s) { return s->p.ld; }
+int adn_stft_pad_frames(const adn_stft* s) { return s->p.pad_frames(); }
+int adn_stft_padded_len(const adn_stft* s, int length) { return s->p.padded_len(length); }
+adn_status adn_stft_forward_fm(adn_stft* s, const float* d_xp, float* d_spec_fm, int rows, int n_frames, int Lp, cudaStream_t st) {
+  GemmArgs g;
+  fill_stft_gemm(g, s->p, d_xp, Lp, s->d_fwd, rows, n_frames, d_spec_fm, (long long)n_frames * s->p.ld, s->p.ld, 1);
+  launch_gemm_ffma(g, EPI_STORE, st);
+  return cudaGetLastError() == cudaSuccess ? ADN_OK : ADN_ERR_CUDA;
+}
+adn_status adn_stft_inverse_fm(adn_stft* s, const float* d_fm_padded, float* d_y, int rows, int n_frames, cudaStream_t st) {
+  if (n_frames != s->T) return ADN_ERR_INVALID;
+  GemmArgs g;
+  fill_istft_gemm(g, s->p, d_fm_padded, s->d_ola, s->d_norm, rows, n_frames, d_y, ADN_F32);
+  launch_gemm_ffma(g, EPI_ISTFT, st);
+  return cudaGetLastError() == cudaSuccess ? ADN_OK : ADN_ERR_CUDA;
+}
+
+extern "C" {
 
 adn_status adn_stft_inverse(adn_stft* s, const float* d_spec, float* d_y, int32_t batch, int32_t n_frames,
                             void* stream) {

@@ -419,8 +419,9 @@ constexpr int DT_THREADS = 288;
 
 __global__ void __launch_bounds__(DT_THREADS)
 dec_tail_kernel(const __grid_constant__ DecTailW w, const ErbW erb, const float* __restrict__ xin,
-                const float* __restrict__ e0, const float* __restrict__ spec, float* __restrict__ enh,
-                float* __restrict__ enh_hi, float* __restrict__ enh_lo, int T, int nframes, int pad_frames) {
+                const float* __restrict__ e0, const float* __restrict__ spec, long long spec_chunk_stride,
+                float* __restrict__ enh, float* __restrict__ enh_hi, float* __restrict__ enh_lo, int T, int nframes,
+                int pad_frames) {
   __shared__ float xs[DT_FR][16][E1_F + 2];      // zero column each side
   __shared__ float ys[DT_FR][16][E0_F + 2];      // d3 + e0, zero column each side
   __shared__ float ms[DT_FR][2][ERB_F];
@@ -498,7 +499,8 @@ dec_tail_kernel(const __grid_constant__ DecTailW w, const ErbW erb, const float*
     long long fg = f0 + fr;
     if (fg >= nframes) continue;
     long long b = fg / T, t = fg - b * T;
-    float re = __ldg(spec + fg * SPEC_LD + f), im = __ldg(spec + fg * SPEC_LD + FB + f);
+    const float* sp = spec + b * spec_chunk_stride + t * SPEC_LD;     // the masked spectrum: chunk b's frames (H-GTCRN: microphone 0's rows)
+    float re = __ldg(sp + f), im = __ldg(sp + FB + f);
     float m0 = mf[fr][0][f], m1 = mf[fr][1][f];
     const long long base = (b * (T + 2 * pad_frames) + pad_frames + t) * SPEC_LD;
     const float er = re * m0 - im * m1, ei = im * m0 + re * m1;
@@ -516,16 +518,10 @@ dec_tail_kernel(const __grid_constant__ DecTailW w, const ErbW erb, const float*
 // =================================================================================
 #define TICK(name) do { ++n; if (tick) tick(tick_ctx, name); if (stop_after > 0 && n >= stop_after) return n; } while (0)
 
-int launch_backbone(const Weights& w, const Buffers& buf, const Dims& d, int enh_pad_frames,
-                    cudaStream_t st, TickFn tick, void* tick_ctx, int stop_after) {
-  int n = 0;
+int launch_backbone_core(const Weights& w, const Buffers& buf, const Dims& d, cudaStream_t st, TickFn tick, void* tick_ctx,
+                         int stop_after, int n, float** last) {
   const int B = d.B, T = d.T;
   const int nframes = B * T;
-
-  enc_front_kernel<<<(nframes + EF_FR - 1) / EF_FR, EF_THREADS, 0, st>>>(w.enc_front, w.erb, buf.spec,
-                                                                       buf.e0, buf.e[1], nframes);
-  TICK("enc_front");
-
   const int dil_enc[3] = {1, 2, 5};
   for (int i = 0; i < 3; ++i) {
     int dl = dil_enc[i];
@@ -564,9 +560,29 @@ int launch_backbone(const Weights& w, const Buffers& buf, const Dims& d, int enh
     TICK("tra_apply");
     float* tmp = cur; cur = nxt; nxt = tmp;
   }
-  dec_tail_kernel<<<(nframes + DT_FR - 1) / DT_FR, DT_THREADS, 0, st>>>(w.dec_tail, w.erb, cur, buf.e0, buf.spec,
-                                                                      buf.enh, buf.enh_hi, buf.enh_lo, T, nframes,
+  *last = cur;
+  return n;
+}
+
+void launch_dec_tail(const Weights& w, const Buffers& buf, const float* xin, const float* spec, long long spec_chunk_stride,
+                     const Dims& d, int enh_pad_frames, cudaStream_t st) {
+  const int nframes = d.B * d.T;
+  dec_tail_kernel<<<(nframes + DT_FR - 1) / DT_FR, DT_THREADS, 0, st>>>(w.dec_tail, w.erb, xin, buf.e0, spec, spec_chunk_stride,
+                                                                      buf.enh, buf.enh_hi, buf.enh_lo, d.T, nframes,
                                                                       enh_pad_frames);
+}
+
+int launch_backbone(const Weights& w, const Buffers& buf, const Dims& d, int enh_pad_frames,
+                    cudaStream_t st, TickFn tick, void* tick_ctx, int stop_after) {
+  int n = 0;
+  const int nframes = d.B * d.T;
+  enc_front_kernel<<<(nframes + EF_FR - 1) / EF_FR, EF_THREADS, 0, st>>>(w.enc_front, w.erb, buf.spec,
+                                                                       buf.e0, buf.e[1], nframes);
+  TICK("enc_front");
+  float* cur = nullptr;
+  n = launch_backbone_core(w, buf, d, st, tick, tick_ctx, stop_after, n, &cur);
+  if (!cur) return n;                       // stopped inside the core
+  launch_dec_tail(w, buf, cur, buf.spec, (long long)d.T * SPEC_LD, d, enh_pad_frames, st);
   TICK("dec_tail");
   return n;
 }

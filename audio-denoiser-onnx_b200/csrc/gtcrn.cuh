@@ -120,6 +120,15 @@ typedef void (*TickFn)(void* ctx, const char* name);
 int launch_backbone(const Weights& w, const Buffers& buf, const Dims& d, int enh_pad_frames,
                     cudaStream_t st, TickFn tick, void* tick_ctx, int stop_after);
 
+// The pieces of launch_backbone, for H-GTCRN (csrc/hgtcrn.cu: its own six-channel encoder front, the same network between
+// en_convs.1 and the band synthesis, the complex ratio mask applied to microphone 0's rows of a two-microphone spectrum).
+// launch_backbone_core continues the launch count from `n` and returns the decoder's last activation in *last (left null
+// when `stop_after` ended the sequence early).
+int launch_backbone_core(const Weights& w, const Buffers& buf, const Dims& d, cudaStream_t st, TickFn tick, void* tick_ctx,
+                         int stop_after, int n, float** last);
+void launch_dec_tail(const Weights& w, const Buffers& buf, const float* xin, const float* spec, long long spec_chunk_stride,
+                     const Dims& d, int enh_pad_frames, cudaStream_t st);
+
 // Input conditioning (cast, 1/32768, DC removal, centre pad): Export_GTCRN.py:637-647 +
 // STFT_Process.py:305-309.
 // hi/lo (nullable): additionally emit the 3xTF32 operand planes.

@@ -58,3 +58,14 @@ ModelImpl* ulunas_create(const std::map<std::string, std::string>& meta, const s
 // ZipEnhancer 16 kHz: csrc/zipenh.cu
 ModelImpl* zipenh_create(const std::map<std::string, std::string>& meta, const std::map<std::string, TensorRef>& index,
                          const float* h_blob, float* d_blob, int device, int sms, std::string& err);
+
+// H-GTCRN 16 kHz stereo (WPE + AuxIVA front end, GTCRN_IVA network): csrc/hgtcrn.cu
+ModelImpl* hgtcrn_create(const std::map<std::string, std::string>& meta, const std::map<std::string, TensorRef>& index,
+                         const float* h_blob, float* d_blob, int device, int sms, std::string& err);
+
+// frame-major STFT / ISTFT on a stand-alone operator handle (api.cu)
+int adn_stft_ld(const adn_stft* s);
+int adn_stft_pad_frames(const adn_stft* s);
+int adn_stft_padded_len(const adn_stft* s, int length);
+adn_status adn_stft_forward_fm(adn_stft* s, const float* d_xp, float* d_spec_fm, int rows, int n_frames, int Lp, cudaStream_t st);
+adn_status adn_stft_inverse_fm(adn_stft* s, const float* d_fm_padded, float* d_y, int rows, int n_frames, cudaStream_t st);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the north-star path: noisy chunk in -> clean chunk out (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--model zipenh|gtcrn|mbr|mf2se|mf2ss|mfgan|dfsmn|ulunas] [--batch B] [--impl adn|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model zipenh|gtcrn|mbr|mf2se|mf2ss|mfgan|dfsmn|ulunas|hgtcrn] [--batch B] [--impl adn|reference]
 
 A "step" is one pass of the hot path over one batch of B synthetic chunks per GPU.
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field's definition.
@@ -610,6 +610,64 @@ class UlunasWorkload:
                       "istft": (4 * (514 * T + 15872), 2 * 514 * 512 * T)})
 
 
+class HgtcrnWorkload:
+    """H-GTCRN 16 kHz two-microphone denoiser: 2-channel STFT -> WPE (36 x 36 normal equations per bin, six CG
+    steps) -> AuxIVA (ten sweeps) -> GTCRN_IVA; windows of 16128 samples (63 hops, 64 frames), stereo in / mono out."""
+    name = "hgtcrn"
+    default_batch = 256
+    chunk, sr, channels, t_frames = 16128, 16000, 2, 64
+    cpu_chunks, ref_chunks = 64, 16
+    in_name = "noisy_audio"
+    cpu_desc = "oracle/hgtcrn_oracle.py (PyTorch-eager restatement, pinned stage by stage to the executed reference wrapper)"
+
+    def describe(self, B):
+        return (f"H-GTCRN 16 kHz, {B} x 1.008 s two-microphone windows (16128 samples, 64 frames x 257 bins; WPE 18 taps, "
+                f"AuxIVA 10 sweeps) per GPU per step, F32 in / F32 out")
+
+    def audio_seconds(self, B):
+        return B * self.chunk / self.sr
+
+    def weights(self):
+        import hgtcrn_oracle as ho
+        return ho.random_state_dict(0)
+
+    def build(self, sd, device):
+        from adn import export
+        return export.hgtcrn_model(sd, self.chunk, "F32", "F32", device_id=device)
+
+    def export(self, sd, path):
+        from adn import export
+        export.export_hgtcrn(sd, path, self.chunk, "F32", "F32")
+
+    def inputs(self, B, n_sets, seed):
+        sets = []
+        for s in range(n_sets):
+            g = torch.Generator().manual_seed(seed + s)
+            n = (torch.rand(B, 2, self.chunk, generator=g) * 2 - 1) * 0.2
+            src = (torch.rand(B, 1, self.chunk, generator=g) * 2 - 1) * 0.4
+            sets.append((n + torch.cat((src, 0.7 * torch.roll(src, 5, -1)), dim=1)).contiguous())
+        return sets
+
+    def cpu_rate(self, sd, n_chunks, threads):
+        import hgtcrn_oracle as ho
+        torch.set_num_threads(threads)
+        x = self.inputs(1, 1, 7)[0]
+        with torch.inference_mode():
+            ho.hgtcrn_forward(sd, x)
+            t0 = time.perf_counter()
+            for _ in range(n_chunks):
+                ho.hgtcrn_forward(sd, x)
+            dt = time.perf_counter() - t0
+        return n_chunks * self.chunk / self.sr / dt, dt
+
+    def kernel_work(self):
+        T = self.t_frames
+        # hg_wpe per window: 257 bins x (R: 666 x T complex MACs, CG: 6 x 36 x 36 x 2, prediction: 2 T x 36) ~ 8 flops per complex MAC
+        wpe_flops = 257 * 8 * (666 * T + 72 * T + 6 * 36 * 36 * 2 + 72 * T)
+        return _Work({"hg_wpe": (4 * 2 * 2 * 2 * T * 257, wpe_flops), "hg_iva": (4 * (2 * 2 * 2 * T * 257 + 2 * T * 257), 257 * 10 * 60 * T),
+                      "stft": (4 * 2 * (16128 + 514 * T), 2 * 2 * 514 * 512 * T), "istft": (4 * (514 * T + 16128), 2 * 514 * 512 * T)})
+
+
 class ZipenhWorkload:
     """ZipEnhancer 16 kHz (BASELINE.json configs[1]: 64 x 1 s chunks, fp32, one B200): dense encoder, four dual-path Zipformer2
     encoders (the middle two down-sampled x2 in time and frequency), mask + phase decoders; 161 frames x 101 sub-bands x 64."""
@@ -699,7 +757,7 @@ class ZipenhWorkload:
 
 
 WORKLOADS = {"gtcrn": GtcrnWorkload, "mbr": MbrWorkload, "mf2se": Mf2seWorkload, "mf2ss": Mf2ssWorkload, "mfgan": MfganWorkload,
-             "dfsmn": DfsmnWorkload, "ulunas": UlunasWorkload, "zipenh": ZipenhWorkload}
+             "dfsmn": DfsmnWorkload, "ulunas": UlunasWorkload, "zipenh": ZipenhWorkload, "hgtcrn": HgtcrnWorkload}
 
 
 class ClockSampler:
@@ -968,7 +1026,7 @@ def main():
     ap.add_argument("--sweep", action="store_true",
                     help="BASELINE.json's metric table in one JSON line: RTF and audio-s/s per model at batch 1 / 64 / 512 on one GPU "
                          "(device-resident and end to end through adn_run_host); --sweep-models / --sweep-batches narrow it")
-    ap.add_argument("--sweep-models", default="gtcrn,zipenh,mf2se,mbr,mfgan,mf2ss,dfsmn,ulunas")
+    ap.add_argument("--sweep-models", default="gtcrn,zipenh,mf2se,mbr,mfgan,mf2ss,dfsmn,ulunas,hgtcrn")
     ap.add_argument("--sweep-batches", default="1,64,512")
     ap.add_argument("--segments", default="", help="NxSs, e.g. 128x8s (BASELINE.json configs[3]): N segments of S seconds, folded on the host "
                                                    "into the model's fixed windows (stride = window, zero tail) -> --batch = N * ceil(S * sr / window)")

@@ -303,10 +303,13 @@ def main_ulunas():
 
 
 def main_hgtcrn():
-    """H-GTCRN fixtures (no restatement and no CUDA path yet): the reference `H_GTCRN_CUSTOM` (2-channel
+    """H-GTCRN fixtures: the reference `H_GTCRN_CUSTOM` (2-channel
     STFT -> WPE -> AuxIVA -> GTCRN_IVA -> ISTFT) executed on seeded default-init weights with randomised BatchNorm statistics;
     the RAW state_dict of `GTCRN_IVA` travels in the fixture (`sd/<key>`).  Stereo windows of 16128 samples (64 frames), F32 and
-    INT16; correlated channels (a delayed, attenuated copy plus independent noise), as a two-microphone pickup would give."""
+    INT16; correlated channels (a delayed, attenuated copy plus independent noise), as a two-microphone pickup would give.
+    The WPE and AuxIVA stage outputs of the executed reference (forward hooks; (2, 2, 257, 64) real / imaginary planes) travel
+    too: the six conjugate-gradient steps of the WPE solve amplify one-ulp differences by up to 1e5 in single bins, so the
+    oracle's later stages are pinned ON the reference's WPE output (tests/test_oracle_pinning.py)."""
     assert ref_loader.reference_available()
     L = 16128
     for dt in ("F32", "INT16"):
@@ -316,9 +319,16 @@ def main_hgtcrn():
         n = synth_audio(L, 98, batch=2)[:, 0]
         x = torch.stack((a, 0.7 * torch.roll(a, 3, dims=-1) + 0.3 * n), dim=1)           # (2 windows, 2 channels, L)
         xin = x if dt == "F32" else torch.round(x * 32767.0).to(torch.int16)
+        cap = {"wpe": [], "iva": []}
+        hooks = [w.wpe.register_forward_hook(lambda m, i, o: cap["wpe"].append(torch.stack(o, dim=0)[:, 0].clone())),
+                 w.iva.register_forward_hook(lambda m, i, o: cap["iva"].append(torch.stack(o, dim=0)[:, 0].clone()))]
         with torch.inference_mode():
             y = torch.cat([w(xin[i:i + 1].clone()) for i in range(2)], dim=0)
+        for h in hooks:
+            h.remove()
+        stage = {k: torch.stack(v, dim=0).numpy() for k, v in cap.items()}             # (window, re|im, mic, F, T)
         np.savez_compressed(GOLDEN / f"hgtcrn_{dt.lower()}_L{L}.npz", x=xin.numpy(), y=y.numpy(), seed=0,
+                            ref_wpe=stage["wpe"], ref_iva=stage["iva"],
                             **{f"sd/{k}": v.numpy() for k, v in raw.items()})
         print(f"hgtcrn {dt}: {tuple(xin.shape)} -> {tuple(y.shape)} max|y| {y.float().abs().max().item():.4f}")
 

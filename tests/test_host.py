@@ -457,3 +457,44 @@ def test_denoise_and_separate_with_resampled_io(in_sr, out_sr, win, out_len):
         full = np.concatenate([fn(a[k * win:(k + 1) * win].reshape(1, 1, -1)) for k in range(numw)], axis=-1).reshape(-1)
         want = full[int(round(400 * scale)):int(round(m * scale))]
         assert np.array_equal(sep[0], want) and np.array_equal(sep[1], want)
+
+
+def test_hgtcrn_packing_matches_oracle_fold():
+    """adn/hgtcrn_params.py: the ConvBlock-wrapper key names map onto GTCRN's packer, en_convs.0 has 18 input channels, the
+    decoder's GTConv blocks stay plain convolutions (no tap flip), and the folds equal the oracle's."""
+    import hgtcrn_oracle as ho
+    from adn import hgtcrn_params as hp
+
+    sd = ho.random_state_dict(3)
+    blob = hp.pack(sd, 256 * 20)
+    w0, b0 = ho._fold(sd, "encoder.en_convs.0")
+    assert np.array_equal(blob["enc_front_h"][:1440], w0[:, :, 0, :].permute(2, 1, 0).reshape(-1).numpy())
+    assert np.array_equal(blob["enc_front_h"][1440:1456], b0.numpy())
+    wd, bd = ho._fold(sd, "decoder.de_convs.0.depth_conv")
+    assert np.array_equal(blob["dec_gt.0"][400:544], wd[:, 0].reshape(-1).numpy())          # un-flipped taps
+    w2, b2 = ho._fold(sd, "decoder.de_convs.0.point_conv2")
+    assert np.array_equal(blob["dec_gt.0"][560:688], w2[:, :, 0, 0].T.reshape(-1).numpy())   # stored [c][o]
+    assert blob["istft.norm"].shape == (256 * 20,) and blob["stft.fwd"].shape == (514, 512)
+    md = hp.metadata(256 * 20, "INT16", "F32")
+    assert md["model_family"] == "h_gtcrn" and md["input_channels"] == "2" and md["output_channels"] == "1"
+    assert md["max_signal_length"] == "21" and md["feature_kind"] == "stft_wpe_auxiva" and md["cg_solve_iter"] == "6"
+    with pytest.raises(ValueError):
+        hp.metadata(1000)
+
+
+@pytest.mark.parametrize("n,pad", [(0, 5), (1, 4), (7, 5), (40, 13)])
+def test_reflect_tail_is_the_reference_context_pad(n, pad):
+    """chunker.tail_pad(mode='reflect') == `pad_audio_tail_with_context` of the un-folded H-GTCRN script
+    (H-GTCRN/Inference_H_GTCRN_ONNX.py:138-153): mirror about the last sample, one sample repeats, nothing -> zeros."""
+    from adn import chunker
+
+    a = (np.arange(2 * n, dtype=np.int16).reshape(2, n) * 3 - 7)
+    got = chunker.tail_pad(a, pad, "reflect")
+    assert got.shape == (2, n + pad) and got.dtype == a.dtype and np.array_equal(got[:, :n], a)
+    if n == 0:
+        assert not got.any()
+    elif n == 1:
+        assert np.array_equal(got[:, n:], np.repeat(a[:, -1:], pad, axis=-1))
+    else:
+        for k in range(pad):
+            assert np.array_equal(got[:, n + k], a[:, n - 2 - k])
