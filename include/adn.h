@@ -68,7 +68,7 @@ typedef struct {
 
 /* Replaces onnxruntime.InferenceSession(path, ...) (Inference_GTCRN_ONNX.py:213-214,237):
  * builds a model of desc["model_family"] (gtcrn | zipenhancer | mel_band_roformer | mossformer2_se |
- * mossformer2_ss | mossformergan_se | dfsmn | ulunas)
+ * mossformer2_ss | mossformergan_se | dfsmn | ulunas | h_gtcrn)
  * on CUDA device `device_id` from a host blob of `nfloats` fp32 values.  The keys are the reference's
  * metadata keys (audio_onnx_metadata.py:115-205) plus, for mossformer2_se, the optional
  * "matmul_dtype" = F32 (default: 3xTF32 tensor-core GEMMs, fp32-class) | BF16 (the layers' GEMMs on bf16
@@ -78,7 +78,9 @@ typedef struct {
  * at 44.1 kHz: the reference's 1.5 s fold window, Mel_Band_Roformer/Stereo/Export_MelBandRoformer.py:46-50) -- a longer
  * un-folded static length (Inference_MelBandRoformer_ONNX.py:301-313) is rejected at adn_create and must be folded on the
  * host (adn.chunker.denoise does); zipenhancer sequences (frames, sub-bands) of more than 256 positions run on the
- * slower one-thread-per-row attention path; every other family takes any window its STFT geometry allows. */
+ * slower one-thread-per-row attention path; h_gtcrn (two microphones in, one channel out: H-GTCRN/Export_H_GTCRN.py:1145-1152,
+ * input_channels = 2) takes windows of k * 256 >= 512 samples at 16 kHz and the reference's front-end constants (wpe_rt60 0.3,
+ * wpe_delay 2, wpe_iter 1, cg_solve_iter 6, iva_iter 10); every other family takes any window its STFT geometry allows. */
 adn_status adn_create(adn_model** out, const adn_desc* desc, const float* weights,
                       size_t nfloats, int device_id);
 
@@ -91,11 +93,12 @@ adn_status adn_io_info(const adn_model* m, adn_tensor_info* in, adn_tensor_info*
 
 /* Replaces session.run_with_iobinding(binding) for a batch of `batch` independent
  * (1,C,L) chunks resident on the device (…:209-210, 314-317).  d_in is (batch,C,L)
- * contiguous in the input dtype, d_outs[i] (i < n_out of adn_io_info) is (batch,C,L_out).
+ * contiguous in the input dtype, d_outs[i] (i < n_out of adn_io_info) is (batch,C_out,L_out) with the channel count
+ * adn_io_info reports for that output (h_gtcrn: C = 2, C_out = 1).
  * Asynchronous on `stream` (a cudaStream_t passed as void*).  On a non-default stream the launch sequence of a
  * (buffers, batch) combination seen before is replayed as one CUDA graph (captured on its second run; environment
  * ADN_GRAPHS=0 disables this); the legacy default stream always runs the kernels one by one.  Families: gtcrn,
- * zipenhancer, mel_band_roformer, mossformer2_se, mossformer2_ss, mossformergan_se, dfsmn, ulunas. */
+ * zipenhancer, mel_band_roformer, mossformer2_se, mossformer2_ss, mossformergan_se, dfsmn, ulunas, h_gtcrn. */
 adn_status adn_run(adn_model* m, const void* d_in, void* const* d_outs, int32_t batch,
                    void* stream);
 

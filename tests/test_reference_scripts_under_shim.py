@@ -1,7 +1,7 @@
 """CPU, build container only: the reference's UNMODIFIED inference scripts executed with `onnxruntime := adn.ort_shim`.
 
-`GTCRN/Inference_GTCRN_ONNX.py`, `ZipEnhancer/Inference_ZipEnhancer_ONNX.py` and
-`MossFormer2_SS_16K/Inference_MossFormer_SS_ONNX.py` are run as `__main__` from /root/reference, byte for byte, against a model
+`GTCRN/Inference_GTCRN_ONNX.py`, `ZipEnhancer/Inference_ZipEnhancer_ONNX.py`,
+`MossFormer2_SS_16K/Inference_MossFormer_SS_ONNX.py` and `H-GTCRN/Inference_H_GTCRN_ONNX.py` are run as `__main__` from /root/reference, byte for byte, against a model
 file written by `adn.export` into a temporary directory (passed as argv[1], the scripts' own override).  Everything the scripts
 touch on the ORT side -- SessionOptions / RunOptions attributes, OrtDevice, provider tables, the metadata sidecar session,
 `get_inputs()` / `_inputs_meta`, `OrtValue.ortvalue_from_numpy / update_inplace / numpy`, `io_binding`, `run_with_iobinding` --
@@ -34,16 +34,17 @@ class _OracleModel:
         from adn.model import IOInfo
 
         self.metadata, _, _ = modelfile.load(path)
-        self.fn, in_name, out_names, out_len = self.registry[Path(path).name]
+        self.fn, in_name, out_names, out_len, *rest = self.registry[Path(path).name]
+        self.in_channels = rest[0] if rest else 1
         code = {"F32": _lib.ADN_F32, "INT16": _lib.ADN_I16, "F16": _lib.ADN_F16}
 
-        def info(name, dtype, length):
+        def info(name, dtype, length, channels=1):
             t = _lib.TensorInfo()
-            t.name, t.dtype, t.channels, t.length = name.encode(), code[dtype], 1, length
+            t.name, t.dtype, t.channels, t.length = name.encode(), code[dtype], channels, length
             return IOInfo(t)
 
         md = self.metadata
-        self.input = info(in_name, md["input_audio_dtype"], int(md["input_audio_length"]))
+        self.input = info(in_name, md["input_audio_dtype"], int(md["input_audio_length"]), self.in_channels)
         self.outputs = [info(n, md["output_audio_dtype"], out_len) for n in out_names]
         self.calls = 0
 
@@ -53,9 +54,9 @@ class _OracleModel:
 
     def run_host_ptr(self, in_ptr, out_ptrs, batch):
         self.calls += 1
-        n = batch * self.input.length
+        n = batch * self.in_channels * self.input.length
         ct = {np.int16: ctypes.c_int16, np.float32: ctypes.c_float}[self.input.np_dtype]
-        x = np.ctypeslib.as_array((ct * n).from_address(in_ptr)).reshape(batch, 1, -1)
+        x = np.ctypeslib.as_array((ct * n).from_address(in_ptr)).reshape(batch, self.in_channels, -1)
         ys = self.fn(torch.from_numpy(x.copy()))
         ys = ys if isinstance(ys, tuple) else (ys,)
         for ptr, y, o in zip(out_ptrs, ys, self.outputs):
@@ -174,3 +175,28 @@ def test_mossformer2_ss_script(tmp_path, monkeypatch):
     for s, (name, (y, sr, subtype)) in enumerate(sorted(written.items())):
         want = np.concatenate([o[s].numpy().reshape(-1) for o in outs])[pad_head:n]
         assert sr == 16000 and np.array_equal(y, want), name
+
+
+def test_h_gtcrn_script(tmp_path, monkeypatch):
+    """Two microphones in, one channel out: the script sizes its buffers from the session's channel counts (:306-309), pads the
+    tail by reflection (`pad_audio_tail_with_context`, :138-153) and concatenates the windows (:369-371)."""
+    import hgtcrn_oracle as ho
+    from adn import chunker, export
+
+    sd = ho.random_state_dict(0)
+    W = 256 * 24
+    export.export_hgtcrn(sd, tmp_path / "H_GTCRN.onnx", W, "INT16", "INT16")
+    assert (tmp_path / "H_GTCRN_Metadata.onnx").exists()
+    fn = lambda x: ho.hgtcrn_forward_batch(sd, x, "INT16", "INT16")
+    _OracleModel.registry["H_GTCRN.onnx"] = (fn, "noisy_audio", ["denoised_audio"], W, 2)
+    rng = np.random.default_rng(1)
+    n = 2 * W + 1234
+    src = rng.integers(-6000, 6000, size=n).astype(np.int16)
+    stereo = np.stack((src, (0.7 * np.roll(src, 4)).astype(np.int16) + rng.integers(-2000, 2000, size=n).astype(np.int16)), axis=0)   # (2, n)
+    written, ns = _run_script(REF / "H-GTCRN" / "Inference_H_GTCRN_ONNX.py", tmp_path, stereo.T.reshape(-1).copy(), monkeypatch)   # interleaved, as pydub gives it
+    y, sr, subtype = written["denoised.wav"]
+    assert sr == 16000 and subtype == "PCM_16" and y.dtype == np.int16 and y.shape == (n,)
+    wins, stride = chunker.split(stereo, W, W, tail="reflect")
+    assert stride == W and wins.shape == (3, 2, W)
+    want = fn(torch.from_numpy(wins)).numpy().reshape(-1)[:n]
+    assert np.array_equal(y, want)
