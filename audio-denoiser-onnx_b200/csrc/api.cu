@@ -1066,6 +1066,16 @@ struct adn_stft {
   size_t xp_cap = 0;
   float* d_fm = nullptr;   // frame-major padded spectrum for the inverse
   size_t fm_cap = 0;
+  // opt-in tensor-core path (adn_stft_enable_tc; model families only -- the public operators stay on the exact fp32 GEMM):
+  // windowed-DFT / overlap-add weights as zero-padded tf32 hi | lo planes, plans keyed by (buffers, rows)
+  bool tc_on = false;
+  int sms = 148;
+  float* d_wf_hl = nullptr; int wf_npad = 0, wf_kpad = 0, wf_bn = 0;
+  float* d_wo_hl = nullptr; int wo_npad = 0, wo_kpad = 0, wo_bn = 0;
+  struct TcSlot { const float* in = nullptr; float* out = nullptr; int rows = 0, frames = 0; tc::TcPlan plan; tc::TcArgs args{}; bool valid = false; };
+  TcSlot fwd_slot, inv_slot;
+  std::vector<float> h_ola;   // kept for the lazily built planes
+  std::vector<float> h_fwd;
 };
 
 namespace {
@@ -1112,6 +1122,8 @@ adn_status adn_stft_create(adn_stft** out, const adn_stft_geom* g, const float* 
   s->T = n_frames;
   const size_t nb = (size_t)s->p.rows2f * g->nfft;
   std::vector<float> ola = build_ola_weight(inv_basis, g->nfft, g->hop, s->p.ld, s->p.R);
+  s->h_ola = ola;
+  s->h_fwd.assign(fwd_basis, fwd_basis + nb);
   const int lout = s->p.out_len(n_frames);
   bool ok = cudaMalloc((void**)&s->d_fwd, nb * 4) == cudaSuccess &&
             cudaMalloc((void**)&s->d_ola, ola.size() * 4) == cudaSuccess &&
@@ -1133,6 +1145,7 @@ void adn_stft_destroy(adn_stft* s) {
   cudaSetDevice(s->device);
   cudaDeviceSynchronize();
   cudaFree(s->d_fwd); cudaFree(s->d_ola); cudaFree(s->d_norm); cudaFree(s->d_xp); cudaFree(s->d_fm);
+  cudaFree(s->d_wf_hl); cudaFree(s->d_wo_hl);
   delete s;
 }
 
@@ -1178,7 +1191,69 @@ adn_status adn_stft_forward(adn_stft* s, const float* d_x, float* d_spec, int32_
 int adn_stft_ld(const adn_stft* s) { return s->p.ld; }
 int adn_stft_pad_frames(const adn_stft* s) { return s->p.pad_frames(); }
 int adn_stft_padded_len(const adn_stft* s, int length) { return s->p.padded_len(length); }
+namespace {
+__global__ void istft_norm_kernel(float* __restrict__ y, const float* __restrict__ norm, int out_len, long long n, int mul) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float nv = __ldg(norm + (int)(i % out_len));
+  y[i] = mul ? y[i] * nv : y[i] / nv;
+}
+}  // namespace
+
+// Tensor-core variants of the frame-major transforms (3xTF32 on the fp32-A GEMM of gemm_tc.cu: the padded waveform / the
+// zero-framed spectrum are the A operand as they lie in memory, overlapping rows through the TMA row stride).  The inverse needs
+// the overlap-added block rows to tile the output exactly (no centre pad, or a centre pad of whole hops) and `slack` floats of
+// finite memory behind the spectrum buffer (the K window of the last rows runs past it; those weights are zero).
+int adn_stft_enable_tc(adn_stft* s, int sms) {
+  const StftPlan& p = s->p;
+  if (p.hop % 4 || p.nfft % 32 || (p.center && p.half % p.hop)) return 0;
+  std::string err;
+  s->sms = sms;
+  s->wf_bn = choose_bn(p.rows2f);
+  if (s->wf_bn == 176) s->wf_bn = 128;             // (the 176-wide tile is not instantiated for the deep-K converter split)
+  s->wf_npad = (p.rows2f + s->wf_bn - 1) / s->wf_bn * s->wf_bn;
+  s->wf_kpad = round_up(p.nfft, 32);
+  s->wo_bn = choose_bn(p.hop);
+  s->wo_npad = (p.hop + s->wo_bn - 1) / s->wo_bn * s->wo_bn;
+  s->wo_kpad = round_up(p.R * p.ld, 32);
+  std::vector<float> wf = split_pad_weight(s->h_fwd.data(), p.rows2f, p.nfft, s->wf_npad, s->wf_kpad);
+  std::vector<float> wo = split_pad_weight(s->h_ola.data(), p.hop, p.R * p.ld, s->wo_npad, s->wo_kpad);
+  if (cudaMalloc((void**)&s->d_wf_hl, wf.size() * 4) != cudaSuccess || cudaMalloc((void**)&s->d_wo_hl, wo.size() * 4) != cudaSuccess ||
+      cudaMemcpy(s->d_wf_hl, wf.data(), wf.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(s->d_wo_hl, wo.data(), wo.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+    return 0;
+  s->tc_on = true;
+  return s->wo_kpad;                               // the slack (floats) the inverse needs behind its input buffer
+}
+
 adn_status adn_stft_forward_fm(adn_stft* s, const float* d_xp, float* d_spec_fm, int rows, int n_frames, int Lp, cudaStream_t st) {
+  const StftPlan& p = s->p;
+  if (s->tc_on && Lp % 4 == 0 && p.ld % 4 == 0) {
+    adn_stft::TcSlot& e = s->fwd_slot;
+    if (!(e.valid && e.in == d_xp && e.out == d_spec_fm && e.rows == rows && e.frames == n_frames)) {
+      std::string err;
+      e.valid = false;
+      e.plan = tc::TcPlan{};
+      e.plan.bn = s->wf_bn; e.plan.a_f32 = true;
+      const int bt = n_frames >= 128 ? 128 : n_frames;
+      const size_t plane = (size_t)s->wf_npad * s->wf_kpad;
+      if (tc::make_row_map(&e.plan.map_a_hi, d_xp, p.nfft, n_frames, p.hop, rows, Lp, bt, 1, err) &&
+          tc::make_weight_map(&e.plan.map_w_hi, s->d_wf_hl, s->wf_kpad, s->wf_npad, s->wf_bn, err) &&
+          tc::make_weight_map(&e.plan.map_w_lo, s->d_wf_hl + plane, s->wf_kpad, s->wf_npad, s->wf_bn, err) &&
+          tc::make_store_map(&e.plan.map_c, d_spec_fm, p.rows2f, n_frames, p.ld, rows, (long long)n_frames * p.ld, err)) {
+        e.plan.map_a_lo = e.plan.map_a_hi; e.plan.map_w2_hi = e.plan.map_w_hi; e.plan.map_w2_lo = e.plan.map_w_lo;
+        tc::TcArgs& a = e.args;
+        a = tc::TcArgs{};
+        a.bb = 1; a.bt = bt; a.tiles_per_chunk = (n_frames + 127) / 128; a.t0 = 0;
+        a.B = rows; a.TM = n_frames; a.N = p.rows2f; a.K = p.nfft;
+        a.m_tiles = rows * a.tiles_per_chunk;
+        a.C = d_spec_fm; a.ldc = p.ld;
+        e.in = d_xp; e.out = d_spec_fm; e.rows = rows; e.frames = n_frames; e.valid = true;
+      }
+    }
+    if (e.valid && tc::launch(e.plan, e.args, EPI_LIN, s->sms, st) == cudaSuccess) return ADN_OK;
+    cudaGetLastError();
+  }
   GemmArgs g;
   fill_stft_gemm(g, s->p, d_xp, Lp, s->d_fwd, rows, n_frames, d_spec_fm, (long long)n_frames * s->p.ld, s->p.ld, 1);
   launch_gemm_ffma(g, EPI_STORE, st);
@@ -1186,6 +1261,39 @@ adn_status adn_stft_forward_fm(adn_stft* s, const float* d_xp, float* d_spec_fm,
 }
 adn_status adn_stft_inverse_fm(adn_stft* s, const float* d_fm_padded, float* d_y, int rows, int n_frames, cudaStream_t st) {
   if (n_frames != s->T) return ADN_ERR_INVALID;
+  const StftPlan& p = s->p;
+  const int lo = p.blk_lo(), hi = p.blk_hi(n_frames), TM = hi - lo + 1, out_len = p.out_len(n_frames);
+  if (s->tc_on && (long long)TM * p.hop == out_len && (p.center ? p.half == lo * p.hop : lo == 0) && out_len % 4 == 0) {
+    adn_stft::TcSlot& e = s->inv_slot;
+    if (!(e.valid && e.in == d_fm_padded && e.out == d_y && e.rows == rows && e.frames == n_frames)) {
+      std::string err;
+      e.valid = false;
+      e.plan = tc::TcPlan{};
+      e.plan.bn = s->wo_bn; e.plan.a_f32 = true;
+      const int frows = n_frames + 2 * p.pad_frames();
+      const int bt = TM >= 128 ? 128 : TM;
+      const size_t plane = (size_t)s->wo_npad * s->wo_kpad;
+      if (tc::make_row_map(&e.plan.map_a_hi, d_fm_padded, s->wo_kpad, frows, p.ld, rows, (long long)frows * p.ld, bt, 1, err) &&
+          tc::make_weight_map(&e.plan.map_w_hi, s->d_wo_hl, s->wo_kpad, s->wo_npad, s->wo_bn, err) &&
+          tc::make_weight_map(&e.plan.map_w_lo, s->d_wo_hl + plane, s->wo_kpad, s->wo_npad, s->wo_bn, err) &&
+          tc::make_store_map(&e.plan.map_c, d_y, p.hop, TM, p.hop, rows, out_len, err)) {
+        e.plan.map_a_lo = e.plan.map_a_hi; e.plan.map_w2_hi = e.plan.map_w_hi; e.plan.map_w2_lo = e.plan.map_w_lo;
+        tc::TcArgs& a = e.args;
+        a = tc::TcArgs{};
+        a.bb = 1; a.bt = bt; a.tiles_per_chunk = (TM + 127) / 128; a.t0 = lo;
+        a.B = rows; a.TM = TM; a.N = p.hop; a.K = p.R * p.ld;
+        a.m_tiles = rows * a.tiles_per_chunk;
+        a.C = d_y; a.ldc = p.hop;
+        e.in = d_fm_padded; e.out = d_y; e.rows = rows; e.frames = n_frames; e.valid = true;
+      }
+    }
+    if (e.valid && tc::launch(e.plan, e.args, EPI_LIN, s->sms, st) == cudaSuccess) {
+      const long long n = (long long)rows * out_len;
+      istft_norm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_y, s->d_norm, out_len, n, p.norm_mul);
+      return cudaGetLastError() == cudaSuccess ? ADN_OK : ADN_ERR_CUDA;
+    }
+    cudaGetLastError();
+  }
   GemmArgs g;
   fill_istft_gemm(g, s->p, d_fm_padded, s->d_ola, s->d_norm, rows, n_frames, d_y, ADN_F32);
   launch_gemm_ffma(g, EPI_ISTFT, st);
@@ -1204,7 +1312,7 @@ adn_status adn_stft_inverse(adn_stft* s, const float* d_spec, float* d_y, int32_
   ADN_CUDA_TRY(cudaSetDevice(s->device), err);
   cudaStream_t st = (cudaStream_t)stream;
   const int T = n_frames, pad = s->p.pad_frames(), ld = s->p.ld;
-  size_t need = (size_t)batch * (T + 2 * pad) * ld;
+  size_t need = (size_t)batch * (T + 2 * pad) * ld + (s->tc_on ? (size_t)s->wo_kpad : 0);   // + the K-window slack of the tensor-core path
   if (need > s->fm_cap) {
     cudaDeviceSynchronize();
     adn_note_free();
@@ -1219,10 +1327,7 @@ adn_status adn_stft_inverse(adn_stft* s, const float* d_spec, float* d_y, int32_
   cudaMemsetAsync(s->d_fm, 0, need * 4, st);
   dim3 grid((T + 31) / 32, (s->p.rows2f + 31) / 32, batch), block(32, 8);
   pack_to_frame_major_kernel<<<grid, block, 0, st>>>(d_spec, s->d_fm, s->p.rows2f, T, ld, pad);
-  GemmArgs g;
-  fill_istft_gemm(g, s->p, s->d_fm, s->d_ola, s->d_norm, batch, T, d_y, ADN_F32);
-  launch_gemm_ffma(g, EPI_ISTFT, st);
-  if (cudaGetLastError() != cudaSuccess) {
+  if (adn_stft_inverse_fm(s, s->d_fm, d_y, batch, T, st) != ADN_OK) {
     set_global_error("adn_stft_inverse: launch failed");
     return ADN_ERR_CUDA;
   }

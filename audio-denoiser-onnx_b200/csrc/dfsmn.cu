@@ -6,6 +6,7 @@
 
 #include "common.cuh"
 #include "gan_exec.cuh"
+#include "model_impl.h"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -123,6 +124,7 @@ class Model : public ModelImpl {
       err = std::string("dfsmn: ") + adn_last_error(nullptr);
       return false;
     }
+    { const char* e = getenv("ADN_STFT_TC"); if (!(e && e[0] == '0')) adn_stft_enable_tc(stft, sms); }   // ISTFT (40 % of the step on the exact GEMM) on tcgen05
     return true;
   }
   bool ensure(int B) {

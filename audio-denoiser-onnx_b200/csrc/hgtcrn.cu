@@ -4,7 +4,7 @@
 //   hg_prep      cast, 1/32768, ONE DC mean over both microphones of a window (:957-967), reflect centre pad
 //   stft         windowed-DFT GEMM (periodic hann, 512 / 256), rows = (window, microphone), frame-major (rows, T, 520)
 //   hg_eps       per-window WPE floor 1e-3 * mean_f max_{m,t} |X|^2 (:699-700)
-//   hg_wpe       one CTA per (window, bin): 36 x 36 weighted correlation of the delay bank, 36 x 2 cross term, SIX fixed
+//   hg_wpe       one CTA per (window, bin): 36 x 36 weighted correlation of the delay bank (2 x 2 register blocks), 36 x 2 cross term, SIX fixed
 //                conjugate-gradient steps per right-hand side, prediction subtracted (:637-753, :499-555)
 //   hg_iva       one CTA per window, one thread per bin: ten AuxIVA sweeps (source activity from ALL bins through a block
 //                reduction, weighted covariances, Cramer 2 x 2 solves, normalisation), projection back on microphone 0,
@@ -117,7 +117,8 @@ __global__ void __launch_bounds__(288) eps_kernel(const float* __restrict__ spec
 
 // ---------------------------------------------------------------------------------- WPE
 // dynamic shared memory: X re / im (2 x T each), 1 / lambda (T)
-__global__ void __launch_bounds__(128) wpe_kernel(const float* __restrict__ spec, const float* __restrict__ epsb,
+constexpr int WPE_THREADS = 192;      // >= 171 = the 2 x 2 blocks of R's lower triangle: one block per thread, one round
+__global__ void __launch_bounds__(WPE_THREADS) wpe_kernel(const float* __restrict__ spec, const float* __restrict__ epsb,
                                                    float* __restrict__ out, int T) {
   extern __shared__ float wsm[];
   float* xr = wsm;                 // [2][T]
@@ -130,39 +131,50 @@ __global__ void __launch_bounds__(128) wpe_kernel(const float* __restrict__ spec
   const int f = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const float eps = epsb[b];
   const float* row0 = spec + ((long long)b * 2) * T * SPEC_LD;
-  for (int i = tid; i < 2 * T; i += 128) {
+  for (int i = tid; i < 2 * T; i += WPE_THREADS) {
     const int m = i / T, t = i - m * T;
     const float* r = row0 + ((long long)m * T + t) * SPEC_LD;
     xr[i] = r[f];
     xi[i] = r[FB + f];
   }
   __syncthreads();
-  for (int t = tid; t < T; t += 128) {
+  for (int t = tid; t < T; t += WPE_THREADS) {
     float p = ((xr[t] * xr[t] + xi[t] * xi[t]) + (xr[T + t] * xr[T + t] + xi[T + t] * xi[T + t])) * 0.5f;   // mean over the two microphones
     p = (p < eps) ? eps : p;
     il[t] = 1.0f / p;
   }
   __syncthreads();
   // unknown u = l * 2 + m is microphone m delayed by DELAY + l frames
-  // R[i][j] = sum_t Xd_i conj(Xd_j) / lambda  (lower triangle computed, mirrored), + eps on the diagonal
-  for (int e = tid; e < NU * (NU + 1) / 2; e += 128) {
-    int i = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
-    while (i * (i + 1) / 2 > e) --i;
-    while ((i + 1) * (i + 2) / 2 <= e) ++i;
-    const int j = e - i * (i + 1) / 2;
-    const int si = DELAY + (i >> 1), sj = DELAY + (j >> 1);
-    const float* ar = xr + (i & 1) * T; const float* ai = xi + (i & 1) * T;
-    const float* br = xr + (j & 1) * T; const float* bi = xi + (j & 1) * T;
-    float re = 0.f, im = 0.f;
-    for (int t = si; t < T; ++t) {               // si >= sj: both delayed samples exist from t = si on
+  // R[i][j] = sum_t Xd_i conj(Xd_j) / lambda, + eps on the diagonal.  A work item is the 2 x 2 block of a tap pair (l >= l'):
+  // its four entries share the eight delayed samples and the weight of every frame (9 shared-memory loads per 16 FMAs
+  // instead of 20); the lower triangle is computed and mirrored, the summation order per entry is frame order.
+  for (int e = tid; e < TAPS * (TAPS + 1) / 2; e += WPE_THREADS) {
+    int bi = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
+    while (bi * (bi + 1) / 2 > e) --bi;
+    while ((bi + 1) * (bi + 2) / 2 <= e) ++bi;
+    const int bj = e - bi * (bi + 1) / 2;
+    const int si = DELAY + bi, sj = DELAY + bj;
+    float re[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, im[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    for (int t = si; t < T; ++t) {                 // si >= sj: both delayed samples exist from t = si on
       const float w = il[t];
-      const float a_r = ar[t - si] * w, a_i = ai[t - si] * w;
-      const float b_r = br[t - sj], b_i = bi[t - sj];
-      re = fmaf(a_r, b_r, fmaf(a_i, b_i, re));
-      im = fmaf(a_i, b_r, fmaf(-a_r, b_i, im));
+      const float a_r[2] = {xr[t - si] * w, xr[T + t - si] * w}, a_i[2] = {xi[t - si] * w, xi[T + t - si] * w};
+      const float b_r[2] = {xr[t - sj], xr[T + t - sj]}, b_i[2] = {xi[t - sj], xi[T + t - sj]};
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int mj = 0; mj < 2; ++mj) {
+          re[mi][mj] = fmaf(a_r[mi], b_r[mj], fmaf(a_i[mi], b_i[mj], re[mi][mj]));
+          im[mi][mj] = fmaf(a_i[mi], b_r[mj], fmaf(-a_r[mi], b_i[mj], im[mi][mj]));
+        }
     }
-    if (i == j) { Rr[i][i] = re + eps; Ri[i][i] = im; }
-    else { Rr[i][j] = re; Ri[i][j] = im; Rr[j][i] = re; Ri[j][i] = -im; }
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int mj = 0; mj < 2; ++mj) {
+        const int i = 2 * bi + mi, j = 2 * bj + mj;
+        if (i == j) { Rr[i][i] = re[mi][mj] + eps; Ri[i][i] = im[mi][mj]; }
+        else if (i > j) { Rr[i][j] = re[mi][mj]; Ri[i][j] = im[mi][mj]; Rr[j][i] = re[mi][mj]; Ri[j][i] = -im[mi][mj]; }
+      }
   }
   // P[i][c] = sum_t Xd_i conj(X_c) / lambda
   if (tid < NU * 2) {
@@ -234,7 +246,7 @@ __global__ void __launch_bounds__(128) wpe_kernel(const float* __restrict__ spec
     __syncthreads();
   }
   // Y_m(t) = X_m(t) - sum_u conj(G[u][m]) Xd_u(t)
-  for (int o = tid; o < 2 * T; o += 128) {
+  for (int o = tid; o < 2 * T; o += WPE_THREADS) {
     const int m = o / T, t = o - m * T;
     float pr = 0.f, pi = 0.f;
     for (int u = 0; u < NU; ++u) {
@@ -511,7 +523,7 @@ class Model : public ModelImpl {
  public:
   int device = 0, sms = 148;
   int in_dtype = ADN_F32, out_dtype = ADN_F32;
-  int L = 0, T = 0, Lp = 0, pad = 0;
+  int L = 0, T = 0, Lp = 0, pad = 0, enh_slack = 0;
   float* d_blob = nullptr;
   std::map<std::string, TensorRef> index;
   gtcrn::Weights W;
@@ -642,6 +654,7 @@ class Model : public ModelImpl {
     Lp = adn_stft_padded_len(stft, L);
     pad = adn_stft_pad_frames(stft);
     if (adn_stft_ld(stft) != SPEC_LD) { err = "h_gtcrn: unexpected spectrum row stride"; return false; }
+    { const char* e = getenv("ADN_STFT_TC"); if (!(e && e[0] == '0')) enh_slack = adn_stft_enable_tc(stft, sms); }   // STFT / ISTFT on tcgen05 (3xTF32)
     return true;
   }
   bool ensure(int B) {
@@ -659,7 +672,7 @@ class Model : public ModelImpl {
     ok = ok && (buf.h1 = dalloc(b * t * 8 * E1_F)) && (buf.zt = dalloc(b * t * 8)) && (buf.at = dalloc(b * t * 8)) &&
          (buf.tgi = dalloc(b * t * 48)) && (buf.thid = dalloc(b * t * 16)) && (buf.gi = dalloc(b * t * 3 * FRAME16)) &&
          (buf.xa = dalloc(b * t * FRAME16)) && (buf.xb = dalloc(b * t * FRAME16)) && (buf.inter = dalloc(b * t * FRAME16)) &&
-         (buf.enh = dalloc(b * (t + 2 * pad) * SPEC_LD, true));
+         (buf.enh = dalloc(b * (t + 2 * pad) * SPEC_LD + enh_slack, true));
     if (!ok) return false;
     buf.xp = xp; buf.spec = spec;
     buf.xp_hi = buf.xp_lo = buf.enh_hi = buf.enh_lo = nullptr;
@@ -703,7 +716,7 @@ class Model : public ModelImpl {
       const size_t sm = (size_t)5 * T * sizeof(float);
       if (sm > 48 * 1024 - 24 * 1024 && adn_first_use_on_device(configured))
         cudaFuncSetAttribute(wpe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      wpe_kernel<<<dim3(FB, B), 128, sm, st>>>(spec, eps, wpe, T);
+      wpe_kernel<<<dim3(FB, B), WPE_THREADS, sm, st>>>(spec, eps, wpe, T);
       HG_TICK("hg_wpe");
     }
     {

@@ -67,5 +67,9 @@ ModelImpl* hgtcrn_create(const std::map<std::string, std::string>& meta, const s
 int adn_stft_ld(const adn_stft* s);
 int adn_stft_pad_frames(const adn_stft* s);
 int adn_stft_padded_len(const adn_stft* s, int length);
+// opt-in 3xTF32 tensor-core path of the frame-major transforms (and of adn_stft_inverse, which packs and then runs the
+// frame-major inverse); returns the number of floats of finite slack the inverse needs behind its input buffer, 0 if the
+// geometry does not qualify (the exact fp32 GEMM stays in use)
+int adn_stft_enable_tc(adn_stft* s, int sms);
 adn_status adn_stft_forward_fm(adn_stft* s, const float* d_xp, float* d_spec_fm, int rows, int n_frames, int Lp, cudaStream_t st);
 adn_status adn_stft_inverse_fm(adn_stft* s, const float* d_fm_padded, float* d_y, int rows, int n_frames, cudaStream_t st);
