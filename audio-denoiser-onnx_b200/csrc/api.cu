@@ -1210,7 +1210,7 @@ int adn_stft_enable_tc(adn_stft* s, int sms) {
   std::string err;
   s->sms = sms;
   s->wf_bn = choose_bn(p.rows2f);
-  if (s->wf_bn == 176) s->wf_bn = 128;             // (the 176-wide tile is not instantiated for the deep-K converter split)
+  if (s->wf_bn == 176) s->wf_bn = 128;             // TMA-store epilogue: N tiles are whole 32-column boxes (gemm_tc.cu launch_bn)
   s->wf_npad = (p.rows2f + s->wf_bn - 1) / s->wf_bn * s->wf_bn;
   s->wf_kpad = round_up(p.nfft, 32);
   s->wo_bn = choose_bn(p.hop);

@@ -775,8 +775,10 @@ static cudaError_t launch_bn(const TcPlan& p, const TcArgs& a, int epi, int sms,
   if (p.bf16) return epi == EPI_LIN ? launch_t<BN, EPI_LIN, true>(p, a, sms, st) : cudaErrorInvalidValue;
   if (p.a_f32) {
     if (epi != EPI_LIN) return cudaErrorInvalidValue;
-    // (the 176-wide tile stays on the 16-warp epilogue: its deep-K split gave wrong results in the H-GTCRN STFT, 514 x 512)
-    if (BN > 64 && BN != 176 && a.K >= 512 && a.taps == 0) return launch_t<BN, EPI_LIN, false, true, true>(p, a, sms, st);
+    // the TMA-store epilogue writes 32-column boxes: a tile width that is not a multiple of 32 (176) would spill its last box
+    // into the next N tile's columns, so it is only usable when ONE tile covers N
+    if (BN % 32 && a.N > BN) return cudaErrorInvalidValue;
+    if (BN > 64 && a.K >= 512 && a.taps == 0) return launch_t<BN, EPI_LIN, false, true, true>(p, a, sms, st);
     return launch_t<BN, EPI_LIN, false, true>(p, a, sms, st);
   }
   if (epi == EPI_STORE) return launch_t<BN, EPI_STORE, false>(p, a, sms, st);
