@@ -18,6 +18,7 @@
 #include "model_impl.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -345,6 +346,168 @@ attention2_kernel(const float* __restrict__ qkvg, int ldq, const float* __restri
       }
       *reinterpret_cast<float4*>(ao_hi + o) = make_float4(h[0], h[1], h[2], h[3]);
       *reinterpret_cast<float4*>(ao_lo + o) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// attention3: attention2 with both products on the warp-level tensor cores -- mma.sync m16n8k8 (tf32, fp32 accumulate) with
+// the 3xTF32 split done in registers on fp32 fragments (hi = low 13 mantissa bits cleared, lo = x - hi; hi*hi + hi*lo + lo*hi).
+//   smem: Qt[64][np] | Kt[64][np] | V[np][72] | S[n][np+1] | rinv[n]      np = n rounded up to 8 (mod 16)
+// np = 8 or 24 (mod 32) makes the Q^T / K^T fragment loads conflict-free (bank = np * (lane & 3) + (lane >> 2)), the 72-float V
+// rows do the same for the value fragments; key columns n .. np-1 of the softmax rows are zeroed so the padded K steps add nothing.
+// A warp task is (16 query rows) x (16 keys) in the score product and (16 query rows) x (8 value columns) in the value product.
+// ---------------------------------------------------------------------------------
+__host__ __device__ inline int att3_np(int n) { return ((n + 7) / 16) * 16 + 8; }
+__host__ __device__ inline size_t att3_smem_floats(int n) {
+  const int np = att3_np(n);
+  size_t s_region = (size_t)n * (np + 1);
+  const size_t tmp = (size_t)2 * n * 65;
+  if (tmp > s_region) s_region = tmp;
+  return (size_t)2 * 64 * np + (size_t)np * 72 + s_region + (size_t)((n + 3) & ~3) + 8;
+}
+__device__ __forceinline__ void mbr_mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split3(float x, uint32_t& h, uint32_t& l) {
+  h = __float_as_uint(x) & 0xFFFFE000u;
+  l = __float_as_uint(x - __uint_as_float(h));
+}
+
+__global__ void __launch_bounds__(1024)
+attention3_kernel(const float* __restrict__ qkvg, int ldq, const float* __restrict__ rcos,
+                  const float* __restrict__ rsin, float* __restrict__ ao_hi, float* __restrict__ ao_lo, int n,
+                  long long stride, int freq_mode, int heads) {
+  extern __shared__ __align__(16) float sm3[];
+  const int np = att3_np(n), ns = np + 1;
+  float* Qt = sm3;                               // [64][np]
+  float* Kt = Qt + 64 * np;                      // [64][np]
+  float* Vs = Kt + 64 * np;                      // [np][72]
+  float* S = Vs + (size_t)np * 72;               // [n][ns]   (first used as tq[n][65] | tk[n][65])
+  size_t s_region = (size_t)n * ns;
+  if ((size_t)2 * n * 65 > s_region) s_region = (size_t)2 * n * 65;
+  float* rinv = S + ((s_region + 3) & ~(size_t)3);   // [n]  gate / softmax sum
+  float* tq = S;
+  float* tk = S + (size_t)n * 65;
+  const int q = blockIdx.x, head = blockIdx.y, tid = threadIdx.x;
+  const int NT = blockDim.x, warp = tid >> 5, lane = tid & 31, NW = NT >> 5;
+  const int gq = lane >> 2, tq4 = lane & 3;
+  const int di = heads * DHEAD;
+  const long long base = freq_mode ? (long long)q : (long long)q * n;
+
+  // phase 0a: coalesced row loads, rotary on q,k
+  for (int i = tid; i < np * 32; i += NT) {
+    const int s = i >> 5, p = i & 31;
+    if (s >= n) { *reinterpret_cast<float2*>(Vs + s * 72 + 2 * p) = make_float2(0.f, 0.f); continue; }
+    const float* row = qkvg + (base + (long long)s * stride) * ldq + head * DHEAD;
+    const float2 qq = *reinterpret_cast<const float2*>(row + 2 * p);
+    const float2 kk = *reinterpret_cast<const float2*>(row + di + 2 * p);
+    const float2 vv = *reinterpret_cast<const float2*>(row + 2 * di + 2 * p);
+    const float2 c = *reinterpret_cast<const float2*>(rcos + s * DHEAD + 2 * p);
+    const float2 sn = *reinterpret_cast<const float2*>(rsin + s * DHEAD + 2 * p);
+    tq[s * 65 + 2 * p] = qq.x * c.x + qq.y * sn.x;
+    tq[s * 65 + 2 * p + 1] = qq.y * c.y + qq.x * sn.y;
+    tk[s * 65 + 2 * p] = kk.x * c.x + kk.y * sn.x;
+    tk[s * 65 + 2 * p + 1] = kk.y * c.y + kk.x * sn.y;
+    *reinterpret_cast<float2*>(Vs + s * 72 + 2 * p) = vv;
+  }
+  __syncthreads();
+  // phase 0b: transpose to [d][s] (zero the padded columns)
+  for (int i = tid; i < 64 * np; i += NT) {
+    const int d = i / np, s = i - d * np;
+    Qt[i] = s < n ? tq[s * 65 + d] : 0.f;
+    Kt[i] = s < n ? tk[s * 65 + d] : 0.f;
+  }
+  __syncthreads();
+
+  // phase 1: S = Q K^T
+  const int MT = (n + 15) >> 4, NG = (np + 15) >> 4;
+  for (int task = warp; task < MT * NG; task += NW) {
+    const int i0 = (task / NG) * 16, j0 = (task % NG) * 16;
+    const bool two = j0 + 8 < np;
+    float acc[2][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+#pragma unroll
+    for (int k8 = 0; k8 < 64; k8 += 8) {
+      const float* qa = Qt + (k8 + tq4) * np + i0 + gq;
+      uint32_t ah[4], al[4];
+      split3(qa[0], ah[0], al[0]); split3(qa[8], ah[1], al[1]);
+      split3(qa[4 * np], ah[2], al[2]); split3(qa[4 * np + 8], ah[3], al[3]);
+      const float* kb = Kt + (k8 + tq4) * np + j0 + gq;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !two) break;
+        uint32_t bh0, bl0, bh1, bl1;
+        split3(kb[8 * h], bh0, bl0); split3(kb[4 * np + 8 * h], bh1, bl1);
+        mbr_mma_tf32(acc[h], al, bh0, bh1);
+        mbr_mma_tf32(acc[h], ah, bl0, bl1);
+        mbr_mma_tf32(acc[h], ah, bh0, bh1);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = i0 + gq + (r >> 1) * 8, j = j0 + 8 * h + 2 * tq4 + (r & 1);
+        if (i < n && j < n) S[i * ns + j] = acc[h][r];
+      }
+  }
+  __syncthreads();
+
+  // phase 2: row softmax (unnormalised exp in place; gate / sum kept per row; padded key columns zeroed)
+  for (int i = warp; i < n; i += NW) {
+    float* sr = S + i * ns;
+    float mx = -INFINITY;
+    for (int j = lane; j < n; j += 32) mx = fmaxf(mx, sr[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < np; j += 32) {
+      const float e = j < n ? expf(sr[j] - mx) : 0.f;
+      sr[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) {
+      const long long row = base + (long long)i * stride;
+      rinv[i] = adn_sigmoid(__ldg(qkvg + row * ldq + 3 * di + head)) / sum;
+    }
+  }
+  __syncthreads();
+
+  // phase 3: O = P V, scaled by gate / sum, written as tf32 planes
+  for (int task = warp; task < MT * 8; task += NW) {
+    const int i0 = (task >> 3) * 16, d0 = (task & 7) * 8;
+    const int ra = min(i0 + gq, n - 1), rb = min(i0 + gq + 8, n - 1);
+    const float* pa = S + (size_t)ra * ns + tq4;
+    const float* pb = S + (size_t)rb * ns + tq4;
+    const float* vb = Vs + tq4 * 72 + d0 + gq;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int j8 = 0; j8 < np; j8 += 8) {
+      uint32_t ah[4], al[4], bh0, bl0, bh1, bl1;
+      split3(pa[j8], ah[0], al[0]); split3(pb[j8], ah[1], al[1]);
+      split3(pa[j8 + 4], ah[2], al[2]); split3(pb[j8 + 4], ah[3], al[3]);
+      split3(vb[j8 * 72], bh0, bl0); split3(vb[(j8 + 4) * 72], bh1, bl1);
+      mbr_mma_tf32(acc, al, bh0, bh1);
+      mbr_mma_tf32(acc, ah, bl0, bl1);
+      mbr_mma_tf32(acc, ah, bh0, bh1);
+    }
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const int i = i0 + gq + hr * 8;
+      if (i >= n) continue;
+      const float sc = rinv[i];
+      const long long o = (base + (long long)i * stride) * di + head * DHEAD + d0 + 2 * tq4;
+      const float x0 = acc[2 * hr] * sc, x1 = acc[2 * hr + 1] * sc;
+      const float h0 = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
+      *reinterpret_cast<float2*>(ao_hi + o) = make_float2(h0, h1);
+      *reinterpret_cast<float2*>(ao_lo + o) = make_float2(x0 - h0, x1 - h1);
     }
   }
 }
@@ -789,9 +952,16 @@ class Model : public ModelImpl {
         if (adn_first_use_on_device(cfg)) {
           cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
           cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+          cudaFuncSetAttribute(attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         }
         const size_t smem2 = att2_smem_floats(nseq) * sizeof(float);
-        if (smem2 <= 220 * 1024) {
+        const size_t smem3 = att3_smem_floats(nseq) * sizeof(float);
+        static const bool use_mma = !(getenv("ADN_MBR_MMA") && getenv("ADN_MBR_MMA")[0] == '0');
+        if (use_mma && nseq > 96 && smem3 <= 220 * 1024) {     // (60-band sequences: the FFMA tiles measured faster, 7.7 vs 8.5 ms per step)
+          const int att_threads = 1024;
+          attention3_kernel<<<dim3((unsigned)nq, heads), att_threads, smem3, st>>>(
+              qkvg, DQ, freq ? fcos : tcos, freq ? fsin : tsin, ao, ao + M * DI, nseq, freq ? Mf : 1, freq ? 1 : 0, heads);
+        } else if (smem2 <= 220 * 1024) {
           const int att_threads = nseq > 96 ? 1024 : 512;     // small sequences: more CTAs per SM instead
           attention2_kernel<<<dim3((unsigned)nq, heads), att_threads, smem2, st>>>(
               qkvg, DQ, freq ? fcos : tcos, freq ? fsin : tsin, ao, ao + M * DI, nseq, freq ? Mf : 1, freq ? 1 : 0, heads);

@@ -1,7 +1,6 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_zhgtcrn.py tests/test_gpu_zdfsmn.py -m gpu -q -s 2>&1 | grep -E "window|hgtcrn|passed|failed|Error|error" | head -12
-for mdl in hgtcrn dfsmn; do
-timeout 200 python bench.py --model $mdl --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('$mdl', d['config']['batch_per_gpu'], round(d['ms_per_step'],2), round(d['value'],1), 'e2e', round(d['e2e']['value'],1), dict(list(d['kernels_ms_per_step'].items())[:8]))"
-done
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:attention3_kernel --launch-skip 2 --launch-count 2 -o gpurun_out/c12_att3 python bench.py --model mbr --batch 8 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/c12_ncu.log 2>&1
+ncu -i gpurun_out/c12_att3.ncu-rep --page raw --csv > gpurun_out/c12_att3_raw.csv 2>/dev/null
+ncu -i gpurun_out/c12_att3.ncu-rep --page source --csv --print-source sass > gpurun_out/c12_att3_src.csv 2>/dev/null
+rm -f gpurun_out/c12_att3.ncu-rep
+ls -la gpurun_out/c12*
