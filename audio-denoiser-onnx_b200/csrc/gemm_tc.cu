@@ -22,6 +22,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace tc {
 
@@ -42,6 +43,22 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// elect.sync: one lane of a CONVERGED warp.  Unlike `lane == 0`, ptxas knows that exactly one thread runs the guarded block, so
+// the uniform-datapath tcgen05 / TMA instructions inside take their operands from uniform registers directly instead of an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall per instruction (ncu + SASS of the 64-wide GEMMs: ~90 clk of issue overhead per
+// MMA against 54 clk of tensor-pipe time -- the MMA warp, not the tensor pipe, bounded every N = 64 GEMM).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n"
@@ -50,6 +67,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// A operand from tensor memory (lane = tile row, one 32-bit column per K element), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -83,6 +111,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
@@ -125,12 +162,21 @@ __device__ __forceinline__ int16_t to_i16(float y, int mode) {
   return (int16_t)(int)fminf(fmaxf(y * 32767.0f, -32768.0f), 32767.0f);
 }
 
-template <int BN, bool BF = false, bool AF = false>
+constexpr int NCONV_TS = 8;             // TS mode: two converter warps per TMEM lane quarter
+constexpr int NE_TS = 8;
+constexpr int NTHREADS_TS = 64 + 32 * (NE_TS + NCONV_TS);
+
+template <int BN, bool BF = false, bool AF = false, bool TS = false>
 struct Smem {
   static constexpr uint32_t W_TILE_BYTES = BN * BK * 4;           // BN rows of 128 bytes (32 tf32 or 64 bf16)
   static constexpr int PLANES = BF ? 1 : 2;
-  static constexpr uint32_t STAGE_BYTES = PLANES * (A_TILE_BYTES + W_TILE_BYTES);
-  static constexpr int STAGES = BF ? 4 : ((BN <= 64) ? 4 : (BN <= 128) ? 3 : 2);
+  // TS: the fp32 A tile as TMA lands it (its tf32 hi / lo operand tiles live in tensor memory) + the W hi / lo tiles
+  static constexpr uint32_t STAGE_BYTES = TS ? A_TILE_BYTES + 2 * W_TILE_BYTES : PLANES * (A_TILE_BYTES + W_TILE_BYTES);
+  static constexpr int STAGES = TS ? 6 : BF ? 4 : ((BN <= 64) ? 4 : (BN <= 128) ? 3 : 2);
+  // TS tensor-memory map: two BN-column accumulators, then STAGES operand slots of 32 hi + 32 lo columns
+  static constexpr int ACC_COLS = TS ? BN : 256;
+  static constexpr int A_COL0 = 2 * BN;
+  static_assert(!TS || 2 * BN + STAGES * 2 * BK <= 512, "TS mode: accumulators + A operand slots exceed tensor memory");
   // epilogue staging behind the pipeline stages (1024-byte aligned): per-warp 8x36 transpose tiles, or, in fp32-A mode, one
   // 16-row x 128-byte swizzled tile per warp that a TMA store drains
   static constexpr uint32_t EPI_STAGE_BYTES = AF ? NEPI * 2048 : 19456 /* >= NEPI * 8 * 36 * 4, multiple of 1024 */;
@@ -142,13 +188,22 @@ struct Smem {
 // hi = x & 0xFFFFE000 (kept where it is) and lo = x - hi (lo slot) -- the 128-byte swizzle is a permutation of 16-byte chunks,
 // so an element-wise pass needs no knowledge of it -- then fence.proxy.async and hand the stage to the MMA warp.  Activations
 // live in HBM once, as fp32: half the A bytes, and no producer writes operand planes.
-template <int BN, int EPI, bool BF, bool AF, bool DK = false>
-__global__ void __launch_bounds__(AF ? NTHREADS_AF : NTHREADS, 1)
+//
+// TS (with AF, 64-wide tiles): the A operand of the MMAs comes from TENSOR MEMORY.  ncu on the SS form of the 64-wide implicit-GEMM
+// convolutions (profiles/r2e_zip_dense_ss_*): one k block took 1 100 clk against 384 clk of MMA issue (12 x 128x64x8), because
+// every MMA streams its 4 KB A tile + 2 KB W tile through the shared-memory port (72 KB per k block = 576 clk at 128 B/clk) and the
+// converter warps' loads / stores (395 wavefronts per k block) share that port.  Here the converters (8 warps, lane = tile row)
+// read the fp32 tile once and write hi / lo with tcgen05.st into per-stage operand columns; the MMAs read only W from shared
+// memory (16 clk per MMA, under the 32 clk issue floor), the stage shrinks to 32 KB (six stages) and nothing is written back to
+// shared memory.  Same products in the same order as the SS form: results are bit-identical (tests/test_gpu_ends.py).
+template <int BN, int EPI, bool BF, bool AF, bool DK = false, bool TS = false>
+__global__ void __launch_bounds__(TS ? NTHREADS_TS : AF ? NTHREADS_AF : NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
                const __grid_constant__ CUtensorMap map_c, const TcArgs g) {
-  using S = Smem<BN, BF, AF>;
+  using S = Smem<BN, BF, AF, TS>;
+  static_assert(!TS || (AF && !BF), "TS mode is the fp32-A path");
   constexpr int BKE = BF ? 2 * BK : BK;          // K elements per 128-byte row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -164,8 +219,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   // 16.1 ms per step); wider tiles keep all 16 epilogue warps (12 measured slower: ff_in 8.2 -> 10.0 ms) and 2 converters.
   // DK (deep K, >= 512: MossFormer2 fl_in): the epilogue is amortised over many K blocks, conversion is not: 12 epilogue + 6
   // converter warps (fl_in 8.3 -> 7.6 ms per step; at K = 256 the 16-warp epilogue still wins).
-  constexpr int NE = AF ? (BN <= 64 ? 8 : DK ? 12 : NEPI) : NEPI;
-  constexpr int NCONV = AF ? NEPI + NCONV_AF - NE : 0;
+  constexpr int NE = TS ? NE_TS : AF ? (BN <= 64 ? 8 : DK ? 12 : NEPI) : NEPI;
+  constexpr int NCONV = TS ? NCONV_TS : AF ? NEPI + NCONV_AF - NE : 0;
   float* stage = (float*)(smem + S::STAGES * S::STAGE_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -184,7 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S::STAGES; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], TS ? 1 + NCONV : 1);   // TS: the converters release the A tile, the MMA commit the W tiles
       if (AF) mbar_init(&conv[i], NCONV);
     }
     for (int i = 0; i < 2; ++i) {
@@ -205,7 +260,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // (all lanes walk the loops, one elected lane issues: see elect_one)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -217,6 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * S::STAGE_BYTES;
+          if (elect_one()) {
           const bool skip_w = AF && (g.probe & 4) && !(tile == (int)blockIdx.x && kb < S::STAGES);
           mbar_expect_tx(&full[stage], (uint32_t)(AF ? 1 : S::PLANES) * (uint32_t)(g.bt * g.bb * BK * 4) + (skip_w ? 0u : (uint32_t)S::PLANES * S::W_TILE_BYTES));
           int wb = g.w_batched ? b0 : 0;            // per-batch weights (mask-estimator bands, attention operands)
@@ -226,7 +283,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           if (second) wk = kb * BKE - g.k_split;
           int ak = kb * BKE, at = t0;
           if (g.taps > 0) { const int tap = kb / g.tap_kb; ak = g.tap_k0 + (kb - tap * g.tap_kb) * BKE; at = t0 + g.tap_shift[tap]; }
-          if (BF) {
+          if (TS) {
+            tma_load_3d(st, &map_a_hi, &full[stage], ak, at, b0);
+            if (!skip_w) {
+              tma_load_3d(st + A_TILE_BYTES, second ? &map_w2_hi : &map_w_hi, &full[stage], wk, nt * BN, wb);
+              tma_load_3d(st + A_TILE_BYTES + S::W_TILE_BYTES, second ? &map_w2_lo : &map_w_lo, &full[stage], wk, nt * BN, wb);
+            }
+          } else if (BF) {
             tma_load_3d(st, &map_a_hi, &full[stage], ak, at, b0);
             tma_load_3d(st + A_TILE_BYTES, second ? &map_w2_hi : &map_w_hi, &full[stage], wk, nt * BN, wb);
           } else {
@@ -237,13 +300,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             tma_load_3d(st + 2 * A_TILE_BYTES + S::W_TILE_BYTES, second ? &map_w2_lo : &map_w_lo, &full[stage], wk, nt * BN, wb);
             }
           }
+          }
+          __syncwarp();
           if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // All 32 lanes walk the loops (warp-uniform control flow: stage / phase / descriptors stay in uniform registers); one
+    // elected lane issues the MMAs and commits of a k block.
+    {
       constexpr uint32_t idesc = BF ? make_idesc_bf16(BM, BN) : make_idesc(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -253,35 +320,106 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty[ab], aphase ^ 1);       // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + ab * 256;
+        const uint32_t d_tmem = tmem_base + ab * S::ACC_COLS;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full[stage], phase);
           if (AF) mbar_wait(&conv[stage], phase);  // operand tiles split by the converter warps
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
-          if (BF) {
-            const uint64_t a_d = make_desc(sa), w_d = make_desc(sa + A_TILE_BYTES);
+          if (elect_one()) {
+            if (TS) {
+              const uint32_t a_hi = tmem_base + S::A_COL0 + stage * 2 * BK, a_lo = a_hi + BK;
+              const uint64_t w_hi = make_desc(sa + A_TILE_BYTES), w_lo = make_desc(sa + A_TILE_BYTES + S::W_TILE_BYTES);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {       // 4 x 16 bf16 = one 128-byte row
-              const uint64_t adv = (uint64_t)((kk * 32) >> 4);
-              umma_bf16(d_tmem, a_d + adv, w_d + adv, idesc, (kb | kk) ? 1u : 0u);
-            }
-          } else {
-            const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_TILE_BYTES);
-            const uint64_t w_hi = make_desc(sa + 2 * A_TILE_BYTES);
-            const uint64_t w_lo = make_desc(sa + 2 * A_TILE_BYTES + S::W_TILE_BYTES);
+              for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);   // +32 B inside the swizzle row
+                umma_tf32_ts(d_tmem, a_lo + kk * UMMA_K, w_hi + adv, idesc, (kb | kk) ? 1u : 0u);
+                umma_tf32_ts(d_tmem, a_hi + kk * UMMA_K, w_lo + adv, idesc, 1u);
+                umma_tf32_ts(d_tmem, a_hi + kk * UMMA_K, w_hi + adv, idesc, 1u);
+              }
+            } else if (BF) {
+              const uint64_t a_d = make_desc(sa), w_d = make_desc(sa + A_TILE_BYTES);
 #pragma unroll
-            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-              const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);   // +32 B inside the swizzle row
-              umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, (kb | kk) ? 1u : 0u);
-              umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1u);
-              umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1u);
+              for (int kk = 0; kk < 4; ++kk) {       // 4 x 16 bf16 = one 128-byte row
+                const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+                umma_bf16(d_tmem, a_d + adv, w_d + adv, idesc, (kb | kk) ? 1u : 0u);
+              }
+            } else {
+              const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_TILE_BYTES);
+              const uint64_t w_hi = make_desc(sa + 2 * A_TILE_BYTES);
+              const uint64_t w_lo = make_desc(sa + 2 * A_TILE_BYTES + S::W_TILE_BYTES);
+#pragma unroll
+              for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);   // +32 B inside the swizzle row
+                umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, (kb | kk) ? 1u : 0u);
+                umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1u);
+                umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1u);
+              }
             }
+            umma_commit(&empty[stage]);              // smem slot free once these MMAs retire
+            if (kb == k_blocks - 1) umma_commit(&tfull[ab]);   // accumulator complete
           }
-          umma_commit(&empty[stage]);              // smem slot free once these MMAs retire
+          __syncwarp();
           if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[ab]);                   // accumulator complete
+      }
+    }
+  } else if (TS && warp >= 2 + NE) {
+    // ===================== fp32 -> tf32 hi / lo converters, operands into tensor memory =====================
+    // lane = tile row (a warp may touch the TMEM lane quarter warp % 4 only); the two warps of a quarter take 16 K columns each.
+    // The swizzled row is read as four 16-byte chunks: a quarter-warp's eight rows hit eight distinct chunk positions, so the
+    // loads are conflict-free.
+    const int q = warp & 3, h = (warp - (2 + NE)) >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t t_dst = tmem_base + ((uint32_t)(q * 32) << 16) + S::A_COL0 + 16 * h;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int mt = tile / n_tiles_n;
+      const int cb = mt / g.tiles_per_chunk, t = (mt - cb * g.tiles_per_chunk) * BM + r;   // chunk and row of this lane
+      float mean = 0.f, rstd = 1.f;
+      if (g.a_rowstat && t < g.TM) {
+        const float2 ms = __ldg(reinterpret_cast<const float2*>(g.a_rowstat) + ((long long)(cb + g.b_off) * g.TM + t));
+        mean = ms.x; rstd = ms.y;
+      }
+      const int tcol = (g.taps > 0 && g.tap_w > 0) ? t % g.tap_w : 0;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full[stage], phase);
+        const uint8_t* row = smem + stage * S::STAGE_BYTES + r * 128;
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(row + (((4 * h + i) ^ (r & 7)) << 4));
+        bool zero = false;
+        if (g.taps > 0 && g.tap_w > 0) {
+          const int col = tcol + g.tap_df[kb / g.tap_kb];
+          zero = col < 0 || col >= g.tap_w;
+        }
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float y = x[j];
+            if (g.a_rowstat) y = (y - mean) * rstd;
+            if (zero) y = 0.f;
+            const uint32_t hb = __float_as_uint(y) & 0xFFFFE000u;
+            hi[4 * i + j] = hb;
+            lo[4 * i + j] = __float_as_uint(y - __uint_as_float(hb));
+          }
+        }
+        if (!(g.probe & 1)) {
+          tmem_st16(t_dst + stage * 2 * BK, hi);
+          tmem_st16(t_dst + stage * 2 * BK + BK, lo);
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&conv[stage]);       // operand columns written: the MMA warp may issue
+          mbar_arrive(&empty[stage]);      // fp32 tile consumed: with the MMA commit this frees the stage for the producer
+        }
+        if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (AF && warp >= 2 + NE) {
@@ -343,6 +481,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
     const int cidx = (warp - 2) >> 2;              // the four warps of a quarter take every fourth 32-column chunk
     const int r = q * 32 + lane;                   // row of the tile
+    const bool store_lane = elect_one();           // issues (and waits for) this warp's TMA stores: bulk groups are per thread
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int mt = tile / n_tiles_n, nt = tile - mt * n_tiles_n;
@@ -356,7 +495,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const bool row_ok = (b < g.B) && (t < g.TM);
       mbar_wait(&tfull[ab], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ab * 256 + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + ab * S::ACC_COLS + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int c0 = cidx * 32; c0 < BN; c0 += 32 * (NE / 4)) {
         uint32_t v[32];
@@ -450,7 +589,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) {
+            if (store_lane) {
               tma_store_3d(&map_c, stg, n0, tile_t + q * 32 + half * 16, tile_b + g.b_off);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
               asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the staging tile may be overwritten
@@ -655,7 +794,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[ab]);
     }
-    if (AF && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this warp's bulk stores have completed
+    if (AF && store_lane) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this warp's bulk stores have completed
   }
 
   tc_fence_before();
@@ -755,18 +894,18 @@ bool make_store_map(CUtensorMap* map, float* base, int cols, int rows, long long
   return true;
 }
 
-template <int BN, int EPI, bool BF, bool AF = false, bool DK = false>
+template <int BN, int EPI, bool BF, bool AF = false, bool DK = false, bool TS = false>
 static cudaError_t launch_t(const TcPlan& p, const TcArgs& a, int sms, cudaStream_t st) {
-  using S = Smem<BN, BF, AF>;
+  using S = Smem<BN, BF, AF, TS>;
   static unsigned long long configured = 0;      // per device
-  auto kern = gemm_tc_kernel<BN, EPI, BF, AF, DK>;
+  auto kern = gemm_tc_kernel<BN, EPI, BF, AF, DK, TS>;
   if (adn_first_use_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
     if (e != cudaSuccess) return e;
   }
   const int n_tiles = a.m_tiles * ((a.N + BN - 1) / BN);
   const int grid = n_tiles < sms ? n_tiles : sms;
-  kern<<<grid, AF ? NTHREADS_AF : NTHREADS, S::TOTAL, st>>>(p.map_a_hi, p.map_a_lo, p.map_w_hi, p.map_w_lo, p.map_w2_hi, p.map_w2_lo, AF ? p.map_c : p.map_a_hi, a);
+  kern<<<grid, TS ? NTHREADS_TS : AF ? NTHREADS_AF : NTHREADS, S::TOTAL, st>>>(p.map_a_hi, p.map_a_lo, p.map_w_hi, p.map_w_lo, p.map_w2_hi, p.map_w2_lo, AF ? p.map_c : p.map_a_hi, a);
   return cudaGetLastError();
 }
 
@@ -778,6 +917,10 @@ static cudaError_t launch_bn(const TcPlan& p, const TcArgs& a, int epi, int sms,
     // the TMA-store epilogue writes 32-column boxes: a tile width that is not a multiple of 32 (176) would spill its last box
     // into the next N tile's columns, so it is only usable when ONE tile covers N
     if (BN % 32 && a.N > BN) return cudaErrorInvalidValue;
+    if (BN == 64) {
+      const char* ss = getenv("ADN_TC_SS");   // diagnostics / A-B test: the shared-memory A operand form (read per launch)
+      if (!(ss && atoi(ss) != 0)) return launch_t<64, EPI_LIN, false, true, false, true>(p, a, sms, st);
+    }
     if (BN > 64 && a.K >= 512 && a.taps == 0) return launch_t<BN, EPI_LIN, false, true, true>(p, a, sms, st);
     return launch_t<BN, EPI_LIN, false, true>(p, a, sms, st);
   }
