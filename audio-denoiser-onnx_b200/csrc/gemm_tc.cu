@@ -162,6 +162,37 @@ __device__ __forceinline__ int16_t to_i16(float y, int mode) {
   return (int16_t)(int)fminf(fmaxf(y * 32767.0f, -32768.0f), 32767.0f);
 }
 
+// ex2.approx.ftz / lg2.approx.ftz: what __expf / __logf evaluate, without their denormal-range guards (FSETP + two predicated
+// FMULs per call).  The guarded forms differ only where the result is denormal, and every use below adds 1 to it.
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// Activation over the 32 registers of an epilogue chunk, the kind fixed at compile time (fp32-A epilogue: one dispatch per chunk).
+template <int ACT>
+__device__ __forceinline__ void act_all(float (&x)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (ACT == ACT_SWOOSH_L || ACT == ACT_SWOOSH_R) {
+      // softplus(y) - 0.08 x, y = x - 4 | 1: max(y, 0) + ln 2 * lg2(1 + 2^(-|y| log2 e)); the log argument is in (1, 2]
+      const float y = x[j] - (ACT == ACT_SWOOSH_L ? 4.0f : 1.0f);
+      x[j] = fmaf(lg2_ftz(1.0f + ex2_ftz(fabsf(y) * -1.4426950408889634f)), 0.69314718055994531f, fmaxf(y, 0.f)) - 0.08f * x[j];
+    } else if (ACT == ACT_SILU) {
+      x[j] = x[j] * __fdividef(1.0f, 1.0f + ex2_ftz(x[j] * -1.4426950408889634f));
+    } else if (ACT == ACT_RELU) {
+      x[j] = fmaxf(x[j], 0.f);
+    } else if (ACT == ACT_RELU2) {
+      const float r = fmaxf(x[j], 0.f);
+      x[j] = r * r;
+    } else if (ACT == ACT_GELU) {
+      x[j] = 0.5f * x[j] * (1.0f + fast_erf(x[j] * 0.70710678118654752440f));
+    } else if (ACT == ACT_TANH) {
+      x[j] = tanhf(x[j]);
+    } else if (ACT == ACT_SIGMOID) {
+      x[j] = 1.0f / (1.0f + expf(-x[j]));
+    }
+  }
+}
+
 constexpr int NCONV_TS = 8;             // TS mode: two converter warps per TMEM lane quarter
 constexpr int NE_TS = 8;
 constexpr int NTHREADS_TS = 64 + 32 * (NE_TS + NCONV_TS);
@@ -514,66 +545,99 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           float x[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-          if (row_ok && !dead) {
-            const float rsc_row = g.rowscale ? __ldg(g.rowscale + (long long)b * g.TM + t) : 1.0f;
-            float4 res4[8];
+          // Valid float4 groups of this chunk (N, BN multiples of 4).  Every optional operand and the activation are dispatched ONCE
+          // per chunk, each as its own pass over the 32 registers: ncu on the per-group form (profiles/r2e_zip_ff_*) showed 875
+          // warp instructions per chunk, 384 of them the activation itself, at 9.4 clk per issued instruction -- the small-K
+          // GEMMs were bound by this instruction stream, not by the stores.
+          const int nv = min(8, min(BN - c0, g.N - n0) >> 2);
+          if (row_ok && !dead && nv > 0) {
+            if (g.rowscale) {
+              const float rsc_row = __ldg(g.rowscale + (long long)b * g.TM + t);
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const bool ok = c0 + 4 * j4 < BN && n0 + 4 * j4 < g.N;
-              res4[j4] = (ok && g.resid) ? *reinterpret_cast<const float4*>(g.resid + o + 4 * j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int j = 0; j < 32; ++j) x[j] *= rsc_row;
             }
+            // The residual of a plain projection (no activation: every *_out GEMM) is fetched before the bias pass so its latency
+            // hides behind it; behind an activation it is fetched afterwards -- 32 more live registers across the activation
+            // pass would spill at the 96-register budget of 5 warps per scheduler.
+            if (g.act == ACT_NONE) {
+              float4 res4[8];
+              if (g.resid) {
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              if (!(c0 + 4 * j4 < BN && n0 + 4 * j4 < g.N)) continue;
-              if (g.rowscale) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) x[4 * j4 + j] *= rsc_row;
+                for (int j4 = 0; j4 < 8; ++j4)
+                  res4[j4] = j4 < nv ? *reinterpret_cast<const float4*>(g.resid + o + 4 * j4) : make_float4(0.f, 0.f, 0.f, 0.f);
               }
               if (g.bias) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j4);
-                x[4 * j4] += b4.x; x[4 * j4 + 1] += b4.y; x[4 * j4 + 2] += b4.z; x[4 * j4 + 3] += b4.w;
-              }
-              if (g.act == ACT_SWOOSH_L || g.act == ACT_SWOOSH_R) {
-                const float off = g.act == ACT_SWOOSH_L ? 4.0f : 1.0f;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float y = x[4 * j4 + j] - off;
-                  x[4 * j4 + j] = fmaxf(y, 0.f) + __logf(1.0f + __expf(-fabsf(y))) - 0.08f * x[4 * j4 + j];
+  #pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  if (j4 < nv) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j4);
+                    x[4 * j4] += b4.x; x[4 * j4 + 1] += b4.y; x[4 * j4 + 2] += b4.z; x[4 * j4 + 3] += b4.w;
+                  }
                 }
-              } else if (g.act == ACT_SILU) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) x[4 * j4 + j] = x[4 * j4 + j] * __fdividef(1.0f, 1.0f + __expf(-x[4 * j4 + j]));
-              } else if (g.act == ACT_RELU) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) x[4 * j4 + j] = fmaxf(x[4 * j4 + j], 0.f);
-              } else if (g.act == ACT_RELU2) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { const float r = fmaxf(x[4 * j4 + j], 0.f); x[4 * j4 + j] = r * r; }
-              } else if (g.act == ACT_PRELU) {
-                const float slope = __ldg(g.act_param);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) x[4 * j4 + j] = x[4 * j4 + j] >= 0.f ? x[4 * j4 + j] : slope * x[4 * j4 + j];
-              } else if (g.act == ACT_PRELU_VEC) {
-                const float4 s4 = __ldg(reinterpret_cast<const float4*>(g.act_vec + n0) + j4);
-                const float sl[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) x[4 * j4 + j] = x[4 * j4 + j] >= 0.f ? x[4 * j4 + j] : sl[j] * x[4 * j4 + j];
-              } else if (g.act == ACT_SIGMOID) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) x[4 * j4 + j] = 1.0f / (1.0f + expf(-x[4 * j4 + j]));
-              } else if (g.act == ACT_GELU) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) x[4 * j4 + j] = 0.5f * x[4 * j4 + j] * (1.0f + fast_erf(x[4 * j4 + j] * 0.70710678118654752440f));
-              } else if (g.act == ACT_TANH) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) x[4 * j4 + j] = tanhf(x[4 * j4 + j]);
               }
-              x[4 * j4] += res4[j4].x; x[4 * j4 + 1] += res4[j4].y; x[4 * j4 + 2] += res4[j4].z; x[4 * j4 + 3] += res4[j4].w;
-              if (g.resid2) {
-                const float4 o4 = *reinterpret_cast<const float4*>(g.resid2 + o + 4 * j4);
-                const float4 s4 = __ldg(reinterpret_cast<const float4*>(g.colscale + n0) + j4);
-                x[4 * j4] = o4.x + (x[4 * j4] - o4.x) * s4.x; x[4 * j4 + 1] = o4.y + (x[4 * j4 + 1] - o4.y) * s4.y;
-                x[4 * j4 + 2] = o4.z + (x[4 * j4 + 2] - o4.z) * s4.z; x[4 * j4 + 3] = o4.w + (x[4 * j4 + 3] - o4.w) * s4.w;
+              if (g.resid) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  x[4 * j4] += res4[j4].x; x[4 * j4 + 1] += res4[j4].y; x[4 * j4 + 2] += res4[j4].z; x[4 * j4 + 3] += res4[j4].w;
+                }
+              }
+            } else {
+              if (g.bias) {
+  #pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  if (j4 < nv) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j4);
+                    x[4 * j4] += b4.x; x[4 * j4 + 1] += b4.y; x[4 * j4 + 2] += b4.z; x[4 * j4 + 3] += b4.w;
+                  }
+                }
+              }
+              switch (g.act) {                       // (columns >= N carry garbage through the activation: the store clips them)
+                case ACT_SWOOSH_L: act_all<ACT_SWOOSH_L>(x); break;
+                case ACT_SWOOSH_R: act_all<ACT_SWOOSH_R>(x); break;
+                case ACT_SILU: act_all<ACT_SILU>(x); break;
+                case ACT_RELU: act_all<ACT_RELU>(x); break;
+                case ACT_RELU2: act_all<ACT_RELU2>(x); break;
+                case ACT_GELU: act_all<ACT_GELU>(x); break;
+                case ACT_TANH: act_all<ACT_TANH>(x); break;
+                case ACT_SIGMOID: act_all<ACT_SIGMOID>(x); break;
+                case ACT_PRELU: {
+                  const float slope = __ldg(g.act_param);
+  #pragma unroll
+                  for (int j = 0; j < 32; ++j) x[j] = x[j] >= 0.f ? x[j] : slope * x[j];
+                } break;
+                case ACT_PRELU_VEC: {
+  #pragma unroll
+                  for (int j4 = 0; j4 < 8; ++j4) {
+                    if (j4 < nv) {
+                      const float4 s4 = __ldg(reinterpret_cast<const float4*>(g.act_vec + n0) + j4);
+                      x[4 * j4] = x[4 * j4] >= 0.f ? x[4 * j4] : s4.x * x[4 * j4];
+                      x[4 * j4 + 1] = x[4 * j4 + 1] >= 0.f ? x[4 * j4 + 1] : s4.y * x[4 * j4 + 1];
+                      x[4 * j4 + 2] = x[4 * j4 + 2] >= 0.f ? x[4 * j4 + 2] : s4.z * x[4 * j4 + 2];
+                      x[4 * j4 + 3] = x[4 * j4 + 3] >= 0.f ? x[4 * j4 + 3] : s4.w * x[4 * j4 + 3];
+                    }
+                  }
+                } break;
+                default: break;
+              }
+              if (g.resid) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  if (j4 < nv) {
+                    const float4 r4 = *reinterpret_cast<const float4*>(g.resid + o + 4 * j4);
+                    x[4 * j4] += r4.x; x[4 * j4 + 1] += r4.y; x[4 * j4 + 2] += r4.z; x[4 * j4 + 3] += r4.w;
+                  }
+                }
+              }
+            }
+            if (g.resid2) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                if (j4 < nv) {
+                  const float4 o4 = *reinterpret_cast<const float4*>(g.resid2 + o + 4 * j4);
+                  const float4 s4 = __ldg(reinterpret_cast<const float4*>(g.colscale + n0) + j4);
+                  x[4 * j4] = o4.x + (x[4 * j4] - o4.x) * s4.x; x[4 * j4 + 1] = o4.y + (x[4 * j4 + 1] - o4.y) * s4.y;
+                  x[4 * j4 + 2] = o4.z + (x[4 * j4 + 2] - o4.z) * s4.z; x[4 * j4 + 3] = o4.w + (x[4 * j4 + 3] - o4.w) * s4.w;
+                }
               }
             }
           }
