@@ -1114,6 +1114,13 @@ def main():
         return
 
     # ---------------- device-resident throughput ("value")
+    # Untimed priming: adn_run runs a (buffers, batch) combination eagerly or under stream capture the first time it sees it
+    # and replays the instantiated CUDA graph afterwards.  Every rotated input set goes through that once here, so the W warm-up
+    # steps and the K timed steps are all steady-state replays (with W = 3, K = 5 and 8 sets every timed step used to be a
+    # capture + instantiate run: 82.5 ms per step against 71 ms in the e2e loop of the same process).
+    for _ in range(2):
+        for s_ in dev_sets:
+            model.run(s_, out=out)
     for i in range(args.warmup):
         model.run(dev_sets[i % n_sets], out=out)
     barrier()
@@ -1252,6 +1259,8 @@ def main():
             "config": {"workload": wl.describe(B), "model": wl.name, "batch_per_gpu": B, "chunk_samples": wl.chunk,
                        "l2_policy": f"{n_sets} distinct input batches rotated ({n_sets * in_bytes / 2**20:.0f} MiB) "
                                     f"+ {ws_mib:.0f} MiB workspace streamed per step, both > 126 MB L2",
+                       "graph_priming": f"2 untimed passes over the {n_sets} input sets before the warm-up (eager run + stream capture per "
+                                        "buffer combination), so warm-up and timed steps replay instantiated CUDA graphs",
                        "parallelism": f"batch-shard x{world}, weights replicated, no data-path collective"},
             "rtf": 1.0 / value,
             "clocks": clk.summary(),
