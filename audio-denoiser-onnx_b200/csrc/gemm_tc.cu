@@ -524,6 +524,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       else { b = tile_b; t = tile_t + r; }
       b += g.b_off;
       const bool row_ok = (b < g.B) && (t < g.TM);
+      // TS tiles are one chunk per epilogue warp: the residual / bypass rows of the chunk (one 128-byte line per lane each) are
+      // prefetched into L1 BEFORE the accumulator wait, so their DRAM / L2 latency is off the per-tile chain of the two epilogue
+      // warps a scheduler has (register prefetch of the 32 values spills at the 96-register budget)
+      if (TS && row_ok && !(g.probe & 2)) {
+        const long long op = ((long long)b * g.TM + t) * g.ldc + nt * BN + cidx * 32;
+        if (nt * BN + cidx * 32 < g.N) {
+          if (g.resid) asm volatile("prefetch.global.L1 [%0];" ::"l"(g.resid + op));
+          if (g.resid2) asm volatile("prefetch.global.L1 [%0];" ::"l"(g.resid2 + op));
+        }
+      }
       mbar_wait(&tfull[ab], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ab * S::ACC_COLS + ((uint32_t)(q * 32) << 16);
@@ -642,6 +652,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
           }
           if (n0 >= g.N || dead) continue;
+          if (TS) {
+            // eight epilogue warps leave 4 KB of staging per warp: the whole 32 x 32 chunk is staged at once (all lanes, still
+            // conflict-free), the two 16-row boxes leave as one bulk group, and the wait for the TMA engine to have READ the
+            // tile moves to the next tile -- behind that tile's accumulator wait, TMEM load and arithmetic
+            uint8_t* stg4 = reinterpret_cast<uint8_t*>(stage) + (warp - 2) * 4096;
+            if (store_lane) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+              *reinterpret_cast<float4*>(stg4 + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (store_lane) {
+              tma_store_3d(&map_c, stg4, n0, tile_t + q * 32, tile_b + g.b_off);
+              tma_store_3d(&map_c, stg4 + 2048, n0, tile_t + q * 32 + 16, tile_b + g.b_off);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            continue;
+          }
           uint8_t* stg = reinterpret_cast<uint8_t*>(stage) + (warp - 2) * 2048;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
