@@ -569,7 +569,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             // The residual of a plain projection (no activation: every *_out GEMM) is fetched before the bias pass so its latency
             // hides behind it; behind an activation it is fetched afterwards -- 32 more live registers across the activation
             // pass would spill at the 96-register budget of 5 warps per scheduler.
-            if (g.act == ACT_NONE) {
+            if (g.act == ACT_NONE && !TS) {
               float4 res4[8];
               if (g.resid) {
 #pragma unroll
@@ -577,7 +577,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                   res4[j4] = j4 < nv ? *reinterpret_cast<const float4*>(g.resid + o + 4 * j4) : make_float4(0.f, 0.f, 0.f, 0.f);
               }
               if (g.bias) {
-  #pragma unroll
+#pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
                   if (j4 < nv) {
                     const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j4);
@@ -629,12 +629,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 } break;
                 default: break;
               }
-              if (g.resid) {
+              if (g.resid) {       // (TS: the rows were prefetched into L1 before the accumulator wait; four float4 in flight at a time
+                                   //  -- ncu showed the eight-deep form spilling a freshly loaded register, i.e. waiting on the load at once)
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                  if (j4 < nv) {
-                    const float4 r4 = *reinterpret_cast<const float4*>(g.resid + o + 4 * j4);
-                    x[4 * j4] += r4.x; x[4 * j4 + 1] += r4.y; x[4 * j4 + 2] += r4.z; x[4 * j4 + 3] += r4.w;
+                for (int hh = 0; hh < 2; ++hh) {
+                  float4 r4[4];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i)
+                    r4[i] = (4 * hh + i) < nv ? *reinterpret_cast<const float4*>(g.resid + o + 4 * (4 * hh + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const int j4 = 4 * hh + i;
+                    x[4 * j4] += r4[i].x; x[4 * j4 + 1] += r4[i].y; x[4 * j4 + 2] += r4[i].z; x[4 * j4 + 3] += r4[i].w;
                   }
                 }
               }
