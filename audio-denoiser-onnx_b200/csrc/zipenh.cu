@@ -426,8 +426,10 @@ __global__ void __launch_bounds__(256) norm_bypass_kernel(const float* __restric
                                                                   (xv.z / nrm) * ns.z + o0.z * rs.z, (xv.w / nrm) * ns.w + o0.w * rs.w);
 }
 
-// InstanceNorm2d apply + PReLU for pool == 1 (every launch but the two sub-pixel ones): 16 threads per destination pixel,
-// one float4 of channels each; pad columns of the destination grid are written as zeros
+// InstanceNorm2d apply + PReLU: 16 threads per destination pixel, one float4 of channels each; pad columns of the destination
+// grid are written as zeros.  POOL == 2 is the sub-pixel shuffle of the two decoders (output column 2 k' + u takes channel
+// 2 c + u of source column k': the four channels of a thread are the even or the odd floats of eight consecutive ones).
+template <int POOL>
 __global__ void __launch_bounds__(256) in_apply_kernel(InApply f, int npix) {
   const int idx = blockIdx.x * 256 + threadIdx.x;
   const int c4 = idx & 15, pix = idx >> 4;
@@ -436,7 +438,14 @@ __global__ void __launch_bounds__(256) in_apply_kernel(InApply f, int npix) {
   const int k = fd - f.dst_lo;
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (k >= 0 && k < f.nout) {
-    const float4 x = *reinterpret_cast<const float4*>(f.raw + ((long long)bt * f.Ws + f.src_lo + k) * f.ld + 4 * c4);
+    float4 x;
+    if (POOL == 1) {
+      x = *reinterpret_cast<const float4*>(f.raw + ((long long)bt * f.Ws + f.src_lo + k) * f.ld + 4 * c4);
+    } else {
+      const float4* src = reinterpret_cast<const float4*>(f.raw + ((long long)bt * f.Ws + f.src_lo + (k >> 1)) * f.ld + 8 * c4);
+      const float4 lo = src[0], hi = src[1];
+      x = (k & 1) ? make_float4(lo.y, lo.w, hi.y, hi.w) : make_float4(lo.x, lo.z, hi.x, hi.z);
+    }
     const float4* st = reinterpret_cast<const float4*>(f.stat + 2 * (bb * C + 4 * c4));
     const float4 s0 = st[0], s1 = st[1];           // (mean, rstd) x 4 channels
     const float4 w = __ldg(reinterpret_cast<const float4*>(f.w) + c4), b = __ldg(reinterpret_cast<const float4*>(f.b) + c4);
@@ -447,6 +456,32 @@ __global__ void __launch_bounds__(256) in_apply_kernel(InApply f, int npix) {
     v.z = v.z >= 0.f ? v.z : a.z * v.z; v.w = v.w >= 0.f ? v.w : a.w * v.w;
   }
   *reinterpret_cast<float4*>(f.of + (long long)pix * f.ldd + f.coff + 4 * c4) = v;
+}
+
+// InstanceNorm2d statistics, second stage: one WARP per (window, channel), lanes over the frames' double partial sums, butterfly
+// reduction (fixed order: deterministic).  The functor walks the T frames with one thread: 4 096 threads in all, 89 us per launch.
+__global__ void __launch_bounds__(256) in_fin_kernel(InFin f, long long n) {
+  const long long i = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const int cn = f.ld / f.pool;
+  const int c = (int)(i % cn);
+  const long long b = i / cn;
+  double s = 0.0, s2 = 0.0;
+  for (int t = lane; t < f.T; t += 32)
+    for (int u = 0; u < f.pool; ++u) {
+      const double2 v = *reinterpret_cast<const double2*>(f.part + 2 * ((b * f.T + t) * f.ld + c * f.pool + u));
+      s += v.x; s2 += v.y;
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  if (lane == 0) {
+    const double cnt = (double)f.T * f.nvalid * f.pool, mu = s / cnt;
+    double var = s2 / cnt - mu * mu;
+    var = var > 0.0 ? var : 0.0;
+    f.stat[2 * i] = (float)mu;
+    f.stat[2 * i + 1] = (float)(1.0 / sqrt(var + (double)IN_EPS));
+  }
 }
 
 // decoder heads: one thread = one (window, frame, bin) with both taps' 2 x 64 inputs read as float4 and all outputs of the head
@@ -585,10 +620,16 @@ struct CudaExec {
     glu_dwconv_kernel<<<(unsigned)((nseq * C + 255) / 256), 256, 0, st>>>(f.cp, f.sm, nseq, f.w, f.b, f.out);
     done("zip_glu_dwconv");
   }
+  void run(long long n, const InFin& f) {
+    if (functors_only) { run_functor(n, f); return; }
+    in_fin_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(f, n);
+    done("zip_in_fin");
+  }
   void run(long long n, const InApply& f) {
-    if (functors_only || f.pool != 1) { run_functor(n, f); return; }
+    if (functors_only || f.pool > 2 || (f.ld & 3)) { run_functor(n, f); return; }
     const long long npix = n / C;
-    in_apply_kernel<<<(unsigned)((npix * 16 + 255) / 256), 256, 0, st>>>(f, (int)npix);
+    if (f.pool == 1) in_apply_kernel<1><<<(unsigned)((npix * 16 + 255) / 256), 256, 0, st>>>(f, (int)npix);
+    else in_apply_kernel<2><<<(unsigned)((npix * 16 + 255) / 256), 256, 0, st>>>(f, (int)npix);
     done("zip_in_apply");
   }
   void run(long long n, const Head& f) {

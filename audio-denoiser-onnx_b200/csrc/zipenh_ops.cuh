@@ -139,11 +139,25 @@ inline void lin_ref(const LinOp& g) {
 }
 
 // ------------------------------------------------------------------------------------------------ functors
+// p -> p / d, returns p % d; 32-bit arithmetic whenever p fits (a 64-bit division by a run-time divisor is ~100 GPU instructions,
+// and the one-output-per-thread functors below do two or three of them per element)
+ZIP_HD int split_mod(long long& p, int d) {
+  if ((unsigned long long)p < 0x100000000ull) {
+    const unsigned q = (unsigned)p / (unsigned)d;
+    const int r = (int)((unsigned)p - q * (unsigned)d);
+    p = (long long)q;
+    return r;
+  }
+  const int r = (int)(p % d);
+  p /= d;
+  return r;
+}
+
 // dense_conv_1 (:851): 1x1 conv over the planar features (window, 2, frame, bin) -> raw channel-last padded map
 struct FeatConv {
   const float* feat; const float* w; const float* b; float* raw; int T;
   ZIP_HD void operator()(long long i) const {
-    const int c = (int)(i % C); long long p = i / C; const int f = (int)(p % FB); p /= FB; const int t = (int)(p % T); const long long bb = p / T;
+    const int c = (int)(i % C); long long p = i / C; const int f = split_mod(p, FB); const int t = split_mod(p, T); const long long bb = p;
     const float* x = feat + (bb * 2 * T + t) * FB + f;
     raw[((bb * T + t) * FPE + f + 1) * C + c] = b[c] + w[c * 2] * x[0] + w[c * 2 + 1] * x[(long long)T * FB];
   }
@@ -182,7 +196,7 @@ struct InApply {
   const float* raw; int ld; int Ws; int src_lo; int pool; const float* stat; const float* w; const float* b; const float* slope;
   float* of; int ldd; int coff; int Wd; int dst_lo; int nout; int T;
   ZIP_HD void operator()(long long i) const {
-    const int c = (int)(i % C); long long p = i / C; const int fd = (int)(p % Wd); p /= Wd; const int t = (int)(p % T); const long long bb = p / T;
+    const int c = (int)(i % C); long long p = i / C; const int fd = split_mod(p, Wd); const int t = split_mod(p, T); const long long bb = p;
     float v = 0.f;
     const int k = fd - dst_lo;
     if (k >= 0 && k < nout) {
@@ -199,7 +213,7 @@ struct InApply {
 struct PadCopy {
   const float* x; float *da, *db; int T;
   ZIP_HD void operator()(long long i) const {
-    const int c = (int)(i % C); long long p = i / C; const int fd = (int)(p % FPD); const long long bt = p / FPD;
+    const int c = (int)(i % C); long long p = i / C; const int fd = split_mod(p, FPD); const long long bt = p;
     float v = 0.f;
     if (fd >= 1 && fd <= FQ) v = x[(bt * FQ + fd - 1) * C + c];
     const long long o = (bt * FPD + fd) * SLOTC + (DEPTH - 1) * C + c;
@@ -306,7 +320,7 @@ struct NormBypass {
 struct Down {
   const float* x; const float* wt; const float* wf; int ds; int T, F, Td, Fd; float* of;
   ZIP_HD void operator()(long long i) const {
-    const int c = (int)(i % C); long long p = i / C; const int fj = (int)(p % Fd); p /= Fd; const int ti = (int)(p % Td); const long long bb = p / Td;
+    const int c = (int)(i % C); long long p = i / C; const int fj = split_mod(p, Fd); const int ti = split_mod(p, Td); const long long bb = p;
     float acc = 0.f;
     for (int e = 0; e < ds; ++e) {
       const int f = fj * ds + e < F ? fj * ds + e : F - 1;
@@ -324,7 +338,7 @@ struct Down {
 struct UpCombine {
   const float* y; const float* scale; const float* rscale; int ds; int T, F, Td, Fd; float* x0;
   ZIP_HD void operator()(long long i) const {
-    const int c = (int)(i % C); long long p = i / C; const int f = (int)(p % F); p /= F; const int t = (int)(p % T); const long long bb = p / T;
+    const int c = (int)(i % C); long long p = i / C; const int f = split_mod(p, F); const int t = split_mod(p, T); const long long bb = p;
     x0[i] = x0[i] * rscale[c] + (y[((bb * Td + t / ds) * Fd + f / ds) * C + c] * scale[c]);
   }
 };
@@ -334,7 +348,7 @@ struct UpCombine {
 struct Head {
   const float* up; const float* w; const float* b; int nout; float* out; int T;     // w (nout, 2, C)
   ZIP_HD void operator()(long long i) const {
-    const int f = (int)(i % FB); long long p = i / FB; const int t = (int)(p % T); p /= T; const int o = (int)(p % nout); const long long bb = p / nout;
+    const int f = (int)(i % FB); long long p = i / FB; const int t = split_mod(p, T); const int o = split_mod(p, nout); const long long bb = p;
     const float* x = up + ((bb * T + t) * FU + f) * C;
     const float* wo = w + o * 2 * C;
     float acc = b[o];

@@ -677,6 +677,10 @@ class ZipenhWorkload:
     cpu_chunks, ref_chunks = 16, 8
     in_name = "noisy_audio"
     cpu_desc = "oracle/zipenh_oracle.py (PyTorch-eager restatement, pinned to the executed reference wrapper)"
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch at B = 64, averaged over the 12 dense-block launches of a step: the
+    # four 201-bin encoder launches measured (ncu --set full, profiles/r2f_zip_dense_ts_ncu_raw.csv: 1.04 / 1.59 / 2.14 / 2.69 GB
+    # for K = 384 / 768 / 1152 / 1536), the eight 101-bin decoder launches at half of that
+    ncu_traffic = (64, {"zip_dense_conv": 1243000000}, "profiles/r2f_zip_dense_ts_ncu_raw.csv")
     tc3_kernels = ("zip_dense_conv", "zip_stride_conv", "zip_up_conv", "zip_attn_in", "zip_ff_in", "zip_ff_out", "zip_nl_in",
                    "zip_nl_out", "zip_sa_in", "zip_sa_out", "zip_cv_in", "zip_cv_out")
 
