@@ -20,6 +20,6 @@ OUT="$ROOT/profiles/sass_summary.txt"
       echo "$(echo "$n" | c++filt | cut -c1-110) | $a | $b | $c | $d | $e | $f"
     done
   echo "# totals over the library:"
-  cuobjdump -sass "$LIB" | grep -o -E "UTCHMMA|UTMALDG\.[0-9]D|LDTM\.[x0-9a-zA-Z.]*|UTCBAR|UTMASTG" | sort | uniq -c
+  cuobjdump -sass "$LIB" | grep -o -E "UTCHMMA|UTMALDG\.[0-9]D|LDTM\.[x0-9a-zA-Z.]*|STTM\.[x0-9a-zA-Z.]*|UTCBAR|UTMASTG|R2UR\.BROADCAST|ELECT" | sort | uniq -c
 } > "$OUT"
 echo "wrote $OUT"
