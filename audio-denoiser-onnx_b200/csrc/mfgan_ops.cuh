@@ -38,6 +38,17 @@ constexpr int SKIPC = C * (DEPTH + 1);
 constexpr float EPS = 1e-5f;
 
 GAN_HD float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// a / d and a % d for a >= 0, d > 0: 32-bit arithmetic whenever a fits (a 64-bit division by a run-time divisor is ~100 GPU
+// instructions; the element-wise functors do two to four per output, which made them instruction-bound, not memory-bound)
+GAN_HD long long idiv(long long a, int d) {
+  return (unsigned long long)a < 0x100000000ull ? (long long)((unsigned)a / (unsigned)d) : a / d;
+}
+GAN_HD long long idiv(long long a, long long d) {
+  return (unsigned long long)(a | d) < 0x100000000ull ? (long long)((unsigned)a / (unsigned)d) : a / d;
+}
+GAN_HD int imod(long long a, int d) {
+  return (unsigned long long)a < 0x100000000ull ? (int)((unsigned)a % (unsigned)d) : (int)(a % d);
+}
 GAN_HD float act(float v, int a, const float* slope, int n) {
   if (a == ACT_RELU) return v > 0.f ? v : 0.f;
   if (a == ACT_SILU) return v * sigmoidf_(v);
@@ -51,7 +62,7 @@ GAN_HD float act(float v, int a, const float* slope, int n) {
 struct PixMap {
   int n2;
   long long sA, sB, sS;
-  GAN_HD long long pix(long long n, int s) const { return (n / n2) * sA + (n % n2) * sB + (long long)s * sS; }
+  GAN_HD long long pix(long long n, int s) const { return idiv(n, n2) * sA + imod(n, n2) * sB + (long long)s * sS; }
 };
 
 // out[r, n] = act(bias[n] + sum_k xin(r, k) * Wt[k, n]);  xin normalised by the row's (mean, rstd) when stat != null
@@ -99,7 +110,7 @@ struct RowStats {
 struct Gather {
   const float* x; const float* pst; PixMap pm; const float* w; const float* b; float* out; int S;
   GAN_HD void operator()(long long i) const {
-    const int o = (int)(i % PI); const long long r = i / PI; const int s = (int)(r % S); const long long n = r / S;
+    const int o = (int)(i % PI); const long long r = i / PI; const int s = imod(r, S); const long long n = idiv(r, S);
     const int ch = o / KS;
     float acc = b[o];
     for (int k = 0; k < KS; ++k) {
@@ -121,7 +132,7 @@ struct DwConv {
   PixMap pm; int S, Cn;
   GAN_HD void operator()(long long i) const {
     constexpr int padl = (KT - 1) / 2;             // 'same' padding of every depthwise conv of the model
-    const int c = (int)(i % Cn); const long long r = i / Cn;
+    const int c = imod(i, Cn); const long long r = idiv(i, Cn);
     const int sg = (S + DWS - 1) / DWS; const int s0 = (int)(r % sg) * DWS; const long long n = r / sg;
     float t[KT], x[DWS + KT - 1];
 #pragma unroll
@@ -179,7 +190,7 @@ struct Shift {
 struct OffsetRot {
   const float* huv; const float* gamma; const float* beta; const float* cs; const float* sn; float* heads; int Q;
   GAN_HD void operator()(long long i) const {
-    const int j = (int)(i % QK); const int h = (int)((i / QK) % 4); const long long r = i / (4 * QK); const int q = (int)(r % Q);
+    const int j = (int)(i % QK); const int h = (int)((i / QK) % 4); const long long r = i / (4 * QK); const int q = imod(r, Q);
     const float* z = huv + r * HUV + HID;
     float v = z[j] * gamma[h * QK + j] + beta[h * QK + j];
     if (j < ROT) {
@@ -305,7 +316,7 @@ struct SeMlp {
 struct ScaleRes {
   const float* t; const float* scale; const float* x; float* out; long long per_window;
   GAN_HD void operator()(long long i) const {
-    const int c = (int)(i % C); const long long b = i / per_window;
+    const int c = (int)(i % C); const long long b = idiv(i, per_window);
     out[i] = scale[b * C + c] * t[i] + x[i];
   }
 };
@@ -339,7 +350,7 @@ struct GroupFin {
 struct GroupNorm {
   float* x; int ld; GroupBounds g; const float* stat; const float* gam; const float* bet; const float* res; float* out; int Fw;
   GAN_HD void operator()(long long i) const {
-    const int c = (int)(i % ld); const long long p = i / ld; const int f = (int)(p % Fw); const long long bt = p / Fw;
+    const int c = imod(i, ld); const long long p = idiv(i, ld); const int f = imod(p, Fw); const long long bt = idiv(p, Fw);
     int gi = 0;
     while (gi + 1 < g.n && c >= g.lo[gi + 1]) ++gi;
     const float* st = stat + 2 * (bt * g.n + gi);
@@ -392,7 +403,7 @@ struct TaAV {
 struct InPart {
   const float* x; int ld; int Cn; double* part; int Fw;
   GAN_HD void operator()(long long i) const {
-    const int c = (int)(i % Cn); const long long bt = i / Cn;
+    const int c = imod(i, Cn); const long long bt = idiv(i, Cn);
     const float* p = x + bt * Fw * ld + c;
     double s = 0.0, s2 = 0.0;
     for (int f = 0; f < Fw; ++f) { const double v = (double)p[(long long)f * ld]; s += v; s2 += v * v; }
@@ -402,7 +413,7 @@ struct InPart {
 struct InFin {
   const double* part; float* stat; int T, Fw, Cn;
   GAN_HD void operator()(long long i) const {
-    const int c = (int)(i % Cn); const long long b = i / Cn;
+    const int c = imod(i, Cn); const long long b = idiv(i, Cn);
     double s = 0.0, s2 = 0.0;
     for (int t = 0; t < T; ++t) { const double* p = part + 2 * ((b * T + t) * Cn + c); s += p[0]; s2 += p[1]; }
     const double cnt = (double)T * Fw, mu = s / cnt;
@@ -416,7 +427,7 @@ struct InApply {
   const float* x; int ld; int Cn; const float* stat; const float* w; const float* b; const float* slope; float* out; int ldo;
   long long per_window;      // frames * sub-bands
   GAN_HD void operator()(long long i) const {
-    const int c = (int)(i % Cn); const long long p = i / Cn; const long long bb = p / per_window;
+    const int c = imod(i, Cn); const long long p = idiv(i, Cn); const long long bb = idiv(p, per_window);
     const float* st = stat + 2 * (bb * Cn + c);
     const float v = (x[p * ld + c] - st[0]) * st[1] * w[c] + b[c];
     out[p * ldo + c] = v >= 0.f ? v : slope[c] * v;
@@ -459,7 +470,7 @@ struct FeatConv {
 struct CopyCh {
   const float* in; int ldi; float* out; int ldo; int Cn;
   GAN_HD void operator()(long long i) const {
-    const int c = (int)(i % Cn); const long long p = i / Cn;
+    const int c = imod(i, Cn); const long long p = idiv(i, Cn);
     out[p * ldo + c] = in[p * ldi + c];
   }
 };
