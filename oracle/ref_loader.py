@@ -83,24 +83,32 @@ def load_export_namespace(model_dir: str, script: str, patches: dict[str, str]) 
     return ns
 
 
-def load_gtcrn(input_audio_length: int = 16000, io_dtype: str = "F32", in_rate: int = 16000, out_rate: int = 16000):
+def load_gtcrn(input_audio_length: int = 16000, io_dtype: str = "F32", in_rate: int = 16000, out_rate: int = 16000,
+               model_rate_frames: bool = False):
     """Build the reference GTCRN_CUSTOM wrapper (random init, eval) for one chunk length.
 
     Returns (namespace, build) where build(state_dict|None) -> wrapper module.
-    Static buffers are baked per chunk length (Export_GTCRN.py:44-46,234-239)."""
+    Static buffers are baked per chunk length (Export_GTCRN.py:44-46,234-239).
+
+    model_rate_frames: the static export sizes its frame count from the INPUT-rate length (:45), so as shipped the
+    forward's reshape (:665-667) fails for IN_SAMPLE_RATE != 16 kHz.  With this flag that ONE constant is patched to the
+    frame count of the resampled (model-rate) signal, floor(L * 16000 / in_rate) // HOP + 1 -- every line of arithmetic
+    that then runs (resample / PCM scale / centring order, STFT, network, ISTFT) is the reference's own."""
     import torch
 
-    ns = load_export_namespace(
-        "GTCRN",
-        "Export_GTCRN.py",
-        {
-            "INPUT_AUDIO_LENGTH   = 32000": f"INPUT_AUDIO_LENGTH   = {int(input_audio_length)}",
-            "IN_AUDIO_DTYPE       = 'INT16'": f"IN_AUDIO_DTYPE       = '{io_dtype}'",
-            "OUT_AUDIO_DTYPE      = 'INT16'": f"OUT_AUDIO_DTYPE      = '{io_dtype}'",
-            "IN_SAMPLE_RATE       = 16000": f"IN_SAMPLE_RATE       = {int(in_rate)}",
-            "OUT_SAMPLE_RATE      = 16000": f"OUT_SAMPLE_RATE      = {int(out_rate)}",
-        },
-    )
+    patches = {
+        "INPUT_AUDIO_LENGTH   = 32000": f"INPUT_AUDIO_LENGTH   = {int(input_audio_length)}",
+        "IN_AUDIO_DTYPE       = 'INT16'": f"IN_AUDIO_DTYPE       = '{io_dtype}'",
+        "OUT_AUDIO_DTYPE      = 'INT16'": f"OUT_AUDIO_DTYPE      = '{io_dtype}'",
+        "IN_SAMPLE_RATE       = 16000": f"IN_SAMPLE_RATE       = {int(in_rate)}",
+        "OUT_SAMPLE_RATE      = 16000": f"OUT_SAMPLE_RATE      = {int(out_rate)}",
+    }
+    if model_rate_frames:
+        import math
+        model_len = int(math.floor(float(input_audio_length) * (1.0 / (in_rate / 16000.0))))   # F.interpolate(scale_factor=...)
+        patches["STATIC_SIGNAL_LENGTH = None if DYNAMIC_AXES else ((FOLD_WINDOW_LENGTH if USE_BATCH_FOLD else EXPORT_AUDIO_LENGTH) // HOP_LENGTH + 1)"] = \
+            f"STATIC_SIGNAL_LENGTH = {model_len // 256 + 1}"
+    ns = load_export_namespace("GTCRN", "Export_GTCRN.py", patches)
 
     def build(state_dict=None):
         with torch.inference_mode():
@@ -130,7 +138,7 @@ def load_gtcrn(input_audio_length: int = 16000, io_dtype: str = "F32", in_rate: 
     return ns, build
 
 
-def load_mbr(input_audio_length: int, io_dtype: str = "F32", out_rate: int = 44100):
+def load_mbr(input_audio_length: int, io_dtype: str = "F32", out_rate: int = 44100, in_rate: int = 44100):
     """Reference Mel-Band-Roformer (stereo) wrapper for one un-folded window.
 
     Returns (namespace, build) with build(state_dict, **model_kwargs) -> module.  The
@@ -138,17 +146,23 @@ def load_mbr(input_audio_length: int, io_dtype: str = "F32", out_rate: int = 441
     redirected to the given state_dict by patching `torch.load` for the duration of the call."""
     import torch
 
-    ns = load_export_namespace(
-        "Mel_Band_Roformer/Stereo",
-        "Export_MelBandRoformer.py",
-        {
-            "INPUT_AUDIO_LENGTH  = 88200": f"INPUT_AUDIO_LENGTH  = {int(input_audio_length)}",
-            "USE_BATCH_FOLD       = True": "USE_BATCH_FOLD       = False",
-            "IN_AUDIO_DTYPE        = 'INT16'": f"IN_AUDIO_DTYPE        = '{io_dtype}'",
-            "OUT_AUDIO_DTYPE       = 'INT16'": f"OUT_AUDIO_DTYPE       = '{io_dtype}'",
-            "OUT_SAMPLE_RATE   = 44100": f"OUT_SAMPLE_RATE   = {int(out_rate)}",
-        },
-    )
+    patches = {
+        "INPUT_AUDIO_LENGTH  = 88200": f"INPUT_AUDIO_LENGTH  = {int(input_audio_length)}",
+        "USE_BATCH_FOLD       = True": "USE_BATCH_FOLD       = False",
+        "IN_AUDIO_DTYPE        = 'INT16'": f"IN_AUDIO_DTYPE        = '{io_dtype}'",
+        "OUT_AUDIO_DTYPE       = 'INT16'": f"OUT_AUDIO_DTYPE       = '{io_dtype}'",
+        "OUT_SAMPLE_RATE   = 44100": f"OUT_SAMPLE_RATE   = {int(out_rate)}",
+    }
+    if in_rate != 44100:
+        # As shipped MAX_SIGNAL_LENGTH is sized from the INPUT-rate length (:50), so the static frame count does not match the
+        # resampled signal; that ONE constant is patched to the model-rate frame count, floor(L * 44100 / in_rate) // HOP + 1,
+        # and the reference's own forward (:629-680) is executed.
+        import math
+        model_len = int(math.floor(float(input_audio_length) * float(44100 / in_rate)))
+        patches["IN_SAMPLE_RATE    = 44100"] = f"IN_SAMPLE_RATE    = {int(in_rate)}"
+        patches["MAX_SIGNAL_LENGTH    = 2048 if DYNAMIC_AXES else (((FOLD_WINDOW_LENGTH if USE_BATCH_FOLD else INPUT_AUDIO_LENGTH) // HOP_LENGTH) + 1)"] = \
+            f"MAX_SIGNAL_LENGTH    = {model_len // 441 + 1}"
+    ns = load_export_namespace("Mel_Band_Roformer/Stereo", "Export_MelBandRoformer.py", patches)
 
     def build(state_dict, **model_kwargs):
         real_load = torch.load

@@ -202,8 +202,8 @@ def test_mbr_oracle_matches_reference_module():
 @pytest.mark.parametrize("L,out_rate,dt", [(4410, 48000, "INT16"), (4410, 16000, "F32"), (4410, 22050, "INT16")])
 def test_mbr_oracle_output_resampling_matches_reference_module(L, out_rate, dt):
     """OUT_SAMPLE_RATE != 44.1 kHz (Export_MelBandRoformer.py:662-678): down-sampling before the x32767 PCM scale,
-    up-sampling after it -- executed reference vs the restatement.  The INPUT-side resampler (:631-644) has no runnable
-    reference configuration (MAX_SIGNAL_LENGTH is sized from the input-rate length, :50): restated from the forward only."""
+    up-sampling after it -- executed reference vs the restatement.  (The INPUT-side resampler, :631-644:
+    test_mbr_oracle_input_resampling_matches_reference_module.)"""
     import mbr_oracle as mo
     from make_golden import mbr_kwargs
 
@@ -219,6 +219,33 @@ def test_mbr_oracle_output_resampling_matches_reference_module(L, out_rate, dt):
         yr = m(xin.clone())
         yo = mo.mbr_forward(cfg, fw, xin, dt, dt, out_rate=out_rate)
     assert yr.shape == yo.shape == (1, 2, int(np.floor(L * float(out_rate / 44100)))) and yr.dtype == yo.dtype
+    if dt == "INT16":
+        assert int((yr.int() - yo.int()).abs().max()) <= 1
+    else:
+        assert float((yr - yo).abs().max()) <= 1e-6
+
+
+@needs_ref
+@pytest.mark.parametrize("L,in_rate,out_rate,dt", [(4800, 48000, 44100, "F32"), (3200, 16000, 44100, "INT16"), (4500, 22500, 16000, "F32")])
+def test_mbr_oracle_input_resampling_matches_reference_module(L, in_rate, out_rate, dt):
+    """IN_SAMPLE_RATE != 44.1 kHz (Export_MelBandRoformer.py:631-644).  As shipped the static frame count is sized from the
+    input-rate length (:50); ref_loader patches that ONE constant to the model-rate frame count and the reference's own
+    forward is executed, so the restatement's input-side resampler is pinned to reference arithmetic."""
+    import mbr_oracle as mo
+    from make_golden import mbr_kwargs
+
+    cfg = mo.MbrConfig(depth=1)
+    sd = mo.random_state_dict(cfg, 3)
+    _, build = ref_loader.load_mbr(L, dt, out_rate, in_rate)
+    m = build(sd, **mbr_kwargs(cfg))
+    fw = mo.fuse(sd, cfg)
+    g = torch.Generator().manual_seed(1)
+    x = (torch.rand(1, 2, L, generator=g) * 2 - 1) * 0.5
+    xin = x if dt == "F32" else torch.round(x * 32767).to(torch.int16)
+    with torch.inference_mode():
+        yr = m(xin.clone())
+        yo = mo.mbr_forward(cfg, fw, xin, dt, dt, in_rate=in_rate, out_rate=out_rate)
+    assert yr.shape == yo.shape and yr.dtype == yo.dtype and yr.shape[-1] > 0
     if dt == "INT16":
         assert int((yr.int() - yo.int()).abs().max()) <= 1
     else:
@@ -433,9 +460,8 @@ def test_mf2se_oracle_resampling_matches_reference_module(L, in_rate, out_rate):
 @pytest.mark.parametrize("L,out_rate,dt", [(16000, 44000, "INT16"), (16000, 8000, "F32"), (8000, 48000, "F32")])
 def test_gtcrn_oracle_output_resampling_matches_reference_module(L, out_rate, dt):
     """OUT_SAMPLE_RATE != 16 kHz (Export_GTCRN.py:629-632, :671-688): down-sampling before the x32767 PCM scale,
-    up-sampling after it -- executed reference (static export) vs the restatement.  The INPUT-side resampler of the
-    restatement (:638-654) has no runnable reference configuration: the static export sizes its frame count from the
-    input-rate length (:45), the dynamic one changes the ISTFT length contract; it is restated from the forward only."""
+    up-sampling after it -- executed reference (static export) vs the restatement.  (The INPUT-side resampler, :638-654:
+    test_gtcrn_oracle_input_resampling_matches_reference_module.)"""
     import gtcrn_oracle as go
 
     sd = go.random_state_dict(0)
@@ -447,6 +473,31 @@ def test_gtcrn_oracle_output_resampling_matches_reference_module(L, out_rate, dt
         r = w(xin.clone())
         o = go.gtcrn_forward(sd, xin, dt, dt, out_rate=out_rate)
     assert r.shape == o.shape and r.dtype == o.dtype
+    if dt == "INT16":
+        assert int((r.int() - o.int()).abs().max()) <= 1
+    else:
+        assert float((r - o).abs().max()) <= 2e-6
+
+
+@needs_ref
+@pytest.mark.parametrize("L,in_rate,out_rate,dt", [(24000, 48000, 16000, "F32"), (8000, 8000, 16000, "INT16"), (22500, 22500, 8000, "F32"),
+                                                   (12000, 24000, 44000, "INT16")])
+def test_gtcrn_oracle_input_resampling_matches_reference_module(L, in_rate, out_rate, dt):
+    """IN_SAMPLE_RATE != 16 kHz (Export_GTCRN.py:638-654): resample-then-centre when down-sampling, centre-then-resample when
+    up-sampling.  As shipped the static export cannot run this configuration (its frame count is sized from the input-rate
+    length, :45); ref_loader patches that ONE constant to the model-rate frame count and the reference's own forward is
+    executed -- so the restatement's input side is pinned to reference arithmetic, not only read off the source."""
+    import gtcrn_oracle as go
+
+    sd = go.random_state_dict(0)
+    _, build = ref_loader.load_gtcrn(L, dt, in_rate, out_rate, model_rate_frames=True)
+    w = build(sd)
+    x = synth_audio(L, 3)
+    xin = x if dt == "F32" else torch.round(x * 32767).to(torch.int16)
+    with torch.inference_mode():
+        r = w(xin.clone())
+        o = go.gtcrn_forward(sd, xin, dt, dt, in_rate=in_rate, out_rate=out_rate)
+    assert r.shape == o.shape and r.dtype == o.dtype and r.shape[-1] > 0
     if dt == "INT16":
         assert int((r.int() - o.int()).abs().max()) <= 1
     else:
