@@ -178,6 +178,50 @@ def main_mf2se():
             print(f"mf2se {dt} L{L}: {tuple(xin.shape)} -> {tuple(y.shape)} max|y| {y.float().abs().max().item():.4f}")
 
 
+def main_fulldepth():
+    """FULL-DEPTH reference-executed fixtures (the other fixtures reduce the layer count): MossFormer2-SE-48K with 24 layers
+    (BASELINE configs[2]), MossFormer2-SS-16K with 24 layers, Mel-Band-Roformer at depth 6 -- the depths bench.py runs.  One or
+    two short windows each: the files carry the input, the reference's output and the seed of the weights only."""
+    import mbr_oracle as bo
+    import mf2se_oracle as mo
+    import mf2ss_oracle as so
+
+    assert ref_loader.reference_available()
+    with torch.inference_mode():
+        cfg = mo.Mf2Config(layers=24)
+        hold = mo.skeleton(cfg)
+        hold.load_state_dict(mo.random_state_dict(cfg, 0))
+        L = 13440
+        _, build = ref_loader.load_mf2se(L, "F32")
+        w = build(hold)
+        x = synth_audio(L, 4321, batch=2)
+        y = torch.cat([w(x[i:i + 1].clone()) for i in range(2)], dim=0)
+        np.savez_compressed(GOLDEN / f"mf2se_f32_L{L}_l24.npz", x=x.numpy(), y=y.numpy(), seed=0, layers=24)
+        print(f"mf2se full depth: {tuple(x.shape)} -> {tuple(y.shape)} max|y| {y.abs().max().item():.4f}")
+
+        cfg = so.SsConfig(layers=24)
+        hold = so.skeleton(cfg)
+        hold.load_state_dict(so.random_state_dict(cfg, 0))
+        L = 4808
+        _, build = ref_loader.load_mf2ss(L, "F32")
+        w = build(hold)
+        x = synth_audio(L, 4321, batch=2) * 32767.0
+        ys = [torch.cat([w(x[i:i + 1].clone())[s] for i in range(2)], dim=0) for s in range(2)]
+        np.savez_compressed(GOLDEN / f"mf2ss_f32_L{L}_l24.npz", x=x.numpy(), y0=ys[0].numpy(), y1=ys[1].numpy(), seed=0, layers=24)
+        print(f"mf2ss full depth: {tuple(x.shape)} -> 2 x {tuple(ys[0].shape)} max|y| {ys[0].abs().max().item():.4f}")
+
+        cfg = bo.MbrConfig(depth=6)
+        sd = bo.random_state_dict(cfg, 0)
+        L = 4410
+        _, build = ref_loader.load_mbr(L, "F32")
+        m = build(sd, **mbr_kwargs(cfg))
+        g = torch.Generator().manual_seed(1234)
+        x = (torch.rand(1, 2, L, generator=g) * 2 - 1) * 0.5
+        y = m(x.clone())
+        np.savez_compressed(GOLDEN / f"mbr_f32_L{L}_d6.npz", x=x.numpy(), y=y.numpy(), seed=0, depth=6)
+        print(f"mbr full depth: {tuple(x.shape)} -> {tuple(y.shape)} max|y| {y.abs().max().item():.4f}")
+
+
 def main_mf2ss():
     """MossFormer2-SS-16K fixtures: the reference wrapper (`MOSSFORMER_SS`) executed around
     `mf2ss_oracle.skeleton()` on seeded weights, 2 FLASH + dilated-FSMN layers (the layer count is the
@@ -350,5 +394,7 @@ if __name__ == "__main__":
         main_mbr()
     elif "--mf2se" in sys.argv:
         main_mf2se()
+    elif "--fulldepth" in sys.argv:
+        main_fulldepth()
     else:
         main()

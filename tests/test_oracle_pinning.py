@@ -808,3 +808,34 @@ def test_zipenh_oracle_and_folds_match_reference_module():
     assert yr.shape == yo.shape == (1, 1, L)
     assert float(yr.abs().max()) > 0.1
     assert (yr - yo).abs().max() <= 5e-6 * max(1.0, float(yr.abs().max()))
+
+
+# ----------------------------------------------------------------------------- full-depth fixtures
+def test_full_depth_fixtures_oracle(golden_dir):
+    """The reduced-depth fixtures above pin the restatements layer for layer; these were made by executing the reference wrappers at
+    the depths bench.py runs (oracle/make_golden.py --fulldepth: MossFormer2-SE-48K 24 layers, MossFormer2-SS-16K 24 layers,
+    Mel-Band-Roformer depth 6), so nothing about parity at depth rests on the restatement alone."""
+    import mbr_oracle as bo
+    import mf2se_oracle as mo
+    import mf2ss_oracle as so
+
+    with torch.inference_mode():
+        g = np.load(golden_dir / "mf2se_f32_L13440_l24.npz")
+        cfg = mo.Mf2Config(layers=int(g["layers"]))
+        assert cfg.layers == 24
+        y = mo.mf2se_forward_batch(mo.random_state_dict(cfg, int(g["seed"])), torch.from_numpy(g["x"]), cfg, "F32", "F32", chunk=1).numpy()
+        assert y.shape == g["y"].shape and np.abs(y - g["y"]).max() <= 5e-6, np.abs(y - g["y"]).max()
+
+        g = np.load(golden_dir / "mf2ss_f32_L4808_l24.npz")
+        cfg = so.SsConfig(layers=int(g["layers"]))
+        assert cfg.layers == 24
+        ys = so.mf2ss_forward_batch(so.random_state_dict(cfg, int(g["seed"])), torch.from_numpy(g["x"]), cfg, "F32", "F32", chunk=1)
+        for s in range(2):
+            assert ys[s].shape == g[f"y{s}"].shape and np.abs(ys[s].numpy() - g[f"y{s}"]).max() <= 2e-5, np.abs(ys[s].numpy() - g[f"y{s}"]).max()
+
+        g = np.load(golden_dir / "mbr_f32_L4410_d6.npz")
+        cfg = bo.MbrConfig(depth=int(g["depth"]))
+        assert cfg.depth == 6
+        fw = bo.fuse(bo.random_state_dict(cfg, int(g["seed"])), cfg)
+        y = bo.mbr_forward_batch(cfg, fw, torch.from_numpy(g["x"]), "F32", "F32").numpy()
+        assert y.shape == g["y"].shape and np.abs(y - g["y"]).max() <= 1e-6, np.abs(y - g["y"]).max()
