@@ -44,13 +44,18 @@ struct TcCache {
   bool enabled = true;
   std::map<int, std::vector<TcEntry>> plans;           // per windows-in-pass
   std::map<const float*, TcWeight> weights;
+  std::map<const float*, float*> tables_t;             // (rows, cols) parameter tables kept transposed for coalesced reads
   std::string err;
   ~TcCache() { clear(); }
   void clear() {
     for (auto& kv : weights) cudaFree(kv.second.planes);
+    for (auto& kv : tables_t) cudaFree(kv.second);
     weights.clear();
+    tables_t.clear();
     plans.clear();
   }
+  // t[c * cols + f] -> (cols, rows) copy, built on first use (an eager run: adn_run never captures the first run of a batch)
+  const float* transposed(const float* t, int rows, int cols, cudaStream_t st);
   // kmajor: w is (N, K) row-major already; otherwise (K, N)
   const TcWeight* weight(const float* w, int K, int N, cudaStream_t st, bool kmajor = false) {
     auto it = weights.find(w);
@@ -102,6 +107,74 @@ GAN_OP_NAME(FeatConv, "gan_feat_conv");
 GAN_OP_NAME(CopyCh, "gan_copy_ch");
 GAN_OP_NAME(MaskTail, "gan_mask_tail");
 GAN_OP_NAME(CplxTail, "gan_cplx_tail");
+
+static __global__ void transpose_table_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < rows * cols) dst[(i % cols) * rows + i / cols] = src[i];
+}
+inline const float* TcCache::transposed(const float* t, int rows, int cols, cudaStream_t st) {
+  auto it = tables_t.find(t);
+  if (it != tables_t.end()) return it->second;
+  float* d = nullptr;
+  if (cudaMalloc((void**)&d, (size_t)rows * cols * sizeof(float)) != cudaSuccess) { err = "out of device memory (transposed table)"; return nullptr; }
+  transpose_table_kernel<<<(unsigned)((rows * cols + 255) / 256), 256, 0, st>>>(t, d, rows, cols);
+  tables_t[t] = d;
+  return d;
+}
+
+// GroupNorm apply (the GroupNorm functor): one thread = four channels of a pixel.  The functor reads its (channel, sub-band)
+// affine tables as gam[c * Fw + f] -- 32 cache lines per warp load, twice per element: the kernel was bound by L1 wavefronts.  Here
+// the tables are read from (sub-band, channel) copies (TcCache::transposed) as float4.  Same arithmetic per element.
+static __global__ void __launch_bounds__(256) group_norm_kernel(GroupNorm f, const float* __restrict__ gamT, const float* __restrict__ betT,
+                                                               long long n4) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= n4) return;
+  const int l4 = f.ld >> 2;
+  const int c = (int)(idx % l4) << 2;
+  const long long p = idx / l4;
+  const int fq = (int)(p % f.Fw);
+  const long long bt = p / f.Fw;
+  const long long i = p * f.ld + c;
+  const float4 x = *reinterpret_cast<const float4*>(f.x + i);
+  const float4 g4 = *reinterpret_cast<const float4*>(gamT + (long long)fq * f.ld + c);
+  const float4 b4 = *reinterpret_cast<const float4*>(betT + (long long)fq * f.ld + c);
+  const float xv[4] = {x.x, x.y, x.z, x.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+  float v[4];
+  int gi = 0;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    while (gi + 1 < f.g.n && c + e >= f.g.lo[gi + 1]) ++gi;
+    const float* st = f.stat + 2 * (bt * f.g.n + gi);
+    v[e] = (xv[e] - st[0]) * st[1] * gv[e] + bv[e];
+  }
+  if (f.res) {
+    const float4 r = *reinterpret_cast<const float4*>(f.res + i);
+    v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+  }
+  *reinterpret_cast<float4*>(f.out + i) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// OffsetScale (4 heads) + rotary (the OffsetRot functor): one thread = four consecutive dims of one (token, head) -- a rotary pair
+// (j, j ^ 1) lies inside the float4.  Same arithmetic per element.
+static __global__ void __launch_bounds__(256) offset_rot_kernel(OffsetRot f, long long n4) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= n4) return;
+  const int j = (int)(idx % (QK / 4)) << 2;
+  const int h = (int)((idx / (QK / 4)) % 4);
+  const long long r = idx / QK;                      // 4 heads x QK / 4 threads per token
+  const int q = (int)(r % f.Q);
+  const float4 z4 = *reinterpret_cast<const float4*>(f.huv + r * HUV + HID + j);
+  const float4 g4 = __ldg(reinterpret_cast<const float4*>(f.gamma + h * QK + j));
+  const float4 b4 = __ldg(reinterpret_cast<const float4*>(f.beta + h * QK + j));
+  float v[4] = {z4.x * g4.x + b4.x, z4.y * g4.y + b4.y, z4.z * g4.z + b4.z, z4.w * g4.w + b4.w};
+  if (j < ROT) {
+    const float4 cs = __ldg(reinterpret_cast<const float4*>(f.cs + q * ROT + j));
+    const float4 sn = __ldg(reinterpret_cast<const float4*>(f.sn + q * ROT + j));
+    const float o[4] = {v[0] * cs.x + v[1] * sn.x, v[1] * cs.y + v[0] * sn.y, v[2] * cs.z + v[3] * sn.z, v[3] * cs.w + v[2] * sn.w};
+    v[0] = o[0]; v[1] = o[1]; v[2] = o[2]; v[3] = o[3];
+  }
+  *reinterpret_cast<float4*>(f.heads + idx * 4) = make_float4(v[0], v[1], v[2], v[3]);
+}
 
 // Depthwise conv along a sequence, one CTA per (sequence, 32-channel group).  The S x 32 strip goes ONCE from global into shared
 // memory with 16-byte cp.async copies (zero halos; no register staging, so nothing waits on a load until the one wait before the
@@ -171,6 +244,25 @@ struct CudaExec {
     op_kernel<F><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, f);
     ++launches;
     if (tick) tick(tick_ctx, OpName<F>::get());
+  }
+  void run(long long n, const GroupNorm& f) {
+    static const bool functor = getenv("ADN_GAN_EW") && !strcmp(getenv("ADN_GAN_EW"), "functor");
+    const float *gt = nullptr, *bt = nullptr;
+    if (!functor && tc && !(f.ld & 3) && n > 0) {
+      gt = tc->transposed(f.gam, f.ld, f.Fw, st);
+      bt = tc->transposed(f.bet, f.ld, f.Fw, st);
+    }
+    if (!gt || !bt) { run<GroupNorm>(n, f); return; }
+    group_norm_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(f, gt, bt, n / 4);
+    ++launches;
+    if (tick) tick(tick_ctx, "gan_group_norm");
+  }
+  void run(long long n, const OffsetRot& f) {
+    static const bool functor = getenv("ADN_GAN_EW") && !strcmp(getenv("ADN_GAN_EW"), "functor");
+    if (functor || n <= 0) { run<OffsetRot>(n, f); return; }
+    offset_rot_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(f, n / 4);
+    ++launches;
+    if (tick) tick(tick_ctx, "gan_offset_rot");
   }
   template <int KT>
   void run(long long n, const DwConv<KT>& f) {
