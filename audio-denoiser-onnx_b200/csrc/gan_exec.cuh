@@ -176,6 +176,57 @@ static __global__ void __launch_bounds__(256) offset_rot_kernel(OffsetRot f, lon
   *reinterpret_cast<float4*>(f.heads + idx * 4) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// LayerNorm statistics of a row (the RowStats functor): eight lanes per row, float4 loads (a quarter-warp reads a contiguous 128-byte
+// piece of the row), butterfly sums inside the lane group.  One thread per row made every load instruction touch 32 cache lines.
+// Two passes like the functor (mean, then centred squares); the summation ORDER differs from the functor's sequential one.
+static __global__ void __launch_bounds__(256) row_stats_kernel(RowStats f, long long rows) {
+  const long long r = ((long long)blockIdx.x * 256 + threadIdx.x) >> 3;
+  const int l = threadIdx.x & 7;
+  const bool ok = r < rows;
+  const F4* x = reinterpret_cast<const F4*>(f.in + (ok ? r : 0) * f.ldi);
+  const int k4 = f.K >> 2;
+  float s = 0.f;
+  if (ok) for (int k = l; k < k4; k += 8) { const F4 v = x[k]; s += (v.x + v.y) + (v.z + v.w); }
+  s += __shfl_xor_sync(0xffffffffu, s, 4); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 1);
+  const float mu = s / (float)f.K;
+  float v2 = 0.f;
+  if (ok) for (int k = l; k < k4; k += 8) {
+    const F4 q = x[k];
+    const float a = q.x - mu, b = q.y - mu, c = q.z - mu, d = q.w - mu;
+    v2 += (a * a + b * b) + (c * c + d * d);
+  }
+  v2 += __shfl_xor_sync(0xffffffffu, v2, 4); v2 += __shfl_xor_sync(0xffffffffu, v2, 2); v2 += __shfl_xor_sync(0xffffffffu, v2, 1);
+  if (ok && l == 0) {
+    f.stat[2 * r] = mu;
+    f.stat[2 * r + 1] = 1.0f / sqrtf(v2 / (float)f.K + EPS);
+  }
+}
+
+// SELayer MLPs (the SeMlp functor): one CTA per window.  The functor recomputes the 64-wide hidden layer for each of its 64 output
+// channels with one thread per output (4 096 threads in all, 8 k dependent loads each: 0.7 ms per launch); here thread (kd, j)
+// computes hidden unit j of MLP kd once, then thread c combines both MLPs' outputs.  Same sums in the same order.
+static __global__ void __launch_bounds__(128) se_mlp_kernel(SeMlp f) {
+  __shared__ float pool[2][C], hid[2][C];
+  const long long b = blockIdx.x;
+  const int kd = threadIdx.x >> 6, j = threadIdx.x & 63;
+  pool[kd][j] = f.pooled[(b * 2 + kd) * C + j];
+  __syncthreads();
+  float h = f.b0[kd][j];
+  for (int k = 0; k < C; ++k) h += f.w0[kd][j * C + k] * pool[kd][k];
+  hid[kd][j] = h > 0.f ? h : 0.f;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x;
+    float tot = 0.f;
+    for (int m = 0; m < 2; ++m) {
+      float o = f.b2[m][c];
+      for (int jj = 0; jj < C; ++jj) o += f.w2[m][c * C + jj] * hid[m][jj];
+      tot += sigmoidf_(o);
+    }
+    f.scale[b * C + c] = tot;
+  }
+}
+
 // Depthwise conv along a sequence, one CTA per (sequence, 32-channel group).  The S x 32 strip goes ONCE from global into shared
 // memory with 16-byte cp.async copies (zero halos; no register staging, so nothing waits on a load until the one wait before the
 // barrier), the taps sit in shared memory too (lanes = channels: every access conflict-free), and each warp computes DWS
@@ -256,6 +307,20 @@ struct CudaExec {
     group_norm_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(f, gt, bt, n / 4);
     ++launches;
     if (tick) tick(tick_ctx, "gan_group_norm");
+  }
+  void run(long long n, const RowStats& f) {
+    static const bool functor = getenv("ADN_GAN_EW") && !strcmp(getenv("ADN_GAN_EW"), "functor");
+    if (functor || n <= 0 || (f.K & 3) || (f.ldi & 3)) { run<RowStats>(n, f); return; }
+    row_stats_kernel<<<(unsigned)((n * 8 + 255) / 256), 256, 0, st>>>(f, n);
+    ++launches;
+    if (tick) tick(tick_ctx, "gan_row_stats");
+  }
+  void run(long long n, const SeMlp& f) {
+    static const bool functor = getenv("ADN_GAN_EW") && !strcmp(getenv("ADN_GAN_EW"), "functor");
+    if (functor || n <= 0) { run<SeMlp>(n, f); return; }
+    se_mlp_kernel<<<(unsigned)(n / C), 128, 0, st>>>(f);
+    ++launches;
+    if (tick) tick(tick_ctx, "gan_se_mlp");
   }
   void run(long long n, const OffsetRot& f) {
     static const bool functor = getenv("ADN_GAN_EW") && !strcmp(getenv("ADN_GAN_EW"), "functor");
