@@ -227,6 +227,20 @@ static __global__ void __launch_bounds__(128) se_mlp_kernel(SeMlp f) {
   }
 }
 
+// Gated attention output (the GateOut functor), four columns per thread; the sigmoid on ex2.approx / rcp.approx (~2 ulp).
+static __global__ void __launch_bounds__(256) gate_out_kernel(GateOut f, long long n4) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= n4) return;
+  const int j = (int)(idx % (HID / 8)) << 2;
+  const long long r = idx / (HID / 8);
+  const float* a = f.att + r * HID; const float* h = f.huv + r * HUV;
+  const float4 a0 = *reinterpret_cast<const float4*>(a + j), a1 = *reinterpret_cast<const float4*>(a + HID / 2 + j);
+  const float4 h0 = *reinterpret_cast<const float4*>(h + j), h1 = *reinterpret_cast<const float4*>(h + HID / 2 + j);
+  auto sg = [](float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); };
+  *reinterpret_cast<float4*>(f.out + idx * 4) = make_float4((a1.x * h0.x) * sg(a0.x * h1.x), (a1.y * h0.y) * sg(a0.y * h1.y),
+                                                            (a1.z * h0.z) * sg(a0.z * h1.z), (a1.w * h0.w) * sg(a0.w * h1.w));
+}
+
 // Depthwise conv along a sequence, one CTA per (sequence, 32-channel group).  The S x 32 strip goes ONCE from global into shared
 // memory with 16-byte cp.async copies (zero halos; no register staging, so nothing waits on a load until the one wait before the
 // barrier), the taps sit in shared memory too (lanes = channels: every access conflict-free), and each warp computes DWS
@@ -321,6 +335,13 @@ struct CudaExec {
     se_mlp_kernel<<<(unsigned)(n / C), 128, 0, st>>>(f);
     ++launches;
     if (tick) tick(tick_ctx, "gan_se_mlp");
+  }
+  void run(long long n, const GateOut& f) {
+    static const bool functor = getenv("ADN_GAN_EW") && !strcmp(getenv("ADN_GAN_EW"), "functor");
+    if (functor || n <= 0) { run<GateOut>(n, f); return; }
+    gate_out_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(f, n / 4);
+    ++launches;
+    if (tick) tick(tick_ctx, "gan_gate_out");
   }
   void run(long long n, const OffsetRot& f) {
     static const bool functor = getenv("ADN_GAN_EW") && !strcmp(getenv("ADN_GAN_EW"), "functor");

@@ -484,6 +484,37 @@ __global__ void __launch_bounds__(256) in_fin_kernel(InFin f, long long n) {
   }
 }
 
+// FeatConv / UpCombine functors, four channels per thread (float4 rows instead of one 4-byte access per thread).
+__global__ void __launch_bounds__(256) feat_conv_kernel(FeatConv f, long long n4) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= n4) return;
+  const int c4 = (int)(idx & 15);
+  long long p = idx >> 4;
+  const int fb = (int)(p % FB); p /= FB;
+  const int t = (int)(p % f.T);
+  const long long bb = p / f.T;
+  const float* x = f.feat + (bb * 2 * f.T + t) * FB + fb;
+  const float x0 = x[0], x1 = x[(long long)f.T * FB];
+  const float4 wa = __ldg(reinterpret_cast<const float4*>(f.w) + 2 * c4), wb = __ldg(reinterpret_cast<const float4*>(f.w) + 2 * c4 + 1);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(f.b) + c4);
+  *reinterpret_cast<float4*>(f.raw + ((bb * f.T + t) * FPE + fb + 1) * C + 4 * c4) =
+      make_float4(b.x + wa.x * x0 + wa.y * x1, b.y + wa.z * x0 + wa.w * x1, b.z + wb.x * x0 + wb.y * x1, b.w + wb.z * x0 + wb.w * x1);
+}
+__global__ void __launch_bounds__(256) up_combine_kernel(UpCombine f, long long n4) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= n4) return;
+  const int c4 = (int)(idx & 15);
+  long long p = idx >> 4;
+  const int fq = (int)(p % f.F); p /= f.F;
+  const int t = (int)(p % f.T);
+  const long long bb = p / f.T;
+  const float4 y = *reinterpret_cast<const float4*>(f.y + ((bb * f.Td + t / f.ds) * f.Fd + fq / f.ds) * C + 4 * c4);
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(f.scale) + c4), rs = __ldg(reinterpret_cast<const float4*>(f.rscale) + c4);
+  float4* o = reinterpret_cast<float4*>(f.x0) + idx;
+  const float4 x = *o;
+  *o = make_float4(x.x * rs.x + (y.x * sc.x), x.y * rs.y + (y.y * sc.y), x.z * rs.z + (y.z * sc.z), x.w * rs.w + (y.w * sc.w));
+}
+
 // decoder heads: one thread = one (window, frame, bin) with both taps' 2 x 64 inputs read as float4 and all outputs of the head
 __global__ void __launch_bounds__(256) head_kernel(Head f, int npix) {
   __shared__ float4 ws[2 * 2 * C / 4];
@@ -637,6 +668,16 @@ struct CudaExec {
     const long long npix = n / f.nout;
     head_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(f, (int)npix);
     done("zip_head");
+  }
+  void run(long long n, const FeatConv& f) {
+    if (functors_only) { run_functor(n, f); return; }
+    feat_conv_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(f, n / 4);
+    done("zip_feat_conv");
+  }
+  void run(long long n, const UpCombine& f) {
+    if (functors_only) { run_functor(n, f); return; }
+    up_combine_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(f, n / 4);
+    done("zip_up_combine");
   }
   void run(long long n, const NormBypass& f) {
     if (functors_only) { run_functor(n, f); return; }
