@@ -6,10 +6,14 @@
 //
 // * A is never framed in memory: a 3-D TMA tensor map with row stride sT (< K: rows overlap)
 //   gathers 128-row tiles straight from the padded waveform (STFT) or from runs of R
-//   consecutive spectrum frames (ISTFT overlap-add).  Operands are pre-split into tf32
-//   hi/lo planes by their producers, so the main loop is pure TMA -> smem -> tcgen05.mma.
-// * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
-//   warps 2..5 = epilogue (TMEM -> registers -> global).  Persistent over output tiles with
+//   consecutive spectrum frames (ISTFT overlap-add).
+// * Three operand forms.  PLANES: operands pre-split into tf32 hi / lo planes by their producers (STFT / ISTFT bases, round-1
+//   layers): pure TMA -> smem -> tcgen05.mma.  AF (fp32-A): TMA lands the fp32 activation tile, converter warps split it in shared
+//   memory, TMA-store epilogue.  TS (AF with 64-wide tiles): the converters write the hi / lo tiles into TENSOR MEMORY with tcgen05.st
+//   and the MMAs take A from there (see the comment at the kernel).
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, then 8 / 12 / 16 epilogue warps (TMEM -> registers -> global or a
+//   TMA store) and, in the AF / TS forms, 2 .. 10 converter warps.  Producer and MMA warps walk their loops with all 32 lanes and
+//   issue under elect.sync (warp-uniform control flow: no per-instruction operand broadcast).  Persistent over output tiles with
 //   two TMEM accumulator buffers so the epilogue of tile i overlaps the main loop of i+1.
 //
 // bf16 variant (TcPlan::bf16, licensed only where the workload spec says "bf16 matmuls": MossFormer2-SE-48K,
