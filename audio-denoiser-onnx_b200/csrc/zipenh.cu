@@ -264,12 +264,14 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 template <bool NL>
-__global__ void __launch_bounds__(256) attn_apply_mma_kernel(const float* __restrict__ aw, SeqMap sm, const float* __restrict__ src,
+__global__ void __launch_bounds__(256, 3) attn_apply_mma_kernel(const float* __restrict__ aw, SeqMap sm, const float* __restrict__ src,
                                                             float* __restrict__ out) {
   extern __shared__ float sh[];
   const int S = sm.S, SP16 = (S + 15) & ~15, ld = aw_ld(S);
-  float* vhi = sh;                    // [SP16][VSM], rows permuted inside every block of 16 (see below)
-  float* vlo = sh + SP16 * VSM;
+  float* vsm = sh;                    // [SP16][VSM] fp32 values, rows permuted inside every block of 16 (see below); split into tf32
+                                      // hi / lo after the fragment load: ONE plane halves the shared memory (78.8 -> 39.4 KB at
+                                      // S = 161), i.e. twice the resident CTAs for a kernel that ncu shows waiting on its global
+                                      // loads at 25 % occupancy (63 % of the stall samples on the long scoreboard)
   const long long n = blockIdx.x;
   for (int idx = threadIdx.x; idx < SP16 * (VSM / 4); idx += 256) {
     const int s = idx / (VSM / 4), e = idx - s * (VSM / 4);
@@ -283,13 +285,10 @@ __global__ void __launch_bounds__(256) attn_apply_mma_kernel(const float* __rest
         v = __ldg(reinterpret_cast<const float4*>(src + sm.tok(n, s) * SV) + e);
       }
     }
-    float4 h, l;
-    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
     // key j = 16 b + 4 t + e lives in row 16 b + 4 e + t: lane t of an MMA reads keys 4t .. 4t+3 of a 16-key block (one 16-byte
     // load of the weights), and this placement keeps its four B-fragment loads on bank 24 t + g
     const int ps = (s & ~15) + ((s & 3) << 2) + ((s >> 2) & 3);
-    *reinterpret_cast<float4*>(vhi + ps * VSM + 4 * e) = h;
-    *reinterpret_cast<float4*>(vlo + ps * VSM + 4 * e) = l;
+    *reinterpret_cast<float4*>(vsm + ps * VSM + 4 * e) = v;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -329,8 +328,10 @@ __global__ void __launch_bounds__(256) attn_apply_mma_kernel(const float* __rest
 #pragma unroll
         for (int q = 0; q < NT; ++q) {
           const int col = c0 + 8 * q + g;
-          const uint32_t bh0 = __float_as_uint(vhi[p0 + col]), bh1 = __float_as_uint(vhi[p1 + col]);
-          const uint32_t bl0 = __float_as_uint(vlo[p0 + col]), bl1 = __float_as_uint(vlo[p1 + col]);
+          float h0, l0, h1, l1;
+          split_tf32(vsm[p0 + col], h0, l0);
+          split_tf32(vsm[p1 + col], h1, l1);
+          const uint32_t bh0 = __float_as_uint(h0), bh1 = __float_as_uint(h1), bl0 = __float_as_uint(l0), bl1 = __float_as_uint(l1);
           mma_tf32(acc[q], al, bh0, bh1);
           mma_tf32(acc[q], ah, bl0, bl1);
           mma_tf32(acc[q], ah, bh0, bh1);
@@ -615,10 +616,10 @@ struct CudaExec {
   void apply(long long nseq, const SeqMap& sm, const float* aw, const float* src, float* out, int jj) {
     static const bool use_mma = !(getenv("ADN_ZIP_APPLY") && !strcmp(getenv("ADN_ZIP_APPLY"), "ffma"));
     if (use_mma) {
-      const size_t smem_m = (size_t)2 * ((sm.S + 15) & ~15) * VSM * sizeof(float);   // <= 2 * 256 * 56 * 4 = 114 688 B
+      const size_t smem_m = (size_t)((sm.S + 15) & ~15) * VSM * sizeof(float);       // <= 256 * 56 * 4 = 57 344 B
       static unsigned long long conf_m = 0;
       auto km = attn_apply_mma_kernel<NL>;
-      if (adn_first_use_on_device(conf_m)) cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * VSM * 4);
+      if (adn_first_use_on_device(conf_m)) cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * VSM * 4);
       km<<<(unsigned)nseq, 256, smem_m, st>>>(aw, sm, src, out);
       return;
     }
