@@ -61,9 +61,29 @@ def load(path):
         raise ValueError(f"{path}: not an ADN1 model file")
     (hlen,) = struct.unpack("<I", raw[4:8])
     header = json.loads(raw[8:8 + hlen].decode())
-    payload = np.frombuffer(raw, dtype=np.float32, offset=8 + hlen).copy() if (len(raw) - 8 - hlen) % 4 == 0 \
-        else np.frombuffer(raw[8 + hlen:], dtype=np.float32).copy()
+    if hlen > len(raw) - 8:
+        raise ValueError(f"{path}: header length {hlen} exceeds the file")
+    if (len(raw) - 8 - hlen) % 4:
+        raise ValueError(f"{path}: payload is not a whole number of fp32 values")
+    payload = np.frombuffer(raw, dtype=np.float32, offset=8 + hlen).copy()
+    _validate_index(path, header.get("tensors"), payload.size)
     return header["metadata"], header["tensors"], payload
+
+
+def _validate_index(path, index, nfloats: int):
+    """Every tensor record must lie inside the payload (the C ABI re-checks offset / count without 64-bit wrap-around,
+    api.cu adn_create; a malformed file should fail here with the tensor's name, not there with an index)."""
+    if not isinstance(index, list):
+        raise ValueError(f"{path}: tensor index missing")
+    for t in index:
+        name = t.get("name") if isinstance(t, dict) else None
+        try:
+            off, cnt = int(t["offset"]), int(t["count"])
+            shape = [int(d) for d in t["shape"]]
+        except (KeyError, TypeError, ValueError):
+            raise ValueError(f"{path}: malformed tensor record {name!r}") from None
+        if off < 0 or cnt < 0 or off > nfloats or cnt > nfloats - off or any(d < 0 for d in shape) or int(np.prod(shape, dtype=np.int64)) != cnt:
+            raise ValueError(f"{path}: tensor {name!r} (offset {off}, count {cnt}, shape {shape}) does not fit the payload of {nfloats} values")
 
 
 def flatten(tensors: dict[str, np.ndarray]):

@@ -69,6 +69,41 @@ def test_modelfile_round_trip(tmp_path):
         modelfile.load(tmp_path / "bad.adn")
 
 
+def test_modelfile_rejects_an_index_that_leaves_the_payload(tmp_path):
+    """A tensor record whose offset / count / shape does not fit the payload fails at load with the tensor's name (ADVICE r1:
+    the C ABI dereferences blob + offset; its own bound check is the second line of defence)."""
+    import json
+    import struct
+
+    from adn import modelfile
+
+    good = {"a": np.arange(6, dtype=np.float32).reshape(2, 3), "b": np.ones(5, np.float32)}
+    modelfile.save(tmp_path / "ok.adn", {"model_family": "gtcrn"}, good)
+    raw = (tmp_path / "ok.adn").read_bytes()
+    (hlen,) = struct.unpack("<I", raw[4:8])
+    header = json.loads(raw[8:8 + hlen].decode())
+    md, index, payload = modelfile.load(tmp_path / "ok.adn")
+    assert [t["name"] for t in index] == ["a", "b"] and payload.size >= 11
+
+    def rewrite(mutate):
+        h = json.loads(json.dumps(header))
+        mutate(h["tensors"])
+        hb = json.dumps(h).encode()
+        (tmp_path / "bad.adn").write_bytes(raw[:4] + struct.pack("<I", len(hb)) + hb + raw[8 + hlen:])
+        return tmp_path / "bad.adn"
+
+    for mutate in (lambda t: t[1].__setitem__("offset", 2**63),            # far outside (the uint64 wrap-around case)
+                   lambda t: t[1].__setitem__("count", payload.size + 1),
+                   lambda t: t[0].__setitem__("shape", [2, 4]),              # shape disagrees with count
+                   lambda t: t[0].__setitem__("offset", -4),
+                   lambda t: t[1].pop("count")):
+        with pytest.raises(ValueError, match="tensor"):
+            modelfile.load(rewrite(mutate))
+    with pytest.raises(ValueError):
+        (tmp_path / "trunc.adn").write_bytes(raw[:-2])                        # payload not a whole number of floats
+        modelfile.load(tmp_path / "trunc.adn")
+
+
 def test_weight_packing_matches_oracle_fold():
     """BN fold + deconv->conv rewrite: the packed GTConv block reproduces the oracle's
     (reference-order) block on random input, computed with plain torch ops."""
